@@ -1,0 +1,403 @@
+"""
+Generates tests/golden/*.npz by running the REAL reference (h3jia/bayesfast, /root/reference).
+
+Run in the authoring container only (the reference does not exist on the GPU box):
+
+    python tests/golden/make_golden.py
+
+It copies /root/reference/bayesfast to a scratch directory, compiles its four Cython files there
+(recipe of SURVEY.md section 8c), imports it through a small shim (numpy-2 aliases, stub matplotlib /
+numdifftools) and records inputs + outputs of the hot path:
+
+    poly_kat.npz      the reference's own tests/test_poly.py case (+ bound / far-point values)
+    poly_eval.npz     PolyModel._fun_and_jac / fun_and_jac for injected coefficients (all orders, masks, bound)
+    density.npz       Density.logp_and_grad(x, original_space=False) with decay + transform + module rescale
+    fit.npz           PolyModel.fit (+ _set_bound) results
+    sampler.npz       NUTS / HMC chains driven by a replayed random stream (include/bfb_rng.h draws)
+
+The random stream: the reference's per-chain numpy Generator is replaced (after _init_chain) by a
+duck-typed object that serves draw t of the Philox stream -- normal(size=k) consumes k draws through
+Phi^-1, uniform() consumes one -- so the reference, the oracle and the CUDA kernels see the same numbers.
+"""
+import os
+import shutil
+import subprocess
+import sys
+import types
+import warnings
+from copy import deepcopy
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+SCRATCH = os.environ.get('BF_REF_SCRATCH', '/tmp/bf_ref')
+
+BUILD_PY = '''
+from setuptools import setup, Extension
+from Cython.Build import cythonize
+import numpy as np
+names = ["bayesfast/modules/_poly", "bayesfast/transforms/_constraint", "bayesfast/utils/_cubic", "bayesfast/utils/_sobol"]
+exts = [Extension(n.replace("/", "."), [n + ".pyx"], include_dirs=[np.get_include()],
+                  extra_compile_args=["-fopenmp", "-O3"],
+                  extra_link_args=["-B/usr/lib/gcc/x86_64-linux-gnu/13/", "-fopenmp"]) for n in names]
+setup(name="bf_ref_ext", ext_modules=cythonize(exts, language_level="3"), script_args=["build_ext", "--inplace"])
+'''
+
+
+def import_reference():
+    if not os.path.exists(os.path.join(SCRATCH, 'bayesfast')):
+        os.makedirs(SCRATCH, exist_ok=True)
+        shutil.copytree('/root/reference/bayesfast', os.path.join(SCRATCH, 'bayesfast'))
+    import glob
+    if not glob.glob(os.path.join(SCRATCH, 'bayesfast', 'modules', '_poly*.so')):
+        with open(os.path.join(SCRATCH, 'build_ext.py'), 'w') as f:
+            f.write(BUILD_PY)
+        subprocess.check_call([sys.executable, 'build_ext.py'], cwd=SCRATCH, stdout=subprocess.DEVNULL)
+    np.int = int
+    np.float = float
+    for name in ('matplotlib', 'matplotlib.pyplot', 'numdifftools'):
+        sys.modules[name] = types.ModuleType(name)
+    sys.modules['matplotlib'].pyplot = sys.modules['matplotlib.pyplot']
+    for a in ('Gradient', 'Hessian', 'Jacobian', 'Hessdiag'):
+        setattr(sys.modules['numdifftools'], a, None)
+    sys.path.insert(0, SCRATCH)
+    import bayesfast
+    return bayesfast
+
+
+bf = import_reference()
+from bayesfast.modules.poly import PolyModel, PolyConfig  # noqa: E402
+from bayesfast.samplers import NUTS, HMC, NTrace, HTrace  # noqa: E402
+from oracle import bf_oracle  # noqa: E402  (only for the Philox draws)
+import _golden_io as gio  # noqa: E402
+
+
+# ---------------------------------------------------------------------------------------------
+def clean_coef(conf):
+    """Dense _coef with the never-read entries (np.empty garbage, poly.py:146) zeroed."""
+    c = np.array(conf._coef, copy=True)
+    n = conf.input_size
+    if conf.order == 'quadratic':
+        c = np.triu(c)
+    elif conf.order == 'cubic-3':
+        mask = np.zeros((n, n, n), bool)
+        for j in range(n):
+            for k in range(j + 1, n):
+                mask[j, k, k + 1:] = True
+        c = np.where(mask, c, 0.)
+    return c
+
+
+def poly_spec(sur):
+    spec = dict(n=sur._input_size, m=sur._output_size, configs=[])
+    for conf in sur._configs:
+        spec['configs'].append(dict(order=conf.order, input_mask=np.asarray(conf._input_mask, np.int64),
+                                    output_mask=np.asarray(conf._output_mask, np.int64), coef=clean_coef(conf)))
+    ub = bool(sur._use_bound and not sur._all_linear and hasattr(sur, '_mu'))
+    spec['use_bound'] = ub
+    if ub:
+        spec.update(mu=sur._mu, hess=sur._hess, alpha=float(sur._alpha), f_mu=np.atleast_1d(sur._f_mu))
+    spec['input_scales'] = None if sur._input_scales is None else np.array(sur._input_scales)
+    return spec
+
+
+def density_spec(den):
+    sur = den._surrogate_list[0]
+    spec = poly_spec(sur)
+    spec['use_decay'] = bool(den._use_decay)
+    if den._use_decay:
+        spec.update(d_mu=den._mu, d_hess=den._hess, d_alpha2=float(den._alpha_2), d_gamma=float(den._gamma))
+    if den._input_scales is None:
+        spec['transform_ranges'] = None
+    else:
+        spec['transform_ranges'] = np.array(den._input_scales)
+        hb = den._hard_bounds
+        if isinstance(hb, bool):
+            hb = hb * np.ones((spec['n'], 2), np.uint8)
+        spec['hard_bounds'] = np.asarray(hb, np.uint8)
+    return spec
+
+
+def inject(sur, rng, scale=0.3):
+    """Random independent coefficients through PolyConfig._set (poly.py:131-158)."""
+    for conf in sur._configs:
+        for i in range(conf.output_size):
+            a = rng.normal(size=conf._a_shape) * scale
+            if conf.order == 'quadratic':
+                a *= 0.5
+            elif conf.order in ('cubic-2', 'cubic-3'):
+                a *= 0.1
+            conf._set(a, i)
+
+
+def set_bound_from(sur, pts):
+    sur._set_bound(pts, None) if False else None
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        sur._set_bound(pts, np.arange(pts.shape[0], dtype=float))
+
+
+# ---------------------------------------------------------------------------------------------
+def make_poly_kat():
+    bf.utils.random.set_generator(0)
+    rng = bf.utils.random.get_generator()
+    x = rng.normal(size=(50, 4))
+
+    def poly_f(x):
+        return (x[..., 0]**3 - 2 * x[..., 1]**3 + 3 * x[..., 1] * x[..., 2] * x[..., 3]
+                - 4 * x[..., 2]**2 * x[..., 3] + 5 * x[..., 0]**2 - 6 * x[..., 0] * x[..., 2]
+                + 7 * x[..., 1] - 8)[..., np.newaxis]
+
+    y = poly_f(x)
+    out = dict(x=x, y=y)
+    for tag, logp in (('nologp', None), ('logp', y[:, 0])):
+        s = PolyModel('cubic-3', input_size=4, output_size=1)
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            s.fit(x, y, logp)
+        vals = np.concatenate([s(xi) for xi in x])
+        far = 5 * x[0]
+        ff, jf = s._fun_and_jac(far)
+        out[tag] = dict(spec=poly_spec(s), values=vals, jac0=s.jac(x[0])[0], far=far, far_f=ff, far_j=jf)
+    gio.save('poly_kat.npz', out)
+
+
+def make_poly_eval():
+    rng = np.random.default_rng(11)
+    cases = []
+
+    def add(name, sur, n, pts_scale=1., with_bound=True, input_scales=None):
+        inject(sur, rng)
+        train = rng.normal(size=(6 * n + 10, n)) * pts_scale
+        if with_bound:
+            set_bound_from(sur, train)
+        else:
+            sur._use_bound = False
+        X = np.concatenate((rng.normal(size=(8, n)) * pts_scale * 0.7,
+                            rng.normal(size=(4, n)) * pts_scale * 6.))
+        raw_f, raw_j, wrp_f, wrp_j = [], [], [], []
+        for xi in X:
+            f, j = sur._fun_and_jac(xi)
+            raw_f.append(f), raw_j.append(j)
+            f, j = sur.fun_and_jac(xi)
+            wrp_f.append(np.concatenate(f)), wrp_j.append(np.concatenate(j))
+        cases.append(dict(name=name, spec=poly_spec(sur), X=X, raw_f=np.array(raw_f), raw_j=np.array(raw_j),
+                          wrapped_f=np.array(wrp_f), wrapped_j=np.array(wrp_j)))
+
+    add('quad_n2', PolyModel('quadratic', input_size=2, output_size=1), 2)
+    add('c2_n16', PolyModel('cubic-2', input_size=16, output_size=1), 16)
+    add('c2_n26', PolyModel('cubic-2', input_size=26, output_size=1), 26)
+    add('c2_n26_nobound', PolyModel('cubic-2', input_size=26, output_size=1), 26, with_bound=False)
+    add('c3_n8', PolyModel('cubic-3', input_size=8, output_size=1), 8)
+    add('c3_n40', PolyModel('cubic-3', input_size=40, output_size=1), 40, pts_scale=0.5)
+    add('linear_n5_m2', PolyModel('linear', input_size=5, output_size=2), 5)
+    sc = np.stack((rng.normal(size=7) - 2., rng.normal(size=7) + 3.), axis=1)
+    add('c2_n7_scaled', PolyModel('cubic-2', input_size=7, output_size=1, input_scales=sc), 7)
+    cfgs = [PolyConfig('linear'),
+            PolyConfig('quadratic', input_mask=[0, 2, 3], output_mask=[0, 2]),
+            PolyConfig('cubic-2', input_mask=[1, 4, 5], output_mask=[1]),
+            PolyConfig('cubic-3', input_mask=[0, 1, 2, 3, 4], output_mask=[2]),
+            PolyConfig('cubic-2', input_mask=[0, 5], output_mask=[0, 2])]
+    add('masked_n6_m3', PolyModel(cfgs, input_size=6, output_size=3), 6)
+    gio.save('poly_eval.npz', dict(cases=cases))
+
+
+def target_logp(P):
+    def f(x):
+        return np.atleast_1d(-0.5 * x @ P @ x - 0.02 * np.sum(x**3 * np.exp(-0.1 * x**2)))
+    return f
+
+
+def make_density(n, order, rng, transform=False, decay=False, module_scales=False, n_fit_mult=4, spread=1.):
+    A = rng.normal(size=(n, n))
+    cov = A @ A.T / n + np.eye(n)
+    P = np.linalg.inv(cov)
+    mod = bf.Module(fun=target_logp(P), input_vars='x', output_vars='logp')
+    kw = {}
+    if module_scales:
+        kw['input_scales'] = np.stack((-2. + 0.1 * rng.normal(size=n), 3. + 0.1 * rng.normal(size=n)), axis=1)
+    sur = PolyModel(order, input_size=n, output_size=1, input_vars='x', output_vars='logp', **kw)
+    dkw = {}
+    if transform:
+        ranges = np.stack((-12. - rng.uniform(size=n), 12. + rng.uniform(size=n)), axis=1)
+        hb = np.zeros((n, 2), np.uint8)
+        hb[0] = (1, 1)
+        if n > 2:
+            hb[2] = (1, 0)
+        if n > 3:
+            hb[3] = (0, 1)
+        dkw.update(input_scales=ranges, hard_bounds=hb)
+    den = bf.Density(density_name='logp', module_list=[mod], surrogate_list=[sur], input_vars='x',
+                     decay_options={'use_decay': decay}, **dkw)
+    L = np.linalg.cholesky(cov)
+    xf = (L @ rng.normal(size=(n, n_fit_mult * sur.n_param))).T * spread
+    vd = [den.fun(x, original_space=True, use_surrogate=False) for x in xf]
+    den.fit(vd)
+    den.use_surrogate = True
+    return den, cov, xf
+
+
+def make_density_cases():
+    rng = np.random.default_rng(23)
+    cases = []
+    for name, n, order, tr, dc, ms in (('c2_n4_all', 4, 'cubic-2', True, True, True),
+                                       ('c2_n6_tr_decay', 6, 'cubic-2', True, True, False),
+                                       ('quad_n3_plain', 3, 'quadratic', False, False, False),
+                                       ('c3_n5_decay', 5, 'cubic-3', False, True, False),
+                                       ('c2_n26_decay', 26, 'cubic-2', False, True, False)):
+        den, cov, xf = make_density(n, order, rng, tr, dc, ms)
+        L = np.linalg.cholesky(cov)
+        Xo = np.concatenate(((L @ rng.normal(size=(n, 8))).T * 0.8, (L @ rng.normal(size=(n, 6))).T * 4.))
+        if tr:
+            Xo = np.clip(Xo, -11.5, 11.5)
+        Xt = np.array([den.from_original(x) for x in Xo])
+        lp, gr = [], []
+        for x in Xt:
+            a, b = den.logp_and_grad(x, original_space=False)
+            lp.append(float(a)), gr.append(np.array(b))
+        cases.append(dict(name=name, spec=density_spec(den), X=Xt, logp=np.array(lp), grad=np.array(gr)))
+    gio.save('density.npz', dict(cases=cases))
+
+
+def make_fit():
+    rng = np.random.default_rng(5)
+    cases = []
+
+    def run(name, configs, n, m, N, w=None, scale=1., alpha_p=100., center_max=True):
+        sur = PolyModel(configs, input_size=n, output_size=m,
+                        bound_options=dict(alpha_p=alpha_p, center_max=center_max))
+        x = rng.normal(size=(N, n)) * scale + 0.3
+        tmp = PolyModel(deepcopy(configs), input_size=n, output_size=m)
+        inject(tmp, rng, 1.)
+        tmp._use_bound = False
+        y = np.array([tmp._fun(xi) for xi in x]) + 1e-3 * rng.normal(size=(N, m))
+        logp = y[:, 0].copy()
+        sur.fit(x, y, logp, w)
+        cases.append(dict(name=name, x=x, y=y, logp=logp, w=w, alpha_p=alpha_p, center_max=center_max,
+                          spec=poly_spec(sur)))
+
+    run('quad_n2', 'quadratic', 2, 1, 30)
+    run('c2_n6_w', 'cubic-2', 6, 1, 300, w=rng.uniform(0.5, 1.5, size=300))
+    run('c3_n5', 'cubic-3', 5, 1, 250, scale=0.7)
+    run('c2_n8_m2_p90', 'cubic-2', 8, 2, 500, alpha_p=90., center_max=False)
+    cfgs = [PolyConfig('linear'), PolyConfig('quadratic', input_mask=[0, 2, 3], output_mask=[0, 2]),
+            PolyConfig('cubic-2', input_mask=[1, 4, 5], output_mask=[1])]
+    run('masked_n6_m3', cfgs, 6, 3, 200)
+    run('c2_n16', 'cubic-2', 16, 1, 4 * 409)
+    gio.save('fit.npz', dict(cases=cases))
+
+
+class Replay:
+    """Duck-typed stand-in for numpy.random.Generator: serves the Philox draws of include/bfb_rng.h."""
+
+    def __init__(self, u, z):
+        self.u, self.z, self.t = u, z, 0
+
+    def normal(self, size=None):
+        k = 1 if size is None else int(size)
+        v = self.z[self.t:self.t + k].copy()
+        assert v.size == k, 'replay stream exhausted'
+        self.t += k
+        return v if size is not None else float(v[0])
+
+    def uniform(self):
+        v = self.u[self.t]
+        self.t += 1
+        return float(v)
+
+
+def run_reference_chains(den, sampler, trace_kw, x0, seed, n_draw_cap):
+    n_chain = x0.shape[0]
+    cls, tcls = (NUTS, NTrace) if sampler == 'NUTS' else (HMC, HTrace)
+    base = tcls(n_chain=n_chain, x_0=x0, random_generator=0, **trace_kw)
+    res = dict(samples=[], final_step=[], final_var=[], n_draws=[], draws_u=[], draws_z=[])
+    names = ('logp', 'energy', 'tree_depth', 'tree_size', 'mean_tree_accept', 'step_size', 'step_size_bar',
+             'energy_change', 'max_energy_change', 'diverging') if sampler == 'NUTS' else \
+            ('logp', 'energy', 'n_int_step', 'accept_stat', 'accepted', 'step_size', 'step_size_bar',
+             'energy_change', 'diverging')
+    for k in names:
+        res[k] = []
+    step0 = var0 = None
+    for i in range(n_chain):
+        t = deepcopy(base)
+        t._init_chain(i)
+        u, z = bf_oracle.rng_fill(seed, i, 0, n_draw_cap)
+        rep = Replay(u, z)
+        t._random_generator = rep
+        if i == 0:
+            step0 = float(np.exp(t.step_size._log_step))
+            var0 = np.array(t.metric._var)
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            cls(logp_and_grad=lambda x: den.logp_and_grad(x, original_space=False), sample_trace=t).run(verbose=False)
+        res['samples'].append(np.array(t._samples))
+        for k in names:
+            res[k].append(np.array(getattr(t.stats, '_' + k), dtype=float))
+        ss = t.step_size
+        res['final_step'].append([ss._log_step, ss._log_bar, ss._hbar, ss._count])
+        res['final_var'].append(np.array(t.metric._var))
+        res['n_draws'].append(rep.t)
+        res['draws_u'].append(u), res['draws_z'].append(z)
+    nmax = max(res['n_draws']) + 4
+    out = {k: np.array(v) for k, v in res.items()}
+    out['draws_u'] = out['draws_u'][:, :nmax]
+    out['draws_z'] = out['draws_z'][:, :nmax]
+    out['step0'] = step0
+    out['var0'] = var0
+    return out
+
+
+def make_sampler():
+    rng = np.random.default_rng(77)
+    cases = []
+
+    def add(name, sampler, den, x0, seed, n_draw_cap=60000, **trace_kw):
+        r = run_reference_chains(den, sampler, trace_kw, x0, seed, n_draw_cap)
+        cases.append(dict(name=name, sampler=sampler, spec=density_spec(den), x0=x0, seed=seed,
+                          trace_kw={k: (v if not isinstance(v, bool) else int(v)) for k, v in trace_kw.items()},
+                          result=r))
+        print(name, 'mean depth', np.mean(r['tree_depth']) if sampler == 'NUTS' else '-',
+              'n_div', int(np.sum(r['diverging'])), 'draws', r['n_draws'])
+
+    den, cov, xf = make_density(2, 'quadratic', rng)
+    add('nuts_quad_n2', 'NUTS', den, xf[:4].copy(), 101, n_iter=80, n_warmup=40)
+
+    den, cov, xf = make_density(6, 'cubic-2', rng, transform=True, decay=True)
+    x0 = np.array([den.from_original(np.clip(x, -11., 11.)) for x in xf[:3]])
+    add('nuts_c2_n6_tr_decay', 'NUTS', den, x0, 202, n_iter=50, n_warmup=25)
+    L = np.linalg.cholesky(cov)
+    far = np.array([den.from_original(np.clip((L @ rng.normal(size=6)) * 3.5, -11., 11.)) for _ in range(2)])
+    add('nuts_c2_n6_far_start', 'NUTS', den, far, 303, n_iter=30, n_warmup=15)
+    add('nuts_c2_n6_depthcap', 'NUTS', den, x0[:2], 404, n_iter=30, n_warmup=10, max_treedepth=2)
+    add('nuts_c2_n6_divergent', 'NUTS', den, x0[:2], 505, n_iter=30, n_warmup=10, max_change=0.2,
+        step_size=2.5, adapt_step_size=False)
+    add('nuts_c2_n6_noadapt', 'NUTS', den, x0[:2], 606, n_iter=25, n_warmup=10, adapt_step_size=False,
+        adapt_metric=False, step_size=0.6)
+    add('hmc_c2_n6', 'HMC', den, x0[:2], 707, n_iter=30, n_warmup=15, n_int_step=8)
+
+    den, cov, xf = make_density(16, 'cubic-2', rng)
+    add('nuts_c2_n16', 'NUTS', den, xf[:2].copy(), 808, n_iter=40, n_warmup=20)
+
+    den, cov, xf = make_density(5, 'cubic-3', rng, decay=True)
+    add('nuts_c3_n5', 'NUTS', den, xf[:2].copy(), 909, n_iter=40, n_warmup=20)
+    gio.save('sampler.npz', dict(cases=cases))
+
+
+if __name__ == '__main__':
+    which = sys.argv[1:] or ['poly_kat', 'poly_eval', 'density', 'fit', 'sampler']
+    if 'poly_kat' in which:
+        make_poly_kat()
+    if 'poly_eval' in which:
+        make_poly_eval()
+    if 'density' in which:
+        make_density_cases()
+    if 'fit' in which:
+        make_fit()
+    if 'sampler' in which:
+        make_sampler()
+    for f in sorted(os.listdir(gio.GOLDEN_DIR)):
+        if f.endswith('.npz'):
+            print(f, os.path.getsize(os.path.join(gio.GOLDEN_DIR, f)))
