@@ -100,8 +100,8 @@ EARLY, EARLY_TOL, LATE_TOL = 8, 1e-10, 2e-4
 def _flt(a, b, tag):
     a, b = np.asarray(a, float), np.asarray(b, float)
     assert a.shape == b.shape, tag
-    assert np.allclose(a[:, :EARLY], b[:, :EARLY], rtol=EARLY_TOL, atol=EARLY_TOL), tag
-    assert np.allclose(a, b, rtol=LATE_TOL, atol=LATE_TOL), tag
+    assert np.allclose(a[:, :EARLY], b[:, :EARLY], rtol=EARLY_TOL, atol=EARLY_TOL, equal_nan=True), tag
+    assert np.allclose(a, b, rtol=LATE_TOL, atol=LATE_TOL, equal_nan=True), tag
 
 
 def test_sampler_cases(oracle):
