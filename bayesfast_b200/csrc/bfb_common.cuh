@@ -1,0 +1,138 @@
+// bfb_common.cuh -- shared declarations of libbfb200 (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/bfb200.h"
+#include "../../include/bfb_rng.h"
+
+#define BFB_WARP 32
+#define BFB_FULL 0xffffffffu
+
+void bfb_set_error(const char *fmt, ...);
+
+#define BFB_CUDA(call)                                                                           \
+    do {                                                                                         \
+        cudaError_t e__ = (call);                                                                \
+        if (e__ != cudaSuccess) {                                                                \
+            bfb_set_error("%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__));   \
+            return BFB_ERR_CUDA;                                                                 \
+        }                                                                                        \
+    } while (0)
+
+#define BFB_REQUIRE(cond, code, ...)                                                             \
+    do {                                                                                         \
+        if (!(cond)) { bfb_set_error(__VA_ARGS__); return (code); }                              \
+    } while (0)
+
+// ----------------------------------------------------------------------------------------------
+// Device-side model tables.  Every output o of the PolyModel is flattened on the host into a full-n
+// polynomial (masked configs scattered into full tensors, zeros elsewhere), so one evaluator serves
+// masks, multiple configs and multiple outputs.  Matrices are stored "k-major": T[k][j] with the lane
+// index j contiguous and padded to np = 32*ceil(n/32) columns (zeros), so lane j reads T[k*np + j].
+// ----------------------------------------------------------------------------------------------
+struct DevModel {
+    int n, np, m;
+    int has_quad, has_c2, has_c3;
+    const double *c0;    // [m]
+    const double *lin;   // [m][np]
+    const double *S;     // [m][n][np]   symmetrised quadratic: S[k][j] = a_kj (k<j), 2 a_jj, a_jk (k>j)
+    const double *A1T;   // [m][n][np]   A1T[k][j] = A[j][k]     (t_j = sum_k A[j][k] x_k)
+    const double *A2;    // [m][n][np]   A2[k][j]  = A[k][j]     (u_j = sum_k A[k][j] x_k^2)
+    const double *c3;    // [m][C(n,3)]  packed j<k<l
+    int64_t n_c3;
+    int use_bound;
+    const double *mu;    // [np]
+    const double *HT;    // [n][np]  HT[k][j] = H[j][k]
+    double alpha;
+    const double *f_mu;  // [m]
+    int use_scales;
+    const double *s0, *sdiff;   // [np] (sdiff padded with 1)
+    int use_decay;
+    const double *d_mu;  // [np]
+    const double *d_H;   // [n][np]  d_H[k][j] = Hd[k][j]
+    double d_alpha2, d_gamma;
+    int use_transform;
+    const double *r_lo, *r_w;   // [np] ranges[:,0], ranges[:,1]-ranges[:,0]
+    const int *hb;       // [np] bit0 = lower bound hard, bit1 = upper bound hard
+};
+
+struct HostConfig {
+    int order, n_in, n_out;
+    std::vector<int64_t> in_mask, out_mask;
+    int64_t coef_off;   // offset of this config's packed coefficients in the concatenated buffer
+    int64_t n_packed;   // packed coefficients per output
+};
+
+// Chain state kept on the device between bfb_sampler_run calls (SoA, chain-major).
+struct ChainState {
+    int64_t C;
+    int n, np;
+    double *q;        // [C][np]
+    double *logp;     // [C]  cached logp at q
+    double *g;        // [C][np] cached grad at q
+    double *var;      // [C][np]
+    double *fg_mean, *fg_raw, *bg_mean, *bg_raw;   // [C][np]
+    double *fg_n, *bg_n;                             // [C]
+    double *log_step, *log_bar, *hbar, *mu_da;       // [C]
+    int64_t *count;                                  // [C]
+    int64_t *n_samples, *previous_update;            // [C]
+    int32_t *adapt_window;                           // [C]
+    int64_t *t_draw;                                 // [C]
+    int64_t *iter;                                   // [C] iterations done
+    int32_t *status;                                 // [C]
+    unsigned long long *tree_total;                  // [1]
+};
+
+struct FitState;
+
+struct bfb_context {
+    int device;
+    cudaStream_t stream;
+    bool own_stream;
+    cudaEvent_t ev0, ev1;
+    float last_ms;
+    int64_t launches;
+    int sm_count;
+    // model
+    bool has_model;
+    int n, m, np;
+    std::vector<HostConfig> configs;
+    std::vector<double> packed;          // host copy of packed coefficients
+    bfb_model_desc desc_flags;           // scalar flags only (pointers invalid)
+    std::vector<double> h_mu, h_hess, h_fmu, h_s0, h_sdiff, h_dmu, h_dhess, h_ranges;
+    std::vector<uint8_t> h_hb;
+    std::vector<void *> model_allocs;
+    DevModel dm;
+    // sampler
+    bool has_chains;
+    bfb_sampler_cfg scfg;
+    ChainState cs;
+    std::vector<void *> chain_allocs;
+    // fit
+    FitState *fit;
+};
+
+int bfb_upload_model(bfb_context *h);          // (re)build the device tables from configs/packed
+void bfb_free_list(std::vector<void *> &v);
+
+// ----------------------------------------------------------------------------------------------
+// warp helpers
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(BFB_FULL, v, o);
+    return v;   // butterfly: bitwise identical on every lane
+}
+
+__device__ __forceinline__ double np_logaddexp(double a, double b)
+{
+    // numpy's logaddexp (the reference: nuts.py:85,163)
+    if (a == b) return a + 0.6931471805599453;
+    double tmp = a - b;
+    if (tmp > 0) return a + log1p(exp(-tmp));
+    else if (tmp <= 0) return b + log1p(exp(tmp));
+    return tmp;
+}

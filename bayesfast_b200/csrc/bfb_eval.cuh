@@ -1,0 +1,247 @@
+// bfb_eval.cuh -- warp-cooperative evaluation of the flattened polynomial and of the surrogate density.
+// One warp evaluates one point; lane `lane` owns dimensions j = lane + 32*r, r < NPL.
+#pragma once
+#include "bfb_common.cuh"
+
+// index of (a<b<c) in the packed cubic-3 order of _poly.pyx:169-177
+__device__ __forceinline__ int64_t c3_index(int a, int b, int c, int n)
+{
+    // triples with first index < a: C(n,3) - C(n-a,3)
+    int64_t na = n - a;
+    int64_t before_a = ((int64_t)n * (n - 1) * (n - 2) - na * (na - 1) * (na - 2)) / 6;
+    // within first index a: pairs (b',c') with a<b'<b : C(n-a-1,2) - C(n-b,2)
+    int64_t nb = n - b;
+    int64_t before_b = ((na - 1) * (na - 2) - nb * (nb - 1)) / 2;
+    return before_a + before_b + (c - b - 1);
+}
+
+// Polynomial value f (all lanes) and Jacobian row J (lane-owned entries) of output `o` at the point whose
+// coordinates are staged in shared memory xsm[0..n) (and held per lane in x[]).
+// Restates _quadratic_f/_j, _cubic_2_f/_j, _cubic_3_f/_j (modules/_poly.pyx:13-137) and _linear (poly.py:339-352).
+template <int NPL>
+__device__ __forceinline__ void poly_fg(const DevModel &M, int o, const double *xsm, const double (&x)[NPL],
+                                        int lane, double &f, double (&J)[NPL])
+{
+    const int n = M.n, np = M.np;
+    double fpart = 0.;
+    const double *lin = M.lin + (size_t)o * np;
+#pragma unroll
+    for (int r = 0; r < NPL; ++r) {
+        J[r] = lin[lane + 32 * r];
+        fpart = fma(J[r], x[r], fpart);
+    }
+    if (M.has_quad) {
+        const double *S = M.S + (size_t)o * n * np;
+        double y[NPL];
+#pragma unroll
+        for (int r = 0; r < NPL; ++r) y[r] = 0.;
+        for (int k = 0; k < n; ++k) {
+            double xk = xsm[k];
+#pragma unroll
+            for (int r = 0; r < NPL; ++r) y[r] = fma(S[(size_t)k * np + lane + 32 * r], xk, y[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < NPL; ++r) {
+            J[r] += y[r];
+            fpart = fma(0.5 * x[r], y[r], fpart);
+        }
+    }
+    if (M.has_c2) {
+        const double *A1T = M.A1T + (size_t)o * n * np;
+        const double *A2 = M.A2 + (size_t)o * n * np;
+        double t[NPL], u[NPL];
+#pragma unroll
+        for (int r = 0; r < NPL; ++r) { t[r] = 0.; u[r] = 0.; }
+        for (int k = 0; k < n; ++k) {
+            double xk = xsm[k];
+            double xk2 = xk * xk;
+#pragma unroll
+            for (int r = 0; r < NPL; ++r) {
+                t[r] = fma(A1T[(size_t)k * np + lane + 32 * r], xk, t[r]);
+                u[r] = fma(A2[(size_t)k * np + lane + 32 * r], xk2, u[r]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < NPL; ++r) {
+            J[r] += fma(2. * x[r], t[r], u[r]);
+            fpart = fma(x[r] * x[r], t[r], fpart);
+        }
+    }
+    if (M.has_c3) {
+        const double *c3 = M.c3 + (size_t)o * M.n_c3;
+#pragma unroll
+        for (int r = 0; r < NPL; ++r) {
+            int j = lane + 32 * r;
+            double g3 = 0.;
+            if (j < n) {
+                for (int k = 0; k < n - 1; ++k) {
+                    if (k == j) continue;
+                    double s = 0.;
+                    for (int l = k + 1; l < n; ++l) {
+                        if (l == j) continue;
+                        int a = min(j, k), c = max(j, l);
+                        int b = j + k + l - a - c;
+                        s = fma(c3[c3_index(a, b, c, n)], xsm[l], s);
+                    }
+                    g3 = fma(s, xsm[k], g3);
+                }
+            }
+            J[r] += g3;
+            fpart = fma(x[r] * (1. / 3.), g3, fpart);   // Euler: sum_j x_j dP3/dx_j = 3 P3
+        }
+    }
+    f = M.c0[o] + warp_sum(fpart);
+}
+
+// sm[k-major][lane] matrix-vector product y_j = sum_k T[k][j] * v[k], v staged in shared memory
+template <int NPL>
+__device__ __forceinline__ void matvec(const double *T, int n, int np, const double *vsm, int lane, double (&y)[NPL])
+{
+#pragma unroll
+    for (int r = 0; r < NPL; ++r) y[r] = 0.;
+    for (int k = 0; k < n; ++k) {
+        double vk = vsm[k];
+#pragma unroll
+        for (int r = 0; r < NPL; ++r) y[r] = fma(T[(size_t)k * np + lane + 32 * r], vk, y[r]);
+    }
+}
+
+// PolyModel._fun_and_jac with the radial bound (poly.py:466-503) preceded by the module-level rescale
+// and followed by jac / scales_diff (core/module.py:80-85, 221-227).  xo: point in the surrogate's
+// (un-rescaled) input space.  xsm, dsm: two per-warp shared buffers of np doubles.
+template <int NPL>
+__device__ __forceinline__ void module_fg(const DevModel &M, int o, const double (&xo)[NPL], int lane,
+                                          double *xsm, double *dsm, double &f, double (&J)[NPL])
+{
+    const int n = M.n, np = M.np;
+    double xs[NPL];
+#pragma unroll
+    for (int r = 0; r < NPL; ++r) {
+        int j = lane + 32 * r;
+        xs[r] = M.use_scales ? (xo[r] - M.s0[j]) / M.sdiff[j] : xo[r];
+        if (j >= n) xs[r] = 0.;
+    }
+    bool outside = false;
+    double beta = 0., d[NPL], Hd[NPL];
+    if (M.use_bound) {
+#pragma unroll
+        for (int r = 0; r < NPL; ++r) {
+            int j = lane + 32 * r;
+            d[r] = (j < n) ? xs[r] - M.mu[j] : 0.;
+            dsm[j] = d[r];
+        }
+        __syncwarp();
+        matvec<NPL>(M.HT, n, np, dsm, lane, Hd);
+        double part = 0.;
+#pragma unroll
+        for (int r = 0; r < NPL; ++r) part = fma(d[r], Hd[r], part);
+        beta = sqrt(warp_sum(part));
+        outside = beta > M.alpha;
+        __syncwarp();
+    }
+    if (!outside) {
+#pragma unroll
+        for (int r = 0; r < NPL; ++r) xsm[lane + 32 * r] = xs[r];
+        __syncwarp();
+        poly_fg<NPL>(M, o, xsm, xs, lane, f, J);
+        __syncwarp();
+    } else {
+        // _fj_bound, poly.py:480-503
+        const double alpha = M.alpha;
+        double x0[NPL], jj0[NPL], ff0;
+#pragma unroll
+        for (int r = 0; r < NPL; ++r) {
+            int j = lane + 32 * r;
+            x0[r] = (j < n) ? (alpha * xs[r] + (beta - alpha) * M.mu[j]) / beta : 0.;
+            xsm[j] = x0[r];
+        }
+        __syncwarp();
+        poly_fg<NPL>(M, o, xsm, x0, lane, ff0, jj0);
+        __syncwarp();
+        const double fmu = M.f_mu[o];
+        f = (beta * ff0 - (beta - alpha) * fmu) / alpha;
+        double part = 0.;
+#pragma unroll
+        for (int r = 0; r < NPL; ++r) part = fma(jj0[r], d[r], part);
+        double jd = warp_sum(part);
+        double s = (ff0 - fmu) / alpha - jd / beta;
+#pragma unroll
+        for (int r = 0; r < NPL; ++r) J[r] = jj0[r] + s * (Hd[r] / beta);
+    }
+    if (M.use_scales) {
+#pragma unroll
+        for (int r = 0; r < NPL; ++r) J[r] = J[r] / M.sdiff[lane + 32 * r];
+    }
+}
+
+// transforms/_constraint.pyx:133-221 for one coordinate: value, first and second derivative of to_original
+__device__ __forceinline__ void to_original_1(double t, double lo, double w, int hb, double &f, double &j, double &jj)
+{
+    double tf, tj, tjj;
+    if (hb == 3) {
+        tf = 1. / (1. + exp(-t));
+        tj = tf * (1. - tf);
+        double e = exp(t);
+        tjj = -e * (e - 1.) / (e + 1.) / (e + 1.) / (e + 1.);
+    } else if (hb == 1) {
+        tf = exp(t); tj = tf; tjj = tf;
+    } else if (hb == 2) {
+        double e = exp(t);
+        tf = 1. - e; tj = -e; tjj = -e;
+    } else {
+        tf = t; tj = 1.; tjj = 0.;
+    }
+    f = lo + tf * w; j = tj * w; jj = tjj * w;
+}
+
+// Density.logp_and_grad(x, original_space=False, use_surrogate=True) for a surrogate-only density
+// (core/density.py:487-566, 724-754).  xt: point in the transformed space. logp on all lanes.
+template <int NPL>
+__device__ __forceinline__ void density_eval(const DevModel &M, const double (&xt)[NPL], int lane,
+                                             double *xsm, double *dsm, double &logp, double (&grad)[NPL])
+{
+    const int n = M.n, np = M.np;
+    double xo[NPL], tj[NPL], tjj[NPL];
+#pragma unroll
+    for (int r = 0; r < NPL; ++r) {
+        int j = lane + 32 * r;
+        if (M.use_transform && j < n) to_original_1(xt[r], M.r_lo[j], M.r_w[j], M.hb[j], xo[r], tj[r], tjj[r]);
+        else { xo[r] = xt[r]; tj[r] = 1.; tjj[r] = 0.; }
+    }
+    double f, J[NPL];
+    module_fg<NPL>(M, 0, xo, lane, xsm, dsm, f, J);
+#pragma unroll
+    for (int r = 0; r < NPL; ++r) grad[r] = J[r] * tj[r];
+    if (M.use_decay) {
+        double d[NPL], Hd[NPL];
+#pragma unroll
+        for (int r = 0; r < NPL; ++r) {
+            int j = lane + 32 * r;
+            d[r] = (j < n) ? xo[r] - M.d_mu[j] : 0.;
+            dsm[j] = d[r];
+        }
+        __syncwarp();
+        matvec<NPL>(M.d_H, n, np, dsm, lane, Hd);
+        double part = 0.;
+#pragma unroll
+        for (int r = 0; r < NPL; ++r) part = fma(d[r], Hd[r], part);
+        double beta2 = warp_sum(part);
+        __syncwarp();
+        double ex = beta2 - M.d_alpha2;
+        f -= M.d_gamma * (ex > 0. ? ex : 0.);
+        if (beta2 > M.d_alpha2) {
+#pragma unroll
+            for (int r = 0; r < NPL; ++r) grad[r] -= 2. * M.d_gamma * Hd[r];
+        }
+    }
+    if (M.use_transform) {
+        double part = 0.;
+#pragma unroll
+        for (int r = 0; r < NPL; ++r) {
+            int j = lane + 32 * r;
+            if (j < n) { part += log(fabs(tj[r])); grad[r] += tjj[r] / tj[r]; }
+        }
+        f += warp_sum(part);
+    }
+    logp = f;
+}

@@ -1,0 +1,502 @@
+// bfb_model.cu -- handle life cycle, model upload (host-side flattening into device tables),
+// batched evaluation entry points, RNG exposure.
+#include "bfb_common.cuh"
+#include "bfb_eval.cuh"
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+
+static thread_local char g_err[1024] = "";
+
+void bfb_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char *bfb_last_error(void) { return g_err; }
+extern "C" int bfb_version(void) { return 100; }
+
+extern "C" int bfb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+void bfb_free_list(std::vector<void *> &v)
+{
+    for (void *p : v) cudaFree(p);
+    v.clear();
+}
+
+void bfb_fit_free(bfb_context *h);
+
+extern "C" int bfb_create(int device, bfb_handle *out)
+{
+    BFB_REQUIRE(out != nullptr, BFB_ERR_ARG, "bfb_create: out is NULL");
+    int cnt = 0;
+    cudaError_t e = cudaGetDeviceCount(&cnt);
+    if (e != cudaSuccess || cnt == 0) {
+        bfb_set_error("bfb_create: no CUDA device available (%s); libbfb200 has no CPU fallback",
+                      e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        cudaGetLastError();
+        return BFB_ERR_CUDA;
+    }
+    BFB_REQUIRE(device >= 0 && device < cnt, BFB_ERR_ARG, "bfb_create: device %d out of range [0,%d)", device, cnt);
+    BFB_CUDA(cudaSetDevice(device));
+    bfb_context *h = new bfb_context();
+    h->device = device;
+    h->own_stream = true;
+    h->last_ms = 0.f;
+    h->launches = 0;
+    h->has_model = false;
+    h->has_chains = false;
+    h->fit = nullptr;
+    memset(&h->dm, 0, sizeof(h->dm));
+    memset(&h->cs, 0, sizeof(h->cs));
+    BFB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    BFB_CUDA(cudaEventCreate(&h->ev0));
+    BFB_CUDA(cudaEventCreate(&h->ev1));
+    cudaDeviceProp prop;
+    BFB_CUDA(cudaGetDeviceProperties(&prop, device));
+    h->sm_count = prop.multiProcessorCount;
+    *out = h;
+    return BFB_OK;
+}
+
+extern "C" int bfb_destroy(bfb_handle h)
+{
+    if (!h) return BFB_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    bfb_free_list(h->model_allocs);
+    bfb_free_list(h->chain_allocs);
+    bfb_fit_free(h);
+    cudaEventDestroy(h->ev0);
+    cudaEventDestroy(h->ev1);
+    if (h->own_stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return BFB_OK;
+}
+
+extern "C" int bfb_set_stream(bfb_handle h, void *cuda_stream)
+{
+    BFB_REQUIRE(h, BFB_ERR_ARG, "null handle");
+    BFB_CUDA(cudaSetDevice(h->device));
+    if (h->own_stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); h->own_stream = false; }
+    h->stream = (cudaStream_t)cuda_stream;
+    return BFB_OK;
+}
+
+extern "C" int bfb_synchronize(bfb_handle h)
+{
+    BFB_REQUIRE(h, BFB_ERR_ARG, "null handle");
+    BFB_CUDA(cudaSetDevice(h->device));
+    BFB_CUDA(cudaStreamSynchronize(h->stream));
+    return BFB_OK;
+}
+
+extern "C" int bfb_last_kernel_ms(bfb_handle h, float *ms)
+{
+    BFB_REQUIRE(h && ms, BFB_ERR_ARG, "null argument");
+    *ms = h->last_ms;
+    return BFB_OK;
+}
+
+extern "C" int64_t bfb_launch_count(bfb_handle h) { return h ? h->launches : 0; }
+
+// ----------------------------------------------------------------------------------------------
+// model
+// ----------------------------------------------------------------------------------------------
+static int64_t packed_size(int order, int64_t ni)
+{
+    switch (order) {
+    case BFB_LINEAR: return ni + 1;
+    case BFB_QUADRATIC: return ni * (ni + 1) / 2;
+    case BFB_CUBIC_2: return ni * ni;
+    case BFB_CUBIC_3: return ni * (ni - 1) * (ni - 2) / 6;
+    }
+    return -1;
+}
+
+static int64_t c3_index_host(int a, int b, int c, int n)
+{
+    int64_t na = n - a;
+    int64_t before_a = ((int64_t)n * (n - 1) * (n - 2) - na * (na - 1) * (na - 2)) / 6;
+    int64_t nb = n - b;
+    int64_t before_b = ((na - 1) * (na - 2) - nb * (nb - 1)) / 2;
+    return before_a + before_b + (c - b - 1);
+}
+
+template <class T>
+static int upload(bfb_context *h, const std::vector<T> &v, const T **dst)
+{
+    void *p = nullptr;
+    size_t bytes = sizeof(T) * (v.empty() ? 1 : v.size());
+    BFB_CUDA(cudaMalloc(&p, bytes));
+    h->model_allocs.push_back(p);
+    if (!v.empty()) BFB_CUDA(cudaMemcpyAsync(p, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice, h->stream));
+    *dst = (const T *)p;
+    return BFB_OK;
+}
+
+int bfb_upload_model(bfb_context *h)
+{
+    BFB_CUDA(cudaSetDevice(h->device));
+    BFB_CUDA(cudaStreamSynchronize(h->stream));
+    bfb_free_list(h->model_allocs);
+    const int n = h->n, m = h->m, np = h->np;
+    DevModel &D = h->dm;
+    memset(&D, 0, sizeof(D));
+    D.n = n; D.np = np; D.m = m;
+    bool hq = false, h2 = false, h3 = false;
+    for (auto &c : h->configs) {
+        hq |= c.order == BFB_QUADRATIC; h2 |= c.order == BFB_CUBIC_2; h3 |= c.order == BFB_CUBIC_3;
+    }
+    D.has_quad = hq; D.has_c2 = h2; D.has_c3 = h3;
+    int64_t nc3 = (int64_t)n * (n - 1) * (n - 2) / 6;
+    D.n_c3 = nc3;
+    std::vector<double> c0(m, 0.), lin((size_t)m * np, 0.), S, A1T, A2, c3;
+    if (hq) S.assign((size_t)m * n * np, 0.);
+    if (h2) { A1T.assign((size_t)m * n * np, 0.); A2.assign((size_t)m * n * np, 0.); }
+    if (h3) c3.assign((size_t)m * (nc3 > 0 ? nc3 : 1), 0.);
+    for (auto &c : h->configs) {
+        const int ni = c.n_in;
+        for (int q = 0; q < c.n_out; ++q) {
+            const int o = (int)c.out_mask[q];
+            const double *a = h->packed.data() + c.coef_off + (int64_t)q * c.n_packed;
+            if (c.order == BFB_LINEAR) {
+                c0[o] += a[0];
+                for (int k = 0; k < ni; ++k) lin[(size_t)o * np + c.in_mask[k]] += a[1 + k];
+            } else if (c.order == BFB_QUADRATIC) {
+                int64_t idx = 0;
+                double *So = S.data() + (size_t)o * n * np;
+                for (int k = 0; k < ni; ++k)
+                    for (int l = k; l < ni; ++l) {
+                        double v = a[idx++];
+                        int64_t K = c.in_mask[k], L = c.in_mask[l];
+                        if (k == l) So[K * np + K] += 2. * v;
+                        else { So[K * np + L] += v; So[L * np + K] += v; }
+                    }
+            } else if (c.order == BFB_CUBIC_2) {
+                double *T1 = A1T.data() + (size_t)o * n * np, *T2 = A2.data() + (size_t)o * n * np;
+                for (int k = 0; k < ni; ++k)
+                    for (int l = 0; l < ni; ++l) {
+                        double v = a[(int64_t)k * ni + l];
+                        int64_t K = c.in_mask[k], L = c.in_mask[l];
+                        T1[L * np + K] += v;   // A1T[k'][j] = A[j][k']
+                        T2[K * np + L] += v;   // A2[k'][j]  = A[k'][j]
+                    }
+            } else {
+                int64_t idx = 0;
+                double *Co = c3.data() + (size_t)o * nc3;
+                for (int k = 0; k < ni; ++k)
+                    for (int l = k + 1; l < ni; ++l)
+                        for (int p = l + 1; p < ni; ++p)
+                            Co[c3_index_host((int)c.in_mask[k], (int)c.in_mask[l], (int)c.in_mask[p], n)] += a[idx++];
+            }
+        }
+    }
+    int rc;
+    if ((rc = upload(h, c0, &D.c0))) return rc;
+    if ((rc = upload(h, lin, &D.lin))) return rc;
+    if ((rc = upload(h, S, &D.S))) return rc;
+    if ((rc = upload(h, A1T, &D.A1T))) return rc;
+    if ((rc = upload(h, A2, &D.A2))) return rc;
+    if ((rc = upload(h, c3, &D.c3))) return rc;
+
+    const bfb_model_desc &F = h->desc_flags;
+    auto pad = [&](const std::vector<double> &v, double fill) {
+        std::vector<double> o(np, fill);
+        for (int j = 0; j < n && j < (int)v.size(); ++j) o[j] = v[j];
+        return o;
+    };
+    D.use_bound = F.use_bound; D.alpha = F.alpha;
+    {
+        std::vector<double> HT((size_t)n * np, 0.);
+        if (F.use_bound)
+            for (int j = 0; j < n; ++j)
+                for (int k = 0; k < n; ++k) HT[(size_t)k * np + j] = h->h_hess[(size_t)j * n + k];
+        if ((rc = upload(h, pad(h->h_mu, 0.), &D.mu))) return rc;
+        if ((rc = upload(h, HT, &D.HT))) return rc;
+        std::vector<double> fm(m, 0.);
+        for (int o = 0; o < m && o < (int)h->h_fmu.size(); ++o) fm[o] = h->h_fmu[o];
+        if ((rc = upload(h, fm, &D.f_mu))) return rc;
+    }
+    D.use_scales = F.use_scales;
+    if ((rc = upload(h, pad(h->h_s0, 0.), &D.s0))) return rc;
+    if ((rc = upload(h, pad(h->h_sdiff, 1.), &D.sdiff))) return rc;
+    D.use_decay = F.use_decay; D.d_alpha2 = F.d_alpha2; D.d_gamma = F.d_gamma;
+    {
+        std::vector<double> DH((size_t)n * np, 0.);
+        if (F.use_decay)
+            for (int k = 0; k < n; ++k)
+                for (int j = 0; j < n; ++j) DH[(size_t)k * np + j] = h->h_dhess[(size_t)k * n + j];
+        if ((rc = upload(h, pad(h->h_dmu, 0.), &D.d_mu))) return rc;
+        if ((rc = upload(h, DH, &D.d_H))) return rc;
+    }
+    D.use_transform = F.use_transform;
+    {
+        std::vector<double> lo(np, 0.), w(np, 1.);
+        std::vector<int> hb(np, 0);
+        if (F.use_transform)
+            for (int j = 0; j < n; ++j) {
+                lo[j] = h->h_ranges[2 * j];
+                w[j] = h->h_ranges[2 * j + 1] - h->h_ranges[2 * j];
+                hb[j] = (h->h_hb[2 * j] ? 1 : 0) | (h->h_hb[2 * j + 1] ? 2 : 0);
+            }
+        if ((rc = upload(h, lo, &D.r_lo))) return rc;
+        if ((rc = upload(h, w, &D.r_w))) return rc;
+        if ((rc = upload(h, hb, &D.hb))) return rc;
+    }
+    BFB_CUDA(cudaStreamSynchronize(h->stream));
+    return BFB_OK;
+}
+
+extern "C" int bfb_set_model(bfb_handle h, const bfb_model_desc *d)
+{
+    BFB_REQUIRE(h && d, BFB_ERR_ARG, "bfb_set_model: null argument");
+    BFB_REQUIRE(d->n > 0 && d->m > 0 && d->n_config > 0, BFB_ERR_ARG, "bfb_set_model: n, m, n_config must be positive");
+    BFB_REQUIRE(d->n <= 128, BFB_ERR_ARG, "bfb_set_model: input_size %d > 128 is not supported", d->n);
+    h->n = d->n; h->m = d->m; h->np = 32 * ((d->n + 31) / 32);
+    h->configs.clear();
+    int64_t ioff = 0, ooff = 0, coff = 0;
+    for (int c = 0; c < d->n_config; ++c) {
+        HostConfig hc;
+        hc.order = d->cfg_order[c]; hc.n_in = d->cfg_n_in[c]; hc.n_out = d->cfg_n_out[c];
+        BFB_REQUIRE(hc.order >= BFB_LINEAR && hc.order <= BFB_CUBIC_3, BFB_ERR_ARG, "config %d: bad order %d", c, hc.order);
+        BFB_REQUIRE(hc.n_in > 0 && hc.n_in <= d->n && hc.n_out > 0 && hc.n_out <= d->m, BFB_ERR_ARG,
+                    "config %d: bad mask sizes", c);
+        hc.in_mask.assign(d->cfg_in_mask + ioff, d->cfg_in_mask + ioff + hc.n_in);
+        hc.out_mask.assign(d->cfg_out_mask + ooff, d->cfg_out_mask + ooff + hc.n_out);
+        for (int k = 0; k < hc.n_in; ++k)
+            BFB_REQUIRE(hc.in_mask[k] >= 0 && hc.in_mask[k] < d->n && (k == 0 || hc.in_mask[k] > hc.in_mask[k - 1]),
+                        BFB_ERR_ARG, "config %d: input_mask must be sorted unique indices in [0,n)", c);
+        for (int k = 0; k < hc.n_out; ++k)
+            BFB_REQUIRE(hc.out_mask[k] >= 0 && hc.out_mask[k] < d->m && (k == 0 || hc.out_mask[k] > hc.out_mask[k - 1]),
+                        BFB_ERR_ARG, "config %d: output_mask must be sorted unique indices in [0,m)", c);
+        hc.n_packed = packed_size(hc.order, hc.n_in);
+        hc.coef_off = coff;
+        ioff += hc.n_in; ooff += hc.n_out; coff += hc.n_packed * hc.n_out;
+        h->configs.push_back(hc);
+    }
+    h->packed.assign((size_t)coff, 0.);
+    if (d->cfg_coef) memcpy(h->packed.data(), d->cfg_coef, sizeof(double) * (size_t)coff);
+    h->desc_flags = *d;
+    const int n = d->n, m = d->m;
+    auto cp = [](std::vector<double> &dst, const double *src, size_t cnt) {
+        dst.clear();
+        if (src) dst.assign(src, src + cnt);
+    };
+    if (d->use_bound) {
+        BFB_REQUIRE(d->mu && d->hess && d->f_mu, BFB_ERR_ARG, "use_bound set but mu/hess/f_mu missing");
+        cp(h->h_mu, d->mu, n); cp(h->h_hess, d->hess, (size_t)n * n); cp(h->h_fmu, d->f_mu, m);
+    } else { h->h_mu.clear(); h->h_hess.clear(); h->h_fmu.clear(); }
+    if (d->use_scales) {
+        BFB_REQUIRE(d->s0 && d->sdiff, BFB_ERR_ARG, "use_scales set but s0/sdiff missing");
+        cp(h->h_s0, d->s0, n); cp(h->h_sdiff, d->sdiff, n);
+    } else { h->h_s0.clear(); h->h_sdiff.clear(); }
+    if (d->use_decay) {
+        BFB_REQUIRE(d->d_mu && d->d_hess, BFB_ERR_ARG, "use_decay set but d_mu/d_hess missing");
+        cp(h->h_dmu, d->d_mu, n); cp(h->h_dhess, d->d_hess, (size_t)n * n);
+    } else { h->h_dmu.clear(); h->h_dhess.clear(); }
+    if (d->use_transform) {
+        BFB_REQUIRE(d->ranges && d->hard_bounds, BFB_ERR_ARG, "use_transform set but ranges/hard_bounds missing");
+        cp(h->h_ranges, d->ranges, (size_t)2 * n);
+        h->h_hb.assign(d->hard_bounds, d->hard_bounds + 2 * n);
+    } else { h->h_ranges.clear(); h->h_hb.clear(); }
+    int rc = bfb_upload_model(h);
+    if (rc) return rc;
+    h->has_model = true;
+    return BFB_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// batched evaluation kernels: one warp per (point, output)
+// ----------------------------------------------------------------------------------------------
+template <int NPL>
+__global__ void __launch_bounds__(128) poly_eval_kernel(DevModel M, const double *__restrict__ X, int64_t C,
+                                                        double *__restrict__ F, double *__restrict__ J)
+{
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    double *xsm = smem + (size_t)wib * 2 * M.np, *dsm = xsm + M.np;
+    const int64_t total = C * M.m;
+    for (int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib; w < total; w += (int64_t)gridDim.x * (blockDim.x >> 5)) {
+        const int64_t c = w / M.m;
+        const int o = (int)(w % M.m);
+        double x[NPL], Jr[NPL], f;
+#pragma unroll
+        for (int r = 0; r < NPL; ++r) {
+            int j = lane + 32 * r;
+            x[r] = (j < M.n) ? X[c * M.n + j] : 0.;
+        }
+        module_fg<NPL>(M, o, x, lane, xsm, dsm, f, Jr);
+        if (lane == 0) F[c * M.m + o] = f;
+        if (J) {
+#pragma unroll
+            for (int r = 0; r < NPL; ++r) {
+                int j = lane + 32 * r;
+                if (j < M.n) J[(c * M.m + o) * M.n + j] = Jr[r];
+            }
+        }
+        __syncwarp();
+    }
+}
+
+template <int NPL>
+__global__ void __launch_bounds__(128) density_eval_kernel(DevModel M, const double *__restrict__ X, int64_t C,
+                                                           double *__restrict__ LP, double *__restrict__ G)
+{
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    double *xsm = smem + (size_t)wib * 2 * M.np, *dsm = xsm + M.np;
+    for (int64_t c = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib; c < C; c += (int64_t)gridDim.x * (blockDim.x >> 5)) {
+        double x[NPL], g[NPL], lp;
+#pragma unroll
+        for (int r = 0; r < NPL; ++r) {
+            int j = lane + 32 * r;
+            x[r] = (j < M.n) ? X[c * M.n + j] : 0.;
+        }
+        density_eval<NPL>(M, x, lane, xsm, dsm, lp, g);
+        if (lane == 0) LP[c] = lp;
+#pragma unroll
+        for (int r = 0; r < NPL; ++r) {
+            int j = lane + 32 * r;
+            if (j < M.n) G[c * M.n + j] = g[r];
+        }
+        __syncwarp();
+    }
+}
+
+struct DevBuf {
+    // stages a caller buffer on the device when it lives on the host
+    void *dev = nullptr; const void *host_src = nullptr; void *host_dst = nullptr; size_t bytes = 0; bool owned = false;
+};
+
+static int stage_in(bfb_context *h, const void *p, size_t bytes, int loc, DevBuf &b)
+{
+    b.bytes = bytes;
+    if (loc == BFB_DEVICE) { b.dev = (void *)p; return BFB_OK; }
+    BFB_CUDA(cudaMalloc(&b.dev, bytes ? bytes : 8));
+    b.owned = true;
+    BFB_CUDA(cudaMemcpyAsync(b.dev, p, bytes, cudaMemcpyHostToDevice, h->stream));
+    return BFB_OK;
+}
+static int stage_out(bfb_context *h, void *p, size_t bytes, int loc, DevBuf &b)
+{
+    b.bytes = bytes;
+    if (!p) { b.dev = nullptr; return BFB_OK; }
+    if (loc == BFB_DEVICE) { b.dev = p; return BFB_OK; }
+    BFB_CUDA(cudaMalloc(&b.dev, bytes ? bytes : 8));
+    b.owned = true; b.host_dst = p;
+    return BFB_OK;
+}
+static int finish(bfb_context *h, DevBuf &b)
+{
+    if (b.owned && b.host_dst) BFB_CUDA(cudaMemcpyAsync(b.host_dst, b.dev, b.bytes, cudaMemcpyDeviceToHost, h->stream));
+    return BFB_OK;
+}
+static void release(DevBuf &b) { if (b.owned && b.dev) cudaFree(b.dev); b.dev = nullptr; }
+
+extern "C" int bfb_poly_eval_batch(bfb_handle h, const double *X, int64_t C, double *F, double *J, int loc)
+{
+    BFB_REQUIRE(h && h->has_model, BFB_ERR_STATE, "bfb_poly_eval_batch: no model set");
+    BFB_REQUIRE(X && F && C >= 0, BFB_ERR_ARG, "bfb_poly_eval_batch: bad arguments");
+    if (C == 0) return BFB_OK;
+    BFB_CUDA(cudaSetDevice(h->device));
+    const int n = h->n, m = h->m, npl = h->np / 32;
+    DevBuf bx, bf, bj;
+    int rc;
+    if ((rc = stage_in(h, X, sizeof(double) * C * n, loc, bx))) return rc;
+    if ((rc = stage_out(h, F, sizeof(double) * C * m, loc, bf))) return rc;
+    if ((rc = stage_out(h, J, sizeof(double) * C * m * n, loc, bj))) return rc;
+    const int wpb = 4;
+    int64_t blocks64 = (C * m + wpb - 1) / wpb;
+    int blocks = (int)(blocks64 < (int64_t)h->sm_count * 16 ? blocks64 : (int64_t)h->sm_count * 16);
+    size_t smem = sizeof(double) * wpb * 2 * h->np;
+    BFB_CUDA(cudaEventRecord(h->ev0, h->stream));
+    switch (npl) {
+    case 1: poly_eval_kernel<1><<<blocks, 32 * wpb, smem, h->stream>>>(h->dm, (const double *)bx.dev, C, (double *)bf.dev, (double *)bj.dev); break;
+    case 2: poly_eval_kernel<2><<<blocks, 32 * wpb, smem, h->stream>>>(h->dm, (const double *)bx.dev, C, (double *)bf.dev, (double *)bj.dev); break;
+    case 3: poly_eval_kernel<3><<<blocks, 32 * wpb, smem, h->stream>>>(h->dm, (const double *)bx.dev, C, (double *)bf.dev, (double *)bj.dev); break;
+    default: poly_eval_kernel<4><<<blocks, 32 * wpb, smem, h->stream>>>(h->dm, (const double *)bx.dev, C, (double *)bf.dev, (double *)bj.dev); break;
+    }
+    h->launches++;
+    BFB_CUDA(cudaGetLastError());
+    BFB_CUDA(cudaEventRecord(h->ev1, h->stream));
+    if ((rc = finish(h, bf))) return rc;
+    if ((rc = finish(h, bj))) return rc;
+    BFB_CUDA(cudaStreamSynchronize(h->stream));
+    BFB_CUDA(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+    release(bx); release(bf); release(bj);
+    return BFB_OK;
+}
+
+extern "C" int bfb_logp_and_grad_batch(bfb_handle h, const double *X, int64_t C, double *logp, double *grad, int loc)
+{
+    BFB_REQUIRE(h && h->has_model, BFB_ERR_STATE, "bfb_logp_and_grad_batch: no model set");
+    BFB_REQUIRE(X && logp && grad && C >= 0, BFB_ERR_ARG, "bfb_logp_and_grad_batch: bad arguments");
+    if (C == 0) return BFB_OK;
+    BFB_CUDA(cudaSetDevice(h->device));
+    const int n = h->n, npl = h->np / 32;
+    DevBuf bx, bl, bg;
+    int rc;
+    if ((rc = stage_in(h, X, sizeof(double) * C * n, loc, bx))) return rc;
+    if ((rc = stage_out(h, logp, sizeof(double) * C, loc, bl))) return rc;
+    if ((rc = stage_out(h, grad, sizeof(double) * C * n, loc, bg))) return rc;
+    const int wpb = 4;
+    int64_t blocks64 = (C + wpb - 1) / wpb;
+    int blocks = (int)(blocks64 < (int64_t)h->sm_count * 16 ? blocks64 : (int64_t)h->sm_count * 16);
+    size_t smem = sizeof(double) * wpb * 2 * h->np;
+    BFB_CUDA(cudaEventRecord(h->ev0, h->stream));
+    switch (npl) {
+    case 1: density_eval_kernel<1><<<blocks, 32 * wpb, smem, h->stream>>>(h->dm, (const double *)bx.dev, C, (double *)bl.dev, (double *)bg.dev); break;
+    case 2: density_eval_kernel<2><<<blocks, 32 * wpb, smem, h->stream>>>(h->dm, (const double *)bx.dev, C, (double *)bl.dev, (double *)bg.dev); break;
+    case 3: density_eval_kernel<3><<<blocks, 32 * wpb, smem, h->stream>>>(h->dm, (const double *)bx.dev, C, (double *)bl.dev, (double *)bg.dev); break;
+    default: density_eval_kernel<4><<<blocks, 32 * wpb, smem, h->stream>>>(h->dm, (const double *)bx.dev, C, (double *)bl.dev, (double *)bg.dev); break;
+    }
+    h->launches++;
+    BFB_CUDA(cudaGetLastError());
+    BFB_CUDA(cudaEventRecord(h->ev1, h->stream));
+    if ((rc = finish(h, bl))) return rc;
+    if ((rc = finish(h, bg))) return rc;
+    BFB_CUDA(cudaStreamSynchronize(h->stream));
+    BFB_CUDA(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+    release(bx); release(bl); release(bg);
+    return BFB_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// RNG exposure
+// ----------------------------------------------------------------------------------------------
+__global__ void rng_fill_kernel(uint64_t seed, uint64_t chain, uint64_t t0, int64_t count, double *u, double *z)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    double uu = bfb_draw_uniform(seed, chain, t0 + (uint64_t)i);
+    u[i] = uu;
+    z[i] = bfb_norminv(uu);
+}
+
+extern "C" int bfb_rng_fill(bfb_handle h, uint64_t seed, uint64_t chain, uint64_t t0, int64_t count, double *u, double *z)
+{
+    BFB_REQUIRE(h && u && z && count >= 0, BFB_ERR_ARG, "bfb_rng_fill: bad arguments");
+    if (count == 0) return BFB_OK;
+    BFB_CUDA(cudaSetDevice(h->device));
+    double *du, *dz;
+    BFB_CUDA(cudaMalloc(&du, sizeof(double) * count));
+    BFB_CUDA(cudaMalloc(&dz, sizeof(double) * count));
+    rng_fill_kernel<<<(unsigned)((count + 255) / 256), 256, 0, h->stream>>>(seed, chain, t0, count, du, dz);
+    h->launches++;
+    BFB_CUDA(cudaGetLastError());
+    BFB_CUDA(cudaMemcpyAsync(u, du, sizeof(double) * count, cudaMemcpyDeviceToHost, h->stream));
+    BFB_CUDA(cudaMemcpyAsync(z, dz, sizeof(double) * count, cudaMemcpyDeviceToHost, h->stream));
+    BFB_CUDA(cudaStreamSynchronize(h->stream));
+    cudaFree(du); cudaFree(dz);
+    return BFB_OK;
+}

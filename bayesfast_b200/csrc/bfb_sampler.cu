@@ -1,0 +1,563 @@
+// bfb_sampler.cu -- lock-step NUTS / HMC: one warp per chain, the whole transition (tree building,
+// U-turn tests, multinomial selection, dual averaging, windowed Welford metric) on the device.
+//
+// Mapping.  Lane j of a warp owns dimension j (+32r) of every state vector of its chain; the binary tree
+// of nuts.py:134-178 is built iteratively: leaf i of a depth-D subtree is followed by ctz(~i) merges
+// against a per-level stack of completed left siblings kept in shared memory (lane-private columns, so
+// no synchronisation is needed for it).  Chains in different warps never wait for each other, so chains
+// with different tree depths do not mask one another; within a warp every decision is warp-uniform
+// (butterfly reductions give bitwise identical sums on all lanes).
+//
+// Reference restated here: samplers/hmc_utils/base_hmc.py:62-85 (astep), samplers/nuts.py:27-217,
+// samplers/hmc.py:16-49, hmc_utils/integration.py:28-95, hmc_utils/metrics.py:73-91,186-211,333-371,
+// hmc_utils/step_size.py:10-51.  Draw order: SURVEY.md 8(a) row N-RNG; stream: include/bfb_rng.h.
+#include "bfb_common.cuh"
+#include "bfb_eval.cuh"
+#include <cstring>
+
+struct RunOutDev {
+    bfb_run_out o;
+    int32_t n_iter;
+};
+
+__host__ __device__ inline size_t warp_smem_doubles(int np, int L)
+{
+    size_t s = (size_t)(12 + 5 * L) * np + 3 * (size_t)L;
+    return (s + 1) & ~(size_t)1;
+}
+
+template <int NPL>
+__device__ __forceinline__ void leapfrog(const DevModel &M, double eps, const double (&var)[NPL], double (&q)[NPL],
+                                         double (&p)[NPL], double (&g)[NPL], int lane, double *xsm, double *dsm,
+                                         double &logp, double &energy)
+{
+    // integration.py:68-95 (kick - drift - kick), metrics.py:88-91 (velocity_energy)
+    const double dt = 0.5 * eps;
+#pragma unroll
+    for (int r = 0; r < NPL; ++r) {
+        p[r] = fma(dt, g[r], p[r]);
+        q[r] = fma(eps, var[r] * p[r], q[r]);
+    }
+    density_eval<NPL>(M, q, lane, xsm, dsm, logp, g);
+    double part = 0.;
+#pragma unroll
+    for (int r = 0; r < NPL; ++r) {
+        p[r] = fma(dt, g[r], p[r]);
+        part = fma(p[r], var[r] * p[r], part);
+    }
+    energy = 0.5 * warp_sum(part) - logp;
+}
+
+template <int NPL>
+__device__ __forceinline__ double vdot(const double (&a)[NPL], const double (&var)[NPL], const double (&b)[NPL])
+{
+    double part = 0.;
+#pragma unroll
+    for (int r = 0; r < NPL; ++r) part = fma(a[r], var[r] * b[r], part);
+    return warp_sum(part);
+}
+
+#define VLD(dst, off)                                                     \
+    _Pragma("unroll") for (int r_ = 0; r_ < NPL; ++r_) dst[r_] = wsm[(off) + lane + 32 * r_]
+#define VST(off, src)                                                     \
+    _Pragma("unroll") for (int r_ = 0; r_ < NPL; ++r_) wsm[(off) + lane + 32 * r_] = src[r_]
+
+template <int NPL, int SAMPLER>
+__global__ void __launch_bounds__(128) sampler_kernel(DevModel M, bfb_sampler_cfg cfg, ChainState st, RunOutDev out, int L)
+{
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t c = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
+    if (c >= st.C) return;
+    const int n = M.n, np = M.np;
+    double *wsm = smem + (size_t)wib * warp_smem_doubles(np, L);
+    double *xsm = wsm, *dsm = wsm + np;
+    const int oTL = 2 * np, oTR = 5 * np, oPS = 8 * np, oPQ = 9 * np, oPG = 10 * np, oPB = 11 * np, oST = 12 * np;
+    double *ssc = wsm + (size_t)(12 + 5 * L) * np;   // [3][L] scalars of the stack: log_size, energy, logp
+    if (st.status[c] != 0) return;
+
+    const uint64_t seed = cfg.seed, chain = (uint64_t)(cfg.chain0 + c);
+    int64_t t = st.t_draw[c];
+    int64_t it0 = st.iter[c];
+    const size_t vb = (size_t)c * np;
+
+    double q[NPL], g[NPL], p[NPL], var[NPL], inv_std[NPL];
+    double fgm[NPL], fgr[NPL], bgm[NPL], bgr[NPL];
+#pragma unroll
+    for (int r = 0; r < NPL; ++r) {
+        const int j = lane + 32 * r;
+        q[r] = st.q[vb + j]; g[r] = st.g[vb + j]; var[r] = st.var[vb + j];
+        inv_std[r] = 1. / sqrt(var[r]);
+        fgm[r] = st.fg_mean[vb + j]; fgr[r] = st.fg_raw[vb + j];
+        bgm[r] = st.bg_mean[vb + j]; bgr[r] = st.bg_raw[vb + j];
+        p[r] = 0.;
+    }
+    double logp_q = st.logp[c];
+    double fg_n = st.fg_n[c], bg_n = st.bg_n[c];
+    double log_step = st.log_step[c], log_bar = st.log_bar[c], hbar = st.hbar[c];
+    const double mu_da = st.mu_da[c];
+    int64_t count = st.count[c], n_samples = st.n_samples[c], previous_update = st.previous_update[c];
+    int adapt_window = st.adapt_window[c];
+    int status = 0;
+    unsigned long long tree_total = 0;
+
+    for (int it = 0; it < out.n_iter; ++it) {
+        const bool warmup = (it0 + it) < cfg.n_warmup;
+        // momentum: metrics.py:83-86
+        double p0[NPL];
+#pragma unroll
+        for (int r = 0; r < NPL; ++r) {
+            const int j = lane + 32 * r;
+            p0[r] = (j < n) ? inv_std[r] * bfb_draw_normal(seed, chain, (uint64_t)(t + j)) : 0.;
+        }
+        t += n;
+        const double E0 = 0.5 * vdot<NPL>(p0, var, p0) - logp_q;    // integration.py:28-34
+        if (!isfinite(E0)) { status = 2; break; }                     // base_hmc.py:72-76
+        const double eps = warmup ? exp(log_step) : exp(log_bar);     // step_size.py:25-29
+
+        double accept_stat, s_logp, s_energy, s_dE, s_maxdE = 0.;
+        int s_depth, s_size, diverging = 0;
+
+        if (SAMPLER == BFB_NUTS) {
+            // Tree.__init__, nuts.py:27-43
+            VST(oTL, q); VST(oTL + np, p0); VST(oTL + 2 * np, g);
+            VST(oTR, q); VST(oTR + np, p0); VST(oTR + 2 * np, g);
+            VST(oPS, p0); VST(oPQ, q); VST(oPG, g);
+            double prop_E = E0, prop_lp = logp_q, tree_ls = 0., acc_sum = 0., maxdE = 0.;
+            int depth = 0, n_prop = 0;
+            bool turn = false, nan_flag = false;
+            for (int d = 0; d < cfg.max_treedepth; ++d) {
+                // nuts.py:210 direction = logbern(log 0.5) * 2 - 1
+                const double ud = bfb_draw_uniform(seed, chain, (uint64_t)t); t++;
+                const int dir = (log(ud) < -0.6931471805599453) ? 1 : -1;
+                const int oEnd = dir > 0 ? oTR : oTL;
+                VLD(q, oEnd); VLD(p, oEnd + np); VLD(g, oEnd + 2 * np);
+                VST(oPB, p);
+                const double step = dir > 0 ? eps : -eps;
+                const int nleaf = 1 << depth;
+                double Rpl[NPL], Rps[NPL], Rqp[NPL], Rgp[NPL];
+                double Rls = 0., REp = 0., Rlpp = 0.;
+                // ---- _build_subtree(depth), nuts.py:134-178, iteratively ----
+                for (int i = 0; i < nleaf; ++i) {
+                    double lp, E;
+                    leapfrog<NPL>(M, step, var, q, p, g, lane, xsm, dsm, lp, E);
+                    // _single_step, nuts.py:105-132
+                    double dE = E - E0;
+                    if (isnan(dE)) dE = INFINITY;
+                    if (fabs(dE) > fabs(maxdE)) maxdE = dE;
+                    n_prop += 1;
+                    if (!(fabs(dE) < cfg.max_change)) { diverging = 1; break; }
+                    { const double e = exp(-dE); acc_sum += e < 1. ? e : 1.; }
+#pragma unroll
+                    for (int r = 0; r < NPL; ++r) { Rpl[r] = p[r]; Rps[r] = p[r]; Rqp[r] = q[r]; Rgp[r] = g[r]; }
+                    Rls = -dE; REp = E; Rlpp = lp;
+                    int lvl = 0;
+                    while ((i >> lvl) & 1) {
+                        const int oS = oST + lvl * 5 * np;
+                        double T1pl[NPL], T1pr[NPL], T1ps[NPL], ps[NPL];
+                        VLD(T1pl, oS); VLD(T1pr, oS + np); VLD(T1ps, oS + 2 * np);
+#pragma unroll
+                        for (int r = 0; r < NPL; ++r) ps[r] = T1ps[r] + Rps[r];
+                        bool turning = (vdot<NPL>(ps, var, T1pl) <= 0.) | (vdot<NPL>(ps, var, p) <= 0.);
+                        if (lvl >= 1) {
+                            double ps1[NPL], ps2[NPL];
+#pragma unroll
+                            for (int r = 0; r < NPL; ++r) { ps1[r] = T1ps[r] + Rpl[r]; ps2[r] = T1pr[r] + Rps[r]; }
+                            turning |= (vdot<NPL>(ps1, var, T1pl) <= 0.) | (vdot<NPL>(ps1, var, Rpl) <= 0.);
+                            turning |= (vdot<NPL>(ps2, var, T1pr) <= 0.) | (vdot<NPL>(ps2, var, p) <= 0.);
+                        }
+                        const double T1ls = ssc[lvl];
+                        const double ls = np_logaddexp(T1ls, Rls);
+                        const double um = bfb_draw_uniform(seed, chain, (uint64_t)t); t++;
+                        const double lb = Rls - ls;
+                        if (isnan(lb)) nan_flag = true;
+                        if (!(log(um) < lb)) {   // keep tree1's proposal
+                            VLD(Rqp, oS + 3 * np); VLD(Rgp, oS + 4 * np);
+                            REp = ssc[L + lvl]; Rlpp = ssc[2 * L + lvl];
+                        }
+#pragma unroll
+                        for (int r = 0; r < NPL; ++r) { Rpl[r] = T1pl[r]; Rps[r] = ps[r]; }
+                        Rls = ls;
+                        if (turning) { turn = true; break; }
+                        lvl++;
+                    }
+                    if (turn) break;
+                    if (i + 1 < nleaf) {
+                        const int oS = oST + lvl * 5 * np;
+                        VST(oS, Rpl); VST(oS + np, p); VST(oS + 2 * np, Rps); VST(oS + 3 * np, Rqp); VST(oS + 4 * np, Rgp);
+                        // every lane writes the same scalars (each lane later reads back its own write: no sync needed)
+                        ssc[lvl] = Rls; ssc[L + lvl] = REp; ssc[2 * L + lvl] = Rlpp;
+                    }
+                }
+                // Tree.extend, nuts.py:45-103
+                VST(oEnd, q); VST(oEnd + np, p); VST(oEnd + 2 * np, g);
+                depth += 1;
+                if (diverging || turn) break;
+                {
+                    const double ue = bfb_draw_uniform(seed, chain, (uint64_t)t); t++;
+                    const double lb = Rls - tree_ls;
+                    if (isnan(lb)) nan_flag = true;
+                    if (log(ue) < lb) { VST(oPQ, Rqp); VST(oPG, Rgp); prop_E = REp; prop_lp = Rlpp; }
+                }
+                tree_ls = np_logaddexp(tree_ls, Rls);
+                double PS[NPL], PB[NPL], TLp[NPL], TRp[NPL], ps1[NPL], ps2[NPL];
+                VLD(PS, oPS); VLD(PB, oPB); VLD(TLp, oTL + np); VLD(TRp, oTR + np);
+#pragma unroll
+                for (int r = 0; r < NPL; ++r) PS[r] += Rps[r];
+                VST(oPS, PS);
+                bool turning = (vdot<NPL>(PS, var, TLp) <= 0.) | (vdot<NPL>(PS, var, TRp) <= 0.);
+                // NB the reference updates self.p_sum in place before forming p_sum1 / p_sum2 (nuts.py:86-98),
+                // so the "old tree" p_sum that enters them is already the total.
+                if (dir > 0) {
+#pragma unroll
+                    for (int r = 0; r < NPL; ++r) { ps1[r] = PS[r] + Rpl[r]; ps2[r] = PB[r] + Rps[r]; }
+                    turning |= (vdot<NPL>(ps1, var, TLp) <= 0.) | (vdot<NPL>(ps1, var, Rpl) <= 0.);
+                    turning |= (vdot<NPL>(ps2, var, PB) <= 0.) | (vdot<NPL>(ps2, var, p) <= 0.);
+                } else {
+#pragma unroll
+                    for (int r = 0; r < NPL; ++r) { ps1[r] = Rps[r] + PB[r]; ps2[r] = Rpl[r] + PS[r]; }
+                    turning |= (vdot<NPL>(ps1, var, p) <= 0.) | (vdot<NPL>(ps1, var, PB) <= 0.);
+                    turning |= (vdot<NPL>(ps2, var, Rpl) <= 0.) | (vdot<NPL>(ps2, var, TRp) <= 0.);
+                }
+                if (turning) { turn = true; break; }
+            }
+            if (nan_flag) { status = 3; break; }
+            accept_stat = acc_sum / (double)n_prop;
+            s_logp = prop_lp; s_energy = prop_E; s_depth = depth; s_size = n_prop;
+            s_dE = prop_E - E0; s_maxdE = maxdE;
+            VLD(q, oPQ); VLD(g, oPG);
+            logp_q = prop_lp;
+            tree_total += (unsigned long long)n_prop;
+        } else {
+            // HMC._hamiltonian_step, hmc.py:16-49
+            double qs[NPL], gs[NPL];
+#pragma unroll
+            for (int r = 0; r < NPL; ++r) { qs[r] = q[r]; gs[r] = g[r]; p[r] = p0[r]; }
+            double lp = logp_q, E = E0;
+            for (int s = 0; s < cfg.n_int_step; ++s) leapfrog<NPL>(M, eps, var, q, p, g, lane, xsm, dsm, lp, E);
+            double dE;
+            if (isfinite(E)) { dE = E0 - E; diverging = fabs(dE) > cfg.max_change; }
+            else { dE = -INFINITY; diverging = 1; }
+            { const double e = exp(dE); accept_stat = e < 1. ? e : 1.; }
+            bool accepted = false;
+            if (!diverging) {
+                const double ua = bfb_draw_uniform(seed, chain, (uint64_t)t); t++;
+                accepted = !(ua >= accept_stat);
+            }
+            s_logp = lp; s_energy = E; s_depth = accepted ? 1 : 0; s_size = cfg.n_int_step; s_dE = dE;
+            if (accepted) logp_q = lp;
+            else {
+#pragma unroll
+                for (int r = 0; r < NPL; ++r) { q[r] = qs[r]; g[r] = gs[r]; }
+            }
+            tree_total += (unsigned long long)cfg.n_int_step;
+        }
+
+        // DualAverageAdaptation.update, step_size.py:31-45
+        if (warmup && cfg.adapt_step_size) {
+            const double cnt = (double)count;
+            const double w = 1. / (cnt + cfg.t0);
+            hbar = ((1. - w) * hbar + w * (cfg.target_accept - accept_stat));
+            log_step = mu_da - hbar * sqrt(cnt) / cfg.gamma;
+            const double mk = pow(cnt, -cfg.k);
+            log_bar = mk * log_step + (1. - mk) * log_bar;
+            count += 1;
+        }
+        // QuadMetricDiagAdapt.update, metrics.py:186-211 with _WeightedVariance.add_sample :351-357
+        if (warmup && cfg.adapt_metric) {
+            const int64_t delta = n_samples - previous_update;
+            fg_n += 1.; bg_n += 1.;
+#pragma unroll
+            for (int r = 0; r < NPL; ++r) {
+                double od = q[r] - fgm[r];
+                fgm[r] += od / fg_n;
+                fgr[r] += 1. * od * (q[r] - fgm[r]);
+                od = q[r] - bgm[r];
+                bgm[r] += od / bg_n;
+                bgr[r] += 1. * od * (q[r] - bgm[r]);
+            }
+            if ((delta + 1) % cfg.update_window == 0) {
+#pragma unroll
+                for (int r = 0; r < NPL; ++r) {
+                    if (lane + 32 * r < n) { var[r] = fgr[r] / fg_n; inv_std[r] = 1. / sqrt(var[r]); }
+                }
+            }
+            if (delta >= adapt_window) {
+#pragma unroll
+                for (int r = 0; r < NPL; ++r) { fgm[r] = bgm[r]; fgr[r] = bgr[r]; bgm[r] = 0.; bgr[r] = 0.; }
+                fg_n = bg_n; bg_n = 10.;     // _WeightedVariance(self._n): default initial_weight 10, zero mean / variance
+                previous_update = n_samples;
+                if (cfg.doubling) adapt_window *= 2;
+            }
+            n_samples += 1;
+        }
+
+        // outputs: base_hmc.py:82-85, stats.py:12-14
+        const size_t o = (size_t)c * out.n_iter + it;
+        if (out.o.samples) {
+#pragma unroll
+            for (int r = 0; r < NPL; ++r) {
+                const int j = lane + 32 * r;
+                if (j < n) out.o.samples[o * n + j] = q[r];
+            }
+        }
+        if (lane == 0) {
+            if (out.o.logp) out.o.logp[o] = s_logp;
+            if (out.o.energy) out.o.energy[o] = s_energy;
+            if (out.o.tree_depth) out.o.tree_depth[o] = s_depth;
+            if (out.o.tree_size) out.o.tree_size[o] = s_size;
+            if (out.o.mean_tree_accept) out.o.mean_tree_accept[o] = accept_stat;
+            if (out.o.step_size) out.o.step_size[o] = exp(log_step);
+            if (out.o.step_size_bar) out.o.step_size_bar[o] = exp(log_bar);
+            if (out.o.energy_change) out.o.energy_change[o] = s_dE;
+            if (out.o.max_energy_change) out.o.max_energy_change[o] = s_maxdE;
+            if (out.o.diverging) out.o.diverging[o] = diverging;
+        }
+        if (status) break;
+    }
+
+    // persist chain state
+#pragma unroll
+    for (int r = 0; r < NPL; ++r) {
+        const int j = lane + 32 * r;
+        st.q[vb + j] = q[r]; st.g[vb + j] = g[r]; st.var[vb + j] = var[r];
+        st.fg_mean[vb + j] = fgm[r]; st.fg_raw[vb + j] = fgr[r];
+        st.bg_mean[vb + j] = bgm[r]; st.bg_raw[vb + j] = bgr[r];
+    }
+    if (lane == 0) {
+        st.logp[c] = logp_q; st.fg_n[c] = fg_n; st.bg_n[c] = bg_n;
+        st.log_step[c] = log_step; st.log_bar[c] = log_bar; st.hbar[c] = hbar;
+        st.count[c] = count; st.n_samples[c] = n_samples; st.previous_update[c] = previous_update;
+        st.adapt_window[c] = adapt_window; st.t_draw[c] = t; st.iter[c] = it0 + out.n_iter;
+        st.status[c] = status;
+        if (tree_total) atomicAdd(st.tree_total, tree_total);
+    }
+}
+
+// logp / grad at x0 and the finite check of base_hmc.py:42-46
+template <int NPL>
+__global__ void __launch_bounds__(128) chain_init_kernel(DevModel M, ChainState st)
+{
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t c = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
+    if (c >= st.C) return;
+    double *xsm = smem + (size_t)wib * 2 * M.np, *dsm = xsm + M.np;
+    double q[NPL], g[NPL], lp;
+#pragma unroll
+    for (int r = 0; r < NPL; ++r) q[r] = st.q[(size_t)c * M.np + lane + 32 * r];
+    density_eval<NPL>(M, q, lane, xsm, dsm, lp, g);
+    bool ok = isfinite(lp);
+#pragma unroll
+    for (int r = 0; r < NPL; ++r) {
+        ok = ok && isfinite(g[r]);
+        st.g[(size_t)c * M.np + lane + 32 * r] = g[r];
+    }
+    ok = __all_sync(BFB_FULL, ok);
+    if (lane == 0) { st.logp[c] = lp; st.status[c] = ok ? 0 : 1; }
+}
+
+// ----------------------------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------------------------
+template <class T>
+static int dalloc(bfb_context *h, T **p, size_t count)
+{
+    void *v = nullptr;
+    BFB_CUDA(cudaMalloc(&v, sizeof(T) * (count ? count : 1)));
+    BFB_CUDA(cudaMemsetAsync(v, 0, sizeof(T) * (count ? count : 1), h->stream));
+    h->chain_allocs.push_back(v);
+    *p = (T *)v;
+    return BFB_OK;
+}
+
+template <class T>
+static int h2d(bfb_context *h, T *dst, const std::vector<T> &src)
+{
+    BFB_CUDA(cudaMemcpyAsync(dst, src.data(), sizeof(T) * src.size(), cudaMemcpyHostToDevice, h->stream));
+    return BFB_OK;
+}
+
+extern "C" int bfb_sampler_init(bfb_handle h, const bfb_sampler_cfg *cfg, int64_t C, const double *x0,
+                                const double *step0, const double *var0, const double *mean0)
+{
+    BFB_REQUIRE(h && h->has_model, BFB_ERR_STATE, "bfb_sampler_init: no model set");
+    BFB_REQUIRE(cfg && x0 && step0 && var0 && mean0 && C > 0, BFB_ERR_ARG, "bfb_sampler_init: bad arguments");
+    BFB_REQUIRE(cfg->max_treedepth > 0 && cfg->max_treedepth <= 20, BFB_ERR_ARG, "max_treedepth must be in [1,20]");
+    BFB_REQUIRE(cfg->update_window > 0 && cfg->adapt_window > 0, BFB_ERR_ARG, "adapt/update window must be positive");
+    BFB_CUDA(cudaSetDevice(h->device));
+    BFB_CUDA(cudaStreamSynchronize(h->stream));
+    bfb_free_list(h->chain_allocs);
+    h->has_chains = false;
+    h->scfg = *cfg;
+    const int n = h->n, np = h->np;
+    ChainState &s = h->cs;
+    memset(&s, 0, sizeof(s));
+    s.C = C; s.n = n; s.np = np;
+    int rc;
+    const size_t V = (size_t)C * np;
+    if ((rc = dalloc(h, &s.q, V)) || (rc = dalloc(h, &s.g, V)) || (rc = dalloc(h, &s.var, V)) ||
+        (rc = dalloc(h, &s.fg_mean, V)) || (rc = dalloc(h, &s.fg_raw, V)) || (rc = dalloc(h, &s.bg_mean, V)) ||
+        (rc = dalloc(h, &s.bg_raw, V)) || (rc = dalloc(h, &s.logp, C)) || (rc = dalloc(h, &s.fg_n, C)) ||
+        (rc = dalloc(h, &s.bg_n, C)) || (rc = dalloc(h, &s.log_step, C)) || (rc = dalloc(h, &s.log_bar, C)) ||
+        (rc = dalloc(h, &s.hbar, C)) || (rc = dalloc(h, &s.mu_da, C)) || (rc = dalloc(h, &s.count, C)) ||
+        (rc = dalloc(h, &s.n_samples, C)) || (rc = dalloc(h, &s.previous_update, C)) ||
+        (rc = dalloc(h, &s.adapt_window, C)) || (rc = dalloc(h, &s.t_draw, C)) || (rc = dalloc(h, &s.iter, C)) ||
+        (rc = dalloc(h, &s.status, C)) || (rc = dalloc(h, &s.tree_total, 1)))
+        return rc;
+    std::vector<double> vq(V, 0.), vvar(V, 1.), vfm(V, 0.), vfr(V, 0.);
+    std::vector<double> fgn(C), bgn(C, 10.), ls(C), mu(C);
+    std::vector<int64_t> cnt(C, 1);
+    std::vector<int32_t> aw(C, cfg->adapt_window);
+    for (int64_t c = 0; c < C; ++c) {
+        for (int j = 0; j < n; ++j) {
+            vq[c * np + j] = x0[c * n + j];
+            vvar[c * np + j] = var0[c * n + j];
+            vfm[c * np + j] = mean0[c * n + j];
+            vfr[c * np + j] = var0[c * n + j] * cfg->initial_weight;     // metrics.py:348
+            BFB_REQUIRE(var0[c * n + j] > 0., BFB_ERR_ARG, "the input diagonal covariance is not positive definite.");
+        }
+        fgn[c] = cfg->initial_weight;
+        BFB_REQUIRE(step0[c] > 0., BFB_ERR_ARG, "initial step size must be positive");
+        ls[c] = log(step0[c]);                 // step_size.py:13
+        mu[c] = log(10. * step0[c]);           // step_size.py:20
+    }
+    if ((rc = h2d(h, s.q, vq)) || (rc = h2d(h, s.var, vvar)) || (rc = h2d(h, s.fg_mean, vfm)) ||
+        (rc = h2d(h, s.fg_raw, vfr)) || (rc = h2d(h, s.fg_n, fgn)) || (rc = h2d(h, s.bg_n, bgn)) ||
+        (rc = h2d(h, s.log_step, ls)) || (rc = h2d(h, s.log_bar, ls)) || (rc = h2d(h, s.mu_da, mu)) ||
+        (rc = h2d(h, s.count, cnt)) || (rc = h2d(h, s.adapt_window, aw)))
+        return rc;
+    const int wpb = 4;
+    const int blocks = (int)((C + wpb - 1) / wpb);
+    const size_t smem = sizeof(double) * wpb * 2 * np;
+    switch (np / 32) {
+    case 1: chain_init_kernel<1><<<blocks, 32 * wpb, smem, h->stream>>>(h->dm, s); break;
+    case 2: chain_init_kernel<2><<<blocks, 32 * wpb, smem, h->stream>>>(h->dm, s); break;
+    case 3: chain_init_kernel<3><<<blocks, 32 * wpb, smem, h->stream>>>(h->dm, s); break;
+    default: chain_init_kernel<4><<<blocks, 32 * wpb, smem, h->stream>>>(h->dm, s); break;
+    }
+    h->launches++;
+    BFB_CUDA(cudaGetLastError());
+    BFB_CUDA(cudaStreamSynchronize(h->stream));
+    h->has_chains = true;
+    return BFB_OK;
+}
+
+template <int NPL, int SAMPLER>
+static int launch_sampler(bfb_context *h, const RunOutDev &out, int wpb)
+{
+    const int L = h->scfg.max_treedepth;
+    const size_t smem = sizeof(double) * wpb * warp_smem_doubles(h->np, L);
+    BFB_REQUIRE(smem <= 227 * 1024, BFB_ERR_ARG, "sampler needs %zu bytes of shared memory per block (> 227 KB)", smem);
+    BFB_CUDA(cudaFuncSetAttribute(sampler_kernel<NPL, SAMPLER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int blocks = (int)((h->cs.C + wpb - 1) / wpb);
+    sampler_kernel<NPL, SAMPLER><<<blocks, 32 * wpb, smem, h->stream>>>(h->dm, h->scfg, h->cs, out, L);
+    h->launches++;
+    BFB_CUDA(cudaGetLastError());
+    return BFB_OK;
+}
+
+extern "C" int bfb_sampler_run(bfb_handle h, int sampler, int32_t n_iter, const bfb_run_out *out, int loc,
+                               int64_t *total_tree_size)
+{
+    BFB_REQUIRE(h && h->has_model && h->has_chains, BFB_ERR_STATE, "bfb_sampler_run: call bfb_sampler_init first");
+    BFB_REQUIRE(sampler == BFB_NUTS || sampler == BFB_HMC, BFB_ERR_ARG, "unknown sampler %d", sampler);
+    BFB_REQUIRE(n_iter > 0 && out, BFB_ERR_ARG, "bfb_sampler_run: bad arguments");
+    BFB_REQUIRE(sampler != BFB_HMC || h->scfg.n_int_step > 0, BFB_ERR_ARG, "n_int_step must be positive");
+    BFB_CUDA(cudaSetDevice(h->device));
+    const int64_t C = h->cs.C;
+    const int n = h->n;
+    RunOutDev od;
+    od.n_iter = n_iter;
+    memset(&od.o, 0, sizeof(od.o));
+    std::vector<std::pair<void *, std::pair<void *, size_t>>> copies;   // dev -> (host, bytes)
+    auto prep = [&](void *user, size_t bytes, void **slot) -> int {
+        if (!user) { *slot = nullptr; return BFB_OK; }
+        if (loc == BFB_DEVICE) { *slot = user; return BFB_OK; }
+        void *d = nullptr;
+        BFB_CUDA(cudaMalloc(&d, bytes));
+        copies.push_back({d, {user, bytes}});
+        *slot = d;
+        return BFB_OK;
+    };
+    int rc;
+    const size_t S = (size_t)C * n_iter;
+    if ((rc = prep(out->samples, sizeof(double) * S * n, (void **)&od.o.samples)) ||
+        (rc = prep(out->logp, sizeof(double) * S, (void **)&od.o.logp)) ||
+        (rc = prep(out->energy, sizeof(double) * S, (void **)&od.o.energy)) ||
+        (rc = prep(out->mean_tree_accept, sizeof(double) * S, (void **)&od.o.mean_tree_accept)) ||
+        (rc = prep(out->step_size, sizeof(double) * S, (void **)&od.o.step_size)) ||
+        (rc = prep(out->step_size_bar, sizeof(double) * S, (void **)&od.o.step_size_bar)) ||
+        (rc = prep(out->energy_change, sizeof(double) * S, (void **)&od.o.energy_change)) ||
+        (rc = prep(out->max_energy_change, sizeof(double) * S, (void **)&od.o.max_energy_change)) ||
+        (rc = prep(out->tree_depth, sizeof(int32_t) * S, (void **)&od.o.tree_depth)) ||
+        (rc = prep(out->tree_size, sizeof(int32_t) * S, (void **)&od.o.tree_size)) ||
+        (rc = prep(out->diverging, sizeof(int32_t) * S, (void **)&od.o.diverging)))
+        return rc;
+    BFB_CUDA(cudaMemsetAsync(h->cs.tree_total, 0, sizeof(unsigned long long), h->stream));
+    BFB_CUDA(cudaEventRecord(h->ev0, h->stream));
+    const int wpb = 4;
+    const int npl = h->np / 32;
+    if (sampler == BFB_NUTS) {
+        switch (npl) {
+        case 1: rc = launch_sampler<1, BFB_NUTS>(h, od, wpb); break;
+        case 2: rc = launch_sampler<2, BFB_NUTS>(h, od, wpb); break;
+        case 3: rc = launch_sampler<3, BFB_NUTS>(h, od, 2); break;
+        default: rc = launch_sampler<4, BFB_NUTS>(h, od, 2); break;
+        }
+    } else {
+        switch (npl) {
+        case 1: rc = launch_sampler<1, BFB_HMC>(h, od, wpb); break;
+        case 2: rc = launch_sampler<2, BFB_HMC>(h, od, wpb); break;
+        case 3: rc = launch_sampler<3, BFB_HMC>(h, od, 2); break;
+        default: rc = launch_sampler<4, BFB_HMC>(h, od, 2); break;
+        }
+    }
+    if (rc) return rc;
+    BFB_CUDA(cudaEventRecord(h->ev1, h->stream));
+    for (auto &cp : copies)
+        BFB_CUDA(cudaMemcpyAsync(cp.second.first, cp.first, cp.second.second, cudaMemcpyDeviceToHost, h->stream));
+    unsigned long long tt = 0;
+    BFB_CUDA(cudaMemcpyAsync(&tt, h->cs.tree_total, sizeof(tt), cudaMemcpyDeviceToHost, h->stream));
+    BFB_CUDA(cudaStreamSynchronize(h->stream));
+    BFB_CUDA(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+    for (auto &cp : copies) cudaFree(cp.first);
+    if (total_tree_size) *total_tree_size = (int64_t)tt;
+    return BFB_OK;
+}
+
+extern "C" int bfb_sampler_get_state(bfb_handle h, double *final_step, double *final_var, int64_t *n_draws,
+                                     int32_t *status, double *q)
+{
+    BFB_REQUIRE(h && h->has_chains, BFB_ERR_STATE, "bfb_sampler_get_state: no chains");
+    BFB_CUDA(cudaSetDevice(h->device));
+    BFB_CUDA(cudaStreamSynchronize(h->stream));
+    const ChainState &s = h->cs;
+    const int64_t C = s.C;
+    const int n = s.n, np = s.np;
+    if (final_step) {
+        std::vector<double> a(C), b(C), c(C);
+        std::vector<int64_t> k(C);
+        BFB_CUDA(cudaMemcpy(a.data(), s.log_step, sizeof(double) * C, cudaMemcpyDeviceToHost));
+        BFB_CUDA(cudaMemcpy(b.data(), s.log_bar, sizeof(double) * C, cudaMemcpyDeviceToHost));
+        BFB_CUDA(cudaMemcpy(c.data(), s.hbar, sizeof(double) * C, cudaMemcpyDeviceToHost));
+        BFB_CUDA(cudaMemcpy(k.data(), s.count, sizeof(int64_t) * C, cudaMemcpyDeviceToHost));
+        for (int64_t i = 0; i < C; ++i) {
+            final_step[4 * i] = a[i]; final_step[4 * i + 1] = b[i]; final_step[4 * i + 2] = c[i];
+            final_step[4 * i + 3] = (double)k[i];
+        }
+    }
+    auto getvec = [&](const double *dev, double *host) -> int {
+        std::vector<double> tmp((size_t)C * np);
+        BFB_CUDA(cudaMemcpy(tmp.data(), dev, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost));
+        for (int64_t i = 0; i < C; ++i)
+            for (int j = 0; j < n; ++j) host[i * n + j] = tmp[i * np + j];
+        return BFB_OK;
+    };
+    int rc;
+    if (final_var && (rc = getvec(s.var, final_var))) return rc;
+    if (q && (rc = getvec(s.q, q))) return rc;
+    if (n_draws) BFB_CUDA(cudaMemcpy(n_draws, s.t_draw, sizeof(int64_t) * C, cudaMemcpyDeviceToHost));
+    if (status) BFB_CUDA(cudaMemcpy(status, s.status, sizeof(int32_t) * C, cudaMemcpyDeviceToHost));
+    return BFB_OK;
+}

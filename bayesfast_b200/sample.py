@@ -1,0 +1,185 @@
+"""
+sample(): the reference's chain pool (bayesfast/core/sample.py:26-220 + utils/parallel.py) replaced by one
+lock-step launch on the GPU: all chains of this process run as warps of one CUDA kernel (csrc/bfb_sampler.cu).
+Under torchrun (one process per GPU) pass comm=True: chains are sharded over the ranks, no collective is
+needed while sampling.
+"""
+import time
+
+import numpy as np
+
+from . import _cabi
+from .density import Density
+from .random import get_generator, new_seed
+from .runtime import dist_info, shard_bounds
+from .sample_trace import NTrace, HTrace, TraceTuple, SampleTrace, DualAverageAdaptation, QuadMetricDiag
+
+__all__ = ['sample']
+
+_ERR = {1: (ValueError, 'failed to get finite logp and/or grad at x_0.'),
+        2: (RuntimeError, 'Bad initial energy, please check the Hamiltonian.'),
+        3: (FloatingPointError, "logp can't be nan.")}
+
+
+def _as_density(density):
+    if isinstance(density, Density):
+        return density
+    if hasattr(density, '_surrogate_list'):            # a reference bayesfast.Density (duck-typed)
+        return Density.from_reference(density)
+    raise ValueError('density should be a bayesfast_b200.Density (or a fitted, surrogate-only bayesfast.Density); '
+                     'arbitrary Python densities cannot run on the device and there is no CPU fallback.')
+
+
+def sample(density, sample_trace=None, sampler='NUTS', n_run=None, parallel_backend='b200', verbose=True,
+           comm=None, fields=None):
+    """
+    Sampling a surrogate density with lock-step NUTS / HMC on the GPU.
+
+    Parameters follow bayesfast.core.sample.sample (sample.py:26-60).  `parallel_backend` is accepted for
+    signature compatibility and must be 'b200' / None.  `comm`: torch.distributed group (or True) to shard
+    the chains over ranks; the returned TraceTuple then holds this rank's chains (global chain ids).
+    `fields`: optional subset of outputs to bring back to the host (default: everything).
+
+    Returns
+    -------
+    tt : TraceTuple
+    """
+    if parallel_backend not in (None, 'b200'):
+        raise ValueError("bayesfast_b200.sample runs on the GPU only: parallel_backend should be 'b200' or None.")
+    den = _as_density(density)
+    resume = None
+    if isinstance(sample_trace, TraceTuple):
+        resume = sample_trace
+        sampler = resume.sampler
+        trace = resume._template
+    elif isinstance(sample_trace, NTrace):
+        sampler, trace = 'NUTS', sample_trace
+    elif isinstance(sample_trace, HTrace):
+        sampler, trace = 'HMC', sample_trace
+    elif sample_trace is None or isinstance(sample_trace, dict):
+        kw = {} if sample_trace is None else sample_trace
+        if sampler == 'NUTS':
+            trace = NTrace(**kw)
+        elif sampler == 'HMC':
+            trace = HTrace(**kw)
+        elif sampler in ('TNUTS', 'THMC', 'Ensemble'):
+            raise NotImplementedError('{} is not available on the device.'.format(sampler))
+        else:
+            raise ValueError('unexpected value for sampler.')
+    else:
+        raise ValueError('unexpected value for sample_trace.')
+
+    n = den.input_size
+    rank, world, _ = dist_info(comm)
+    if resume is not None:
+        return _continue(den, resume, n_run, verbose)
+
+    if trace.random_generator is None:
+        trace.random_generator = new_seed()
+        get_generator().normal()                       # sample.py:101
+    seed = trace.random_generator
+    hostrng = np.random.default_rng(seed)
+    C = trace.n_chain
+    if trace.x_0 is None:
+        # the reference seeds x_0 with Sobol multivariate-normal points (sample.py:107-112); plain normals here
+        x0 = hostrng.normal(size=(C, n))
+        trace._x_0_transformed = True
+    else:
+        x0 = np.asarray(trace.x_0, dtype=np.float64).reshape((-1, trace.x_0.shape[-1]))
+        if x0.shape[-1] != n:
+            raise ValueError('x_0 should have {} columns.'.format(n))
+        if not trace.x_0_transformed:
+            x0 = den.from_original(x0)                 # sample.py:113-116
+        if x0.shape[0] != C:                           # sample_trace.py:201-205
+            x0 = x0[hostrng.integers(0, x0.shape[0], size=C)]
+    lo, hi = shard_bounds(C, rank, world)
+    x0 = np.ascontiguousarray(x0[lo:hi])
+    Cl = hi - lo
+    if Cl == 0:
+        raise ValueError('rank {} received no chain: n_chain={} < world_size={}.'.format(rank, C, world))
+
+    # sample_trace.py:365-373 and :417-455
+    if isinstance(trace._step_size, DualAverageAdaptation):
+        step0 = np.full(Cl, np.exp(trace._step_size._log_step))
+    else:
+        step0 = np.full(Cl, (1. if trace._step_size is None else trace._step_size) / n**0.25)
+    m = trace._metric
+    if isinstance(m, QuadMetricDiag):
+        var0 = np.broadcast_to(m._var, (Cl, n))
+    elif isinstance(m, str):
+        var0 = np.ones((Cl, n))
+    else:
+        if m.shape != (n,):
+            raise ValueError('metric should have shape ({},).'.format(n))
+        var0 = np.broadcast_to(m, (Cl, n))
+    mean0 = x0 if trace._initial_mean is None else np.broadcast_to(trace._initial_mean, (Cl, n))
+
+    h = den._sync(False)
+    h.sampler_init(trace._cfg_dict(seed, lo), x0, step0, np.ascontiguousarray(var0), np.ascontiguousarray(mean0))
+    n_run = trace.n_iter if n_run is None else int(n_run)
+    if n_run <= 0:
+        raise ValueError('invalid value for n_run.')
+    if n_run > trace.n_iter:
+        trace._n_iter = n_run
+    t0 = time.time()
+    res = h.sampler_run(sampler, n_run, fields=fields)
+    final = h.sampler_state()
+    _raise_status(final['status'], lo)
+    final['step0'], final['x_0'] = step0, x0
+    arrays = _finish_arrays(den, res)
+    tt = TraceTuple(trace, arrays, final, chain0=lo, device_state=h)
+    tt.total_tree_size = res['total_tree_size']
+    tt.kernel_ms = h.last_kernel_ms()
+    if verbose:
+        print(' B200 : sampling finished [ {} / {} ], {} chains, {} leapfrog steps in {:.2f} seconds '
+              '(kernel {:.1f} ms).'.format(n_run, trace.n_iter, Cl, res['total_tree_size'], time.time() - t0,
+                                           tt.kernel_ms))
+    return tt
+
+
+def _raise_status(status, chain0):
+    bad = np.flatnonzero(status)
+    if bad.size:
+        code = int(status[bad[0]])
+        exc, msg = _ERR.get(code, (RuntimeError, 'sampler failed with status {}.'.format(code)))
+        raise exc(' CHAIN #{} : {}'.format(chain0 + int(bad[0]), msg))
+
+
+def _finish_arrays(den, res):
+    """sample.py:175-177: samples / logp in the original space"""
+    arrays = {k: v for k, v in res.items() if isinstance(v, np.ndarray)}
+    if 'samples' in arrays and 'logp' in arrays:
+        if den.input_scales is None:
+            arrays['samples_original'] = arrays['samples']
+            arrays['logp_original'] = arrays['logp']
+        else:
+            arrays['samples_original'] = den.to_original(arrays['samples'])
+            arrays['logp_original'] = den.to_original_density(arrays['logp'], x_trans=arrays['samples'])
+    return arrays
+
+
+def _continue(den, tt, n_run, verbose):
+    """in-memory resume (sample.py:91-98, base_hmc.py:101-111): the chains are still resident on the device"""
+    h = tt._device_state
+    if h is None or h is not den._sync(False):
+        raise RuntimeError('these chains are no longer resident on the device (or the density changed): '
+                           'cannot continue them.')
+    trace = tt._template
+    left = trace.n_iter - tt.i_iter
+    n_run = left if n_run is None else int(n_run)
+    if n_run <= 0:
+        raise ValueError('invalid value for n_run.')
+    if n_run > left:
+        trace._n_iter = tt.i_iter + n_run
+    res = h.sampler_run(tt.sampler, n_run)
+    final = h.sampler_state()
+    _raise_status(final['status'], tt._chain0)
+    final['step0'], final['x_0'] = tt._final['step0'], tt._final['x_0']
+    new = _finish_arrays(den, res)
+    arrays = {k: np.concatenate((tt._arrays[k], new[k]), axis=1) for k in new}
+    out = TraceTuple(trace, arrays, final, chain0=tt._chain0, device_state=h)
+    out.total_tree_size = res['total_tree_size']
+    out.kernel_ms = h.last_kernel_ms()
+    if verbose:
+        print(' B200 : sampling continued [ {} / {} ].'.format(out.i_iter, trace.n_iter))
+    return out

@@ -1,0 +1,170 @@
+/*
+ * bfb200.h -- C ABI of libbfb200.so, the B200 (sm_100a) implementation of BayesFast's hot path:
+ * PolyModel surrogate fit + value/gradient evaluation inside lock-step NUTS/HMC.
+ *
+ * The reference (h3jia/bayesfast) is pure Python + Cython and has no FFI seam of its own; its seams are
+ * Python duck types.  Each entry point below names the reference interface it
+ * replaces (paths relative to the reference root); bayesfast_b200/_cabi.py is the ctypes binding and
+ * INTEGRATION.md shows the stub a maintainer of the reference would add.
+ *
+ * Conventions: plain pointers and sizes, no exceptions; every function returns 0 on success and a
+ * negative code on failure, with a message available from bfb_last_error() (thread-local).
+ * All floating point data is IEEE double; matrices are row-major.  "loc" arguments say where caller
+ * buffers live: BFB_HOST (pageable or pinned host memory) or BFB_DEVICE (device memory of the handle's GPU).
+ * A handle owns one CUDA stream; calls on one handle are not thread-safe, different handles are independent.
+ * There is no CPU fallback: if no CUDA device is usable bfb_create fails.
+ */
+#ifndef BFB200_H
+#define BFB200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BFB_HOST 0
+#define BFB_DEVICE 1
+
+#define BFB_OK 0
+#define BFB_ERR_CUDA (-1)
+#define BFB_ERR_ARG (-2)
+#define BFB_ERR_STATE (-3)
+#define BFB_ERR_NUMERIC (-4)
+
+enum { BFB_LINEAR = 1, BFB_QUADRATIC = 2, BFB_CUBIC_2 = 3, BFB_CUBIC_3 = 4 };
+enum { BFB_NUTS = 0, BFB_HMC = 1 };
+
+typedef struct bfb_context *bfb_handle;
+
+const char *bfb_last_error(void);
+int bfb_version(void);
+int bfb_device_count(void);
+
+int bfb_create(int device, bfb_handle *out);
+int bfb_destroy(bfb_handle h);
+/* Use an existing CUDA stream (e.g. torch.cuda.current_stream().cuda_stream) instead of the handle's own. */
+int bfb_set_stream(bfb_handle h, void *cuda_stream);
+int bfb_synchronize(bfb_handle h);
+
+/* ------------------------------------------------------------------------------------------------
+ * Model: replaces the state of bayesfast.modules.poly.PolyModel (configs[i]._coef, _mu, _hess, _alpha,
+ * _f_mu; poly.py:19-158, 262-292), the ModuleBase input rescale (core/module.py:47-96, 221-227) and,
+ * for the sampler, the surrogate-only bayesfast.core.density.Density (decay: density.py:740-746, 796-811;
+ * variable transform: transforms/_constraint.pyx).
+ * Coefficients are passed PACKED, i.e. as the lstsq solution slices of poly.py:572-587: per config and per
+ * output of that config, in config order: linear n_in+1 | quadratic n_in(n_in+1)/2 (k<=l) |
+ * cubic-2 n_in^2 (k,l) | cubic-3 C(n_in,3) (k<l<p)  -- the column order of _poly.pyx:143-177.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t n, m, n_config;
+    const int32_t *cfg_order;     /* [n_config] BFB_LINEAR.. */
+    const int32_t *cfg_n_in;      /* [n_config] */
+    const int32_t *cfg_n_out;     /* [n_config] */
+    const int64_t *cfg_in_mask;   /* concatenated, sorted unique per config */
+    const int64_t *cfg_out_mask;  /* concatenated */
+    const double *cfg_coef;       /* concatenated packed coefficients, [config][output-in-config][packed] */
+    int32_t use_bound;            /* PolyModel._use_bound and not _all_linear */
+    const double *mu;             /* [n] */
+    const double *hess;           /* [n,n] */
+    double alpha;
+    const double *f_mu;           /* [m] */
+    int32_t use_scales;           /* module-level input_scales */
+    const double *s0, *sdiff;     /* [n] */
+    int32_t use_decay;
+    const double *d_mu, *d_hess;  /* [n], [n,n] */
+    double d_alpha2, d_gamma;
+    int32_t use_transform;        /* Density.input_scales is not None */
+    const double *ranges;         /* [n,2] */
+    const uint8_t *hard_bounds;   /* [n,2] */
+} bfb_model_desc;
+
+int bfb_set_model(bfb_handle h, const bfb_model_desc *desc);
+
+/* PolyModel.fun_and_jac for C points (module rescale included): replaces poly.py:443-503 called through
+ * core/module.py:221-227.  X [C,n] -> F [C,m], J [C,m,n] (J may be NULL). */
+int bfb_poly_eval_batch(bfb_handle h, const double *X, int64_t C, double *F, double *J, int loc);
+
+/* Density.logp_and_grad(x, original_space=False, use_surrogate=True) for C points of the TRANSFORMED space:
+ * replaces core/density.py:724-754 (+ Pipeline.fun_and_jac :487-566) for a surrogate-only density whose
+ * logp is output 0 of the PolyModel.  X [C,n] -> logp [C], grad [C,n]. */
+int bfb_logp_and_grad_batch(bfb_handle h, const double *X, int64_t C, double *logp, double *grad, int loc);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fit: replaces PolyModel.fit (poly.py:505-589): the design-matrix builders _lsq_* (_poly.pyx:143-177),
+ * scipy.linalg.lstsq (poly.py:570) and _set_bound (poly.py:262-292).  One design matrix per recipe row
+ * is shared by all outputs that use the same configs.
+ * Rows may be accumulated in several calls (and on several GPUs: bfb_fit_export/import carry the
+ * packed partial sums through an all-reduce).  The model set by bfb_set_model supplies the configs
+ * (coefficients there are ignored).  y [N,m]; w NULL or [N] (rows are scaled by w like poly.py:566-568).
+ * ---------------------------------------------------------------------------------------------- */
+int bfb_fit_begin(bfb_handle h);
+int bfb_fit_accumulate(bfb_handle h, const double *x, const double *y, const double *w, int64_t N, int loc);
+/* number of doubles in the partial-sum buffer (Gram blocks, X^T y, moments) */
+int64_t bfb_fit_buffer_size(bfb_handle h);
+/* device pointer of that buffer (for an in-place NCCL all-reduce by the host framework) */
+int bfb_fit_buffer(bfb_handle h, double **dev_ptr);
+/* solve the normal equations (equilibrated Cholesky + refinement), write packed coefficients in the
+ * layout of bfb_model_desc.cfg_coef; also installs them into the handle's model. */
+int bfb_fit_solve(bfb_handle h, double *coef_out, double *rel_resid);
+/* _set_bound pieces: mean and covariance^-1 of the accumulated x (unweighted), max Mahalanobis radius of
+ * the rows given here (second pass), all reductions on device. */
+int bfb_fit_moments(bfb_handle h, double *mu, double *hess);
+int bfb_fit_max_beta(bfb_handle h, const double *x, int64_t N, const double *mu, const double *hess,
+                     double *max_beta, double *beta_out /* NULL or [N] */, int loc);
+
+/* ------------------------------------------------------------------------------------------------
+ * Sampler: replaces bayesfast.core.sample.sample()'s worker pool (core/sample.py:165-214,
+ * utils/parallel.py:130-150) and NUTS/HMC.run (samplers/hmc_utils/base_hmc.py:62-172, samplers/nuts.py,
+ * samplers/hmc.py, hmc_utils/integration.py, metrics.py, step_size.py) for C chains at once, one warp per chain.
+ * Random stream: include/bfb_rng.h, chain ids chain0 .. chain0+C-1.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t n_warmup, max_treedepth, n_int_step;
+    double max_change;
+    int32_t adapt_step_size;
+    double target_accept, gamma, k, t0;
+    int32_t adapt_metric;
+    double initial_weight;
+    int32_t adapt_window, update_window, doubling;
+    uint64_t seed;
+    int64_t chain0;
+} bfb_sampler_cfg;
+
+/* Outputs of one bfb_sampler_run call, chain-major [C, n_iter(, n)]; any pointer may be NULL. */
+typedef struct {
+    double *samples;
+    double *logp, *energy, *mean_tree_accept, *step_size, *step_size_bar, *energy_change, *max_energy_change;
+    int32_t *tree_depth, *tree_size, *diverging;  /* HMC: tree_depth = accepted, tree_size = n_int_step */
+} bfb_run_out;
+
+/* x0 [C,n] (transformed space), step0 [C] (DualAverageAdaptation initial_step, i.e. already / n^0.25,
+ * sample_trace.py:365-373), var0 [C,n], mean0 [C,n] (initial_mean, sample_trace.py:437-444). Host pointers. */
+int bfb_sampler_init(bfb_handle h, const bfb_sampler_cfg *cfg, int64_t C, const double *x0,
+                     const double *step0, const double *var0, const double *mean0);
+/* advance every chain by n_iter iterations; out pointers in `loc`; total_tree_size (host, may be NULL) =
+ * sum over chains and iterations of tree_size = leapfrog steps performed in trees. */
+int bfb_sampler_run(bfb_handle h, int sampler, int32_t n_iter, const bfb_run_out *out, int loc,
+                    int64_t *total_tree_size);
+/* final adaptation state for the host-side trace objects: final_step [C,4] = log_step, log_bar, hbar, count;
+ * final_var [C,n]; n_draws [C]; status [C] (0 ok, 1 non-finite logp/grad at x0, 2 non-finite start energy,
+ * 3 nan in logbern); q [C,n] current position.  Host pointers, any may be NULL. */
+int bfb_sampler_get_state(bfb_handle h, double *final_step, double *final_var, int64_t *n_draws,
+                          int32_t *status, double *q);
+/* device time of the last bfb_sampler_run / bfb_fit_accumulate / bfb_poly_eval_batch kernel(s), CUDA events
+ * on the handle's stream, milliseconds */
+int bfb_last_kernel_ms(bfb_handle h, float *ms);
+/* number of kernels launched by this handle since creation */
+int64_t bfb_launch_count(bfb_handle h);
+
+/* draws t0..t0+count-1 of the stream (seed, chain) computed ON THE DEVICE: u (uniform view) and z (normal
+ * view).  Host pointers.  Used by the parity tests to teacher-force the oracle. */
+int bfb_rng_fill(bfb_handle h, uint64_t seed, uint64_t chain, uint64_t t0, int64_t count, double *u, double *z);
+
+/* FP64 peak microbenchmarks for the roofline denominator (MEASURED_PEAKS.json has no FP64 entry):
+ * kind 0 = DFMA, 1 = DMMA m8n8k4, 2 = both interleaved.  Returns TFLOP/s. */
+int bfb_fp64_peak(bfb_handle h, int kind, double *tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

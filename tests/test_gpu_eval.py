@@ -1,0 +1,115 @@
+"""GPU parity: batched PolyModel / Density evaluation through the C ABI vs golden vectors and the oracle."""
+import pickle
+
+import numpy as np
+import pytest
+
+import _golden_io as gio
+from _specs import to_device_spec, synthetic_spec
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-10     # BASELINE.json north_star: values within 1e-10 relative error in FP64
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, float).ravel(), np.asarray(b, float).ravel()
+    return np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-3 * np.max(np.abs(b)) + 1e-300))
+
+
+@pytest.fixture(scope='module')
+def handle():
+    from bayesfast_b200 import _cabi
+    h = _cabi.Handle(0)
+    yield h
+    h.close()
+
+
+def test_device_rng_matches_spec(handle, oracle):
+    u_d, z_d = handle.rng_fill(99, 12345678901, 5, 100000)
+    u_h, z_h = oracle.rng_fill(99, 12345678901, 5, 100000)
+    assert np.array_equal(u_d, u_h)                       # Philox + uniform conversion: bit exact
+    central = np.abs(u_h - 0.5) <= 0.425                  # Phi^-1 central branch: fma-only arithmetic
+    assert np.max(np.abs(z_d[central] - z_h[central]) / np.abs(z_h[central]).clip(1e-300)) < 4e-16
+    assert np.max(np.abs(z_d - z_h)) < 1e-14              # tails go through log()/sqrt()
+
+
+def test_poly_eval_golden(handle, oracle):
+    for c in gio.load('poly_eval.npz')['cases']:
+        handle.set_model(to_device_spec(c['spec']))
+        F, J = handle.poly_eval_batch(c['X'])
+        assert rel_err(F, c['wrapped_f']) < RTOL, c['name']
+        assert rel_err(J, c['wrapped_j']) < RTOL, c['name']
+        Fo, Jo = oracle.OracleDensity(c['spec']).poly_eval_batch(c['X'])
+        assert rel_err(F, Fo) < RTOL and rel_err(J, Jo) < RTOL, c['name']
+
+
+def test_poly_kat(handle):
+    g = gio.load('poly_kat.npz')
+    c = g['logp']
+    handle.set_model(to_device_spec(c['spec']))
+    F, J = handle.poly_eval_batch(g['x'])
+    assert rel_err(F, c['values']) < RTOL
+    assert rel_err(J[0, 0], c['jac0']) < RTOL
+    F, J = handle.poly_eval_batch(c['far'][None])
+    assert rel_err(F[0], c['far_f']) < RTOL and rel_err(J[0], c['far_j']) < RTOL
+    # SURVEY.md 8c known answers
+    assert abs(F[0, 0] - (-46.7409242042374)) < 1e-9
+    assert np.allclose(J[0, 0], [-11.740561821414351, 9.420776593640085, -18.24732501727469, -47.35933812148955],
+                       rtol=1e-10)
+
+
+def test_density_golden(handle, oracle):
+    for c in gio.load('density.npz')['cases']:
+        handle.set_model(to_device_spec(c['spec']))
+        lp, g = handle.logp_and_grad_batch(c['X'])
+        assert rel_err(lp, c['logp']) < RTOL, c['name']
+        assert rel_err(g, c['grad']) < RTOL, c['name']
+
+
+@pytest.mark.parametrize('n,order', [(26, 'cubic-2'), (16, 'cubic-2'), (2, 'quadratic'), (40, 'cubic-3'), (64, 'cubic-2')])
+def test_density_large_batch_vs_oracle(handle, oracle, n, order):
+    spec, cov = synthetic_spec(n, order, seed=n, decay=True, transform=(n == 26))
+    handle.set_model(to_device_spec(spec))
+    rng = np.random.default_rng(1)
+    L = np.linalg.cholesky(cov)
+    C = 4099 if n < 40 else 300                           # ragged: not a multiple of the block size
+    X = (L @ rng.normal(size=(n, C))).T * rng.choice([0.5, 1., 3.], size=(C, 1))
+    if spec['transform_ranges'] is not None:
+        X = np.clip(X, spec['transform_ranges'][:, 0] * 0.9, spec['transform_ranges'][:, 1] * 0.9)
+        X = np.array([oracle.from_original(x, spec['transform_ranges'], spec['hard_bounds']) for x in X])
+    lp, g = handle.logp_and_grad_batch(X)
+    lpo, go = oracle.OracleDensity(spec).logp_and_grad_batch(X)
+    assert rel_err(lp, lpo) < RTOL and rel_err(g, go) < RTOL
+
+
+def test_empty_batch_and_errors(handle):
+    spec, _ = synthetic_spec(5)
+    handle.set_model(to_device_spec(spec))
+    F, J = handle.poly_eval_batch(np.zeros((0, 5)))
+    assert F.shape == (0, 1) and J.shape == (0, 1, 5)
+    from bayesfast_b200 import _cabi
+    bad = to_device_spec(spec)
+    bad['configs'][0]['input_mask'] = np.array([0, 1, 2, 3, 7])
+    with pytest.raises(_cabi.BfbError):
+        handle.set_model(bad)
+
+
+def test_polymodel_api(oracle):
+    import bayesfast_b200 as bfb
+    rng = np.random.default_rng(3)
+    s = bfb.PolyModel('cubic-3', input_size=5, output_size=2, bound_options={'use_bound': False})
+    for conf in s.configs:
+        for i in range(conf.output_size):
+            conf._set(rng.normal(size=conf._a_shape), i)
+    x = rng.normal(size=5)
+    f, j = s._fun_and_jac(x)
+    spec = s.to_spec()
+    Fo, Jo = oracle.OracleDensity(spec).poly_eval_batch(x[None])
+    assert rel_err(f, Fo[0]) < RTOL and rel_err(j, Jo[0]) < RTOL
+    assert isinstance(s(x), list) and s(x)[0].shape == (2,) and s.jac(x)[0].shape == (2, 5)
+    s2 = pickle.loads(pickle.dumps(s))
+    assert np.array_equal(s2._fun(x), s._fun(x))
+    with pytest.raises(ValueError):
+        s._fun(np.zeros(4))
+    with pytest.raises(ValueError):
+        bfb.PolyModel([bfb.PolyConfig('linear'), bfb.PolyConfig('linear')], input_size=2, output_size=1)

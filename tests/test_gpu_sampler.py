@@ -1,0 +1,182 @@
+"""GPU parity of the lock-step NUTS / HMC kernels vs golden runs of the real reference and vs the oracle."""
+import numpy as np
+import pytest
+
+import _golden_io as gio
+from _specs import to_device_spec, synthetic_spec
+
+pytestmark = pytest.mark.gpu
+
+INT_STATS = ('tree_depth', 'tree_size', 'diverging')
+FLT_STATS = ('logp', 'energy', 'mean_tree_accept', 'step_size', 'step_size_bar', 'energy_change', 'max_energy_change')
+# floats: tight over the first EARLY iterations, loose later (chaotic amplification of rounding differences through
+# step-size / metric adaptation, see tests/test_oracle_golden.py); integer outcomes must be identical throughout.
+EARLY, EARLY_TOL, LATE_TOL = 8, 1e-9, 1e-3
+
+
+def cfg_from(kw, n_warmup, seed, chain0=0):
+    d = dict(n_warmup=n_warmup, max_treedepth=10, n_int_step=0, max_change=1000., adapt_step_size=1,
+             target_accept=0.8, gamma=0.05, k=0.75, t0=10., adapt_metric=1, initial_weight=10., adapt_window=60,
+             update_window=1, doubling=1, seed=seed, chain0=chain0)
+    for k, v in kw.items():
+        if k in d:
+            d[k] = type(d[k])(v)
+    return d
+
+
+@pytest.fixture(scope='module')
+def handle():
+    from bayesfast_b200 import _cabi
+    h = _cabi.Handle(0)
+    yield h
+    h.close()
+
+
+def device_draws(handle, seed, n_draws, chain0=0):
+    nmax = int(max(n_draws)) + 8
+    U = np.zeros((len(n_draws), nmax))
+    Z = np.zeros((len(n_draws), nmax))
+    for c in range(len(n_draws)):
+        U[c], Z[c] = handle.rng_fill(seed, chain0 + c, 0, nmax)
+    return U, Z
+
+
+def check_floats(a, b, tag):
+    assert np.allclose(a[:, :EARLY], b[:, :EARLY], rtol=EARLY_TOL, atol=EARLY_TOL, equal_nan=True), tag
+    assert np.allclose(a, b, rtol=LATE_TOL, atol=LATE_TOL, equal_nan=True), tag
+
+
+@pytest.mark.parametrize('case', gio.load('sampler.npz')['cases'], ids=lambda c: c['name'])
+def test_golden_chains(handle, oracle, case):
+    """same seeds and draw stream as the recorded runs of the real reference"""
+    r, kw = case['result'], case['trace_kw']
+    n_iter, n_warmup = int(kw['n_iter']), int(kw['n_warmup'])
+    handle.set_model(to_device_spec(case['spec']))
+    cfg = cfg_from(kw, n_warmup, int(case['seed']))
+    handle.sampler_init(cfg, case['x0'], float(r['step0']), r['var0'], case['x0'])
+    out = handle.sampler_run(case['sampler'], n_iter)
+    st = handle.sampler_state()
+    assert np.all(st['status'] == 0)
+    assert np.array_equal(st['n_draws'], r['n_draws'])
+    if case['sampler'] == 'NUTS':
+        for k in INT_STATS:
+            assert np.array_equal(out[k], r[k].astype(np.int32)), k
+        for k in FLT_STATS:
+            check_floats(out[k], r[k], k)
+        assert out['total_tree_size'] == int(r['tree_size'].sum())
+    else:
+        assert np.array_equal(out['tree_depth'], r['accepted'].astype(np.int32))
+        assert np.array_equal(out['diverging'], r['diverging'].astype(np.int32))
+        for k, k2 in (('logp', 'logp'), ('energy', 'energy'), ('mean_tree_accept', 'accept_stat'),
+                      ('step_size', 'step_size'), ('energy_change', 'energy_change')):
+            check_floats(out[k], r[k2], k)
+    check_floats(out['samples'], r['samples'], 'samples')
+    assert np.allclose(st['final_step'], r['final_step'], rtol=LATE_TOL)
+    assert np.allclose(st['final_var'], r['final_var'], rtol=LATE_TOL)
+
+
+@pytest.mark.parametrize('n,order,C,n_iter', [(26, 'cubic-2', 256, 40), (16, 'cubic-2', 130, 40), (40, 'cubic-3', 6, 12),
+                                               (2, 'quadratic', 64, 60)])
+def test_teacher_forced_vs_oracle(handle, oracle, n, order, C, n_iter):
+    """per-chain tree depths / sizes / divergences identical to the oracle fed with the device's own draws"""
+    spec, cov = synthetic_spec(n, order, seed=7 + n, decay=True)
+    handle.set_model(to_device_spec(spec))
+    rng = np.random.default_rng(5)
+    x0 = (np.linalg.cholesky(cov) @ rng.normal(size=(n, C))).T
+    seed, chain0 = 4242, 1000
+    cfg = cfg_from({}, n_iter // 2, seed, chain0)
+    step0 = 1. / n**0.25
+    handle.sampler_init(cfg, x0, step0, np.ones(n), x0)
+    out = handle.sampler_run('NUTS', n_iter)
+    st = handle.sampler_state()
+    assert np.all(st['status'] == 0)
+    U, Z = device_draws(handle, seed, st['n_draws'], chain0)
+    ref = oracle.OracleDensity(spec).run('NUTS', dict(n_iter=n_iter, n_warmup=n_iter // 2), x0, step0, np.ones(n),
+                                         draws_u=U, draws_z=Z)
+    assert np.all(ref['status'] == 0)
+    assert np.array_equal(st['n_draws'], ref['n_draws'])
+    for k in INT_STATS:
+        assert np.array_equal(out[k], ref[k]), k
+    check_floats(out['samples'], ref['samples'], 'samples')
+    assert out['total_tree_size'] == int(ref['tree_size'].sum())
+
+
+def test_hmc_vs_oracle(handle, oracle):
+    n, C, n_iter = 12, 64, 40
+    spec, cov = synthetic_spec(n, 'cubic-2', seed=3)
+    handle.set_model(to_device_spec(spec))
+    x0 = (np.linalg.cholesky(cov) @ np.random.default_rng(2).normal(size=(n, C))).T
+    cfg = cfg_from({'n_int_step': 12}, 20, 77)
+    handle.sampler_init(cfg, x0, 0.5, np.ones(n), x0)
+    out = handle.sampler_run('HMC', n_iter)
+    st = handle.sampler_state()
+    U, Z = device_draws(handle, 77, st['n_draws'])
+    ref = oracle.OracleDensity(spec).run('HMC', dict(n_iter=n_iter, n_warmup=20, n_int_step=12), x0, 0.5, np.ones(n),
+                                         draws_u=U, draws_z=Z)
+    assert np.array_equal(out['tree_depth'], ref['tree_depth'])
+    assert np.array_equal(out['diverging'], ref['diverging'])
+    check_floats(out['samples'], ref['samples'], 'samples')
+
+
+def test_full_size_posterior_moments(handle):
+    """BASELINE config shape (d=26 cubic-2, 4096 chains): size-independent checks on a pure Gaussian surrogate
+    whose posterior is known exactly: mean / variance within Monte Carlo error, no divergences after warm-up,
+    chains are reproducible (same seed -> same bits) and independent of how they are batched."""
+    n, C = 26, 4096
+    spec, cov = synthetic_spec(n, 'quadratic', seed=11, bound=False)
+    lin = spec['configs'][0]['coef'][0, 1:]
+    mean = cov @ lin
+    handle.set_model(to_device_spec(spec))
+    x0 = np.random.default_rng(0).normal(size=(C, n))
+    cfg = cfg_from({}, 150, 2024)
+    handle.sampler_init(cfg, x0, 1. / n**0.25, np.ones(n), x0)
+    out = handle.sampler_run('NUTS', 250)
+    post = out['samples'][:, 150:].reshape(-1, n)
+    sd = np.sqrt(np.diag(cov))
+    ess = post.shape[0] / 4.
+    assert np.all(np.abs(post.mean(axis=0) - mean) < 6. * sd / np.sqrt(ess))
+    assert np.all(np.abs(post.var(axis=0) / np.diag(cov) - 1.) < 0.05)
+    assert out['diverging'][:, 150:].sum() == 0
+    assert np.all(out['tree_size'] <= 2 ** out['tree_depth'] - 1) and np.all(out['tree_size'] >= 2 ** (out['tree_depth'] - 1))
+    # reproducibility + batching independence: chains 100..163 alone, with chain0 = 100
+    cfg2 = cfg_from({}, 150, 2024, chain0=100)
+    handle.sampler_init(cfg2, x0[100:164], 1. / n**0.25, np.ones(n), x0[100:164])
+    out2 = handle.sampler_run('NUTS', 250, fields=('samples', 'tree_depth'))
+    assert np.array_equal(out2['samples'], out['samples'][100:164])
+    assert np.array_equal(out2['tree_depth'], out['tree_depth'][100:164])
+
+
+def test_sample_api(oracle):
+    import bayesfast_b200 as bfb
+    n = 6
+    spec, cov = synthetic_spec(n, 'cubic-2', seed=4, decay=True, transform=True)
+    sur = bfb.PolyModel('cubic-2', input_size=n, output_size=1)
+    from _specs import pack
+    for conf, cf in zip(sur.configs, spec['configs']):
+        conf._set(pack(cf['order'], cf['coef'][0], n), 0)
+    sur._mu, sur._hess, sur._alpha, sur._f_mu = spec['mu'], spec['hess'], spec['alpha'], spec['f_mu']
+    den = bfb.Density(sur, input_scales=spec['transform_ranges'], hard_bounds=spec['hard_bounds'],
+                      decay_options=dict(use_decay=True, alpha=float(np.sqrt(spec['d_alpha2'])), alpha_p=None))
+    den._mu, den._hess = spec['d_mu'], spec['d_hess']
+    x0 = (np.linalg.cholesky(cov) @ np.random.default_rng(1).normal(size=(n, 16))).T * 0.5
+    tt = bfb.sample(den, dict(n_chain=16, n_iter=60, n_warmup=30, x_0=x0, random_generator=5), verbose=False)
+    assert tt.n_chain == 16 and tt.samples.shape == (16, 60, n)
+    t3 = tt[3]
+    assert isinstance(t3, bfb.NTrace) and t3.chain_id == 3 and t3.samples.shape == (60, n)
+    assert len(t3.stats._tree_depth) == 60 and t3.stats.n_warmup == 30
+    assert tt.get().shape == (16 * 30, n)
+    assert np.allclose(t3.samples_original, den.to_original(t3.samples))
+    assert t3.n_call == int(np.sum(t3.stats._tree_size[1:])) + 60 + 1
+    # vs the oracle with the same stream
+    od = oracle.OracleDensity(den.to_spec())
+    U, Z = device_draws(den._sync(False), 5, tt._final['n_draws'])
+    ref = od.run('NUTS', dict(n_iter=60, n_warmup=30), den.from_original(x0), 1. / n**0.25, np.ones(n), draws_u=U, draws_z=Z)
+    assert np.array_equal(tt.arrays['tree_depth'], ref['tree_depth'])
+    # resume
+    tt2 = bfb.sample(den, tt, n_run=10, verbose=False)
+    assert tt2.samples.shape == (16, 70, n) and np.array_equal(tt2.samples[:, :60], tt.samples)
+    # errors surface like the reference's (base_hmc.py:42-46)
+    bad = x0.copy()
+    bad[2] = np.nan
+    with pytest.raises(ValueError):
+        bfb.sample(den, dict(n_chain=16, n_iter=20, n_warmup=10, x_0=bad, random_generator=5), verbose=False)
