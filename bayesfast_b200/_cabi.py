@@ -91,9 +91,8 @@ def lib():
                     ('bfb_fit_buffer', [C.c_void_p, C.POINTER(C.c_void_p)], C.c_int),
                     ('bfb_fit_solve', [C.c_void_p, _dp, _dp], C.c_int),
                     ('bfb_fit_moments', [C.c_void_p, _dp, _dp], C.c_int),
-                    ('bfb_fit_max_beta', [C.c_void_p, C.c_void_p, C.c_int64, _dp, _dp, _dp, C.c_void_p, C.c_int], C.c_int),
-                    ('bfb_fit_refine', [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int], C.c_int),
-                    ('bfb_fit_refine_solve', [C.c_void_p, _dp], C.c_int)):
+                    ('bfb_fit_max_beta', [C.c_void_p, C.c_void_p, C.c_int64, _dp, _dp, C.POINTER(C.c_double), C.c_void_p, C.c_int], C.c_int),
+                    ):
                 if hasattr(L, name):
                     f = getattr(L, name)
                     f.argtypes, f.restype = args, res

@@ -1,13 +1,190 @@
-"""Host orchestration of PolyModel.fit on the device (filled in with the Gram / Cholesky kernels)."""
+"""
+Host orchestration of PolyModel.fit / _set_bound on the device (reference: bayesfast/modules/poly.py:505-589,
+262-292; bayesfast/core/density.py:796-811).
+
+  rows (x, y, w) --H2D--> fused feature expansion + FP64 DMMA Gram (+ shifted moments)   [csrc/bfb_fit.cu]
+                 --(NCCL all-reduce of ONE packed buffer when rows are sharded over GPUs)-->
+                 equilibrated Cholesky solve + refinement on every rank (bit-identical inputs -> identical
+                 coefficients, no broadcast needed) --> packed coefficients --> PolyConfig._set
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _cabi
+from .runtime import dist_info
 
 
-def fit_polymodel(model, x, y, logp, w, comm=None, refine=1):
-    raise NotImplementedError('fit kernels are not built yet')
+def _allreduce_buffer(h, group, op='sum'):
+    """in-place NCCL all-reduce of the handle's partial-sum buffer (device pointer wrapped as a torch tensor)"""
+    import torch
+    import torch.distributed as dist
+    L = _cabi.lib()
+    n = int(L.bfb_fit_buffer_size(h._h))
+    ptr = C.c_void_p()
+    _cabi.check(L.bfb_fit_buffer(h._h, C.byref(ptr)))
+    if dist.get_backend(group) == 'nccl':
+        t = _wrap_device_ptr(ptr.value, n, h.device)
+        h.synchronize()
+        dist.all_reduce(t, group=group)
+        torch.cuda.synchronize(h.device)
+    else:   # gloo (CPU tests): stage through the host
+        raise RuntimeError('sharded fit needs the nccl backend')
 
 
-def set_bound(model, x, logp):
-    raise NotImplementedError('fit kernels are not built yet')
+def _wrap_device_ptr(ptr, n, device):
+    """zero-copy torch view of `n` doubles at device address `ptr` (via __cuda_array_interface__)"""
+    import torch
+
+    class _Arr:
+        __cuda_array_interface__ = {'shape': (n,), 'typestr': '<f8', 'data': (int(ptr), False), 'version': 3,
+                                    'strides': None}
+    return torch.as_tensor(_Arr(), device='cuda:{}'.format(device))
 
 
-def ellipsoid(model, x, alpha_p):
-    raise NotImplementedError('fit kernels are not built yet')
+def _handle_for(model):
+    h = model._dev()
+    # the configs must be on the device before bfb_fit_begin; coefficients may still be missing (zeros)
+    h.set_model(model.to_spec(with_bound=False))
+    model._dirty = True
+    return h
+
+
+def fit_polymodel(model, x, y, logp=None, w=None, comm=None, refine=1):
+    x = np.asarray(x, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64)
+    n, m = model._input_size, model._output_size
+    if not (x.ndim == 2 and x.shape[-1] == n):
+        raise ValueError('x should be a 2-d array, with shape (# of points, # of input_size), instead of '
+                         '{}.'.format(x.shape))
+    if not (y.ndim == 2 and y.shape[-1] == m):
+        raise ValueError('y should be a 2-d array, with shape (# of points, # of output_size), instead of '
+                         '{}.'.format(y.shape))
+    if x.shape[0] != y.shape[0]:
+        raise ValueError('x and y have different # of points.')
+    rank, world, group = dist_info(comm)
+    n_total = x.shape[0]
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        t = torch.tensor([n_total], dtype=torch.int64, device='cuda:{}'.format(model._dev().device))
+        dist.all_reduce(t, group=group)
+        n_total = int(t.item())
+    if n_total < model.n_param:
+        raise ValueError('I need at least {} points, but you only gave me {}.'.format(model.n_param, n_total))
+    if w is not None:
+        w = np.atleast_1d(np.asarray(w, dtype=np.float64))
+        if not (w.ndim == 1 and w.shape[0] == x.shape[0]):
+            raise ValueError('invalid shape for w.')
+    h = _handle_for(model)
+    L = _cabi.lib()
+    shift = np.ascontiguousarray(x[0] if (world == 1 and x.shape[0]) else np.zeros(n))
+    _cabi.check(L.bfb_fit_begin(h._h, shift.ctypes.data))
+    xc, yc = _cabi.f64(x), _cabi.f64(y)
+    wc = None if w is None else _cabi.f64(w)
+    _cabi.check(L.bfb_fit_accumulate(h._h, xc.ctypes.data, yc.ctypes.data, None if wc is None else wc.ctypes.data,
+                                     xc.shape[0], _cabi.BFB_HOST))
+    model._fit_kernel_ms = h.last_kernel_ms()
+    if world > 1:
+        _allreduce_buffer(h, group)
+    total = sum(_cabi.n_packed(c.order, c.input_size) * c.output_size for c in model._configs)
+    coef = np.empty(total)
+    rr = C.c_double(0.)
+    _cabi.check(L.bfb_fit_solve(h._h, coef.ctypes.data_as(_cabi._dp), C.byref(rr)))
+    model._fit_rel_resid = float(rr.value)
+    off, packed = 0, []
+    for c in model._configs:
+        k = _cabi.n_packed(c.order, c.input_size)
+        packed.append(coef[off:off + k * c.output_size].reshape(c.output_size, k))
+        off += k * c.output_size
+    model._install(packed)
+    if model._use_bound and not model._all_linear:
+        set_bound(model, x, logp, _handle=h, _have_moments=True, comm=comm)
+
+
+def ellipsoid(model, x, alpha_p, _handle=None, _have_moments=False, comm=None):
+    """mean, inverse covariance and radius alpha of the points x (poly.py:266-276, density.py:802-811)"""
+    rank, world, group = dist_info(comm)
+    L = _cabi.lib()
+    h = _handle
+    n = x.shape[1]
+    if h is None:
+        h = _handle_for(model)
+    if not _have_moments:
+        if x.shape[1] != model._input_size:
+            raise ValueError('invalid value for x.')
+        shift = np.ascontiguousarray(x[0] if world == 1 else np.zeros(n))
+        _cabi.check(L.bfb_fit_begin(h._h, shift.ctypes.data))
+        xc = _cabi.f64(x)
+        yz = np.zeros((xc.shape[0], model._output_size))
+        _cabi.check(L.bfb_fit_accumulate(h._h, xc.ctypes.data, yz.ctypes.data, None, xc.shape[0], _cabi.BFB_HOST))
+        if world > 1:
+            _allreduce_buffer(h, group)
+    mu, cov = np.empty(n), np.empty((n, n))
+    _cabi.check(L.bfb_fit_moments(h._h, mu.ctypes.data_as(_cabi._dp), cov.ctypes.data_as(_cabi._dp)))
+    hess = np.linalg.inv(cov)                        # n x n host glue, the same LAPACK call as poly.py:268
+    alpha = None
+    if alpha_p is not None:
+        xc = _cabi.f64(x)
+        mb = C.c_double(0.)
+        want_all = alpha_p < 100.
+        beta = np.empty(xc.shape[0]) if want_all else None
+        _cabi.check(L.bfb_fit_max_beta(h._h, xc.ctypes.data, xc.shape[0], mu.ctypes.data_as(_cabi._dp),
+                                       hess.ctypes.data_as(_cabi._dp), C.byref(mb),
+                                       None if beta is None else beta.ctypes.data, _cabi.BFB_HOST))
+        if want_all:
+            if world > 1:
+                raise NotImplementedError('alpha_p < 100 (a percentile of the radii) is not supported with sharded '
+                                          'rows; use alpha_p >= 100.')
+            alpha = float(np.percentile(beta, alpha_p))       # poly.py:273
+        else:
+            mx = float(mb.value)
+            if world > 1:
+                import torch
+                import torch.distributed as dist
+                t = torch.tensor([mx], dtype=torch.float64, device='cuda:{}'.format(h.device))
+                dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+                mx = float(t.item())
+            alpha = mx * alpha_p / 100.                       # poly.py:275
+    return mu, hess, alpha
+
+
+def set_bound(model, x, logp=None, _handle=None, _have_moments=False, comm=None):
+    """PolyModel._set_bound (poly.py:262-292)"""
+    from .poly import warn_center_max
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    if not (x.ndim == 2 and x.shape[-1] == model._input_size):
+        raise ValueError('invalid value for x.')
+    rank, world, group = dist_info(comm)
+    mu, hess, alpha = ellipsoid(model, x, model._alpha_p, _handle, _have_moments, comm)
+    model._mu, model._hess = mu, hess
+    if model._alpha_p is not None:
+        model._alpha = alpha
+    mu_f = mu
+    if model._center_max:
+        try:
+            logp = np.asarray(logp, dtype=np.float64)
+            assert x.shape[0] == logp.shape[0] and logp.ndim == 1
+            i = int(np.argmax(logp))
+            mu_f, best = x[i], float(logp[i])
+            if world > 1:
+                import torch
+                import torch.distributed as dist
+                dev = 'cuda:{}'.format(model._dev().device)
+                cand = torch.tensor(np.concatenate(([best], mu_f)), dtype=torch.float64, device=dev)
+                allc = [torch.empty_like(cand) for _ in range(world)]
+                dist.all_gather(allc, cand, group=group)
+                allc = torch.stack(allc).cpu().numpy()
+                mu_f = allc[int(np.argmax(allc[:, 0])), 1:]
+        except Exception:
+            warn_center_max()
+            mu_f = mu
+    # f_mu is evaluated with the bound disabled (poly.py:288-292)
+    save = model._use_bound
+    try:
+        model._use_bound = False
+        model._dirty = True
+        model._f_mu = model._fun(np.ascontiguousarray(mu_f))
+    finally:
+        model._use_bound = save
+        model._dirty = True

@@ -97,7 +97,7 @@ int bfb_logp_and_grad_batch(bfb_handle h, const double *X, int64_t C, double *lo
  * packed partial sums through an all-reduce).  The model set by bfb_set_model supplies the configs
  * (coefficients there are ignored).  y [N,m]; w NULL or [N] (rows are scaled by w like poly.py:566-568).
  * ---------------------------------------------------------------------------------------------- */
-int bfb_fit_begin(bfb_handle h);
+int bfb_fit_begin(bfb_handle h, const double *shift /* [n] or NULL: reference point of the shifted moments, identical on all ranks */);
 int bfb_fit_accumulate(bfb_handle h, const double *x, const double *y, const double *w, int64_t N, int loc);
 /* number of doubles in the partial-sum buffer (Gram blocks, X^T y, moments) */
 int64_t bfb_fit_buffer_size(bfb_handle h);
@@ -108,7 +108,7 @@ int bfb_fit_buffer(bfb_handle h, double **dev_ptr);
 int bfb_fit_solve(bfb_handle h, double *coef_out, double *rel_resid);
 /* _set_bound pieces: mean and covariance^-1 of the accumulated x (unweighted), max Mahalanobis radius of
  * the rows given here (second pass), all reductions on device. */
-int bfb_fit_moments(bfb_handle h, double *mu, double *hess);
+int bfb_fit_moments(bfb_handle h, double *mu, double *cov);
 int bfb_fit_max_beta(bfb_handle h, const double *x, int64_t N, const double *mu, const double *hess,
                      double *max_beta, double *beta_out /* NULL or [N] */, int loc);
 

@@ -88,7 +88,7 @@ BFB_HD double bfb_norminv(double p)
 {
     double q = p - 0.5, r, num, den, val;
     if (fabs(q) <= 0.425) {
-        r = 0.180625 - q * q;
+        r = BFB_FMA(-q, q, 0.180625);
         num = 2.5090809287301226727e+3;
         num = BFB_FMA(num, r, 3.3430575583588128105e+4);
         num = BFB_FMA(num, r, 6.7265770927008700853e+4);

@@ -372,8 +372,8 @@ def make_sampler():
     far = np.array([den.from_original(np.clip((L @ rng.normal(size=6)) * 3.5, -11., 11.)) for _ in range(2)])
     add('nuts_c2_n6_far_start', 'NUTS', den, far, 303, n_iter=30, n_warmup=15)
     add('nuts_c2_n6_depthcap', 'NUTS', den, x0[:2], 404, n_iter=30, n_warmup=10, max_treedepth=2)
-    add('nuts_c2_n6_divergent', 'NUTS', den, x0[:2], 505, n_iter=30, n_warmup=10, max_change=0.2,
-        step_size=2.5, adapt_step_size=False)
+    add('nuts_c2_n6_divergent', 'NUTS', den, x0[:2], 505, n_iter=30, n_warmup=10, max_change=3.0,
+        step_size=1.1, adapt_step_size=False)
     add('nuts_c2_n6_noadapt', 'NUTS', den, x0[:2], 606, n_iter=25, n_warmup=10, adapt_step_size=False,
         adapt_metric=False, step_size=0.6)
     add('hmc_c2_n6', 'HMC', den, x0[:2], 707, n_iter=30, n_warmup=15, n_int_step=8)
