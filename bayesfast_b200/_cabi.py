@@ -78,6 +78,7 @@ def lib():
             L.bfb_logp_and_grad_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int]
             L.bfb_fit_begin.argtypes = [C.c_void_p, C.c_void_p]
             L.bfb_sampler_init.argtypes = [C.c_void_p, C.POINTER(SamplerCfg), C.c_int64, _dp, _dp, _dp, _dp]
+            L.bfb_sampler_reset.argtypes = [C.c_void_p]
             L.bfb_sampler_run.argtypes = [C.c_void_p, C.c_int, C.c_int32, C.POINTER(RunOut), C.c_int, _lp]
             L.bfb_sampler_get_state.argtypes = [C.c_void_p, _dp, _dp, _lp, _ip, _dp]
             L.bfb_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
@@ -270,6 +271,9 @@ class Handle:
                                       C.byref(tot)))
         res['total_tree_size'] = int(tot.value)
         return res
+
+    def sampler_reset(self):
+        check(self._L.bfb_sampler_reset(self._h))
 
     def sampler_state(self):
         nc, n = self.n_chain, self.n

@@ -110,6 +110,7 @@ struct bfb_context {
     bfb_sampler_cfg scfg;
     ChainState cs;
     std::vector<void *> chain_allocs;
+    std::vector<void *> chain_snapshot;
     // fit
     FitState *fit;
 };

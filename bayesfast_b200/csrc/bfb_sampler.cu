@@ -378,6 +378,26 @@ static int h2d(bfb_context *h, T *dst, const std::vector<T> &src)
     return BFB_OK;
 }
 
+// (pointer, bytes) list of every chain-state array, for snapshot / reset
+static std::vector<std::pair<void *, size_t>> state_arrays(const ChainState &s)
+{
+    const size_t V = (size_t)s.C * s.np * sizeof(double), D = (size_t)s.C * sizeof(double), I = (size_t)s.C * sizeof(int64_t);
+    return {{s.q, V}, {s.g, V}, {s.var, V}, {s.fg_mean, V}, {s.fg_raw, V}, {s.bg_mean, V}, {s.bg_raw, V},
+            {s.logp, D}, {s.fg_n, D}, {s.bg_n, D}, {s.log_step, D}, {s.log_bar, D}, {s.hbar, D}, {s.mu_da, D},
+            {s.count, I}, {s.n_samples, I}, {s.previous_update, I}, {s.adapt_window, (size_t)s.C * sizeof(int32_t)},
+            {s.t_draw, I}, {s.iter, I}, {s.status, (size_t)s.C * sizeof(int32_t)}};
+}
+
+extern "C" int bfb_sampler_reset(bfb_handle h)
+{
+    BFB_REQUIRE(h && h->has_chains && !h->chain_snapshot.empty(), BFB_ERR_STATE, "bfb_sampler_reset: no chains");
+    BFB_CUDA(cudaSetDevice(h->device));
+    auto arrs = state_arrays(h->cs);
+    for (size_t i = 0; i < arrs.size(); ++i)
+        BFB_CUDA(cudaMemcpyAsync(arrs[i].first, h->chain_snapshot[i], arrs[i].second, cudaMemcpyDeviceToDevice, h->stream));
+    return BFB_OK;
+}
+
 extern "C" int bfb_sampler_init(bfb_handle h, const bfb_sampler_cfg *cfg, int64_t C, const double *x0,
                                 const double *step0, const double *var0, const double *mean0)
 {
@@ -388,6 +408,7 @@ extern "C" int bfb_sampler_init(bfb_handle h, const bfb_sampler_cfg *cfg, int64_
     BFB_CUDA(cudaSetDevice(h->device));
     BFB_CUDA(cudaStreamSynchronize(h->stream));
     bfb_free_list(h->chain_allocs);
+    h->chain_snapshot.clear();
     h->has_chains = false;
     h->scfg = *cfg;
     const int n = h->n, np = h->np;
@@ -438,6 +459,15 @@ extern "C" int bfb_sampler_init(bfb_handle h, const bfb_sampler_cfg *cfg, int64_
     }
     h->launches++;
     BFB_CUDA(cudaGetLastError());
+    // device-resident snapshot of the initial state (bfb_sampler_reset restarts the same run without host traffic)
+    h->chain_snapshot.clear();
+    for (auto &a : state_arrays(s)) {
+        void *p = nullptr;
+        BFB_CUDA(cudaMalloc(&p, a.second));
+        h->chain_allocs.push_back(p);
+        h->chain_snapshot.push_back(p);
+        BFB_CUDA(cudaMemcpyAsync(p, a.first, a.second, cudaMemcpyDeviceToDevice, h->stream));
+    }
     BFB_CUDA(cudaStreamSynchronize(h->stream));
     h->has_chains = true;
     return BFB_OK;

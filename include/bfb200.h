@@ -141,6 +141,8 @@ typedef struct {
  * sample_trace.py:365-373), var0 [C,n], mean0 [C,n] (initial_mean, sample_trace.py:437-444). Host pointers. */
 int bfb_sampler_init(bfb_handle h, const bfb_sampler_cfg *cfg, int64_t C, const double *x0,
                      const double *step0, const double *var0, const double *mean0);
+/* restore every chain to its state right after bfb_sampler_init (device-to-device copies only) */
+int bfb_sampler_reset(bfb_handle h);
 /* advance every chain by n_iter iterations; out pointers in `loc`; total_tree_size (host, may be NULL) =
  * sum over chains and iterations of tree_size = leapfrog steps performed in trees. */
 int bfb_sampler_run(bfb_handle h, int sampler, int32_t n_iter, const bfb_run_out *out, int loc,
