@@ -253,13 +253,14 @@ class Handle:
         nc, n = self.n_chain, self.n
         if out_ptrs is None:
             want = fields if fields is not None else ('samples',) + FLOAT_STATS + INT_STATS
+            from . import _pinned
             for k in want:
                 if k == 'samples':
-                    res[k] = np.empty((nc, n_iter, n))
+                    res[k] = _pinned.empty((nc, n_iter, n))
                 elif k in FLOAT_STATS:
-                    res[k] = np.empty((nc, n_iter))
+                    res[k] = _pinned.empty((nc, n_iter))
                 else:
-                    res[k] = np.empty((nc, n_iter), np.int32)
+                    res[k] = _pinned.empty((nc, n_iter), np.int32)
                 setattr(ro, k, res[k].ctypes.data)
             loc = BFB_HOST
         else:

@@ -111,6 +111,12 @@ struct bfb_context {
     ChainState cs;
     std::vector<void *> chain_allocs;
     std::vector<void *> chain_snapshot;
+    cudaStream_t copy_stream;  // device-to-host output pipeline of bfb_sampler_run
+    cudaEvent_t ev_k[2], ev_c[2];
+    void *stage[2];
+    size_t stage_len[2];
+    double *gstack;            // deep NUTS stack levels of the multi-chain kernel (L2 resident)
+    size_t gstack_len;
     // fit
     FitState *fit;
 };

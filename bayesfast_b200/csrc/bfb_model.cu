@@ -56,6 +56,11 @@ extern "C" int bfb_create(int device, bfb_handle *out)
     h->has_model = false;
     h->has_chains = false;
     h->fit = nullptr;
+    h->gstack = nullptr;
+    h->gstack_len = 0;
+    h->copy_stream = nullptr;
+    h->stage[0] = h->stage[1] = nullptr;
+    h->stage_len[0] = h->stage_len[1] = 0;
     memset(&h->dm, 0, sizeof(h->dm));
     memset(&h->cs, 0, sizeof(h->cs));
     BFB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
@@ -76,6 +81,12 @@ extern "C" int bfb_destroy(bfb_handle h)
     bfb_free_list(h->model_allocs);
     bfb_free_list(h->chain_allocs);
     bfb_fit_free(h);
+    if (h->gstack) cudaFree(h->gstack);
+    for (int i = 0; i < 2; ++i) if (h->stage[i]) cudaFree(h->stage[i]);
+    if (h->copy_stream) {
+        for (int i = 0; i < 2; ++i) { cudaEventDestroy(h->ev_k[i]); cudaEventDestroy(h->ev_c[i]); }
+        cudaStreamDestroy(h->copy_stream);
+    }
     cudaEventDestroy(h->ev0);
     cudaEventDestroy(h->ev1);
     if (h->own_stream) cudaStreamDestroy(h->stream);

@@ -14,6 +14,9 @@
 #include "bfb_common.cuh"
 #include "bfb_eval.cuh"
 #include <cstring>
+#include <cstdlib>
+
+int bfb_launch_nuts_fast(bfb_context *h, const bfb_run_out &o, int n_iter);   // bfb_sampler_fast.cu
 
 struct RunOutDev {
     bfb_run_out o;
@@ -487,45 +490,16 @@ static int launch_sampler(bfb_context *h, const RunOutDev &out, int wpb)
     return BFB_OK;
 }
 
-extern "C" int bfb_sampler_run(bfb_handle h, int sampler, int32_t n_iter, const bfb_run_out *out, int loc,
-                               int64_t *total_tree_size)
+// launch the kernel(s) that advance every chain by n_iter iterations, outputs (device pointers) laid out [C, n_iter(, n)]
+static int launch_run(bfb_context *h, int sampler, int n_iter, const bfb_run_out &dev_out)
 {
-    BFB_REQUIRE(h && h->has_model && h->has_chains, BFB_ERR_STATE, "bfb_sampler_run: call bfb_sampler_init first");
-    BFB_REQUIRE(sampler == BFB_NUTS || sampler == BFB_HMC, BFB_ERR_ARG, "unknown sampler %d", sampler);
-    BFB_REQUIRE(n_iter > 0 && out, BFB_ERR_ARG, "bfb_sampler_run: bad arguments");
-    BFB_REQUIRE(sampler != BFB_HMC || h->scfg.n_int_step > 0, BFB_ERR_ARG, "n_int_step must be positive");
-    BFB_CUDA(cudaSetDevice(h->device));
-    const int64_t C = h->cs.C;
-    const int n = h->n;
     RunOutDev od;
     od.n_iter = n_iter;
-    memset(&od.o, 0, sizeof(od.o));
-    std::vector<std::pair<void *, std::pair<void *, size_t>>> copies;   // dev -> (host, bytes)
-    auto prep = [&](void *user, size_t bytes, void **slot) -> int {
-        if (!user) { *slot = nullptr; return BFB_OK; }
-        if (loc == BFB_DEVICE) { *slot = user; return BFB_OK; }
-        void *d = nullptr;
-        BFB_CUDA(cudaMalloc(&d, bytes));
-        copies.push_back({d, {user, bytes}});
-        *slot = d;
-        return BFB_OK;
-    };
-    int rc;
-    const size_t S = (size_t)C * n_iter;
-    if ((rc = prep(out->samples, sizeof(double) * S * n, (void **)&od.o.samples)) ||
-        (rc = prep(out->logp, sizeof(double) * S, (void **)&od.o.logp)) ||
-        (rc = prep(out->energy, sizeof(double) * S, (void **)&od.o.energy)) ||
-        (rc = prep(out->mean_tree_accept, sizeof(double) * S, (void **)&od.o.mean_tree_accept)) ||
-        (rc = prep(out->step_size, sizeof(double) * S, (void **)&od.o.step_size)) ||
-        (rc = prep(out->step_size_bar, sizeof(double) * S, (void **)&od.o.step_size_bar)) ||
-        (rc = prep(out->energy_change, sizeof(double) * S, (void **)&od.o.energy_change)) ||
-        (rc = prep(out->max_energy_change, sizeof(double) * S, (void **)&od.o.max_energy_change)) ||
-        (rc = prep(out->tree_depth, sizeof(int32_t) * S, (void **)&od.o.tree_depth)) ||
-        (rc = prep(out->tree_size, sizeof(int32_t) * S, (void **)&od.o.tree_size)) ||
-        (rc = prep(out->diverging, sizeof(int32_t) * S, (void **)&od.o.diverging)))
-        return rc;
-    BFB_CUDA(cudaMemsetAsync(h->cs.tree_total, 0, sizeof(unsigned long long), h->stream));
-    BFB_CUDA(cudaEventRecord(h->ev0, h->stream));
+    od.o = dev_out;
+    int rc = BFB_OK, fast_rc = 1;
+    if (sampler == BFB_NUTS && !getenv("BFB200_FORCE_GENERIC")) fast_rc = bfb_launch_nuts_fast(h, od.o, n_iter);
+    if (fast_rc < 0) return fast_rc;
+    if (fast_rc == 0) return BFB_OK;
     const int wpb = 4;
     const int npl = h->np / 32;
     if (sampler == BFB_NUTS) {
@@ -543,16 +517,100 @@ extern "C" int bfb_sampler_run(bfb_handle h, int sampler, int32_t n_iter, const 
         default: rc = launch_sampler<4, BFB_HMC>(h, od, 2); break;
         }
     }
-    if (rc) return rc;
-    BFB_CUDA(cudaEventRecord(h->ev1, h->stream));
-    for (auto &cp : copies)
-        BFB_CUDA(cudaMemcpyAsync(cp.second.first, cp.first, cp.second.second, cudaMemcpyDeviceToHost, h->stream));
+    return rc;
+}
+
+// byte size of one (chain, iteration) record of output field f (order of bfb_run_out)
+static size_t field_bytes(int f, int n) { return f == 0 ? sizeof(double) * n : (f <= 7 ? sizeof(double) : sizeof(int32_t)); }
+
+extern "C" int bfb_sampler_run(bfb_handle h, int sampler, int32_t n_iter, const bfb_run_out *out, int loc,
+                               int64_t *total_tree_size)
+{
+    BFB_REQUIRE(h && h->has_model && h->has_chains, BFB_ERR_STATE, "bfb_sampler_run: call bfb_sampler_init first");
+    BFB_REQUIRE(sampler == BFB_NUTS || sampler == BFB_HMC, BFB_ERR_ARG, "unknown sampler %d", sampler);
+    BFB_REQUIRE(n_iter > 0 && out, BFB_ERR_ARG, "bfb_sampler_run: bad arguments");
+    BFB_REQUIRE(sampler != BFB_HMC || h->scfg.n_int_step > 0, BFB_ERR_ARG, "n_int_step must be positive");
+    BFB_CUDA(cudaSetDevice(h->device));
+    const int64_t C = h->cs.C;
+    const int n = h->n;
+    void *const user[11] = {out->samples, out->logp, out->energy, out->mean_tree_accept, out->step_size, out->step_size_bar,
+                            out->energy_change, out->max_energy_change, out->tree_depth, out->tree_size, out->diverging};
+    BFB_CUDA(cudaMemsetAsync(h->cs.tree_total, 0, sizeof(unsigned long long), h->stream));
     unsigned long long tt = 0;
+    if (loc == BFB_DEVICE) {
+        BFB_CUDA(cudaEventRecord(h->ev0, h->stream));
+        int rc = launch_run(h, sampler, n_iter, *out);
+        if (rc) return rc;
+        BFB_CUDA(cudaEventRecord(h->ev1, h->stream));
+    } else {
+        // Host outputs: the run is cut into chunks of iterations; chunk k's kernel writes a device staging buffer while
+        // chunk k-1 is copied to the caller's arrays on a second stream (strided 2-D copies: the host layout is
+        // chain-major).  With pinned host memory (bfb_host_alloc) the copies are hidden behind the kernels.
+        int n_chunks = n_iter >= 512 ? 6 : (n_iter >= 128 ? 3 : 1);
+        const int K = (n_iter + n_chunks - 1) / n_chunks;
+        n_chunks = (n_iter + K - 1) / K;
+        size_t rec = 0;
+        for (int f = 0; f < 11; ++f) if (user[f]) rec += field_bytes(f, n);
+        const size_t need = rec * (size_t)C * K;
+        if (!h->copy_stream) {
+            BFB_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+            for (int i = 0; i < 2; ++i) { BFB_CUDA(cudaEventCreateWithFlags(&h->ev_k[i], cudaEventDisableTiming));
+                                          BFB_CUDA(cudaEventCreateWithFlags(&h->ev_c[i], cudaEventDisableTiming)); }
+        }
+        for (int i = 0; i < 2; ++i) {
+            if (h->stage_len[i] < need) {
+                if (h->stage[i]) cudaFree(h->stage[i]);
+                h->stage[i] = nullptr; h->stage_len[i] = 0;
+                BFB_CUDA(cudaMalloc(&h->stage[i], need ? need : 8));
+                h->stage_len[i] = need;
+            }
+        }
+        BFB_CUDA(cudaEventRecord(h->ev0, h->stream));
+        for (int k = 0; k < n_chunks; ++k) {
+            const int it_begin = k * K, Kk = (it_begin + K <= n_iter) ? K : n_iter - it_begin;
+            const int sb = k & 1;
+            if (k >= 2) BFB_CUDA(cudaStreamWaitEvent(h->stream, h->ev_c[sb], 0));   // staging buffer free again
+            void *dptr[11];
+            char *base = (char *)h->stage[sb];
+            for (int f = 0; f < 11; ++f) {
+                dptr[f] = nullptr;
+                if (user[f]) { dptr[f] = base; base += field_bytes(f, n) * (size_t)C * Kk; }
+            }
+            bfb_run_out dev = {(double *)dptr[0], (double *)dptr[1], (double *)dptr[2], (double *)dptr[3], (double *)dptr[4],
+                               (double *)dptr[5], (double *)dptr[6], (double *)dptr[7], (int32_t *)dptr[8],
+                               (int32_t *)dptr[9], (int32_t *)dptr[10]};
+            int rc = launch_run(h, sampler, Kk, dev);
+            if (rc) return rc;
+            BFB_CUDA(cudaEventRecord(h->ev_k[sb], h->stream));
+            BFB_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_k[sb], 0));
+            for (int f = 0; f < 11; ++f) {
+                if (!user[f]) continue;
+                const size_t fb = field_bytes(f, n);
+                BFB_CUDA(cudaMemcpy2DAsync((char *)user[f] + fb * (size_t)it_begin, fb * (size_t)n_iter, dptr[f], fb * (size_t)Kk,
+                                           fb * (size_t)Kk, (size_t)C, cudaMemcpyDeviceToHost, h->copy_stream));
+            }
+            BFB_CUDA(cudaEventRecord(h->ev_c[sb], h->copy_stream));
+        }
+        BFB_CUDA(cudaEventRecord(h->ev1, h->stream));
+        BFB_CUDA(cudaStreamSynchronize(h->copy_stream));
+    }
     BFB_CUDA(cudaMemcpyAsync(&tt, h->cs.tree_total, sizeof(tt), cudaMemcpyDeviceToHost, h->stream));
     BFB_CUDA(cudaStreamSynchronize(h->stream));
     BFB_CUDA(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
-    for (auto &cp : copies) cudaFree(cp.first);
     if (total_tree_size) *total_tree_size = (int64_t)tt;
+    return BFB_OK;
+}
+
+// pinned host memory for the outputs of bfb_sampler_run (asynchronous, full-speed device-to-host copies)
+extern "C" int bfb_host_alloc(size_t bytes, void **ptr)
+{
+    BFB_REQUIRE(ptr, BFB_ERR_ARG, "bfb_host_alloc: null pointer");
+    BFB_CUDA(cudaHostAlloc(ptr, bytes ? bytes : 8, cudaHostAllocDefault));
+    return BFB_OK;
+}
+extern "C" int bfb_host_free(void *ptr)
+{
+    if (ptr) BFB_CUDA(cudaFreeHost(ptr));
     return BFB_OK;
 }
 

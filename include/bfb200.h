@@ -16,6 +16,7 @@
  */
 #ifndef BFB200_H
 #define BFB200_H
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -147,6 +148,10 @@ int bfb_sampler_reset(bfb_handle h);
  * sum over chains and iterations of tree_size = leapfrog steps performed in trees. */
 int bfb_sampler_run(bfb_handle h, int sampler, int32_t n_iter, const bfb_run_out *out, int loc,
                     int64_t *total_tree_size);
+/* page-locked host memory for the outputs of bfb_sampler_run: with it the device-to-host copies of one chunk of
+ * iterations overlap the kernel of the next chunk */
+int bfb_host_alloc(size_t bytes, void **ptr);
+int bfb_host_free(void *ptr);
 /* final adaptation state for the host-side trace objects: final_step [C,4] = log_step, log_bar, hbar, count;
  * final_var [C,n]; n_draws [C]; status [C] (0 ok, 1 non-finite logp/grad at x0, 2 non-finite start energy,
  * 3 nan in logbern); q [C,n] current position.  Host pointers, any may be NULL. */
