@@ -1,0 +1,153 @@
+"""Host-side logic of the reference-interface mirrors (no device needed)."""
+import pickle
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+
+import bayesfast_b200 as bfb
+from bayesfast_b200 import transforms as tf
+from bayesfast_b200.poly import pack_dense, unpack_dense
+from bayesfast_b200.runtime import shard_bounds
+from bayesfast_b200.sample_trace import NTrace, HTrace, TraceTuple, _get_step_size
+
+
+def test_polyconfig_and_recipe():
+    s = bfb.PolyModel('cubic-3', input_size=4, output_size=1)
+    assert [c.order for c in s.configs] == ['linear', 'quadratic', 'cubic-2', 'cubic-3']
+    assert s.n_param == 5 + 10 + 16 + 4                 # reference: poly.py:592-593
+    assert bfb.PolyModel('cubic-2', input_size=26, output_size=1).n_param == 1054
+    assert np.array_equal(s.recipe, [[0, 1, 2, 3]])
+    with pytest.raises(ValueError):
+        bfb.PolyConfig('quartic')
+    with pytest.raises(ValueError):
+        bfb.PolyModel([bfb.PolyConfig('quadratic', output_mask=[0]), bfb.PolyConfig('quadratic', output_mask=[0, 1])],
+                      input_size=3, output_size=2)
+    with pytest.raises(ValueError):
+        bfb.PolyModel([bfb.PolyConfig('linear', output_mask=[0])], input_size=3, output_size=2)   # output 1 uncovered
+    c = bfb.PolyConfig('quadratic', input_mask=[3, 1, 1], output_mask=[0])
+    assert np.array_equal(c.input_mask, [1, 3]) and c._a_shape == (3,) and c._A_shape == (1, 2, 2)
+    with pytest.raises(ValueError):
+        c._set(np.zeros(4), 0)
+    c._set(np.array([1., 2., 3.]), 0)
+    assert np.array_equal(c._coef[0], [[1., 2.], [0., 3.]])
+    with pytest.raises(ValueError):
+        s.set_bound_options(alpha=None, alpha_p=None)
+
+
+def test_pack_unpack_roundtrip(oracle):
+    rng = np.random.default_rng(0)
+    for order, n in (('linear', 5), ('quadratic', 6), ('cubic-2', 4), ('cubic-3', 7)):
+        a = rng.normal(size=bfb.PolyConfig(order, np.arange(n), [0])._a_shape)
+        dense = unpack_dense(order, a, n)
+        assert np.array_equal(dense, oracle.unpack_coef(order, a, n))
+        assert np.array_equal(pack_dense(order, dense, n), a)
+
+
+def test_transforms_match_oracle_and_reference_test(oracle):
+    # the configuration of the reference's tests/test_constraint.py:5-7
+    ranges = np.array([[-10, 10], [-5, 8], [-4, 6], [-8, 6]], float)
+    hb = np.array([[0, 0], [0, 1], [1, 0], [1, 1]], np.uint8)
+    x = np.ones(4) * 0.6
+    f, j, jj = oracle.to_original(x, ranges, hb)
+    assert np.allclose(tf.to_original(x, ranges, hb), f, rtol=1e-15)
+    assert np.allclose(tf.to_original_grad(x, ranges, hb), j, rtol=1e-15)
+    assert np.allclose(tf.to_original_grad2(x, ranges, hb), jj, rtol=1e-14)
+    eps = 1e-6                                           # analytic vs numerical, like the reference test
+    num = (tf.to_original(x + eps, ranges, hb) - tf.to_original(x - eps, ranges, hb)) / (2 * eps)
+    assert np.allclose(j, num, rtol=1e-7)
+    num2 = (tf.to_original_grad(x + eps, ranges, hb) - tf.to_original_grad(x - eps, ranges, hb)) / (2 * eps)
+    assert np.allclose(jj, num2, rtol=1e-6, atol=1e-8)
+    xo = tf.to_original(x, ranges, hb)
+    assert np.allclose(tf.from_original(xo, ranges, hb), x, rtol=1e-12)
+    assert np.allclose(oracle.from_original(xo, ranges, hb), x, rtol=1e-12)
+    assert np.allclose(tf.from_original_grad(xo, ranges, hb) * j, 1., rtol=1e-12)
+    with pytest.raises(ValueError):
+        tf.from_original(np.array([0., 0., 0., 7.]), ranges, hb)      # variable #3 out of bound
+    X = np.stack([x, 0.5 * x])
+    assert tf.to_original(X, ranges, hb).shape == (2, 4)
+
+
+def test_density_host_logic_and_pickle():
+    s = bfb.PolyModel('quadratic', input_size=3, output_size=1, input_scales=[[0, 2], [0, 2], [-1, 1]])
+    for c in s.configs:
+        c._set(np.arange(c._a_shape[0], dtype=float), 0)
+    d = bfb.Density(s, input_scales=[[-1, 1]] * 3, hard_bounds=[[1, 1], [0, 0], [1, 0]],
+                    decay_options=dict(use_decay=True, alpha=3., alpha_p=None, gamma=0.2))
+    d._mu, d._hess = np.zeros(3), np.eye(3)
+    spec = d.to_spec()
+    assert spec['use_decay'] and spec['d_alpha2'] == 9. and spec['d_gamma'] == 0.2
+    assert spec['transform_ranges'].shape == (3, 2) and spec['hard_bounds'].tolist() == [[1, 1], [0, 0], [1, 0]]
+    assert spec['input_scales'].shape == (3, 2) and not spec['use_bound']
+    x = np.array([0.1, -0.3, 0.2])
+    assert np.allclose(d.from_original(d.to_original(x)), x)
+    assert np.isclose(d.to_original_density(1., x_trans=x), 1. - np.sum(np.log(np.abs(d.to_original_grad(x)))))
+    d2 = pickle.loads(pickle.dumps(d))
+    assert d2._handle is None and np.array_equal(d2.surrogate.configs[1]._coef, s.configs[1]._coef)
+    with pytest.raises(ValueError):
+        bfb.Density(object())
+    with pytest.raises(ValueError):
+        d.set_decay_options(gamma=-1.)
+
+
+def test_from_reference_duck_typing():
+    """a stand-in with the attribute layout of a fitted reference Density / PolyModel (core/density.py, modules/poly.py)"""
+    n = 3
+    lin = SimpleNamespace(order='linear', _input_mask=np.arange(n), _output_mask=np.arange(1), _coef=np.array([[1., 2., 3., 4.]]))
+    quad = SimpleNamespace(order='quadratic', _input_mask=np.arange(n), _output_mask=np.arange(1),
+                           _coef=np.triu(np.arange(9.).reshape(1, 3, 3)[0])[None])
+    sur = SimpleNamespace(_configs=(lin, quad), _recipe=None, _scope=(0, 1), _use_bound=True, _alpha=2.5, _alpha_p=100.,
+                          _center_max=True, _input_size=n, _output_size=1, _input_scales=None, _mu=np.zeros(n),
+                          _hess=np.eye(n), _f_mu=np.array([0.5]))
+    ref = SimpleNamespace(_surrogate_list=[sur], _module_list=[object()], use_surrogate=True, _input_scales=None,
+                          _hard_bounds=False, _use_decay=False, _alpha=None, _alpha_p=150., _gamma=0.1, density_name='logp')
+    d = bfb.Density.from_reference(ref)
+    spec = d.to_spec()
+    assert spec['use_bound'] and spec['alpha'] == 2.5 and np.array_equal(spec['configs'][1]['packed'][0], [0, 1, 2, 4, 5, 8])
+    ref2 = SimpleNamespace(**{**ref.__dict__, '_module_list': [object(), object()]})
+    with pytest.raises(ValueError, match='whole module list'):
+        bfb.Density.from_reference(ref2)
+    with pytest.raises(ValueError):
+        bfb.sample(object())
+
+
+def test_trace_objects():
+    with pytest.raises(ValueError):
+        NTrace(n_iter=10, n_warmup=10)
+    with pytest.raises(NotImplementedError):
+        NTrace(metric='full')
+    with pytest.raises(ValueError):
+        NTrace(max_treedepth=0)
+    t = NTrace(n_chain=3, n_iter=6, n_warmup=2, x_0=np.zeros((3, 2)), random_generator=7)
+    cfg = t._cfg_dict(7, 5)
+    assert cfg['max_treedepth'] == 10 and cfg['chain0'] == 5 and cfg['n_warmup'] == 2 and cfg['target_accept'] == 0.8
+    assert HTrace(n_int_step=8).n_call == 1500 * 9 + 1
+    C, n_it, n = 3, 6, 2
+    rng = np.random.default_rng(0)
+    arrays = dict(samples=rng.normal(size=(C, n_it, n)), logp=rng.normal(size=(C, n_it)))
+    arrays['samples_original'], arrays['logp_original'] = arrays['samples'], arrays['logp']
+    for k in ('energy', 'mean_tree_accept', 'step_size', 'step_size_bar', 'energy_change', 'max_energy_change'):
+        arrays[k] = rng.normal(size=(C, n_it))
+    arrays['tree_depth'] = np.full((C, n_it), 2, np.int32)
+    arrays['tree_size'] = np.full((C, n_it), 3, np.int32)
+    arrays['diverging'] = np.zeros((C, n_it), np.int32)
+    final = dict(final_step=np.tile([np.log(0.3), np.log(0.25), 0.1, 4.], (C, 1)), final_var=np.ones((C, n)),
+                 step0=np.full(C, 0.5), x_0=np.zeros((C, n)))
+    tt = TraceTuple(t, arrays, final, chain0=10)
+    assert len(tt) == 3 and tt.sampler == 'NUTS' and tt.get().shape == (C * 4, n) and tt.get(return_type='logp').shape == (12,)
+    t1 = tt[1]
+    assert t1.chain_id == 11 and t1.samples.shape == (n_it, n) and t1.stats.n_warmup == 2 and t1.i_iter == 6
+    assert t1.n_call == 3 * 5 + 6 + 1 and tt.n_call == 3 * (15 + 7)
+    assert np.isclose(t1.step_size.current(False), 0.25) and np.isclose(_get_step_size(tt), 0.25 * 2**0.25)
+    assert list(t1.stats.get().keys())[2] == 'tree_depth' and len(t1.stats.get()['logp']) == 4
+    with pytest.raises(ValueError):
+        tt.get(since_iter=5)
+
+
+def test_shard_bounds():
+    for total, world in ((4096, 8), (10, 3), (2, 2), (7, 8)):
+        cover = []
+        for r in range(world):
+            lo, hi = shard_bounds(total, r, world)
+            cover += list(range(lo, hi))
+        assert cover == list(range(total))
