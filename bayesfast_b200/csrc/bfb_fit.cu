@@ -57,38 +57,34 @@ __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double
                  : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-__device__ __forceinline__ double feature_value(short4 f, const double *xrow, const double *y, int64_t row, int m)
-{
-    if (f.w == 0) {
-        // (a*b)*c with missing factors = 1: the multiplication order of _lsq_quadratic / _lsq_cubic_2 / _lsq_cubic_3
-        double a = f.x >= 0 ? xrow[f.x] : 1.;
-        double b = f.y >= 0 ? xrow[f.y] : 1.;
-        double c = f.z >= 0 ? xrow[f.z] : 1.;
-        return (a * b) * c;
-    }
-    if (f.w == 1) return y[row * m + f.x];
-    return 0.;
-}
-
+// One CTA = one 64 x 64 tile (ti <= tj) of the Gram over one chunk of rows.  Per stage of KC rows:
+//   1. the x rows are staged in shared memory with a constant-1 column appended at index n, so that a monomial with
+//      fewer than three factors needs no branch (missing factors index the 1);
+//   2. every thread owns ONE feature column of each of the two tiles (its three factor indices sit in registers for
+//      the whole kernel) and expands it for its 16 rows: (x[i0] * x[i1]) * x[i2] * w -- the multiplication order of
+//      _lsq_quadratic / _lsq_cubic_2 / _lsq_cubic_3; y columns are read from global memory;
+//   3. 4 warps (2 x 2) multiply the two 64-feature panels with DMMA m8n8k4, 32 x 32 per warp.
 __global__ void __launch_bounds__(128) gram_kernel(const double *__restrict__ x, const double *__restrict__ y,
                                                    const double *__restrict__ w, int64_t N, int n, int m,
                                                    const short4 *__restrict__ feat, int nt, int64_t rows_per_chunk,
                                                    double *__restrict__ ws)
 {
     extern __shared__ double sm[];
-    // tile (ti <= tj) from the linear upper-triangular index
     int t = blockIdx.x, ti = 0;
     while (t >= nt - ti) { t -= nt - ti; ++ti; }
     const int tj = ti + t;
     const bool diag = (ti == tj);
-    const int ldx = n + 1;
+    const int ldx = n + 2;                   // n values + the constant 1 (+1 pad)
     double *xs = sm;                         // [KC][ldx]
     double *wk = xs + KC * ldx;              // [KC]
     double *phiI = wk + KC;                  // [KC][LDP]
     double *phiJ = diag ? phiI : phiI + KC * LDP;
-    __shared__ short4 fI[TS], fJ[TS];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid < TS) { fI[tid] = feat[ti * TS + tid]; fJ[tid] = feat[tj * TS + tid]; }
+    // this thread's feature column in each tile
+    const int fcol = tid & (TS - 1), khalf = tid >> 6;          // rows khalf, khalf + 2, ...
+    const short4 fi = feat[ti * TS + fcol], fj = feat[tj * TS + fcol];
+    const int i0 = fi.x >= 0 ? fi.x : n, i1 = fi.y >= 0 ? fi.y : n, i2 = fi.z >= 0 ? fi.z : n;
+    const int j0 = fj.x >= 0 ? fj.x : n, j1 = fj.y >= 0 ? fj.y : n, j2 = fj.z >= 0 ? fj.z : n;
     const int wm = warp >> 1, wn = warp & 1;
     double acc[4][4][2];
 #pragma unroll
@@ -97,27 +93,51 @@ __global__ void __launch_bounds__(128) gram_kernel(const double *__restrict__ x,
         for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.;
     const int64_t r_begin = (int64_t)blockIdx.y * rows_per_chunk;
     const int64_t r_end = min(N, r_begin + rows_per_chunk);
+    // flat, division-free walk over the KC x n block of x (contiguous in global memory): element e = tid + 128 s
+    const int k_init = tid / n, j_init = tid - k_init * n, dk = 128 / n, dj = 128 - dk * n;
+    const int n_el = KC * n;
     for (int64_t r0 = r_begin; r0 < r_end; r0 += KC) {
         __syncthreads();
-        for (int e = tid; e < KC * n; e += 128) {
-            int k = e / n, j = e - k * n;
-            int64_t row = r0 + k;
-            xs[k * ldx + j] = (row < r_end) ? x[row * n + j] : 0.;
-        }
-        if (tid < KC) {
-            int64_t row = r0 + tid;
-            wk[tid] = (row < r_end) ? (w ? w[row] : 1.) : 0.;
+        {
+            const int64_t last = (r_end - 1 - r0) * n;          // rows past the end re-read the last row (their w is 0)
+            const double *xb = x + r0 * n;
+            int k = k_init, j = j_init;
+            for (int e = tid; e < n_el; e += 128) {
+                const int64_t src = (int64_t)k * n + j;
+                xs[k * ldx + j] = xb[src <= last + n - 1 ? src : last + j];
+                j += dj; k += dk;
+                if (j >= n) { j -= n; k += 1; }
+            }
+            if (tid < KC) {
+                xs[tid * ldx + n] = 1.;
+                wk[tid] = (r0 + tid < r_end) ? (w ? w[r0 + tid] : 1.) : 0.;
+            }
         }
         __syncthreads();
-        for (int e = tid; e < KC * TS; e += 128) {
-            int k = e / TS, f = e - k * TS;
-            int64_t row = r0 + k;
-            double wv = wk[k];
-            double v = (row < r_end) ? feature_value(fI[f], xs + k * ldx, y, row, m) * wv : 0.;
-            phiI[k * LDP + f] = v;
-            if (!diag) {
-                double u = (row < r_end) ? feature_value(fJ[f], xs + k * ldx, y, row, m) * wv : 0.;
-                phiJ[k * LDP + f] = u;
+        if (fi.w == 0) {
+#pragma unroll 8
+            for (int k = khalf; k < KC; k += 2) {
+                const double *xr = xs + k * ldx;
+                phiI[k * LDP + fcol] = ((xr[i0] * xr[i1]) * xr[i2]) * wk[k];
+            }
+        } else {
+            for (int k = khalf; k < KC; k += 2) {
+                const int64_t row = min(r0 + k, r_end - 1);
+                phiI[k * LDP + fcol] = (fi.w == 1 ? y[row * m + fi.x] : 0.) * wk[k];
+            }
+        }
+        if (!diag) {
+            if (fj.w == 0) {
+#pragma unroll 8
+                for (int k = khalf; k < KC; k += 2) {
+                    const double *xr = xs + k * ldx;
+                    phiJ[k * LDP + fcol] = ((xr[j0] * xr[j1]) * xr[j2]) * wk[k];
+                }
+            } else {
+                for (int k = khalf; k < KC; k += 2) {
+                    const int64_t row = min(r0 + k, r_end - 1);
+                    phiJ[k * LDP + fcol] = (fj.w == 1 ? y[row * m + fj.x] : 0.) * wk[k];
+                }
             }
         }
         __syncthreads();
@@ -366,7 +386,7 @@ extern "C" int bfb_fit_accumulate(bfb_handle h, const double *x, const double *y
         n_chunks = (int)((N + rows_per_chunk - 1) / rows_per_chunk);
         int rc = ensure_ws(fs, (size_t)n_tiles * n_chunks * TS * TS);
         if (rc) return rc;
-        size_t smem = sizeof(double) * (KC * (n + 1) + KC + 2 * KC * LDP);
+        size_t smem = sizeof(double) * (KC * (n + 2) + KC + 2 * KC * LDP);
         dim3 grid(n_tiles, n_chunks);
         gram_kernel<<<grid, 128, smem, h->stream>>>(dx, dy, dw, N, n, m, g.d_feat, g.nt, rows_per_chunk, fs->ws);
         h->launches++;
