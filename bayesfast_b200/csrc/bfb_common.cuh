@@ -115,6 +115,9 @@ struct bfb_context {
     cudaEvent_t ev_k[2], ev_c[2];
     void *stage[2];
     size_t stage_len[2];
+    int *queue;                // work queue of the multi-chain kernel
+    size_t queue_len;
+    int64_t iters_done;        // iterations completed by every chain since bfb_sampler_init / reset
     double *gstack;            // deep NUTS stack levels of the multi-chain kernel (L2 resident)
     size_t gstack_len;
     // fit

@@ -59,6 +59,9 @@ extern "C" int bfb_create(int device, bfb_handle *out)
     h->gstack = nullptr;
     h->gstack_len = 0;
     h->copy_stream = nullptr;
+    h->queue = nullptr;
+    h->queue_len = 0;
+    h->iters_done = 0;
     h->stage[0] = h->stage[1] = nullptr;
     h->stage_len[0] = h->stage_len[1] = 0;
     memset(&h->dm, 0, sizeof(h->dm));
@@ -82,6 +85,7 @@ extern "C" int bfb_destroy(bfb_handle h)
     bfb_free_list(h->chain_allocs);
     bfb_fit_free(h);
     if (h->gstack) cudaFree(h->gstack);
+    if (h->queue) cudaFree(h->queue);
     for (int i = 0; i < 2; ++i) if (h->stage[i]) cudaFree(h->stage[i]);
     if (h->copy_stream) {
         for (int i = 0; i < 2; ++i) { cudaEventDestroy(h->ev_k[i]); cudaEventDestroy(h->ev_c[i]); }

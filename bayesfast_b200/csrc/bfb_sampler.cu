@@ -398,6 +398,7 @@ extern "C" int bfb_sampler_reset(bfb_handle h)
     auto arrs = state_arrays(h->cs);
     for (size_t i = 0; i < arrs.size(); ++i)
         BFB_CUDA(cudaMemcpyAsync(arrs[i].first, h->chain_snapshot[i], arrs[i].second, cudaMemcpyDeviceToDevice, h->stream));
+    h->iters_done = 0;
     return BFB_OK;
 }
 
@@ -473,6 +474,7 @@ extern "C" int bfb_sampler_init(bfb_handle h, const bfb_sampler_cfg *cfg, int64_
     }
     BFB_CUDA(cudaStreamSynchronize(h->stream));
     h->has_chains = true;
+    h->iters_done = 0;
     return BFB_OK;
 }
 
@@ -541,6 +543,7 @@ extern "C" int bfb_sampler_run(bfb_handle h, int sampler, int32_t n_iter, const 
         BFB_CUDA(cudaEventRecord(h->ev0, h->stream));
         int rc = launch_run(h, sampler, n_iter, *out);
         if (rc) return rc;
+        h->iters_done += n_iter;
         BFB_CUDA(cudaEventRecord(h->ev1, h->stream));
     } else {
         // Host outputs: the run is cut into chunks of iterations; chunk k's kernel writes a device staging buffer while
@@ -581,6 +584,7 @@ extern "C" int bfb_sampler_run(bfb_handle h, int sampler, int32_t n_iter, const 
                                (int32_t *)dptr[9], (int32_t *)dptr[10]};
             int rc = launch_run(h, sampler, Kk, dev);
             if (rc) return rc;
+            h->iters_done += Kk;
             BFB_CUDA(cudaEventRecord(h->ev_k[sb], h->stream));
             BFB_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_k[sb], 0));
             for (int f = 0; f < 11; ++f) {

@@ -130,28 +130,56 @@ __device__ __forceinline__ bool gany_nonpos6(double v0, double v1, double v2, do
     return (bal & gmask) != 0u;
 }
 
-// shared memory per chain, in doubles: XX (2 NP) | DD (NP) | TL q,p,g | TR q,p,g | PS | PQ | PG | PB | stack levels
-// | per-level scalars [4][10]: weight mantissa, weight exponent, proposal energy, proposal logp
-__host__ __device__ inline int chain_smem_doubles(int NP, int LS) { return (13 + 5 * LS) * NP + 40; }
+// shared memory per chain, in doubles: XX (2 NP) | DD (NP) | TL q,p,g | TR q,p,g | PS | PB | stack levels (pl, pr, psum)
+// | per-level scalars [5][10]: weight mantissa, weight exponent, proposal energy, proposal logp, proposal slot
+__host__ __device__ inline int chain_smem_doubles(int NP, int LS) { return (11 + 3 * LS) * NP + 50; }
+#define BFB_NSLOT 12   // proposal slots per chain: tree proposal + one per pending subtree (<= L - 1) + the current one
 
 template <int G, int D, bool HAS_C2, int NK, int MB>
 __global__ void __launch_bounds__(32, MB) nuts_multi_kernel(DevModel M, bfb_sampler_cfg cfg, ChainState st, RunOutDevF out,
-                                                        int L, int LS, double *__restrict__ gstack)
+                                                            int L, int LS, double *__restrict__ gstack,
+                                                            double *__restrict__ gprop, int base_iter, int chunk_iters,
+                                                            int n_groups, int n_units, int *__restrict__ queue)
 {
     constexpr int CW = 32 / G;          // chains per warp
     constexpr int NP = G * D;           // padded dimension (16 or 32)
     constexpr int H2 = D / 2;           // 16-byte pairs per lane
     extern __shared__ double smem[];
     const int lane = threadIdx.x, gi = lane / G, lg = lane % G;
-    const int64_t c_raw = (int64_t)blockIdx.x * CW + gi;
+    // Persistent warps + ready ring.  A unit = (group of CW chains, chunk of `chunk_iters` iterations).  queue[0] = head,
+    // queue[1] = tail, queue[2 .. 2 + n_groups) = chunks finished per group, then ring[n_units]: the ids of the groups
+    // whose next chunk can start (initially every group once; a group is appended again when one of its chunks
+    // completes).  Workers pop ready groups FIFO, so nobody waits for a particular predecessor and the SMs stay full
+    // until the end of the launch instead of running 1.73 waves of whole-run blocks (4096 chains).
+    volatile int *qv = queue;
+    volatile int *ring = queue + 2 + n_groups;
+#pragma unroll 1
+    for (;;) {
+    int idx = 0, group = 0;
+    if (lane == 0) {
+        idx = atomicAdd(queue, 1);
+        if (idx < n_units) { while ((group = ring[idx]) < 0) __nanosleep(100); }
+    }
+    idx = __shfl_sync(BFB_FULL, idx, 0);
+    if (idx >= n_units) break;
+    group = __shfl_sync(BFB_FULL, group, 0);
+    __threadfence();
+    const int chunk = qv[2 + group];
+    const int it_lo = chunk * chunk_iters;
+    const int it_hi = min(out.n_iter, it_lo + chunk_iters);
+    const int64_t c_raw = (int64_t)group * CW + gi;
     const bool exists = c_raw < st.C;
     const int64_t c = exists ? c_raw : st.C - 1;
     const int n = NK > 0 ? NK : M.n;
     double *csm = smem + (size_t)gi * chain_smem_doubles(NP, LS);
     double2 *XX = reinterpret_cast<double2 *>(csm);
     double *DD = csm + 2 * NP;
-    const int oTL = 3 * NP, oTR = 6 * NP, oPS = 9 * NP, oPQ = 10 * NP, oPG = 11 * NP, oPB = 12 * NP, oST = 13 * NP;
-    double *gst = gstack + (size_t)c_raw * (size_t)(L > LS ? L - LS : 0) * 5 * NP;   // deep stack levels (L2 resident)
+    const int oTL = 3 * NP, oTR = 6 * NP, oPS = 9 * NP, oPB = 10 * NP, oST = 11 * NP;
+    double *ssc = csm + (11 + 3 * LS) * NP;
+    double *gst = gstack + (size_t)c_raw * (size_t)(L > LS ? L - LS : 0) * 3 * NP;   // deep stack levels (L2 resident)
+    // proposals (q, grad) are written once, at the leaf, into a slot of an L2-resident pool and are afterwards only
+    // referred to by their slot index: merges move no vectors.  Same thread writes and reads a given element.
+    double *gpr = gprop + (size_t)c * BFB_NSLOT * 2 * NP;
 
     // ---- vector access: lane owns dims j = r2*2G + 2*lg + e ----
     auto jdim = [&](int r) { return (r >> 1) * 2 * G + 2 * lg + (r & 1); };
@@ -163,54 +191,41 @@ __global__ void __launch_bounds__(32, MB) nuts_multi_kernel(DevModel M, bfb_samp
 #define VST(base, src)                                                                      \
     _Pragma("unroll") for (int r2_ = 0; r2_ < H2; ++r2_)                                    \
         reinterpret_cast<double2 *>(base)[r2_ * G + lg] = make_double2(src[2 * r2_], src[2 * r2_ + 1]);
-#define VSTP(pred, base, src) if (pred) { VST(base, src) }
 
-    double lin[D], mu[D];
-#pragma unroll
-    for (int r = 0; r < D; ++r) { lin[r] = M.lin[jdim(r)]; mu[r] = M.use_bound ? M.mu[jdim(r)] : 0.; }
     const double c0 = M.c0[0];
     const double alpha = M.alpha, alpha2 = M.use_bound ? M.alpha * M.alpha : INFINITY;
-    const double f_mu = M.use_bound ? M.f_mu[0] : 0.;
 
-    // ---- chain state ----
+    // ---- chain state (adaptation scalars stay in global memory: they are touched once per iteration) ----
     const size_t vb = (size_t)c * M.np;
-    double q[D], p[D], g[D], var[D], inv_std[D];
+    double q[D], p[D], g[D], var[D];
 #pragma unroll
     for (int r = 0; r < D; ++r) {
         const int j = jdim(r);
-        q[r] = st.q[vb + j]; g[r] = st.g[vb + j]; var[r] = st.var[vb + j];
-        inv_std[r] = 1. / sqrt(var[r]); p[r] = 0.;
+        q[r] = st.q[vb + j]; g[r] = st.g[vb + j]; var[r] = st.var[vb + j]; p[r] = 0.;
     }
     RngF rng;
     rng.seed = cfg.seed; rng.chain = (uint64_t)(cfg.chain0 + c); rng.cached = ~0ull;
     int64_t t = st.t_draw[c];
-    const int64_t it0 = st.iter[c];
-    double logp_q = st.logp[c], fg_n = st.fg_n[c], bg_n = st.bg_n[c];
-    double log_step = st.log_step[c], log_bar = st.log_bar[c], hbar = st.hbar[c];
-    const double mu_da = st.mu_da[c];
-    int64_t count = st.count[c], n_samples = st.n_samples[c], previous_update = st.previous_update[c];
-    int adapt_window = st.adapt_window[c];
+    const int it0 = base_iter;                 // iterations done before this launch (same for every chain)
+    double logp_q = st.logp[c];
     int status = exists ? st.status[c] : 9;
-    unsigned long long tree_total = 0;
-    bool done = (status != 0) || out.n_iter <= 0;
-    int it = 0;
+    unsigned tree_total = 0;
+    bool done = (status != 0) || it_lo >= it_hi;
+    int it = it_lo;
 
     // transition state
-    double E0 = 0., eps = 0., step = 0., prop_E = 0., prop_lp = 0., acc_sum = 0., maxdE = 0.;
+    double E0 = 0., step = 0., prop_E = 0., prop_lp = 0., acc_sum = 0., maxdE = 0.;
     WT Wtree; Wtree.m = 1.; Wtree.k = 0;
-    int depth = 0, dir = 1, ileaf = 0, nleaf = 1, n_prop = 0, diverging = 0;
-    double Rpl[D], Rps[D], Rqp[D], Rgp[D], REp = 0., Rlpp = 0.;
+    int depth = 0, ileaf = 0, n_prop = 0, diverging = 0, prop_slot = 0, Rslot = 0;
+    unsigned freemask = 0;
+    double Rpl[D], Rps[D], REp = 0., Rlpp = 0.;
     WT RW; RW.m = 0.; RW.k = 0;
 #pragma unroll
-    for (int r = 0; r < D; ++r) Rpl[r] = Rps[r] = Rqp[r] = Rgp[r] = 0.;
+    for (int r = 0; r < D; ++r) Rpl[r] = Rps[r] = 0.;
 
-    // stack level address (shared for lvl < LS, global beyond)
     auto stack_ptr = [&](int lvl) -> double * {
-        return (lvl < LS) ? (csm + oST + lvl * 5 * NP) : (gst + (size_t)(lvl - LS) * 5 * NP);
+        return (lvl < LS) ? (csm + oST + lvl * 3 * NP) : (gst + (size_t)(lvl - LS) * 3 * NP);
     };
-    // per-level scalars of the pending left subtrees (L <= 10 on this path); every lane of a chain writes the
-    // same value and later reads back what it wrote itself, so no synchronisation is needed
-    double *ssc = csm + (13 + 5 * LS) * NP;
 
     // ---- start of an iteration: base_hmc.py:62-80, Tree.__init__ nuts.py:27-43 ----
     auto start_iteration = [&](bool pred) {
@@ -218,7 +233,7 @@ __global__ void __launch_bounds__(32, MB) nuts_multi_kernel(DevModel M, bfb_samp
 #pragma unroll
         for (int r = 0; r < D; ++r) {
             const int j = jdim(r);
-            p0[r] = (j < n) ? inv_std[r] * bfb_draw_normal(rng.seed, rng.chain, (uint64_t)(t + j)) : 0.;
+            p0[r] = (j < n) ? bfb_draw_normal(rng.seed, rng.chain, (uint64_t)(t + j)) / sqrt(var[r]) : 0.;
             part = fma(p0[r], var[r] * p0[r], part);
         }
         const double ke = gsum<G>(part);
@@ -227,10 +242,13 @@ __global__ void __launch_bounds__(32, MB) nuts_multi_kernel(DevModel M, bfb_samp
             E0 = 0.5 * ke - logp_q;
             if (!isfinite(E0)) { status = 2; done = true; }
             const bool warm = (it0 + it) < cfg.n_warmup;
-            eps = warm ? exp(log_step) : exp(log_bar);
+            const double eps = warm ? exp(st.log_step[c]) : exp(st.log_bar[c]);
+            step = eps;
             VST(csm + oTL, q) VST(csm + oTL + NP, p0) VST(csm + oTL + 2 * NP, g)
             VST(csm + oTR, q) VST(csm + oTR + NP, p0) VST(csm + oTR + 2 * NP, g)
-            VST(csm + oPS, p0) VST(csm + oPQ, q) VST(csm + oPG, g)
+            VST(csm + oPS, p0)
+            VST(gpr, q) VST(gpr + NP, g)                       // slot 0 = the starting point
+            prop_slot = 0; freemask = ((1u << BFB_NSLOT) - 1u) & ~1u;
             prop_E = E0; prop_lp = logp_q; Wtree.m = 1.; Wtree.k = 0; acc_sum = 0.; maxdE = 0.;
             depth = 0; n_prop = 0; diverging = 0;
         }
@@ -240,12 +258,12 @@ __global__ void __launch_bounds__(32, MB) nuts_multi_kernel(DevModel M, bfb_samp
         const double ud = rng_uniform(rng, t);
         if (pred) {
             t += 1;
-            dir = (ud < 0.5) ? 1 : -1;       // log(u) < log(0.5) on the draw grid of bfb_rng.h
-            const double *src = csm + (dir > 0 ? oTR : oTL);
+            const bool right = ud < 0.5;                     // log(u) < log(0.5) on the draw grid of bfb_rng.h
+            const double *src = csm + (right ? oTR : oTL);
             VLD(q, src) VLD(p, src + NP) VLD(g, src + 2 * NP)
             VST(csm + oPB, p)
-            step = dir > 0 ? eps : -eps;
-            ileaf = 0; nleaf = 1 << depth;
+            step = right ? fabs(step) : -fabs(step);
+            ileaf = 0;
         }
     };
 
@@ -257,27 +275,27 @@ __global__ void __launch_bounds__(32, MB) nuts_multi_kernel(DevModel M, bfb_samp
         const bool live = !done;
         // ================= leapfrog: integration.py:68-95 =================
         const double dt = 0.5 * step;
-        double ph[D], x[D], x2[D], dd[D];
+        double ph[D], x[D];
 #pragma unroll
         for (int r = 0; r < D; ++r) {
             ph[r] = fma(dt, g[r], p[r]);
             x[r] = fma(step, var[r] * ph[r], q[r]);
         }
-        double gn[D], hd[D], fp = 0., beta2 = 0., ff0 = 0.;
+        double gn[D], fp = 0., ke2 = 0.;
         bool outside = false;
         double beta = 0., d0[D], hd0[D];
 #pragma unroll 1
         for (int pass = 0; pass < 2; ++pass) {
             // pass 0: polynomial at the new point; pass 1 (only if some chain left the ellipsoid): at its projection
-#pragma unroll
-            for (int r = 0; r < D; ++r) { x2[r] = x[r] * x[r]; dd[r] = x[r] - mu[r]; }
             __syncwarp();
 #pragma unroll
             for (int r2 = 0; r2 < H2; ++r2) {
                 const int j0 = r2 * 2 * G + 2 * lg;
-                XX[j0] = make_double2(x[2 * r2], x2[2 * r2]);
-                XX[j0 + 1] = make_double2(x[2 * r2 + 1], x2[2 * r2 + 1]);
-                reinterpret_cast<double2 *>(DD)[r2 * G + lg] = make_double2(dd[2 * r2], dd[2 * r2 + 1]);
+                const double xa = x[2 * r2], xb = x[2 * r2 + 1];
+                XX[j0] = make_double2(xa, xa * xa);
+                XX[j0 + 1] = make_double2(xb, xb * xb);
+                const double2 mu2 = M.use_bound ? __ldg(reinterpret_cast<const double2 *>(M.mu) + r2 * G + lg) : make_double2(0., 0.);
+                reinterpret_cast<double2 *>(DD)[r2 * G + lg] = make_double2(xa - mu2.x, xb - mu2.y);
             }
             __syncwarp();
             double y[D], tt[D], u[D], hh[D];
@@ -312,31 +330,34 @@ __global__ void __launch_bounds__(32, MB) nuts_multi_kernel(DevModel M, bfb_samp
             double gg[D];
 #pragma unroll
             for (int r = 0; r < D; ++r) {
-                gg[r] = lin[r] + y[r];
-                fpart = fma(lin[r], x[r], fpart);
+                const double lin = __ldg(M.lin + jdim(r));
+                const double dr = x[r] - (M.use_bound ? __ldg(M.mu + jdim(r)) : 0.);
+                gg[r] = lin + y[r];
+                fpart = fma(lin, x[r], fpart);
                 fpart = fma(0.5 * x[r], y[r], fpart);
-                if (HAS_C2) { gg[r] += fma(2. * x[r], tt[r], u[r]); fpart = fma(x2[r], tt[r], fpart); }
-                bpart = fma(dd[r], hh[r], bpart);
+                if (HAS_C2) { gg[r] += fma(2. * x[r], tt[r], u[r]); fpart = fma(x[r] * x[r], tt[r], fpart); }
+                bpart = fma(dr, hh[r], bpart);
             }
             if (pass == 0) {
                 double pn_part = 0.;
 #pragma unroll
                 for (int r = 0; r < D; ++r) {
-                    gn[r] = gg[r]; hd[r] = hh[r];
+                    gn[r] = gg[r];
                     const double pn = fma(dt, gg[r], ph[r]);
                     pn_part = fma(pn, var[r] * pn, pn_part);
                 }
                 double zz = 0.;
                 gsum4<G>(pn_part, bpart, fpart, zz, lane);
-                fp = fpart; beta2 = bpart; ff0 = pn_part;      // ff0 temporarily holds 2*KE
-                outside = live && (beta2 > alpha2);
+                fp = fpart; ke2 = pn_part;
+                outside = live && (bpart > alpha2);
                 if (!__any_sync(BFB_FULL, outside)) break;
                 // PolyModel._fj_bound, poly.py:480-503: project onto the ellipsoid and evaluate there
-                beta = sqrt(beta2);
+                beta = sqrt(bpart);
 #pragma unroll
                 for (int r = 0; r < D; ++r) {
-                    d0[r] = dd[r]; hd0[r] = hh[r];
-                    if (outside) x[r] = (jdim(r) < n) ? (alpha * x[r] + (beta - alpha) * mu[r]) / beta : 0.;
+                    const double mur = M.use_bound ? __ldg(M.mu + jdim(r)) : 0.;
+                    d0[r] = x[r] - mur; hd0[r] = hh[r];
+                    if (outside) x[r] = (jdim(r) < n) ? (alpha * x[r] + (beta - alpha) * mur) / beta : 0.;
                 }
             } else {
                 double jd_part = 0.;
@@ -344,26 +365,25 @@ __global__ void __launch_bounds__(32, MB) nuts_multi_kernel(DevModel M, bfb_samp
                 for (int r = 0; r < D; ++r) jd_part = fma(gg[r], d0[r], jd_part);
                 double zz = 0., z2 = 0.;
                 gsum4<G>(fpart, jd_part, zz, z2, lane);
+                double pn_part = 0.;
                 if (outside) {
+                    const double f_mu = M.f_mu[0];
                     const double f0 = c0 + fpart;
-                    const double s = (f0 - f_mu) / alpha - jd_part / beta;
-                    double pn_part = 0.;
+                    const double sfac = (f0 - f_mu) / alpha - jd_part / beta;
 #pragma unroll
                     for (int r = 0; r < D; ++r) {
-                        gn[r] = gg[r] + s * (hd0[r] / beta);
+                        gn[r] = gg[r] + sfac * (hd0[r] / beta);
                         const double pn = fma(dt, gn[r], ph[r]);
                         pn_part = fma(pn, var[r] * pn, pn_part);
                     }
                     fp = (beta * f0 - (beta - alpha) * f_mu) / alpha - c0;     // so that logp = c0 + fp below
-                    pn_part = gsum<G>(pn_part);
-                    ff0 = pn_part;
-                } else {
-                    (void)gsum<G>(0.);      // keep the warp's shuffles aligned
                 }
+                pn_part = gsum<G>(pn_part);
+                if (outside) ke2 = pn_part;
             }
         }
         const double lp = c0 + fp;
-        const double E = 0.5 * ff0 - lp;
+        const double E = 0.5 * ke2 - lp;
         if (live) {
 #pragma unroll
             for (int r = 0; r < D; ++r) {
@@ -385,8 +405,12 @@ __global__ void __launch_bounds__(32, MB) nuts_multi_kernel(DevModel M, bfb_samp
         if (live && !div_now) {
             acc_sum += wt_min1(wl);
 #pragma unroll
-            for (int r = 0; r < D; ++r) { Rpl[r] = p[r]; Rps[r] = p[r]; Rqp[r] = q[r]; Rgp[r] = g[r]; }
+            for (int r = 0; r < D; ++r) { Rpl[r] = p[r]; Rps[r] = p[r]; }
             RW = wl; REp = E; Rlpp = lp;
+            Rslot = __ffs(freemask) - 1;
+            freemask &= ~(1u << Rslot);
+            double *slot = gpr + (size_t)Rslot * 2 * NP;
+            VST(slot, q) VST(slot + NP, g)
         }
         if (div_now) diverging = 1;
         // ================= merges: Tree._build_subtree, nuts.py:134-178 =================
@@ -394,7 +418,8 @@ __global__ void __launch_bounds__(32, MB) nuts_multi_kernel(DevModel M, bfb_samp
         bool need = live && !div_now && ((ileaf >> lvl) & 1);
 #pragma unroll 1
         while (__any_sync(BFB_FULL, need)) {
-            const double *sp = stack_ptr(need ? lvl : 0);
+            const int lv = need ? lvl : 0;
+            const double *sp = stack_ptr(lv);
             double T1pl[D], T1pr[D], T1ps[D];
             VLD(T1pl, sp) VLD(T1pr, sp + NP) VLD(T1ps, sp + 2 * NP)
             double v0 = 0., v1 = 0., v2 = 0., v3 = 0., v4 = 0., v5 = 0.;
@@ -413,11 +438,14 @@ __global__ void __launch_bounds__(32, MB) nuts_multi_kernel(DevModel M, bfb_samp
             const double um = rng_uniform(rng, t);
             if (need) {
                 t += 1;
-                WT T1W; T1W.m = ssc[lvl]; T1W.k = (int)ssc[10 + lvl];
+                WT T1W; T1W.m = ssc[lv]; T1W.k = (int)ssc[10 + lv];
+                const int T1slot = (int)ssc[40 + lv];
                 const WT tot = wt_add(T1W, RW);
                 if (!wt_select(um, tot, RW)) {               // keep tree1's proposal (nuts.py:164-167)
-                    VLD(Rqp, sp + 3 * NP) VLD(Rgp, sp + 4 * NP)
-                    REp = ssc[20 + lvl]; Rlpp = ssc[30 + lvl];
+                    freemask |= 1u << Rslot;
+                    Rslot = T1slot; REp = ssc[20 + lv]; Rlpp = ssc[30 + lv];
+                } else {
+                    freemask |= 1u << T1slot;
                 }
 #pragma unroll
                 for (int r = 0; r < D; ++r) { Rpl[r] = T1pl[r]; Rps[r] = ps[r]; }
@@ -427,22 +455,23 @@ __global__ void __launch_bounds__(32, MB) nuts_multi_kernel(DevModel M, bfb_samp
             }
             need = need && !turn && ((ileaf >> lvl) & 1);
         }
-        const bool fin = live && (div_now || turn || (ileaf + 1 == nleaf));
+        const bool fin = live && (div_now || turn || (ileaf + 1 == (1 << depth)));
         const bool push = live && !fin;
         if (__any_sync(BFB_FULL, push)) {
             double *sp = stack_ptr(push ? lvl : 0);
             if (push) {
-                VST(sp, Rpl) VST(sp + NP, p) VST(sp + 2 * NP, Rps) VST(sp + 3 * NP, Rqp) VST(sp + 4 * NP, Rgp)
+                VST(sp, Rpl) VST(sp + NP, p) VST(sp + 2 * NP, Rps)
                 ssc[lvl] = RW.m; ssc[10 + lvl] = (double)RW.k; ssc[20 + lvl] = REp; ssc[30 + lvl] = Rlpp;
+                ssc[40 + lvl] = (double)Rslot;
                 ileaf += 1;
             }
         }
         // ================= end of a doubling: Tree.extend, nuts.py:45-103 =================
         if (__any_sync(BFB_FULL, fin)) {
-            bool stop = false;
             const double ue = rng_uniform(rng, t);
+            const bool right = step > 0.;
             if (fin) {
-                double *dst = csm + (dir > 0 ? oTR : oTL);
+                double *dst = csm + (right ? oTR : oTL);
                 VST(dst, q) VST(dst + NP, p) VST(dst + 2 * NP, g)
                 depth += 1;
             }
@@ -458,7 +487,7 @@ __global__ void __launch_bounds__(32, MB) nuts_multi_kernel(DevModel M, bfb_samp
                 v0 = fma(PS[r], vTL, v0); v1 = fma(PS[r], vTR, v1);
                 // nuts.py:86-98: self.p_sum is updated in place BEFORE p_sum1 / p_sum2 are formed, so the
                 // "old tree" p_sum entering them is already the total (see the oracle, bf_oracle.c tree_extend)
-                if (dir > 0) {
+                if (right) {
                     const double ps1 = PS[r] + Rpl[r], ps2 = PB[r] + Rps[r];
                     v2 = fma(ps1, vTL, v2); v3 = fma(ps1, vRpl, v3); v4 = fma(ps2, vPB, v4); v5 = fma(ps2, vp, v5);
                 } else {
@@ -471,38 +500,48 @@ __global__ void __launch_bounds__(32, MB) nuts_multi_kernel(DevModel M, bfb_samp
                 t += 1;
                 const WT tot = wt_add(Wtree, RW);
                 if (wt_select(ue, Wtree, RW)) {               // nuts.py:81-83 biased progressive: log(u) < size2 - size1
-                    VST(csm + oPQ, Rqp) VST(csm + oPG, Rgp)
-                    prop_E = REp; prop_lp = Rlpp;
+                    freemask |= 1u << prop_slot;
+                    prop_slot = Rslot; prop_E = REp; prop_lp = Rlpp;
+                } else {
+                    freemask |= 1u << Rslot;
                 }
                 Wtree = tot;
                 VST(csm + oPS, PS)
                 if (turning) turn = true;
             }
-            if (fin) stop = div_now || turn || (depth >= cfg.max_treedepth);
-            const bool iter_end = fin && stop;
+            const bool iter_end = fin && (div_now || turn || (depth >= cfg.max_treedepth));
             // ---------- end of the iteration: base_hmc.py:80-85 ----------
             if (__any_sync(BFB_FULL, iter_end)) {
                 const bool warm = (it0 + it) < cfg.n_warmup;
+                const double *slot = gpr + (size_t)(iter_end ? prop_slot : 0) * 2 * NP;
                 double qn[D], gnx[D];
-                VLD(qn, csm + oPQ) VLD(gnx, csm + oPG)
+                VLD(qn, slot) VLD(gnx, slot + NP)
                 const double accept_stat = acc_sum / (double)(n_prop > 0 ? n_prop : 1);
+                // adaptation scalars live in global memory: EVERY lane of the chain reads them first, then (after a
+                // warp barrier) lane 0 of the chain writes the updated values
+                double log_step = st.log_step[c], log_bar = st.log_bar[c];
+                const double hbar0 = st.hbar[c], mu_da = st.mu_da[c];
+                const int64_t count = st.count[c];
+                const int64_t n_samples = st.n_samples[c], previous_update = st.previous_update[c];
+                const int adapt_window = st.adapt_window[c];
+                const double fg_n = st.fg_n[c] + 1., bg_n = st.bg_n[c] + 1.;
+                __syncwarp();
                 if (iter_end) {
 #pragma unroll
                     for (int r = 0; r < D; ++r) { q[r] = qn[r]; g[r] = gnx[r]; }
                     logp_q = prop_lp;
-                    tree_total += (unsigned long long)n_prop;
+                    tree_total += (unsigned)n_prop;
                     if (warm && cfg.adapt_step_size) {      // step_size.py:31-45
                         const double cnt = (double)count;
                         const double w = 1. / (cnt + cfg.t0);
-                        hbar = ((1. - w) * hbar + w * (cfg.target_accept - accept_stat));
+                        const double hbar = ((1. - w) * hbar0 + w * (cfg.target_accept - accept_stat));
                         log_step = mu_da - hbar * sqrt(cnt) / cfg.gamma;
                         const double mk = pow(cnt, -cfg.k);
                         log_bar = mk * log_step + (1. - mk) * log_bar;
-                        count += 1;
+                        if (lg == 0) { st.hbar[c] = hbar; st.log_step[c] = log_step; st.log_bar[c] = log_bar; st.count[c] = count + 1; }
                     }
                     if (warm && cfg.adapt_metric) {         // metrics.py:186-211, Welford state kept in global memory
                         const int64_t delta = n_samples - previous_update;
-                        fg_n += 1.; bg_n += 1.;
                         const bool upd = ((delta + 1) % cfg.update_window == 0);
                         const bool swap = delta >= adapt_window;
 #pragma unroll
@@ -516,17 +555,17 @@ __global__ void __launch_bounds__(32, MB) nuts_multi_kernel(DevModel M, bfb_samp
                             od = q[r] - bgm;
                             bgm += od / bg_n;
                             bgr += 1. * od * (q[r] - bgm);
-                            if (upd && j < n) { var[r] = fgr / fg_n; inv_std[r] = 1. / sqrt(var[r]); }
+                            if (upd && j < n) var[r] = fgr / fg_n;
                             if (swap) { fgm = bgm; fgr = bgr; bgm = 0.; bgr = 0.; }
                             st.fg_mean[vb + j] = fgm; st.fg_raw[vb + j] = fgr;
                             st.bg_mean[vb + j] = bgm; st.bg_raw[vb + j] = bgr;
                         }
-                        if (swap) {
-                            fg_n = bg_n; bg_n = 10.;
-                            previous_update = n_samples;
-                            if (cfg.doubling) adapt_window *= 2;
+                        if (lg == 0) {
+                            st.fg_n[c] = swap ? bg_n : fg_n;
+                            st.bg_n[c] = swap ? 10. : bg_n;
+                            if (swap) { st.previous_update[c] = n_samples; if (cfg.doubling) st.adapt_window[c] = adapt_window * 2; }
+                            st.n_samples[c] = n_samples + 1;
                         }
-                        n_samples += 1;
                     }
                     const size_t o = (size_t)c * out.n_iter + it;
                     if (out.o.samples) {
@@ -546,8 +585,9 @@ __global__ void __launch_bounds__(32, MB) nuts_multi_kernel(DevModel M, bfb_samp
                         if (out.o.diverging) out.o.diverging[o] = diverging;
                     }
                     it += 1;
-                    if (it >= out.n_iter) done = true;
+                    if (it >= it_hi) done = true;
                 }
+                __syncwarp();      // the adaptation scalars written by lane 0 of a chain are re-read by all its lanes
                 start_iteration(iter_end && !done);
             }
             start_doubling(fin && !done);
@@ -562,14 +602,30 @@ __global__ void __launch_bounds__(32, MB) nuts_multi_kernel(DevModel M, bfb_samp
             st.q[vb + j] = q[r]; st.g[vb + j] = g[r]; st.var[vb + j] = var[r];
         }
         if (lg == 0) {
-            st.logp[c] = logp_q; st.fg_n[c] = fg_n; st.bg_n[c] = bg_n;
-            st.log_step[c] = log_step; st.log_bar[c] = log_bar; st.hbar[c] = hbar;
-            st.count[c] = count; st.n_samples[c] = n_samples; st.previous_update[c] = previous_update;
-            st.adapt_window[c] = adapt_window; st.t_draw[c] = t; st.iter[c] = it0 + it;
+            st.logp[c] = logp_q; st.t_draw[c] = t; st.iter[c] = it0 + it;
             st.status[c] = status;
-            if (tree_total) atomicAdd(st.tree_total, tree_total);
+            if (tree_total) atomicAdd(st.tree_total, (unsigned long long)tree_total);
         }
     }
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) {
+        qv[2 + group] = chunk + 1;
+        if ((chunk + 1) * chunk_iters < out.n_iter) {
+            const int ti = atomicAdd(queue + 1, 1);
+            __threadfence();
+            ring[ti] = group;
+        }
+    }
+    }   // unit loop
+}
+
+__global__ void queue_init_kernel(int *queue, int n_groups, int n_units)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) { queue[0] = 0; queue[1] = n_groups; }
+    if (i < n_groups) queue[2 + i] = 0;
+    if (i < n_units) queue[2 + n_groups + i] = (i < n_groups) ? i : -1;
 }
 
 template <int G, int D, bool HAS_C2, int NK, int MB = 8>
@@ -589,17 +645,39 @@ static int launch_multi(bfb_context *h, const bfb_run_out &o, int n_iter)
     const size_t smem = sizeof(double) * CW * chain_smem_doubles(NP, LS);
     BFB_CUDA(cudaFuncSetAttribute(nuts_multi_kernel<G, D, HAS_C2, NK, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t C = h->cs.C;
-    const size_t deep = (size_t)(L > LS ? L - LS : 0) * 5 * NP;
-    if (deep * (size_t)C > h->gstack_len) {
+    // L2-resident pools: deep stack levels (3 vectors each) followed by the proposal slots (q, grad per slot)
+    const size_t deep = (size_t)(L > LS ? L - LS : 0) * 3 * NP;
+    const size_t prop = (size_t)BFB_NSLOT * 2 * NP;
+    if ((deep + prop) * (size_t)C > h->gstack_len) {
         if (h->gstack) cudaFree(h->gstack);
         h->gstack = nullptr; h->gstack_len = 0;
-        BFB_CUDA(cudaMalloc((void **)&h->gstack, sizeof(double) * deep * (size_t)C));
-        h->gstack_len = deep * (size_t)C;
+        BFB_CUDA(cudaMalloc((void **)&h->gstack, sizeof(double) * (deep + prop) * (size_t)C));
+        h->gstack_len = (deep + prop) * (size_t)C;
     }
     RunOutDevF od;
     od.o = o; od.n_iter = n_iter;
-    const int blocks = (int)((C + CW - 1) / CW);
-    nuts_multi_kernel<G, D, HAS_C2, NK, MB><<<blocks, 32, smem, h->stream>>>(h->dm, h->scfg, h->cs, od, L, LS, h->gstack);
+    const int n_groups = (int)((C + CW - 1) / CW);
+    int chunk_iters = (n_iter + 5) / 6;
+    if (chunk_iters < 16) chunk_iters = n_iter < 16 ? n_iter : 16;
+    if (const char *e = getenv("BFB200_CHUNK_ITERS")) { int v = atoi(e); if (v >= 1) chunk_iters = v; }
+    const int n_chunks = (n_iter + chunk_iters - 1) / chunk_iters;
+    const int64_t n_units64 = (int64_t)n_groups * n_chunks;
+    BFB_REQUIRE(n_units64 < (1ll << 31), BFB_ERR_ARG, "too many work units");
+    const size_t qlen = 2 + (size_t)n_groups + (size_t)n_units64;
+    if (qlen > h->queue_len) {
+        if (h->queue) cudaFree(h->queue);
+        h->queue = nullptr; h->queue_len = 0;
+        BFB_CUDA(cudaMalloc((void **)&h->queue, sizeof(int) * qlen));
+        h->queue_len = qlen;
+    }
+    queue_init_kernel<<<(unsigned)((n_units64 + 255) / 256), 256, 0, h->stream>>>(h->queue, n_groups, (int)n_units64);
+    h->launches++;
+    int blocks = h->sm_count * MB;
+    if (const char *e = getenv("BFB200_PERSISTENT")) { if (atoi(e) == 0) blocks = (int)n_units64; }
+    if ((int64_t)blocks > n_units64) blocks = (int)n_units64;
+    nuts_multi_kernel<G, D, HAS_C2, NK, MB><<<blocks, 32, smem, h->stream>>>(h->dm, h->scfg, h->cs, od, L, LS, h->gstack,
+                                                                           h->gstack + deep * (size_t)C, (int)h->iters_done,
+                                                                           chunk_iters, n_groups, (int)n_units64, h->queue);
     h->launches++;
     BFB_CUDA(cudaGetLastError());
     return BFB_OK;

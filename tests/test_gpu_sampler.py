@@ -180,3 +180,21 @@ def test_sample_api(oracle):
     bad[2] = np.nan
     with pytest.raises(ValueError):
         bfb.sample(den, dict(n_chain=16, n_iter=20, n_warmup=10, x_0=bad, random_generator=5), verbose=False)
+
+
+def test_work_queue_chunking_is_invisible(handle, monkeypatch):
+    """the fast path cuts a launch into (chain-group, iteration-chunk) work units handed out by an atomic queue;
+    results must not depend on the chunk length (chain state is carried through global memory between units)"""
+    n, C, n_iter = 26, 96, 48
+    spec, cov = synthetic_spec(n, 'cubic-2', seed=33)
+    handle.set_model(to_device_spec(spec))
+    x0 = (np.linalg.cholesky(cov) @ np.random.default_rng(5).normal(size=(n, C))).T
+    cfg = cfg_from({}, n_iter // 2, 99)
+    outs = []
+    for chunk in (str(n_iter), '16', '5'):
+        monkeypatch.setenv('BFB200_CHUNK_ITERS', chunk)
+        handle.sampler_init(cfg, x0, 1. / n**0.25, np.ones(n), x0)
+        outs.append(handle.sampler_run('NUTS', n_iter))
+    for o in outs[1:]:
+        for k in ('samples', 'tree_depth', 'tree_size', 'step_size', 'energy'):
+            assert np.array_equal(o[k], outs[0][k]), k
