@@ -56,6 +56,9 @@ struct DevModel {
     int use_transform;
     const double *r_lo, *r_w;   // [np] ranges[:,0], ranges[:,1]-ranges[:,0]
     const int *hb;       // [np] bit0 = lower bound hard, bit1 = upper bound hard
+    // DMMA operand table of output 0 (bfb_dmma.cuh): bfrag[kt][tile][lane]; frag_nr = 0 when the model does not qualify
+    const double *bfrag;
+    int frag_nr, frag_nt;
 };
 
 struct HostConfig {

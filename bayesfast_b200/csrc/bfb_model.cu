@@ -2,6 +2,8 @@
 // batched evaluation entry points, RNG exposure.
 #include "bfb_common.cuh"
 #include "bfb_eval.cuh"
+#include "bfb_dmma.cuh"
+int bfb_launch_eval_dmma(bfb_context *h, const double *X, int64_t C, double *LP, double *G);
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -238,6 +240,27 @@ int bfb_upload_model(bfb_context *h)
                 for (int k = 0; k < n; ++k) HT[(size_t)k * np + j] = h->h_hess[(size_t)j * n + k];
         if ((rc = upload(h, pad(h->h_mu, 0.), &D.mu))) return rc;
         if ((rc = upload(h, HT, &D.HT))) return rc;
+        // operand table of the tensor-core evaluator (bfb_dmma.cuh), output 0
+        const int nr = bfb_frag_nr(n);
+        if (nr > 0 && !h3 && np == 32) {
+            const bool c2 = h2;
+            const int TX = c2 ? nr : (nr + 1) / 2, T2 = c2 ? (nr + 1) / 2 : 0, NT = bfb_frag_tiles(nr, c2);
+            std::vector<double> fr((size_t)nr * NT * 32, 0.);
+            for (int kt = 0; kt < nr; ++kt)
+                for (int t = 0; t < NT; ++t)
+                    for (int lane = 0; lane < 32; ++lane) {
+                        const int k = 4 * kt + (lane & 3), gid = lane >> 2, own = gid >> 1, e = gid & 1;
+                        const std::vector<double> *T = nullptr;
+                        int v;
+                        if (t < TX) { v = 2 * t + e; if (v < nr) T = &S; else if (c2 && v < 2 * nr) { T = &A1T; v -= nr; } }
+                        else if (t < TX + T2) { v = 2 * (t - TX) + e; if (v < nr) T = &A2; }
+                        else { v = 2 * (t - TX - T2) + e; if (v < nr) T = &HT; }
+                        const int j = 4 * v + own;
+                        if (T && !T->empty() && k < n && j < n) fr[((size_t)kt * NT + t) * 32 + lane] = (*T)[(size_t)k * np + j];
+                    }
+            if ((rc = upload(h, fr, &D.bfrag))) return rc;
+            D.frag_nr = nr; D.frag_nt = NT;
+        }
         std::vector<double> fm(m, 0.);
         for (int o = 0; o < m && o < (int)h->h_fmu.size(); ++o) fm[o] = h->h_fmu[o];
         if ((rc = upload(h, fm, &D.f_mu))) return rc;
@@ -469,6 +492,9 @@ extern "C" int bfb_logp_and_grad_batch(bfb_handle h, const double *X, int64_t C,
     int blocks = (int)(blocks64 < (int64_t)h->sm_count * 16 ? blocks64 : (int64_t)h->sm_count * 16);
     size_t smem = sizeof(double) * wpb * 2 * h->np;
     BFB_CUDA(cudaEventRecord(h->ev0, h->stream));
+    rc = bfb_launch_eval_dmma(h, (const double *)bx.dev, C, (double *)bl.dev, (double *)bg.dev);
+    if (rc < 0) return rc;
+    if (rc == 1) {
     switch (npl) {
     case 1: density_eval_kernel<1><<<blocks, 32 * wpb, smem, h->stream>>>(h->dm, (const double *)bx.dev, C, (double *)bl.dev, (double *)bg.dev); break;
     case 2: density_eval_kernel<2><<<blocks, 32 * wpb, smem, h->stream>>>(h->dm, (const double *)bx.dev, C, (double *)bl.dev, (double *)bg.dev); break;
@@ -476,6 +502,7 @@ extern "C" int bfb_logp_and_grad_batch(bfb_handle h, const double *X, int64_t C,
     default: density_eval_kernel<4><<<blocks, 32 * wpb, smem, h->stream>>>(h->dm, (const double *)bx.dev, C, (double *)bl.dev, (double *)bg.dev); break;
     }
     h->launches++;
+    }
     BFB_CUDA(cudaGetLastError());
     BFB_CUDA(cudaEventRecord(h->ev1, h->stream));
     if ((rc = finish(h, bl))) return rc;

@@ -113,3 +113,29 @@ def test_polymodel_api(oracle):
         s._fun(np.zeros(4))
     with pytest.raises(ValueError):
         bfb.PolyModel([bfb.PolyConfig('linear'), bfb.PolyConfig('linear')], input_size=2, output_size=1)
+
+
+@pytest.mark.parametrize('n,order', [(26, 'cubic-2'), (28, 'cubic-2'), (16, 'cubic-2'), (5, 'cubic-2'), (31, 'cubic-2'),
+                                     (26, 'quadratic'), (13, 'quadratic'), (32, 'quadratic')])
+def test_tensor_core_evaluator_vs_oracle(handle, oracle, n, order, monkeypatch):
+    """bfb_eval_dmma.cu (8 points per warp on FP64 DMMA) against the oracle, incl. points outside the radial bound
+    (PolyModel._fj_bound) and a ragged batch; and against the generic warp-per-point kernel."""
+    spec, cov = synthetic_spec(n, order, seed=100 + n)
+    handle.set_model(to_device_spec(spec))
+    rng = np.random.default_rng(2)
+    L = np.linalg.cholesky(cov)
+    C = 2051
+    X = (L @ rng.normal(size=(n, C))).T * rng.choice([0.3, 1., 2.5, 6.], size=(C, 1))
+    d = X - spec['mu']
+    beta = np.einsum('ij,jk,ik->i', d, spec['hess'], d) ** 0.5
+    assert (beta > spec['alpha']).sum() > 50 and (beta < spec['alpha']).sum() > 500
+    lp, g = handle.logp_and_grad_batch(X)
+    lpo, go = oracle.OracleDensity(spec).logp_and_grad_batch(X)
+    assert rel_err(lp, lpo) < RTOL and rel_err(g, go) < RTOL
+    monkeypatch.setenv('BFB200_EVAL', 'generic')
+    lp2, g2 = handle.logp_and_grad_batch(X)
+    assert rel_err(lp, lp2) < 1e-12 and rel_err(g, g2) < 1e-12
+    monkeypatch.delenv('BFB200_EVAL')
+    # batches smaller than a warp's 8 points
+    lp3, g3 = handle.logp_and_grad_batch(X[:3])
+    assert np.array_equal(lp3, lp[:3]) and np.array_equal(g3, g[:3])
