@@ -85,7 +85,7 @@ struct ChainState {
     int64_t *t_draw;                                 // [C]
     int64_t *iter;                                   // [C] iterations done
     int32_t *status;                                 // [C]
-    unsigned long long *tree_total;                  // [1]
+    unsigned long long *tree_total;                  // [4]: leapfrogs in trees; debug counters of the multi-chain kernels
 };
 
 struct FitState;

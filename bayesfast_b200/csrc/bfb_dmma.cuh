@@ -31,7 +31,7 @@ struct DmmaShape {
 
 inline int bfb_frag_tiles(int nr, bool c2) { return (c2 ? nr : (nr + 1) / 2) + (c2 ? (nr + 1) / 2 : 0) + (nr + 1) / 2; }
 // instantiated dims-per-lane for input_size n (0: not supported)
-inline int bfb_frag_nr(int n) { return n <= 8 ? 2 : n <= 16 ? 4 : n <= 28 ? 7 : n <= 32 ? 8 : 0; }
+inline int bfb_frag_nr(int n) { return n <= 16 ? 4 : n <= 28 ? 7 : n <= 32 ? 8 : 0; }
 
 __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b)
 {
@@ -67,9 +67,11 @@ __device__ __forceinline__ double qsum(double v)
 // fpart = sum_own lin x + x.(Sx)/2 + x^2 (A x), bpart = sum_own (x - mu) hh
 template <int NR, bool C2>
 __device__ __forceinline__ void dmma_core(const double *bsm, int lane, const double (&x)[NR],
-                                          const double (&mu)[NR], const double (&lin)[NR], double (&gg)[NR],
+                                          const double *mu_t, const double *lin_t, double (&gg)[NR],
                                           double (&hh)[NR], double &fpart, double &bpart)
 {
+    // mu_t / lin_t: [32] tables indexed by dimension (shared memory); read where used instead of living in registers
+    const int lg_ = lane & 3;
     using SH = DmmaShape<NR, C2>;
     double acc[SH::NT][2];
 #pragma unroll
@@ -80,7 +82,7 @@ __device__ __forceinline__ void dmma_core(const double *bsm, int lane, const dou
     asm volatile("" ::: "memory");
 #pragma unroll
     for (int kt = 0; kt < NR; ++kt) {
-        const double ax = x[kt], ax2 = x[kt] * x[kt], ad = x[kt] - mu[kt];
+        const double ax = x[kt], ax2 = x[kt] * x[kt], ad = x[kt] - mu_t[4 * kt + lg_];
 #pragma unroll
         for (int t = 0; t < SH::NT; ++t) {
             const double b = bp[(kt * SH::NT + t) * 32];
@@ -93,8 +95,9 @@ __device__ __forceinline__ void dmma_core(const double *bsm, int lane, const dou
     for (int r = 0; r < NR; ++r) {
         const double y = acc[r / 2][r % 2];
         const double h = acc[SH::TX + SH::T2 + r / 2][r % 2];
-        double g = lin[r] + y;
-        fpart = fma(lin[r], x[r], fpart);
+        const double lin_r = lin_t[4 * r + lg_];
+        double g = lin_r + y;
+        fpart = fma(lin_r, x[r], fpart);
         fpart = fma(0.5 * x[r], y, fpart);
         if (C2) {
             const double t = acc[(NR + r) / 2][(NR + r) % 2];
@@ -103,7 +106,7 @@ __device__ __forceinline__ void dmma_core(const double *bsm, int lane, const dou
             fpart = fma(x[r] * x[r], t, fpart);
         }
         gg[r] = g; hh[r] = h;
-        bpart = fma(x[r] - mu[r], h, bpart);
+        bpart = fma(x[r] - mu_t[4 * r + lg_], h, bpart);
     }
 }
 
@@ -117,7 +120,7 @@ struct DmmaConsts {
 // kinetic energy of the new momentum); `live` masks points whose outside test should not trigger the second pass.
 template <int NR, bool C2, class KE>
 __device__ __forceinline__ void dmma_logp_grad(const double *bsm, int lane, const DmmaConsts &K,
-                                               const double (&x_in)[NR], const double (&mu)[NR], const double (&lin)[NR],
+                                               const double (&x_in)[NR], const double *mu, const double *lin,
                                                bool live, double &lp, double (&gn)[NR], KE &&ke_of, double &ke)
 {
     const int lg = lane & 3;
@@ -135,12 +138,15 @@ __device__ __forceinline__ void dmma_logp_grad(const double *bsm, int lane, cons
     const bool outside = live && (bpart > K.alpha2);
     if (__any_sync(BFB_FULL, outside)) {
         // PolyModel._fj_bound, poly.py:480-503: project onto the ellipsoid and evaluate there
-        const double beta = sqrt(bpart);
+        // divisions by beta are done as multiplications by 1 / beta: the padded dimensions hold exact zeros and a zero
+        // numerator sends the FP64 division to its slow path (measured: one ~100-instruction subroutine call per round)
+        const double beta = sqrt(bpart), rbeta = 1. / beta;
         double d0[NR], hd0[NR];
 #pragma unroll
         for (int r = 0; r < NR; ++r) {
-            d0[r] = x[r] - mu[r]; hd0[r] = hh[r];
-            if (outside) x[r] = (4 * r + lg < K.n) ? (K.alpha * x[r] + (beta - K.alpha) * mu[r]) / beta : 0.;
+            const double mu_r = mu[4 * r + lg];
+            d0[r] = x[r] - mu_r; hd0[r] = hh[r];
+            if (outside) x[r] = (4 * r + lg < K.n) ? (K.alpha * x[r] + (beta - K.alpha) * mu_r) * rbeta : 0.;
         }
         double f1, b1;
         dmma_core<NR, C2>(bsm, lane, x, mu, lin, gg, hh, f1, b1);
@@ -151,9 +157,9 @@ __device__ __forceinline__ void dmma_logp_grad(const double *bsm, int lane, cons
         qsum4(f1, jd, z1, z2, lane);
         double g2[NR];
         const double f0 = K.c0 + f1;
-        const double sfac = (f0 - K.f_mu) / K.alpha - jd / beta;
+        const double sfac = (f0 - K.f_mu) / K.alpha - jd * rbeta;
 #pragma unroll
-        for (int r = 0; r < NR; ++r) g2[r] = gg[r] + sfac * (hd0[r] / beta);
+        for (int r = 0; r < NR; ++r) g2[r] = gg[r] + sfac * (hd0[r] * rbeta);
         const double k2 = qsum(ke_of(g2));
         if (outside) {
 #pragma unroll

@@ -16,19 +16,18 @@ __global__ void __launch_bounds__(128) eval_dmma_kernel(DevModel M, const double
 {
     using SH = DmmaShape<NR, C2>;
     extern __shared__ double bsm[];
+    double *msm = bsm + SH::FRAG_DOUBLES;     // mu[32] | lin[32]
     for (int i = threadIdx.x; i < SH::FRAG_DOUBLES; i += blockDim.x) bsm[i] = M.bfrag[i];
+    if (threadIdx.x < 32) {
+        msm[threadIdx.x] = M.use_bound ? M.mu[threadIdx.x] : 0.;
+        msm[32 + threadIdx.x] = M.lin[threadIdx.x];
+    }
     __syncthreads();
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, gi = lane >> 2, lg = lane & 3;
     const int n = M.n;
     DmmaConsts K;
     K.c0 = M.c0[0]; K.alpha = M.alpha; K.alpha2 = M.use_bound ? M.alpha * M.alpha : INFINITY;
     K.f_mu = M.use_bound ? M.f_mu[0] : 0.; K.n = n;
-    double mu[NR], lin[NR];
-#pragma unroll
-    for (int r = 0; r < NR; ++r) {
-        mu[r] = M.use_bound ? M.mu[4 * r + lg] : 0.;
-        lin[r] = M.lin[4 * r + lg];
-    }
     const int64_t stride = (int64_t)gridDim.x * 4 * 8;
     for (int64_t base = ((int64_t)blockIdx.x * 4 + wib) * 8; base < C; base += stride) {
         const int64_t c = base + gi;
@@ -37,7 +36,7 @@ __global__ void __launch_bounds__(128) eval_dmma_kernel(DevModel M, const double
         double x[NR], gn[NR], lp, ke;
 #pragma unroll
         for (int r = 0; r < NR; ++r) x[r] = (4 * r + lg < n) ? X[cc * n + 4 * r + lg] : 0.;
-        dmma_logp_grad<NR, C2>(bsm, lane, K, x, mu, lin, valid, lp, gn, [](const double (&)[NR]) { return 0.; }, ke);
+        dmma_logp_grad<NR, C2>(bsm, lane, K, x, msm, msm + 32, valid, lp, gn, [](const double (&)[NR]) { return 0.; }, ke);
         if (valid) {
             if (lg == 0) LP[c] = lp;
 #pragma unroll
@@ -50,7 +49,7 @@ template <int NR, bool C2>
 static int launch_eval(bfb_context *h, const double *X, int64_t C, double *LP, double *G)
 {
     using SH = DmmaShape<NR, C2>;
-    const size_t smem = sizeof(double) * SH::FRAG_DOUBLES;
+    const size_t smem = sizeof(double) * (SH::FRAG_DOUBLES + 64);
     BFB_CUDA(cudaFuncSetAttribute(eval_dmma_kernel<NR, C2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 2;
     if (const char *e = getenv("BFB200_EVAL_BLOCKS_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 8) per_sm = v; }
@@ -70,7 +69,6 @@ int bfb_launch_eval_dmma(bfb_context *h, const double *X, int64_t C, double *LP,
     if (const char *e = getenv("BFB200_EVAL")) { if (!strcmp(e, "generic")) return 1; }
     const bool c2 = M.has_c2;
     switch (M.frag_nr) {
-    case 2: return c2 ? launch_eval<2, true>(h, X, C, LP, G) : launch_eval<2, false>(h, X, C, LP, G);
     case 4: return c2 ? launch_eval<4, true>(h, X, C, LP, G) : launch_eval<4, false>(h, X, C, LP, G);
     case 7: return c2 ? launch_eval<7, true>(h, X, C, LP, G) : launch_eval<7, false>(h, X, C, LP, G);
     case 8: return c2 ? launch_eval<8, true>(h, X, C, LP, G) : launch_eval<8, false>(h, X, C, LP, G);

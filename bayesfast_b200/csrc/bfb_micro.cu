@@ -30,6 +30,67 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, 
     if (s == 12345.678) out[0] = s;
 }
 
+// single-warp-per-scheduler DMMA issue test: NACC independent accumulators, operands from registers (SRC = 0) or one
+// 8-byte shared-memory load per DMMA (SRC = 1); reports cycles per DMMA seen by one warp
+template <int NACC, int SRC>
+__global__ void __launch_bounds__(256) dmma_issue_kernel(double *out, long long *cyc, int iters, double a0, double b0)
+{
+    __shared__ double tab[32 * 128];
+    for (int i = threadIdx.x; i < 32 * 128; i += blockDim.x) tab[i] = b0 + 1e-9 * i;
+    __syncthreads();
+    double acc[NACC][2];
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) acc[i][0] = acc[i][1] = (double)(threadIdx.x + i);
+    double a = a0 + 1e-9 * threadIdx.x;
+    const double *bp = tab + (threadIdx.x & 31);
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+        asm volatile("" ::: "memory");
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+#pragma unroll
+            for (int i = 0; i < NACC; ++i) {
+                const double b = SRC ? bp[((k * NACC + i) & 127) * 32] : b0;
+                dmma884(acc[i][0], acc[i][1], a, b);
+            }
+        }
+    }
+    const long long t1 = clock64();
+    double s = 0.;
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) s += acc[i][0] + acc[i][1];
+    if (s == 12345.678) out[0] = s;
+    if (threadIdx.x == 0 && blockIdx.x == 0) cyc[0] = t1 - t0;
+}
+
+extern "C" int bfb_dmma_issue_test(bfb_handle h, int nacc, int src, int warps_per_sm, double *cycles_per_dmma)
+{
+    BFB_REQUIRE(h && cycles_per_dmma, BFB_ERR_ARG, "bfb_dmma_issue_test: bad arguments");
+    BFB_CUDA(cudaSetDevice(h->device));
+    double *d; long long *c;
+    BFB_CUDA(cudaMalloc(&d, 8));
+    BFB_CUDA(cudaMalloc(&c, 8));
+    const int iters = 2000;
+    for (int rep = 0; rep < 2; ++rep) {
+        if (nacc == 15 && src == 0) dmma_issue_kernel<15, 0><<<h->sm_count, 32 * warps_per_sm, 0, h->stream>>>(d, c, iters, 0.999999, 1e-3);
+        else if (nacc == 15) dmma_issue_kernel<15, 1><<<h->sm_count, 32 * warps_per_sm, 0, h->stream>>>(d, c, iters, 0.999999, 1e-3);
+        else if (nacc == 8 && src == 0) dmma_issue_kernel<8, 0><<<h->sm_count, 32 * warps_per_sm, 0, h->stream>>>(d, c, iters, 0.999999, 1e-3);
+        else if (nacc == 8) dmma_issue_kernel<8, 1><<<h->sm_count, 32 * warps_per_sm, 0, h->stream>>>(d, c, iters, 0.999999, 1e-3);
+        else if (nacc == 4 && src == 0) dmma_issue_kernel<4, 0><<<h->sm_count, 32 * warps_per_sm, 0, h->stream>>>(d, c, iters, 0.999999, 1e-3);
+        else if (nacc == 2 && src == 0) dmma_issue_kernel<2, 0><<<h->sm_count, 32 * warps_per_sm, 0, h->stream>>>(d, c, iters, 0.999999, 1e-3);
+        else dmma_issue_kernel<1, 0><<<h->sm_count, 32 * warps_per_sm, 0, h->stream>>>(d, c, iters, 0.999999, 1e-3);
+        h->launches++;
+        BFB_CUDA(cudaGetLastError());
+        BFB_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    long long cy;
+    BFB_CUDA(cudaMemcpy(&cy, c, 8, cudaMemcpyDeviceToHost));
+    cudaFree(d); cudaFree(c);
+    const int na = (nacc == 15 || nacc == 8 || nacc == 4 || nacc == 2) ? nacc : 1;
+    *cycles_per_dmma = (double)cy / ((double)iters * 7 * na);
+    return BFB_OK;
+}
+
 extern "C" int bfb_fp64_peak(bfb_handle h, int kind, double *tflops)
 {
     BFB_REQUIRE(h && tflops && kind >= 0 && kind <= 2, BFB_ERR_ARG, "bfb_fp64_peak: bad arguments");

@@ -14,9 +14,11 @@
 #include "bfb_common.cuh"
 #include "bfb_eval.cuh"
 #include <cstring>
+#include <cstdio>
 #include <cstdlib>
 
 int bfb_launch_nuts_fast(bfb_context *h, const bfb_run_out &o, int n_iter);   // bfb_sampler_fast.cu
+int bfb_launch_nuts_dmma(bfb_context *h, const bfb_run_out &o, int n_iter);   // bfb_sampler_dmma.cu
 
 struct RunOutDev {
     bfb_run_out o;
@@ -428,7 +430,7 @@ extern "C" int bfb_sampler_init(bfb_handle h, const bfb_sampler_cfg *cfg, int64_
         (rc = dalloc(h, &s.hbar, C)) || (rc = dalloc(h, &s.mu_da, C)) || (rc = dalloc(h, &s.count, C)) ||
         (rc = dalloc(h, &s.n_samples, C)) || (rc = dalloc(h, &s.previous_update, C)) ||
         (rc = dalloc(h, &s.adapt_window, C)) || (rc = dalloc(h, &s.t_draw, C)) || (rc = dalloc(h, &s.iter, C)) ||
-        (rc = dalloc(h, &s.status, C)) || (rc = dalloc(h, &s.tree_total, 1)))
+        (rc = dalloc(h, &s.status, C)) || (rc = dalloc(h, &s.tree_total, 16)))
         return rc;
     std::vector<double> vq(V, 0.), vvar(V, 1.), vfm(V, 0.), vfr(V, 0.);
     std::vector<double> fgn(C), bgn(C, 10.), ls(C), mu(C);
@@ -499,7 +501,15 @@ static int launch_run(bfb_context *h, int sampler, int n_iter, const bfb_run_out
     od.n_iter = n_iter;
     od.o = dev_out;
     int rc = BFB_OK, fast_rc = 1;
-    if (sampler == BFB_NUTS && !getenv("BFB200_FORCE_GENERIC")) fast_rc = bfb_launch_nuts_fast(h, od.o, n_iter);
+    // NUTS kernel selection: tensor-core path, then the FMA multi-chain path, then the generic warp-per-chain kernel
+    // (BFB200_SAMPLER = dmma | fast | generic pins one for tests and profiles)
+    if (sampler == BFB_NUTS && !getenv("BFB200_FORCE_GENERIC")) {
+        fast_rc = bfb_launch_nuts_dmma(h, od.o, n_iter);
+        if (fast_rc == 1) {
+            const char *sel = getenv("BFB200_SAMPLER");
+            if (!sel || !strcmp(sel, "fast") || !strcmp(sel, "dmma")) fast_rc = bfb_launch_nuts_fast(h, od.o, n_iter);
+        }
+    }
     if (fast_rc < 0) return fast_rc;
     if (fast_rc == 0) return BFB_OK;
     const int wpb = 4;
@@ -537,7 +547,7 @@ extern "C" int bfb_sampler_run(bfb_handle h, int sampler, int32_t n_iter, const 
     const int n = h->n;
     void *const user[11] = {out->samples, out->logp, out->energy, out->mean_tree_accept, out->step_size, out->step_size_bar,
                             out->energy_change, out->max_energy_change, out->tree_depth, out->tree_size, out->diverging};
-    BFB_CUDA(cudaMemsetAsync(h->cs.tree_total, 0, sizeof(unsigned long long), h->stream));
+    BFB_CUDA(cudaMemsetAsync(h->cs.tree_total, 0, 16 * sizeof(unsigned long long), h->stream));
     unsigned long long tt = 0;
     if (loc == BFB_DEVICE) {
         BFB_CUDA(cudaEventRecord(h->ev0, h->stream));
@@ -602,6 +612,14 @@ extern "C" int bfb_sampler_run(bfb_handle h, int sampler, int32_t n_iter, const 
     BFB_CUDA(cudaStreamSynchronize(h->stream));
     BFB_CUDA(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
     if (total_tree_size) *total_tree_size = (int64_t)tt;
+    if (getenv("BFB200_DEBUG")) {
+        unsigned long long dbg[16];
+        BFB_CUDA(cudaMemcpy(dbg, h->cs.tree_total, sizeof(dbg), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "[bfb200] leaves %llu warp-rounds %llu merge-sections %llu iter-end-sections %llu  ms %.3f\n", dbg[0], dbg[1], dbg[2], dbg[3], h->last_ms);
+        if (dbg[1]) fprintf(stderr, "[bfb200] cycles per warp-round: boundary %.0f rng+dbl %.0f eval %.0f leaf %.0f merges %.0f push %.0f extend %.0f | unit setup+teardown per round %.0f\n",
+                            (double)dbg[4] / dbg[1], (double)dbg[5] / dbg[1], (double)dbg[6] / dbg[1], (double)dbg[7] / dbg[1],
+                            (double)dbg[8] / dbg[1], (double)dbg[9] / dbg[1], (double)dbg[10] / dbg[1], (double)dbg[11] / dbg[1]);
+    }
     return BFB_OK;
 }
 

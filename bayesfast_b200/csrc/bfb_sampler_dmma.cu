@@ -1,0 +1,592 @@
+// bfb_sampler_dmma.cu -- NUTS with the surrogate evaluated on the FP64 tensor cores: EIGHT chains per warp.
+//
+// Applies to input_size <= 32, logp = output 0 of a linear + quadratic (+ cubic-2) PolyModel with the radial bound and
+// no decay / variable transform / module rescale (the BASELINE.json headline configuration); anything else runs the
+// kernels of bfb_sampler_fast.cu / bfb_sampler.cu.  Same algorithm, same draw order (SURVEY.md 8a N-RNG).
+//
+// Mapping (bfb_dmma.cuh): a chain is owned by the 4 lanes of a quad, lane lg owning the dimensions j = 4 r + lg; the
+// 8 chains of a warp are the 8 rows of an m8n8k4 DMMA whose B operand is the (chain-independent) coefficient table, so one
+// leapfrog of 8 chains is 105 DMMAs (n = 26, cubic-2) instead of ~1500 warp-wide DFMAs + their operand loads.
+// Everything else follows the asynchronous state machine of bfb_sampler_fast.cu: the chains of a warp are NOT in lock
+// step (own iteration / depth / leaf counters); the warp loops "one leapfrog for every live chain, then whatever each
+// chain needs" with every section entered on __any_sync and committed per chain by predication.  Multinomial weights in
+// the linear domain (mantissa, exponent), U-turn dot products reduced packed over the quad, proposals referred to by slot
+// index into an L2-resident pool, deep tree-stack levels in an L2-resident buffer, persistent warps fed by the ready ring
+// of (chain group, iteration chunk) units.
+//
+// Reference restated here: samplers/hmc_utils/base_hmc.py:62-85, samplers/nuts.py:27-217, hmc_utils/integration.py:28-95,
+// hmc_utils/metrics.py:73-91,186-211,333-371, hmc_utils/step_size.py:10-51.
+#include "bfb_dmma.cuh"
+#include "bfb_nuts_common.cuh"
+#include <cstring>
+#include <cstdlib>
+
+// per chain: is any of the six sums over its 4 lanes <= 0 ?
+__device__ __forceinline__ bool quad_any_nonpos6(double v0, double v1, double v2, double v3, double v4, double v5, int lane)
+{
+    const bool b0 = lane & 1, b1 = lane & 2;
+    double k0 = b0 ? v4 : v0, k1 = b0 ? v5 : v1, k2 = b0 ? 1. : v2, k3 = b0 ? 1. : v3;
+    const double s0 = b0 ? v0 : v4, s1 = b0 ? v1 : v5, s2 = b0 ? v2 : 1., s3 = b0 ? v3 : 1.;
+    k0 += shx4(s0, 1); k1 += shx4(s1, 1); k2 += shx4(s2, 1); k3 += shx4(s3, 1);
+    double m0 = b1 ? k2 : k0, m1 = b1 ? k3 : k1;
+    const double t0 = b1 ? k0 : k2, t1 = b1 ? k1 : k3;
+    m0 += shx4(t0, 2); m1 += shx4(t1, 2);
+    const unsigned bal = __ballot_sync(BFB_FULL, (m0 <= 0.) || (m1 <= 0.));
+    return ((bal >> (lane & ~3)) & 0xfu) != 0u;
+}
+
+// one instance of Philox + Phi^-1 in the kernel image instead of one per call site (the code of a round must stay
+// small: with one or two warps per scheduler instruction-fetch stalls are not hidden by other warps)
+__device__ __noinline__ double draw_normal_ni(uint64_t seed, uint64_t chain, uint64_t t) { return bfb_draw_normal(seed, chain, t); }
+__device__ __noinline__ double draw_uniform_ni(uint64_t seed, uint64_t chain, uint64_t t) { return bfb_draw_uniform(seed, chain, t); }
+__device__ __noinline__ double2 philox_pair_ni(uint64_t seed, uint64_t chain, uint64_t blk)
+{
+    double u0, u1;
+    const bfb_philox_block b = bfb_philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)chain,
+                                                 (uint32_t)(chain >> 32), (uint32_t)seed, (uint32_t)(seed >> 32));
+    u0 = bfb_u64_to_uniform((uint64_t)b.v[0] | ((uint64_t)b.v[1] << 32));
+    u1 = bfb_u64_to_uniform((uint64_t)b.v[2] | ((uint64_t)b.v[3] << 32));
+    return make_double2(u0, u1);
+}
+__device__ __forceinline__ int64_t shfl64(int64_t v, int src)
+{
+    return (int64_t)__shfl_sync(BFB_FULL, (long long)v, src);
+}
+
+// shared memory per warp, in doubles: TL q,p,g | TR q,p,g | PS | PB | stack levels (pl, pr, psum) | per-level scalars
+// [5][10][8 chains]: weight mantissa, weight exponent, proposal energy, proposal logp, proposal slot.
+// A vector slot holds element (r, lane) at r * 32 + lane: every access is one conflict-free 256-byte row.
+__host__ __device__ inline int warp_smem_doubles(int NR, int LS) { return (8 + 3 * LS) * NR * 32 + 400; }
+
+template <int NR, bool C2, int W>
+__global__ void __launch_bounds__(32 * W, 1) nuts_dmma_kernel(DevModel M, bfb_sampler_cfg cfg, ChainState st, RunOutDevF out,
+                                                              int L, int LS, double *__restrict__ gstack,
+                                                              double *__restrict__ gprop, int base_iter, int chunk_iters,
+                                                              int n_groups, int n_units, int *__restrict__ queue)
+{
+    using SH = DmmaShape<NR, C2>;
+    constexpr int SLOT = NR * 32;
+    extern __shared__ double smem[];
+    double *bsm = smem;                       // coefficient operand table
+    double *msm = smem + SH::FRAG_DOUBLES;    // mu[32] | lin[32]
+    for (int i = threadIdx.x; i < SH::FRAG_DOUBLES; i += blockDim.x) bsm[i] = M.bfrag[i];
+    if (threadIdx.x < 32) {
+        msm[threadIdx.x] = M.use_bound ? M.mu[threadIdx.x] : 0.;
+        msm[32 + threadIdx.x] = M.lin[threadIdx.x];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, gi = lane >> 2, lg = lane & 3;
+    double *wsm = smem + SH::FRAG_DOUBLES + 64 + (size_t)wib * warp_smem_doubles(NR, LS);
+    double *sTL = wsm, *sTR = wsm + 3 * SLOT, *sPS = wsm + 6 * SLOT, *sPB = wsm + 7 * SLOT, *sST = wsm + 8 * SLOT;
+    double *ssc = wsm + (8 + 3 * LS) * SLOT + gi;        // scalar (field f, level l) of this chain at ssc[(f * 10 + l) * 8]
+    const int n = M.n;
+    DmmaConsts K;
+    K.c0 = M.c0[0]; K.alpha = M.alpha; K.alpha2 = M.use_bound ? M.alpha * M.alpha : INFINITY;
+    K.f_mu = M.use_bound ? M.f_mu[0] : 0.; K.n = n;
+
+#ifdef BFB_DMMA_TIMING
+#define TICK(k) { const long long now_ = clock64(); tacc[k] += now_ - tlast; tlast = now_; }
+#else
+#define TICK(k)
+#endif
+#define VLD(dst, base)  _Pragma("unroll") for (int r_ = 0; r_ < NR; ++r_) dst[r_] = (base)[r_ * 32 + lane];
+#define VST(base, src)  _Pragma("unroll") for (int r_ = 0; r_ < NR; ++r_) (base)[r_ * 32 + lane] = src[r_];
+
+    volatile int *qv = queue;
+    volatile int *ring = queue + 2 + n_groups;
+#pragma unroll 1
+    for (;;) {
+    int idx = 0, group = 0;
+    if (lane == 0) {
+        idx = atomicAdd(queue, 1);
+        if (idx < n_units) { while ((group = ring[idx]) < 0) __nanosleep(100); }
+    }
+    idx = __shfl_sync(BFB_FULL, idx, 0);
+    if (idx >= n_units) break;
+    group = __shfl_sync(BFB_FULL, group, 0);
+    __threadfence();
+    const int chunk = qv[2 + group];
+    const int it_lo = chunk * chunk_iters;
+    const int it_hi = min(out.n_iter, it_lo + chunk_iters);
+    const long long t_unit0 = clock64(); (void)t_unit0;
+    const int64_t c_raw = (int64_t)group * 8 + gi;
+    const bool exists = c_raw < st.C;
+    const int64_t c = exists ? c_raw : st.C - 1;
+    double *gst = gstack + (size_t)group * (size_t)(L > LS ? L - LS : 0) * 3 * SLOT;   // deep stack levels (L2 resident)
+    // proposals (q, grad) are written once, at the leaf, into a slot of an L2-resident pool and are afterwards only
+    // referred to by their slot index: merges move no vectors.  Same thread writes and reads a given element.
+    double *gpr = gprop + (size_t)group * BFB_NSLOT * 2 * SLOT;
+
+    // ---- chain state (adaptation scalars stay in global memory: they are touched once per iteration) ----
+    const size_t vb = (size_t)c * M.np;
+    double q[NR], p[NR], g[NR], var[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        const int j = 4 * r + lg;
+        q[r] = st.q[vb + j]; g[r] = st.g[vb + j]; var[r] = st.var[vb + j]; p[r] = 0.;
+    }
+    const uint64_t seed = cfg.seed, chain_id = (uint64_t)(cfg.chain0 + c);
+    int64_t t = st.t_draw[c];
+    const int it0 = base_iter;                 // iterations done before this launch (same for every chain)
+    double logp_q = st.logp[c];
+    double log_step = st.log_step[c], log_bar = st.log_bar[c];
+    int status = exists ? st.status[c] : 9;
+    unsigned tree_total = 0, dbg_rounds = 0, dbg_merges = 0, dbg_iend = 0;
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64(); (void)tacc; (void)tlast;
+    bool done = (status != 0) || it_lo >= it_hi;
+    int it = it_lo;
+
+    // transition state
+    double E0 = 0., step = 0., prop_E = 0., prop_lp = 0., acc_sum = 0., maxdE = 0.;
+    WT Wtree; Wtree.m = 1.; Wtree.k = 0;
+    int depth = 0, ileaf = 0, n_prop = 0, diverging = 0, prop_slot = 0, Rslot = 0;
+    unsigned freemask = 0;
+    double Rpl[NR], Rps[NR], REp = 0., Rlpp = 0.;
+    WT RW; RW.m = 0.; RW.k = 0;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) Rpl[r] = Rps[r] = 0.;
+    // per-chain control flags: bnd = an iteration boundary is pending (end the previous iteration unless `fresh`,
+    // start the next unless done), ns_dbl = a doubling must be started
+    bool bnd = !done, fresh = true, ns_dbl = false;
+    // scratch vectors of the boundary section alias the (then empty) level-0 stack entry
+    double *sP0 = sST, *sVAR = sST + SLOT;
+
+    auto stack_ptr = [&](int lvl) -> double * {
+        return (lvl < LS) ? (sST + lvl * 3 * SLOT) : (gst + (size_t)(lvl - LS) * 3 * SLOT);
+    };
+
+#pragma unroll 1
+    while (__any_sync(BFB_FULL, !done)) {
+        TICK(7)
+        // ================= iteration boundary: base_hmc.py:62-85, Tree.__init__ nuts.py:27-43 =================
+        if (__any_sync(BFB_FULL, bnd)) {
+            ++dbg_iend;
+            const bool endp = bnd && !fresh;
+            const bool warm_old = (it0 + it) < cfg.n_warmup;            // of the iteration that ends
+            const size_t orow = (size_t)c * out.n_iter + it;
+            // ---- (1) per chain (its quad), predicated: accept statistic, dual averaging, statistics ----
+            const double accept_stat = acc_sum / (double)(n_prop > 0 ? n_prop : 1);
+            if (__any_sync(BFB_FULL, endp && warm_old && cfg.adapt_step_size)) {      // step_size.py:31-45
+                const double hbar0 = st.hbar[c], mu_da = st.mu_da[c];
+                const int64_t count = st.count[c];
+                __syncwarp();
+                if (endp && warm_old && cfg.adapt_step_size) {
+                    const double cnt = (double)count;
+                    const double w = 1. / (cnt + cfg.t0);
+                    const double hbar = ((1. - w) * hbar0 + w * (cfg.target_accept - accept_stat));
+                    log_step = mu_da - hbar * sqrt(cnt) / cfg.gamma;
+                    const double mk = pow(cnt, -cfg.k);
+                    log_bar = mk * log_step + (1. - mk) * log_bar;
+                    if (lg == 0) { st.hbar[c] = hbar; st.log_step[c] = log_step; st.log_bar[c] = log_bar; st.count[c] = count + 1; }
+                }
+            }
+            const double e_step = exp(log_step), e_bar = exp(log_bar);
+            if (endp) {
+                if (lg == 0) {
+                    if (out.o.logp) out.o.logp[orow] = prop_lp;
+                    if (out.o.energy) out.o.energy[orow] = prop_E;
+                    if (out.o.tree_depth) out.o.tree_depth[orow] = depth;
+                    if (out.o.tree_size) out.o.tree_size[orow] = n_prop;
+                    if (out.o.mean_tree_accept) out.o.mean_tree_accept[orow] = accept_stat;
+                    if (out.o.step_size) out.o.step_size[orow] = e_step;
+                    if (out.o.step_size_bar) out.o.step_size_bar[orow] = e_bar;
+                    if (out.o.energy_change) out.o.energy_change[orow] = prop_E - E0;
+                    if (out.o.max_energy_change) out.o.max_energy_change[orow] = maxdE;
+                    if (out.o.diverging) out.o.diverging[orow] = diverging;
+                }
+                logp_q = prop_lp;
+                tree_total += (unsigned)n_prop;
+                it += 1;
+                if (it >= it_hi) done = true;
+            }
+            if (bnd) { VST(sVAR, var) }
+            __syncwarp();
+            // ---- (2) cooperative, lane j = dimension j, one chain at a time: new sample out, windowed Welford
+            //      metric (metrics.py:186-211, 333-371), momentum draw (metrics.py:83-86) ----
+            unsigned mask = __ballot_sync(BFB_FULL, bnd);
+#pragma unroll 1
+            while (mask) {
+                const int src = (__ffs(mask) - 1) & ~3;
+                mask &= ~(0xfu << src);
+                const int64_t c_s = shfl64(c, src), t_s = shfl64(t, src);
+                const int it_s = __shfl_sync(BFB_FULL, it, src), slot_s = __shfl_sync(BFB_FULL, prop_slot, src);
+                const int fl = __shfl_sync(BFB_FULL, (endp ? 1 : 0) | (done ? 2 : 0) | (warm_old ? 4 : 0), src);
+                const int j = lane, e = (j >> 2) * 32 + src + (j & 3);     // element of a vector slot holding dim j of that chain
+                if (fl & 1) {
+                    const double qj = (j < 4 * NR) ? gpr[(size_t)slot_s * 2 * SLOT + e] : 0.;
+                    if (out.o.samples && j < n) out.o.samples[((size_t)c_s * out.n_iter + (it_s - 1)) * n + j] = qj;
+                    if ((fl & 4) && cfg.adapt_metric) {
+                        const int64_t n_samples = st.n_samples[c_s], previous_update = st.previous_update[c_s];
+                        const int adapt_window = st.adapt_window[c_s];
+                        const double fg_n = st.fg_n[c_s] + 1., bg_n = st.bg_n[c_s] + 1.;
+                        __syncwarp();
+                        const int64_t delta = n_samples - previous_update;
+                        const bool upd = ((delta + 1) % cfg.update_window == 0);
+                        const bool swap = delta >= adapt_window;
+                        const size_t vi = (size_t)c_s * M.np + (j < n ? j : 0);
+                        if (j < n) {
+                        double fgm = st.fg_mean[vi], fgr = st.fg_raw[vi], bgm = st.bg_mean[vi], bgr = st.bg_raw[vi];
+                        double od = qj - fgm;
+                        fgm += od / fg_n;
+                        fgr += 1. * od * (qj - fgm);
+                        od = qj - bgm;
+                        bgm += od / bg_n;
+                        bgr += 1. * od * (qj - bgm);
+                        if (upd) sVAR[e] = fgr / fg_n;
+                        if (swap) { fgm = bgm; fgr = bgr; bgm = 0.; bgr = 0.; }
+                        st.fg_mean[vi] = fgm; st.fg_raw[vi] = fgr; st.bg_mean[vi] = bgm; st.bg_raw[vi] = bgr;
+                        }
+                        if (lane == 0) {
+                            st.fg_n[c_s] = swap ? bg_n : fg_n;
+                            st.bg_n[c_s] = swap ? 10. : bg_n;
+                            if (swap) { st.previous_update[c_s] = n_samples; if (cfg.doubling) st.adapt_window[c_s] = adapt_window * 2; }
+                            st.n_samples[c_s] = n_samples + 1;
+                        }
+                    }
+                }
+                if (!(fl & 2)) {
+                    double p0j = 0.;
+                    if (j < n) p0j = draw_normal_ni(seed, (uint64_t)(cfg.chain0 + c_s), (uint64_t)(t_s + j)) / sqrt(sVAR[e]);
+                    if (j < 4 * NR) sP0[e] = p0j;
+                }
+            }
+            __syncwarp();
+            // ---- (3) per chain, predicated: the new state and the empty tree ----
+            double p0[NR], part = 0.;
+            {
+                const double *slot = gpr + (size_t)((bnd && !fresh) ? prop_slot : 0) * 2 * SLOT;
+                double qn[NR], gx[NR], vn[NR];
+                VLD(qn, slot) VLD(gx, slot + SLOT) VLD(vn, sVAR) VLD(p0, sP0)
+                if (bnd) {
+#pragma unroll
+                    for (int r = 0; r < NR; ++r) { if (!fresh) { q[r] = qn[r]; g[r] = gx[r]; } var[r] = vn[r]; }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < NR; ++r) part = fma(p0[r], var[r] * p0[r], part);
+            const double ke = qsum(part);
+            const bool warm_new = (it0 + it) < cfg.n_warmup;
+            const bool startp = bnd && !done;
+            __syncwarp();                                     // sP0 / sVAR alias the level-0 stack entry: reads before writes
+            if (startp) {
+                t += n;
+                E0 = 0.5 * ke - logp_q;
+                if (!isfinite(E0)) { status = 2; done = true; }
+                step = warm_new ? e_step : e_bar;
+                VST(sTL, q) VST(sTL + SLOT, p0) VST(sTL + 2 * SLOT, g)
+                VST(sTR, q) VST(sTR + SLOT, p0) VST(sTR + 2 * SLOT, g)
+                VST(sPS, p0)
+                if (fresh) { VST(gpr, q) VST(gpr + SLOT, g) prop_slot = 0; }    // starting point = slot of the accepted proposal
+                freemask = ((1u << BFB_NSLOT) - 1u) & ~(1u << prop_slot);
+                prop_E = E0; prop_lp = logp_q; Wtree.m = 1.; Wtree.k = 0; acc_sum = 0.; maxdE = 0.;
+                depth = 0; n_prop = 0; diverging = 0;
+                ns_dbl = !done;
+            }
+            bnd = false; fresh = false;
+            if (!__any_sync(BFB_FULL, !done)) break;
+        }
+        const bool live = !done;
+        ++dbg_rounds;
+        TICK(0)
+        // ---- uniforms of this round: lane lg of a quad holds draws 2 (t/2 + lg) + {0, 1} of its chain ----
+        const int64_t tb2 = (t >> 1) << 1;
+        const double2 ub = philox_pair_ni(seed, chain_id, (uint64_t)(t >> 1) + (uint64_t)lg);
+        const double ub0 = ub.x, ub1 = ub.y;
+        auto uni = [&](int64_t tt) -> double {
+            const int k = (int)(tt - tb2);
+            const int sl = (lane & ~3) | ((k >> 1) & 3);
+            const double a0 = __shfl_sync(BFB_FULL, ub0, sl), a1 = __shfl_sync(BFB_FULL, ub1, sl);
+            double u = (k & 1) ? a1 : a0;
+            if (__any_sync(BFB_FULL, k >= 8)) { if (k >= 8) u = draw_uniform_ni(seed, chain_id, (uint64_t)tt); }
+            return u;
+        };
+        // ================= start of a doubling: nuts.py:210 + the first lines of Tree.extend =================
+        if (__any_sync(BFB_FULL, ns_dbl)) {
+            const double ud = uni(t);
+            if (ns_dbl) {
+                t += 1;
+                const bool right = ud < 0.5;                     // log(u) < log(0.5) on the draw grid of bfb_rng.h
+                const double *src = right ? sTR : sTL;
+                VLD(q, src) VLD(p, src + SLOT) VLD(g, src + 2 * SLOT)
+                VST(sPB, p)
+                step = right ? fabs(step) : -fabs(step);
+                ileaf = 0;
+                ns_dbl = false;
+            }
+        }
+        TICK(1)
+        // ================= leapfrog: integration.py:68-95 =================
+        const double dt = 0.5 * step;
+        // in place (register diet: the state of a dead chain is left untouched, its MMA rows compute garbage that is ignored):
+        // p <- p + dt g (half kick), q <- q + step var p (drift); the old gradient is dead from here on
+        if (live) {
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+                p[r] = fma(dt, g[r], p[r]);
+                q[r] = fma(step, var[r] * p[r], q[r]);
+            }
+        }
+        double lp, ke2;
+        {
+            double gn[NR];
+            dmma_logp_grad<NR, C2>(bsm, lane, K, q, msm, msm + 32, live, lp, gn,
+                                   [&](const double (&gg)[NR]) {
+                                       double s_ = 0.;
+#pragma unroll
+                                       for (int r = 0; r < NR; ++r) { const double pn = fma(dt, gg[r], p[r]); s_ = fma(pn, var[r] * pn, s_); }
+                                       return s_;
+                                   }, ke2);
+            if (live) {
+#pragma unroll
+                for (int r = 0; r < NR; ++r) {
+                    g[r] = gn[r];
+                    p[r] = fma(dt, gn[r], p[r]);
+                }
+            }
+        }
+        const double E = 0.5 * ke2 - lp;
+        TICK(2)
+        // ================= leaf: Tree._single_step, nuts.py:105-132 =================
+        double dE = E - E0;
+        if (isnan(dE)) dE = INFINITY;
+        bool div_now = false, turn = false;
+        if (live) {
+            if (fabs(dE) > fabs(maxdE)) maxdE = dE;
+            n_prop += 1;
+            div_now = !(fabs(dE) < cfg.max_change);
+        }
+        const WT wl = wt_from_dE(div_now ? 0. : dE);
+        if (live && !div_now) {
+            acc_sum += wt_min1(wl);
+#pragma unroll
+            for (int r = 0; r < NR; ++r) { Rpl[r] = p[r]; Rps[r] = p[r]; }
+            RW = wl; REp = E; Rlpp = lp;
+            Rslot = __ffs(freemask) - 1;
+            freemask &= ~(1u << Rslot);
+            double *slot = gpr + (size_t)Rslot * 2 * SLOT;
+            VST(slot, q) VST(slot + SLOT, g)
+        }
+        if (div_now) diverging = 1;
+        TICK(3)
+        // ================= merges: Tree._build_subtree, nuts.py:134-178 =================
+        int lvl = 0;
+        bool need = live && !div_now && ((ileaf >> lvl) & 1);
+#pragma unroll 1
+        while (__any_sync(BFB_FULL, need)) {
+            const int lv = need ? lvl : 0;
+            ++dbg_merges;
+            const double *sp = stack_ptr(lv);
+            double T1pl[NR], T1pr[NR], T1ps[NR];
+            VLD(T1pl, sp) VLD(T1pr, sp + SLOT) VLD(T1ps, sp + 2 * SLOT)
+            double v0 = 0., v1 = 0., v2 = 0., v3 = 0., v4 = 0., v5 = 0.;
+            double ps[NR];
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+                ps[r] = T1ps[r] + Rps[r];
+                const double vT1pl = var[r] * T1pl[r], vp = var[r] * p[r];
+                const double ps1 = T1ps[r] + Rpl[r], ps2 = T1pr[r] + Rps[r];
+                v0 = fma(ps[r], vT1pl, v0); v1 = fma(ps[r], vp, v1);
+                v2 = fma(ps1, vT1pl, v2); v3 = fma(ps1, var[r] * Rpl[r], v3);
+                v4 = fma(ps2, var[r] * T1pr[r], v4); v5 = fma(ps2, vp, v5);
+            }
+            if (lvl < 1) { v2 = v3 = v4 = v5 = 1.; }         // extra checks only when depth > 1 (nuts.py:154)
+            const bool turning = quad_any_nonpos6(v0, v1, v2, v3, v4, v5, lane);
+            const double um = uni(t);
+            if (need) {
+                t += 1;
+                WT T1W; T1W.m = ssc[lv * 8]; T1W.k = (int)ssc[(10 + lv) * 8];
+                const int T1slot = (int)ssc[(40 + lv) * 8];
+                const WT tot = wt_add(T1W, RW);
+                if (!wt_select(um, tot, RW)) {               // keep tree1's proposal (nuts.py:164-167)
+                    freemask |= 1u << Rslot;
+                    Rslot = T1slot; REp = ssc[(20 + lv) * 8]; Rlpp = ssc[(30 + lv) * 8];
+                } else {
+                    freemask |= 1u << T1slot;
+                }
+#pragma unroll
+                for (int r = 0; r < NR; ++r) { Rpl[r] = T1pl[r]; Rps[r] = ps[r]; }
+                RW = tot;
+                if (turning) turn = true;
+                lvl++;
+            }
+            need = need && !turn && ((ileaf >> lvl) & 1);
+        }
+        TICK(4)
+        const bool fin = live && (div_now || turn || (ileaf + 1 == (1 << depth)));
+        const bool push = live && !fin;
+        if (__any_sync(BFB_FULL, push)) {
+            double *sp = stack_ptr(push ? lvl : 0);
+            if (push) {
+                VST(sp, Rpl) VST(sp + SLOT, p) VST(sp + 2 * SLOT, Rps)
+                ssc[lvl * 8] = RW.m; ssc[(10 + lvl) * 8] = (double)RW.k; ssc[(20 + lvl) * 8] = REp; ssc[(30 + lvl) * 8] = Rlpp;
+                ssc[(40 + lvl) * 8] = (double)Rslot;
+                ileaf += 1;
+            }
+        }
+        TICK(5)
+        // ================= end of a doubling: Tree.extend, nuts.py:45-103 =================
+        if (__any_sync(BFB_FULL, fin)) {
+            const double ue = uni(t);
+            const bool right = step > 0.;
+            if (fin) {
+                double *dst = right ? sTR : sTL;
+                VST(dst, q) VST(dst + SLOT, p) VST(dst + 2 * SLOT, g)
+                depth += 1;
+            }
+            const bool ok = fin && !div_now && !turn;
+            double PS[NR], PB[NR], TLp[NR], TRp[NR];
+            VLD(PS, sPS) VLD(PB, sPB) VLD(TLp, sTL + SLOT) VLD(TRp, sTR + SLOT)
+            double v0 = 0., v1 = 0., v2 = 0., v3 = 0., v4 = 0., v5 = 0.;
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+                PS[r] += Rps[r];
+                const double vp = var[r] * p[r], vRpl = var[r] * Rpl[r], vPB = var[r] * PB[r];
+                const double vTL = var[r] * TLp[r], vTR = var[r] * TRp[r];
+                v0 = fma(PS[r], vTL, v0); v1 = fma(PS[r], vTR, v1);
+                // nuts.py:86-98: self.p_sum is updated in place BEFORE p_sum1 / p_sum2 are formed, so the
+                // "old tree" p_sum entering them is already the total (see the oracle, bf_oracle.c tree_extend)
+                if (right) {
+                    const double ps1 = PS[r] + Rpl[r], ps2 = PB[r] + Rps[r];
+                    v2 = fma(ps1, vTL, v2); v3 = fma(ps1, vRpl, v3); v4 = fma(ps2, vPB, v4); v5 = fma(ps2, vp, v5);
+                } else {
+                    const double ps1 = Rps[r] + PB[r], ps2 = Rpl[r] + PS[r];
+                    v2 = fma(ps1, vp, v2); v3 = fma(ps1, vPB, v3); v4 = fma(ps2, vRpl, v4); v5 = fma(ps2, vTR, v5);
+                }
+            }
+            const bool turning = quad_any_nonpos6(v0, v1, v2, v3, v4, v5, lane);
+            if (ok) {
+                t += 1;
+                const WT tot = wt_add(Wtree, RW);
+                if (wt_select(ue, Wtree, RW)) {               // nuts.py:81-83 biased progressive: log(u) < size2 - size1
+                    freemask |= 1u << prop_slot;
+                    prop_slot = Rslot; prop_E = REp; prop_lp = Rlpp;
+                } else {
+                    freemask |= 1u << Rslot;
+                }
+                Wtree = tot;
+                VST(sPS, PS)
+                if (turning) turn = true;
+            }
+            if (fin) {
+                const bool iter_end = div_now || turn || (depth >= cfg.max_treedepth);
+                bnd = iter_end;
+                ns_dbl = !iter_end;
+            }
+        }
+        TICK(6)
+    }
+
+    // ---- persist chain state ----
+    if (exists && st.status[c] == 0) {
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            const int j = 4 * r + lg;
+            st.q[vb + j] = q[r]; st.g[vb + j] = g[r]; st.var[vb + j] = var[r];
+        }
+        if (lg == 0) {
+            st.logp[c] = logp_q; st.t_draw[c] = t; st.iter[c] = it0 + it;
+            st.status[c] = status;
+            if (tree_total) atomicAdd(st.tree_total, (unsigned long long)tree_total);
+        }
+    }
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) {
+        atomicAdd(st.tree_total + 1, (unsigned long long)dbg_rounds);
+        atomicAdd(st.tree_total + 2, (unsigned long long)dbg_merges);
+        atomicAdd(st.tree_total + 3, (unsigned long long)dbg_iend);
+#ifdef BFB_DMMA_TIMING
+        long long tsum = 0;
+        for (int k_ = 0; k_ < 7; ++k_) { atomicAdd(st.tree_total + 4 + k_, (unsigned long long)tacc[k_]); tsum += tacc[k_]; }
+        atomicAdd(st.tree_total + 11, (unsigned long long)(clock64() - t_unit0 - tsum));
+#endif
+        qv[2 + group] = chunk + 1;
+        if ((chunk + 1) * chunk_iters < out.n_iter) {
+            const int ti = atomicAdd(queue + 1, 1);
+            __threadfence();
+            ring[ti] = group;
+        }
+    }
+    }   // unit loop
+#undef VLD
+#undef VST
+}
+
+template <int NR, bool C2, int W>
+static int launch_dmma(bfb_context *h, const bfb_run_out &o, int n_iter)
+{
+    using SH = DmmaShape<NR, C2>;
+    constexpr int SLOT = NR * 32;
+    const int L = h->scfg.max_treedepth;
+    const int64_t C = h->cs.C;
+    const int n_groups = (int)((C + 7) / 8);
+    // one persistent block of W warps per SM (W = 4: one warp per scheduler, 4096 chains = 512 warps on 592 schedulers;
+    // W = 8 when there are more groups than that); the first LS levels of the tree stack live in shared memory, deeper
+    // (rarely touched) levels in an L2-resident buffer
+    const size_t fixed = sizeof(double) * (SH::FRAG_DOUBLES + 64);
+    const size_t budget = (size_t)(227 * 1024) - 1024 - fixed;
+    int LS = L;
+    while (LS > 1 && sizeof(double) * W * warp_smem_doubles(NR, LS) > budget) --LS;
+    if (const char *e = getenv("BFB200_STACK_LEVELS_SMEM")) { int v = atoi(e); if (v >= 1 && v <= L) LS = v; }
+    const size_t smem = fixed + sizeof(double) * W * warp_smem_doubles(NR, LS);
+    BFB_REQUIRE(smem <= 227 * 1024, BFB_ERR_ARG, "sampler needs %zu bytes of shared memory per block (> 227 KB)", smem);
+    BFB_CUDA(cudaFuncSetAttribute(nuts_dmma_kernel<NR, C2, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t deep = (size_t)(L > LS ? L - LS : 0) * 3 * SLOT;
+    const size_t prop = (size_t)BFB_NSLOT * 2 * SLOT;
+    if ((deep + prop) * (size_t)n_groups > h->gstack_len) {
+        if (h->gstack) cudaFree(h->gstack);
+        h->gstack = nullptr; h->gstack_len = 0;
+        BFB_CUDA(cudaMalloc((void **)&h->gstack, sizeof(double) * (deep + prop) * (size_t)n_groups));
+        h->gstack_len = (deep + prop) * (size_t)n_groups;
+    }
+    RunOutDevF od;
+    od.o = o; od.n_iter = n_iter;
+    int chunk_iters = (n_iter + 5) / 6;
+    if (chunk_iters < 16) chunk_iters = n_iter < 16 ? n_iter : 16;
+    if (const char *e = getenv("BFB200_CHUNK_ITERS")) { int v = atoi(e); if (v >= 1) chunk_iters = v; }
+    const int n_chunks = (n_iter + chunk_iters - 1) / chunk_iters;
+    const int64_t n_units64 = (int64_t)n_groups * n_chunks;
+    BFB_REQUIRE(n_units64 < (1ll << 31), BFB_ERR_ARG, "too many work units");
+    const size_t qlen = 2 + (size_t)n_groups + (size_t)n_units64;
+    if (qlen > h->queue_len) {
+        if (h->queue) cudaFree(h->queue);
+        h->queue = nullptr; h->queue_len = 0;
+        BFB_CUDA(cudaMalloc((void **)&h->queue, sizeof(int) * qlen));
+        h->queue_len = qlen;
+    }
+    queue_init_kernel<<<(unsigned)((n_units64 + 255) / 256), 256, 0, h->stream>>>(h->queue, n_groups, (int)n_units64);
+    h->launches++;
+    int blocks = h->sm_count;
+    const int64_t want = (n_groups + W - 1) / W;          // more warps than groups would only poll the queue
+    if ((int64_t)blocks > want) blocks = (int)want;
+    nuts_dmma_kernel<NR, C2, W><<<blocks, 32 * W, smem, h->stream>>>(h->dm, h->scfg, h->cs, od, L, LS, h->gstack,
+                                                                    h->gstack + deep * (size_t)n_groups, (int)h->iters_done,
+                                                                    chunk_iters, n_groups, (int)n_units64, h->queue);
+    h->launches++;
+    BFB_CUDA(cudaGetLastError());
+    return BFB_OK;
+}
+
+template <int NR, bool C2>
+static int launch_dmma_w(bfb_context *h, const bfb_run_out &o, int n_iter)
+{
+    int W = ((h->cs.C + 7) / 8 > (int64_t)h->sm_count * 4) ? 8 : 4;
+    if (const char *e = getenv("BFB200_WARPS_PER_SM")) { int v = atoi(e); if (v == 4 || v == 8) W = v; }
+    return W == 8 ? launch_dmma<NR, C2, 8>(h, o, n_iter) : launch_dmma<NR, C2, 4>(h, o, n_iter);
+}
+
+// returns 1 if this path does not apply (caller tries the next kernel), 0 on launch, <0 on error
+int bfb_launch_nuts_dmma(bfb_context *h, const bfb_run_out &o, int n_iter)
+{
+    const DevModel &M = h->dm;
+    if (M.frag_nr == 0 || M.has_c3 || M.use_decay || M.use_transform || M.use_scales) return 1;
+    if (h->scfg.max_treedepth > 10) return 1;
+    if (const char *e = getenv("BFB200_SAMPLER")) { if (strcmp(e, "dmma")) return 1; }
+    const bool c2 = M.has_c2;
+    switch (M.frag_nr) {
+    case 4: return c2 ? launch_dmma_w<4, true>(h, o, n_iter) : launch_dmma_w<4, false>(h, o, n_iter);
+    case 7: return c2 ? launch_dmma_w<7, true>(h, o, n_iter) : launch_dmma_w<7, false>(h, o, n_iter);
+    case 8: return c2 ? launch_dmma_w<8, true>(h, o, n_iter) : launch_dmma_w<8, false>(h, o, n_iter);
+    }
+    return 1;
+}

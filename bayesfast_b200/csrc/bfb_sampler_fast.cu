@@ -22,63 +22,9 @@
 //     u * (w1 + w2) < w2; one exp2 per leaf gives both the leaf weight and min(1, exp(-dE));
 //   * U-turn dot products of a merge are reduced packed (8 values over the G lanes) and only signs are voted;
 //   * Philox blocks are cached (two uniforms per block).
-#include "bfb_common.cuh"
+#include "bfb_nuts_common.cuh"
 #include <cstring>
-
-struct RunOutDevF {
-    bfb_run_out o;
-    int32_t n_iter;
-};
-
-struct WT { double m; int k; };   // weight = m * 2^k, m in [1, 2) (or m == 0)
-
-__device__ __forceinline__ double pow2i(int d)   // 2^d for d in [-1022, 1023], 0 below, +inf above
-{
-    if (d < -1022) return 0.;
-    if (d > 1023) return INFINITY;
-    return __longlong_as_double((long long)(d + 1023) << 52);
-}
-__device__ __forceinline__ WT wt_from_dE(double dE)
-{
-    // exp(-dE) = 2^y, y = -dE * log2(e)
-    const double y = -dE * 1.4426950408889634;
-    const double kf = floor(y);
-    WT w;
-    w.m = exp2(y - kf);
-    w.k = (int)kf;
-    return w;
-}
-__device__ __forceinline__ WT wt_add(WT a, WT b)
-{
-    WT r;
-    if (a.k >= b.k) { r.m = fma(b.m, pow2i(b.k - a.k), a.m); r.k = a.k; }
-    else { r.m = fma(a.m, pow2i(a.k - b.k), b.m); r.k = b.k; }
-    if (r.m >= 2.) { r.m *= 0.5; r.k += 1; }
-    return r;
-}
-// u * a < b
-__device__ __forceinline__ bool wt_select(double u, WT a, WT b)
-{
-    return u * a.m < b.m * pow2i(b.k - a.k);
-}
-__device__ __forceinline__ double wt_min1(WT w) { return (w.k >= 0) ? 1. : w.m * pow2i(w.k); }
-
-struct RngF {
-    uint64_t seed, chain, cached;
-    uint32_t w0, w1, w2, w3;
-};
-__device__ __forceinline__ double rng_uniform(RngF &r, int64_t t)
-{
-    const uint64_t blk = (uint64_t)t >> 1;
-    if (blk != r.cached) {
-        bfb_philox_block b = bfb_philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)r.chain,
-                                               (uint32_t)(r.chain >> 32), (uint32_t)r.seed, (uint32_t)(r.seed >> 32));
-        r.w0 = b.v[0]; r.w1 = b.v[1]; r.w2 = b.v[2]; r.w3 = b.v[3];
-        r.cached = blk;
-    }
-    const uint64_t w = (t & 1) ? ((uint64_t)r.w2 | ((uint64_t)r.w3 << 32)) : ((uint64_t)r.w0 | ((uint64_t)r.w1 << 32));
-    return bfb_u64_to_uniform(w);
-}
+#include <cstdlib>
 
 __device__ __forceinline__ double shx(double v, int m) { return __shfl_xor_sync(BFB_FULL, v, m); }
 
@@ -133,7 +79,6 @@ __device__ __forceinline__ bool gany_nonpos6(double v0, double v1, double v2, do
 // shared memory per chain, in doubles: XX (2 NP) | DD (NP) | TL q,p,g | TR q,p,g | PS | PB | stack levels (pl, pr, psum)
 // | per-level scalars [5][10]: weight mantissa, weight exponent, proposal energy, proposal logp, proposal slot
 __host__ __device__ inline int chain_smem_doubles(int NP, int LS) { return (11 + 3 * LS) * NP + 50; }
-#define BFB_NSLOT 12   // proposal slots per chain: tree proposal + one per pending subtree (<= L - 1) + the current one
 
 template <int G, int D, bool HAS_C2, int NK, int MB>
 __global__ void __launch_bounds__(32, MB) nuts_multi_kernel(DevModel M, bfb_sampler_cfg cfg, ChainState st, RunOutDevF out,
@@ -618,14 +563,6 @@ __global__ void __launch_bounds__(32, MB) nuts_multi_kernel(DevModel M, bfb_samp
         }
     }
     }   // unit loop
-}
-
-__global__ void queue_init_kernel(int *queue, int n_groups, int n_units)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) { queue[0] = 0; queue[1] = n_groups; }
-    if (i < n_groups) queue[2 + i] = 0;
-    if (i < n_units) queue[2 + n_groups + i] = (i < n_groups) ? i : -1;
 }
 
 template <int G, int D, bool HAS_C2, int NK, int MB = 8>
