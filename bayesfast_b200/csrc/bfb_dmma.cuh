@@ -15,8 +15,8 @@
 // C fragment: column 2 lg + e of tile tau is assigned the value index v = 2 tau + e of lane lg (dimension r = v, or r =
 // v - NR for the second matrix of a block).  No shuffles or shared-memory transposes between x and the results.
 //
-// Coefficient operand: host-built table bfrag[kt][tile][lane] (bfb_build_frag, bfb_model.cu), tiles grouped in blocks by
-// the A operand they multiply:  [S | A] . x   |   A^T . x^2   |   H . (x - mu).
+// Coefficient operand: host-built table bfrag[kt][tile pair][lane][2] (bfb_upload_model, bfb_model.cu), tiles grouped in
+// blocks by the A operand they multiply:  [S | A] . x   |   A^T . x^2   |   H . (x - mu).
 #pragma once
 #include "bfb_common.cuh"
 
@@ -26,7 +26,8 @@ struct DmmaShape {
     static constexpr int T2 = C2 ? (NR + 1) / 2 : 0;      // tiles multiplying x^2
     static constexpr int TD = (NR + 1) / 2;               // tiles multiplying x - mu
     static constexpr int NT = TX + T2 + TD;
-    static constexpr int FRAG_DOUBLES = NR * NT * 32;
+    static constexpr int NTP = (NT + 1) / 2;              // tile pairs: the B fragments of two tiles are one 16-byte load
+    static constexpr int FRAG_DOUBLES = NR * NTP * 64;
 };
 
 inline int bfb_frag_tiles(int nr, bool c2) { return (c2 ? nr : (nr + 1) / 2) + (c2 ? (nr + 1) / 2 : 0) + (nr + 1) / 2; }
@@ -63,50 +64,35 @@ __device__ __forceinline__ double qsum(double v)
     return v;
 }
 
-// lane partials of the polynomial part: gg = lin + S x + 2 x.(A x) + A^T x^2, hh = H (x - mu),
-// fpart = sum_own lin x + x.(Sx)/2 + x^2 (A x), bpart = sum_own (x - mu) hh
-template <int NR, bool C2>
-__device__ __forceinline__ void dmma_core(const double *bsm, int lane, const double (&x)[NR],
-                                          const double *mu_t, const double *lin_t, double (&gg)[NR],
-                                          double (&hh)[NR], double &fpart, double &bpart)
+// One evaluation = two GEMM stages.  Stage A: h = H (x - mu) (the TD tiles of the D block) gives the Mahalanobis radius,
+// i.e. the inside / outside decision of the radial bound (poly.py:466-469).  Outside points are then REPLACED by their
+// projection onto the ellipsoid before stage B, so the polynomial blocks ([S | A] . x, A^T . x^2) are evaluated exactly
+// once per point -- at x inside, at x_0 outside, which is all PolyModel._fj_bound (poly.py:480-503) needs.
+// Table tile order: D block first (tiles [0, TD)), then the x block (TX tiles), then the x^2 block (T2 tiles).
+template <int NR, bool C2, int T_LO, int T_HI>
+__device__ __forceinline__ void dmma_tiles(const double *bsm, int lane, const double (&a0)[NR], const double (&a1)[NR],
+                                           double (&acc)[DmmaShape<NR, C2>::NT][2])
 {
-    // mu_t / lin_t: [32] tables indexed by dimension (shared memory); read where used instead of living in registers
-    const int lg_ = lane & 3;
     using SH = DmmaShape<NR, C2>;
-    double acc[SH::NT][2];
-#pragma unroll
-    for (int t = 0; t < SH::NT; ++t) acc[t][0] = acc[t][1] = 0.;
-    const double *bp = bsm + lane;
+    const double2 *bp = reinterpret_cast<const double2 *>(bsm) + lane;
     // the table is loop invariant for the callers; without this fence the compiler hoists all B fragments into
     // registers (and spills them) instead of streaming them from shared memory next to the MMAs
     asm volatile("" ::: "memory");
 #pragma unroll
     for (int kt = 0; kt < NR; ++kt) {
-        const double ax = x[kt], ax2 = x[kt] * x[kt], ad = x[kt] - mu_t[4 * kt + lg_];
 #pragma unroll
-        for (int t = 0; t < SH::NT; ++t) {
-            const double b = bp[(kt * SH::NT + t) * 32];
-            const double a = (t < SH::TX) ? ax : (t < SH::TX + SH::T2) ? ax2 : ad;
-            dmma884(acc[t][0], acc[t][1], a, b);
-        }
-    }
-    fpart = 0.; bpart = 0.;
+        for (int tp = T_LO / 2; tp < (T_HI + 1) / 2; ++tp) {
+            const double2 b = bp[(kt * SH::NTP + tp) * 32];
 #pragma unroll
-    for (int r = 0; r < NR; ++r) {
-        const double y = acc[r / 2][r % 2];
-        const double h = acc[SH::TX + SH::T2 + r / 2][r % 2];
-        const double lin_r = lin_t[4 * r + lg_];
-        double g = lin_r + y;
-        fpart = fma(lin_r, x[r], fpart);
-        fpart = fma(0.5 * x[r], y, fpart);
-        if (C2) {
-            const double t = acc[(NR + r) / 2][(NR + r) % 2];
-            const double u = acc[SH::TX + r / 2][r % 2];
-            g += fma(2. * x[r], t, u);
-            fpart = fma(x[r] * x[r], t, fpart);
+            for (int e = 0; e < 2; ++e) {
+                const int t = 2 * tp + e;
+                if (t >= T_LO && t < T_HI) {
+                    // operand: the D block and the x block take a0 (x - mu, resp. x), the x^2 block takes a1
+                    const double a = (t < SH::TD + SH::TX) ? a0[kt] : a1[kt];
+                    dmma884(acc[t][0], acc[t][1], a, e ? b.y : b.x);
+                }
+            }
         }
-        gg[r] = g; hh[r] = h;
-        bpart = fma(x[r] - mu_t[4 * r + lg_], h, bpart);
     }
 }
 
@@ -116,50 +102,70 @@ struct DmmaConsts {
 };
 
 // PolyModel._fun_and_jac with the radial bound (poly.py:443-503) for the 8 points of the warp.
-// `ke_of` maps the gradient (own dims) to a lane partial that is reduced together with the others (the sampler's
-// kinetic energy of the new momentum); `live` masks points whose outside test should not trigger the second pass.
+// mu_t / lin_t: [32] tables indexed by dimension (shared memory).  `ke_of` maps the gradient (own dims) to a lane partial
+// that is reduced over the quad (the sampler's kinetic energy of the new momentum); `live` masks points whose outside
+// test must not count.  On return x holds the point the polynomial was evaluated at is NOT exposed: x_in is unchanged.
 template <int NR, bool C2, class KE>
 __device__ __forceinline__ void dmma_logp_grad(const double *bsm, int lane, const DmmaConsts &K,
-                                               const double (&x_in)[NR], const double *mu, const double *lin,
+                                               const double (&x_in)[NR], const double *mu_t, const double *lin_t,
                                                bool live, double &lp, double (&gn)[NR], KE &&ke_of, double &ke)
 {
+    using SH = DmmaShape<NR, C2>;
     const int lg = lane & 3;
-    double x[NR];
+    double acc[SH::NT][2];
 #pragma unroll
-    for (int r = 0; r < NR; ++r) x[r] = x_in[r];
-    double gg[NR], hh[NR], fpart, bpart;
-    dmma_core<NR, C2>(bsm, lane, x, mu, lin, gg, hh, fpart, bpart);
-    double kp = ke_of(gg), zz = 0.;
-    qsum4(kp, bpart, fpart, zz, lane);
-    double fp = fpart;
-    ke = kp;
+    for (int t = 0; t < SH::NT; ++t) acc[t][0] = acc[t][1] = 0.;
+    double d0[NR], x[NR];
 #pragma unroll
-    for (int r = 0; r < NR; ++r) gn[r] = gg[r];
-    const bool outside = live && (bpart > K.alpha2);
-    if (__any_sync(BFB_FULL, outside)) {
-        // PolyModel._fj_bound, poly.py:480-503: project onto the ellipsoid and evaluate there
-        // divisions by beta are done as multiplications by 1 / beta: the padded dimensions hold exact zeros and a zero
-        // numerator sends the FP64 division to its slow path (measured: one ~100-instruction subroutine call per round)
-        const double beta = sqrt(bpart), rbeta = 1. / beta;
-        double d0[NR], hd0[NR];
+    for (int r = 0; r < NR; ++r) { x[r] = x_in[r]; d0[r] = x_in[r] - mu_t[4 * r + lg]; }
+    // ---- stage A: h = H d, beta^2 = d . h ----
+    dmma_tiles<NR, C2, 0, SH::TD>(bsm, lane, d0, d0, acc);
+    double bpart = 0.;
 #pragma unroll
-        for (int r = 0; r < NR; ++r) {
-            const double mu_r = mu[4 * r + lg];
-            d0[r] = x[r] - mu_r; hd0[r] = hh[r];
-            if (outside) x[r] = (4 * r + lg < K.n) ? (K.alpha * x[r] + (beta - K.alpha) * mu_r) * rbeta : 0.;
+    for (int r = 0; r < NR; ++r) bpart = fma(d0[r], acc[r / 2][r % 2], bpart);
+    const double beta2 = qsum(bpart);
+    const bool outside = live && (beta2 > K.alpha2);
+    // divisions by beta are multiplications by 1 / beta: the padded dimensions hold exact zeros and a zero numerator
+    // sends the FP64 division to its slow path
+    const double beta = sqrt(beta2), rbeta = 1. / beta;
+    if (outside) {
+#pragma unroll
+        for (int r = 0; r < NR; ++r)
+            x[r] = (4 * r + lg < K.n) ? (K.alpha * x[r] + (beta - K.alpha) * mu_t[4 * r + lg]) * rbeta : 0.;
+    }
+    // ---- stage B: the polynomial at x (inside) or at the projection x_0 (outside) ----
+    double x2[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) x2[r] = x[r] * x[r];
+    dmma_tiles<NR, C2, SH::TD, SH::NT>(bsm, lane, x, x2, acc);
+    double fpart = 0., jd = 0.;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        const double y = acc[SH::TD + r / 2][r % 2];
+        const double lin_r = lin_t[4 * r + lg];
+        double g = lin_r + y;
+        fpart = fma(lin_r, x[r], fpart);
+        fpart = fma(0.5 * x[r], y, fpart);
+        if (C2) {
+            const double t = acc[SH::TD + (NR + r) / 2][(NR + r) % 2];
+            const double u = acc[SH::TD + SH::TX + r / 2][r % 2];
+            g += fma(2. * x[r], t, u);
+            fpart = fma(x2[r], t, fpart);
         }
-        double f1, b1;
-        dmma_core<NR, C2>(bsm, lane, x, mu, lin, gg, hh, f1, b1);
-        double jd = 0.;
-#pragma unroll
-        for (int r = 0; r < NR; ++r) jd = fma(gg[r], d0[r], jd);
-        double z1 = 0., z2 = 0.;
-        qsum4(f1, jd, z1, z2, lane);
-        double g2[NR];
-        const double f0 = K.c0 + f1;
+        gn[r] = g;
+        jd = fma(g, d0[r], jd);
+    }
+    double kp = ke_of(gn), zz = 0.;
+    qsum4(kp, jd, fpart, zz, lane);
+    ke = kp;
+    double fp = fpart;
+    if (__any_sync(BFB_FULL, outside)) {
+        // PolyModel._fj_bound, poly.py:480-503
+        const double f0 = K.c0 + fpart;
         const double sfac = (f0 - K.f_mu) / K.alpha - jd * rbeta;
+        double g2[NR];
 #pragma unroll
-        for (int r = 0; r < NR; ++r) g2[r] = gg[r] + sfac * (hd0[r] * rbeta);
+        for (int r = 0; r < NR; ++r) g2[r] = outside ? gn[r] + sfac * (acc[r / 2][r % 2] * rbeta) : gn[r];
         const double k2 = qsum(ke_of(g2));
         if (outside) {
 #pragma unroll

@@ -244,19 +244,21 @@ int bfb_upload_model(bfb_context *h)
         const int nr = bfb_frag_nr(n);
         if (nr > 0 && !h3 && np == 32) {
             const bool c2 = h2;
-            const int TX = c2 ? nr : (nr + 1) / 2, T2 = c2 ? (nr + 1) / 2 : 0, NT = bfb_frag_tiles(nr, c2);
-            std::vector<double> fr((size_t)nr * NT * 32, 0.);
+            const int TX = c2 ? nr : (nr + 1) / 2, NT = bfb_frag_tiles(nr, c2);
+            const int NTP = (NT + 1) / 2;
+            std::vector<double> fr((size_t)nr * NTP * 64, 0.);
             for (int kt = 0; kt < nr; ++kt)
                 for (int t = 0; t < NT; ++t)
                     for (int lane = 0; lane < 32; ++lane) {
                         const int k = 4 * kt + (lane & 3), gid = lane >> 2, own = gid >> 1, e = gid & 1;
                         const std::vector<double> *T = nullptr;
                         int v;
-                        if (t < TX) { v = 2 * t + e; if (v < nr) T = &S; else if (c2 && v < 2 * nr) { T = &A1T; v -= nr; } }
-                        else if (t < TX + T2) { v = 2 * (t - TX) + e; if (v < nr) T = &A2; }
-                        else { v = 2 * (t - TX - T2) + e; if (v < nr) T = &HT; }
+                        const int TD = (nr + 1) / 2;          // tile order: D block | x block | x^2 block
+                        if (t < TD) { v = 2 * t + e; if (v < nr) T = &HT; }
+                        else if (t < TD + TX) { v = 2 * (t - TD) + e; if (v < nr) T = &S; else if (c2 && v < 2 * nr) { T = &A1T; v -= nr; } }
+                        else { v = 2 * (t - TD - TX) + e; if (v < nr) T = &A2; }
                         const int j = 4 * v + own;
-                        if (T && !T->empty() && k < n && j < n) fr[((size_t)kt * NT + t) * 32 + lane] = (*T)[(size_t)k * np + j];
+                        if (T && !T->empty() && k < n && j < n) fr[(((size_t)kt * NTP + t / 2) * 32 + lane) * 2 + (t & 1)] = (*T)[(size_t)k * np + j];
                     }
             if ((rc = upload(h, fr, &D.bfrag))) return rc;
             D.frag_nr = nr; D.frag_nt = NT;

@@ -130,6 +130,7 @@ __global__ void __launch_bounds__(32 * W, 1) nuts_dmma_kernel(DevModel M, bfb_sa
     const int it0 = base_iter;                 // iterations done before this launch (same for every chain)
     double logp_q = st.logp[c];
     double log_step = st.log_step[c], log_bar = st.log_bar[c];
+    double e_step = exp(log_step), e_bar = exp(log_bar);    // refreshed only when dual averaging moves them
     int status = exists ? st.status[c] : 9;
     unsigned tree_total = 0, dbg_rounds = 0, dbg_merges = 0, dbg_iend = 0;
     long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64(); (void)tacc; (void)tlast;
@@ -149,7 +150,7 @@ __global__ void __launch_bounds__(32 * W, 1) nuts_dmma_kernel(DevModel M, bfb_sa
     // start the next unless done), ns_dbl = a doubling must be started
     bool bnd = !done, fresh = true, ns_dbl = false;
     // scratch vectors of the boundary section alias the (then empty) level-0 stack entry
-    double *sP0 = sST, *sVAR = sST + SLOT;
+    double *sP0 = sST, *sVAR = sST + SLOT, *sQN = sST + 2 * SLOT;
 
     auto stack_ptr = [&](int lvl) -> double * {
         return (lvl < LS) ? (sST + lvl * 3 * SLOT) : (gst + (size_t)(lvl - LS) * 3 * SLOT);
@@ -164,6 +165,12 @@ __global__ void __launch_bounds__(32 * W, 1) nuts_dmma_kernel(DevModel M, bfb_sa
             const bool endp = bnd && !fresh;
             const bool warm_old = (it0 + it) < cfg.n_warmup;            // of the iteration that ends
             const size_t orow = (size_t)c * out.n_iter + it;
+            // the accepted proposal (position, gradient) comes from the L2-resident pool: issue the loads first
+            double qn[NR], gx[NR];
+            {
+                const double *slot = gpr + (size_t)(endp ? prop_slot : 0) * 2 * SLOT;
+                VLD(qn, slot) VLD(gx, slot + SLOT)
+            }
             // ---- (1) per chain (its quad), predicated: accept statistic, dual averaging, statistics ----
             const double accept_stat = acc_sum / (double)(n_prop > 0 ? n_prop : 1);
             if (__any_sync(BFB_FULL, endp && warm_old && cfg.adapt_step_size)) {      // step_size.py:31-45
@@ -179,8 +186,9 @@ __global__ void __launch_bounds__(32 * W, 1) nuts_dmma_kernel(DevModel M, bfb_sa
                     log_bar = mk * log_step + (1. - mk) * log_bar;
                     if (lg == 0) { st.hbar[c] = hbar; st.log_step[c] = log_step; st.log_bar[c] = log_bar; st.count[c] = count + 1; }
                 }
+                const double es_ = exp(log_step), eb_ = exp(log_bar);
+                if (endp && warm_old && cfg.adapt_step_size) { e_step = es_; e_bar = eb_; }
             }
-            const double e_step = exp(log_step), e_bar = exp(log_bar);
             if (endp) {
                 if (lg == 0) {
                     if (out.o.logp) out.o.logp[orow] = prop_lp;
@@ -199,7 +207,7 @@ __global__ void __launch_bounds__(32 * W, 1) nuts_dmma_kernel(DevModel M, bfb_sa
                 it += 1;
                 if (it >= it_hi) done = true;
             }
-            if (bnd) { VST(sVAR, var) }
+            if (bnd) { VST(sVAR, var) VST(sQN, qn) }
             __syncwarp();
             // ---- (2) cooperative, lane j = dimension j, one chain at a time: new sample out, windowed Welford
             //      metric (metrics.py:186-211, 333-371), momentum draw (metrics.py:83-86) ----
@@ -213,7 +221,7 @@ __global__ void __launch_bounds__(32 * W, 1) nuts_dmma_kernel(DevModel M, bfb_sa
                 const int fl = __shfl_sync(BFB_FULL, (endp ? 1 : 0) | (done ? 2 : 0) | (warm_old ? 4 : 0), src);
                 const int j = lane, e = (j >> 2) * 32 + src + (j & 3);     // element of a vector slot holding dim j of that chain
                 if (fl & 1) {
-                    const double qj = (j < 4 * NR) ? gpr[(size_t)slot_s * 2 * SLOT + e] : 0.;
+                    const double qj = (j < 4 * NR) ? sQN[e] : 0.;
                     if (out.o.samples && j < n) out.o.samples[((size_t)c_s * out.n_iter + (it_s - 1)) * n + j] = qj;
                     if ((fl & 4) && cfg.adapt_metric) {
                         const int64_t n_samples = st.n_samples[c_s], previous_update = st.previous_update[c_s];
@@ -254,9 +262,8 @@ __global__ void __launch_bounds__(32 * W, 1) nuts_dmma_kernel(DevModel M, bfb_sa
             // ---- (3) per chain, predicated: the new state and the empty tree ----
             double p0[NR], part = 0.;
             {
-                const double *slot = gpr + (size_t)((bnd && !fresh) ? prop_slot : 0) * 2 * SLOT;
-                double qn[NR], gx[NR], vn[NR];
-                VLD(qn, slot) VLD(gx, slot + SLOT) VLD(vn, sVAR) VLD(p0, sP0)
+                double vn[NR];
+                VLD(vn, sVAR) VLD(p0, sP0)
                 if (bnd) {
 #pragma unroll
                     for (int r = 0; r < NR; ++r) { if (!fresh) { q[r] = qn[r]; g[r] = gx[r]; } var[r] = vn[r]; }
@@ -375,9 +382,14 @@ __global__ void __launch_bounds__(32 * W, 1) nuts_dmma_kernel(DevModel M, bfb_sa
         while (__any_sync(BFB_FULL, need)) {
             const int lv = need ? lvl : 0;
             ++dbg_merges;
-            const double *sp = stack_ptr(lv);
             double T1pl[NR], T1pr[NR], T1ps[NR];
-            VLD(T1pl, sp) VLD(T1pr, sp + SLOT) VLD(T1ps, sp + 2 * SLOT)
+            if (__any_sync(BFB_FULL, lv >= LS)) {             // a deep level somewhere in the warp: generic loads
+                const double *sp = stack_ptr(lv);
+                VLD(T1pl, sp) VLD(T1pr, sp + SLOT) VLD(T1ps, sp + 2 * SLOT)
+            } else {                                          // common case: shared-memory loads
+                const double *sp = sST + lv * 3 * SLOT;
+                VLD(T1pl, sp) VLD(T1pr, sp + SLOT) VLD(T1ps, sp + 2 * SLOT)
+            }
             double v0 = 0., v1 = 0., v2 = 0., v3 = 0., v4 = 0., v5 = 0.;
             double ps[NR];
 #pragma unroll
@@ -415,9 +427,15 @@ __global__ void __launch_bounds__(32 * W, 1) nuts_dmma_kernel(DevModel M, bfb_sa
         const bool fin = live && (div_now || turn || (ileaf + 1 == (1 << depth)));
         const bool push = live && !fin;
         if (__any_sync(BFB_FULL, push)) {
-            double *sp = stack_ptr(push ? lvl : 0);
+            const int lv = push ? lvl : 0;
+            if (__any_sync(BFB_FULL, lv >= LS)) {
+                double *sp = stack_ptr(lv);
+                if (push) { VST(sp, Rpl) VST(sp + SLOT, p) VST(sp + 2 * SLOT, Rps) }
+            } else {
+                double *sp = sST + lv * 3 * SLOT;
+                if (push) { VST(sp, Rpl) VST(sp + SLOT, p) VST(sp + 2 * SLOT, Rps) }
+            }
             if (push) {
-                VST(sp, Rpl) VST(sp + SLOT, p) VST(sp + 2 * SLOT, Rps)
                 ssc[lvl * 8] = RW.m; ssc[(10 + lvl) * 8] = (double)RW.k; ssc[(20 + lvl) * 8] = REp; ssc[(30 + lvl) * 8] = Rlpp;
                 ssc[(40 + lvl) * 8] = (double)Rslot;
                 ileaf += 1;
