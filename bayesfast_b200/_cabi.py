@@ -86,6 +86,8 @@ def lib():
             L.bfb_launch_count.restype = C.c_int64
             L.bfb_rng_fill.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int64, _dp, _dp]
             L.bfb_fp64_peak.argtypes = [C.c_void_p, C.c_int, _dp]
+            L.bfb_dmma_issue_test.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _dp]
+            L.bfb_sampler_last_path.argtypes = [C.c_void_p]
             for name, args, res in (
                     ('bfb_fit_accumulate', [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int], C.c_int),
                     ('bfb_fit_buffer_size', [C.c_void_p], C.c_int64),
@@ -288,6 +290,15 @@ class Handle:
         ms = C.c_float(0)
         check(self._L.bfb_last_kernel_ms(self._h, C.byref(ms)))
         return float(ms.value)
+
+    def sampler_last_path(self):
+        """kernel family of the last sampler run: 'generic', 'fast' (FMA multi-chain) or 'dmma' (FP64 tensor core)"""
+        return {0: 'generic', 1: 'fast', 2: 'dmma'}.get(int(self._L.bfb_sampler_last_path(self._h)), 'none')
+
+    def dmma_issue_test(self, nacc, src, warps_per_sm):
+        v = C.c_double(0)
+        check(self._L.bfb_dmma_issue_test(self._h, int(nacc), int(src), int(warps_per_sm), C.byref(v)))
+        return float(v.value)
 
     def launch_count(self):
         return int(self._L.bfb_launch_count(self._h))

@@ -120,6 +120,7 @@ struct bfb_context {
     size_t stage_len[2];
     int *queue;                // work queue of the multi-chain kernel
     size_t queue_len;
+    int last_path;             // kernel family of the last sampler launch: 0 generic, 1 FMA multi-chain, 2 tensor core
     int64_t iters_done;        // iterations completed by every chain since bfb_sampler_init / reset
     double *gstack;            // deep NUTS stack levels of the multi-chain kernel (L2 resident)
     size_t gstack_len;

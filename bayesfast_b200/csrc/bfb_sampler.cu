@@ -503,15 +503,19 @@ static int launch_run(bfb_context *h, int sampler, int n_iter, const bfb_run_out
     int rc = BFB_OK, fast_rc = 1;
     // NUTS kernel selection: tensor-core path, then the FMA multi-chain path, then the generic warp-per-chain kernel
     // (BFB200_SAMPLER = dmma | fast | generic pins one for tests and profiles)
-    if (sampler == BFB_NUTS && !getenv("BFB200_FORCE_GENERIC")) {
+    const char *sel_ = getenv("BFB200_SAMPLER");
+    if (sampler == BFB_NUTS && !getenv("BFB200_FORCE_GENERIC") && !(sel_ && !strcmp(sel_, "generic"))) {
         fast_rc = bfb_launch_nuts_dmma(h, od.o, n_iter);
+        if (fast_rc == 0) h->last_path = 2;
         if (fast_rc == 1) {
             const char *sel = getenv("BFB200_SAMPLER");
             if (!sel || !strcmp(sel, "fast") || !strcmp(sel, "dmma")) fast_rc = bfb_launch_nuts_fast(h, od.o, n_iter);
+            if (fast_rc == 0) h->last_path = 1;
         }
     }
     if (fast_rc < 0) return fast_rc;
     if (fast_rc == 0) return BFB_OK;
+    h->last_path = 0;
     const int wpb = 4;
     const int npl = h->np / 32;
     if (sampler == BFB_NUTS) {
@@ -621,6 +625,11 @@ extern "C" int bfb_sampler_run(bfb_handle h, int sampler, int32_t n_iter, const 
                             (double)dbg[8] / dbg[1], (double)dbg[9] / dbg[1], (double)dbg[10] / dbg[1], (double)dbg[11] / dbg[1]);
     }
     return BFB_OK;
+}
+
+extern "C" int bfb_sampler_last_path(bfb_handle h)
+{
+    return h ? h->last_path : -1;
 }
 
 // pinned host memory for the outputs of bfb_sampler_run (asynchronous, full-speed device-to-host copies)

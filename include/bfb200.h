@@ -148,6 +148,10 @@ int bfb_sampler_reset(bfb_handle h);
  * sum over chains and iterations of tree_size = leapfrog steps performed in trees. */
 int bfb_sampler_run(bfb_handle h, int sampler, int32_t n_iter, const bfb_run_out *out, int loc,
                     int64_t *total_tree_size);
+/* which kernel family ran the last bfb_sampler_run of this handle: 0 = generic warp-per-chain (bfb_sampler.cu),
+ * 1 = FMA multi-chain-per-warp (bfb_sampler_fast.cu), 2 = FP64 tensor core, 8 chains per warp (bfb_sampler_dmma.cu);
+ * -1 before the first run.  The environment variable BFB200_SAMPLER = dmma | fast | generic pins one (tests, profiles). */
+int bfb_sampler_last_path(bfb_handle h);
 /* page-locked host memory for the outputs of bfb_sampler_run: with it the device-to-host copies of one chunk of
  * iterations overlap the kernel of the next chunk */
 int bfb_host_alloc(size_t bytes, void **ptr);
@@ -170,6 +174,10 @@ int bfb_rng_fill(bfb_handle h, uint64_t seed, uint64_t chain, uint64_t t0, int64
 /* FP64 peak microbenchmarks for the roofline denominator (MEASURED_PEAKS.json has no FP64 entry):
  * kind 0 = DFMA, 1 = DMMA m8n8k4, 2 = both interleaved.  Returns TFLOP/s. */
 int bfb_fp64_peak(bfb_handle h, int kind, double *tflops);
+/* cycles one warp needs per dependent-free m8n8k4 DMMA with `nacc` (1, 2, 4, 8 or 15) independent accumulators, B operand
+ * from registers (src 0) or one shared-memory load per DMMA (src 1), `warps_per_sm` (4 or 8) resident warps: the issue
+ * model behind the tensor-core sampler. */
+int bfb_dmma_issue_test(bfb_handle h, int nacc, int src, int warps_per_sm, double *cycles_per_dmma);
 
 #ifdef __cplusplus
 }

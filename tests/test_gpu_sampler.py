@@ -198,3 +198,66 @@ def test_work_queue_chunking_is_invisible(handle, monkeypatch):
     for o in outs[1:]:
         for k in ('samples', 'tree_depth', 'tree_size', 'step_size', 'energy'):
             assert np.array_equal(o[k], outs[0][k]), k
+
+
+@pytest.mark.parametrize('n,order,C,n_iter,env', [
+    (26, 'cubic-2', 203, 40, {}),                                  # ragged: 203 = 25 groups of 8 + 3 chains
+    (26, 'cubic-2', 203, 40, {'BFB200_WARPS_PER_SM': '8'}),        # the 8-warps-per-SM launch used above 4736 chains
+    (26, 'cubic-2', 64, 48, {'BFB200_STACK_LEVELS_SMEM': '1', 'BFB200_CHUNK_ITERS': '7'}),   # deep stack levels in L2, odd chunks
+    (16, 'cubic-2', 70, 40, {}),
+    (31, 'cubic-2', 40, 30, {}),
+    (5, 'cubic-2', 50, 40, {}),
+    (26, 'quadratic', 100, 40, {}),
+])
+def test_tensor_core_nuts_vs_oracle(handle, oracle, monkeypatch, n, order, C, n_iter, env):
+    """bfb_sampler_dmma.cu (8 chains per warp as the rows of FP64 DMMAs): per-chain tree depths / sizes / divergences and
+    draw counts identical to the oracle fed with the device's own draws, and to the generic warp-per-chain kernel"""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    spec, cov = synthetic_spec(n, order, seed=70 + n)              # radial bound, no decay / transform: the headline shape
+    spec['alpha'] = spec['alpha'] / 1.6 * 0.9                      # tight bound: many leapfrogs leave the ellipsoid
+    handle.set_model(to_device_spec(spec))
+    x0 = (np.linalg.cholesky(cov) @ np.random.default_rng(8).normal(size=(n, C))).T
+    seed, chain0 = 777, 500
+    cfg = cfg_from({}, n_iter // 2, seed, chain0)
+    step0 = 1. / n**0.25
+    handle.sampler_init(cfg, x0, step0, np.ones(n), x0)
+    out = handle.sampler_run('NUTS', n_iter)
+    assert handle.sampler_last_path() == 'dmma'
+    st = handle.sampler_state()
+    assert np.all(st['status'] == 0)
+    U, Z = device_draws(handle, seed, st['n_draws'], chain0)
+    ref = oracle.OracleDensity(spec).run('NUTS', dict(n_iter=n_iter, n_warmup=n_iter // 2), x0, step0, np.ones(n),
+                                         draws_u=U, draws_z=Z)
+    assert np.array_equal(st['n_draws'], ref['n_draws'])
+    for k in INT_STATS:
+        assert np.array_equal(out[k], ref[k]), k
+    for k in FLT_STATS:
+        check_floats(out[k], ref[k], k)
+    check_floats(out['samples'], ref['samples'], 'samples')
+    assert out['total_tree_size'] == int(ref['tree_size'].sum())
+    assert np.allclose(st['final_var'], ref['final_var'], rtol=LATE_TOL)
+    # same run on the generic kernel
+    monkeypatch.setenv('BFB200_SAMPLER', 'generic')
+    handle.sampler_init(cfg, x0, step0, np.ones(n), x0)
+    gen = handle.sampler_run('NUTS', n_iter)
+    assert handle.sampler_last_path() == 'generic'
+    for k in INT_STATS:
+        assert np.array_equal(out[k], gen[k]), k
+
+
+def test_tensor_core_nuts_resume_and_reset(handle):
+    """chain state survives between launches (bfb_sampler_run called twice == once), and bfb_sampler_reset restarts it"""
+    n, C = 26, 96
+    spec, cov = synthetic_spec(n, 'cubic-2', seed=12)
+    handle.set_model(to_device_spec(spec))
+    x0 = (np.linalg.cholesky(cov) @ np.random.default_rng(3).normal(size=(n, C))).T
+    cfg = cfg_from({}, 30, 31)
+    handle.sampler_init(cfg, x0, 1. / n**0.25, np.ones(n), x0)
+    a = handle.sampler_run('NUTS', 50)
+    assert handle.sampler_last_path() == 'dmma'
+    handle.sampler_reset()
+    b1 = handle.sampler_run('NUTS', 20)
+    b2 = handle.sampler_run('NUTS', 30)
+    for k in ('samples', 'tree_depth', 'energy', 'step_size'):
+        assert np.array_equal(np.concatenate([b1[k], b2[k]], axis=1), a[k]), k
