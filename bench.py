@@ -6,9 +6,13 @@ bench.py -- NUTS leapfrog-steps x chains / s, cubic-2 PolyModel surrogate, d=26 
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
 One "step" = one complete NUTS run (n_iter=1500, n_warmup=500: reference defaults, sample_trace.py:499-512)
-of 4096 lock-step chains per GPU on the 26-D DES-Y1-shaped synthetic posterior through
-its fitted cubic-2 surrogate: ONE kernel launch (+ device-side reset of the chain state).  Weak scaling:
-every rank runs its own 4096 chains (global chain ids -> distinct Philox streams), no data-path collective.
+of 4096 chains per GPU on the 26-D DES-Y1-shaped synthetic posterior (SURVEY.md 8d config 3 = BASELINE.json
+configs[2]: 32768 chains over 8 GPUs) through its fitted cubic-2 surrogate: ONE kernel launch (+ device-side reset of
+the chain state).  Weak scaling: every rank runs its own 4096 chains (global chain ids -> distinct Philox streams), no
+data-path collective.  The dominant kernel is nuts_dmma_kernel (bfb_sampler_dmma.cu: 8 chains per warp as the rows of
+FP64 m8n8k4 DMMAs).  4096 chains are 512 warps -- fewer than the 592 warp schedulers of a B200 -- so the line also
+carries `more_chains` (north_star: "at least 4096 chains per GPU"): the same run with 16384 chains on this GPU, and
+`eval_kernel`: the batched surrogate evaluation kernel alone (bfb_eval_dmma.cu) against the same FP64 peak.
 
   value : sum(tree_size) of all ranks / max-over-ranks device time of K steps, inputs resident in HBM
   e2e   : the same through bayesfast_b200.sample() with host x_0 and all samples + stats copied back
@@ -113,6 +117,7 @@ def main():
     ap.add_argument('--chains-per-gpu', type=int, default=CHAINS_PER_GPU)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-budget', type=float, default=15.)
+    ap.add_argument('--no-extras', action='store_true', help='skip the more_chains / eval_kernel supplementary measurements')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
@@ -209,6 +214,7 @@ def main():
         leaves += lv
         kern_ms.append(kms)
     launches = h.launch_count() - l0
+    kernel_family = h.sampler_last_path()
     # device time of the timed steps: CUDA events around the kernel on the launching stream (+ the reset copies,
     # which the wall clock above includes); report the event time, max over ranks
     dev_ms = float(sum(kern_ms))
@@ -266,14 +272,52 @@ def main():
     except Exception:
         pass
     hbm_bytes = (leaves / args.steps) * 0 + C * N_ITER * (N_DIM * 8 + 7 * 8 + 3 * 4)
-    roofline = dict(bound='tensor', pipe='FP64 FMA pipe (DFMA; the FP64 tensor op DMMA issues to the same pipe: measured '
-                    '37.0 vs 37.2 TFLOP/s, 31 when interleaved)', achieved=achieved, peak=peak, unit='TFLOP/s',
+    roofline = dict(bound='tensor', pipe='FP64 pipe: the kernel evaluates the surrogate with m8n8k4 DMMAs; DFMA and DMMA issue to the same '
+                    'pipe (measured 37.0 vs 37.2 TFLOP/s, 31 when interleaved)', kernel='nuts_%s_kernel' % kernel_family, achieved=achieved, peak=peak, unit='TFLOP/s',
                     frac=achieved / peak, traffic=traffic,
                     peak_source='bfb_fp64_peak DFMA microbenchmark run just before the timed region on this GPU '
                                 '(MEASURED_PEAKS.json has no FP64 entry; nominal 37 TFLOP/s)',
                     algorithmic_flops_per_leapfrog=FLOPS_PER_LEAF, kernel_ms=k_ms,
                     hbm=dict(algorithmic_bytes_per_launch=hbm_bytes, achieved_gbs=hbm_bytes / (k_ms * 1e-3) / 1e9,
                              peak_gbs=peaks.get('hbm_gbs'), note='outputs only; the tree state stays in shared memory'))
+    extras = {}
+    if not args.no_extras:
+        # (a) the same run with 16384 chains on this GPU (two warps per scheduler instead of one): kernel-only value
+        C2 = 16384
+        prob2 = synthetic.des_shaped(N_DIM, seed=1, n_chain=C2, order=ORDER)
+        cfg2 = bfb.NTrace(n_chain=C2, n_iter=N_ITER, n_warmup=N_WARMUP, x_0=prob2['x_0'], random_generator=SEED)._cfg_dict(SEED, 0)
+        h.sampler_init(cfg2, prob2['x_0'], 1. / N_DIM**0.25, np.ones(N_DIM), prob2['x_0'])
+        best = None
+        for i in range(3):
+            h.sampler_reset()
+            flush.zero_()
+            torch.cuda.synchronize(dev)
+            r2 = h.sampler_run('NUTS', N_ITER, out_ptrs={})
+            ms2 = h.last_kernel_ms()
+            if i > 0 and (best is None or ms2 < best[1]):
+                best = (r2['total_tree_size'], ms2)
+        tf2 = FLOPS_PER_LEAF * best[0] / (best[1] * 1e-3) / 1e12
+        extras['more_chains'] = dict(chains_per_gpu=C2, value=best[0] / (best[1] * 1e-3), unit='leapfrog-steps*chains/s',
+                                     kernel_ms=best[1], outputs='none written (kernel only)', kernel=h.sampler_last_path(),
+                                     roofline_frac=tf2 / peak, achieved_tflops=tf2)
+        # (b) the surrogate evaluation kernel alone: logp + gradient of 2^22 device-resident points
+        Ce = 1 << 22
+        Xe = torch.randn(Ce, N_DIM, dtype=torch.float64, device='cuda:%d' % dev) @ torch.tensor(np.linalg.cholesky(prob['cov']).T, device='cuda:%d' % dev)
+        Xe = Xe.contiguous()
+        lpe = torch.empty(Ce, dtype=torch.float64, device='cuda:%d' % dev)
+        ge = torch.empty(Ce, N_DIM, dtype=torch.float64, device='cuda:%d' % dev)
+        torch.cuda.synchronize(dev)
+        mse = []
+        for i in range(6):
+            h.logp_and_grad_batch_dev(Xe.data_ptr(), Ce, lpe.data_ptr(), ge.data_ptr())
+            mse.append(h.last_kernel_ms())
+        mse = float(np.mean(mse[1:]))
+        fe = (8 * N_DIM * N_DIM + 15 * N_DIM) * Ce
+        extras['eval_kernel'] = dict(kernel='eval_dmma_kernel', points=Ce, ms=mse, points_per_s=Ce / mse * 1e3,
+                                     algorithmic_flops_per_point=8 * N_DIM * N_DIM + 15 * N_DIM,
+                                     roofline=dict(bound='tensor', achieved=fe / mse / 1e9, peak=peak, unit='TFLOP/s', frac=fe / mse / 1e9 / peak),
+                                     hbm_gbs=Ce * (2 * N_DIM + 1) * 8 / mse / 1e6)
+        del Xe, lpe, ge
     out = dict(metric='nuts_leapfrog_steps_x_chains_per_s', value=value, unit='leapfrog-steps*chains/s', n_gpus=world,
                steps=args.steps, warmup=args.warmup, ms_per_step=step_ms / args.steps, higher_is_better=True,
                scaling='weak', vs_baseline=None, dtype='f64', data='synthetic', config=config,
@@ -282,7 +326,7 @@ def main():
                gpu_launches=int(launches_all), roofline=roofline, clocks=summarize_clocks(samples),
                fit=dict(seconds=fit_s, kernel_ms=getattr(sur, '_fit_kernel_ms', None), n=N_DIM,
                         P=config['n_param'], N=config['n_fit'], rel_resid=getattr(sur, '_fit_rel_resid', None)),
-               mean_tree_size=leaves / args.steps / (C * N_ITER))
+               mean_tree_size=leaves / args.steps / (C * N_ITER), kernel='nuts_%s_kernel' % kernel_family, **extras)
     if world == 1 and not args.no_cpu_baseline:
         spec = den.to_spec()
         out['cpu_baseline'] = run_cpu_baseline(spec, prob, budget_s=args.cpu_budget)[0]
