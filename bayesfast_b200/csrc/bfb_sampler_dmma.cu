@@ -62,7 +62,7 @@ template <int NR, bool C2, int W>
 __global__ void __launch_bounds__(32 * W, 1) nuts_dmma_kernel(DevModel M, bfb_sampler_cfg cfg, ChainState st, RunOutDevF out,
                                                               int L, int LS, double *__restrict__ gstack,
                                                               double *__restrict__ gprop, int base_iter, int chunk_iters,
-                                                              int n_groups, int n_units, int *__restrict__ queue)
+                                                              int n_groups, int n_units, int *__restrict__ queue, int cpg)
 {
     using SH = DmmaShape<NR, C2>;
     constexpr int SLOT = NR * 32;
@@ -109,8 +109,8 @@ __global__ void __launch_bounds__(32 * W, 1) nuts_dmma_kernel(DevModel M, bfb_sa
     const int it_lo = chunk * chunk_iters;
     const int it_hi = min(out.n_iter, it_lo + chunk_iters);
     const long long t_unit0 = clock64(); (void)t_unit0;
-    const int64_t c_raw = (int64_t)group * 8 + gi;
-    const bool exists = c_raw < st.C;
+    const int64_t c_raw = (int64_t)group * cpg + gi;          // cpg <= 8 chains per group (rows of the MMA); the other quads idle
+    const bool exists = gi < cpg && c_raw < st.C;
     const int64_t c = exists ? c_raw : st.C - 1;
     double *gst = gstack + (size_t)group * (size_t)(L > LS ? L - LS : 0) * 3 * SLOT;   // deep stack levels (L2 resident)
     // proposals (q, grad) are written once, at the leaf, into a slot of an L2-resident pool and are afterwards only
@@ -531,13 +531,13 @@ __global__ void __launch_bounds__(32 * W, 1) nuts_dmma_kernel(DevModel M, bfb_sa
 }
 
 template <int NR, bool C2, int W>
-static int launch_dmma(bfb_context *h, const bfb_run_out &o, int n_iter)
+static int launch_dmma(bfb_context *h, const bfb_run_out &o, int n_iter, int cpg)
 {
     using SH = DmmaShape<NR, C2>;
     constexpr int SLOT = NR * 32;
     const int L = h->scfg.max_treedepth;
     const int64_t C = h->cs.C;
-    const int n_groups = (int)((C + 7) / 8);
+    const int n_groups = (int)((C + cpg - 1) / cpg);
     // one persistent block of W warps per SM (W = 4: one warp per scheduler, 4096 chains = 512 warps on 592 schedulers;
     // W = 8 when there are more groups than that); the first LS levels of the tree stack live in shared memory, deeper
     // (rarely touched) levels in an L2-resident buffer
@@ -579,7 +579,7 @@ static int launch_dmma(bfb_context *h, const bfb_run_out &o, int n_iter)
     if ((int64_t)blocks > want) blocks = (int)want;
     nuts_dmma_kernel<NR, C2, W><<<blocks, 32 * W, smem, h->stream>>>(h->dm, h->scfg, h->cs, od, L, LS, h->gstack,
                                                                     h->gstack + deep * (size_t)n_groups, (int)h->iters_done,
-                                                                    chunk_iters, n_groups, (int)n_units64, h->queue);
+                                                                    chunk_iters, n_groups, (int)n_units64, h->queue, cpg);
     h->launches++;
     BFB_CUDA(cudaGetLastError());
     return BFB_OK;
@@ -588,9 +588,16 @@ static int launch_dmma(bfb_context *h, const bfb_run_out &o, int n_iter)
 template <int NR, bool C2>
 static int launch_dmma_w(bfb_context *h, const bfb_run_out &o, int n_iter)
 {
-    int W = ((h->cs.C + 7) / 8 > (int64_t)h->sm_count * 4) ? 8 : 4;
+    // chains per group (MMA rows in use) and warps per SM.  The tree logic, not the tensor pipe, bounds a round, so with
+    // few chains it pays to leave MMA rows empty and spread the chains over more warps: the largest group count that still
+    // fits the resident warps wins (4096 chains: 7 per group = 586 warps on the 592 schedulers instead of 512).
+    const int64_t C = h->cs.C, slots4 = (int64_t)h->sm_count * 4;
+    int cpg = 8;
+    while (cpg > 7 && (C + cpg - 2) / (cpg - 1) <= slots4) --cpg;
+    if (const char *e = getenv("BFB200_CHAINS_PER_GROUP")) { int v = atoi(e); if (v >= 1 && v <= 8) cpg = v; }
+    int W = ((C + cpg - 1) / cpg > slots4) ? 8 : 4;
     if (const char *e = getenv("BFB200_WARPS_PER_SM")) { int v = atoi(e); if (v == 4 || v == 8) W = v; }
-    return W == 8 ? launch_dmma<NR, C2, 8>(h, o, n_iter) : launch_dmma<NR, C2, 4>(h, o, n_iter);
+    return W == 8 ? launch_dmma<NR, C2, 8>(h, o, n_iter, cpg) : launch_dmma<NR, C2, 4>(h, o, n_iter, cpg);
 }
 
 // returns 1 if this path does not apply (caller tries the next kernel), 0 on launch, <0 on error
