@@ -588,12 +588,11 @@ static int launch_dmma(bfb_context *h, const bfb_run_out &o, int n_iter, int cpg
 template <int NR, bool C2>
 static int launch_dmma_w(bfb_context *h, const bfb_run_out &o, int n_iter)
 {
-    // chains per group (MMA rows in use) and warps per SM.  The tree logic, not the tensor pipe, bounds a round, so with
-    // few chains it pays to leave MMA rows empty and spread the chains over more warps: the largest group count that still
-    // fits the resident warps wins (4096 chains: 7 per group = 586 warps on the 592 schedulers instead of 512).
+    // chains per group (MMA rows in use) and warps per SM.  Measured at 4096 chains (scripts/imbalance.py, full run): 8 per
+    // group 184 ms, 7 (586 warps on the 592 schedulers) 187 ms, 6 212 ms, 4 with two warps per scheduler 214 ms -- the cost of
+    // a round is per warp, not per live chain, so full MMAs win; BFB200_CHAINS_PER_GROUP overrides for experiments.
     const int64_t C = h->cs.C, slots4 = (int64_t)h->sm_count * 4;
     int cpg = 8;
-    while (cpg > 7 && (C + cpg - 2) / (cpg - 1) <= slots4) --cpg;
     if (const char *e = getenv("BFB200_CHAINS_PER_GROUP")) { int v = atoi(e); if (v >= 1 && v <= 8) cpg = v; }
     int W = ((C + cpg - 1) / cpg > slots4) ? 8 : 4;
     if (const char *e = getenv("BFB200_WARPS_PER_SM")) { int v = atoi(e); if (v == 4 || v == 8) W = v; }
