@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(32 * W, 1) nuts_dmma_kernel(DevModel M, bfb_sa
     const int64_t c_raw = (int64_t)group * cpg + gi;          // cpg <= 8 chains per group (rows of the MMA); the other quads idle
     const bool exists = gi < cpg && c_raw < st.C;
     const int64_t c = exists ? c_raw : st.C - 1;
-    double *gst = gstack + (size_t)group * (size_t)(L > LS ? L - LS : 0) * 3 * SLOT;   // deep stack levels (L2 resident)
+    double *gst = gstack + (size_t)group * (size_t)(L - 1 > LS ? L - 1 - LS : 0) * 3 * SLOT;   // deep stack levels (L2 resident)
     // proposals (q, grad) are written once, at the leaf, into a slot of an L2-resident pool and are afterwards only
     // referred to by their slot index: merges move no vectors.  Same thread writes and reads a given element.
     double *gpr = gprop + (size_t)group * BFB_NSLOT * 2 * SLOT;
@@ -152,8 +152,9 @@ __global__ void __launch_bounds__(32 * W, 1) nuts_dmma_kernel(DevModel M, bfb_sa
     // scratch vectors of the boundary section alias the (then empty) level-0 stack entry
     double *sP0 = sST, *sVAR = sST + SLOT, *sQN = sST + 2 * SLOT;
 
+    // stack entry of level lvl >= 1 (level 0 lives in registers, see "two leaves per round"): the first LS in shared memory
     auto stack_ptr = [&](int lvl) -> double * {
-        return (lvl < LS) ? (sST + lvl * 3 * SLOT) : (gst + (size_t)(lvl - LS) * 3 * SLOT);
+        return (lvl <= LS) ? (sST + (lvl - 1) * 3 * SLOT) : (gst + (size_t)(lvl - 1 - LS) * 3 * SLOT);
     };
 
 #pragma unroll 1
@@ -322,72 +323,115 @@ __global__ void __launch_bounds__(32 * W, 1) nuts_dmma_kernel(DevModel M, bfb_sa
             }
         }
         TICK(1)
-        // ================= leapfrog: integration.py:68-95 =================
+        // ================= two leaves per round =================
+        // A leaf with an even index is never followed by a decision (it is the left child of a level-0 merge), so a
+        // round integrates a PAIR of leaves whenever the doubling has at least two: the fixed cost of a round (every
+        // section below is paid per warp, not per chain) is spread over two leapfrogs, and the level-0 merge works on
+        // registers (level 0 of the stack is never stored).  Doublings of one leaf and divergent first leaves skip the
+        // second half.
         const double dt = 0.5 * step;
-        // in place (register diet: the state of a dead chain is left untouched, its MMA rows compute garbage that is ignored):
-        // p <- p + dt g (half kick), q <- q + step var p (drift); the old gradient is dead from here on
-        if (live) {
-#pragma unroll
-            for (int r = 0; r < NR; ++r) {
-                p[r] = fma(dt, g[r], p[r]);
-                q[r] = fma(step, var[r] * p[r], q[r]);
-            }
-        }
-        double lp, ke2;
-        {
-            double gn[NR];
-            dmma_logp_grad<NR, C2>(bsm, lane, K, q, msm, msm + 32, live, lp, gn,
-                                   [&](const double (&gg)[NR]) {
-                                       double s_ = 0.;
-#pragma unroll
-                                       for (int r = 0; r < NR; ++r) { const double pn = fma(dt, gg[r], p[r]); s_ = fma(pn, var[r] * pn, s_); }
-                                       return s_;
-                                   }, ke2);
-            if (live) {
+        bool div_now = false, turn = false, did2 = false;
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            const bool go = live && (half == 0 || (!div_now && depth >= 1));
+            if (half == 1 && !__any_sync(BFB_FULL, go)) break;
+            // ---- leapfrog: integration.py:68-95.  In place (register diet: the state of a chain that sits this half out is
+            // left untouched, its MMA row computes garbage that is ignored): p <- p + dt g, q <- q + step var p
+            if (go) {
 #pragma unroll
                 for (int r = 0; r < NR; ++r) {
-                    g[r] = gn[r];
-                    p[r] = fma(dt, gn[r], p[r]);
+                    p[r] = fma(dt, g[r], p[r]);
+                    q[r] = fma(step, var[r] * p[r], q[r]);
+                }
+            }
+            double lp, ke2;
+            {
+                double gn[NR];
+                dmma_logp_grad<NR, C2>(bsm, lane, K, q, msm, msm + 32, go, lp, gn,
+                                       [&](const double (&gg)[NR]) {
+                                           double s_ = 0.;
+#pragma unroll
+                                           for (int r = 0; r < NR; ++r) { const double pn = fma(dt, gg[r], p[r]); s_ = fma(pn, var[r] * pn, s_); }
+                                           return s_;
+                                       }, ke2);
+                if (go) {
+#pragma unroll
+                    for (int r = 0; r < NR; ++r) {
+                        g[r] = gn[r];
+                        p[r] = fma(dt, gn[r], p[r]);
+                    }
+                }
+            }
+            const double E = 0.5 * ke2 - lp;
+            // ---- leaf: Tree._single_step, nuts.py:105-132 ----
+            double dE = E - E0;
+            if (isnan(dE)) dE = INFINITY;
+            bool div_leaf = false;
+            if (go) {
+                if (fabs(dE) > fabs(maxdE)) maxdE = dE;
+                n_prop += 1;
+                div_leaf = !(fabs(dE) < cfg.max_change);
+                if (half == 1) ileaf += 1;
+            }
+            const WT wl = wt_from_dE(div_leaf ? 0. : dE);
+            const bool okl = go && !div_leaf;
+            int nslot = 0;
+            if (okl) {
+                acc_sum += wt_min1(wl);
+                nslot = __ffs(freemask) - 1;
+                freemask &= ~(1u << nslot);
+                double *slot = gpr + (size_t)nslot * 2 * SLOT;
+                VST(slot, q) VST(slot + SLOT, g)
+            }
+            if (div_leaf) { diverging = 1; div_now = true; }
+            if (half == 0) {
+                if (okl) {
+#pragma unroll
+                    for (int r = 0; r < NR; ++r) { Rpl[r] = p[r]; Rps[r] = p[r]; }
+                    RW = wl; REp = E; Rlpp = lp; Rslot = nslot;
+                }
+            } else {
+                // ---- level-0 merge of the two leaves (nuts.py:134-178 with depth 1: only the full-span U-turn test) ----
+                double v0 = 0., v1 = 0.;
+#pragma unroll
+                for (int r = 0; r < NR; ++r) {
+                    const double ps = Rps[r] + p[r];
+                    v0 = fma(ps, var[r] * Rpl[r], v0); v1 = fma(ps, var[r] * p[r], v1);
+                }
+                double z0 = 1., z1 = 1.;
+                qsum4(v0, v1, z0, z1, lane);
+                const double um = uni(t);
+                if (okl) {
+                    t += 1;
+                    const WT tot = wt_add(RW, wl);
+                    if (!wt_select(um, tot, wl)) {               // keep the first leaf as the proposal (nuts.py:164-167)
+                        freemask |= 1u << nslot;
+                    } else {
+                        freemask |= 1u << Rslot;
+                        Rslot = nslot; REp = E; Rlpp = lp;
+                    }
+#pragma unroll
+                    for (int r = 0; r < NR; ++r) Rps[r] += p[r];
+                    RW = tot;
+                    if (v0 <= 0. || v1 <= 0.) turn = true;
+                    did2 = true;
                 }
             }
         }
-        const double E = 0.5 * ke2 - lp;
-        TICK(2)
-        // ================= leaf: Tree._single_step, nuts.py:105-132 =================
-        double dE = E - E0;
-        if (isnan(dE)) dE = INFINITY;
-        bool div_now = false, turn = false;
-        if (live) {
-            if (fabs(dE) > fabs(maxdE)) maxdE = dE;
-            n_prop += 1;
-            div_now = !(fabs(dE) < cfg.max_change);
-        }
-        const WT wl = wt_from_dE(div_now ? 0. : dE);
-        if (live && !div_now) {
-            acc_sum += wt_min1(wl);
-#pragma unroll
-            for (int r = 0; r < NR; ++r) { Rpl[r] = p[r]; Rps[r] = p[r]; }
-            RW = wl; REp = E; Rlpp = lp;
-            Rslot = __ffs(freemask) - 1;
-            freemask &= ~(1u << Rslot);
-            double *slot = gpr + (size_t)Rslot * 2 * SLOT;
-            VST(slot, q) VST(slot + SLOT, g)
-        }
-        if (div_now) diverging = 1;
         TICK(3)
-        // ================= merges: Tree._build_subtree, nuts.py:134-178 =================
-        int lvl = 0;
-        bool need = live && !div_now && ((ileaf >> lvl) & 1);
+        // ================= merges above level 0: Tree._build_subtree, nuts.py:134-178 =================
+        int lvl = 1;
+        bool need = did2 && !turn && ((ileaf >> lvl) & 1);
 #pragma unroll 1
         while (__any_sync(BFB_FULL, need)) {
-            const int lv = need ? lvl : 0;
+            const int lv = need ? lvl : 1;
             ++dbg_merges;
             double T1pl[NR], T1pr[NR], T1ps[NR];
-            if (__any_sync(BFB_FULL, lv >= LS)) {             // a deep level somewhere in the warp: generic loads
+            if (__any_sync(BFB_FULL, lv > LS)) {              // a deep level somewhere in the warp: generic loads
                 const double *sp = stack_ptr(lv);
                 VLD(T1pl, sp) VLD(T1pr, sp + SLOT) VLD(T1ps, sp + 2 * SLOT)
             } else {                                          // common case: shared-memory loads
-                const double *sp = sST + lv * 3 * SLOT;
+                const double *sp = sST + (lv - 1) * 3 * SLOT;
                 VLD(T1pl, sp) VLD(T1pr, sp + SLOT) VLD(T1ps, sp + 2 * SLOT)
             }
             double v0 = 0., v1 = 0., v2 = 0., v3 = 0., v4 = 0., v5 = 0.;
@@ -401,7 +445,6 @@ __global__ void __launch_bounds__(32 * W, 1) nuts_dmma_kernel(DevModel M, bfb_sa
                 v2 = fma(ps1, vT1pl, v2); v3 = fma(ps1, var[r] * Rpl[r], v3);
                 v4 = fma(ps2, var[r] * T1pr[r], v4); v5 = fma(ps2, vp, v5);
             }
-            if (lvl < 1) { v2 = v3 = v4 = v5 = 1.; }         // extra checks only when depth > 1 (nuts.py:154)
             const bool turning = quad_any_nonpos6(v0, v1, v2, v3, v4, v5, lane);
             const double um = uni(t);
             if (need) {
@@ -427,12 +470,12 @@ __global__ void __launch_bounds__(32 * W, 1) nuts_dmma_kernel(DevModel M, bfb_sa
         const bool fin = live && (div_now || turn || (ileaf + 1 == (1 << depth)));
         const bool push = live && !fin;
         if (__any_sync(BFB_FULL, push)) {
-            const int lv = push ? lvl : 0;
-            if (__any_sync(BFB_FULL, lv >= LS)) {
+            const int lv = push ? lvl : 1;
+            if (__any_sync(BFB_FULL, lv > LS)) {
                 double *sp = stack_ptr(lv);
                 if (push) { VST(sp, Rpl) VST(sp + SLOT, p) VST(sp + 2 * SLOT, Rps) }
             } else {
-                double *sp = sST + lv * 3 * SLOT;
+                double *sp = sST + (lv - 1) * 3 * SLOT;
                 if (push) { VST(sp, Rpl) VST(sp + SLOT, p) VST(sp + 2 * SLOT, Rps) }
             }
             if (push) {
@@ -549,7 +592,7 @@ static int launch_dmma(bfb_context *h, const bfb_run_out &o, int n_iter, int cpg
     const size_t smem = fixed + sizeof(double) * W * warp_smem_doubles(NR, LS);
     BFB_REQUIRE(smem <= 227 * 1024, BFB_ERR_ARG, "sampler needs %zu bytes of shared memory per block (> 227 KB)", smem);
     BFB_CUDA(cudaFuncSetAttribute(nuts_dmma_kernel<NR, C2, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const size_t deep = (size_t)(L > LS ? L - LS : 0) * 3 * SLOT;
+    const size_t deep = (size_t)(L - 1 > LS ? L - 1 - LS : 0) * 3 * SLOT;
     const size_t prop = (size_t)BFB_NSLOT * 2 * SLOT;
     if ((deep + prop) * (size_t)n_groups > h->gstack_len) {
         if (h->gstack) cudaFree(h->gstack);
