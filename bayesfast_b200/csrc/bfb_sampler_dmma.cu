@@ -331,7 +331,11 @@ __global__ void __launch_bounds__(32 * W, 1) nuts_dmma_kernel(DevModel M, bfb_sa
         // second half.
         const double dt = 0.5 * step;
         bool div_now = false, turn = false, did2 = false;
+#ifdef BFB_UNROLL_HALVES
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
         for (int half = 0; half < 2; ++half) {
             const bool go = live && (half == 0 || (!div_now && depth >= 1));
             if (half == 1 && !__any_sync(BFB_FULL, go)) break;
