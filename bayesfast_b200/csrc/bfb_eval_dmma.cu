@@ -11,7 +11,7 @@
 #include <cstdlib>
 
 template <int NR, bool C2>
-__global__ void __launch_bounds__(128) eval_dmma_kernel(DevModel M, const double *__restrict__ X, int64_t C,
+__global__ void __launch_bounds__(128, 4) eval_dmma_kernel(DevModel M, const double *__restrict__ X, int64_t C,
                                                         double *__restrict__ LP, double *__restrict__ G)
 {
     using SH = DmmaShape<NR, C2>;
@@ -51,7 +51,7 @@ static int launch_eval(bfb_context *h, const double *X, int64_t C, double *LP, d
     using SH = DmmaShape<NR, C2>;
     const size_t smem = sizeof(double) * (SH::FRAG_DOUBLES + 64);
     BFB_CUDA(cudaFuncSetAttribute(eval_dmma_kernel<NR, C2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 3;
+    int per_sm = 4;
     if (const char *e = getenv("BFB200_EVAL_BLOCKS_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 8) per_sm = v; }
     int64_t want = (C + 31) / 32;
     int blocks = (int)(want < (int64_t)h->sm_count * per_sm ? want : (int64_t)h->sm_count * per_sm);
