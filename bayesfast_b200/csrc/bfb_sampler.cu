@@ -19,6 +19,7 @@
 
 int bfb_launch_nuts_fast(bfb_context *h, const bfb_run_out &o, int n_iter);   // bfb_sampler_fast.cu
 int bfb_launch_nuts_dmma(bfb_context *h, const bfb_run_out &o, int n_iter);   // bfb_sampler_dmma.cu
+int bfb_launch_hmc_dmma(bfb_context *h, const bfb_run_out &o, int n_iter);    // bfb_sampler_dmma.cu
 
 struct RunOutDev {
     bfb_run_out o;
@@ -512,6 +513,10 @@ static int launch_run(bfb_context *h, int sampler, int n_iter, const bfb_run_out
             if (!sel || !strcmp(sel, "fast") || !strcmp(sel, "dmma")) fast_rc = bfb_launch_nuts_fast(h, od.o, n_iter);
             if (fast_rc == 0) h->last_path = 1;
         }
+    }
+    if (sampler == BFB_HMC && !getenv("BFB200_FORCE_GENERIC") && !(sel_ && !strcmp(sel_, "generic"))) {
+        fast_rc = bfb_launch_hmc_dmma(h, od.o, n_iter);
+        if (fast_rc == 0) h->last_path = 2;
     }
     if (fast_rc < 0) return fast_rc;
     if (fast_rc == 0) return BFB_OK;

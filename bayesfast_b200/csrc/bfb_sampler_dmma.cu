@@ -577,6 +577,276 @@ __global__ void __launch_bounds__(32 * W, 1) nuts_dmma_kernel(DevModel M, bfb_sa
 #undef VST
 }
 
+// ----------------------------------------------------------------------------------------------------------------------
+// HMC (samplers/hmc.py:16-49): every chain makes n_int_step leapfrogs per iteration, so the 8 chains of a warp ARE in lock
+// step and nothing of the tree machinery is needed: an iteration is momentum draw, n_int_step x (kick, drift, tensor-core
+// evaluation, kick), Metropolis test, adaptation, outputs.  Same work units and queue as the NUTS kernel.
+// ----------------------------------------------------------------------------------------------------------------------
+template <int NR, bool C2, int W>
+__global__ void __launch_bounds__(32 * W, 1) hmc_dmma_kernel(DevModel M, bfb_sampler_cfg cfg, ChainState st, RunOutDevF out,
+                                                             int base_iter, int chunk_iters, int n_groups, int n_units,
+                                                             int *__restrict__ queue)
+{
+    using SH = DmmaShape<NR, C2>;
+    extern __shared__ double smem[];
+    double *bsm = smem;
+    double *msm = smem + SH::FRAG_DOUBLES;    // mu[32] | lin[32]
+    for (int i = threadIdx.x; i < SH::FRAG_DOUBLES; i += blockDim.x) bsm[i] = M.bfrag[i];
+    if (threadIdx.x < 32) {
+        msm[threadIdx.x] = M.use_bound ? M.mu[threadIdx.x] : 0.;
+        msm[32 + threadIdx.x] = M.lin[threadIdx.x];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, gi = lane >> 2, lg = lane & 3;
+    const int n = M.n;
+    DmmaConsts K;
+    K.c0 = M.c0[0]; K.alpha = M.alpha; K.alpha2 = M.use_bound ? M.alpha * M.alpha : INFINITY;
+    K.f_mu = M.use_bound ? M.f_mu[0] : 0.; K.n = n;
+    volatile int *qv = queue;
+    volatile int *ring = queue + 2 + n_groups;
+#pragma unroll 1
+    for (;;) {
+    int idx = 0, group = 0;
+    if (lane == 0) {
+        idx = atomicAdd(queue, 1);
+        if (idx < n_units) { while ((group = ring[idx]) < 0) __nanosleep(100); }
+    }
+    idx = __shfl_sync(BFB_FULL, idx, 0);
+    if (idx >= n_units) break;
+    group = __shfl_sync(BFB_FULL, group, 0);
+    __threadfence();
+    const int chunk = qv[2 + group];
+    const int it_lo = chunk * chunk_iters;
+    const int it_hi = min(out.n_iter, it_lo + chunk_iters);
+    const int64_t c_raw = (int64_t)group * 8 + gi;
+    const bool exists = c_raw < st.C;
+    const int64_t c = exists ? c_raw : st.C - 1;
+    const size_t vb = (size_t)c * M.np;
+    double q[NR], p[NR], g[NR], var[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        const int j = 4 * r + lg;
+        q[r] = st.q[vb + j]; g[r] = st.g[vb + j]; var[r] = st.var[vb + j]; p[r] = 0.;
+    }
+    const uint64_t seed = cfg.seed, chain_id = (uint64_t)(cfg.chain0 + c);
+    int64_t t = st.t_draw[c];
+    const int it0 = base_iter;
+    double logp_q = st.logp[c];
+    double log_step = st.log_step[c], log_bar = st.log_bar[c], hbar = st.hbar[c];
+    const double mu_da = st.mu_da[c];
+    int64_t count = st.count[c], n_samples = st.n_samples[c], previous_update = st.previous_update[c];
+    int adapt_window = st.adapt_window[c];
+    double fg_n = st.fg_n[c], bg_n = st.bg_n[c];
+    int status = exists ? st.status[c] : 9;
+    unsigned long long tree_total = 0;
+
+#pragma unroll 1
+    for (int it = it_lo; it < it_hi; ++it) {
+        if (!__any_sync(BFB_FULL, status == 0)) break;
+        const bool warm = (it0 + it) < cfg.n_warmup;
+        // momentum: metrics.py:83-86 (each quad draws the n normals of its chain, lane lg the dimensions 4 r + lg)
+        double qs[NR], gs[NR], part = 0.;
+#pragma unroll 1
+        for (int r = 0; r < NR; ++r) {
+            // rolled: one call site; the register arrays are indexed through the unrolled select below
+            const int j = 4 * r + lg;
+            const double z = (j < n) ? draw_normal_ni(seed, chain_id, (uint64_t)(t + j)) : 0.;
+#pragma unroll
+            for (int rr = 0; rr < NR; ++rr) if (rr == r) p[rr] = z;
+        }
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            p[r] = (4 * r + lg < n) ? p[r] / sqrt(var[r]) : 0.;
+            part = fma(p[r], var[r] * p[r], part);
+            qs[r] = q[r]; gs[r] = g[r];
+        }
+        const double ke0 = qsum(part);
+        bool live = status == 0;
+        double E0 = 0.5 * ke0 - logp_q;
+        if (live) {
+            t += n;
+            if (!isfinite(E0)) { status = 2; live = false; }                 // base_hmc.py:72-76
+        }
+        const double eps = warm ? exp(log_step) : exp(log_bar);               // step_size.py:25-29
+        const double dt = 0.5 * eps;
+        double lp = logp_q, E = E0;
+#pragma unroll 1
+        for (int s_ = 0; s_ < cfg.n_int_step; ++s_) {
+            // integration.py:68-95
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+                p[r] = fma(dt, g[r], p[r]);
+                q[r] = fma(eps, var[r] * p[r], q[r]);
+            }
+            double gn[NR], ke2;
+            dmma_logp_grad<NR, C2>(bsm, lane, K, q, msm, msm + 32, live, lp, gn,
+                                   [&](const double (&gg)[NR]) {
+                                       double a_ = 0.;
+#pragma unroll
+                                       for (int r = 0; r < NR; ++r) { const double pn = fma(dt, gg[r], p[r]); a_ = fma(pn, var[r] * pn, a_); }
+                                       return a_;
+                                   }, ke2);
+#pragma unroll
+            for (int r = 0; r < NR; ++r) { g[r] = gn[r]; p[r] = fma(dt, gn[r], p[r]); }
+            E = 0.5 * ke2 - lp;
+        }
+        // HMC._hamiltonian_step, hmc.py:31-49
+        double dE;
+        int diverging = 0;
+        if (isfinite(E)) { dE = E0 - E; diverging = fabs(dE) > cfg.max_change; }
+        else { dE = -INFINITY; diverging = 1; }
+        double accept_stat;
+        { const double e_ = exp(dE); accept_stat = e_ < 1. ? e_ : 1.; }
+        const double ua = draw_uniform_ni(seed, chain_id, (uint64_t)t);
+        bool accepted = false;
+        if (live && !diverging) { t += 1; accepted = !(ua >= accept_stat); }
+        const double s_logp = lp, s_energy = E;
+        if (accepted) logp_q = lp;
+        else {
+#pragma unroll
+            for (int r = 0; r < NR; ++r) { q[r] = qs[r]; g[r] = gs[r]; }
+        }
+        if (live) {
+            tree_total += (unsigned long long)cfg.n_int_step;
+            if (warm && cfg.adapt_step_size) {          // step_size.py:31-45
+                const double cnt = (double)count;
+                const double w = 1. / (cnt + cfg.t0);
+                hbar = ((1. - w) * hbar + w * (cfg.target_accept - accept_stat));
+                log_step = mu_da - hbar * sqrt(cnt) / cfg.gamma;
+                const double mk = pow(cnt, -cfg.k);
+                log_bar = mk * log_step + (1. - mk) * log_bar;
+                count += 1;
+            }
+            if (warm && cfg.adapt_metric) {             // metrics.py:186-211, 351-357; Welford state in global memory
+                const int64_t delta = n_samples - previous_update;
+                const bool upd = ((delta + 1) % cfg.update_window == 0);
+                const bool swap = delta >= adapt_window;
+                fg_n += 1.; bg_n += 1.;
+#pragma unroll
+                for (int r = 0; r < NR; ++r) {
+                    const int j = 4 * r + lg;
+                    if (j < n) {
+                        double fgm = st.fg_mean[vb + j], fgr = st.fg_raw[vb + j], bgm = st.bg_mean[vb + j], bgr = st.bg_raw[vb + j];
+                        double od = q[r] - fgm;
+                        fgm += od / fg_n;
+                        fgr += 1. * od * (q[r] - fgm);
+                        od = q[r] - bgm;
+                        bgm += od / bg_n;
+                        bgr += 1. * od * (q[r] - bgm);
+                        if (upd) var[r] = fgr / fg_n;
+                        if (swap) { fgm = bgm; fgr = bgr; bgm = 0.; bgr = 0.; }
+                        st.fg_mean[vb + j] = fgm; st.fg_raw[vb + j] = fgr; st.bg_mean[vb + j] = bgm; st.bg_raw[vb + j] = bgr;
+                    }
+                }
+                if (swap) { fg_n = bg_n; bg_n = 10.; previous_update = n_samples; if (cfg.doubling) adapt_window *= 2; }
+                n_samples += 1;
+            }
+            const size_t o = (size_t)c * out.n_iter + it;
+            if (out.o.samples) {
+#pragma unroll
+                for (int r = 0; r < NR; ++r) if (4 * r + lg < n) out.o.samples[o * n + 4 * r + lg] = q[r];
+            }
+            if (lg == 0) {
+                if (out.o.logp) out.o.logp[o] = s_logp;
+                if (out.o.energy) out.o.energy[o] = s_energy;
+                if (out.o.tree_depth) out.o.tree_depth[o] = accepted ? 1 : 0;
+                if (out.o.tree_size) out.o.tree_size[o] = cfg.n_int_step;
+                if (out.o.mean_tree_accept) out.o.mean_tree_accept[o] = accept_stat;
+                if (out.o.step_size) out.o.step_size[o] = exp(log_step);
+                if (out.o.step_size_bar) out.o.step_size_bar[o] = exp(log_bar);
+                if (out.o.energy_change) out.o.energy_change[o] = dE;
+                if (out.o.max_energy_change) out.o.max_energy_change[o] = 0.;
+                if (out.o.diverging) out.o.diverging[o] = diverging;
+            }
+        }
+    }
+    // ---- persist chain state ----
+    if (exists && st.status[c] == 0) {
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            const int j = 4 * r + lg;
+            st.q[vb + j] = q[r]; st.g[vb + j] = g[r]; st.var[vb + j] = var[r];
+        }
+        if (lg == 0) {
+            st.logp[c] = logp_q; st.fg_n[c] = fg_n; st.bg_n[c] = bg_n;
+            st.log_step[c] = log_step; st.log_bar[c] = log_bar; st.hbar[c] = hbar;
+            st.count[c] = count; st.n_samples[c] = n_samples; st.previous_update[c] = previous_update;
+            st.adapt_window[c] = adapt_window; st.t_draw[c] = t; st.iter[c] = it0 + it_hi;
+            st.status[c] = status;
+            if (tree_total) atomicAdd(st.tree_total, tree_total);
+        }
+    }
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) {
+        qv[2 + group] = chunk + 1;
+        if ((chunk + 1) * chunk_iters < out.n_iter) {
+            const int ti = atomicAdd(queue + 1, 1);
+            __threadfence();
+            ring[ti] = group;
+        }
+    }
+    }   // unit loop
+}
+
+template <int NR, bool C2, int W>
+static int launch_hmc_dmma(bfb_context *h, const bfb_run_out &o, int n_iter)
+{
+    using SH = DmmaShape<NR, C2>;
+    const int64_t C = h->cs.C;
+    const int n_groups = (int)((C + 7) / 8);
+    const size_t smem = sizeof(double) * (SH::FRAG_DOUBLES + 64);
+    BFB_CUDA(cudaFuncSetAttribute(hmc_dmma_kernel<NR, C2, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RunOutDevF od;
+    od.o = o; od.n_iter = n_iter;
+    int chunk_iters = (n_iter + 5) / 6;
+    if (chunk_iters < 16) chunk_iters = n_iter < 16 ? n_iter : 16;
+    if (const char *e = getenv("BFB200_CHUNK_ITERS")) { int v = atoi(e); if (v >= 1) chunk_iters = v; }
+    const int n_chunks = (n_iter + chunk_iters - 1) / chunk_iters;
+    const int64_t n_units64 = (int64_t)n_groups * n_chunks;
+    BFB_REQUIRE(n_units64 < (1ll << 31), BFB_ERR_ARG, "too many work units");
+    const size_t qlen = 2 + (size_t)n_groups + (size_t)n_units64;
+    if (qlen > h->queue_len) {
+        if (h->queue) cudaFree(h->queue);
+        h->queue = nullptr; h->queue_len = 0;
+        BFB_CUDA(cudaMalloc((void **)&h->queue, sizeof(int) * qlen));
+        h->queue_len = qlen;
+    }
+    queue_init_kernel<<<(unsigned)((n_units64 + 255) / 256), 256, 0, h->stream>>>(h->queue, n_groups, (int)n_units64);
+    h->launches++;
+    int blocks = h->sm_count;
+    const int64_t want = (n_groups + W - 1) / W;
+    if ((int64_t)blocks > want) blocks = (int)want;
+    hmc_dmma_kernel<NR, C2, W><<<blocks, 32 * W, smem, h->stream>>>(h->dm, h->scfg, h->cs, od, (int)h->iters_done, chunk_iters,
+                                                                   n_groups, (int)n_units64, h->queue);
+    h->launches++;
+    BFB_CUDA(cudaGetLastError());
+    return BFB_OK;
+}
+
+template <int NR, bool C2>
+static int launch_hmc_dmma_w(bfb_context *h, const bfb_run_out &o, int n_iter)
+{
+    int W = ((h->cs.C + 7) / 8 > (int64_t)h->sm_count * 4) ? 8 : 4;
+    if (const char *e = getenv("BFB200_WARPS_PER_SM")) { int v = atoi(e); if (v == 4 || v == 8) W = v; }
+    return W == 8 ? launch_hmc_dmma<NR, C2, 8>(h, o, n_iter) : launch_hmc_dmma<NR, C2, 4>(h, o, n_iter);
+}
+
+// returns 1 if this path does not apply (caller uses the generic kernel), 0 on launch, <0 on error
+int bfb_launch_hmc_dmma(bfb_context *h, const bfb_run_out &o, int n_iter)
+{
+    const DevModel &M = h->dm;
+    if (M.frag_nr == 0 || M.has_c3 || M.use_decay || M.use_transform || M.use_scales) return 1;
+    if (const char *e = getenv("BFB200_SAMPLER")) { if (strcmp(e, "dmma")) return 1; }
+    const bool c2 = M.has_c2;
+    switch (M.frag_nr) {
+    case 4: return c2 ? launch_hmc_dmma_w<4, true>(h, o, n_iter) : launch_hmc_dmma_w<4, false>(h, o, n_iter);
+    case 7: return c2 ? launch_hmc_dmma_w<7, true>(h, o, n_iter) : launch_hmc_dmma_w<7, false>(h, o, n_iter);
+    case 8: return c2 ? launch_hmc_dmma_w<8, true>(h, o, n_iter) : launch_hmc_dmma_w<8, false>(h, o, n_iter);
+    }
+    return 1;
+}
+
 template <int NR, bool C2, int W>
 static int launch_dmma(bfb_context *h, const bfb_run_out &o, int n_iter, int cpg)
 {
