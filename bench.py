@@ -300,6 +300,19 @@ def main():
         extras['more_chains'] = dict(chains_per_gpu=C2, value=best[0] / (best[1] * 1e-3), unit='leapfrog-steps*chains/s',
                                      kernel_ms=best[1], outputs='none written (kernel only)', kernel=h.sampler_last_path(),
                                      roofline_frac=tf2 / peak, achieved_tflops=tf2)
+        # (a2) lock-step HMC (hmc.py:16-49, n_int_step = 32) on the same chains: the tensor-core integrator without the NUTS
+        # tree bookkeeping (hmc_dmma_kernel), kernel only
+        hm = {}
+        for Ch, x0h in ((C, x0), (C2, prob2['x_0'])):
+            cfgh = bfb.HTrace(n_chain=Ch, n_iter=300, n_warmup=100, x_0=x0h, n_int_step=32, random_generator=SEED)._cfg_dict(SEED, 0)
+            h.sampler_init(cfgh, x0h, 1. / N_DIM**0.25, np.ones(N_DIM), x0h)
+            h.sampler_run('HMC', 100, out_ptrs={})                         # step-size adaptation
+            rh = h.sampler_run('HMC', 100, out_ptrs={})
+            msh = h.last_kernel_ms()
+            tfh = FLOPS_PER_LEAF * rh['total_tree_size'] / (msh * 1e-3) / 1e12
+            hm[str(Ch)] = dict(chains_per_gpu=Ch, value=rh['total_tree_size'] / (msh * 1e-3), unit='leapfrog-steps*chains/s',
+                               kernel_ms=msh, roofline_frac=tfh / peak, achieved_tflops=tfh)
+        extras['hmc_kernel'] = dict(kernel='hmc_dmma_kernel', n_int_step=32, iterations=100, outputs='none written (kernel only)', runs=hm)
         # (b) the surrogate evaluation kernel alone: logp + gradient of 2^22 device-resident points
         Ce = 1 << 22
         Xe = torch.randn(Ce, N_DIM, dtype=torch.float64, device='cuda:%d' % dev) @ torch.tensor(np.linalg.cholesky(prob['cov']).T, device='cuda:%d' % dev)
