@@ -114,6 +114,8 @@ struct bfb_context {
     ChainState cs;
     std::vector<void *> chain_allocs;
     std::vector<void *> chain_snapshot;
+    int64_t alloc_C;           // shape the chain arrays were allocated for (reused by bfb_sampler_init)
+    int alloc_np;
     cudaStream_t copy_stream;  // device-to-host output pipeline of bfb_sampler_run
     cudaEvent_t ev_k[2], ev_c[2];
     void *stage[2];

@@ -65,6 +65,7 @@ extern "C" int bfb_create(int device, bfb_handle *out)
     h->queue_len = 0;
     h->iters_done = 0;
     h->last_path = -1;
+    h->alloc_C = 0; h->alloc_np = 0;
     h->stage[0] = h->stage[1] = nullptr;
     h->stage_len[0] = h->stage_len[1] = 0;
     memset(&h->dm, 0, sizeof(h->dm));

@@ -414,25 +414,42 @@ extern "C" int bfb_sampler_init(bfb_handle h, const bfb_sampler_cfg *cfg, int64_
     BFB_REQUIRE(cfg->update_window > 0 && cfg->adapt_window > 0, BFB_ERR_ARG, "adapt/update window must be positive");
     BFB_CUDA(cudaSetDevice(h->device));
     BFB_CUDA(cudaStreamSynchronize(h->stream));
-    bfb_free_list(h->chain_allocs);
-    h->chain_snapshot.clear();
     h->has_chains = false;
     h->scfg = *cfg;
     const int n = h->n, np = h->np;
     ChainState &s = h->cs;
-    memset(&s, 0, sizeof(s));
-    s.C = C; s.n = n; s.np = np;
     int rc;
     const size_t V = (size_t)C * np;
-    if ((rc = dalloc(h, &s.q, V)) || (rc = dalloc(h, &s.g, V)) || (rc = dalloc(h, &s.var, V)) ||
-        (rc = dalloc(h, &s.fg_mean, V)) || (rc = dalloc(h, &s.fg_raw, V)) || (rc = dalloc(h, &s.bg_mean, V)) ||
-        (rc = dalloc(h, &s.bg_raw, V)) || (rc = dalloc(h, &s.logp, C)) || (rc = dalloc(h, &s.fg_n, C)) ||
-        (rc = dalloc(h, &s.bg_n, C)) || (rc = dalloc(h, &s.log_step, C)) || (rc = dalloc(h, &s.log_bar, C)) ||
-        (rc = dalloc(h, &s.hbar, C)) || (rc = dalloc(h, &s.mu_da, C)) || (rc = dalloc(h, &s.count, C)) ||
-        (rc = dalloc(h, &s.n_samples, C)) || (rc = dalloc(h, &s.previous_update, C)) ||
-        (rc = dalloc(h, &s.adapt_window, C)) || (rc = dalloc(h, &s.t_draw, C)) || (rc = dalloc(h, &s.iter, C)) ||
-        (rc = dalloc(h, &s.status, C)) || (rc = dalloc(h, &s.tree_total, 16)))
-        return rc;
+    // device arrays are kept between calls with the same shape: cudaMalloc / cudaFree are slow (and contended when every
+    // GPU of a box has its own process), and sample() calls this once per run
+    const bool reuse = !h->chain_allocs.empty() && h->alloc_C == C && h->alloc_np == np && !h->chain_snapshot.empty();
+    if (reuse) {
+        for (auto &a : state_arrays(s)) BFB_CUDA(cudaMemsetAsync(a.first, 0, a.second, h->stream));
+        BFB_CUDA(cudaMemsetAsync(s.tree_total, 0, 16 * sizeof(unsigned long long), h->stream));
+    } else {
+        bfb_free_list(h->chain_allocs);
+        h->chain_snapshot.clear();
+        h->alloc_C = 0; h->alloc_np = 0;
+        memset(&s, 0, sizeof(s));
+        s.C = C; s.n = n; s.np = np;
+        if ((rc = dalloc(h, &s.q, V)) || (rc = dalloc(h, &s.g, V)) || (rc = dalloc(h, &s.var, V)) ||
+            (rc = dalloc(h, &s.fg_mean, V)) || (rc = dalloc(h, &s.fg_raw, V)) || (rc = dalloc(h, &s.bg_mean, V)) ||
+            (rc = dalloc(h, &s.bg_raw, V)) || (rc = dalloc(h, &s.logp, C)) || (rc = dalloc(h, &s.fg_n, C)) ||
+            (rc = dalloc(h, &s.bg_n, C)) || (rc = dalloc(h, &s.log_step, C)) || (rc = dalloc(h, &s.log_bar, C)) ||
+            (rc = dalloc(h, &s.hbar, C)) || (rc = dalloc(h, &s.mu_da, C)) || (rc = dalloc(h, &s.count, C)) ||
+            (rc = dalloc(h, &s.n_samples, C)) || (rc = dalloc(h, &s.previous_update, C)) ||
+            (rc = dalloc(h, &s.adapt_window, C)) || (rc = dalloc(h, &s.t_draw, C)) || (rc = dalloc(h, &s.iter, C)) ||
+            (rc = dalloc(h, &s.status, C)) || (rc = dalloc(h, &s.tree_total, 16)))
+            return rc;
+        for (auto &a : state_arrays(s)) {
+            void *p = nullptr;
+            BFB_CUDA(cudaMalloc(&p, a.second));
+            h->chain_allocs.push_back(p);
+            h->chain_snapshot.push_back(p);
+        }
+        h->alloc_C = C; h->alloc_np = np;
+    }
+    s.C = C; s.n = n; s.np = np;
     std::vector<double> vq(V, 0.), vvar(V, 1.), vfm(V, 0.), vfr(V, 0.);
     std::vector<double> fgn(C), bgn(C, 10.), ls(C), mu(C);
     std::vector<int64_t> cnt(C, 1);
@@ -467,13 +484,10 @@ extern "C" int bfb_sampler_init(bfb_handle h, const bfb_sampler_cfg *cfg, int64_
     h->launches++;
     BFB_CUDA(cudaGetLastError());
     // device-resident snapshot of the initial state (bfb_sampler_reset restarts the same run without host traffic)
-    h->chain_snapshot.clear();
-    for (auto &a : state_arrays(s)) {
-        void *p = nullptr;
-        BFB_CUDA(cudaMalloc(&p, a.second));
-        h->chain_allocs.push_back(p);
-        h->chain_snapshot.push_back(p);
-        BFB_CUDA(cudaMemcpyAsync(p, a.first, a.second, cudaMemcpyDeviceToDevice, h->stream));
+    {
+        auto arrs = state_arrays(s);
+        for (size_t i = 0; i < arrs.size(); ++i)
+            BFB_CUDA(cudaMemcpyAsync(h->chain_snapshot[i], arrs[i].first, arrs[i].second, cudaMemcpyDeviceToDevice, h->stream));
     }
     BFB_CUDA(cudaStreamSynchronize(h->stream));
     h->has_chains = true;

@@ -30,3 +30,35 @@ def shard_bounds(total, rank, world):
     base, rem = divmod(int(total), int(world))
     lo = rank * base + min(rank, rem)
     return lo, lo + base + (1 if rank < rem else 0)
+
+
+def bind_to_gpu_numa(device):
+    """Pin this process (and hence its first-touch / page-locked host buffers) to the CPUs of the NUMA node the GPU hangs off.
+    With one process per GPU the device-to-host output copies of all ranks otherwise land on whatever node the scheduler
+    picked (measured on an 8 x B200 box: end-to-end 260 ms per step against 161 ms for a single rank).  Best effort:
+    returns the CPU list used, or None when the topology cannot be read."""
+    import subprocess
+    try:
+        bus = subprocess.run(['nvidia-smi', '-i', str(int(device)), '--query-gpu=pci.bus_id', '--format=csv,noheader'],
+                             capture_output=True, text=True, timeout=10).stdout.strip().lower()
+        if not bus:
+            return None
+        if bus.count(':') == 2 and len(bus.split(':')[0]) == 8:
+            bus = bus[4:]                                   # 00000000:1B:00.0 -> 0000:1b:00.0
+        base = '/sys/bus/pci/devices/' + bus
+        cpulist = open(base + '/local_cpulist').read().strip()
+        cpus = set()
+        for part in cpulist.split(','):
+            if '-' in part:
+                a, b = part.split('-')
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = set(os.sched_getaffinity(0))
+        cpus &= allowed
+        if not cpus or cpus == allowed:
+            return sorted(cpus) if cpus else None
+        os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:
+        return None

@@ -156,7 +156,10 @@ def main():
     import torch.distributed as dist
     import bayesfast_b200 as bfb
     from bayesfast_b200 import _cabi
+    numa_cpus = None
     if world > 1:
+        from bayesfast_b200.runtime import bind_to_gpu_numa
+        numa_cpus = bind_to_gpu_numa(local)       # host buffers of this rank on the NUMA node of its GPU
         torch.cuda.set_device(local)
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     dev = local
@@ -230,7 +233,7 @@ def main():
     value = leaves_all / (step_ms * 1e-3)
 
     # ---- e2e: the public API, host buffers in and out ----
-    e2e_leaves, e2e_ms, h2d, d2h = 0, 0., 0, 0
+    e2e_leaves, e2e_ms, h2d, d2h, e2e_kernel_ms = 0, 0., 0, 0, 0.
     n_e2e = max(1, min(args.steps, 3))
     for i in range(1 + n_e2e):
         flush.zero_()
@@ -240,6 +243,7 @@ def main():
         barrier()
         if i > 0:
             e2e_ms += (time.perf_counter() - t0) * 1e3
+            e2e_kernel_ms += tt.kernel_ms
             e2e_leaves += tt.total_tree_size
             h2d = x0.nbytes * 2 + 8 * C + x0.nbytes
             d2h = sum(v.nbytes for k, v in tt.arrays.items() if k not in ('samples_original', 'logp_original'))
@@ -335,7 +339,8 @@ def main():
                steps=args.steps, warmup=args.warmup, ms_per_step=step_ms / args.steps, higher_is_better=True,
                scaling='weak', vs_baseline=None, dtype='f64', data='synthetic', config=config,
                e2e=dict(value=e2e_value, unit='leapfrog-steps*chains/s', h2d_bytes_per_step=int(h2d),
-                        d2h_bytes_per_step=int(d2h), ms_per_step=e2e_ms / n_e2e),
+                        d2h_bytes_per_step=int(d2h), ms_per_step=e2e_ms / n_e2e, kernel_ms_per_step=e2e_kernel_ms / n_e2e,
+                        numa_cpus_rank0=(len(numa_cpus) if numa_cpus else None)),
                gpu_launches=int(launches_all), roofline=roofline, clocks=summarize_clocks(samples),
                fit=dict(seconds=fit_s, kernel_ms=getattr(sur, '_fit_kernel_ms', None), n=N_DIM,
                         P=config['n_param'], N=config['n_fit'], rel_resid=getattr(sur, '_fit_rel_resid', None)),
