@@ -85,7 +85,7 @@ def test_fit_vs_lstsq(oracle, n, N, scale):
     Fo, _ = oracle.OracleDensity(spec).poly_eval_batch(x[:512])
     verr = np.max(np.abs(F - Fo) / np.maximum(np.abs(Fo), 1e-3 * np.max(np.abs(Fo))))
     print('n', n, 'N', N, 'scale', scale, 'coef errs', errs, 'value err', verr, 'resid', s._fit_rel_resid)
-    assert max(errs) < (COEF_TOL if scale == 1.0 else 1e-8)
+    assert max(errs) < COEF_TOL          # measured 4e-12 .. 2e-11, also for the ill-scaled inputs (scale 0.3)
     assert verr < VAL_TOL
     mu, hess, alpha = oracle.bound_from_points(x)
     assert block_err(s._hess, hess) < 1e-10 and abs(s._alpha - alpha) < 1e-11 * alpha
