@@ -827,9 +827,20 @@ static int launch_hmc_dmma(bfb_context *h, const bfb_run_out &o, int n_iter)
 template <int NR, bool C2>
 static int launch_hmc_dmma_w(bfb_context *h, const bfb_run_out &o, int n_iter)
 {
-    int W = ((h->cs.C + 7) / 8 > (int64_t)h->sm_count * 4) ? 8 : 4;
-    if (const char *e = getenv("BFB200_WARPS_PER_SM")) { int v = atoi(e); if (v == 4 || v == 8) W = v; }
-    return W == 8 ? launch_hmc_dmma<NR, C2, 8>(h, o, n_iter) : launch_hmc_dmma<NR, C2, 4>(h, o, n_iter);
+    // warps per SM: the kernel needs no per-warp shared memory, so the register file is the only limit (255 registers up
+    // to 8 warps, 168 at 12, 128 at 16: ptxas spills a few hundred bytes per thread, which the extra warps more than hide)
+    const int64_t groups = (h->cs.C + 7) / 8, sms = h->sm_count;
+    // measured (d=26 cubic-2, n_int_step=32): 16384 chains 52.5 % of the FP64 peak with 8 warps, 51.6 % with 12; 32768 chains
+    // 56.0 / 57.9 / 57.9 % with 8 / 12 / 16
+    int W = groups > sms * 16 ? 12 : groups > sms * 4 ? 8 : 4;
+    if (const char *e = getenv("BFB200_HMC_WARPS_PER_SM")) { int v = atoi(e); if (v == 4 || v == 8 || v == 12 || v == 16) W = v; }
+    else if (const char *e2 = getenv("BFB200_WARPS_PER_SM")) { int v = atoi(e2); if (v == 4 || v == 8) W = v; }
+    switch (W) {
+    case 16: return launch_hmc_dmma<NR, C2, 16>(h, o, n_iter);
+    case 12: return launch_hmc_dmma<NR, C2, 12>(h, o, n_iter);
+    case 8: return launch_hmc_dmma<NR, C2, 8>(h, o, n_iter);
+    }
+    return launch_hmc_dmma<NR, C2, 4>(h, o, n_iter);
 }
 
 // returns 1 if this path does not apply (caller uses the generic kernel), 0 on launch, <0 on error
