@@ -29,13 +29,26 @@ __global__ void __launch_bounds__(128, 4) eval_dmma_kernel(DevModel M, const dou
     K.c0 = M.c0[0]; K.alpha = M.alpha; K.alpha2 = M.use_bound ? M.alpha * M.alpha : INFINITY;
     K.f_mu = M.use_bound ? M.f_mu[0] : 0.; K.n = n;
     const int64_t stride = (int64_t)gridDim.x * 4 * 8;
-    for (int64_t base = ((int64_t)blockIdx.x * 4 + wib) * 8; base < C; base += stride) {
+    int64_t base = ((int64_t)blockIdx.x * 4 + wib) * 8;
+    // software pipeline: the points of the next group are in flight while this one is evaluated
+    double xn[NR];
+    {
+        const int64_t cc = (base + gi < C) ? base + gi : C - 1;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) xn[r] = (4 * r + lg < n && base < C) ? X[cc * n + 4 * r + lg] : 0.;
+    }
+    for (; base < C; base += stride) {
         const int64_t c = base + gi;
         const bool valid = c < C;
-        const int64_t cc = valid ? c : C - 1;
         double x[NR], gn[NR], lp, ke;
 #pragma unroll
-        for (int r = 0; r < NR; ++r) x[r] = (4 * r + lg < n) ? X[cc * n + 4 * r + lg] : 0.;
+        for (int r = 0; r < NR; ++r) x[r] = xn[r];
+        {
+            const int64_t nb = base + stride;
+            const int64_t cc = (nb + gi < C) ? nb + gi : C - 1;
+#pragma unroll
+            for (int r = 0; r < NR; ++r) xn[r] = (4 * r + lg < n && nb < C) ? X[cc * n + 4 * r + lg] : 0.;
+        }
         dmma_logp_grad<NR, C2>(bsm, lane, K, x, msm, msm + 32, valid, lp, gn, [](const double (&)[NR]) { return 0.; }, ke);
         if (valid) {
             if (lg == 0) LP[c] = lp;
