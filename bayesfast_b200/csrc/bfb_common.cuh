@@ -58,7 +58,7 @@ struct DevModel {
     const int *hb;       // [np] bit0 = lower bound hard, bit1 = upper bound hard
     // DMMA operand table of output 0 (bfb_dmma.cuh): bfrag[kt][tile][lane]; frag_nr = 0 when the model does not qualify
     const double *bfrag;
-    int frag_nr, frag_nt;
+    int frag_nr, frag_nt, frag_ext;
 };
 
 struct HostConfig {

@@ -19,18 +19,25 @@
 // blocks by the A operand they multiply:  [S | A] . x   |   A^T . x^2   |   H . (x - mu).
 #pragma once
 #include "bfb_common.cuh"
+#include "bfb_eval.cuh"      // to_original_1
 
-template <int NR, bool C2>
+// MV = model variant: bit 0 = cubic-2 configs present, bit 1 = extended density (decay ellipsoid, variable transform,
+// module rescale: core/density.py:724-754, core/module.py:47-96) -- a second H block and the elementwise maps around it
+template <int NR, int MV>
 struct DmmaShape {
+    static constexpr bool C2 = MV & 1, EXT = (MV & 2) != 0;
     static constexpr int TX = C2 ? NR : (NR + 1) / 2;     // tiles of the block multiplying x
     static constexpr int T2 = C2 ? (NR + 1) / 2 : 0;      // tiles multiplying x^2
     static constexpr int TD = (NR + 1) / 2;               // tiles multiplying x - mu
-    static constexpr int NT = TX + T2 + TD;
+    static constexpr int TD2 = EXT ? (NR + 1) / 2 : 0;    // tiles multiplying x_orig - mu_decay
+    static constexpr int O_D2 = TD, O_X = TD + TD2, O_X2 = O_X + TX;
+    static constexpr int NT = TX + T2 + TD + TD2;
+    static constexpr int MSM_DOUBLES = EXT ? 288 : 64;    // per-dimension tables staged next to the operand table
     static constexpr int NTP = (NT + 1) / 2;              // tile pairs: the B fragments of two tiles are one 16-byte load
     static constexpr int FRAG_DOUBLES = NR * NTP * 64;
 };
 
-inline int bfb_frag_tiles(int nr, bool c2) { return (c2 ? nr : (nr + 1) / 2) + (c2 ? (nr + 1) / 2 : 0) + (nr + 1) / 2; }
+inline int bfb_frag_tiles(int nr, bool c2, bool ext) { return (c2 ? nr : (nr + 1) / 2) + (c2 ? (nr + 1) / 2 : 0) + (ext ? 2 : 1) * ((nr + 1) / 2); }
 // instantiated dims-per-lane for input_size n (0: not supported)
 inline int bfb_frag_nr(int n) { return n <= 16 ? 4 : n <= 28 ? 7 : n <= 32 ? 8 : 0; }
 
@@ -64,16 +71,17 @@ __device__ __forceinline__ double qsum(double v)
     return v;
 }
 
-// One evaluation = two GEMM stages.  Stage A: h = H (x - mu) (the TD tiles of the D block) gives the Mahalanobis radius,
-// i.e. the inside / outside decision of the radial bound (poly.py:466-469).  Outside points are then REPLACED by their
-// projection onto the ellipsoid before stage B, so the polynomial blocks ([S | A] . x, A^T . x^2) are evaluated exactly
-// once per point -- at x inside, at x_0 outside, which is all PolyModel._fj_bound (poly.py:480-503) needs.
-// Table tile order: D block first (tiles [0, TD)), then the x block (TX tiles), then the x^2 block (T2 tiles).
-template <int NR, bool C2, int T_LO, int T_HI>
-__device__ __forceinline__ void dmma_tiles(const double *bsm, int lane, const double (&a0)[NR], const double (&a1)[NR],
-                                           double (&acc)[DmmaShape<NR, C2>::NT][2])
+// One evaluation = two GEMM stages.  Stage A: h = H (x - mu) (the TD tiles of the D block; with the extended density also
+// h2 = H_decay (x_orig - mu_decay)) gives the Mahalanobis radius, i.e. the inside / outside decision of the radial bound
+// (poly.py:466-469).  Outside points are then REPLACED by their projection onto the ellipsoid before stage B, so the
+// polynomial blocks ([S | A] . x, A^T . x^2) are evaluated exactly once per point -- at x inside, at x_0 outside, which is all
+// PolyModel._fj_bound (poly.py:480-503) needs.  Table tile order: D | D2 | x block (TX tiles) | x^2 block (T2 tiles).
+template <int NR, int MV, int T_LO, int T_HI>
+__device__ __forceinline__ void dmma_tiles(const double *bsm, int lane, const double (&aD)[NR], const double (&aD2)[NR],
+                                           const double (&aX)[NR], const double (&aX2)[NR],
+                                           double (&acc)[DmmaShape<NR, MV>::NT][2])
 {
-    using SH = DmmaShape<NR, C2>;
+    using SH = DmmaShape<NR, MV>;
     const double2 *bp = reinterpret_cast<const double2 *>(bsm) + lane;
     // the table is loop invariant for the callers; without this fence the compiler hoists all B fragments into
     // registers (and spills them) instead of streaming them from shared memory next to the MMAs
@@ -87,8 +95,7 @@ __device__ __forceinline__ void dmma_tiles(const double *bsm, int lane, const do
             for (int e = 0; e < 2; ++e) {
                 const int t = 2 * tp + e;
                 if (t >= T_LO && t < T_HI) {
-                    // operand: the D block and the x block take a0 (x - mu, resp. x), the x^2 block takes a1
-                    const double a = (t < SH::TD + SH::TX) ? a0[kt] : a1[kt];
+                    const double a = (t < SH::O_D2) ? aD[kt] : (t < SH::O_X) ? aD2[kt] : (t < SH::O_X2) ? aX[kt] : aX2[kt];
                     dmma884(acc[t][0], acc[t][1], a, e ? b.y : b.x);
                 }
             }
@@ -99,31 +106,86 @@ __device__ __forceinline__ void dmma_tiles(const double *bsm, int lane, const do
 struct DmmaConsts {
     double c0, alpha, alpha2, f_mu;
     int n;
+    // extended density
+    double d_alpha2, d_gamma;
+    int use_transform, use_scales, use_decay;
 };
 
-// PolyModel._fun_and_jac with the radial bound (poly.py:443-503) for the 8 points of the warp.
-// mu_t / lin_t: [32] tables indexed by dimension (shared memory).  `ke_of` maps the gradient (own dims) to a lane partial
-// that is reduced over the quad (the sampler's kinetic energy of the new momentum); `live` masks points whose outside
-// test must not count.  On return x holds the point the polynomial was evaluated at is NOT exposed: x_in is unchanged.
-template <int NR, bool C2, class KE>
+__device__ __forceinline__ DmmaConsts dmma_consts(const DevModel &M)
+{
+    DmmaConsts K;
+    K.c0 = M.c0[0]; K.alpha = M.alpha; K.alpha2 = M.use_bound ? M.alpha * M.alpha : INFINITY;
+    K.f_mu = M.use_bound ? M.f_mu[0] : 0.; K.n = M.n;
+    K.d_alpha2 = M.d_alpha2; K.d_gamma = M.d_gamma;
+    K.use_transform = M.use_transform; K.use_scales = M.use_scales; K.use_decay = M.use_decay;
+    return K;
+}
+
+// per-dimension tables in shared memory (first 32 threads of the block): mu | lin  [| s0 | sdiff | d_mu | r_lo | r_w | hb | log|r_w|]
+template <int MV>
+__device__ __forceinline__ void dmma_stage_tables(const DevModel &M, double *msm)
+{
+    if (threadIdx.x < 32) {
+        const int j = threadIdx.x;
+        msm[j] = M.use_bound ? M.mu[j] : 0.;
+        msm[32 + j] = M.lin[j];
+        if (MV & 2) {
+            msm[64 + j] = M.s0[j]; msm[96 + j] = M.sdiff[j]; msm[128 + j] = M.d_mu[j];
+            msm[160 + j] = M.r_lo[j]; msm[192 + j] = M.r_w[j]; msm[224 + j] = (double)M.hb[j];
+            msm[256 + j] = log(fabs(M.r_w[j]));     // log |dx/dx~| of an unbounded (affine) coordinate: constant
+        }
+    }
+}
+
+// Density.logp_and_grad(x, original_space=False, use_surrogate=True) of a surrogate-only density for the 8 points of the
+// warp: PolyModel._fun_and_jac with the radial bound (poly.py:443-503), and with MV & 2 the variable transform, module
+// rescale and decay around it (core/density.py:724-754, core/module.py:80-85; same order of operations as density_eval,
+// bfb_eval.cuh).  msm: tables of dmma_stage_tables.  `ke_of` maps the final gradient (own dims) to a lane partial that is
+// reduced over the quad (the sampler's kinetic energy of the new momentum); `live` masks points whose outside test must not
+// count.  x_in is the point in the sampler's (transformed) space and is left unchanged.
+template <int NR, int MV, class KE>
 __device__ __forceinline__ void dmma_logp_grad(const double *bsm, int lane, const DmmaConsts &K,
-                                               const double (&x_in)[NR], const double *mu_t, const double *lin_t,
+                                               const double (&x_in)[NR], const double *msm,
                                                bool live, double &lp, double (&gn)[NR], KE &&ke_of, double &ke)
 {
-    using SH = DmmaShape<NR, C2>;
+    using SH = DmmaShape<NR, MV>;
+    constexpr bool C2 = SH::C2, EXT = SH::EXT;
+    const double *mu_t = msm, *lin_t = msm + 32;
     const int lg = lane & 3;
     double acc[SH::NT][2];
 #pragma unroll
     for (int t = 0; t < SH::NT; ++t) acc[t][0] = acc[t][1] = 0.;
-    double d0[NR], x[NR];
+    double d0[NR], x[NR], d2[NR], tj[NR], tjj[NR];
 #pragma unroll
-    for (int r = 0; r < NR; ++r) { x[r] = x_in[r]; d0[r] = x_in[r] - mu_t[4 * r + lg]; }
-    // ---- stage A: h = H d, beta^2 = d . h ----
-    dmma_tiles<NR, C2, 0, SH::TD>(bsm, lane, d0, d0, acc);
-    double bpart = 0.;
+    for (int r = 0; r < NR; ++r) {
+        const int j = 4 * r + lg;
+        double xo = x_in[r];
+        tj[r] = 1.; tjj[r] = 0.; d2[r] = 0.;
+        if (EXT) {
+            if (K.use_transform && j < K.n) {
+                // only hard-bounded coordinates need exp(): the others are affine (transforms/_constraint.pyx:133-215)
+                const int hbj = (int)msm[224 + j];
+                if (hbj != 0) to_original_1(x_in[r], msm[160 + j], msm[192 + j], hbj, xo, tj[r], tjj[r]);
+                else { xo = msm[160 + j] + x_in[r] * msm[192 + j]; tj[r] = msm[192 + j]; }
+            }
+            d2[r] = (j < K.n) ? xo - msm[128 + j] : 0.;
+            if (K.use_scales) xo = (xo - msm[64 + j]) / msm[96 + j];
+            if (j >= K.n) xo = 0.;
+        }
+        x[r] = xo;
+        d0[r] = (EXT && j >= K.n) ? 0. : xo - mu_t[j];
+    }
+    // ---- stage A: h = H d, beta^2 = d . h  (and the decay ellipsoid) ----
+    dmma_tiles<NR, MV, 0, SH::O_X>(bsm, lane, d0, d2, d0, d0, acc);
+    double bpart = 0., b2part = 0.;
 #pragma unroll
-    for (int r = 0; r < NR; ++r) bpart = fma(d0[r], acc[r / 2][r % 2], bpart);
-    const double beta2 = qsum(bpart);
+    for (int r = 0; r < NR; ++r) {
+        bpart = fma(d0[r], acc[r / 2][r % 2], bpart);
+        if (EXT) b2part = fma(d2[r], acc[SH::O_D2 + r / 2][r % 2], b2part);
+    }
+    double beta2, beta2d = 0.;
+    if (EXT) { double z0 = 0., z1 = 0.; qsum4(bpart, b2part, z0, z1, lane); beta2 = bpart; beta2d = b2part; }
+    else beta2 = qsum(bpart);
     const bool outside = live && (beta2 > K.alpha2);
     // divisions by beta are multiplications by 1 / beta: the padded dimensions hold exact zeros and a zero numerator
     // sends the FP64 division to its slow path
@@ -137,25 +199,25 @@ __device__ __forceinline__ void dmma_logp_grad(const double *bsm, int lane, cons
     double x2[NR];
 #pragma unroll
     for (int r = 0; r < NR; ++r) x2[r] = x[r] * x[r];
-    dmma_tiles<NR, C2, SH::TD, SH::NT>(bsm, lane, x, x2, acc);
+    dmma_tiles<NR, MV, SH::O_X, SH::NT>(bsm, lane, x, x, x, x2, acc);
     double fpart = 0., jd = 0.;
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
-        const double y = acc[SH::TD + r / 2][r % 2];
+        const double y = acc[SH::O_X + r / 2][r % 2];
         const double lin_r = lin_t[4 * r + lg];
         double g = lin_r + y;
         fpart = fma(lin_r, x[r], fpart);
         fpart = fma(0.5 * x[r], y, fpart);
         if (C2) {
-            const double t = acc[SH::TD + (NR + r) / 2][(NR + r) % 2];
-            const double u = acc[SH::TD + SH::TX + r / 2][r % 2];
+            const double t = acc[SH::O_X + (NR + r) / 2][(NR + r) % 2];
+            const double u = acc[SH::O_X2 + r / 2][r % 2];
             g += fma(2. * x[r], t, u);
             fpart = fma(x2[r], t, fpart);
         }
         gn[r] = g;
         jd = fma(g, d0[r], jd);
     }
-    double kp = ke_of(gn), zz = 0.;
+    double kp = EXT ? 0. : ke_of(gn), zz = 0.;
     qsum4(kp, jd, fpart, zz, lane);
     ke = kp;
     double fp = fpart;
@@ -166,7 +228,8 @@ __device__ __forceinline__ void dmma_logp_grad(const double *bsm, int lane, cons
         double g2[NR];
 #pragma unroll
         for (int r = 0; r < NR; ++r) g2[r] = outside ? gn[r] + sfac * (acc[r / 2][r % 2] * rbeta) : gn[r];
-        const double k2 = qsum(ke_of(g2));
+        double k2 = 0.;
+        if (!EXT) k2 = qsum(ke_of(g2));
         if (outside) {
 #pragma unroll
             for (int r = 0; r < NR; ++r) gn[r] = g2[r];
@@ -175,4 +238,27 @@ __device__ __forceinline__ void dmma_logp_grad(const double *bsm, int lane, cons
         }
     }
     lp = K.c0 + fp;
+    if (EXT) {
+        // module rescale of the Jacobian, chain rule of the transform, decay, log-determinant of the transform
+        double tpart = 0.;
+        const bool dec = K.use_decay && (beta2d > K.d_alpha2);
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            const int j = 4 * r + lg;
+            double g = gn[r];
+            if (K.use_scales) g = g / msm[96 + j];
+            g *= tj[r];
+            if (dec) g -= 2. * K.d_gamma * acc[SH::O_D2 + r / 2][r % 2];
+            if (K.use_transform && j < K.n) {
+                if ((int)msm[224 + j] != 0) { tpart += log(fabs(tj[r])); g += tjj[r] / tj[r]; }
+                else tpart += msm[256 + j];            // tjj = 0: nothing to add to the gradient
+            }
+            gn[r] = (j < K.n) ? g : 0.;
+        }
+        if (K.use_decay) { const double ex = beta2d - K.d_alpha2; lp -= K.d_gamma * (ex > 0. ? ex : 0.); }
+        double kq = ke_of(gn), z0 = 0., z1 = 0.;
+        qsum4(kq, tpart, z0, z1, lane);
+        ke = kq;
+        if (K.use_transform) lp += tpart;
+    }
 }

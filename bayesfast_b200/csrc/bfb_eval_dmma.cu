@@ -10,24 +10,19 @@
 #include <cstring>
 #include <cstdlib>
 
-template <int NR, bool C2>
+template <int NR, int MV>
 __global__ void __launch_bounds__(128, 4) eval_dmma_kernel(DevModel M, const double *__restrict__ X, int64_t C,
                                                         double *__restrict__ LP, double *__restrict__ G)
 {
-    using SH = DmmaShape<NR, C2>;
+    using SH = DmmaShape<NR, MV>;
     extern __shared__ double bsm[];
-    double *msm = bsm + SH::FRAG_DOUBLES;     // mu[32] | lin[32]
+    double *msm = bsm + SH::FRAG_DOUBLES;     // per-dimension tables (dmma_stage_tables)
     for (int i = threadIdx.x; i < SH::FRAG_DOUBLES; i += blockDim.x) bsm[i] = M.bfrag[i];
-    if (threadIdx.x < 32) {
-        msm[threadIdx.x] = M.use_bound ? M.mu[threadIdx.x] : 0.;
-        msm[32 + threadIdx.x] = M.lin[threadIdx.x];
-    }
+    dmma_stage_tables<MV>(M, msm);
     __syncthreads();
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, gi = lane >> 2, lg = lane & 3;
     const int n = M.n;
-    DmmaConsts K;
-    K.c0 = M.c0[0]; K.alpha = M.alpha; K.alpha2 = M.use_bound ? M.alpha * M.alpha : INFINITY;
-    K.f_mu = M.use_bound ? M.f_mu[0] : 0.; K.n = n;
+    const DmmaConsts K = dmma_consts(M);
     const int64_t stride = (int64_t)gridDim.x * 4 * 8;
     int64_t base = ((int64_t)blockIdx.x * 4 + wib) * 8;
     // software pipeline: the points of the next group are in flight while this one is evaluated
@@ -49,7 +44,7 @@ __global__ void __launch_bounds__(128, 4) eval_dmma_kernel(DevModel M, const dou
 #pragma unroll
             for (int r = 0; r < NR; ++r) xn[r] = (4 * r + lg < n && nb < C) ? X[cc * n + 4 * r + lg] : 0.;
         }
-        dmma_logp_grad<NR, C2>(bsm, lane, K, x, msm, msm + 32, valid, lp, gn, [](const double (&)[NR]) { return 0.; }, ke);
+        dmma_logp_grad<NR, MV>(bsm, lane, K, x, msm, valid, lp, gn, [](const double (&)[NR]) { return 0.; }, ke);
         if (valid) {
             if (lg == 0) LP[c] = lp;
 #pragma unroll
@@ -58,17 +53,17 @@ __global__ void __launch_bounds__(128, 4) eval_dmma_kernel(DevModel M, const dou
     }
 }
 
-template <int NR, bool C2>
+template <int NR, int MV>
 static int launch_eval(bfb_context *h, const double *X, int64_t C, double *LP, double *G)
 {
-    using SH = DmmaShape<NR, C2>;
-    const size_t smem = sizeof(double) * (SH::FRAG_DOUBLES + 64);
-    BFB_CUDA(cudaFuncSetAttribute(eval_dmma_kernel<NR, C2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    using SH = DmmaShape<NR, MV>;
+    const size_t smem = sizeof(double) * (SH::FRAG_DOUBLES + SH::MSM_DOUBLES);
+    BFB_CUDA(cudaFuncSetAttribute(eval_dmma_kernel<NR, MV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 4;
     if (const char *e = getenv("BFB200_EVAL_BLOCKS_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 8) per_sm = v; }
     int64_t want = (C + 31) / 32;
     int blocks = (int)(want < (int64_t)h->sm_count * per_sm ? want : (int64_t)h->sm_count * per_sm);
-    eval_dmma_kernel<NR, C2><<<blocks, 128, smem, h->stream>>>(h->dm, X, C, LP, G);
+    eval_dmma_kernel<NR, MV><<<blocks, 128, smem, h->stream>>>(h->dm, X, C, LP, G);
     h->launches++;
     BFB_CUDA(cudaGetLastError());
     return BFB_OK;
@@ -78,13 +73,12 @@ static int launch_eval(bfb_context *h, const double *X, int64_t C, double *LP, d
 int bfb_launch_eval_dmma(bfb_context *h, const double *X, int64_t C, double *LP, double *G)
 {
     const DevModel &M = h->dm;
-    if (M.frag_nr == 0 || M.has_c3 || M.use_decay || M.use_transform || M.use_scales) return 1;
+    if (M.frag_nr == 0 || M.has_c3) return 1;
     if (const char *e = getenv("BFB200_EVAL")) { if (!strcmp(e, "generic")) return 1; }
-    const bool c2 = M.has_c2;
-    switch (M.frag_nr) {
-    case 4: return c2 ? launch_eval<4, true>(h, X, C, LP, G) : launch_eval<4, false>(h, X, C, LP, G);
-    case 7: return c2 ? launch_eval<7, true>(h, X, C, LP, G) : launch_eval<7, false>(h, X, C, LP, G);
-    case 8: return c2 ? launch_eval<8, true>(h, X, C, LP, G) : launch_eval<8, false>(h, X, C, LP, G);
-    }
+    const int mv = (M.has_c2 ? 1 : 0) | (M.frag_ext ? 2 : 0);
+#define BFB_CASE(NR_, MV_) if (M.frag_nr == NR_ && mv == MV_) return launch_eval<NR_, MV_>(h, X, C, LP, G);
+    BFB_CASE(4, 0) BFB_CASE(4, 1) BFB_CASE(4, 2) BFB_CASE(4, 3) BFB_CASE(7, 0) BFB_CASE(7, 1) BFB_CASE(7, 2) BFB_CASE(7, 3)
+    BFB_CASE(8, 0) BFB_CASE(8, 1) BFB_CASE(8, 2) BFB_CASE(8, 3)
+#undef BFB_CASE
     return 1;
 }

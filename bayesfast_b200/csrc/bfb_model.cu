@@ -235,6 +235,10 @@ int bfb_upload_model(bfb_context *h)
         return o;
     };
     D.use_bound = F.use_bound; D.alpha = F.alpha;
+    std::vector<double> DH((size_t)n * np, 0.);          // decay ellipsoid, d_H[k][j] = Hd[k][j]
+    if (F.use_decay)
+        for (int k = 0; k < n; ++k)
+            for (int j = 0; j < n; ++j) DH[(size_t)k * np + j] = h->h_dhess[(size_t)k * n + j];
     {
         std::vector<double> HT((size_t)n * np, 0.);
         if (F.use_bound)
@@ -246,7 +250,8 @@ int bfb_upload_model(bfb_context *h)
         const int nr = bfb_frag_nr(n);
         if (nr > 0 && !h3 && np == 32) {
             const bool c2 = h2;
-            const int TX = c2 ? nr : (nr + 1) / 2, NT = bfb_frag_tiles(nr, c2);
+            const bool ext = F.use_decay || F.use_transform || F.use_scales;     // MV bit 1 (bfb_dmma.cuh)
+            const int TX = c2 ? nr : (nr + 1) / 2, NT = bfb_frag_tiles(nr, c2, ext);
             const int NTP = (NT + 1) / 2;
             std::vector<double> fr((size_t)nr * NTP * 64, 0.);
             for (int kt = 0; kt < nr; ++kt)
@@ -255,15 +260,16 @@ int bfb_upload_model(bfb_context *h)
                         const int k = 4 * kt + (lane & 3), gid = lane >> 2, own = gid >> 1, e = gid & 1;
                         const std::vector<double> *T = nullptr;
                         int v;
-                        const int TD = (nr + 1) / 2;          // tile order: D block | x block | x^2 block
+                        const int TD = (nr + 1) / 2, TD2 = ext ? TD : 0;   // tile order: D | D2 (decay) | x block | x^2 block
                         if (t < TD) { v = 2 * t + e; if (v < nr) T = &HT; }
-                        else if (t < TD + TX) { v = 2 * (t - TD) + e; if (v < nr) T = &S; else if (c2 && v < 2 * nr) { T = &A1T; v -= nr; } }
-                        else { v = 2 * (t - TD - TX) + e; if (v < nr) T = &A2; }
+                        else if (t < TD + TD2) { v = 2 * (t - TD) + e; if (v < nr) T = &DH; }
+                        else if (t < TD + TD2 + TX) { v = 2 * (t - TD - TD2) + e; if (v < nr) T = &S; else if (c2 && v < 2 * nr) { T = &A1T; v -= nr; } }
+                        else { v = 2 * (t - TD - TD2 - TX) + e; if (v < nr) T = &A2; }
                         const int j = 4 * v + own;
                         if (T && !T->empty() && k < n && j < n) fr[(((size_t)kt * NTP + t / 2) * 32 + lane) * 2 + (t & 1)] = (*T)[(size_t)k * np + j];
                     }
             if ((rc = upload(h, fr, &D.bfrag))) return rc;
-            D.frag_nr = nr; D.frag_nt = NT;
+            D.frag_nr = nr; D.frag_nt = NT; D.frag_ext = ext ? 1 : 0;
         }
         std::vector<double> fm(m, 0.);
         for (int o = 0; o < m && o < (int)h->h_fmu.size(); ++o) fm[o] = h->h_fmu[o];
@@ -274,10 +280,6 @@ int bfb_upload_model(bfb_context *h)
     if ((rc = upload(h, pad(h->h_sdiff, 1.), &D.sdiff))) return rc;
     D.use_decay = F.use_decay; D.d_alpha2 = F.d_alpha2; D.d_gamma = F.d_gamma;
     {
-        std::vector<double> DH((size_t)n * np, 0.);
-        if (F.use_decay)
-            for (int k = 0; k < n; ++k)
-                for (int j = 0; j < n; ++j) DH[(size_t)k * np + j] = h->h_dhess[(size_t)k * n + j];
         if ((rc = upload(h, pad(h->h_dmu, 0.), &D.d_mu))) return rc;
         if ((rc = upload(h, DH, &D.d_H))) return rc;
     }
@@ -462,6 +464,12 @@ extern "C" int bfb_poly_eval_batch(bfb_handle h, const double *X, int64_t C, dou
     int blocks = (int)(blocks64 < (int64_t)h->sm_count * 16 ? blocks64 : (int64_t)h->sm_count * 16);
     size_t smem = sizeof(double) * wpb * 2 * h->np;
     BFB_CUDA(cudaEventRecord(h->ev0, h->stream));
+    // single-output PolyModel (value + Jacobian row): the tensor-core evaluator computes exactly module_fg
+    int fast = 1;
+    if (m == 1 && bj.dev && !h->dm.use_decay && !h->dm.use_transform)
+        fast = bfb_launch_eval_dmma(h, (const double *)bx.dev, C, (double *)bf.dev, (double *)bj.dev);
+    if (fast < 0) return fast;
+    if (fast == 1) {
     switch (npl) {
     case 1: poly_eval_kernel<1><<<blocks, 32 * wpb, smem, h->stream>>>(h->dm, (const double *)bx.dev, C, (double *)bf.dev, (double *)bj.dev); break;
     case 2: poly_eval_kernel<2><<<blocks, 32 * wpb, smem, h->stream>>>(h->dm, (const double *)bx.dev, C, (double *)bf.dev, (double *)bj.dev); break;
@@ -469,6 +477,7 @@ extern "C" int bfb_poly_eval_batch(bfb_handle h, const double *X, int64_t C, dou
     default: poly_eval_kernel<4><<<blocks, 32 * wpb, smem, h->stream>>>(h->dm, (const double *)bx.dev, C, (double *)bf.dev, (double *)bj.dev); break;
     }
     h->launches++;
+    }
     BFB_CUDA(cudaGetLastError());
     BFB_CUDA(cudaEventRecord(h->ev1, h->stream));
     if ((rc = finish(h, bf))) return rc;

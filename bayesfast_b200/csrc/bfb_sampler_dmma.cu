@@ -58,31 +58,26 @@ __device__ __forceinline__ int64_t shfl64(int64_t v, int src)
 // A vector slot holds element (r, lane) at r * 32 + lane: every access is one conflict-free 256-byte row.
 __host__ __device__ inline int warp_smem_doubles(int NR, int LS) { return (8 + 3 * LS) * NR * 32 + 400; }
 
-template <int NR, bool C2, int W>
+template <int NR, int MV, int W>
 __global__ void __launch_bounds__(32 * W, 1) nuts_dmma_kernel(DevModel M, bfb_sampler_cfg cfg, ChainState st, RunOutDevF out,
                                                               int L, int LS, double *__restrict__ gstack,
                                                               double *__restrict__ gprop, int base_iter, int chunk_iters,
                                                               int n_groups, int n_units, int *__restrict__ queue, int cpg)
 {
-    using SH = DmmaShape<NR, C2>;
+    using SH = DmmaShape<NR, MV>;
     constexpr int SLOT = NR * 32;
     extern __shared__ double smem[];
     double *bsm = smem;                       // coefficient operand table
-    double *msm = smem + SH::FRAG_DOUBLES;    // mu[32] | lin[32]
+    double *msm = smem + SH::FRAG_DOUBLES;    // per-dimension tables (dmma_stage_tables)
     for (int i = threadIdx.x; i < SH::FRAG_DOUBLES; i += blockDim.x) bsm[i] = M.bfrag[i];
-    if (threadIdx.x < 32) {
-        msm[threadIdx.x] = M.use_bound ? M.mu[threadIdx.x] : 0.;
-        msm[32 + threadIdx.x] = M.lin[threadIdx.x];
-    }
+    dmma_stage_tables<MV>(M, msm);
     __syncthreads();
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, gi = lane >> 2, lg = lane & 3;
-    double *wsm = smem + SH::FRAG_DOUBLES + 64 + (size_t)wib * warp_smem_doubles(NR, LS);
+    double *wsm = smem + SH::FRAG_DOUBLES + SH::MSM_DOUBLES + (size_t)wib * warp_smem_doubles(NR, LS);
     double *sTL = wsm, *sTR = wsm + 3 * SLOT, *sPS = wsm + 6 * SLOT, *sPB = wsm + 7 * SLOT, *sST = wsm + 8 * SLOT;
     double *ssc = wsm + (8 + 3 * LS) * SLOT + gi;        // scalar (field f, level l) of this chain at ssc[(f * 10 + l) * 8]
     const int n = M.n;
-    DmmaConsts K;
-    K.c0 = M.c0[0]; K.alpha = M.alpha; K.alpha2 = M.use_bound ? M.alpha * M.alpha : INFINITY;
-    K.f_mu = M.use_bound ? M.f_mu[0] : 0.; K.n = n;
+    const DmmaConsts K = dmma_consts(M);
 
 #ifdef BFB_DMMA_TIMING
 #define TICK(k) { const long long now_ = clock64(); tacc[k] += now_ - tlast; tlast = now_; }
@@ -351,7 +346,7 @@ __global__ void __launch_bounds__(32 * W, 1) nuts_dmma_kernel(DevModel M, bfb_sa
             double lp, ke2;
             {
                 double gn[NR];
-                dmma_logp_grad<NR, C2>(bsm, lane, K, q, msm, msm + 32, go, lp, gn,
+                dmma_logp_grad<NR, MV>(bsm, lane, K, q, msm, go, lp, gn,
                                        [&](const double (&gg)[NR]) {
                                            double s_ = 0.;
 #pragma unroll
@@ -582,26 +577,21 @@ __global__ void __launch_bounds__(32 * W, 1) nuts_dmma_kernel(DevModel M, bfb_sa
 // step and nothing of the tree machinery is needed: an iteration is momentum draw, n_int_step x (kick, drift, tensor-core
 // evaluation, kick), Metropolis test, adaptation, outputs.  Same work units and queue as the NUTS kernel.
 // ----------------------------------------------------------------------------------------------------------------------
-template <int NR, bool C2, int W>
+template <int NR, int MV, int W>
 __global__ void __launch_bounds__(32 * W, 1) hmc_dmma_kernel(DevModel M, bfb_sampler_cfg cfg, ChainState st, RunOutDevF out,
                                                              int base_iter, int chunk_iters, int n_groups, int n_units,
                                                              int *__restrict__ queue)
 {
-    using SH = DmmaShape<NR, C2>;
+    using SH = DmmaShape<NR, MV>;
     extern __shared__ double smem[];
     double *bsm = smem;
-    double *msm = smem + SH::FRAG_DOUBLES;    // mu[32] | lin[32]
+    double *msm = smem + SH::FRAG_DOUBLES;    // per-dimension tables (dmma_stage_tables)
     for (int i = threadIdx.x; i < SH::FRAG_DOUBLES; i += blockDim.x) bsm[i] = M.bfrag[i];
-    if (threadIdx.x < 32) {
-        msm[threadIdx.x] = M.use_bound ? M.mu[threadIdx.x] : 0.;
-        msm[32 + threadIdx.x] = M.lin[threadIdx.x];
-    }
+    dmma_stage_tables<MV>(M, msm);
     __syncthreads();
     const int lane = threadIdx.x & 31, gi = lane >> 2, lg = lane & 3;
     const int n = M.n;
-    DmmaConsts K;
-    K.c0 = M.c0[0]; K.alpha = M.alpha; K.alpha2 = M.use_bound ? M.alpha * M.alpha : INFINITY;
-    K.f_mu = M.use_bound ? M.f_mu[0] : 0.; K.n = n;
+    const DmmaConsts K = dmma_consts(M);
     volatile int *qv = queue;
     volatile int *ring = queue + 2 + n_groups;
 #pragma unroll 1
@@ -679,7 +669,7 @@ __global__ void __launch_bounds__(32 * W, 1) hmc_dmma_kernel(DevModel M, bfb_sam
                 q[r] = fma(eps, var[r] * p[r], q[r]);
             }
             double gn[NR], ke2;
-            dmma_logp_grad<NR, C2>(bsm, lane, K, q, msm, msm + 32, live, lp, gn,
+            dmma_logp_grad<NR, MV>(bsm, lane, K, q, msm, live, lp, gn,
                                    [&](const double (&gg)[NR]) {
                                        double a_ = 0.;
 #pragma unroll
@@ -789,14 +779,14 @@ __global__ void __launch_bounds__(32 * W, 1) hmc_dmma_kernel(DevModel M, bfb_sam
     }   // unit loop
 }
 
-template <int NR, bool C2, int W>
+template <int NR, int MV, int W>
 static int launch_hmc_dmma(bfb_context *h, const bfb_run_out &o, int n_iter)
 {
-    using SH = DmmaShape<NR, C2>;
+    using SH = DmmaShape<NR, MV>;
     const int64_t C = h->cs.C;
     const int n_groups = (int)((C + 7) / 8);
-    const size_t smem = sizeof(double) * (SH::FRAG_DOUBLES + 64);
-    BFB_CUDA(cudaFuncSetAttribute(hmc_dmma_kernel<NR, C2, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem = sizeof(double) * (SH::FRAG_DOUBLES + SH::MSM_DOUBLES);
+    BFB_CUDA(cudaFuncSetAttribute(hmc_dmma_kernel<NR, MV, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     RunOutDevF od;
     od.o = o; od.n_iter = n_iter;
     int chunk_iters = (n_iter + 5) / 6;
@@ -817,14 +807,14 @@ static int launch_hmc_dmma(bfb_context *h, const bfb_run_out &o, int n_iter)
     int blocks = h->sm_count;
     const int64_t want = (n_groups + W - 1) / W;
     if ((int64_t)blocks > want) blocks = (int)want;
-    hmc_dmma_kernel<NR, C2, W><<<blocks, 32 * W, smem, h->stream>>>(h->dm, h->scfg, h->cs, od, (int)h->iters_done, chunk_iters,
+    hmc_dmma_kernel<NR, MV, W><<<blocks, 32 * W, smem, h->stream>>>(h->dm, h->scfg, h->cs, od, (int)h->iters_done, chunk_iters,
                                                                    n_groups, (int)n_units64, h->queue);
     h->launches++;
     BFB_CUDA(cudaGetLastError());
     return BFB_OK;
 }
 
-template <int NR, bool C2>
+template <int NR, int MV>
 static int launch_hmc_dmma_w(bfb_context *h, const bfb_run_out &o, int n_iter)
 {
     // warps per SM: the kernel needs no per-warp shared memory, so the register file is the only limit (255 registers up
@@ -836,32 +826,31 @@ static int launch_hmc_dmma_w(bfb_context *h, const bfb_run_out &o, int n_iter)
     if (const char *e = getenv("BFB200_HMC_WARPS_PER_SM")) { int v = atoi(e); if (v == 4 || v == 8 || v == 12 || v == 16) W = v; }
     else if (const char *e2 = getenv("BFB200_WARPS_PER_SM")) { int v = atoi(e2); if (v == 4 || v == 8) W = v; }
     switch (W) {
-    case 16: return launch_hmc_dmma<NR, C2, 16>(h, o, n_iter);
-    case 12: return launch_hmc_dmma<NR, C2, 12>(h, o, n_iter);
-    case 8: return launch_hmc_dmma<NR, C2, 8>(h, o, n_iter);
+    case 16: return launch_hmc_dmma<NR, MV, 16>(h, o, n_iter);
+    case 12: return launch_hmc_dmma<NR, MV, 12>(h, o, n_iter);
+    case 8: return launch_hmc_dmma<NR, MV, 8>(h, o, n_iter);
     }
-    return launch_hmc_dmma<NR, C2, 4>(h, o, n_iter);
+    return launch_hmc_dmma<NR, MV, 4>(h, o, n_iter);
 }
 
 // returns 1 if this path does not apply (caller uses the generic kernel), 0 on launch, <0 on error
 int bfb_launch_hmc_dmma(bfb_context *h, const bfb_run_out &o, int n_iter)
 {
     const DevModel &M = h->dm;
-    if (M.frag_nr == 0 || M.has_c3 || M.use_decay || M.use_transform || M.use_scales) return 1;
+    if (M.frag_nr == 0 || M.has_c3) return 1;
     if (const char *e = getenv("BFB200_SAMPLER")) { if (strcmp(e, "dmma")) return 1; }
-    const bool c2 = M.has_c2;
-    switch (M.frag_nr) {
-    case 4: return c2 ? launch_hmc_dmma_w<4, true>(h, o, n_iter) : launch_hmc_dmma_w<4, false>(h, o, n_iter);
-    case 7: return c2 ? launch_hmc_dmma_w<7, true>(h, o, n_iter) : launch_hmc_dmma_w<7, false>(h, o, n_iter);
-    case 8: return c2 ? launch_hmc_dmma_w<8, true>(h, o, n_iter) : launch_hmc_dmma_w<8, false>(h, o, n_iter);
-    }
+    const int mv = (M.has_c2 ? 1 : 0) | (M.frag_ext ? 2 : 0);
+#define BFB_CASE(NR_, MV_) if (M.frag_nr == NR_ && mv == MV_) return launch_hmc_dmma_w<NR_, MV_>(h, o, n_iter);
+    BFB_CASE(4, 0) BFB_CASE(4, 1) BFB_CASE(4, 2) BFB_CASE(4, 3) BFB_CASE(7, 0) BFB_CASE(7, 1) BFB_CASE(7, 2) BFB_CASE(7, 3)
+    BFB_CASE(8, 0) BFB_CASE(8, 1) BFB_CASE(8, 2) BFB_CASE(8, 3)
+#undef BFB_CASE
     return 1;
 }
 
-template <int NR, bool C2, int W>
+template <int NR, int MV, int W>
 static int launch_dmma(bfb_context *h, const bfb_run_out &o, int n_iter, int cpg)
 {
-    using SH = DmmaShape<NR, C2>;
+    using SH = DmmaShape<NR, MV>;
     constexpr int SLOT = NR * 32;
     const int L = h->scfg.max_treedepth;
     const int64_t C = h->cs.C;
@@ -869,14 +858,14 @@ static int launch_dmma(bfb_context *h, const bfb_run_out &o, int n_iter, int cpg
     // one persistent block of W warps per SM (W = 4: one warp per scheduler, 4096 chains = 512 warps on 592 schedulers;
     // W = 8 when there are more groups than that); the first LS levels of the tree stack live in shared memory, deeper
     // (rarely touched) levels in an L2-resident buffer
-    const size_t fixed = sizeof(double) * (SH::FRAG_DOUBLES + 64);
+    const size_t fixed = sizeof(double) * (SH::FRAG_DOUBLES + SH::MSM_DOUBLES);
     const size_t budget = (size_t)(227 * 1024) - 1024 - fixed;
     int LS = L;
     while (LS > 1 && sizeof(double) * W * warp_smem_doubles(NR, LS) > budget) --LS;
     if (const char *e = getenv("BFB200_STACK_LEVELS_SMEM")) { int v = atoi(e); if (v >= 1 && v <= L) LS = v; }
     const size_t smem = fixed + sizeof(double) * W * warp_smem_doubles(NR, LS);
     BFB_REQUIRE(smem <= 227 * 1024, BFB_ERR_ARG, "sampler needs %zu bytes of shared memory per block (> 227 KB)", smem);
-    BFB_CUDA(cudaFuncSetAttribute(nuts_dmma_kernel<NR, C2, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BFB_CUDA(cudaFuncSetAttribute(nuts_dmma_kernel<NR, MV, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const size_t deep = (size_t)(L - 1 > LS ? L - 1 - LS : 0) * 3 * SLOT;
     const size_t prop = (size_t)BFB_NSLOT * 2 * SLOT;
     if ((deep + prop) * (size_t)n_groups > h->gstack_len) {
@@ -905,7 +894,7 @@ static int launch_dmma(bfb_context *h, const bfb_run_out &o, int n_iter, int cpg
     int blocks = h->sm_count;
     const int64_t want = (n_groups + W - 1) / W;          // more warps than groups would only poll the queue
     if ((int64_t)blocks > want) blocks = (int)want;
-    nuts_dmma_kernel<NR, C2, W><<<blocks, 32 * W, smem, h->stream>>>(h->dm, h->scfg, h->cs, od, L, LS, h->gstack,
+    nuts_dmma_kernel<NR, MV, W><<<blocks, 32 * W, smem, h->stream>>>(h->dm, h->scfg, h->cs, od, L, LS, h->gstack,
                                                                     h->gstack + deep * (size_t)n_groups, (int)h->iters_done,
                                                                     chunk_iters, n_groups, (int)n_units64, h->queue, cpg);
     h->launches++;
@@ -913,7 +902,7 @@ static int launch_dmma(bfb_context *h, const bfb_run_out &o, int n_iter, int cpg
     return BFB_OK;
 }
 
-template <int NR, bool C2>
+template <int NR, int MV>
 static int launch_dmma_w(bfb_context *h, const bfb_run_out &o, int n_iter)
 {
     // chains per group (MMA rows in use) and warps per SM.  Measured at 4096 chains (scripts/imbalance.py, full run): 8 per
@@ -924,21 +913,20 @@ static int launch_dmma_w(bfb_context *h, const bfb_run_out &o, int n_iter)
     if (const char *e = getenv("BFB200_CHAINS_PER_GROUP")) { int v = atoi(e); if (v >= 1 && v <= 8) cpg = v; }
     int W = ((C + cpg - 1) / cpg > slots4) ? 8 : 4;
     if (const char *e = getenv("BFB200_WARPS_PER_SM")) { int v = atoi(e); if (v == 4 || v == 8) W = v; }
-    return W == 8 ? launch_dmma<NR, C2, 8>(h, o, n_iter, cpg) : launch_dmma<NR, C2, 4>(h, o, n_iter, cpg);
+    return W == 8 ? launch_dmma<NR, MV, 8>(h, o, n_iter, cpg) : launch_dmma<NR, MV, 4>(h, o, n_iter, cpg);
 }
 
 // returns 1 if this path does not apply (caller tries the next kernel), 0 on launch, <0 on error
 int bfb_launch_nuts_dmma(bfb_context *h, const bfb_run_out &o, int n_iter)
 {
     const DevModel &M = h->dm;
-    if (M.frag_nr == 0 || M.has_c3 || M.use_decay || M.use_transform || M.use_scales) return 1;
+    if (M.frag_nr == 0 || M.has_c3) return 1;
     if (h->scfg.max_treedepth > 10) return 1;
     if (const char *e = getenv("BFB200_SAMPLER")) { if (strcmp(e, "dmma")) return 1; }
-    const bool c2 = M.has_c2;
-    switch (M.frag_nr) {
-    case 4: return c2 ? launch_dmma_w<4, true>(h, o, n_iter) : launch_dmma_w<4, false>(h, o, n_iter);
-    case 7: return c2 ? launch_dmma_w<7, true>(h, o, n_iter) : launch_dmma_w<7, false>(h, o, n_iter);
-    case 8: return c2 ? launch_dmma_w<8, true>(h, o, n_iter) : launch_dmma_w<8, false>(h, o, n_iter);
-    }
+    const int mv = (M.has_c2 ? 1 : 0) | (M.frag_ext ? 2 : 0);
+#define BFB_CASE(NR_, MV_) if (M.frag_nr == NR_ && mv == MV_) return launch_dmma_w<NR_, MV_>(h, o, n_iter);
+    BFB_CASE(4, 0) BFB_CASE(4, 1) BFB_CASE(4, 2) BFB_CASE(4, 3) BFB_CASE(7, 0) BFB_CASE(7, 1) BFB_CASE(7, 2) BFB_CASE(7, 3)
+    BFB_CASE(8, 0) BFB_CASE(8, 1) BFB_CASE(8, 2) BFB_CASE(8, 3)
+#undef BFB_CASE
     return 1;
 }

@@ -139,3 +139,24 @@ def test_tensor_core_evaluator_vs_oracle(handle, oracle, n, order, monkeypatch):
     # batches smaller than a warp's 8 points
     lp3, g3 = handle.logp_and_grad_batch(X[:3])
     assert np.array_equal(lp3, lp[:3]) and np.array_equal(g3, g[:3])
+
+
+def test_tensor_core_evaluator_extended_density(handle, oracle, monkeypatch):
+    """decay + variable transform + module rescale through eval_dmma_kernel (model variant bit 1) vs the oracle and the
+    generic kernel"""
+    n = 26
+    spec, cov = synthetic_spec(n, 'cubic-2', seed=77, decay=True, transform=True)
+    rng = np.random.default_rng(4)
+    s0 = -0.2 + 0.1 * rng.normal(size=n)
+    spec['input_scales'] = np.stack((s0, s0 + 1.3 + 0.3 * rng.random(n)), axis=1)
+    handle.set_model(to_device_spec(spec))
+    C = 1500
+    X = (np.linalg.cholesky(cov) @ rng.normal(size=(n, C))).T * rng.choice([0.5, 1., 2.5], size=(C, 1))
+    X = np.clip(X, spec['transform_ranges'][:, 0] * 0.9, spec['transform_ranges'][:, 1] * 0.9)
+    X = np.array([oracle.from_original(x, spec['transform_ranges'], spec['hard_bounds']) for x in X])
+    lp, g = handle.logp_and_grad_batch(X)
+    lpo, go = oracle.OracleDensity(spec).logp_and_grad_batch(X)
+    assert rel_err(lp, lpo) < RTOL and rel_err(g, go) < RTOL
+    monkeypatch.setenv('BFB200_EVAL', 'generic')
+    lp2, g2 = handle.logp_and_grad_batch(X)
+    assert rel_err(lp, lp2) < 1e-12 and rel_err(g, g2) < 1e-12

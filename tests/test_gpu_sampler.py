@@ -299,3 +299,44 @@ def test_tensor_core_hmc_vs_oracle(handle, oracle, monkeypatch, n, order, C, env
     assert handle.sampler_last_path() == 'generic'
     assert np.array_equal(out['tree_depth'], gen['tree_depth']) and np.array_equal(out['diverging'], gen['diverging'])
     check_floats(out['samples'], gen['samples'], 'samples', late=1e-2)
+
+
+@pytest.mark.parametrize('n,order,sampler,kw', [(26, 'cubic-2', 'NUTS', dict(decay=True, transform=True)),
+                                                (12, 'quadratic', 'NUTS', dict(decay=True)),
+                                                (7, 'cubic-2', 'NUTS', dict(transform=True, scales=True)),
+                                                (26, 'cubic-2', 'HMC', dict(decay=True, transform=True, scales=True))])
+def test_tensor_core_extended_density(handle, oracle, monkeypatch, n, order, sampler, kw):
+    """decay ellipsoid, variable transform and module rescale (core/density.py:724-754, core/module.py:80-85) inside the
+    tensor-core kernels (model variant bit 1): decisions identical to the oracle and to the generic kernel"""
+    scales = kw.pop('scales', False)
+    spec, cov = synthetic_spec(n, order, seed=40 + n, **kw)
+    if scales:
+        rng = np.random.default_rng(1)
+        s0, s1 = -0.3 + 0.1 * rng.normal(size=n), 1.5 + 0.2 * rng.random(n)
+        spec['input_scales'] = np.stack((s0, s0 + s1), axis=1)
+    handle.set_model(to_device_spec(spec))
+    C, n_iter = 90, 36
+    x0 = (np.linalg.cholesky(cov) @ np.random.default_rng(6).normal(size=(n, C))).T * 0.7
+    if spec['transform_ranges'] is not None:
+        x0 = np.clip(x0, spec['transform_ranges'][:, 0] * 0.9, spec['transform_ranges'][:, 1] * 0.9)
+        x0 = np.array([oracle.from_original(x, spec['transform_ranges'], spec['hard_bounds']) for x in x0])
+    cfg = cfg_from({'n_int_step': 10}, n_iter // 2, 321, chain0=3)
+    step0 = 0.5 / n**0.25
+    ocfg = dict(n_iter=n_iter, n_warmup=n_iter // 2, n_int_step=10)
+    handle.sampler_init(cfg, x0, step0, np.ones(n), x0)
+    out = handle.sampler_run(sampler, n_iter)
+    assert handle.sampler_last_path() == 'dmma'
+    st = handle.sampler_state()
+    assert np.all(st['status'] == 0)
+    U, Z = device_draws(handle, 321, st['n_draws'], 3)
+    ref = oracle.OracleDensity(spec).run(sampler, ocfg, x0, step0, np.ones(n), draws_u=U, draws_z=Z)
+    assert np.array_equal(st['n_draws'], ref['n_draws'])
+    for k in ('tree_depth', 'diverging') + (('tree_size',) if sampler == 'NUTS' else ()):
+        assert np.array_equal(out[k], ref[k]), k
+    check_floats(out['samples'], ref['samples'], 'samples', late=1e-2)
+    check_floats(out['logp'], ref['logp'], 'logp', late=1e-2)
+    monkeypatch.setenv('BFB200_SAMPLER', 'generic')
+    handle.sampler_init(cfg, x0, step0, np.ones(n), x0)
+    gen = handle.sampler_run(sampler, n_iter)
+    assert handle.sampler_last_path() == 'generic'
+    assert np.array_equal(out['tree_depth'], gen['tree_depth']) and np.array_equal(out['diverging'], gen['diverging'])
