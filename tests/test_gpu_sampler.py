@@ -340,3 +340,29 @@ def test_tensor_core_extended_density(handle, oracle, monkeypatch, n, order, sam
     gen = handle.sampler_run(sampler, n_iter)
     assert handle.sampler_last_path() == 'generic'
     assert np.array_equal(out['tree_depth'], gen['tree_depth']) and np.array_equal(out['diverging'], gen['diverging'])
+
+
+@pytest.mark.parametrize('env', [{}, {'BFB200_STACK_LEVELS_SMEM': '2'}])
+def test_tensor_core_nuts_deep_trees(handle, oracle, monkeypatch, env):
+    """tiny fixed step size: trees reach depth 8-10 (up to 1023 leaves), i.e. every stack level, the L2-resident deep
+    levels, the proposal-slot pool and the depth cap are exercised; outcomes identical to the oracle"""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    n, C, n_iter = 26, 19, 5
+    spec, cov = synthetic_spec(n, 'cubic-2', seed=5)
+    handle.set_model(to_device_spec(spec))
+    x0 = (np.linalg.cholesky(cov) @ np.random.default_rng(11).normal(size=(n, C))).T
+    cfg = cfg_from({'adapt_step_size': 0, 'adapt_metric': 0}, 0, 55)
+    step0 = 0.0035
+    handle.sampler_init(cfg, x0, step0, np.ones(n), x0)
+    out = handle.sampler_run('NUTS', n_iter)
+    assert handle.sampler_last_path() == 'dmma'
+    assert out["tree_depth"].max() == 10 and out["tree_depth"].min() >= 8
+    st = handle.sampler_state()
+    U, Z = device_draws(handle, 55, st['n_draws'])
+    ref = oracle.OracleDensity(spec).run('NUTS', dict(n_iter=n_iter, n_warmup=0, adapt_step_size=0, adapt_metric=0), x0, step0,
+                                         np.ones(n), draws_u=U, draws_z=Z)
+    assert np.array_equal(st['n_draws'], ref['n_draws'])
+    for k in INT_STATS:
+        assert np.array_equal(out[k], ref[k]), k
+    check_floats(out['samples'], ref['samples'], 'samples')
