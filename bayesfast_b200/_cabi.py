@@ -9,7 +9,7 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libbfb200.so')
+LIB_PATH = os.environ.get('BFB200_LIB', os.path.join(_HERE, 'libbfb200.so'))     # BFB200_LIB: experiment builds
 
 BFB_HOST, BFB_DEVICE = 0, 1
 ORDER_CODE = {'linear': 1, 'quadratic': 2, 'cubic-2': 3, 'cubic-3': 4}

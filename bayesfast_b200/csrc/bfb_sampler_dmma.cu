@@ -841,8 +841,12 @@ int bfb_launch_hmc_dmma(bfb_context *h, const bfb_run_out &o, int n_iter)
     if (const char *e = getenv("BFB200_SAMPLER")) { if (strcmp(e, "dmma")) return 1; }
     const int mv = (M.has_c2 ? 1 : 0) | (M.frag_ext ? 2 : 0);
 #define BFB_CASE(NR_, MV_) if (M.frag_nr == NR_ && mv == MV_) return launch_hmc_dmma_w<NR_, MV_>(h, o, n_iter);
+#ifdef BFB_QUICK_BUILD      // kernel experiments: only the headline instantiation (d = 26 cubic-2), seconds instead of minutes
+    BFB_CASE(7, 1)
+#else
     BFB_CASE(4, 0) BFB_CASE(4, 1) BFB_CASE(4, 2) BFB_CASE(4, 3) BFB_CASE(7, 0) BFB_CASE(7, 1) BFB_CASE(7, 2) BFB_CASE(7, 3)
     BFB_CASE(8, 0) BFB_CASE(8, 1) BFB_CASE(8, 2) BFB_CASE(8, 3)
+#endif
 #undef BFB_CASE
     return 1;
 }
@@ -925,8 +929,12 @@ int bfb_launch_nuts_dmma(bfb_context *h, const bfb_run_out &o, int n_iter)
     if (const char *e = getenv("BFB200_SAMPLER")) { if (strcmp(e, "dmma")) return 1; }
     const int mv = (M.has_c2 ? 1 : 0) | (M.frag_ext ? 2 : 0);
 #define BFB_CASE(NR_, MV_) if (M.frag_nr == NR_ && mv == MV_) return launch_dmma_w<NR_, MV_>(h, o, n_iter);
+#ifdef BFB_QUICK_BUILD
+    BFB_CASE(7, 1)
+#else
     BFB_CASE(4, 0) BFB_CASE(4, 1) BFB_CASE(4, 2) BFB_CASE(4, 3) BFB_CASE(7, 0) BFB_CASE(7, 1) BFB_CASE(7, 2) BFB_CASE(7, 3)
     BFB_CASE(8, 0) BFB_CASE(8, 1) BFB_CASE(8, 2) BFB_CASE(8, 3)
+#endif
 #undef BFB_CASE
     return 1;
 }
