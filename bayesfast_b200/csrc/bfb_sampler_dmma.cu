@@ -23,7 +23,7 @@
 
 #if defined(BFB_DMMA_PART_HEADLINE) && defined(BFB_CODE_PAD)
 // Code-placement padding (BFB_CODE_PAD = number of 16-byte instructions): shifts the kernels of this module relative to the
-// instruction-cache sets; see the note at bfb_launch_nuts_dmma_headline.  Never launched.
+// instruction-cache sets (a scan over 0..28 KB moved the run time by +-2 %).  Never launched.
 template <int N>
 __global__ void bfb_pad_kernel(double *p)
 {
@@ -848,9 +848,9 @@ static int launch_hmc_dmma_w(bfb_context *h, const bfb_run_out &o, int n_iter)
 }
 
 // The headline instantiation (d = 26 cubic-2: NR = 7, MV = 1) is compiled into a translation unit of its own
-// (-DBFB_DMMA_PART_HEADLINE, see the Makefile): the CUDA module it is loaded from then has the same layout whatever else the
-// library contains.  Measured: the SAME SASS ran 16 % slower (164 ms vs 141 ms per 4096-chain run) when the kernel sat in the
-// middle of the 60-kernel module than in a small one -- the hot loop (41 KB) lives on the edge of the instruction cache.
+// (-DBFB_DMMA_PART_HEADLINE, see the Makefile): a small CUDA module loads in a few ms, whereas the first launch out of the
+// ~60-kernel module of all instantiations paid 25-60 ms of lazy module loading (measured: 161-197 ms for the first
+// 4096-chain run of a process against 137 ms for the following ones; scripts/variance.py).
 int bfb_launch_hmc_dmma_headline(bfb_context *h, const bfb_run_out &o, int n_iter);
 int bfb_launch_nuts_dmma_headline(bfb_context *h, const bfb_run_out &o, int n_iter);
 #ifdef BFB_DMMA_PART_HEADLINE
@@ -863,7 +863,11 @@ int bfb_launch_hmc_dmma(bfb_context *h, const bfb_run_out &o, int n_iter)
     if (M.frag_nr == 0 || M.has_c3) return 1;
     if (const char *e = getenv("BFB200_SAMPLER")) { if (strcmp(e, "dmma")) return 1; }
     const int mv = (M.has_c2 ? 1 : 0) | (M.frag_ext ? 2 : 0);
+#ifdef BFB_NO_HEADLINE_SPLIT     // experiment: the headline instantiation inside the big module
+    if (M.frag_nr == 7 && mv == 1) return launch_hmc_dmma_w<7, 1>(h, o, n_iter);
+#else
     if (M.frag_nr == 7 && mv == 1) return bfb_launch_hmc_dmma_headline(h, o, n_iter);
+#endif
 #define BFB_CASE(NR_, MV_) if (M.frag_nr == NR_ && mv == MV_) return launch_hmc_dmma_w<NR_, MV_>(h, o, n_iter);
     BFB_CASE(4, 0) BFB_CASE(4, 1) BFB_CASE(4, 2) BFB_CASE(4, 3) BFB_CASE(7, 0) BFB_CASE(7, 2) BFB_CASE(7, 3)
     BFB_CASE(8, 0) BFB_CASE(8, 1) BFB_CASE(8, 2) BFB_CASE(8, 3)
@@ -952,7 +956,11 @@ int bfb_launch_nuts_dmma(bfb_context *h, const bfb_run_out &o, int n_iter)
     if (h->scfg.max_treedepth > 10) return 1;
     if (const char *e = getenv("BFB200_SAMPLER")) { if (strcmp(e, "dmma")) return 1; }
     const int mv = (M.has_c2 ? 1 : 0) | (M.frag_ext ? 2 : 0);
+#ifdef BFB_NO_HEADLINE_SPLIT
+    if (M.frag_nr == 7 && mv == 1) return launch_dmma_w<7, 1>(h, o, n_iter);
+#else
     if (M.frag_nr == 7 && mv == 1) return bfb_launch_nuts_dmma_headline(h, o, n_iter);
+#endif
 #define BFB_CASE(NR_, MV_) if (M.frag_nr == NR_ && mv == MV_) return launch_dmma_w<NR_, MV_>(h, o, n_iter);
     BFB_CASE(4, 0) BFB_CASE(4, 1) BFB_CASE(4, 2) BFB_CASE(4, 3) BFB_CASE(7, 0) BFB_CASE(7, 2) BFB_CASE(7, 3)
     BFB_CASE(8, 0) BFB_CASE(8, 1) BFB_CASE(8, 2) BFB_CASE(8, 3)
