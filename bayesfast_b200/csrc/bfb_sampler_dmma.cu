@@ -93,10 +93,12 @@ __global__ void __launch_bounds__(32 * W, 1) nuts_dmma_kernel(DevModel M, bfb_sa
     const int n = M.n;
     const DmmaConsts K = dmma_consts(M);
 
-#ifdef BFB_DMMA_TIMING
+#ifdef BFB_DMMA_TIMING     // per-section cycle counters and round / section counts (printed with BFB200_DEBUG=1); costs ~1 %
 #define TICK(k) { const long long now_ = clock64(); tacc[k] += now_ - tlast; tlast = now_; }
+#define DBG_COUNT(v) ++v;
 #else
 #define TICK(k)
+#define DBG_COUNT(v)
 #endif
 #define VLD(dst, base)  _Pragma("unroll") for (int r_ = 0; r_ < NR; ++r_) dst[r_] = (base)[r_ * 32 + lane];
 #define VST(base, src)  _Pragma("unroll") for (int r_ = 0; r_ < NR; ++r_) (base)[r_ * 32 + lane] = src[r_];
@@ -141,7 +143,7 @@ __global__ void __launch_bounds__(32 * W, 1) nuts_dmma_kernel(DevModel M, bfb_sa
     double log_step = st.log_step[c], log_bar = st.log_bar[c];
     double e_step = exp(log_step), e_bar = exp(log_bar);    // refreshed only when dual averaging moves them
     int status = exists ? st.status[c] : 9;
-    unsigned tree_total = 0, dbg_rounds = 0, dbg_merges = 0, dbg_iend = 0;
+    unsigned tree_total = 0, dbg_rounds = 0, dbg_merges = 0, dbg_iend = 0; (void)dbg_rounds; (void)dbg_merges; (void)dbg_iend;
     long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64(); (void)tacc; (void)tlast;
     bool done = (status != 0) || it_lo >= it_hi;
     int it = it_lo;
@@ -171,7 +173,7 @@ __global__ void __launch_bounds__(32 * W, 1) nuts_dmma_kernel(DevModel M, bfb_sa
         TICK(7)
         // ================= iteration boundary: base_hmc.py:62-85, Tree.__init__ nuts.py:27-43 =================
         if (__any_sync(BFB_FULL, bnd)) {
-            ++dbg_iend;
+            DBG_COUNT(dbg_iend)
             const bool endp = bnd && !fresh;
             const bool warm_old = (it0 + it) < cfg.n_warmup;            // of the iteration that ends
             const size_t orow = (size_t)c * out.n_iter + it;
@@ -303,7 +305,7 @@ __global__ void __launch_bounds__(32 * W, 1) nuts_dmma_kernel(DevModel M, bfb_sa
             if (!__any_sync(BFB_FULL, !done)) break;
         }
         const bool live = !done;
-        ++dbg_rounds;
+        DBG_COUNT(dbg_rounds)
         TICK(0)
         // ---- uniforms of this round: lane lg of a quad holds draws 2 (t/2 + lg) + {0, 1} of its chain ----
         const int64_t tb2 = (t >> 1) << 1;
@@ -438,7 +440,7 @@ __global__ void __launch_bounds__(32 * W, 1) nuts_dmma_kernel(DevModel M, bfb_sa
 #pragma unroll 1
         while (__any_sync(BFB_FULL, need)) {
             const int lv = need ? lvl : 1;
-            ++dbg_merges;
+            DBG_COUNT(dbg_merges)
             double T1pl[NR], T1pr[NR], T1ps[NR];
             if (__any_sync(BFB_FULL, lv > LS)) {              // a deep level somewhere in the warp: generic loads
                 const double *sp = stack_ptr(lv);
@@ -566,10 +568,10 @@ __global__ void __launch_bounds__(32 * W, 1) nuts_dmma_kernel(DevModel M, bfb_sa
     __threadfence();
     __syncwarp();
     if (lane == 0) {
+#ifdef BFB_DMMA_TIMING
         atomicAdd(st.tree_total + 1, (unsigned long long)dbg_rounds);
         atomicAdd(st.tree_total + 2, (unsigned long long)dbg_merges);
         atomicAdd(st.tree_total + 3, (unsigned long long)dbg_iend);
-#ifdef BFB_DMMA_TIMING
         long long tsum = 0;
         for (int k_ = 0; k_ < 7; ++k_) { atomicAdd(st.tree_total + 4 + k_, (unsigned long long)tacc[k_]); tsum += tacc[k_]; }
         atomicAdd(st.tree_total + 11, (unsigned long long)(clock64() - t_unit0 - tsum));
