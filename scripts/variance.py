@@ -5,7 +5,7 @@ sys.path.insert(0, ROOT)
 import numpy as np
 import bayesfast_b200 as bfb
 from bayesfast_b200 import synthetic
-C = 4096
+C = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
 prob = synthetic.des_shaped(26, seed=1, n_chain=C)
 sur = bfb.PolyModel('cubic-2', input_size=26, output_size=1)
 sur.fit(prob['x_fit'], prob['y_fit'], logp=prob['y_fit'][:, 0])
