@@ -42,6 +42,7 @@ struct DevModel {
     const double *A2;    // [m][n][np]   A2[k][j]  = A[k][j]     (u_j = sum_k A[k][j] x_k^2)
     const double *c3;    // [m][C(n,3)]  packed j<k<l
     int64_t n_c3;
+    const int *c3_row;   // [n][n]  offset of the packed row (j, k), j < k < n - 1, i.e. of a_(j,k,k+1); -1 elsewhere
     int use_bound;
     const double *mu;    // [np]
     const double *HT;    // [n][np]  HT[k][j] = H[j][k]

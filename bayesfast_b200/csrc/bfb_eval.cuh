@@ -68,27 +68,63 @@ __device__ __forceinline__ void poly_fg(const DevModel &M, int o, const double *
         }
     }
     if (M.has_c3) {
+        // _cubic_3_f / _cubic_3_j (_poly.pyx:86-137).  The packed coefficients a_jkl (j < k < l, lexicographic) are read in
+        // rows (j, k): the lanes own l, so every row is one coalesced load and every coefficient is read twice per
+        // evaluation (333 KB at n = 64) instead of once per gradient entry through scattered loads.
+        //   pass A (j outer):  dP3/dx_j |_(j smallest) = sum_k x_k sum_l a_jkl x_l   -> one warp reduction per j
+        //                      dP3/dx_l |_(l largest)  = sum_(j<k) a_jkl x_j x_k      -> lane-private, no reduction
+        //                      P3 = sum_j x_j * (first sum)
+        //   pass B (k outer):  dP3/dx_k |_(k middle)   = sum_j x_j sum_l a_jkl x_l   -> one warp reduction per k
         const double *c3 = M.c3 + (size_t)o * M.n_c3;
+        const int *row = M.c3_row;
+        double Gl[NPL], f3 = 0.;
 #pragma unroll
-        for (int r = 0; r < NPL; ++r) {
-            int j = lane + 32 * r;
-            double g3 = 0.;
-            if (j < n) {
-                for (int k = 0; k < n - 1; ++k) {
-                    if (k == j) continue;
-                    double s = 0.;
-                    for (int l = k + 1; l < n; ++l) {
-                        if (l == j) continue;
-                        int a = min(j, k), c = max(j, l);
-                        int b = j + k + l - a - c;
-                        s = fma(c3[c3_index(a, b, c, n)], xsm[l], s);
+        for (int r = 0; r < NPL; ++r) Gl[r] = 0.;
+        for (int j = 0; j < n - 2; ++j) {
+            const double xj = xsm[j];
+            double pj = 0.;
+#pragma unroll 4
+            for (int k = j + 1; k < n - 1; ++k) {
+                const double xk = xsm[k], xjk = xj * xk;
+                const double *rp = c3 + __ldg(row + j * n + k) - (k + 1);        // rp[l] = a_jkl
+#pragma unroll
+                for (int r = 0; r < NPL; ++r) {
+                    if (32 * r + 31 > k) {
+                        const int l = lane + 32 * r;
+                        if (l > k && l < n) {
+                            const double a = __ldg(rp + l);
+                            pj = fma(xk, a * x[r], pj);
+                            Gl[r] = fma(a, xjk, Gl[r]);
+                        }
                     }
-                    g3 = fma(s, xsm[k], g3);
                 }
             }
-            J[r] += g3;
-            fpart = fma(x[r] * (1. / 3.), g3, fpart);   // Euler: sum_j x_j dP3/dx_j = 3 P3
+            const double tot = warp_sum(pj);
+            f3 = fma(xj, tot, f3);
+#pragma unroll
+            for (int r = 0; r < NPL; ++r) if (j == lane + 32 * r) J[r] += tot;
         }
+        for (int k = 1; k < n - 1; ++k) {
+            double qk = 0.;
+#pragma unroll 4
+            for (int j = 0; j < k; ++j) {
+                const double xj = xsm[j];
+                const double *rp = c3 + __ldg(row + j * n + k) - (k + 1);
+#pragma unroll
+                for (int r = 0; r < NPL; ++r) {
+                    if (32 * r + 31 > k) {
+                        const int l = lane + 32 * r;
+                        if (l > k && l < n) qk = fma(xj, __ldg(rp + l) * x[r], qk);
+                    }
+                }
+            }
+            const double tot = warp_sum(qk);
+#pragma unroll
+            for (int r = 0; r < NPL; ++r) if (k == lane + 32 * r) J[r] += tot;
+        }
+#pragma unroll
+        for (int r = 0; r < NPL; ++r) J[r] += Gl[r];
+        if (lane == 0) fpart += f3;
     }
     f = M.c0[o] + warp_sum(fpart);
 }

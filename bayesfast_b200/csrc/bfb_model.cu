@@ -227,6 +227,13 @@ int bfb_upload_model(bfb_context *h)
     if ((rc = upload(h, A1T, &D.A1T))) return rc;
     if ((rc = upload(h, A2, &D.A2))) return rc;
     if ((rc = upload(h, c3, &D.c3))) return rc;
+    {
+        std::vector<int> c3row(h3 ? (size_t)n * n : 1, -1);
+        if (h3)
+            for (int j = 0; j < n - 2; ++j)
+                for (int k = j + 1; k < n - 1; ++k) c3row[(size_t)j * n + k] = (int)c3_index_host(j, k, k + 1, n);
+        if ((rc = upload(h, c3row, &D.c3_row))) return rc;
+    }
 
     const bfb_model_desc &F = h->desc_flags;
     auto pad = [&](const std::vector<double> &v, double fill) {

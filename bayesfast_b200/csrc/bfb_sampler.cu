@@ -69,7 +69,7 @@ __device__ __forceinline__ double vdot(const double (&a)[NPL], const double (&va
     _Pragma("unroll") for (int r_ = 0; r_ < NPL; ++r_) wsm[(off) + lane + 32 * r_] = src[r_]
 
 template <int NPL, int SAMPLER>
-__global__ void __launch_bounds__(128) sampler_kernel(DevModel M, bfb_sampler_cfg cfg, ChainState st, RunOutDev out, int L)
+__global__ void __launch_bounds__(256) sampler_kernel(DevModel M, bfb_sampler_cfg cfg, ChainState st, RunOutDev out, int L)
 {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -535,21 +535,25 @@ static int launch_run(bfb_context *h, int sampler, int n_iter, const bfb_run_out
     if (fast_rc < 0) return fast_rc;
     if (fast_rc == 0) return BFB_OK;
     h->last_path = 0;
-    const int wpb = 4;
+    // warps per block: as many as the per-warp tree state leaves room for in shared memory (the evaluation is latency bound:
+    // at n = 64 a warp needs 32 KB, and 7 resident warps per SM instead of 4 are 1.7x the throughput)
     const int npl = h->np / 32;
+    int wpb = (int)((size_t)(227 * 1024) / (sizeof(double) * warp_smem_doubles(h->np, h->scfg.max_treedepth)));
+    if (wpb > 8) wpb = 8;
+    if (wpb < 1) wpb = 1;
     if (sampler == BFB_NUTS) {
         switch (npl) {
         case 1: rc = launch_sampler<1, BFB_NUTS>(h, od, wpb); break;
         case 2: rc = launch_sampler<2, BFB_NUTS>(h, od, wpb); break;
-        case 3: rc = launch_sampler<3, BFB_NUTS>(h, od, 2); break;
-        default: rc = launch_sampler<4, BFB_NUTS>(h, od, 2); break;
+        case 3: rc = launch_sampler<3, BFB_NUTS>(h, od, wpb); break;
+        default: rc = launch_sampler<4, BFB_NUTS>(h, od, wpb); break;
         }
     } else {
         switch (npl) {
         case 1: rc = launch_sampler<1, BFB_HMC>(h, od, wpb); break;
         case 2: rc = launch_sampler<2, BFB_HMC>(h, od, wpb); break;
-        case 3: rc = launch_sampler<3, BFB_HMC>(h, od, 2); break;
-        default: rc = launch_sampler<4, BFB_HMC>(h, od, 2); break;
+        case 3: rc = launch_sampler<3, BFB_HMC>(h, od, wpb); break;
+        default: rc = launch_sampler<4, BFB_HMC>(h, od, wpb); break;
         }
     }
     return rc;
