@@ -22,10 +22,14 @@
 #include "bfb_eval.cuh"      // to_original_1
 
 // MV = model variant: bit 0 = cubic-2 configs present, bit 1 = extended density (decay ellipsoid, variable transform,
-// module rescale: core/density.py:724-754, core/module.py:47-96) -- a second H block and the elementwise maps around it
+// module rescale: core/density.py:724-754, core/module.py:47-96) -- a second H block and the elementwise maps around it,
+// bit 2 = cubic-3 configs present: the gradient of P3 = sum_(j<k<l) a_jkl x_j x_k x_l is the GEMM
+// [chains x pairs (k<l)] . [pairs x n] of the pair products x_k x_l with T[(k,l)][j] = a_sorted(j,k,l) (0 if j in {k,l});
+// its operand table (k-tiles x N3T tiles) follows the per-dimension tables in shared memory, P3 = (sum_j x_j dP3/dx_j) / 3
 template <int NR, int MV>
 struct DmmaShape {
-    static constexpr bool C2 = MV & 1, EXT = (MV & 2) != 0;
+    static constexpr bool C2 = MV & 1, EXT = (MV & 2) != 0, C3 = (MV & 4) != 0;
+    static constexpr int N3T = (NR + 1) / 2;              // output tiles of the cubic-3 GEMM
     static constexpr int TX = C2 ? NR : (NR + 1) / 2;     // tiles of the block multiplying x
     static constexpr int T2 = C2 ? (NR + 1) / 2 : 0;      // tiles multiplying x^2
     static constexpr int TD = (NR + 1) / 2;               // tiles multiplying x - mu
@@ -39,6 +43,8 @@ struct DmmaShape {
 
 inline int bfb_frag_tiles(int nr, bool c2, bool ext) { return (c2 ? nr : (nr + 1) / 2) + (c2 ? (nr + 1) / 2 : 0) + (ext ? 2 : 1) * ((nr + 1) / 2); }
 // instantiated dims-per-lane for input_size n (0: not supported)
+// doubles of shared memory after the per-dimension tables for the cubic-3 block: operand table, pair table, per-warp x scratch
+__host__ __device__ inline int dmma_c3_doubles(int nr, int c3_kt, int nwarps) { return c3_kt * ((nr + 1) / 2) * 32 + c3_kt * 2 + nwarps * 256; }
 inline int bfb_frag_nr(int n) { return n <= 16 ? 4 : n <= 28 ? 7 : n <= 32 ? 8 : 0; }
 
 __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b)
@@ -109,6 +115,7 @@ struct DmmaConsts {
     // extended density
     double d_alpha2, d_gamma;
     int use_transform, use_scales, use_decay;
+    int c3_kt;          // k-tiles of the cubic-3 GEMM (pairs / 4, rounded up)
 };
 
 __device__ __forceinline__ DmmaConsts dmma_consts(const DevModel &M)
@@ -118,6 +125,7 @@ __device__ __forceinline__ DmmaConsts dmma_consts(const DevModel &M)
     K.f_mu = M.use_bound ? M.f_mu[0] : 0.; K.n = M.n;
     K.d_alpha2 = M.d_alpha2; K.d_gamma = M.d_gamma;
     K.use_transform = M.use_transform; K.use_scales = M.use_scales; K.use_decay = M.use_decay;
+    K.c3_kt = M.c3_kt;
     return K;
 }
 
@@ -134,6 +142,14 @@ __device__ __forceinline__ void dmma_stage_tables(const DevModel &M, double *msm
             msm[160 + j] = M.r_lo[j]; msm[192 + j] = M.r_w[j]; msm[224 + j] = (double)M.hb[j];
             msm[256 + j] = log(fabs(M.r_w[j]));     // log |dx/dx~| of an unbounded (affine) coordinate: constant
         }
+    }
+    if (MV & 4) {
+        // cubic-3 block: operand table [kt][tile][lane], then the pair table (k | l << 8) as ints
+        const int nd = M.c3_kt * M.c3_n3t * 32;
+        double *t3 = msm + ((MV & 2) ? 288 : 64);
+        for (int i = threadIdx.x; i < nd; i += blockDim.x) t3[i] = M.bfrag3[i];
+        int *pr = reinterpret_cast<int *>(t3 + nd);
+        for (int i = threadIdx.x; i < M.c3_kt * 4; i += blockDim.x) pr[i] = M.c3pair[i];
     }
 }
 
@@ -200,6 +216,32 @@ __device__ __forceinline__ void dmma_logp_grad(const double *bsm, int lane, cons
 #pragma unroll
     for (int r = 0; r < NR; ++r) x2[r] = x[r] * x[r];
     dmma_tiles<NR, MV, SH::O_X, SH::NT>(bsm, lane, x, x, x, x2, acc);
+    double g3[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) g3[r] = 0.;
+    if (SH::C3) {
+        // ---- cubic-3: pair products of the (possibly projected) point times the pair-by-dimension coefficient matrix ----
+        const double *t3 = msm + SH::MSM_DOUBLES;
+        const int *pr = reinterpret_cast<const int *>(t3 + K.c3_kt * SH::N3T * 32);
+        double *xs = reinterpret_cast<double *>(const_cast<int *>(pr) + K.c3_kt * 4) + (threadIdx.x >> 5) * 256 + (lane >> 2) * 32;
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < NR; ++r) xs[4 * r + lg] = x[r];
+        __syncwarp();
+        double a3[SH::N3T][2];
+#pragma unroll
+        for (int t = 0; t < SH::N3T; ++t) a3[t][0] = a3[t][1] = 0.;
+        const double *b3 = t3 + lane;
+#pragma unroll 2
+        for (int kt = 0; kt < K.c3_kt; ++kt) {
+            const int pk = pr[4 * kt + lg];
+            const double a = xs[pk & 0xff] * xs[pk >> 8];
+#pragma unroll
+            for (int t = 0; t < SH::N3T; ++t) dmma884(a3[t][0], a3[t][1], a, b3[(kt * SH::N3T + t) * 32]);
+        }
+#pragma unroll
+        for (int r = 0; r < NR; ++r) g3[r] = a3[r / 2][r % 2];
+    }
     double fpart = 0., jd = 0.;
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
@@ -214,6 +256,7 @@ __device__ __forceinline__ void dmma_logp_grad(const double *bsm, int lane, cons
             g += fma(2. * x[r], t, u);
             fpart = fma(x2[r], t, fpart);
         }
+        if (SH::C3) { g += g3[r]; fpart = fma(x[r] * (1. / 3.), g3[r], fpart); }     // Euler: sum_j x_j dP3/dx_j = 3 P3
         gn[r] = g;
         jd = fma(g, d0[r], jd);
     }

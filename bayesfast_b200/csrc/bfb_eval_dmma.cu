@@ -57,7 +57,8 @@ template <int NR, int MV>
 static int launch_eval(bfb_context *h, const double *X, int64_t C, double *LP, double *G)
 {
     using SH = DmmaShape<NR, MV>;
-    const size_t smem = sizeof(double) * (SH::FRAG_DOUBLES + SH::MSM_DOUBLES);
+    const size_t smem = sizeof(double) * (SH::FRAG_DOUBLES + SH::MSM_DOUBLES + (SH::C3 ? dmma_c3_doubles(NR, h->dm.c3_kt, 4) : 0));
+    if (smem > (size_t)(227 * 1024)) return 1;
     BFB_CUDA(cudaFuncSetAttribute(eval_dmma_kernel<NR, MV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 4;
     if (const char *e = getenv("BFB200_EVAL_BLOCKS_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 8) per_sm = v; }
@@ -73,12 +74,13 @@ static int launch_eval(bfb_context *h, const double *X, int64_t C, double *LP, d
 int bfb_launch_eval_dmma(bfb_context *h, const double *X, int64_t C, double *LP, double *G)
 {
     const DevModel &M = h->dm;
-    if (M.frag_nr == 0 || M.has_c3) return 1;
+    if (M.frag_nr == 0 || (M.has_c3 && (M.c3_kt == 0 || !M.has_c2))) return 1;
     if (const char *e = getenv("BFB200_EVAL")) { if (!strcmp(e, "generic")) return 1; }
-    const int mv = (M.has_c2 ? 1 : 0) | (M.frag_ext ? 2 : 0);
+    const int mv = (M.has_c2 ? 1 : 0) | (M.frag_ext ? 2 : 0) | (M.has_c3 ? 4 : 0);
 #define BFB_CASE(NR_, MV_) if (M.frag_nr == NR_ && mv == MV_) return launch_eval<NR_, MV_>(h, X, C, LP, G);
     BFB_CASE(4, 0) BFB_CASE(4, 1) BFB_CASE(4, 2) BFB_CASE(4, 3) BFB_CASE(7, 0) BFB_CASE(7, 1) BFB_CASE(7, 2) BFB_CASE(7, 3)
     BFB_CASE(8, 0) BFB_CASE(8, 1) BFB_CASE(8, 2) BFB_CASE(8, 3)
+    BFB_CASE(4, 5) BFB_CASE(4, 7) BFB_CASE(7, 5) BFB_CASE(7, 7)          // with cubic-3 configs (n <= 28)
 #undef BFB_CASE
     return 1;
 }

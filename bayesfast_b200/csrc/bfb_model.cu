@@ -4,6 +4,7 @@
 #include "bfb_eval.cuh"
 #include "bfb_dmma.cuh"
 int bfb_launch_eval_dmma(bfb_context *h, const double *X, int64_t C, double *LP, double *G);
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -255,7 +256,7 @@ int bfb_upload_model(bfb_context *h)
         if ((rc = upload(h, HT, &D.HT))) return rc;
         // operand table of the tensor-core evaluator (bfb_dmma.cuh), output 0
         const int nr = bfb_frag_nr(n);
-        if (nr > 0 && !h3 && np == 32) {
+        if (nr > 0 && np == 32) {
             const bool c2 = h2;
             const bool ext = F.use_decay || F.use_transform || F.use_scales;     // MV bit 1 (bfb_dmma.cuh)
             const int TX = c2 ? nr : (nr + 1) / 2, NT = bfb_frag_tiles(nr, c2, ext);
@@ -277,6 +278,35 @@ int bfb_upload_model(bfb_context *h)
                     }
             if ((rc = upload(h, fr, &D.bfrag))) return rc;
             D.frag_nr = nr; D.frag_nt = NT; D.frag_ext = ext ? 1 : 0;
+        }
+        // cubic-3 block (bfb_dmma.cuh, MV bit 2): pairs (k < l) in lexicographic order, 4 per k-tile; column (tile t, lane
+        // quad-owner `own`, e) holds dimension j = 4 (2 t + e) + own like the other blocks
+        if (nr > 0 && h3 && np == 32 && nr <= 7) {
+            const int n3t = (nr + 1) / 2, n_pairs = n * (n - 1) / 2, kt3 = (n_pairs + 3) / 4;
+            std::vector<int> pairs((size_t)kt3 * 4, 0);
+            {
+                int p = 0;
+                for (int k = 0; k < n; ++k)
+                    for (int l = k + 1; l < n; ++l) pairs[p++] = k | (l << 8);
+            }
+            std::vector<double> f3((size_t)kt3 * n3t * 32, 0.);
+            for (int kt = 0; kt < kt3; ++kt)
+                for (int t = 0; t < n3t; ++t)
+                    for (int lane = 0; lane < 32; ++lane) {
+                        const int p = 4 * kt + (lane & 3), gid = lane >> 2, own = gid >> 1, e = gid & 1;
+                        const int v = 2 * t + e, j = 4 * v + own;
+                        if (p >= n_pairs || v >= nr || j >= n) continue;
+                        const int k = pairs[p] & 0xff, l = pairs[p] >> 8;
+                        if (j == k || j == l) continue;
+                        int a = j, b = k, c = l;
+                        if (a > b) std::swap(a, b);
+                        if (b > c) std::swap(b, c);
+                        if (a > b) std::swap(a, b);
+                        f3[((size_t)kt * n3t + t) * 32 + lane] = c3[c3_index_host(a, b, c, n)];     // output 0
+                    }
+            if ((rc = upload(h, f3, &D.bfrag3))) return rc;
+            if ((rc = upload(h, pairs, &D.c3pair))) return rc;
+            D.c3_kt = kt3; D.c3_n3t = n3t;
         }
         std::vector<double> fm(m, 0.);
         for (int o = 0; o < m && o < (int)h->h_fmu.size(); ++o) fm[o] = h->h_fmu[o];

@@ -87,7 +87,8 @@ __global__ void __launch_bounds__(32 * W, 1) nuts_dmma_kernel(DevModel M, bfb_sa
     dmma_stage_tables<MV>(M, msm);
     __syncthreads();
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, gi = lane >> 2, lg = lane & 3;
-    double *wsm = smem + SH::FRAG_DOUBLES + SH::MSM_DOUBLES + (size_t)wib * warp_smem_doubles(NR, LS);
+    const int c3x = SH::C3 ? dmma_c3_doubles(NR, M.c3_kt, W) : 0;          // cubic-3 operand table, pair table, x scratch
+    double *wsm = smem + SH::FRAG_DOUBLES + SH::MSM_DOUBLES + c3x + (size_t)wib * warp_smem_doubles(NR, LS);
     double *sTL = wsm, *sTR = wsm + 3 * SLOT, *sPS = wsm + 6 * SLOT, *sPB = wsm + 7 * SLOT, *sST = wsm + 8 * SLOT;
     double *ssc = wsm + (8 + 3 * LS) * SLOT + gi;        // scalar (field f, level l) of this chain at ssc[(f * 10 + l) * 8]
     const int n = M.n;
@@ -801,7 +802,8 @@ static int launch_hmc_dmma(bfb_context *h, const bfb_run_out &o, int n_iter)
     using SH = DmmaShape<NR, MV>;
     const int64_t C = h->cs.C;
     const int n_groups = (int)((C + 7) / 8);
-    const size_t smem = sizeof(double) * (SH::FRAG_DOUBLES + SH::MSM_DOUBLES);
+    const size_t smem = sizeof(double) * (SH::FRAG_DOUBLES + SH::MSM_DOUBLES + (SH::C3 ? dmma_c3_doubles(NR, h->dm.c3_kt, W) : 0));
+    if (smem > (size_t)(227 * 1024)) return 1;
     BFB_CUDA(cudaFuncSetAttribute(hmc_dmma_kernel<NR, MV, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     RunOutDevF od;
     od.o = o; od.n_iter = n_iter;
@@ -862,9 +864,9 @@ int bfb_launch_hmc_dmma_headline(bfb_context *h, const bfb_run_out &o, int n_ite
 int bfb_launch_hmc_dmma(bfb_context *h, const bfb_run_out &o, int n_iter)
 {
     const DevModel &M = h->dm;
-    if (M.frag_nr == 0 || M.has_c3) return 1;
+    if (M.frag_nr == 0 || (M.has_c3 && (M.c3_kt == 0 || !M.has_c2))) return 1;
     if (const char *e = getenv("BFB200_SAMPLER")) { if (strcmp(e, "dmma")) return 1; }
-    const int mv = (M.has_c2 ? 1 : 0) | (M.frag_ext ? 2 : 0);
+    const int mv = (M.has_c2 ? 1 : 0) | (M.frag_ext ? 2 : 0) | (M.has_c3 ? 4 : 0);
 #ifdef BFB_NO_HEADLINE_SPLIT     // experiment: the headline instantiation inside the big module
     if (M.frag_nr == 7 && mv == 1) return launch_hmc_dmma_w<7, 1>(h, o, n_iter);
 #else
@@ -873,6 +875,7 @@ int bfb_launch_hmc_dmma(bfb_context *h, const bfb_run_out &o, int n_iter)
 #define BFB_CASE(NR_, MV_) if (M.frag_nr == NR_ && mv == MV_) return launch_hmc_dmma_w<NR_, MV_>(h, o, n_iter);
     BFB_CASE(4, 0) BFB_CASE(4, 1) BFB_CASE(4, 2) BFB_CASE(4, 3) BFB_CASE(7, 0) BFB_CASE(7, 2) BFB_CASE(7, 3)
     BFB_CASE(8, 0) BFB_CASE(8, 1) BFB_CASE(8, 2) BFB_CASE(8, 3)
+    BFB_CASE(4, 5) BFB_CASE(4, 7) BFB_CASE(7, 5) BFB_CASE(7, 7)          // with cubic-3 configs (n <= 28)
 #undef BFB_CASE
     return 1;
 }
@@ -889,7 +892,8 @@ static int launch_dmma(bfb_context *h, const bfb_run_out &o, int n_iter, int cpg
     // one persistent block of W warps per SM (W = 4: one warp per scheduler, 4096 chains = 512 warps on 592 schedulers;
     // W = 8 when there are more groups than that); the first LS levels of the tree stack live in shared memory, deeper
     // (rarely touched) levels in an L2-resident buffer
-    const size_t fixed = sizeof(double) * (SH::FRAG_DOUBLES + SH::MSM_DOUBLES);
+    const size_t fixed = sizeof(double) * (SH::FRAG_DOUBLES + SH::MSM_DOUBLES + (SH::C3 ? dmma_c3_doubles(NR, h->dm.c3_kt, W) : 0));
+    if (fixed + sizeof(double) * W * warp_smem_doubles(NR, 1) > (size_t)(227 * 1024)) return 1;      // does not fit: generic kernel
     const size_t budget = (size_t)(227 * 1024) - 1024 - fixed;
     int LS = L;
     while (LS > 1 && sizeof(double) * W * warp_smem_doubles(NR, LS) > budget) --LS;
@@ -954,10 +958,10 @@ int bfb_launch_nuts_dmma_headline(bfb_context *h, const bfb_run_out &o, int n_it
 int bfb_launch_nuts_dmma(bfb_context *h, const bfb_run_out &o, int n_iter)
 {
     const DevModel &M = h->dm;
-    if (M.frag_nr == 0 || M.has_c3) return 1;
+    if (M.frag_nr == 0 || (M.has_c3 && (M.c3_kt == 0 || !M.has_c2))) return 1;
     if (h->scfg.max_treedepth > 10) return 1;
     if (const char *e = getenv("BFB200_SAMPLER")) { if (strcmp(e, "dmma")) return 1; }
-    const int mv = (M.has_c2 ? 1 : 0) | (M.frag_ext ? 2 : 0);
+    const int mv = (M.has_c2 ? 1 : 0) | (M.frag_ext ? 2 : 0) | (M.has_c3 ? 4 : 0);
 #ifdef BFB_NO_HEADLINE_SPLIT
     if (M.frag_nr == 7 && mv == 1) return launch_dmma_w<7, 1>(h, o, n_iter);
 #else
@@ -966,6 +970,7 @@ int bfb_launch_nuts_dmma(bfb_context *h, const bfb_run_out &o, int n_iter)
 #define BFB_CASE(NR_, MV_) if (M.frag_nr == NR_ && mv == MV_) return launch_dmma_w<NR_, MV_>(h, o, n_iter);
     BFB_CASE(4, 0) BFB_CASE(4, 1) BFB_CASE(4, 2) BFB_CASE(4, 3) BFB_CASE(7, 0) BFB_CASE(7, 2) BFB_CASE(7, 3)
     BFB_CASE(8, 0) BFB_CASE(8, 1) BFB_CASE(8, 2) BFB_CASE(8, 3)
+    BFB_CASE(4, 5) BFB_CASE(4, 7) BFB_CASE(7, 5) BFB_CASE(7, 7)          // with cubic-3 configs (n <= 28)
 #undef BFB_CASE
     return 1;
 }

@@ -160,3 +160,23 @@ def test_tensor_core_evaluator_extended_density(handle, oracle, monkeypatch):
     monkeypatch.setenv('BFB200_EVAL', 'generic')
     lp2, g2 = handle.logp_and_grad_batch(X)
     assert rel_err(lp, lp2) < 1e-12 and rel_err(g, g2) < 1e-12
+
+
+@pytest.mark.parametrize('n,kw', [(26, {}), (12, {}), (7, dict(decay=True, transform=True)), (28, {})])
+def test_tensor_core_evaluator_cubic3(handle, oracle, monkeypatch, n, kw):
+    """cubic-3 configs on the tensor-core evaluator (model variant bit 2: pair products x [pairs x n] coefficient GEMM)
+    vs the oracle (_cubic_3_f / _cubic_3_j, _poly.pyx:86-137) and vs the generic kernel, inside and outside the bound"""
+    spec, cov = synthetic_spec(n, 'cubic-3', seed=200 + n, cubic_scale=0.05, **kw)
+    handle.set_model(to_device_spec(spec))
+    rng = np.random.default_rng(3)
+    C = 1037
+    X = (np.linalg.cholesky(cov) @ rng.normal(size=(n, C))).T * rng.choice([0.4, 1., 2.5, 5.], size=(C, 1))
+    if spec['transform_ranges'] is not None:
+        X = np.clip(X, spec['transform_ranges'][:, 0] * 0.9, spec['transform_ranges'][:, 1] * 0.9)
+        X = np.array([oracle.from_original(x, spec['transform_ranges'], spec['hard_bounds']) for x in X])
+    lp, g = handle.logp_and_grad_batch(X)
+    lpo, go = oracle.OracleDensity(spec).logp_and_grad_batch(X)
+    assert rel_err(lp, lpo) < RTOL and rel_err(g, go) < RTOL
+    monkeypatch.setenv('BFB200_EVAL', 'generic')
+    lp2, g2 = handle.logp_and_grad_batch(X)
+    assert rel_err(lp, lp2) < 1e-11 and rel_err(g, g2) < 1e-11

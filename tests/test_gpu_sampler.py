@@ -366,3 +366,32 @@ def test_tensor_core_nuts_deep_trees(handle, oracle, monkeypatch, env):
     for k in INT_STATS:
         assert np.array_equal(out[k], ref[k]), k
     check_floats(out['samples'], ref['samples'], 'samples')
+
+
+@pytest.mark.parametrize('n,sampler,C', [(26, 'NUTS', 50), (10, 'NUTS', 33), (26, 'HMC', 40)])
+def test_tensor_core_cubic3_samplers(handle, oracle, monkeypatch, n, sampler, C):
+    """cubic-3 surrogates (n <= 28) on the tensor-core NUTS / HMC kernels: decisions identical to the oracle and the generic kernel"""
+    spec, cov = synthetic_spec(n, 'cubic-3', seed=60 + n, cubic_scale=0.05)
+    spec['alpha'] = spec['alpha'] / 1.6
+    handle.set_model(to_device_spec(spec))
+    n_iter = 30
+    x0 = (np.linalg.cholesky(cov) @ np.random.default_rng(9).normal(size=(n, C))).T
+    cfg = cfg_from({'n_int_step': 10}, n_iter // 2, 909, chain0=2)
+    step0 = 0.6 / n**0.25
+    handle.sampler_init(cfg, x0, step0, np.ones(n), x0)
+    out = handle.sampler_run(sampler, n_iter)
+    assert handle.sampler_last_path() == 'dmma'
+    st = handle.sampler_state()
+    assert np.all(st['status'] == 0)
+    U, Z = device_draws(handle, 909, st['n_draws'], 2)
+    ref = oracle.OracleDensity(spec).run(sampler, dict(n_iter=n_iter, n_warmup=n_iter // 2, n_int_step=10), x0, step0, np.ones(n),
+                                         draws_u=U, draws_z=Z)
+    assert np.array_equal(st['n_draws'], ref['n_draws'])
+    for k in ('tree_depth', 'diverging') + (('tree_size',) if sampler == 'NUTS' else ()):
+        assert np.array_equal(out[k], ref[k]), k
+    check_floats(out['samples'], ref['samples'], 'samples', late=1e-2)
+    monkeypatch.setenv('BFB200_SAMPLER', 'generic')
+    handle.sampler_init(cfg, x0, step0, np.ones(n), x0)
+    gen = handle.sampler_run(sampler, n_iter)
+    assert handle.sampler_last_path() == 'generic'
+    assert np.array_equal(out['tree_depth'], gen['tree_depth']) and np.array_equal(out['diverging'], gen['diverging'])
