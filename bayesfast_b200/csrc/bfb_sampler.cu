@@ -538,9 +538,15 @@ static int launch_run(bfb_context *h, int sampler, int n_iter, const bfb_run_out
     // warps per block: as many as the per-warp tree state leaves room for in shared memory (the evaluation is latency bound:
     // at n = 64 a warp needs 32 KB, and 7 resident warps per SM instead of 4 are 1.7x the throughput)
     const int npl = h->np / 32;
-    int wpb = (int)((size_t)(227 * 1024) / (sizeof(double) * warp_smem_doubles(h->np, h->scfg.max_treedepth)));
-    if (wpb > 8) wpb = 8;
-    if (wpb < 1) wpb = 1;
+    int wpb = 1;
+    {
+        const size_t per_warp = sizeof(double) * warp_smem_doubles(h->np, h->scfg.max_treedepth), cap = 227 * 1024;
+        size_t best = 0;
+        for (int w = 1; w <= 8; ++w) {                       // resident warps per SM = blocks that fit x warps per block
+            const size_t resident = (cap / (w * per_warp + 1024)) * w;
+            if (resident > best) { best = resident; wpb = w; }
+        }
+    }
     if (sampler == BFB_NUTS) {
         switch (npl) {
         case 1: rc = launch_sampler<1, BFB_NUTS>(h, od, wpb); break;
