@@ -1,11 +1,13 @@
 // bfb_eval_dmma.cu -- batched surrogate evaluation on the FP64 tensor cores: logp and gradient of C points,
 // eight points per warp (bfb_dmma.cuh).  Replaces Density.logp_and_grad (core/density.py:724-754) over
-// PolyModel._fun_and_jac (modules/poly.py:443-503) for a surrogate-only density with linear + quadratic (+ cubic-2)
-// configs, radial bound, no decay / transform / module rescale; everything else runs density_eval_kernel (bfb_model.cu).
+// PolyModel._fun_and_jac (modules/poly.py:443-503) for a surrogate-only density with linear + quadratic (+ cubic-2
+// (+ cubic-3)) configs, n <= 32 (28 with cubic-3), with or without radial bound, decay, variable transform and module
+// rescale; everything else runs density_eval_kernel (bfb_model.cu).
 //
-// Persistent blocks of 4 warps; the operand table (27 KB at n = 26) is staged once per block in shared memory and
-// every DMMA reads its B fragment with one conflict-free 8-byte load per lane.  Points are read and gradients written
-// in the caller's [C, n] layout: the 4 lanes of a quad touch one 32-byte sector per r.
+// Persistent blocks of 4 warps; the operand table (29 KB at n = 26 cubic-2) is staged once per block in shared memory and
+// every two DMMAs read their B fragments with one conflict-free 16-byte load per lane.  Points are read (software
+// pipelined: the next group is in flight during the evaluation) and gradients written in the caller's [C, n] layout: the 4
+// lanes of a quad touch one 32-byte sector per r.
 #include "bfb_dmma.cuh"
 #include <cstring>
 #include <cstdlib>

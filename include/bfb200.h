@@ -116,7 +116,8 @@ int bfb_fit_max_beta(bfb_handle h, const double *x, int64_t N, const double *mu,
 /* ------------------------------------------------------------------------------------------------
  * Sampler: replaces bayesfast.core.sample.sample()'s worker pool (core/sample.py:165-214,
  * utils/parallel.py:130-150) and NUTS/HMC.run (samplers/hmc_utils/base_hmc.py:62-172, samplers/nuts.py,
- * samplers/hmc.py, hmc_utils/integration.py, metrics.py, step_size.py) for C chains at once, one warp per chain.
+ * samplers/hmc.py, hmc_utils/integration.py, metrics.py, step_size.py) for C chains at once (eight chains per warp on the
+ * FP64 tensor cores for input_size <= 32 without multi-output / n > 28 cubic-3 models; one warp per chain otherwise).
  * Random stream: include/bfb_rng.h, chain ids chain0 .. chain0+C-1.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct {
