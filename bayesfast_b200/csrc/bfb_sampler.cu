@@ -593,6 +593,7 @@ extern "C" int bfb_sampler_run(bfb_handle h, int sampler, int32_t n_iter, const 
         // chunk k-1 is copied to the caller's arrays on a second stream (strided 2-D copies: the host layout is
         // chain-major).  With pinned host memory (bfb_host_alloc) the copies are hidden behind the kernels.
         int n_chunks = n_iter >= 512 ? 6 : (n_iter >= 128 ? 3 : 1);
+        if (const char *e = getenv("BFB200_E2E_CHUNKS")) { int v = atoi(e); if (v >= 1 && v <= n_iter) n_chunks = v; }
         const int K = (n_iter + n_chunks - 1) / n_chunks;
         n_chunks = (n_iter + K - 1) / K;
         size_t rec = 0;
