@@ -476,22 +476,83 @@ static void wvar_add(wvar *w, int n, const double *x, double weight)
     }
 }
 
-/* metrics.py:51-91 QuadMetricDiag and :135-211 QuadMetricDiagAdapt */
+/* metrics.py:374-417 _WeightedCovariance (dense metric) */
+typedef struct { double n_samples; double *mean, *raw_cov; } wcov;
+static void wcov_init(wcov *w, int n, const double *mean0, const double *cov0, double weight)
+{
+    w->n_samples = weight;
+    w->mean = (double *)calloc((size_t)n, sizeof(double));
+    w->raw_cov = (double *)calloc((size_t)n * n, sizeof(double));
+    if (mean0) memcpy(w->mean, mean0, sizeof(double) * (size_t)n);
+    if (cov0) memcpy(w->raw_cov, cov0, sizeof(double) * (size_t)n * n);
+    else for (int i = 0; i < n; ++i) w->raw_cov[(size_t)i * n + i] = 1.;      /* np.eye(nelem) */
+    for (size_t i = 0; i < (size_t)n * n; ++i) w->raw_cov[i] *= w->n_samples;
+}
+static void wcov_free(wcov *w) { free(w->mean); free(w->raw_cov); }
+static void wcov_add(wcov *w, int n, const double *x, double weight, double *old_diff, double *new_diff)
+{
+    w->n_samples += 1.;
+    for (int i = 0; i < n; ++i) {
+        old_diff[i] = x[i] - w->mean[i];
+        w->mean[i] += old_diff[i] / w->n_samples;
+        new_diff[i] = x[i] - w->mean[i];
+    }
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) w->raw_cov[(size_t)i * n + j] += weight * new_diff[i] * old_diff[j];
+}
+
+/* scipy.linalg.cholesky(cov, lower=True) (LAPACK dpotrf, lower triangle of cov only); returns 0 on a
+ * non-positive pivot, in which case `chol` is left untouched (metrics.py:282-287 keeps the old factor) */
+static int chol_lower(const double *cov, double *chol, double *work, int n)
+{
+    for (int j = 0; j < n; ++j) {
+        for (int i = j; i < n; ++i) {
+            double s = cov[(size_t)i * n + j];
+            for (int k = 0; k < j; ++k) s -= work[(size_t)i * n + k] * work[(size_t)j * n + k];
+            if (i == j) {
+                if (!(s > 0.)) return 0;
+                work[(size_t)j * n + j] = sqrt(s);
+            } else work[(size_t)i * n + j] = s / work[(size_t)j * n + j];
+        }
+        for (int i = 0; i < j; ++i) work[(size_t)i * n + j] = 0.;
+    }
+    memcpy(chol, work, sizeof(double) * (size_t)n * n);
+    return 1;
+}
+
+/* metrics.py:51-91 QuadMetricDiag, :94-132 QuadMetricFull, :135-211 QuadMetricDiagAdapt, :240-330 QuadMetricFullAdapt */
 typedef struct {
-    int n, adapt; double *var, *std, *inv_std;
-    wvar fg, bg; int64_t n_samples, previous_update; int adapt_window, update_window, doubling;
+    int n, adapt, dense; double *var, *std, *inv_std;
+    double *cov, *chol, *work, *d_old, *d_new; int chol_error;
+    wvar fg, bg; wcov fgc, bgc; int64_t n_samples, previous_update; int adapt_window, update_window, doubling;
 } metric_t;
 
 static void metric_init(metric_t *mt, int n, const double *mean0, const double *var0, const bfo_sampler_cfg *cfg)
 {
-    mt->n = n; mt->adapt = cfg->adapt_metric;
-    mt->var = (double *)malloc(sizeof(double) * (size_t)n);
-    mt->std = (double *)malloc(sizeof(double) * (size_t)n);
-    mt->inv_std = (double *)malloc(sizeof(double) * (size_t)n);
-    for (int i = 0; i < n; ++i) { mt->var[i] = var0[i]; mt->std[i] = sqrt(var0[i]); mt->inv_std[i] = 1. / mt->std[i]; }
-    if (mt->adapt) {
-        wvar_init(&mt->fg, n, mean0, var0, cfg->initial_weight);
-        wvar_init(&mt->bg, n, NULL, NULL, 10.);   /* _WeightedVariance(self._n): default weight 10, zero mean/var */
+    mt->n = n; mt->adapt = cfg->adapt_metric; mt->dense = cfg->dense_metric; mt->chol_error = 0;
+    mt->var = mt->std = mt->inv_std = mt->cov = mt->chol = mt->work = mt->d_old = mt->d_new = NULL;
+    if (mt->dense) {
+        size_t nn = (size_t)n * n;
+        mt->cov = (double *)malloc(sizeof(double) * nn);
+        mt->chol = (double *)calloc(nn, sizeof(double));
+        mt->work = (double *)malloc(sizeof(double) * nn);
+        mt->d_old = (double *)malloc(sizeof(double) * (size_t)n);
+        mt->d_new = (double *)malloc(sizeof(double) * (size_t)n);
+        memcpy(mt->cov, var0, sizeof(double) * nn);
+        if (!chol_lower(mt->cov, mt->chol, mt->work, n)) mt->chol_error = 1;
+        if (mt->adapt) {
+            wcov_init(&mt->fgc, n, mean0, var0, cfg->initial_weight);
+            wcov_init(&mt->bgc, n, NULL, NULL, 10.);   /* _WeightedCovariance(self._n): weight 10, zero mean, identity */
+        }
+    } else {
+        mt->var = (double *)malloc(sizeof(double) * (size_t)n);
+        mt->std = (double *)malloc(sizeof(double) * (size_t)n);
+        mt->inv_std = (double *)malloc(sizeof(double) * (size_t)n);
+        for (int i = 0; i < n; ++i) { mt->var[i] = var0[i]; mt->std[i] = sqrt(var0[i]); mt->inv_std[i] = 1. / mt->std[i]; }
+        if (mt->adapt) {
+            wvar_init(&mt->fg, n, mean0, var0, cfg->initial_weight);
+            wvar_init(&mt->bg, n, NULL, NULL, 10.);   /* _WeightedVariance(self._n): default weight 10, zero mean/var */
+        }
     }
     mt->n_samples = 0; mt->previous_update = 0;
     mt->adapt_window = cfg->adapt_window; mt->update_window = cfg->update_window; mt->doubling = cfg->doubling;
@@ -499,14 +560,56 @@ static void metric_init(metric_t *mt, int n, const double *mean0, const double *
 static void metric_free(metric_t *mt)
 {
     free(mt->var); free(mt->std); free(mt->inv_std);
-    if (mt->adapt) { wvar_free(&mt->fg); wvar_free(&mt->bg); }
+    free(mt->cov); free(mt->chol); free(mt->work); free(mt->d_old); free(mt->d_new);
+    if (mt->adapt && !mt->dense) { wvar_free(&mt->fg); wvar_free(&mt->bg); }
+    if (mt->adapt && mt->dense) { wcov_free(&mt->fgc); wcov_free(&mt->bgc); }
 }
-/* metrics.py:186-211 */
+/* metrics.py:73-75 / :113-115 velocity */
+static void metric_velocity(const metric_t *mt, const double *p, double *v)
+{
+    int n = mt->n;
+    if (!mt->dense) { for (int i = 0; i < n; ++i) v[i] = mt->var[i] * p[i]; return; }
+    for (int i = 0; i < n; ++i) {
+        double s = 0.;
+        for (int j = 0; j < n; ++j) s += mt->cov[(size_t)i * n + j] * p[j];
+        v[i] = s;
+    }
+}
+/* metrics.py:83-86 / :123-127 random: `z` holds the n normals in draw order */
+static void metric_random(const metric_t *mt, const double *z, double *p)
+{
+    int n = mt->n;
+    if (!mt->dense) { for (int i = 0; i < n; ++i) p[i] = mt->inv_std[i] * z[i]; return; }
+    /* solve_triangular(chol.T, vals): back substitution with U = L^T */
+    for (int i = n - 1; i >= 0; --i) {
+        double s = z[i];
+        for (int j = i + 1; j < n; ++j) s -= mt->chol[(size_t)j * n + i] * p[j];
+        p[i] = s / mt->chol[(size_t)i * n + i];
+    }
+}
+/* metrics.py:186-211 / :289-313 */
 static void metric_update(metric_t *mt, const double *sample, int warmup)
 {
     if (!mt->adapt || !warmup) return;
     int n = mt->n;
     int64_t delta = mt->n_samples - mt->previous_update;
+    if (mt->dense) {
+        wcov_add(&mt->fgc, n, sample, 1., mt->d_old, mt->d_new);
+        wcov_add(&mt->bgc, n, sample, 1., mt->d_old, mt->d_new);
+        if ((delta + 1) % mt->update_window == 0) {
+            for (size_t i = 0; i < (size_t)n * n; ++i) mt->cov[i] = mt->fgc.raw_cov[i] / mt->fgc.n_samples;
+            if (!chol_lower(mt->cov, mt->chol, mt->work, n)) mt->chol_error = 1;
+        }
+        if (delta >= mt->adapt_window) {
+            wcov_free(&mt->fgc);
+            mt->fgc = mt->bgc;
+            wcov_init(&mt->bgc, n, NULL, NULL, 10.);
+            mt->previous_update = mt->n_samples;
+            if (mt->doubling) mt->adapt_window *= 2;
+        }
+        mt->n_samples += 1;
+        return;
+    }
     wvar_add(&mt->fg, n, sample, 1.);
     wvar_add(&mt->bg, n, sample, 1.);
     if ((delta + 1) % mt->update_window == 0) {
@@ -555,7 +658,7 @@ static state_t compute_state(integ_t *ig, const double *q, const double *p)
     memcpy(s.p, p, sizeof(double) * (size_t)n);
     bfo_logp_and_grad(ig->den, s.q, &s.logp, s.g); ig->n_eval++;
     double kin = 0.;
-    for (int i = 0; i < n; ++i) { s.v[i] = ig->mt->var[i] * s.p[i]; }
+    metric_velocity(ig->mt, s.p, s.v);
     for (int i = 0; i < n; ++i) kin += s.p[i] * s.v[i];
     kin *= 0.5;
     s.energy = kin - s.logp;
@@ -569,12 +672,12 @@ static state_t leapfrog(integ_t *ig, double epsilon, const state_t *st)
     state_t s = new_state(ig);
     double dt = 0.5 * epsilon;
     for (int i = 0; i < n; ++i) s.p[i] = st->p[i] + dt * st->g[i];         /* axpy */
-    for (int i = 0; i < n; ++i) s.v[i] = ig->mt->var[i] * s.p[i];
+    metric_velocity(ig->mt, s.p, s.v);
     for (int i = 0; i < n; ++i) s.q[i] = st->q[i] + epsilon * s.v[i];      /* axpy */
     bfo_logp_and_grad(ig->den, s.q, &s.logp, s.g); ig->n_eval++;
     for (int i = 0; i < n; ++i) s.p[i] = s.p[i] + dt * s.g[i];            /* axpy */
     double kin = 0.;
-    for (int i = 0; i < n; ++i) s.v[i] = ig->mt->var[i] * s.p[i];
+    metric_velocity(ig->mt, s.p, s.v);
     for (int i = 0; i < n; ++i) kin += s.p[i] * s.v[i];
     kin *= 0.5;
     s.energy = kin - s.logp;
@@ -759,6 +862,7 @@ static int run_chain(const bfo_density *den, const bfo_sampler_cfg *cfg, int is_
     double *q = (double *)malloc(sizeof(double) * (size_t)n);
     double *p0 = (double *)malloc(sizeof(double) * (size_t)n);
     double *psum = (double *)malloc(sizeof(double) * (size_t)n);
+    double *zz = (double *)malloc(sizeof(double) * (size_t)n);
     memcpy(q, x0, sizeof(double) * (size_t)n);
 
     /* base_hmc.py:42-46 */
@@ -774,7 +878,8 @@ static int run_chain(const bfo_density *den, const bfo_sampler_cfg *cfg, int is_
     for (int it = 0; it < n_iter; ++it) {
         int warmup = it < cfg->n_warmup;
         ig.arena_used = 0;
-        for (int i = 0; i < n; ++i) p0[i] = mt.inv_std[i] * rng_normal(&rng);     /* metrics.py:83-86 */
+        for (int i = 0; i < n; ++i) zz[i] = rng_normal(&rng);
+        metric_random(&mt, zz, p0);                                               /* metrics.py:83-86, 123-127 */
         state_t start = compute_state(&ig, q, p0);
         if (!isfinite(start.energy)) { status = 2; break; }
         double step_size = da_current(&da, warmup);
@@ -839,10 +944,13 @@ done:
         out->final_step[c * 4 + 0] = da.log_step; out->final_step[c * 4 + 1] = da.log_bar;
         out->final_step[c * 4 + 2] = da.hbar; out->final_step[c * 4 + 3] = (double)da.count;
     }
-    if (out->final_var) memcpy(out->final_var + c * n, mt.var, sizeof(double) * (size_t)n);
+    if (out->final_var) {
+        if (mt.dense) memcpy(out->final_var + (size_t)c * n * n, mt.cov, sizeof(double) * (size_t)n * n);
+        else memcpy(out->final_var + c * n, mt.var, sizeof(double) * (size_t)n);
+    }
     if (out->n_draws) out->n_draws[c] = rng.t;
     if (out->status) out->status[c] = status;
-    free(ig.arena); free(vecs); free(q); free(p0); free(psum);
+    free(ig.arena); free(vecs); free(q); free(p0); free(psum); free(zz);
     metric_free(&mt);
     return status;
 }
@@ -859,7 +967,7 @@ static int run_all(const bfo_density *den, const bfo_sampler_cfg *cfg, int is_nu
 #pragma omp parallel for schedule(dynamic, 1) num_threads(nt) reduction(| : bad)
 #endif
     for (int64_t c = 0; c < C; ++c) {
-        int s = run_chain(den, cfg, is_nuts, c, chain0 + c, x0 + c * n, step0[c], var0 + c * n, mean0 + c * n,
+        int s = run_chain(den, cfg, is_nuts, c, chain0 + c, x0 + c * n, step0[c], var0 + c * (cfg->dense_metric ? (int64_t)n * n : n), mean0 + c * n,
                           ru ? ru + c * n_replay : NULL, rz ? rz + c * n_replay : NULL, n_replay, out);
         bad |= (s != 0);
     }

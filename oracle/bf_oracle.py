@@ -60,7 +60,7 @@ class _Cfg(C.Structure):
                 ('target_accept', C.c_double), ('gamma', C.c_double), ('k', C.c_double), ('t0', C.c_double),
                 ('adapt_metric', C.c_int32), ('initial_weight', C.c_double), ('adapt_window', C.c_int32),
                 ('update_window', C.c_int32), ('doubling', C.c_int32), ('seed', C.c_uint64),
-                ('n_threads', C.c_int32)]
+                ('n_threads', C.c_int32), ('dense_metric', C.c_int32)]
 
 
 class _Out(C.Structure):
@@ -188,15 +188,17 @@ class OracleDensity:
         c = _Cfg()
         dflt = dict(n_iter=1500, n_warmup=500, max_treedepth=10, n_int_step=32, max_change=1000.,
                     adapt_step_size=1, target_accept=0.8, gamma=0.05, k=0.75, t0=10., adapt_metric=1,
-                    initial_weight=10., adapt_window=60, update_window=1, doubling=1, seed=0, n_threads=0)
+                    initial_weight=10., adapt_window=60, update_window=1, doubling=1, seed=0, n_threads=0,
+                    dense_metric=0)
         dflt.update(cfg)
         for k, v in dflt.items():
             setattr(c, k, v)
         step0 = _f64(np.broadcast_to(step0, (nc,)))
-        var0 = _f64(np.broadcast_to(var0, (nc, n)))
+        vshape = (nc, n, n) if c.dense_metric else (nc, n)      # dense: covariance matrices (metrics.py:94-132)
+        var0 = _f64(np.broadcast_to(var0, vshape))
         mean0 = x0.copy() if mean0 is None else _f64(np.broadcast_to(mean0, (nc, n)))
         ni = c.n_iter
-        res = dict(samples=np.zeros((nc, ni, n)), final_step=np.zeros((nc, 4)), final_var=np.zeros((nc, n)),
+        res = dict(samples=np.zeros((nc, ni, n)), final_step=np.zeros((nc, 4)), final_var=np.zeros(vshape),
                    n_draws=np.zeros(nc, np.int64), status=np.zeros(nc, np.int32))
         for k in ('logp', 'energy', 'mean_tree_accept', 'step_size', 'step_size_bar', 'energy_change',
                   'max_energy_change'):

@@ -14,6 +14,7 @@ numdifftools) and records inputs + outputs of the hot path:
     density.npz       Density.logp_and_grad(x, original_space=False) with decay + transform + module rescale
     fit.npz           PolyModel.fit (+ _set_bound) results
     sampler.npz       NUTS / HMC chains driven by a replayed random stream (include/bfb_rng.h draws)
+    sampler_dense.npz the same with the dense mass matrix (metric='full' or a covariance; QuadMetricFull / FullAdapt)
 
 The random stream: the reference's per-chain numpy Generator is replaced (after _init_chain) by a
 duck-typed object that serves draw t of the Philox stream -- normal(size=k) consumes k draws through
@@ -71,6 +72,7 @@ def import_reference():
 bf = import_reference()
 from bayesfast.modules.poly import PolyModel, PolyConfig  # noqa: E402
 from bayesfast.samplers import NUTS, HMC, NTrace, HTrace  # noqa: E402
+from bayesfast.samplers.hmc_utils.metrics import QuadMetricFull  # noqa: E402
 from oracle import bf_oracle  # noqa: E402  (only for the Philox draws)
 import _golden_io as gio  # noqa: E402
 
@@ -329,7 +331,7 @@ def run_reference_chains(den, sampler, trace_kw, x0, seed, n_draw_cap):
         t._random_generator = rep
         if i == 0:
             step0 = float(np.exp(t.step_size._log_step))
-            var0 = np.array(t.metric._var)
+            var0 = np.array(t.metric._cov if hasattr(t.metric, '_cov') else t.metric._var)
         with warnings.catch_warnings():
             warnings.simplefilter('ignore')
             cls(logp_and_grad=lambda x: den.logp_and_grad(x, original_space=False), sample_trace=t).run(verbose=False)
@@ -338,7 +340,7 @@ def run_reference_chains(den, sampler, trace_kw, x0, seed, n_draw_cap):
             res[k].append(np.array(getattr(t.stats, '_' + k), dtype=float))
         ss = t.step_size
         res['final_step'].append([ss._log_step, ss._log_bar, ss._hbar, ss._count])
-        res['final_var'].append(np.array(t.metric._var))
+        res['final_var'].append(np.array(t.metric._cov if hasattr(t.metric, '_cov') else t.metric._var))
         res['n_draws'].append(rep.t)
         res['draws_u'].append(u), res['draws_z'].append(z)
     nmax = max(res['n_draws']) + 4
@@ -386,8 +388,32 @@ def make_sampler():
     gio.save('sampler.npz', dict(cases=cases))
 
 
+def make_sampler_dense():
+    """dense mass matrix (metric='full': QuadMetricFull / QuadMetricFullAdapt, metrics.py:94-132, 240-330)"""
+    rng = np.random.default_rng(78)
+    cases = []
+
+    def add(name, sampler, den, x0, seed, n_draw_cap=60000, **trace_kw):
+        r = run_reference_chains(den, sampler, trace_kw, x0, seed, n_draw_cap)
+        kw = {k: (int(v) if isinstance(v, bool) else v) for k, v in trace_kw.items() if k != 'metric'}
+        if isinstance(trace_kw['metric'], QuadMetricFull):       # a fixed covariance (a QuadMetric instance is used as is)
+            kw['adapt_metric'] = 0
+        cases.append(dict(name=name, sampler=sampler, spec=density_spec(den), x0=x0, seed=seed, trace_kw=kw, result=r))
+        print(name, 'mean depth', np.mean(r['tree_depth']) if sampler == 'NUTS' else '-',
+              'n_div', int(np.sum(r['diverging'])), 'draws', r['n_draws'])
+
+    den, cov, xf = make_density(6, 'cubic-2', rng, transform=True, decay=True)
+    x0 = np.array([den.from_original(np.clip(x, -11., 11.)) for x in xf[:3]])
+    add('nuts_c2_n6_full_adapt', 'NUTS', den, x0, 1101, n_iter=60, n_warmup=30, metric='full')
+    add('hmc_c2_n6_full_adapt', 'HMC', den, x0[:2], 1202, n_iter=30, n_warmup=15, n_int_step=8, metric='full')
+    den, cov, xf = make_density(16, 'cubic-2', rng)
+    add('nuts_c2_n16_full_fixed', 'NUTS', den, xf[:2].copy(), 1303, n_iter=30, n_warmup=15, metric=QuadMetricFull(0.7 * cov + 0.3 * np.eye(16)))
+    add('nuts_c2_n16_full_adapt', 'NUTS', den, xf[:2].copy(), 1404, n_iter=40, n_warmup=30, metric='full', adapt_window=12)
+    gio.save('sampler_dense.npz', dict(cases=cases))
+
+
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['poly_kat', 'poly_eval', 'density', 'fit', 'sampler']
+    which = sys.argv[1:] or ['poly_kat', 'poly_eval', 'density', 'fit', 'sampler', 'sampler_dense']
     if 'poly_kat' in which:
         make_poly_kat()
     if 'poly_eval' in which:
@@ -398,6 +424,8 @@ if __name__ == '__main__':
         make_fit()
     if 'sampler' in which:
         make_sampler()
+    if 'sampler_dense' in which:
+        make_sampler_dense()
     for f in sorted(os.listdir(gio.GOLDEN_DIR)):
         if f.endswith('.npz'):
             print(f, os.path.getsize(os.path.join(gio.GOLDEN_DIR, f)))

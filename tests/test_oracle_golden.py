@@ -104,14 +104,17 @@ def _flt(a, b, tag):
     assert np.allclose(a, b, rtol=LATE_TOL, atol=LATE_TOL, equal_nan=True), tag
 
 
-def test_sampler_cases(oracle):
-    g = gio.load('sampler.npz')
+@pytest.mark.parametrize('golden', ['sampler.npz', 'sampler_dense.npz'])
+def test_sampler_cases(oracle, golden):
+    """sampler_dense.npz: the dense mass matrix (metrics.py:94-132, 240-330); var0 / final_var are covariances"""
+    g = gio.load(golden)
     for c in g['cases']:
         r = c['result']
         od = oracle.OracleDensity(c['spec'])
         cfg = {k: (int(v) if float(v) == int(v) and k not in ('max_change', 'step_size') else float(v))
                for k, v in c['trace_kw'].items()}
         cfg.pop('step_size', None)
+        cfg['dense_metric'] = int(np.ndim(r['var0']) == 2)
         out = od.run(c['sampler'], cfg, c['x0'], float(r['step0']), r['var0'], draws_u=r['draws_u'],
                      draws_z=r['draws_z'])
         assert np.all(out['status'] == 0), c['name']
