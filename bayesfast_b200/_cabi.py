@@ -78,6 +78,8 @@ def lib():
             L.bfb_logp_and_grad_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int]
             L.bfb_fit_begin.argtypes = [C.c_void_p, C.c_void_p]
             L.bfb_sampler_init.argtypes = [C.c_void_p, C.POINTER(SamplerCfg), C.c_int64, _dp, _dp, _dp, _dp]
+            L.bfb_sampler_init_dense.argtypes = [C.c_void_p, C.POINTER(SamplerCfg), C.c_int64, _dp, _dp, _dp, _dp]
+            L.bfb_sampler_get_cov.argtypes = [C.c_void_p, _dp, _ip]
             L.bfb_sampler_reset.argtypes = [C.c_void_p]
             L.bfb_sampler_run.argtypes = [C.c_void_p, C.c_int, C.c_int32, C.POINTER(RunOut), C.c_int, _lp]
             L.bfb_sampler_get_state.argtypes = [C.c_void_p, _dp, _dp, _lp, _ip, _dp]
@@ -234,7 +236,7 @@ class Handle:
         check(self._L.bfb_logp_and_grad_batch(self._h, x_ptr, int(C_), lp_ptr, g_ptr, BFB_DEVICE))
 
     # ------------------------------------------------------------------ sampler
-    def sampler_init(self, cfg, x0, step0, var0, mean0):
+    def sampler_init(self, cfg, x0, step0, var0, mean0, dense=False):
         n = self.n
         x0 = f64(x0).reshape(-1, n)
         nc = x0.shape[0]
@@ -242,9 +244,15 @@ class Handle:
         for k, v in cfg.items():
             setattr(c, k, v)
         step0 = f64(np.broadcast_to(step0, (nc,)))
-        var0 = f64(np.broadcast_to(var0, (nc, n)))
         mean0 = f64(np.broadcast_to(mean0, (nc, n)))
-        check(self._L.bfb_sampler_init(self._h, C.byref(c), nc, _d(x0), _d(step0), _d(var0), _d(mean0)))
+        # dense: var0 is a covariance (n, n) / (C, n, n) -- dense mass matrix (metrics.py:94-132, 240-330)
+        self.dense = bool(dense)
+        if self.dense:
+            cov0 = f64(np.broadcast_to(var0, (nc, n, n)))
+            check(self._L.bfb_sampler_init_dense(self._h, C.byref(c), nc, _d(x0), _d(step0), _d(cov0), _d(mean0)))
+        else:
+            var0 = f64(np.broadcast_to(var0, (nc, n)))
+            check(self._L.bfb_sampler_init(self._h, C.byref(c), nc, _d(x0), _d(step0), _d(var0), _d(mean0)))
         self.n_chain = nc
 
     def sampler_run(self, sampler, n_iter, out_ptrs=None, fields=None):
@@ -284,7 +292,13 @@ class Handle:
         nd, stt = np.empty(nc, np.int64), np.empty(nc, np.int32)
         check(self._L.bfb_sampler_get_state(self._h, _d(fs), _d(fv), nd.ctypes.data_as(_lp), stt.ctypes.data_as(_ip),
                                             _d(q)))
-        return dict(final_step=fs, final_var=fv, n_draws=nd, status=stt, q=q)
+        res = dict(final_step=fs, final_var=fv, n_draws=nd, status=stt, q=q)
+        if getattr(self, 'dense', False):
+            cov, ce = np.empty((nc, n, n)), np.empty(nc, np.int32)
+            check(self._L.bfb_sampler_get_cov(self._h, _d(cov), ce.ctypes.data_as(_ip)))
+            res['final_var'] = cov
+            res['chol_error'] = ce
+        return res
 
     def last_kernel_ms(self):
         ms = C.c_float(0)

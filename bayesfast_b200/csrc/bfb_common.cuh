@@ -91,6 +91,9 @@ struct ChainState {
     int64_t *iter;                                   // [C] iterations done
     int32_t *status;                                 // [C]
     unsigned long long *tree_total;                  // [4]: leapfrogs in trees; debug counters of the multi-chain kernels
+    // dense mass matrix (bfb_sampler_init_dense; generic kernel only): [C][n][np], transposed XT[k][j] = X[j][k]
+    double *covT, *cholT, *cholW, *fgcT, *bgcT;      // covariance, its Cholesky factor (+ work copy), Welford fore/background
+    int32_t *chol_error;                             // [C]
 };
 
 struct FitState;
@@ -115,6 +118,8 @@ struct bfb_context {
     DevModel dm;
     // sampler
     bool has_chains;
+    bool dense_metric;         // chains were set up by bfb_sampler_init_dense
+    std::vector<void *> dense_allocs;
     bfb_sampler_cfg scfg;
     ChainState cs;
     std::vector<void *> chain_allocs;

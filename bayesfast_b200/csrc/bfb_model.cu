@@ -58,6 +58,7 @@ extern "C" int bfb_create(int device, bfb_handle *out)
     h->launches = 0;
     h->has_model = false;
     h->has_chains = false;
+    h->dense_metric = false;
     h->fit = nullptr;
     h->gstack = nullptr;
     h->gstack_len = 0;
@@ -88,6 +89,7 @@ extern "C" int bfb_destroy(bfb_handle h)
     cudaStreamSynchronize(h->stream);
     bfb_free_list(h->model_allocs);
     bfb_free_list(h->chain_allocs);
+    bfb_free_list(h->dense_allocs);
     bfb_fit_free(h);
     if (h->gstack) cudaFree(h->gstack);
     if (h->queue) cudaFree(h->queue);

@@ -26,30 +26,138 @@ struct RunOutDev {
     int32_t n_iter;
 };
 
-__host__ __device__ inline size_t warp_smem_doubles(int np, int L)
+// dense metric (QuadMetricFull, metrics.py:94-132): every stored momentum that can become a tree end also carries its
+// velocity cov . p (3 more fixed vectors, 2 more per stack level)
+__host__ __device__ inline size_t warp_smem_doubles(int np, int L, bool dense = false)
 {
-    size_t s = (size_t)(12 + 5 * L) * np + 3 * (size_t)L;
+    size_t s = (size_t)((dense ? 15 : 12) + (dense ? 7 : 5) * L) * np + 3 * (size_t)L;
     return (s + 1) & ~(size_t)1;
 }
 
+// v = cov . p with the covariance stored transposed and padded, covT[k * np + j] = cov[j][k] (lane j reads row k coalesced;
+// the Welford covariance of metrics.py:374-417 is not bitwise symmetric, so the reference's element order is kept).
+// scr: np doubles of per-warp scratch.
 template <int NPL>
-__device__ __forceinline__ void leapfrog(const DevModel &M, double eps, const double (&var)[NPL], double (&q)[NPL],
-                                         double (&p)[NPL], double (&g)[NPL], int lane, double *xsm, double *dsm,
-                                         double &logp, double &energy)
+__device__ __forceinline__ void dense_velocity(const double *__restrict__ covT, int n, int np, const double (&p)[NPL],
+                                               double (&v)[NPL], int lane, double *scr)
 {
-    // integration.py:68-95 (kick - drift - kick), metrics.py:88-91 (velocity_energy)
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < NPL; ++r) { scr[lane + 32 * r] = p[r]; v[r] = 0.; }
+    __syncwarp();
+#pragma unroll 4
+    for (int k = 0; k < n; ++k) {
+        const double pk = scr[k];
+#pragma unroll
+        for (int r = 0; r < NPL; ++r) v[r] = fma(covT[(size_t)k * np + lane + 32 * r], pk, v[r]);
+    }
+    __syncwarp();
+}
+
+template <int NPL>
+__device__ __forceinline__ double pdot(const double (&a)[NPL], const double (&b)[NPL])
+{
+    double part = 0.;
+#pragma unroll
+    for (int r = 0; r < NPL; ++r) part = fma(a[r], b[r], part);
+    return warp_sum(part);
+}
+
+// scipy.linalg.cholesky(cov, lower=True) (metrics.py:108, 282-287) of the lower triangle of cov, left-looking by columns with
+// the lanes over the rows: out[k * np + j] = L[j][k].  Returns false on a non-positive pivot (the reference then keeps its
+// old factor).  diag: 1 double of per-warp scratch.
+template <int NPL>
+__device__ __forceinline__ bool dense_cholesky(const double *__restrict__ covT, double *__restrict__ out, int n, int np, int lane,
+                                               double *diag)
+{
+    bool ok = true;
+    for (int k = 0; k < n; ++k) {
+        double s_[NPL];
+#pragma unroll
+        for (int r = 0; r < NPL; ++r) s_[r] = covT[(size_t)k * np + lane + 32 * r];
+#pragma unroll 4
+        for (int m = 0; m < k; ++m) {
+            const double lkm = out[(size_t)m * np + k];
+#pragma unroll
+            for (int r = 0; r < NPL; ++r) s_[r] = fma(-out[(size_t)m * np + lane + 32 * r], lkm, s_[r]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < NPL; ++r) if (lane + 32 * r == k) diag[0] = s_[r];
+        __syncwarp();
+        const double d2 = diag[0];
+        if (!(d2 > 0.)) { ok = false; break; }
+        const double d = sqrt(d2);
+#pragma unroll
+        for (int r = 0; r < NPL; ++r) {
+            const int j = lane + 32 * r;
+            out[(size_t)k * np + j] = (j == k) ? d : (j > k && j < n) ? s_[r] / d : 0.;
+        }
+        __syncwarp();
+    }
+    return ok;
+}
+
+// QuadMetricFull.random (metrics.py:123-127): solve_triangular(chol.T, z), back substitution; cholT[k * np + j] = L[j][k],
+// so row i of L^T is one coalesced load.  z / the result are lane-owned (dimension j = lane + 32 r).
+template <int NPL>
+__device__ __forceinline__ void dense_momentum(const double *__restrict__ cholT, int n, int np, const double (&z)[NPL],
+                                               double (&x)[NPL], int lane)
+{
+#pragma unroll
+    for (int r = 0; r < NPL; ++r) x[r] = 0.;
+    double row[NPL];
+#pragma unroll
+    for (int r = 0; r < NPL; ++r) row[r] = cholT[(size_t)(n - 1) * np + lane + 32 * r];
+    for (int i = n - 1; i >= 0; --i) {
+        double nxt[NPL];
+#pragma unroll
+        for (int r = 0; r < NPL; ++r) nxt[r] = (i > 0) ? cholT[(size_t)(i - 1) * np + lane + 32 * r] : 0.;
+        double part = 0., zi = 0., lii = 0.;
+#pragma unroll
+        for (int r = 0; r < NPL; ++r) {
+            const int j = lane + 32 * r;
+            if (j > i) part = fma(row[r], x[r], part);      // x_j of the rows already solved; zeros elsewhere
+            if (j == i) { zi = z[r]; lii = row[r]; }
+        }
+        const double sum = warp_sum(part);
+        const int src = i & 31;
+        zi = __shfl_sync(BFB_FULL, zi, src); lii = __shfl_sync(BFB_FULL, lii, src);
+        const double xi = (zi - sum) / lii;
+#pragma unroll
+        for (int r = 0; r < NPL; ++r) { if (lane + 32 * r == i) x[r] = xi; row[r] = nxt[r]; }
+    }
+}
+
+template <int NPL, bool DENSE>
+__device__ __forceinline__ void leapfrog(const DevModel &M, double eps, const double (&var)[NPL], const double *covT,
+                                         double (&q)[NPL], double (&p)[NPL], double (&g)[NPL], double (&v)[NPL], int lane,
+                                         double *xsm, double *dsm, double &logp, double &energy)
+{
+    // integration.py:68-95 (kick - drift - kick), metrics.py:88-91 / 129-132 (velocity_energy); v = velocity of the new state
+    // (dense metric only)
     const double dt = 0.5 * eps;
 #pragma unroll
-    for (int r = 0; r < NPL; ++r) {
-        p[r] = fma(dt, g[r], p[r]);
-        q[r] = fma(eps, var[r] * p[r], q[r]);
+    for (int r = 0; r < NPL; ++r) p[r] = fma(dt, g[r], p[r]);
+    if (DENSE) {
+        dense_velocity<NPL>(covT, M.n, M.np, p, v, lane, dsm);
+#pragma unroll
+        for (int r = 0; r < NPL; ++r) q[r] = fma(eps, v[r], q[r]);
+    } else {
+#pragma unroll
+        for (int r = 0; r < NPL; ++r) q[r] = fma(eps, var[r] * p[r], q[r]);
     }
     density_eval<NPL>(M, q, lane, xsm, dsm, logp, g);
     double part = 0.;
 #pragma unroll
-    for (int r = 0; r < NPL; ++r) {
-        p[r] = fma(dt, g[r], p[r]);
-        part = fma(p[r], var[r] * p[r], part);
+    for (int r = 0; r < NPL; ++r) p[r] = fma(dt, g[r], p[r]);
+    if (DENSE) {
+        dense_velocity<NPL>(covT, M.n, M.np, p, v, lane, dsm);
+#pragma unroll
+        for (int r = 0; r < NPL; ++r) part = fma(p[r], v[r], part);
+    } else {
+#pragma unroll
+        for (int r = 0; r < NPL; ++r) part = fma(p[r], var[r] * p[r], part);
     }
     energy = 0.5 * warp_sum(part) - logp;
 }
@@ -68,7 +176,10 @@ __device__ __forceinline__ double vdot(const double (&a)[NPL], const double (&va
 #define VST(off, src)                                                     \
     _Pragma("unroll") for (int r_ = 0; r_ < NPL; ++r_) wsm[(off) + lane + 32 * r_] = src[r_]
 
-template <int NPL, int SAMPLER>
+// U-turn products p_sum . velocity(end): the velocity is var * p (diagonal metric, recomputed) or the stored cov . p
+#define UDOT(a, bp, bv) (DENSE ? pdot<NPL>(a, bv) : vdot<NPL>(a, var, bp))
+
+template <int NPL, int SAMPLER, bool DENSE>
 __global__ void __launch_bounds__(256) sampler_kernel(DevModel M, bfb_sampler_cfg cfg, ChainState st, RunOutDev out, int L)
 {
     extern __shared__ double smem[];
@@ -76,18 +187,25 @@ __global__ void __launch_bounds__(256) sampler_kernel(DevModel M, bfb_sampler_cf
     const int64_t c = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
     if (c >= st.C) return;
     const int n = M.n, np = M.np;
-    double *wsm = smem + (size_t)wib * warp_smem_doubles(np, L);
+    double *wsm = smem + (size_t)wib * warp_smem_doubles(np, L, DENSE);
     double *xsm = wsm, *dsm = wsm + np;
-    const int oTL = 2 * np, oTR = 5 * np, oPS = 8 * np, oPQ = 9 * np, oPG = 10 * np, oPB = 11 * np, oST = 12 * np;
-    double *ssc = wsm + (size_t)(12 + 5 * L) * np;   // [3][L] scalars of the stack: log_size, energy, logp
+    const int oTL = 2 * np, oTR = 5 * np, oPS = 8 * np, oPQ = 9 * np, oPG = 10 * np, oPB = 11 * np;
+    const int oTLv = 12 * np, oTRv = 13 * np, oPBv = 14 * np;            // dense metric: velocities of the tree ends
+    const int oST = (DENSE ? 15 : 12) * np, SV = DENSE ? 7 : 5;          // stack entry: pl, pr, ps, q', g' (, vl, vr)
+    double *ssc = wsm + (size_t)((DENSE ? 15 : 12) + SV * L) * np;   // [3][L] scalars of the stack: log_size, energy, logp
     if (st.status[c] != 0) return;
+    // dense metric state of this chain (transposed, padded: XT[k * np + j] = X[j][k]); the Welford covariances and the
+    // Cholesky factor stay in global memory (L2): they are touched once per warm-up iteration / momentum draw
+    const size_t mb = (size_t)c * n * np;
+    double *covT = DENSE ? st.covT + mb : nullptr, *cholT = DENSE ? st.cholT + mb : nullptr, *cholW = DENSE ? st.cholW + mb : nullptr;
+    double *fgcT = DENSE ? st.fgcT + mb : nullptr, *bgcT = DENSE ? st.bgcT + mb : nullptr;
 
     const uint64_t seed = cfg.seed, chain = (uint64_t)(cfg.chain0 + c);
     int64_t t = st.t_draw[c];
     int64_t it0 = st.iter[c];
     const size_t vb = (size_t)c * np;
 
-    double q[NPL], g[NPL], p[NPL], var[NPL], inv_std[NPL];
+    double q[NPL], g[NPL], p[NPL], v[NPL], var[NPL], inv_std[NPL];
     double fgm[NPL], fgr[NPL], bgm[NPL], bgr[NPL];
 #pragma unroll
     for (int r = 0; r < NPL; ++r) {
@@ -96,7 +214,7 @@ __global__ void __launch_bounds__(256) sampler_kernel(DevModel M, bfb_sampler_cf
         inv_std[r] = 1. / sqrt(var[r]);
         fgm[r] = st.fg_mean[vb + j]; fgr[r] = st.fg_raw[vb + j];
         bgm[r] = st.bg_mean[vb + j]; bgr[r] = st.bg_raw[vb + j];
-        p[r] = 0.;
+        p[r] = 0.; v[r] = 0.;
     }
     double logp_q = st.logp[c];
     double fg_n = st.fg_n[c], bg_n = st.bg_n[c];
@@ -110,14 +228,22 @@ __global__ void __launch_bounds__(256) sampler_kernel(DevModel M, bfb_sampler_cf
     for (int it = 0; it < out.n_iter; ++it) {
         const bool warmup = (it0 + it) < cfg.n_warmup;
         // momentum: metrics.py:83-86
-        double p0[NPL];
+        double p0[NPL], v0[NPL];
 #pragma unroll
         for (int r = 0; r < NPL; ++r) {
             const int j = lane + 32 * r;
-            p0[r] = (j < n) ? inv_std[r] * bfb_draw_normal(seed, chain, (uint64_t)(t + j)) : 0.;
+            p0[r] = (j < n) ? (DENSE ? 1. : inv_std[r]) * bfb_draw_normal(seed, chain, (uint64_t)(t + j)) : 0.;
+            v0[r] = 0.;
         }
         t += n;
-        const double E0 = 0.5 * vdot<NPL>(p0, var, p0) - logp_q;    // integration.py:28-34
+        if (DENSE) {                                                  // metrics.py:123-127, 113-121
+            double z[NPL];
+#pragma unroll
+            for (int r = 0; r < NPL; ++r) z[r] = p0[r];
+            dense_momentum<NPL>(cholT, n, np, z, p0, lane);
+            dense_velocity<NPL>(covT, n, np, p0, v0, lane, dsm);
+        }
+        const double E0 = 0.5 * UDOT(p0, p0, v0) - logp_q;           // integration.py:28-34
         if (!isfinite(E0)) { status = 2; break; }                     // base_hmc.py:72-76
         const double eps = warmup ? exp(log_step) : exp(log_bar);     // step_size.py:25-29
 
@@ -129,6 +255,7 @@ __global__ void __launch_bounds__(256) sampler_kernel(DevModel M, bfb_sampler_cf
             VST(oTL, q); VST(oTL + np, p0); VST(oTL + 2 * np, g);
             VST(oTR, q); VST(oTR + np, p0); VST(oTR + 2 * np, g);
             VST(oPS, p0); VST(oPQ, q); VST(oPG, g);
+            if (DENSE) { VST(oTLv, v0); VST(oTRv, v0); }
             double prop_E = E0, prop_lp = logp_q, tree_ls = 0., acc_sum = 0., maxdE = 0.;
             int depth = 0, n_prop = 0;
             bool turn = false, nan_flag = false;
@@ -137,16 +264,20 @@ __global__ void __launch_bounds__(256) sampler_kernel(DevModel M, bfb_sampler_cf
                 const double ud = bfb_draw_uniform(seed, chain, (uint64_t)t); t++;
                 const int dir = (log(ud) < -0.6931471805599453) ? 1 : -1;
                 const int oEnd = dir > 0 ? oTR : oTL;
+                const int oEndv = dir > 0 ? oTRv : oTLv;
                 VLD(q, oEnd); VLD(p, oEnd + np); VLD(g, oEnd + 2 * np);
                 VST(oPB, p);
+                if (DENSE) { VLD(v, oEndv); VST(oPBv, v); }
                 const double step = dir > 0 ? eps : -eps;
                 const int nleaf = 1 << depth;
-                double Rpl[NPL], Rps[NPL], Rqp[NPL], Rgp[NPL];
+                double Rpl[NPL], Rps[NPL], Rqp[NPL], Rgp[NPL], Rvl[NPL];
+#pragma unroll
+                for (int r = 0; r < NPL; ++r) Rvl[r] = 0.;
                 double Rls = 0., REp = 0., Rlpp = 0.;
                 // ---- _build_subtree(depth), nuts.py:134-178, iteratively ----
                 for (int i = 0; i < nleaf; ++i) {
                     double lp, E;
-                    leapfrog<NPL>(M, step, var, q, p, g, lane, xsm, dsm, lp, E);
+                    leapfrog<NPL, DENSE>(M, step, var, covT, q, p, g, v, lane, xsm, dsm, lp, E);
                     // _single_step, nuts.py:105-132
                     double dE = E - E0;
                     if (isnan(dE)) dE = INFINITY;
@@ -155,22 +286,27 @@ __global__ void __launch_bounds__(256) sampler_kernel(DevModel M, bfb_sampler_cf
                     if (!(fabs(dE) < cfg.max_change)) { diverging = 1; break; }
                     { const double e = exp(-dE); acc_sum += e < 1. ? e : 1.; }
 #pragma unroll
-                    for (int r = 0; r < NPL; ++r) { Rpl[r] = p[r]; Rps[r] = p[r]; Rqp[r] = q[r]; Rgp[r] = g[r]; }
+                    for (int r = 0; r < NPL; ++r) { Rpl[r] = p[r]; Rps[r] = p[r]; Rqp[r] = q[r]; Rgp[r] = g[r]; if (DENSE) Rvl[r] = v[r]; }
                     Rls = -dE; REp = E; Rlpp = lp;
                     int lvl = 0;
                     while ((i >> lvl) & 1) {
-                        const int oS = oST + lvl * 5 * np;
-                        double T1pl[NPL], T1pr[NPL], T1ps[NPL], ps[NPL];
+                        const int oS = oST + lvl * SV * np;
+                        double T1pl[NPL], T1pr[NPL], T1ps[NPL], ps[NPL], T1vl[NPL], T1vr[NPL];
                         VLD(T1pl, oS); VLD(T1pr, oS + np); VLD(T1ps, oS + 2 * np);
+                        if (DENSE) { VLD(T1vl, oS + 5 * np); VLD(T1vr, oS + 6 * np); }
+                        else {
+#pragma unroll
+                            for (int r = 0; r < NPL; ++r) T1vl[r] = T1vr[r] = 0.;
+                        }
 #pragma unroll
                         for (int r = 0; r < NPL; ++r) ps[r] = T1ps[r] + Rps[r];
-                        bool turning = (vdot<NPL>(ps, var, T1pl) <= 0.) | (vdot<NPL>(ps, var, p) <= 0.);
+                        bool turning = (UDOT(ps, T1pl, T1vl) <= 0.) | (UDOT(ps, p, v) <= 0.);
                         if (lvl >= 1) {
                             double ps1[NPL], ps2[NPL];
 #pragma unroll
                             for (int r = 0; r < NPL; ++r) { ps1[r] = T1ps[r] + Rpl[r]; ps2[r] = T1pr[r] + Rps[r]; }
-                            turning |= (vdot<NPL>(ps1, var, T1pl) <= 0.) | (vdot<NPL>(ps1, var, Rpl) <= 0.);
-                            turning |= (vdot<NPL>(ps2, var, T1pr) <= 0.) | (vdot<NPL>(ps2, var, p) <= 0.);
+                            turning |= (UDOT(ps1, T1pl, T1vl) <= 0.) | (UDOT(ps1, Rpl, Rvl) <= 0.);
+                            turning |= (UDOT(ps2, T1pr, T1vr) <= 0.) | (UDOT(ps2, p, v) <= 0.);
                         }
                         const double T1ls = ssc[lvl];
                         const double ls = np_logaddexp(T1ls, Rls);
@@ -182,21 +318,23 @@ __global__ void __launch_bounds__(256) sampler_kernel(DevModel M, bfb_sampler_cf
                             REp = ssc[L + lvl]; Rlpp = ssc[2 * L + lvl];
                         }
 #pragma unroll
-                        for (int r = 0; r < NPL; ++r) { Rpl[r] = T1pl[r]; Rps[r] = ps[r]; }
+                        for (int r = 0; r < NPL; ++r) { Rpl[r] = T1pl[r]; Rps[r] = ps[r]; if (DENSE) Rvl[r] = T1vl[r]; }
                         Rls = ls;
                         if (turning) { turn = true; break; }
                         lvl++;
                     }
                     if (turn) break;
                     if (i + 1 < nleaf) {
-                        const int oS = oST + lvl * 5 * np;
+                        const int oS = oST + lvl * SV * np;
                         VST(oS, Rpl); VST(oS + np, p); VST(oS + 2 * np, Rps); VST(oS + 3 * np, Rqp); VST(oS + 4 * np, Rgp);
+                        if (DENSE) { VST(oS + 5 * np, Rvl); VST(oS + 6 * np, v); }
                         // every lane writes the same scalars (each lane later reads back its own write: no sync needed)
                         ssc[lvl] = Rls; ssc[L + lvl] = REp; ssc[2 * L + lvl] = Rlpp;
                     }
                 }
                 // Tree.extend, nuts.py:45-103
                 VST(oEnd, q); VST(oEnd + np, p); VST(oEnd + 2 * np, g);
+                if (DENSE) VST(oEndv, v);
                 depth += 1;
                 if (diverging || turn) break;
                 {
@@ -206,24 +344,29 @@ __global__ void __launch_bounds__(256) sampler_kernel(DevModel M, bfb_sampler_cf
                     if (log(ue) < lb) { VST(oPQ, Rqp); VST(oPG, Rgp); prop_E = REp; prop_lp = Rlpp; }
                 }
                 tree_ls = np_logaddexp(tree_ls, Rls);
-                double PS[NPL], PB[NPL], TLp[NPL], TRp[NPL], ps1[NPL], ps2[NPL];
+                double PS[NPL], PB[NPL], TLp[NPL], TRp[NPL], ps1[NPL], ps2[NPL], PBv[NPL], TLv[NPL], TRv[NPL];
                 VLD(PS, oPS); VLD(PB, oPB); VLD(TLp, oTL + np); VLD(TRp, oTR + np);
+                if (DENSE) { VLD(PBv, oPBv); VLD(TLv, oTLv); VLD(TRv, oTRv); }
+                else {
+#pragma unroll
+                    for (int r = 0; r < NPL; ++r) PBv[r] = TLv[r] = TRv[r] = 0.;
+                }
 #pragma unroll
                 for (int r = 0; r < NPL; ++r) PS[r] += Rps[r];
                 VST(oPS, PS);
-                bool turning = (vdot<NPL>(PS, var, TLp) <= 0.) | (vdot<NPL>(PS, var, TRp) <= 0.);
+                bool turning = (UDOT(PS, TLp, TLv) <= 0.) | (UDOT(PS, TRp, TRv) <= 0.);
                 // NB the reference updates self.p_sum in place before forming p_sum1 / p_sum2 (nuts.py:86-98),
                 // so the "old tree" p_sum that enters them is already the total.
                 if (dir > 0) {
 #pragma unroll
                     for (int r = 0; r < NPL; ++r) { ps1[r] = PS[r] + Rpl[r]; ps2[r] = PB[r] + Rps[r]; }
-                    turning |= (vdot<NPL>(ps1, var, TLp) <= 0.) | (vdot<NPL>(ps1, var, Rpl) <= 0.);
-                    turning |= (vdot<NPL>(ps2, var, PB) <= 0.) | (vdot<NPL>(ps2, var, p) <= 0.);
+                    turning |= (UDOT(ps1, TLp, TLv) <= 0.) | (UDOT(ps1, Rpl, Rvl) <= 0.);
+                    turning |= (UDOT(ps2, PB, PBv) <= 0.) | (UDOT(ps2, p, v) <= 0.);
                 } else {
 #pragma unroll
                     for (int r = 0; r < NPL; ++r) { ps1[r] = Rps[r] + PB[r]; ps2[r] = Rpl[r] + PS[r]; }
-                    turning |= (vdot<NPL>(ps1, var, p) <= 0.) | (vdot<NPL>(ps1, var, PB) <= 0.);
-                    turning |= (vdot<NPL>(ps2, var, Rpl) <= 0.) | (vdot<NPL>(ps2, var, TRp) <= 0.);
+                    turning |= (UDOT(ps1, p, v) <= 0.) | (UDOT(ps1, PB, PBv) <= 0.);
+                    turning |= (UDOT(ps2, Rpl, Rvl) <= 0.) | (UDOT(ps2, TRp, TRv) <= 0.);
                 }
                 if (turning) { turn = true; break; }
             }
@@ -240,7 +383,7 @@ __global__ void __launch_bounds__(256) sampler_kernel(DevModel M, bfb_sampler_cf
 #pragma unroll
             for (int r = 0; r < NPL; ++r) { qs[r] = q[r]; gs[r] = g[r]; p[r] = p0[r]; }
             double lp = logp_q, E = E0;
-            for (int s = 0; s < cfg.n_int_step; ++s) leapfrog<NPL>(M, eps, var, q, p, g, lane, xsm, dsm, lp, E);
+            for (int s = 0; s < cfg.n_int_step; ++s) leapfrog<NPL, DENSE>(M, eps, var, covT, q, p, g, v, lane, xsm, dsm, lp, E);
             double dE;
             if (isfinite(E)) { dE = E0 - E; diverging = fabs(dE) > cfg.max_change; }
             else { dE = -INFINITY; diverging = 1; }
@@ -270,7 +413,51 @@ __global__ void __launch_bounds__(256) sampler_kernel(DevModel M, bfb_sampler_cf
             count += 1;
         }
         // QuadMetricDiagAdapt.update, metrics.py:186-211 with _WeightedVariance.add_sample :351-357
-        if (warmup && cfg.adapt_metric) {
+        if (DENSE && warmup && cfg.adapt_metric) {
+            // QuadMetricFullAdapt.update, metrics.py:289-313 with _WeightedCovariance.add_sample :398-404
+            // (raw_cov[i][j] += new_diff[i] * old_diff[j]; stored transposed, lane j owns new_diff[j])
+            const int64_t delta = n_samples - previous_update;
+            const bool upd = ((delta + 1) % cfg.update_window == 0), swap = delta >= adapt_window;
+            fg_n += 1.; bg_n += 1.;
+            double fn[NPL], bn[NPL];
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < NPL; ++r) {
+                const double fo = q[r] - fgm[r], bo = q[r] - bgm[r];
+                fgm[r] += fo / fg_n; bgm[r] += bo / bg_n;
+                fn[r] = q[r] - fgm[r]; bn[r] = q[r] - bgm[r];
+                xsm[lane + 32 * r] = fo; dsm[lane + 32 * r] = bo;
+            }
+            __syncwarp();
+            for (int k = 0; k < n; ++k) {
+                const double fok = xsm[k], bok = dsm[k];
+#pragma unroll
+                for (int r = 0; r < NPL; ++r) {
+                    const size_t idx = (size_t)k * np + lane + 32 * r;
+                    const double f = fgcT[idx] + 1. * fn[r] * fok, b = bgcT[idx] + 1. * bn[r] * bok;
+                    if (upd) covT[idx] = f / fg_n;
+                    // end of the adaptation window: foreground <- background, fresh background (identity x weight 10)
+                    fgcT[idx] = swap ? b : f;
+                    bgcT[idx] = swap ? ((lane + 32 * r == k) ? 10. : 0.) : b;
+                }
+            }
+            __syncwarp();
+            if (upd) {
+                if (dense_cholesky<NPL>(covT, cholW, n, np, lane, ssc)) {
+                    for (int i = lane; i < n * np; i += 32) cholT[i] = cholW[i];
+                } else if (lane == 0) st.chol_error[c] = 1;      // metrics.py:284-287: the old factor stays in use
+                __syncwarp();
+            }
+            if (swap) {
+#pragma unroll
+                for (int r = 0; r < NPL; ++r) { fgm[r] = bgm[r]; bgm[r] = 0.; }
+                fg_n = bg_n; bg_n = 10.;
+                previous_update = n_samples;
+                if (cfg.doubling) adapt_window *= 2;
+            }
+            n_samples += 1;
+        }
+        if (!DENSE && warmup && cfg.adapt_metric) {
             const int64_t delta = n_samples - previous_update;
             fg_n += 1.; bg_n += 1.;
 #pragma unroll
@@ -401,12 +588,20 @@ extern "C" int bfb_sampler_reset(bfb_handle h)
     auto arrs = state_arrays(h->cs);
     for (size_t i = 0; i < arrs.size(); ++i)
         BFB_CUDA(cudaMemcpyAsync(arrs[i].first, h->chain_snapshot[i], arrs[i].second, cudaMemcpyDeviceToDevice, h->stream));
+    if (h->dense_metric) {
+        const ChainState &s = h->cs;
+        const size_t MB = (size_t)s.C * s.n * s.np * sizeof(double);
+        double *live[4] = {s.covT, s.cholT, s.fgcT, s.bgcT};
+        for (int i = 0; i < 4; ++i)
+            BFB_CUDA(cudaMemcpyAsync(live[i], h->dense_allocs[6 + i], MB, cudaMemcpyDeviceToDevice, h->stream));
+        BFB_CUDA(cudaMemsetAsync(s.chol_error, 0, sizeof(int32_t) * s.C, h->stream));
+    }
     h->iters_done = 0;
     return BFB_OK;
 }
 
-extern "C" int bfb_sampler_init(bfb_handle h, const bfb_sampler_cfg *cfg, int64_t C, const double *x0,
-                                const double *step0, const double *var0, const double *mean0)
+static int sampler_init_common(bfb_handle h, const bfb_sampler_cfg *cfg, int64_t C, const double *x0,
+                               const double *step0, const double *var0, const double *mean0)
 {
     BFB_REQUIRE(h && h->has_model, BFB_ERR_STATE, "bfb_sampler_init: no model set");
     BFB_REQUIRE(cfg && x0 && step0 && var0 && mean0 && C > 0, BFB_ERR_ARG, "bfb_sampler_init: bad arguments");
@@ -495,18 +690,114 @@ extern "C" int bfb_sampler_init(bfb_handle h, const bfb_sampler_cfg *cfg, int64_
     return BFB_OK;
 }
 
-template <int NPL, int SAMPLER>
+extern "C" int bfb_sampler_init(bfb_handle h, const bfb_sampler_cfg *cfg, int64_t C, const double *x0,
+                                const double *step0, const double *var0, const double *mean0)
+{
+    BFB_REQUIRE(h, BFB_ERR_STATE, "bfb_sampler_init: null handle");
+    bfb_free_list(h->dense_allocs);
+    h->dense_metric = false;
+    return sampler_init_common(h, cfg, C, x0, step0, var0, mean0);
+}
+
+// Dense mass matrix: QuadMetricFull / QuadMetricFullAdapt (hmc_utils/metrics.py:94-132, 240-330, 374-417).  cov0 [C,n,n].
+// The chains then run on the generic warp-per-chain kernel (sampler_kernel<.., DENSE = true>).
+extern "C" int bfb_sampler_init_dense(bfb_handle h, const bfb_sampler_cfg *cfg, int64_t C, const double *x0,
+                                      const double *step0, const double *cov0, const double *mean0)
+{
+    BFB_REQUIRE(h && h->has_model, BFB_ERR_STATE, "bfb_sampler_init_dense: no model set");
+    BFB_REQUIRE(cfg && x0 && step0 && cov0 && mean0 && C > 0, BFB_ERR_ARG, "bfb_sampler_init_dense: bad arguments");
+    const int n = h->n, np = h->np;
+    const size_t M1 = (size_t)n * np, MT = (size_t)C * M1;
+    // host-side factorisation of the initial covariances (scipy.linalg.cholesky(cov, lower=True), metrics.py:108 / 271)
+    std::vector<double> covT(MT, 0.), cholT(MT, 0.), fgT(MT, 0.), bgT(MT, 0.), L((size_t)n * n);
+    for (int64_t c = 0; c < C; ++c) {
+        const double *A = cov0 + (size_t)c * n * n;
+        std::fill(L.begin(), L.end(), 0.);
+        for (int j = 0; j < n; ++j)
+            for (int i = j; i < n; ++i) {
+                double s_ = A[(size_t)i * n + j];
+                for (int k = 0; k < j; ++k) s_ -= L[(size_t)i * n + k] * L[(size_t)j * n + k];
+                if (i == j) {
+                    BFB_REQUIRE(s_ > 0., BFB_ERR_ARG, "the input covariance is not positive definite.");
+                    L[(size_t)j * n + j] = sqrt(s_);
+                } else L[(size_t)i * n + j] = s_ / L[(size_t)j * n + j];
+            }
+        for (int k = 0; k < n; ++k)
+            for (int j = 0; j < n; ++j) {
+                const size_t d = (size_t)c * M1 + (size_t)k * np + j;
+                covT[d] = A[(size_t)j * n + k];
+                cholT[d] = L[(size_t)j * n + k];
+                fgT[d] = A[(size_t)j * n + k] * cfg->initial_weight;       // metrics.py:392
+                bgT[d] = (j == k) ? 10. : 0.;                               // _WeightedCovariance(self._n): eye * 10
+            }
+    }
+    bfb_free_list(h->dense_allocs);
+    h->dense_metric = false;
+    std::vector<double> ones((size_t)C * n, 1.);
+    int rc = sampler_init_common(h, cfg, C, x0, step0, ones.data(), mean0);
+    if (rc) return rc;
+    h->has_chains = false;
+    ChainState &s = h->cs;
+    // [0..4] covT cholT cholW fgcT bgcT, [5] chol_error, [6..9] snapshots of covT cholT fgcT bgcT (bfb_sampler_reset)
+    for (int i = 0; i < 10; ++i) {
+        void *p = nullptr;
+        const size_t bytes = (i == 5) ? sizeof(int32_t) * C : sizeof(double) * MT;
+        BFB_CUDA(cudaMalloc(&p, bytes));
+        h->dense_allocs.push_back(p);
+        BFB_CUDA(cudaMemsetAsync(p, 0, bytes, h->stream));
+    }
+    s.covT = (double *)h->dense_allocs[0]; s.cholT = (double *)h->dense_allocs[1]; s.cholW = (double *)h->dense_allocs[2];
+    s.fgcT = (double *)h->dense_allocs[3]; s.bgcT = (double *)h->dense_allocs[4]; s.chol_error = (int32_t *)h->dense_allocs[5];
+    const std::vector<double> *src[4] = {&covT, &cholT, &fgT, &bgT};
+    double *dst[4] = {s.covT, s.cholT, s.fgcT, s.bgcT};
+    for (int i = 0; i < 4; ++i) {
+        BFB_CUDA(cudaMemcpyAsync(dst[i], src[i]->data(), sizeof(double) * MT, cudaMemcpyHostToDevice, h->stream));
+        BFB_CUDA(cudaMemcpyAsync(h->dense_allocs[6 + i], dst[i], sizeof(double) * MT, cudaMemcpyDeviceToDevice, h->stream));
+    }
+    BFB_CUDA(cudaStreamSynchronize(h->stream));
+    h->dense_metric = true;
+    h->has_chains = true;
+    return BFB_OK;
+}
+
+// final covariances [C,n,n] of a dense-metric run (QuadMetricFullAdapt._cov) and, per chain, whether a Cholesky
+// factorisation failed during adaptation (metrics.py:284-287, 315-317)
+extern "C" int bfb_sampler_get_cov(bfb_handle h, double *cov, int32_t *chol_error)
+{
+    BFB_REQUIRE(h && h->has_chains && h->dense_metric, BFB_ERR_STATE, "bfb_sampler_get_cov: no dense-metric chains");
+    BFB_CUDA(cudaSetDevice(h->device));
+    BFB_CUDA(cudaStreamSynchronize(h->stream));
+    const ChainState &s = h->cs;
+    const int n = s.n, np = s.np;
+    if (cov) {
+        std::vector<double> t((size_t)s.C * n * np);
+        BFB_CUDA(cudaMemcpy(t.data(), s.covT, sizeof(double) * t.size(), cudaMemcpyDeviceToHost));
+        for (int64_t c = 0; c < s.C; ++c)
+            for (int j = 0; j < n; ++j)
+                for (int k = 0; k < n; ++k) cov[((size_t)c * n + j) * n + k] = t[((size_t)c * n + k) * np + j];
+    }
+    if (chol_error) BFB_CUDA(cudaMemcpy(chol_error, s.chol_error, sizeof(int32_t) * s.C, cudaMemcpyDeviceToHost));
+    return BFB_OK;
+}
+
+template <int NPL, int SAMPLER, bool DENSE>
 static int launch_sampler(bfb_context *h, const RunOutDev &out, int wpb)
 {
     const int L = h->scfg.max_treedepth;
-    const size_t smem = sizeof(double) * wpb * warp_smem_doubles(h->np, L);
+    const size_t smem = sizeof(double) * wpb * warp_smem_doubles(h->np, L, DENSE);
     BFB_REQUIRE(smem <= 227 * 1024, BFB_ERR_ARG, "sampler needs %zu bytes of shared memory per block (> 227 KB)", smem);
-    BFB_CUDA(cudaFuncSetAttribute(sampler_kernel<NPL, SAMPLER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BFB_CUDA(cudaFuncSetAttribute(sampler_kernel<NPL, SAMPLER, DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int blocks = (int)((h->cs.C + wpb - 1) / wpb);
-    sampler_kernel<NPL, SAMPLER><<<blocks, 32 * wpb, smem, h->stream>>>(h->dm, h->scfg, h->cs, out, L);
+    sampler_kernel<NPL, SAMPLER, DENSE><<<blocks, 32 * wpb, smem, h->stream>>>(h->dm, h->scfg, h->cs, out, L);
     h->launches++;
     BFB_CUDA(cudaGetLastError());
     return BFB_OK;
+}
+
+template <int NPL, int SAMPLER>
+static int launch_sampler(bfb_context *h, const RunOutDev &out, int wpb)
+{
+    return h->dense_metric ? launch_sampler<NPL, SAMPLER, true>(h, out, wpb) : launch_sampler<NPL, SAMPLER, false>(h, out, wpb);
 }
 
 // launch the kernel(s) that advance every chain by n_iter iterations, outputs (device pointers) laid out [C, n_iter(, n)]
@@ -519,7 +810,8 @@ static int launch_run(bfb_context *h, int sampler, int n_iter, const bfb_run_out
     // NUTS kernel selection: tensor-core path, then the FMA multi-chain path, then the generic warp-per-chain kernel
     // (BFB200_SAMPLER = dmma | fast | generic pins one for tests and profiles)
     const char *sel_ = getenv("BFB200_SAMPLER");
-    if (sampler == BFB_NUTS && !getenv("BFB200_FORCE_GENERIC") && !(sel_ && !strcmp(sel_, "generic"))) {
+    // a dense mass matrix runs on the generic kernel only
+    if (sampler == BFB_NUTS && !h->dense_metric && !getenv("BFB200_FORCE_GENERIC") && !(sel_ && !strcmp(sel_, "generic"))) {
         fast_rc = bfb_launch_nuts_dmma(h, od.o, n_iter);
         if (fast_rc == 0) h->last_path = 2;
         if (fast_rc == 1) {
@@ -528,7 +820,7 @@ static int launch_run(bfb_context *h, int sampler, int n_iter, const bfb_run_out
             if (fast_rc == 0) h->last_path = 1;
         }
     }
-    if (sampler == BFB_HMC && !getenv("BFB200_FORCE_GENERIC") && !(sel_ && !strcmp(sel_, "generic"))) {
+    if (sampler == BFB_HMC && !h->dense_metric && !getenv("BFB200_FORCE_GENERIC") && !(sel_ && !strcmp(sel_, "generic"))) {
         fast_rc = bfb_launch_hmc_dmma(h, od.o, n_iter);
         if (fast_rc == 0) h->last_path = 2;
     }
@@ -540,7 +832,7 @@ static int launch_run(bfb_context *h, int sampler, int n_iter, const bfb_run_out
     const int npl = h->np / 32;
     int wpb = 1;
     {
-        const size_t per_warp = sizeof(double) * warp_smem_doubles(h->np, h->scfg.max_treedepth), cap = 227 * 1024;
+        const size_t per_warp = sizeof(double) * warp_smem_doubles(h->np, h->scfg.max_treedepth, h->dense_metric), cap = 227 * 1024;
         size_t best = 0;
         for (int w = 1; w <= 8; ++w) {                       // resident warps per SM = blocks that fit x warps per block
             const size_t resident = (cap / (w * per_warp + 1024)) * w;

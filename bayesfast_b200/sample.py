@@ -12,7 +12,7 @@ from . import _cabi
 from .density import Density
 from .random import get_generator, new_seed
 from .runtime import dist_info, shard_bounds
-from .sample_trace import NTrace, HTrace, TraceTuple, SampleTrace, DualAverageAdaptation, QuadMetricDiag
+from .sample_trace import NTrace, HTrace, TraceTuple, SampleTrace, DualAverageAdaptation, QuadMetricDiag, QuadMetricFull
 
 __all__ = ['sample']
 
@@ -104,18 +104,24 @@ def sample(density, sample_trace=None, sampler='NUTS', n_run=None, parallel_back
     else:
         step0 = np.full(Cl, (1. if trace._step_size is None else trace._step_size) / n**0.25)
     m = trace._metric
-    if isinstance(m, QuadMetricDiag):
-        var0 = np.broadcast_to(m._var, (Cl, n))
+    dense = False
+    if isinstance(m, QuadMetricFull):
+        m, dense = m._cov, True
+    elif isinstance(m, QuadMetricDiag):
+        m = m._var
     elif isinstance(m, str):
-        var0 = np.ones((Cl, n))
+        m, dense = (np.eye(n), True) if m == 'full' else (np.ones(n), False)       # sample_trace.py:428-431
     else:
-        if m.shape != (n,):
-            raise ValueError('metric should have shape ({},).'.format(n))
-        var0 = np.broadcast_to(m, (Cl, n))
+        dense = m.ndim == 2
+    if m.shape != ((n, n) if dense else (n,)):
+        raise ValueError('metric should have shape ({0},) or ({0}, {0}).'.format(n))
+    var0 = np.broadcast_to(m, (Cl, n, n) if dense else (Cl, n))
     mean0 = x0 if trace._initial_mean is None else np.broadcast_to(trace._initial_mean, (Cl, n))
 
     h = den._sync(False)
-    h.sampler_init(trace._cfg_dict(seed, lo), x0, step0, np.ascontiguousarray(var0), np.ascontiguousarray(mean0))
+    # a dense mass matrix (metric='full' / a covariance: QuadMetricFull(Adapt), metrics.py:94-132, 240-330) runs on the
+    # generic warp-per-chain kernel; the diagonal default takes the tensor-core path
+    h.sampler_init(trace._cfg_dict(seed, lo), x0, step0, np.ascontiguousarray(var0), np.ascontiguousarray(mean0), dense=dense)
     n_run = trace.n_iter if n_run is None else int(n_run)
     if n_run <= 0:
         raise ValueError('invalid value for n_run.')

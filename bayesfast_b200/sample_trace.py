@@ -12,7 +12,7 @@ from collections import OrderedDict, namedtuple
 import numpy as np
 
 __all__ = ['SampleTrace', 'NTrace', 'HTrace', 'TraceTuple', 'DualAverageAdaptation', 'QuadMetricDiag',
-           'QuadMetricDiagAdapt', 'NStats', 'HStats', 'NStepStats', 'HStepStats', '_get_step_size', '_get_metric']
+           'QuadMetricDiagAdapt', 'QuadMetricFull', 'QuadMetricFullAdapt', 'NStats', 'HStats', 'NStepStats', 'HStepStats', '_get_step_size', '_get_metric']
 
 hstats_items = ('logp', 'energy', 'n_int_step', 'accept_stat', 'accepted', 'step_size', 'step_size_bar', 'warmup',
                 'energy_change', 'diverging')
@@ -57,6 +57,29 @@ class QuadMetricDiag:
 
 class QuadMetricDiagAdapt(QuadMetricDiag):
     """metrics.py:135-237 (state only: the windowed Welford update runs on the device)"""
+
+
+class QuadMetricFull:
+    """metrics.py:94-132 (state only): dense mass matrix"""
+
+    def __init__(self, cov):
+        cov = np.atleast_2d(cov).astype(np.float64)
+        if cov.ndim != 2 or cov.shape[0] != cov.shape[1]:
+            raise ValueError('cov should be a 2-d array.')
+        if not np.all(np.linalg.eigvalsh(cov) > 0):
+            raise ValueError('the input covariance is not positive definite.')
+        self._cov = cov.copy()
+        self._chol = np.linalg.cholesky(cov)
+        self._n = len(cov)
+
+
+class QuadMetricFullAdapt(QuadMetricFull):
+    """metrics.py:240-330 (state only: the windowed Welford covariance and its Cholesky factor live on the device)"""
+    _chol_error = None
+
+    def raise_ok(self, vmap=None):
+        if self._chol_error is not None:
+            raise ValueError('{0}'.format(self._chol_error))
 
 
 class _Stats:
@@ -226,20 +249,18 @@ class _HTrace(SampleTrace):
         except Exception:
             raise ValueError('invalid value for k or t_0.')
         self._target_accept, self._gamma, self._k, self._t_0 = target_accept, gamma, k, t_0
-        if isinstance(metric, QuadMetricDiag):
+        # sample_trace.py:375-390, 424-455: 'diag' | 'full' | variances (n,) | covariance (n, n) | a QuadMetric
+        if isinstance(metric, (QuadMetricDiag, QuadMetricFull)):
             self._metric = metric
         elif isinstance(metric, str):
-            if metric == 'full':
-                raise NotImplementedError('metric="full" (dense mass matrix) is not available on the device yet; '
-                                          'use "diag" or a 1-d variance array.')
-            if metric != 'diag':
+            if metric not in ('diag', 'full'):
                 raise ValueError('invalid value for metric.')
             self._metric = metric
         else:
-            metric = np.asarray(metric, dtype=np.float64)
-            if metric.ndim == 2:
-                raise NotImplementedError('dense mass matrices are not available on the device yet.')
-            if metric.ndim != 1:
+            try:
+                metric = np.asarray(metric, dtype=np.float64)
+                assert metric.ndim == 1 or (metric.ndim == 2 and metric.shape[0] == metric.shape[1])
+            except Exception:
                 raise ValueError('invalid value for metric.')
             self._metric = metric
         self._adapt_metric = bool(adapt_metric)
@@ -418,8 +439,13 @@ class TraceTuple:
                                    t._adapt_step_size)
         da._log_step, da._log_bar, da._hbar, da._count = float(fs[0]), float(fs[1]), float(fs[2]), int(fs[3])
         t._step_size = da
-        cls = QuadMetricDiagAdapt if t._adapt_metric else QuadMetricDiag
-        t._metric = cls(self._final['final_var'][i])
+        fv = self._final['final_var'][i]
+        if fv.ndim == 2:
+            t._metric = (QuadMetricFullAdapt if t._adapt_metric else QuadMetricFull)(fv)
+            if 'chol_error' in self._final and self._final['chol_error'][i]:
+                t._metric._chol_error = 'a Cholesky factorisation of the adapted covariance failed (metrics.py:284-287).'
+        else:
+            t._metric = (QuadMetricDiagAdapt if t._adapt_metric else QuadMetricDiag)(fv)
         return t
 
     @property
@@ -483,9 +509,11 @@ def _get_metric(sample_trace, target, from_samples=True):
     if from_samples:
         cov = np.cov(sample_trace.get(original_space=False, flatten=True), rowvar=False)
     elif isinstance(sample_trace, TraceTuple):
-        cov = np.diag(np.mean(sample_trace._final['final_var'], axis=0))
+        fv = np.mean(sample_trace._final['final_var'], axis=0)
+        cov = fv if fv.ndim == 2 else np.diag(fv)
     elif isinstance(sample_trace, _HTrace):
-        cov = np.diag(sample_trace.metric._var)
+        m = sample_trace.metric
+        cov = np.copy(m._cov) if isinstance(m, QuadMetricFull) else np.diag(m._var)
     else:
         raise ValueError('invalid value for sample_trace.')
     if target == 'diag':

@@ -143,6 +143,14 @@ typedef struct {
  * sample_trace.py:365-373), var0 [C,n], mean0 [C,n] (initial_mean, sample_trace.py:437-444). Host pointers. */
 int bfb_sampler_init(bfb_handle h, const bfb_sampler_cfg *cfg, int64_t C, const double *x0,
                      const double *step0, const double *var0, const double *mean0);
+/* Dense mass matrix: replaces QuadMetricFull / QuadMetricFullAdapt (samplers/hmc_utils/metrics.py:94-132, 240-330,
+ * 374-417; NTrace(metric='full') or a covariance, samplers/sample_trace.py:430-453).  cov0 [C,n,n] initial covariances
+ * (positive definite, else BFB_ERR_ARG like metrics.py:105-106); everything else as bfb_sampler_init.  The chains then run
+ * on the generic warp-per-chain kernel.  bfb_sampler_get_cov: final covariances [C,n,n] and per-chain flag "a Cholesky
+ * factorisation failed during adaptation" (metrics.py:284-287); host pointers, either may be NULL. */
+int bfb_sampler_init_dense(bfb_handle h, const bfb_sampler_cfg *cfg, int64_t C, const double *x0,
+                           const double *step0, const double *cov0, const double *mean0);
+int bfb_sampler_get_cov(bfb_handle h, double *cov, int32_t *chol_error);
 /* restore every chain to its state right after bfb_sampler_init (device-to-device copies only) */
 int bfb_sampler_reset(bfb_handle h);
 /* advance every chain by n_iter iterations; out pointers in `loc`; total_tree_size (host, may be NULL) =

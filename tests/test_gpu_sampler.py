@@ -172,6 +172,15 @@ def test_sample_api(oracle):
     U, Z = device_draws(den._sync(False), 5, tt._final['n_draws'])
     ref = od.run('NUTS', dict(n_iter=60, n_warmup=30), den.from_original(x0), 1. / n**0.25, np.ones(n), draws_u=U, draws_z=Z)
     assert np.array_equal(tt.arrays['tree_depth'], ref['tree_depth'])
+    # dense mass matrix through the same API (sample_trace.py:430-431, 445-449): identity start, adapted covariance back
+    ttf = bfb.sample(den, dict(n_chain=16, n_iter=60, n_warmup=30, x_0=x0, random_generator=5, metric='full'), verbose=False)
+    assert isinstance(ttf[2].metric, bfb.sample_trace.QuadMetricFullAdapt) and ttf[2].metric._cov.shape == (n, n)
+    U, Z = device_draws(den._sync(False), 5, ttf._final['n_draws'])
+    reff = od.run('NUTS', dict(n_iter=60, n_warmup=30, dense_metric=1), den.from_original(x0), 1. / n**0.25, np.eye(n),
+                  draws_u=U, draws_z=Z)
+    assert np.array_equal(ttf.arrays['tree_depth'], reff['tree_depth'])
+    assert np.allclose(ttf._final['final_var'], reff['final_var'], rtol=1e-3, atol=1e-3 * np.abs(reff['final_var']).max())
+    assert bfb.sample_trace._get_metric(ttf, 'full', from_samples=False).shape == (n, n)
     # resume
     tt2 = bfb.sample(den, tt, n_run=10, verbose=False)
     assert tt2.samples.shape == (16, 70, n) and np.array_equal(tt2.samples[:, :60], tt.samples)
@@ -395,3 +404,77 @@ def test_tensor_core_cubic3_samplers(handle, oracle, monkeypatch, n, sampler, C)
     gen = handle.sampler_run(sampler, n_iter)
     assert handle.sampler_last_path() == 'generic'
     assert np.array_equal(out['tree_depth'], gen['tree_depth']) and np.array_equal(out['diverging'], gen['diverging'])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# dense mass matrix (metric='full'): QuadMetricFull / QuadMetricFullAdapt, hmc_utils/metrics.py:94-132, 240-330
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('case', gio.load('sampler_dense.npz')['cases'], ids=lambda c: c['name'])
+def test_golden_chains_dense_metric(handle, case):
+    """recorded runs of the real reference with metric='full' (adapted) and a fixed covariance"""
+    r, kw = case['result'], case['trace_kw']
+    n_iter, n_warmup = int(kw['n_iter']), int(kw['n_warmup'])
+    handle.set_model(to_device_spec(case['spec']))
+    cfg = cfg_from(kw, n_warmup, int(case['seed']))
+    handle.sampler_init(cfg, case['x0'], float(r['step0']), r['var0'], case['x0'], dense=True)
+    out = handle.sampler_run(case['sampler'], n_iter)
+    assert handle.sampler_last_path() == 'generic'
+    st = handle.sampler_state()
+    assert np.all(st['status'] == 0) and np.all(st['chol_error'] == 0)
+    assert np.array_equal(st['n_draws'], r['n_draws'])
+    if case['sampler'] == 'NUTS':
+        for k in INT_STATS:
+            assert np.array_equal(out[k], r[k].astype(np.int32)), k
+        for k in FLT_STATS:
+            check_floats(out[k], r[k], k)
+    else:
+        assert np.array_equal(out['tree_depth'], r['accepted'].astype(np.int32))
+        assert np.array_equal(out['diverging'], r['diverging'].astype(np.int32))
+        for k, k2 in (('logp', 'logp'), ('energy', 'energy'), ('mean_tree_accept', 'accept_stat'),
+                      ('step_size', 'step_size'), ('energy_change', 'energy_change')):
+            check_floats(out[k], r[k2], k)
+    check_floats(out['samples'], r['samples'], 'samples')
+    assert np.allclose(st['final_step'], r['final_step'], rtol=LATE_TOL)
+    assert st['final_var'].shape == r['final_var'].shape
+    assert np.allclose(st['final_var'], r['final_var'], rtol=LATE_TOL, atol=LATE_TOL * np.abs(r['final_var']).max())
+
+
+@pytest.mark.parametrize('n,C,n_iter', [(26, 96, 40), (40, 8, 24)])
+def test_dense_metric_teacher_forced_vs_oracle(handle, oracle, n, C, n_iter):
+    """dense metric, adapted during warm-up: integer outcomes identical to the oracle fed with the device's own draws;
+    after bfb_sampler_reset the run repeats bit for bit"""
+    spec, cov = synthetic_spec(n, 'cubic-2', seed=7 + n, decay=True)
+    handle.set_model(to_device_spec(spec))
+    rng = np.random.default_rng(6)
+    x0 = (np.linalg.cholesky(cov) @ rng.normal(size=(n, C))).T
+    seed, chain0 = 777, 50
+    cfg = cfg_from({'adapt_window': 10}, n_iter // 2, seed, chain0)
+    step0 = 1. / n**0.25
+    cov0 = 0.5 * cov + 0.5 * np.eye(n)
+    handle.sampler_init(cfg, x0, step0, cov0, x0, dense=True)
+    out = handle.sampler_run('NUTS', n_iter)
+    st = handle.sampler_state()
+    assert np.all(st['status'] == 0) and np.all(st['chol_error'] == 0)
+    U, Z = device_draws(handle, seed, st['n_draws'], chain0)
+    ref = oracle.OracleDensity(spec).run('NUTS', dict(n_iter=n_iter, n_warmup=n_iter // 2, adapt_window=10, dense_metric=1),
+                                         x0, step0, cov0, draws_u=U, draws_z=Z)
+    assert np.all(ref['status'] == 0)
+    assert np.array_equal(st['n_draws'], ref['n_draws'])
+    for k in INT_STATS:
+        assert np.array_equal(out[k], ref[k]), k
+    check_floats(out['samples'], ref['samples'], 'samples')
+    assert np.allclose(st['final_var'], ref['final_var'], rtol=LATE_TOL, atol=LATE_TOL * np.abs(ref['final_var']).max())
+    handle.sampler_reset()
+    out2 = handle.sampler_run('NUTS', n_iter)
+    assert np.array_equal(out2['samples'], out['samples']) and np.array_equal(out2['tree_size'], out['tree_size'])
+
+
+def test_dense_metric_rejects_indefinite_covariance(handle):
+    from bayesfast_b200 import _cabi
+    n = 4
+    spec, cov = synthetic_spec(n, 'quadratic', seed=1)
+    handle.set_model(to_device_spec(spec))
+    bad = np.eye(n)
+    bad[0, 0] = -1.
+    with pytest.raises(_cabi.BfbError, match='positive definite'):
+        handle.sampler_init(cfg_from({}, 5, 1), np.zeros((2, n)), 0.5, bad, np.zeros((2, n)), dense=True)

@@ -114,8 +114,13 @@ def test_from_reference_duck_typing():
 def test_trace_objects():
     with pytest.raises(ValueError):
         NTrace(n_iter=10, n_warmup=10)
-    with pytest.raises(NotImplementedError):
-        NTrace(metric='full')
+    # dense mass matrix: 'full', a covariance or a QuadMetricFull (sample_trace.py:375-390, 424-455)
+    from bayesfast_b200.sample_trace import QuadMetricFull, QuadMetricFullAdapt, _get_metric
+    assert NTrace(metric='full').metric == 'full' and NTrace(metric=np.eye(3)).metric.shape == (3, 3)
+    with pytest.raises(ValueError):
+        NTrace(metric=np.ones((2, 3)))
+    with pytest.raises(ValueError, match='positive definite'):
+        QuadMetricFull(np.diag([1., -1.]))
     with pytest.raises(ValueError):
         NTrace(max_treedepth=0)
     t = NTrace(n_chain=3, n_iter=6, n_warmup=2, x_0=np.zeros((3, 2)), random_generator=7)
@@ -142,6 +147,15 @@ def test_trace_objects():
     assert list(t1.stats.get().keys())[2] == 'tree_depth' and len(t1.stats.get()['logp']) == 4
     with pytest.raises(ValueError):
         tt.get(since_iter=5)
+    # a dense-metric run hands back covariances: the per-chain traces carry QuadMetricFullAdapt, _get_metric averages them
+    cov = np.array([[2., 0.3], [0.3, 1.]])
+    ttd = TraceTuple(t, arrays, dict(final, final_var=np.tile(cov, (C, 1, 1)), chol_error=np.array([0, 1, 0], np.int32)))
+    assert isinstance(ttd[0].metric, QuadMetricFullAdapt) and np.array_equal(ttd[0].metric._cov, cov)
+    ttd[0].metric.raise_ok()
+    with pytest.raises(ValueError, match='Cholesky'):
+        ttd[1].metric.raise_ok()
+    assert np.allclose(_get_metric(ttd, 'full', from_samples=False), cov)
+    assert np.allclose(_get_metric(ttd[2], 'diag', from_samples=False), [2., 1.])
 
 
 def test_shard_bounds():
