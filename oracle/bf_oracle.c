@@ -358,6 +358,31 @@ void bfo_logp_and_grad(const bfo_density *den, const double *x, double *logp, do
     }
     module_fun_and_jac(mod, xo, f, jac);
     double lp = f[0];                                            /* density.py:737 */
+    if (den->use_epilogue) {
+        /* two-module pipeline (density.py:487-566): the surrogate's m outputs feed a Gaussian-likelihood module
+         * logp = c - 1/2 (f - d)^T Cinv (f - d), jac = -(Cinv_sym (f - d))^T; Pipeline chains the Jacobians (J_1 . J_0).
+         * m = 1, d = 5, Cinv = 4 is f_1 of examples/2d-donut.ipynb. */
+        double *r = (double *)malloc(sizeof(double) * (size_t)m);
+        double *w = (double *)malloc(sizeof(double) * (size_t)m);
+        for (int o = 0; o < m; ++o) r[o] = f[o] - den->e_d[o];
+        double q = 0.;
+        for (int o = 0; o < m; ++o) {
+            double t = 0., ts = 0.;
+            for (int p2 = 0; p2 < m; ++p2) {
+                t += den->e_cinv[(size_t)o * m + p2] * r[p2];
+                ts += 0.5 * (den->e_cinv[(size_t)o * m + p2] + den->e_cinv[(size_t)p2 * m + o]) * r[p2];
+            }
+            q += r[o] * t;
+            w[o] = -ts;
+        }
+        lp = den->e_c0 - 0.5 * q;
+        for (int k = 0; k < n; ++k) {
+            double t = 0.;
+            for (int o = 0; o < m; ++o) t += w[o] * jac[(size_t)o * n + k];
+            grad[k] = t * tj[k];
+        }
+        free(r); free(w);
+    } else
     for (int k = 0; k < n; ++k) grad[k] = jac[k] * tj[k];         /* density.py:558 np.dot(J, diag) */
     if (den->use_decay) {                                         /* density.py:740-746 */
         double *d = (double *)malloc(sizeof(double) * (size_t)n);

@@ -51,7 +51,8 @@ class _PolyModel(C.Structure):
 class _Density(C.Structure):
     _fields_ = [('model', C.POINTER(_PolyModel)), ('use_decay', C.c_int32), ('d_mu', _dp), ('d_hess', _dp),
                 ('d_alpha2', C.c_double), ('d_gamma', C.c_double), ('use_transform', C.c_int32),
-                ('ranges', _dp), ('hard_bounds', _bp)]
+                ('ranges', _dp), ('hard_bounds', _bp), ('use_epilogue', C.c_int32), ('e_d', _dp), ('e_cinv', _dp),
+                ('e_c0', C.c_double)]
 
 
 class _Cfg(C.Structure):
@@ -161,6 +162,14 @@ class OracleDensity:
         hb = np.ascontiguousarray(spec['hard_bounds'], dtype=np.uint8) if tr is not None else np.zeros((n, 2), np.uint8)
         self._keep += [d_mu, d_hess, ranges, hb]
         dn.d_mu, dn.d_hess, dn.ranges, dn.hard_bounds = _d(d_mu), _d(d_hess), _d(ranges), hb.ctypes.data_as(_bp)
+        ep = spec.get('epilogue', None)       # dict(d [m], cinv [m,m], c0): Gaussian likelihood of the m outputs
+        dn.use_epilogue = int(ep is not None)
+        e_d = _f64(np.atleast_1d(ep['d'])) if ep is not None else np.zeros(m)
+        e_ci = _f64(np.atleast_2d(ep['cinv'])) if ep is not None else np.eye(m)
+        assert e_d.shape == (m,) and e_ci.shape == (m, m)
+        dn.e_c0 = float(ep.get('c0', 0.)) if ep is not None else 0.
+        self._keep += [e_d, e_ci]
+        dn.e_d, dn.e_cinv = _d(e_d), _d(e_ci)
         self._dn = dn
 
     # PolyModel.fun_and_jac for a batch of points (module rescale included, no Density wrapper)

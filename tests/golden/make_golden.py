@@ -14,6 +14,7 @@ numdifftools) and records inputs + outputs of the hot path:
     density.npz       Density.logp_and_grad(x, original_space=False) with decay + transform + module rescale
     fit.npz           PolyModel.fit (+ _set_bound) results
     sampler.npz       NUTS / HMC chains driven by a replayed random stream (include/bfb_rng.h draws)
+    pipeline.npz      surrogate + Gaussian-likelihood module pipelines (2-D donut of examples/2d-donut.ipynb, multi-output)
     sampler_dense.npz the same with the dense mass matrix (metric='full' or a covariance; QuadMetricFull / FullAdapt)
 
 The random stream: the reference's per-chain numpy Generator is replaced (after _init_chain) by a
@@ -412,8 +413,73 @@ def make_sampler_dense():
     gio.save('sampler_dense.npz', dict(cases=cases))
 
 
+def make_pipeline():
+    """Two-module pipelines: PolyModel surrogate (x -> m outputs) followed by a Gaussian-likelihood module
+    logp = c - 1/2 (f - d)^T Cinv (f - d) written as a user bf.Module (fun + jac), as in examples/2d-donut.ipynb (m = 1,
+    d = 5, Cinv = 4: f_1 = -(m - 5)^2 / 0.5) and, multi-output with masked configs, like the DES-Y1 example.  Records
+    Density.logp_and_grad of the real reference and NUTS runs driven by the replayed stream."""
+    rng = np.random.default_rng(91)
+    cases = []
+
+    def lik_module(d, cinv, c0):
+        cs = 0.5 * (cinv + cinv.T)
+        return bf.Module(fun=lambda f: np.atleast_1d(c0 - 0.5 * (f - d) @ cinv @ (f - d)),
+                         jac=lambda f: np.atleast_2d(-(cs @ (f - d))), input_vars='m', output_vars='logp')
+
+    def finish(name, den, ep, Xt, x0, seed, **trace_kw):
+        lp, gr = [], []
+        for x in Xt:
+            a_, b_ = den.logp_and_grad(x, original_space=False)
+            lp.append(float(a_)), gr.append(np.array(b_))
+        r = run_reference_chains(den, 'NUTS', trace_kw, x0, seed, 60000)
+        spec = density_spec(den)
+        spec['epilogue'] = ep
+        cases.append(dict(name=name, spec=spec, X=Xt, logp=np.array(lp), grad=np.array(gr), x0=x0, seed=seed,
+                          trace_kw=trace_kw, result=r))
+        print(name, 'mean depth', np.mean(r['tree_depth']), 'n_div', int(np.sum(r['diverging'])), 'draws', r['n_draws'])
+
+    # --- BASELINE configs[0]: 2-D donut, quadratic surrogate of m = |x|, analytic f_1, decay on, bound off, 4 chains ---
+    a, b = 5., 0.5
+    m0 = bf.Module(fun=lambda x: np.atleast_1d(np.linalg.norm(x, 2, -1)), input_vars='x', output_vars='m')
+    m1 = bf.Module(fun=lambda x: -(x - a)**2 / b, jac=lambda x: np.atleast_2d(-2 * (x - a) / b), input_vars='m',
+                   output_vars='logp')
+    sur = PolyModel('quadratic', input_size=2, output_size=1, input_vars='x', output_vars='m')
+    sur.set_bound_options(use_bound=False)
+    den = bf.Density(module_list=[m0, m1], surrogate_list=[sur], input_shapes=[2], input_vars='x', density_name='logp')
+    den.set_decay_options(use_decay=True)
+    th = rng.uniform(0., 2. * np.pi, size=30)                 # 5 P = 30 fit points on the ring (recipe.py:84-86)
+    rad = 5. + 0.5 * rng.normal(size=30)
+    xf = np.stack((rad * np.cos(th), rad * np.sin(th)), axis=1)
+    den.fit([den.fun(x, original_space=True, use_surrogate=False) for x in xf])
+    den.use_surrogate = True
+    Xt = np.concatenate((xf[:6] * 1.02, rng.normal(size=(4, 2)) * 2., xf[6:9] * 2.5))
+    finish('donut_quadratic', den, dict(d=np.array([a]), cinv=np.array([[2. / b]]), c0=0.), Xt, xf[10:14].copy(), 2101,
+           n_iter=40, n_warmup=20)       # short: the ring amplifies rounding differences ~1.3x per iteration
+
+    # --- multi-output: n = 5 inputs, m = 6 outputs from two masked quadratic configs + a linear one, full Cinv ---
+    n, m = 5, 6
+    cfgs = [PolyConfig('linear', input_mask=None, output_mask=None),
+            PolyConfig('quadratic', input_mask=[0, 1, 3], output_mask=[0, 1, 2]),
+            PolyConfig('quadratic', input_mask=[1, 2, 3, 4], output_mask=[3, 4, 5])]
+    W = rng.normal(size=(m, n)) * 0.6
+    truth = lambda x: W @ x + 0.15 * np.array([x[0] * x[1], x[3]**2, x[0] * x[3], x[2] * x[4], x[1]**2, x[3] * x[4]])
+    d = rng.normal(size=m) * 0.3
+    B = rng.normal(size=(m, m))
+    cinv = B @ B.T / m + 0.5 * np.eye(m)
+    mA = bf.Module(fun=truth, input_vars='x', output_vars='m')
+    sur = PolyModel(cfgs, input_size=n, output_size=m, input_vars='x', output_vars='m')
+    den = bf.Density(module_list=[mA, lik_module(d, cinv, -1.25)], surrogate_list=[sur], input_shapes=[n], input_vars='x',
+                     density_name='logp', decay_options={'use_decay': True})
+    xf = rng.normal(size=(4 * sur.n_param, n)) * 1.5
+    den.fit([den.fun(x, original_space=True, use_surrogate=False) for x in xf])
+    den.use_surrogate = True
+    Xt = np.concatenate((xf[:8] * 0.7, xf[8:14] * 3.))
+    finish('multi_output_n5_m6', den, dict(d=d, cinv=cinv, c0=-1.25), Xt, xf[20:23] * 0.5, 2202, n_iter=60, n_warmup=30)
+    gio.save('pipeline.npz', dict(cases=cases))
+
+
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['poly_kat', 'poly_eval', 'density', 'fit', 'sampler', 'sampler_dense']
+    which = sys.argv[1:] or ['poly_kat', 'poly_eval', 'density', 'fit', 'sampler', 'sampler_dense', 'pipeline']
     if 'poly_kat' in which:
         make_poly_kat()
     if 'poly_eval' in which:
@@ -426,6 +492,8 @@ if __name__ == '__main__':
         make_sampler()
     if 'sampler_dense' in which:
         make_sampler_dense()
+    if 'pipeline' in which:
+        make_pipeline()
     for f in sorted(os.listdir(gio.GOLDEN_DIR)):
         if f.endswith('.npz'):
             print(f, os.path.getsize(os.path.join(gio.GOLDEN_DIR, f)))
