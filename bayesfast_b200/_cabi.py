@@ -77,6 +77,7 @@ def lib():
             L.bfb_poly_eval_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int]
             L.bfb_logp_and_grad_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int]
             L.bfb_fit_begin.argtypes = [C.c_void_p, C.c_void_p]
+            L.bfb_set_epilogue.argtypes = [C.c_void_p, C.c_int, C.c_double]
             L.bfb_sampler_init.argtypes = [C.c_void_p, C.POINTER(SamplerCfg), C.c_int64, _dp, _dp, _dp, _dp]
             L.bfb_sampler_init_dense.argtypes = [C.c_void_p, C.POINTER(SamplerCfg), C.c_int64, _dp, _dp, _dp, _dp]
             L.bfb_sampler_get_cov.argtypes = [C.c_void_p, _dp, _ip]
@@ -211,6 +212,9 @@ class Handle:
         check(self._L.bfb_set_model(self._h, C.byref(d)))
         self.n, self.m = n, m
         self._keep = keep
+        ss = spec.get('epilogue_sumsq', None)     # set by Density._sync: logp = c0 - 1/2 sum_o f_o^2 over whitened outputs
+        if ss is not None:
+            check(self._L.bfb_set_epilogue(self._h, 1, float(ss)))
 
     def poly_eval_batch(self, X, want_jac=True):
         X = f64(X).reshape(-1, self.n)

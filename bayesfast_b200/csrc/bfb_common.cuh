@@ -64,6 +64,10 @@ struct DevModel {
     const double *bfrag3;
     const int *c3pair;
     int c3_kt, c3_n3t;
+    // second module of the pipeline (bfb_set_epilogue): 1 = Gaussian likelihood of the m (pre-whitened) outputs,
+    // logp = e_c0 - 1/2 sum_o f_o^2
+    int epilogue;
+    double e_c0;
 };
 
 struct HostConfig {

@@ -245,9 +245,26 @@ __device__ __forceinline__ void density_eval(const DevModel &M, const double (&x
         else { xo[r] = xt[r]; tj[r] = 1.; tjj[r] = 0.; }
     }
     double f, J[NPL];
-    module_fg<NPL>(M, 0, xo, lane, xsm, dsm, f, J);
+    if (M.epilogue) {
+        // two-module pipeline (density.py:487-566): Gaussian likelihood of the m pre-whitened surrogate outputs,
+        // logp = c0 - 1/2 sum_o f_o^2, Jacobians chained: grad = -sum_o f_o J_o
+        double acc = 0., gs[NPL];
 #pragma unroll
-    for (int r = 0; r < NPL; ++r) grad[r] = J[r] * tj[r];
+        for (int r = 0; r < NPL; ++r) gs[r] = 0.;
+        for (int o = 0; o < M.m; ++o) {
+            module_fg<NPL>(M, o, xo, lane, xsm, dsm, f, J);
+            acc = fma(f, f, acc);
+#pragma unroll
+            for (int r = 0; r < NPL; ++r) gs[r] = fma(-f, J[r], gs[r]);
+        }
+        f = M.e_c0 - 0.5 * acc;
+#pragma unroll
+        for (int r = 0; r < NPL; ++r) grad[r] = gs[r] * tj[r];
+    } else {
+        module_fg<NPL>(M, 0, xo, lane, xsm, dsm, f, J);
+#pragma unroll
+        for (int r = 0; r < NPL; ++r) grad[r] = J[r] * tj[r];
+    }
     if (M.use_decay) {
         double d[NPL], Hd[NPL];
 #pragma unroll

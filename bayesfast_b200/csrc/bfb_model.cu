@@ -398,6 +398,24 @@ extern "C" int bfb_set_model(bfb_handle h, const bfb_model_desc *d)
     return BFB_OK;
 }
 
+// Second module of a two-module pipeline (core/density.py:487-566: surrogate x -> m outputs, then a user Module m -> logp):
+// kind 1 = Gaussian likelihood logp = c0 - 1/2 |f|^2 of the m outputs of the model set before, which the caller has
+// pre-whitened (f' = Lt (f - d) with Cinv = Lt^T Lt folds into the polynomial coefficients, the constants and f_mu because
+// all of them are linear in the outputs: bayesfast_b200/density.py whiten_spec).  kind 0 removes it.  Evaluated by the
+// generic kernels (density_eval, bfb_eval.cuh); the tensor-core evaluators take logp = output 0 and are switched off.
+extern "C" int bfb_set_epilogue(bfb_handle h, int kind, double c0)
+{
+    BFB_REQUIRE(h && h->has_model, BFB_ERR_STATE, "bfb_set_epilogue: no model set");
+    BFB_REQUIRE(kind == 0 || kind == 1, BFB_ERR_ARG, "bfb_set_epilogue: unknown kind %d", kind);
+    BFB_CUDA(cudaSetDevice(h->device));
+    BFB_CUDA(cudaStreamSynchronize(h->stream));
+    if (kind == 0 && h->dm.epilogue) return bfb_upload_model(h);      // rebuilds the tensor-core tables
+    h->dm.epilogue = kind;
+    h->dm.e_c0 = kind ? c0 : 0.;
+    if (kind) h->dm.frag_nr = 0;
+    return BFB_OK;
+}
+
 // ----------------------------------------------------------------------------------------------
 // batched evaluation kernels: one warp per (point, output)
 // ----------------------------------------------------------------------------------------------

@@ -624,7 +624,7 @@ static int launch_multi(bfb_context *h, const bfb_run_out &o, int n_iter)
 int bfb_launch_nuts_fast(bfb_context *h, const bfb_run_out &o, int n_iter)
 {
     const DevModel &M = h->dm;
-    if (M.n > 32 || M.has_c3 || M.use_decay || M.use_transform || M.use_scales) return 1;
+    if (M.n > 32 || M.has_c3 || M.use_decay || M.use_transform || M.use_scales || M.epilogue) return 1;
     if (h->scfg.max_treedepth > 10) return 1;
     const int n = M.n;
     const char *gsel = getenv("BFB200_LANES_PER_CHAIN");

@@ -13,11 +13,94 @@ from collections import namedtuple
 import numpy as np
 
 from . import transforms as tf
-from .poly import PolyModel, PolyConfig, pack_dense
+from ._cabi import n_packed
+from .poly import PolyModel, PolyConfig, pack_dense, unpack_dense
 
-__all__ = ['Density', 'DecayOptions']
+__all__ = ['Density', 'DecayOptions', 'GaussianLikelihood', 'whiten_spec']
 
 DecayOptions = namedtuple('DecayOptions', ('use_decay', 'alpha', 'alpha_p', 'gamma'))
+
+
+class GaussianLikelihood:
+    """
+    The second module of a two-module pipeline, m surrogate outputs -> logp:
+
+        logp(f) = const - 1/2 (f - mean)^T inv_cov (f - mean)
+
+    In the reference this is a user `bayesfast.Module(fun=..., jac=...)` placed after the surrogate in
+    `Density(module_list=[...])` (core/density.py:487-566 chains the Jacobians): f_1 = -(m - 5)^2 / 0.5 of
+    examples/2d-donut.ipynb is GaussianLikelihood([5.], [[4.]]), the chi^2 + prior module of
+    examples/des-y1-w-cosmosis.ipynb is one with the data vector and the inverse covariance.  Arbitrary Python
+    modules cannot run on the device; this closed form can.
+    """
+
+    def __init__(self, mean, inv_cov, const=0.):
+        self.mean = np.atleast_1d(np.asarray(mean, dtype=np.float64))
+        m = self.mean.size
+        ic = np.asarray(inv_cov, dtype=np.float64)
+        if ic.ndim == 1:
+            ic = np.diag(ic)
+        ic = np.atleast_2d(ic)
+        if self.mean.ndim != 1 or ic.shape != (m, m):
+            raise ValueError('mean should have shape (m,) and inv_cov (m, m) or (m,).')
+        self.inv_cov = ic.copy()
+        self.const = float(const)
+        lam, V = np.linalg.eigh(0.5 * (ic + ic.T))
+        if not np.all(lam >= -1e-12 * max(1., np.abs(lam).max())):
+            raise ValueError('inv_cov should be positive semi-definite.')
+        # inv_cov_sym = Lt^T Lt  (rows of zero eigenvalues dropped later is not needed: they contribute nothing)
+        self._lt = np.sqrt(np.clip(lam, 0., None))[:, None] * V.T
+
+    output_size = property(lambda self: self.mean.size)
+
+    def logp(self, f):
+        r = np.asarray(f, dtype=np.float64) - self.mean
+        return self.const - 0.5 * np.einsum('...i,ij,...j->...', r, self.inv_cov, r)
+
+    __call__ = logp
+
+    def to_spec(self):
+        return dict(d=self.mean.copy(), cinv=self.inv_cov.copy(), c0=self.const)
+
+
+def whiten_spec(spec, lik):
+    """
+    Fold a GaussianLikelihood into the surrogate: f'(x) = Lt (f(x) - mean) with inv_cov = Lt^T Lt is again a polynomial
+    of the same orders (every coefficient, the constants and the bound's f_mu are linear in the outputs), so that
+    logp = const - 1/2 sum_o f'_o(x)^2 and grad = -sum_o f'_o grad f'_o: the device then needs no m x m product.
+    Returns a spec with one full-input config per order present (all m outputs), `epilogue_sumsq` = const.
+    """
+    n, m = int(spec['n']), int(spec['m'])
+    if lik.output_size != m:
+        raise ValueError('the likelihood takes {} inputs but the surrogate has {} outputs.'.format(lik.output_size, m))
+    full = {}
+    for c in spec['configs']:
+        order, im, om = c['order'], np.asarray(c['input_mask'], np.int64), np.asarray(c['output_mask'], np.int64)
+        if c.get('packed', None) is None:
+            raise RuntimeError('the surrogate has no coefficients yet.')
+        pk = np.asarray(c['packed'], np.float64).reshape(om.size, n_packed(order, im.size))
+        acc = full.setdefault(order, np.zeros((m, n_packed(order, n))))
+        for i, o in enumerate(om):
+            dense = unpack_dense(order, pk[i], im.size)
+            if order == 'linear':
+                big = np.zeros(n + 1)
+                big[0] = dense[0]
+                big[1 + im] = dense[1:]
+            else:
+                big = np.zeros((n,) * dense.ndim)
+                big[np.ix_(*([im] * dense.ndim))] = dense
+            acc[o] += pack_dense(order, big, n)
+    lin = full.setdefault('linear', np.zeros((m, n + 1)))
+    lin[:, 0] -= lik.mean
+    lt = lik._lt
+    out = dict(spec)
+    out['configs'] = [dict(order=o, input_mask=np.arange(n), output_mask=np.arange(m), packed=lt @ full[o], coef=None)
+                      for o in ('linear', 'quadratic', 'cubic-2', 'cubic-3') if o in full]
+    if spec.get('use_bound', False):
+        out['f_mu'] = lt @ (np.atleast_1d(spec['f_mu']).astype(np.float64) - lik.mean)
+    out['epilogue_sumsq'] = lik.const
+    out.pop('epilogue', None)
+    return out
 
 
 class Density:
@@ -32,11 +115,17 @@ class Density:
     """
 
     def __init__(self, surrogate, input_scales=None, hard_bounds=False, decay_options=None,
-                 density_name='__var__', input_vars='__var__'):
+                 density_name='__var__', input_vars='__var__', likelihood=None):
         if not isinstance(surrogate, PolyModel):
             raise ValueError('surrogate should be a bayesfast_b200.PolyModel: only surrogate-only densities run '
                              'on the device, there is no CPU fallback.')
         self._surrogate = surrogate
+        if likelihood is not None and not isinstance(likelihood, GaussianLikelihood):
+            raise ValueError('likelihood should be a GaussianLikelihood: arbitrary Python modules cannot run on the device.')
+        if likelihood is not None and likelihood.output_size != surrogate.output_size:
+            raise ValueError('the likelihood takes {} inputs but the surrogate has {} outputs.'.format(
+                likelihood.output_size, surrogate.output_size))
+        self._likelihood = likelihood
         self.density_name = str(density_name)
         self.input_vars = [input_vars] if isinstance(input_vars, str) else list(input_vars)
         n = surrogate.input_size
@@ -53,6 +142,7 @@ class Density:
 
     surrogate = property(lambda self: self._surrogate)
     surrogate_list = property(lambda self: [self._surrogate])
+    likelihood = property(lambda self: self.__dict__.get('_likelihood', None))
     input_size = property(lambda self: self._surrogate.input_size)
     input_scales = property(lambda self: self._input_scales)
     hard_bounds = property(lambda self: self._hard_bounds)
@@ -159,6 +249,8 @@ class Density:
         else:
             spec['transform_ranges'] = self._input_scales.copy()
             spec['hard_bounds'] = self._hard_bounds.copy()
+        if self.likelihood is not None:
+            spec['epilogue'] = self.likelihood.to_spec()      # un-whitened (what the oracle restates); _sync whitens
         return spec
 
     def _sync(self, original_space=False):
@@ -184,6 +276,8 @@ class Density:
             spec = self.to_spec()
             if original_space:
                 spec['transform_ranges'] = None
+            if self.likelihood is not None:
+                spec = whiten_spec(spec, self.likelihood)
             self._handle[key].set_model(spec)
             self._synced.add(key)
         return self._handle[key]
@@ -226,6 +320,8 @@ class Density:
             if y.ndim == 1:
                 y = y[:, None]
             logp = y[:, 0].copy()
+        if self.likelihood is not None:         # logp of the pipeline, for center_max (poly.py:277-286)
+            logp = self.likelihood.logp(y)
         if self._use_decay:
             self._set_decay(x)
         su = self._surrogate
@@ -237,10 +333,12 @@ class Density:
 
     # ------------------------------------------------------------------ adapter
     @classmethod
-    def from_reference(cls, ref, device=None):
+    def from_reference(cls, ref, device=None, likelihood=None):
         """
         Build from a fitted bayesfast.Density (duck-typed: reads _surrogate_list, _module_list, _input_scales,
         _hard_bounds, decay attributes).  Raises if the density is not surrogate-only / PolyModel-representable.
+        With `likelihood` (a GaussianLikelihood restating the LAST module of the reference's list) the surrogate
+        must replace every module but that one.
         """
         sl = list(getattr(ref, '_surrogate_list', []))
         if len(sl) != 1:
@@ -250,7 +348,11 @@ class Density:
             raise ValueError('the surrogate is not a PolyModel.')
         n_mod = len(getattr(ref, '_module_list', []))
         i_step, n_step = rs._scope
-        if not (i_step % max(n_mod, 1) == 0 and n_step == n_mod):
+        if likelihood is not None:
+            if not (i_step == 0 and n_step == n_mod - 1):
+                raise ValueError('with a likelihood the surrogate must replace all modules but the last '
+                                 '(scope={}, {} modules).'.format(tuple(rs._scope), n_mod))
+        elif not (i_step % max(n_mod, 1) == 0 and n_step == n_mod):
             raise ValueError('the surrogate must replace the whole module list (scope={}, {} modules): arbitrary '
                              'Python modules cannot run on the device.'.format(tuple(rs._scope), n_mod))
         if not getattr(ref, 'use_surrogate', True):
@@ -276,7 +378,7 @@ class Density:
                   hard_bounds=hb if isinstance(hb, bool) else np.array(hb),
                   decay_options=dict(use_decay=ref._use_decay, alpha=ref._alpha, alpha_p=ref._alpha_p,
                                      gamma=ref._gamma),
-                  density_name=getattr(ref, 'density_name', '__var__'))
+                  density_name=getattr(ref, 'density_name', '__var__'), likelihood=likelihood)
         if ref._use_decay and hasattr(ref, '_mu'):
             den._mu, den._hess = np.array(ref._mu), np.array(ref._hess)
             den._alpha_2 = float(ref._alpha_2)

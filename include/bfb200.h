@@ -90,6 +90,13 @@ int bfb_poly_eval_batch(bfb_handle h, const double *X, int64_t C, double *F, dou
  * logp is output 0 of the PolyModel.  X [C,n] -> logp [C], grad [C,n]. */
 int bfb_logp_and_grad_batch(bfb_handle h, const double *X, int64_t C, double *logp, double *grad, int loc);
 
+/* Second module of a two-module pipeline (core/density.py:487-566; examples/2d-donut.ipynb f_1, the chi^2 module of
+ * examples/des-y1-w-cosmosis.ipynb): kind 1 = Gaussian likelihood logp = c0 - 1/2 sum_o f_o^2 of the m outputs of the model
+ * set with bfb_set_model, pre-whitened by the caller (bayesfast_b200/density.py: whiten_spec); kind 0 removes it.
+ * Density-level calls (bfb_logp_and_grad_batch, the samplers) then evaluate the pipeline; bfb_poly_eval_batch still
+ * returns the (whitened) outputs.  bfb_set_model / bfb_fit_solve reset it. */
+int bfb_set_epilogue(bfb_handle h, int kind, double c0);
+
 /* ------------------------------------------------------------------------------------------------
  * Fit: replaces PolyModel.fit (poly.py:505-589): the design-matrix builders _lsq_* (_poly.pyx:143-177),
  * scipy.linalg.lstsq (poly.py:570) and _set_bound (poly.py:262-292).  One design matrix per recipe row

@@ -1,0 +1,122 @@
+"""GPU parity of the two-module pipeline (PolyModel surrogate -> Gaussian-likelihood module; core/density.py:487-566):
+BASELINE configs[0] (2-D donut of examples/2d-donut.ipynb) and a multi-output surrogate with masked configs, against recorded
+runs of the real reference (tests/golden/pipeline.npz) and against the oracle."""
+import numpy as np
+import pytest
+
+import _golden_io as gio
+from _specs import to_device_spec
+from test_gpu_sampler import cfg_from, device_draws, check_floats, INT_STATS, FLT_STATS
+
+pytestmark = pytest.mark.gpu
+CASES = gio.load('pipeline.npz')['cases']
+
+
+@pytest.fixture(scope='module')
+def handle():
+    from bayesfast_b200 import _cabi
+    h = _cabi.Handle(0)
+    yield h
+    h.close()
+
+
+def _whitened(case):
+    from bayesfast_b200.density import whiten_spec, GaussianLikelihood
+    spec = to_device_spec(case['spec'])
+    ep = spec['epilogue']
+    return whiten_spec(spec, GaussianLikelihood(ep['d'], ep['cinv'], ep['c0']))
+
+
+@pytest.mark.parametrize('case', CASES, ids=lambda c: c['name'])
+def test_pipeline_logp_and_grad_golden(handle, case):
+    handle.set_model(_whitened(case))
+    lp, g = handle.logp_and_grad_batch(case['X'])
+    assert np.allclose(lp, case['logp'], rtol=1e-10, atol=1e-10)
+    assert np.allclose(g, case['grad'], rtol=1e-10, atol=1e-10 * np.abs(case['grad']).max())
+
+
+@pytest.mark.parametrize('case', CASES, ids=lambda c: c['name'])
+def test_pipeline_golden_chains(handle, case):
+    """NUTS through the pipeline: same seeds and draw stream as the recorded runs of the real reference"""
+    r, kw = case['result'], case['trace_kw']
+    n_iter, n_warmup = int(kw['n_iter']), int(kw['n_warmup'])
+    handle.set_model(_whitened(case))
+    handle.sampler_init(cfg_from(kw, n_warmup, int(case['seed'])), case['x0'], float(r['step0']), r['var0'], case['x0'])
+    out = handle.sampler_run('NUTS', n_iter)
+    assert handle.sampler_last_path() == 'generic'
+    st = handle.sampler_state()
+    assert np.all(st['status'] == 0)
+    assert np.array_equal(st['n_draws'], r['n_draws'])
+    for k in INT_STATS:
+        assert np.array_equal(out[k], r[k].astype(np.int32)), k
+    # first trees of the donut are 6-7 doublings deep: 1e-9 over the first 4 iterations (see tests/test_oracle_golden.py)
+    for k in FLT_STATS:
+        assert np.allclose(out[k][:, :4], r[k][:, :4], rtol=1e-9, atol=1e-9), k
+        assert np.allclose(out[k], r[k], rtol=1e-3, atol=1e-3), k
+    assert np.allclose(out['samples'], r['samples'], rtol=1e-3, atol=1e-3)
+
+
+def test_donut_public_api(oracle):
+    """BASELINE configs[0] through the public interface: quadratic PolyModel surrogate of m = |x| fitted on the device,
+    GaussianLikelihood([5], [[4]]) = f_1 of the notebook, decay on, bound off, 4 NUTS chains; the oracle restates the pipeline"""
+    import bayesfast_b200 as bfb
+    rng = np.random.default_rng(3)
+    th, rad = rng.uniform(0., 2. * np.pi, size=30), 5. + 0.5 * rng.normal(size=30)
+    xf = np.stack((rad * np.cos(th), rad * np.sin(th)), axis=1)
+    sur = bfb.PolyModel('quadratic', input_size=2, output_size=1, bound_options=dict(use_bound=False))
+    den = bfb.Density(sur, decay_options=dict(use_decay=True), likelihood=bfb.GaussianLikelihood([5.], [[4.]]))
+    den.fit(xf, np.linalg.norm(xf, axis=1))
+    spec = den.to_spec()
+    assert spec['epilogue']['cinv'][0, 0] == 4. and spec['use_decay'] and not spec['use_bound']
+    od = oracle.OracleDensity(spec)
+    X = np.concatenate((xf[:8] * 1.03, rng.normal(size=(6, 2)) * 2., xf[8:12] * 3.))
+    lp, g = den.logp_and_grad(X, original_space=False)
+    lpo, go = od.logp_and_grad_batch(X)
+    assert np.allclose(lp, lpo, rtol=1e-10, atol=1e-10) and np.allclose(g, go, rtol=1e-10, atol=1e-10 * np.abs(go).max())
+    # a quadratic in x approximates |x| on the ring only roughly: the pipeline's logp follows the true -(|x| - 5)^2 / 0.5
+    assert np.max(np.abs(lp[:8] + (np.linalg.norm(X[:8], axis=1) - 5.)**2 / 0.5)) < 1.
+    x0 = xf[12:16].copy()
+    tt = bfb.sample(den, dict(n_chain=4, n_iter=60, n_warmup=30, x_0=x0, random_generator=11), verbose=False)
+    assert tt.samples.shape == (4, 60, 2)
+    U, Z = device_draws(den._sync(False), 11, tt._final['n_draws'])
+    ref = od.run('NUTS', dict(n_iter=60, n_warmup=30), x0, 1. / 2**0.25, np.ones(2), draws_u=U, draws_z=Z)
+    for k in INT_STATS:
+        assert np.array_equal(tt.arrays[k], ref[k]), k
+    assert np.allclose(tt.samples, ref['samples'], rtol=1e-3, atol=1e-3)
+    rr = np.linalg.norm(tt.samples[:, 30:].reshape(-1, 2), axis=1)
+    assert abs(rr.mean() - 5.) < 1.
+
+
+def test_multi_output_likelihood_vs_oracle(handle, oracle):
+    """m = 40 outputs (block-quadratic masked configs), n = 12: evaluation and teacher-forced NUTS against the oracle"""
+    from bayesfast_b200.density import whiten_spec, GaussianLikelihood
+    rng = np.random.default_rng(8)
+    n, m, C, n_iter = 12, 40, 48, 30
+    masks = [np.sort(rng.choice(n, size=5, replace=False)) for _ in range(4)]
+    cfgs = [dict(order='linear', input_mask=np.arange(n), output_mask=np.arange(m),
+                 coef=np.concatenate((rng.normal(size=(m, 1)) * 0.2, rng.normal(size=(m, n)) * 0.5), axis=1))]
+    for b, im in enumerate(masks):
+        q = np.triu(rng.normal(size=(10, 5, 5))) * 0.08
+        cfgs.append(dict(order='quadratic', input_mask=im, output_mask=np.arange(10 * b, 10 * b + 10), coef=q))
+    B = rng.normal(size=(m, m))
+    ep = dict(d=rng.normal(size=m) * 0.2, cinv=B @ B.T / m + 0.3 * np.eye(m), c0=0.75)
+    spec = dict(n=n, m=m, configs=cfgs, use_bound=False, input_scales=None, use_decay=False, transform_ranges=None, epilogue=ep)
+    w = whiten_spec(to_device_spec(spec), GaussianLikelihood(ep['d'], ep['cinv'], ep['c0']))
+    handle.set_model(w)
+    X = rng.normal(size=(64, n)) * 0.7
+    lp, g = handle.logp_and_grad_batch(X)
+    od = oracle.OracleDensity(spec)
+    lpo, go = od.logp_and_grad_batch(X)
+    assert np.allclose(lp, lpo, rtol=1e-10, atol=1e-10) and np.allclose(g, go, rtol=1e-10, atol=1e-10 * np.abs(go).max())
+    x0 = rng.normal(size=(C, n)) * 0.3
+    seed = 515
+    handle.sampler_init(cfg_from({}, n_iter // 2, seed), x0, 1. / n**0.25, np.ones(n), x0)
+    out = handle.sampler_run('NUTS', n_iter)
+    st = handle.sampler_state()
+    assert np.all(st['status'] == 0)
+    U, Z = device_draws(handle, seed, st['n_draws'])
+    ref = od.run('NUTS', dict(n_iter=n_iter, n_warmup=n_iter // 2), x0, 1. / n**0.25, np.ones(n), draws_u=U, draws_z=Z)
+    assert np.array_equal(st['n_draws'], ref['n_draws'])
+    for k in INT_STATS:
+        assert np.array_equal(out[k], ref[k]), k
+    check_floats(out['samples'], ref['samples'], 'samples')

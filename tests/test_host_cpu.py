@@ -165,3 +165,31 @@ def test_shard_bounds():
             lo, hi = shard_bounds(total, r, world)
             cover += list(range(lo, hi))
         assert cover == list(range(total))
+
+
+def test_likelihood_whitening_matches_oracle(oracle):
+    """whiten_spec folds the Gaussian likelihood into the polynomial coefficients (f' = Lt (f - d)); the oracle evaluates the
+    un-whitened pipeline the way the reference does: both must agree (golden pipelines of the real reference)."""
+    import _golden_io as gio
+    from _specs import to_device_spec
+    from bayesfast_b200.density import whiten_spec, GaussianLikelihood
+    from bayesfast_b200.poly import unpack_dense
+    for c in gio.load('pipeline.npz')['cases']:
+        spec = to_device_spec(c['spec'])
+        ep = spec['epilogue']
+        lik = GaussianLikelihood(ep['d'], ep['cinv'], ep['c0'])
+        w = whiten_spec(spec, lik)
+        assert w['epilogue_sumsq'] == ep['c0'] and 'epilogue' not in w
+        assert all(len(cf['input_mask']) == spec['n'] and len(cf['output_mask']) == spec['m'] for cf in w['configs'])
+        for cf in w['configs']:
+            cf['coef'] = np.array([unpack_dense(cf['order'], a, int(spec['n'])) for a in cf['packed']])
+        F, J = oracle.OracleDensity(dict(w, use_decay=False, transform_ranges=None)).poly_eval_batch(c['X'])
+        lp0, gr0 = oracle.OracleDensity(dict(c['spec'], use_decay=False)).logp_and_grad_batch(c['X'])
+        assert np.allclose(lik.const - 0.5 * np.sum(F * F, axis=1), lp0, rtol=1e-12, atol=1e-12)
+        assert np.allclose(-np.einsum('co,con->cn', F, J), gr0, rtol=1e-12, atol=1e-12 * np.abs(gr0).max())
+        assert np.allclose(lik.logp(np.zeros(spec['m'])), ep['c0'] - 0.5 * ep['d'] @ ep['cinv'] @ ep['d'])
+    with pytest.raises(ValueError, match='semi-definite'):
+        GaussianLikelihood([0., 0.], [[1., 0.], [0., -1.]])
+    sur = bfb.PolyModel('quadratic', input_size=2, output_size=1)
+    with pytest.raises(ValueError, match='outputs'):
+        bfb.Density(sur, likelihood=GaussianLikelihood([0., 0.], np.eye(2)))
