@@ -143,11 +143,20 @@ __device__ __forceinline__ void matvec(const double *T, int n, int np, const dou
 }
 
 // PolyModel._fun_and_jac with the radial bound (poly.py:466-503) preceded by the module-level rescale
-// and followed by jac / scales_diff (core/module.py:80-85, 221-227).  xo: point in the surrogate's
-// (un-rescaled) input space.  xsm, dsm: two per-warp shared buffers of np doubles.
+// and followed by jac / scales_diff (core/module.py:80-85, 221-227), in two steps so that a multi-output model pays for the
+// rescale, the Mahalanobis radius and the projection once: module_prepare stages the evaluation point (x inside the
+// ellipsoid, its projection x_0 outside) in xsm, module_output evaluates output o there and applies _fj_bound.
+// xo: point in the surrogate's (un-rescaled) input space.  xsm, dsm: two per-warp shared buffers of np doubles.
 template <int NPL>
-__device__ __forceinline__ void module_fg(const DevModel &M, int o, const double (&xo)[NPL], int lane,
-                                          double *xsm, double *dsm, double &f, double (&J)[NPL])
+struct ModuleCtx {
+    bool outside;
+    double beta;
+    double xe[NPL], d[NPL], Hd[NPL];
+};
+
+template <int NPL>
+__device__ __forceinline__ void module_prepare(const DevModel &M, const double (&xo)[NPL], int lane,
+                                               double *xsm, double *dsm, ModuleCtx<NPL> &K)
 {
     const int n = M.n, np = M.np;
     double xs[NPL];
@@ -156,58 +165,70 @@ __device__ __forceinline__ void module_fg(const DevModel &M, int o, const double
         int j = lane + 32 * r;
         xs[r] = M.use_scales ? (xo[r] - M.s0[j]) / M.sdiff[j] : xo[r];
         if (j >= n) xs[r] = 0.;
+        K.d[r] = 0.; K.Hd[r] = 0.;
     }
-    bool outside = false;
-    double beta = 0., d[NPL], Hd[NPL];
+    K.outside = false;
+    K.beta = 0.;
     if (M.use_bound) {
 #pragma unroll
         for (int r = 0; r < NPL; ++r) {
             int j = lane + 32 * r;
-            d[r] = (j < n) ? xs[r] - M.mu[j] : 0.;
-            dsm[j] = d[r];
+            K.d[r] = (j < n) ? xs[r] - M.mu[j] : 0.;
+            dsm[j] = K.d[r];
         }
         __syncwarp();
-        matvec<NPL>(M.HT, n, np, dsm, lane, Hd);
+        matvec<NPL>(M.HT, n, np, dsm, lane, K.Hd);
         double part = 0.;
 #pragma unroll
-        for (int r = 0; r < NPL; ++r) part = fma(d[r], Hd[r], part);
-        beta = sqrt(warp_sum(part));
-        outside = beta > M.alpha;
+        for (int r = 0; r < NPL; ++r) part = fma(K.d[r], K.Hd[r], part);
+        K.beta = sqrt(warp_sum(part));
+        K.outside = K.beta > M.alpha;
         __syncwarp();
     }
-    if (!outside) {
 #pragma unroll
-        for (int r = 0; r < NPL; ++r) xsm[lane + 32 * r] = xs[r];
-        __syncwarp();
-        poly_fg<NPL>(M, o, xsm, xs, lane, f, J);
-        __syncwarp();
+    for (int r = 0; r < NPL; ++r) {
+        int j = lane + 32 * r;
+        // _fj_bound, poly.py:480-503: outside points are evaluated at their projection onto the ellipsoid
+        K.xe[r] = !K.outside ? xs[r] : (j < n) ? (M.alpha * xs[r] + (K.beta - M.alpha) * M.mu[j]) / K.beta : 0.;
+        xsm[j] = K.xe[r];
+    }
+    __syncwarp();
+}
+
+template <int NPL>
+__device__ __forceinline__ void module_output(const DevModel &M, int o, const ModuleCtx<NPL> &K, int lane,
+                                              const double *xsm, double &f, double (&J)[NPL])
+{
+    if (!K.outside) {
+        poly_fg<NPL>(M, o, xsm, K.xe, lane, f, J);
     } else {
-        // _fj_bound, poly.py:480-503
-        const double alpha = M.alpha;
-        double x0[NPL], jj0[NPL], ff0;
-#pragma unroll
-        for (int r = 0; r < NPL; ++r) {
-            int j = lane + 32 * r;
-            x0[r] = (j < n) ? (alpha * xs[r] + (beta - alpha) * M.mu[j]) / beta : 0.;
-            xsm[j] = x0[r];
-        }
-        __syncwarp();
-        poly_fg<NPL>(M, o, xsm, x0, lane, ff0, jj0);
-        __syncwarp();
+        const double alpha = M.alpha, beta = K.beta;
+        double jj0[NPL], ff0;
+        poly_fg<NPL>(M, o, xsm, K.xe, lane, ff0, jj0);
         const double fmu = M.f_mu[o];
         f = (beta * ff0 - (beta - alpha) * fmu) / alpha;
         double part = 0.;
 #pragma unroll
-        for (int r = 0; r < NPL; ++r) part = fma(jj0[r], d[r], part);
+        for (int r = 0; r < NPL; ++r) part = fma(jj0[r], K.d[r], part);
         double jd = warp_sum(part);
         double s = (ff0 - fmu) / alpha - jd / beta;
 #pragma unroll
-        for (int r = 0; r < NPL; ++r) J[r] = jj0[r] + s * (Hd[r] / beta);
+        for (int r = 0; r < NPL; ++r) J[r] = jj0[r] + s * (K.Hd[r] / beta);
     }
     if (M.use_scales) {
 #pragma unroll
         for (int r = 0; r < NPL; ++r) J[r] = J[r] / M.sdiff[lane + 32 * r];
     }
+}
+
+template <int NPL>
+__device__ __forceinline__ void module_fg(const DevModel &M, int o, const double (&xo)[NPL], int lane,
+                                          double *xsm, double *dsm, double &f, double (&J)[NPL])
+{
+    ModuleCtx<NPL> K;
+    module_prepare<NPL>(M, xo, lane, xsm, dsm, K);
+    module_output<NPL>(M, o, K, lane, xsm, f, J);
+    __syncwarp();
 }
 
 // transforms/_constraint.pyx:133-221 for one coordinate: value, first and second derivative of to_original
@@ -251,12 +272,15 @@ __device__ __forceinline__ void density_eval(const DevModel &M, const double (&x
         double acc = 0., gs[NPL];
 #pragma unroll
         for (int r = 0; r < NPL; ++r) gs[r] = 0.;
+        ModuleCtx<NPL> K;
+        module_prepare<NPL>(M, xo, lane, xsm, dsm, K);
         for (int o = 0; o < M.m; ++o) {
-            module_fg<NPL>(M, o, xo, lane, xsm, dsm, f, J);
+            module_output<NPL>(M, o, K, lane, xsm, f, J);
             acc = fma(f, f, acc);
 #pragma unroll
             for (int r = 0; r < NPL; ++r) gs[r] = fma(-f, J[r], gs[r]);
         }
+        __syncwarp();
         f = M.e_c0 - 0.5 * acc;
 #pragma unroll
         for (int r = 0; r < NPL; ++r) grad[r] = gs[r] * tj[r];

@@ -1,0 +1,51 @@
+"""DES-Y1-shaped two-module pipeline: n = 26 parameters -> m block-quadratic surrogate outputs (masked
+configs, examples/des-y1-w-cosmosis.ipynb cells 12-18) -> Gaussian likelihood with a dense inverse covariance.  Measures the
+batched pipeline evaluation and a NUTS run on the generic kernels; the oracle port on the host cores runs beside it."""
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+import numpy as np
+from bayesfast_b200 import _cabi
+from bayesfast_b200.density import whiten_spec, GaussianLikelihood
+from _specs import to_device_spec
+n = 26
+m = int(sys.argv[1]) if len(sys.argv) > 1 else 457
+C = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
+rng = np.random.default_rng(0)
+nb = 8                                                  # blocks of outputs, each a quadratic in 10 of the 26 inputs
+edges = np.linspace(0, m, nb + 1).astype(int)
+cfgs = [dict(order='linear', input_mask=np.arange(n), output_mask=np.arange(m),
+             coef=np.concatenate((rng.normal(size=(m, 1)) * 0.1, rng.normal(size=(m, n)) * 0.3), axis=1))]
+for b in range(nb):
+    im = np.sort(rng.choice(n, size=10, replace=False))
+    k = edges[b + 1] - edges[b]
+    cfgs.append(dict(order='quadratic', input_mask=im, output_mask=np.arange(edges[b], edges[b + 1]),
+                     coef=np.triu(rng.normal(size=(k, 10, 10))) * 0.03))
+B = rng.normal(size=(m, m))
+ep = dict(d=rng.normal(size=m) * 0.1, cinv=(B @ B.T / m + 0.5 * np.eye(m)) * (26. / m), c0=0.)
+spec = dict(n=n, m=m, configs=cfgs, use_bound=False, input_scales=None, use_decay=False, transform_ranges=None, epilogue=ep)
+h = _cabi.Handle(0)
+h.set_model(whiten_spec(to_device_spec(spec), GaussianLikelihood(ep['d'], ep['cinv'], ep['c0'])))
+X = rng.normal(size=(65536, n)) * 0.3
+for rep in range(3):
+    lp, g = h.logp_and_grad_batch(X)
+    ms = h.last_kernel_ms()
+print('pipeline eval: n=%d m=%d  %d points  %.2f ms  %.3e points/s' % (n, m, X.shape[0], ms, X.shape[0] / ms * 1e3), flush=True)
+cfg = dict(n_warmup=100, max_treedepth=10, n_int_step=0, max_change=1000., adapt_step_size=1, target_accept=0.8, gamma=0.05,
+           k=0.75, t0=10., adapt_metric=1, initial_weight=10., adapt_window=60, update_window=1, doubling=1, seed=1, chain0=0)
+x0 = rng.normal(size=(C, n)) * 0.2
+h.sampler_init(cfg, x0, 1. / n**0.25, np.ones(n), x0)
+r = h.sampler_run('NUTS', 200, out_ptrs={})
+ms = h.last_kernel_ms()
+print('pipeline NUTS (%s kernel): %d chains x 200 iterations  %.1f ms  %.3e leapfrogs/s  mean tree size %.2f' % (
+    h.sampler_last_path(), C, ms, r['total_tree_size'] / ms * 1e3, r['total_tree_size'] / (C * 200.)), flush=True)
+if '--cpu' in sys.argv:
+    from oracle import bf_oracle
+    bf_oracle.build()
+    od = bf_oracle.OracleDensity(spec)
+    t0 = time.time()
+    lpo, go = od.logp_and_grad_batch(X[:8192])
+    dt = time.time() - t0
+    print('oracle port, %d host threads: %.3e points/s; max rel diff logp %.1e grad %.1e' % (
+        os.cpu_count(), 8192 / dt, np.max(np.abs(lp[:8192] - lpo) / np.abs(lpo)), np.max(np.abs(g[:8192] - go)) / np.max(np.abs(go))))
