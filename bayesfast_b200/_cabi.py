@@ -91,6 +91,7 @@ def lib():
             L.bfb_fp64_peak.argtypes = [C.c_void_p, C.c_int, _dp]
             L.bfb_dmma_issue_test.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _dp]
             L.bfb_sampler_last_path.argtypes = [C.c_void_p]
+            L.bfb_eval_last_path.argtypes = [C.c_void_p]
             for name, args, res in (
                     ('bfb_fit_accumulate', [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int], C.c_int),
                     ('bfb_fit_buffer_size', [C.c_void_p], C.c_int64),
@@ -312,6 +313,10 @@ class Handle:
     def sampler_last_path(self):
         """kernel family of the last sampler run: 'generic', 'fast' (FMA multi-chain) or 'dmma' (FP64 tensor core)"""
         return {0: 'generic', 1: 'fast', 2: 'dmma'}.get(int(self._L.bfb_sampler_last_path(self._h)), 'none')
+
+    def eval_last_path(self):
+        """evaluator of the last logp_and_grad_batch: 'generic', 'dmma' or 'lik_dmma' (tensor-core likelihood pipeline)"""
+        return {0: 'generic', 2: 'dmma', 3: 'lik_dmma'}.get(int(self._L.bfb_eval_last_path(self._h)), 'none')
 
     def dmma_issue_test(self, nacc, src, warps_per_sm):
         v = C.c_double(0)

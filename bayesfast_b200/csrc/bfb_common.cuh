@@ -138,6 +138,9 @@ struct bfb_context {
     size_t queue_len;
     int last_path;             // kernel family of the last sampler launch: 0 generic, 1 FMA multi-chain, 2 tensor core
     int64_t iters_done;        // iterations completed by every chain since bfb_sampler_init / reset
+    double *lik_tab;           // operand table of the tensor-core likelihood evaluator (bfb_lik_dmma.cu), or null
+    int lik_nr;
+    int last_eval_path;        // evaluator of the last bfb_logp_and_grad_batch: 0 generic, 2 tensor core, 3 tensor-core likelihood pipeline
     double *gstack;            // deep NUTS stack levels of the multi-chain kernel (L2 resident)
     size_t gstack_len;
     // fit

@@ -4,6 +4,8 @@
 #include "bfb_eval.cuh"
 #include "bfb_dmma.cuh"
 int bfb_launch_eval_dmma(bfb_context *h, const double *X, int64_t C, double *LP, double *G);
+int bfb_launch_lik_dmma(bfb_context *h, const double *X, int64_t C, double *LP, double *G);   // bfb_lik_dmma.cu
+int bfb_build_lik_table(bfb_context *h);
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
@@ -59,6 +61,7 @@ extern "C" int bfb_create(int device, bfb_handle *out)
     h->has_model = false;
     h->has_chains = false;
     h->dense_metric = false;
+    h->lik_tab = nullptr; h->lik_nr = 0; h->last_eval_path = -1;
     h->fit = nullptr;
     h->gstack = nullptr;
     h->gstack_len = 0;
@@ -171,6 +174,7 @@ int bfb_upload_model(bfb_context *h)
     BFB_CUDA(cudaSetDevice(h->device));
     BFB_CUDA(cudaStreamSynchronize(h->stream));
     bfb_free_list(h->model_allocs);
+    h->lik_tab = nullptr; h->lik_nr = 0;
     const int n = h->n, m = h->m, np = h->np;
     DevModel &D = h->dm;
     memset(&D, 0, sizeof(D));
@@ -413,6 +417,7 @@ extern "C" int bfb_set_epilogue(bfb_handle h, int kind, double c0)
     h->dm.epilogue = kind;
     h->dm.e_c0 = kind ? c0 : 0.;
     if (kind) h->dm.frag_nr = 0;
+    if (kind && !h->lik_tab) return bfb_build_lik_table(h);      // tensor-core evaluator of the pipeline, if it applies
     return BFB_OK;
 }
 
@@ -562,8 +567,11 @@ extern "C" int bfb_logp_and_grad_batch(bfb_handle h, const double *X, int64_t C,
     int blocks = (int)(blocks64 < (int64_t)h->sm_count * 16 ? blocks64 : (int64_t)h->sm_count * 16);
     size_t smem = sizeof(double) * wpb * 2 * h->np;
     BFB_CUDA(cudaEventRecord(h->ev0, h->stream));
-    rc = bfb_launch_eval_dmma(h, (const double *)bx.dev, C, (double *)bl.dev, (double *)bg.dev);
+    rc = bfb_launch_lik_dmma(h, (const double *)bx.dev, C, (double *)bl.dev, (double *)bg.dev);
+    h->last_eval_path = 3;
+    if (rc == 1) { rc = bfb_launch_eval_dmma(h, (const double *)bx.dev, C, (double *)bl.dev, (double *)bg.dev); h->last_eval_path = 2; }
     if (rc < 0) return rc;
+    if (rc == 1) h->last_eval_path = 0;
     if (rc == 1) {
     switch (npl) {
     case 1: density_eval_kernel<1><<<blocks, 32 * wpb, smem, h->stream>>>(h->dm, (const double *)bx.dev, C, (double *)bl.dev, (double *)bg.dev); break;
@@ -581,6 +589,11 @@ extern "C" int bfb_logp_and_grad_batch(bfb_handle h, const double *X, int64_t C,
     BFB_CUDA(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
     release(bx); release(bl); release(bg);
     return BFB_OK;
+}
+
+extern "C" int bfb_eval_last_path(bfb_handle h)
+{
+    return h ? h->last_eval_path : -1;
 }
 
 // ----------------------------------------------------------------------------------------------

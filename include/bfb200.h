@@ -89,6 +89,9 @@ int bfb_poly_eval_batch(bfb_handle h, const double *X, int64_t C, double *F, dou
  * replaces core/density.py:724-754 (+ Pipeline.fun_and_jac :487-566) for a surrogate-only density whose
  * logp is output 0 of the PolyModel.  X [C,n] -> logp [C], grad [C,n]. */
 int bfb_logp_and_grad_batch(bfb_handle h, const double *X, int64_t C, double *logp, double *grad, int loc);
+/* which evaluator served the last bfb_logp_and_grad_batch: 0 = generic warp-per-point (bfb_eval.cuh), 2 = FP64 tensor core
+ * (bfb_eval_dmma.cu), 3 = tensor-core likelihood pipeline (bfb_lik_dmma.cu); -1 before the first call */
+int bfb_eval_last_path(bfb_handle h);
 
 /* Second module of a two-module pipeline (core/density.py:487-566; examples/2d-donut.ipynb f_1, the chi^2 module of
  * examples/des-y1-w-cosmosis.ipynb): kind 1 = Gaussian likelihood logp = c0 - 1/2 sum_o f_o^2 of the m outputs of the model

@@ -120,3 +120,64 @@ def test_multi_output_likelihood_vs_oracle(handle, oracle):
     for k in INT_STATS:
         assert np.array_equal(out[k], ref[k]), k
     check_floats(out['samples'], ref['samples'], 'samples')
+
+
+def _lik_spec(rng, n, m, with_bound=False):
+    """block-quadratic masked surrogate (DES-Y1 shape) + dense inverse covariance"""
+    nb = max(1, m // 10)
+    edges = np.linspace(0, m, nb + 1).astype(int)
+    cfgs = [dict(order='linear', input_mask=np.arange(n), output_mask=np.arange(m),
+                 coef=np.concatenate((rng.normal(size=(m, 1)) * 0.2, rng.normal(size=(m, n)) * 0.4), axis=1))]
+    for b in range(nb):
+        k, ni = edges[b + 1] - edges[b], min(n, 6)
+        cfgs.append(dict(order='quadratic', input_mask=np.sort(rng.choice(n, size=ni, replace=False)),
+                         output_mask=np.arange(edges[b], edges[b + 1]), coef=np.triu(rng.normal(size=(k, ni, ni))) * 0.1))
+    B = rng.normal(size=(m, m))
+    ep = dict(d=rng.normal(size=m) * 0.2, cinv=B @ B.T / m + 0.3 * np.eye(m), c0=-0.5)
+    spec = dict(n=n, m=m, configs=cfgs, use_bound=False, input_scales=None, use_decay=False, transform_ranges=None, epilogue=ep)
+    if with_bound:
+        spec.update(use_bound=True, mu=np.zeros(n), hess=np.eye(n), alpha=1.5, f_mu=rng.normal(size=m))
+    return spec
+
+
+@pytest.mark.parametrize('n,m,C', [(26, 61, 1000), (12, 40, 7), (30, 9, 129), (16, 33, 1), (5, 3, 64)])
+def test_likelihood_tensor_core_evaluator(handle, oracle, monkeypatch, n, m, C):
+    """lik_eval_dmma_kernel (bfb_lik_dmma.cu: the outputs' S_o x as one DMMA GEMM per 8 points, operand chunks staged in
+    shared memory) against the oracle and against the generic kernel, ragged point counts included"""
+    from bayesfast_b200.density import whiten_spec, GaussianLikelihood
+    rng = np.random.default_rng(100 + n + m)
+    spec = _lik_spec(rng, n, m)
+    ep = spec['epilogue']
+    w = whiten_spec(to_device_spec(spec), GaussianLikelihood(ep['d'], ep['cinv'], ep['c0']))
+    X = rng.normal(size=(C, n)) * 0.6
+    lpo, go = oracle.OracleDensity(spec).logp_and_grad_batch(X)
+    handle.set_model(w)
+    lp, g = handle.logp_and_grad_batch(X)
+    assert handle.eval_last_path() == 'lik_dmma'
+    monkeypatch.setenv('BFB200_EVAL', 'generic')
+    lpg, gg = handle.logp_and_grad_batch(X)
+    assert handle.eval_last_path() == 'generic'
+    monkeypatch.delenv('BFB200_EVAL')
+    for a, b in ((lp, lpo), (lpg, lpo)):
+        assert np.allclose(a, b, rtol=1e-10, atol=1e-10)
+    for a, b in ((g, go), (gg, go)):
+        assert np.allclose(a, b, rtol=1e-10, atol=1e-10 * np.abs(go).max())
+    # small staging chunks (several chunks per pass, a ragged last one) give the same bits
+    monkeypatch.setenv('BFB200_LIK_CHUNK', '4')
+    lp2, g2 = handle.logp_and_grad_batch(X)
+    assert np.array_equal(lp2, lp) and np.array_equal(g2, g)
+
+
+def test_likelihood_with_bound_takes_generic_kernel(handle, oracle):
+    """a radial bound (poly.py:466-503) applies to every output: such a model stays on the generic evaluator and still matches"""
+    from bayesfast_b200.density import whiten_spec, GaussianLikelihood
+    rng = np.random.default_rng(4)
+    spec = _lik_spec(rng, 8, 12, with_bound=True)
+    ep = spec['epilogue']
+    handle.set_model(whiten_spec(to_device_spec(spec), GaussianLikelihood(ep['d'], ep['cinv'], ep['c0'])))
+    X = rng.normal(size=(40, 8)) * 0.9              # radius 1.5: a good part of the points is outside
+    lp, g = handle.logp_and_grad_batch(X)
+    assert handle.eval_last_path() == 'generic'
+    lpo, go = oracle.OracleDensity(spec).logp_and_grad_batch(X)
+    assert np.sum(np.linalg.norm(X, axis=1) > 1.5) > 5
+    assert np.allclose(lp, lpo, rtol=1e-10, atol=1e-10) and np.allclose(g, go, rtol=1e-10, atol=1e-10 * np.abs(go).max())
