@@ -68,6 +68,9 @@ struct DevModel {
     // logp = e_c0 - 1/2 sum_o f_o^2
     int epilogue;
     double e_c0;
+    // operand table of the tensor-core likelihood pipeline (bfb_lik_dmma.cu: one record per output), or null
+    const double *lik_tab;
+    int lik_nr;
 };
 
 struct HostConfig {

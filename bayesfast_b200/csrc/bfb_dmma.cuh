@@ -26,9 +26,13 @@
 // bit 2 = cubic-3 configs present: the gradient of P3 = sum_(j<k<l) a_jkl x_j x_k x_l is the GEMM
 // [chains x pairs (k<l)] . [pairs x n] of the pair products x_k x_l with T[(k,l)][j] = a_sorted(j,k,l) (0 if j in {k,l});
 // its operand table (k-tiles x N3T tiles) follows the per-dimension tables in shared memory, P3 = (sum_j x_j dP3/dx_j) / 3
+// bit 3 = likelihood pipeline (bfb_set_epilogue, bfb_lik_dmma.cu): logp = c0 - 1/2 sum_o f_o^2 over the m pre-whitened
+// quadratic outputs; the m n x n operand is streamed from L2 (one record per output), nothing is staged in shared memory.
+__host__ __device__ constexpr int lik_rec_doubles(int NR) { return NR * ((NR + 1) / 2) * 32 + 40; }   // fragments | lin[32] | c0 | pad
+
 template <int NR, int MV>
 struct DmmaShape {
-    static constexpr bool C2 = MV & 1, EXT = (MV & 2) != 0, C3 = (MV & 4) != 0;
+    static constexpr bool C2 = MV & 1, EXT = (MV & 2) != 0, C3 = (MV & 4) != 0, LIK = (MV & 8) != 0;
     static constexpr int N3T = (NR + 1) / 2;              // output tiles of the cubic-3 GEMM
     static constexpr int TX = C2 ? NR : (NR + 1) / 2;     // tiles of the block multiplying x
     static constexpr int T2 = C2 ? (NR + 1) / 2 : 0;      // tiles multiplying x^2
@@ -38,7 +42,7 @@ struct DmmaShape {
     static constexpr int NT = TX + T2 + TD + TD2;
     static constexpr int MSM_DOUBLES = EXT ? 288 : 64;    // per-dimension tables staged next to the operand table
     static constexpr int NTP = (NT + 1) / 2;              // tile pairs: the B fragments of two tiles are one 16-byte load
-    static constexpr int FRAG_DOUBLES = NR * NTP * 64;
+    static constexpr int FRAG_DOUBLES = LIK ? 0 : NR * NTP * 64;
 };
 
 inline int bfb_frag_tiles(int nr, bool c2, bool ext) { return (c2 ? nr : (nr + 1) / 2) + (c2 ? (nr + 1) / 2 : 0) + (ext ? 2 : 1) * ((nr + 1) / 2); }
@@ -116,6 +120,10 @@ struct DmmaConsts {
     double d_alpha2, d_gamma;
     int use_transform, use_scales, use_decay;
     int c3_kt;          // k-tiles of the cubic-3 GEMM (pairs / 4, rounded up)
+    // likelihood pipeline
+    const double *lik_tab;
+    int m;
+    double e_c0;
 };
 
 __device__ __forceinline__ DmmaConsts dmma_consts(const DevModel &M)
@@ -126,6 +134,7 @@ __device__ __forceinline__ DmmaConsts dmma_consts(const DevModel &M)
     K.d_alpha2 = M.d_alpha2; K.d_gamma = M.d_gamma;
     K.use_transform = M.use_transform; K.use_scales = M.use_scales; K.use_decay = M.use_decay;
     K.c3_kt = M.c3_kt;
+    K.lik_tab = M.lik_tab; K.m = M.m; K.e_c0 = M.e_c0;
     return K;
 }
 
@@ -166,6 +175,40 @@ __device__ __forceinline__ void dmma_logp_grad(const double *bsm, int lane, cons
 {
     using SH = DmmaShape<NR, MV>;
     constexpr bool C2 = SH::C2, EXT = SH::EXT;
+    if constexpr (SH::LIK) {
+        // likelihood pipeline: y_o = S_o x for every output as DMMAs against the output's record in L2 (the 8 points of the warp
+        // are the rows), f_o by one quad reduction, sum f_o^2 and the gradient accumulated on the fly (bfb_lik_dmma.cu)
+        constexpr int NT4 = (NR + 1) / 2, REC = lik_rec_doubles(NR), OL = NR * NT4 * 32;
+        const int lg_ = lane & 3;
+        double acc2 = 0.;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) gn[r] = 0.;
+        const double *rec = K.lik_tab + lane;
+#pragma unroll 1
+        for (int o = 0; o < K.m; ++o, rec += REC) {
+            double a_[NT4][2];
+#pragma unroll
+            for (int t = 0; t < NT4; ++t) a_[t][0] = a_[t][1] = 0.;
+#pragma unroll
+            for (int kt = 0; kt < NR; ++kt)
+#pragma unroll
+                for (int t = 0; t < NT4; ++t) dmma884(a_[t][0], a_[t][1], x_in[kt], __ldg(rec + (kt * NT4 + t) * 32));
+            double fpart = 0., jr[NR];
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+                const double l_ = __ldg(rec - lane + OL + 4 * r + lg_), y_ = a_[r / 2][r % 2];
+                fpart = fma(fma(0.5, y_, l_), x_in[r], fpart);
+                jr[r] = l_ + y_;
+            }
+            const double f_ = __ldg(rec - lane + OL + 32) + qsum(fpart);
+            acc2 = fma(f_, f_, acc2);
+#pragma unroll
+            for (int r = 0; r < NR; ++r) gn[r] = fma(-f_, jr[r], gn[r]);
+        }
+        lp = K.e_c0 - 0.5 * acc2;
+        ke = qsum(ke_of(gn));
+        return;
+    }
     const double *mu_t = msm, *lin_t = msm + 32;
     const int lg = lane & 3;
     double acc[SH::NT][2];

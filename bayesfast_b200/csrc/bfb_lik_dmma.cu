@@ -17,7 +17,6 @@
 #include <cstring>
 #include <cstdlib>
 
-__host__ __device__ constexpr int lik_rec_doubles(int NR) { return NR * ((NR + 1) / 2) * 32 + 40; }   // fragments | lin[32] | c0 | pad
 
 template <int NR, int PG>
 __global__ void __launch_bounds__(128) lik_eval_dmma_kernel(const double *__restrict__ tab, int m, int n, double e_c0, int chunk,
@@ -125,6 +124,7 @@ int bfb_build_lik_table(bfb_context *h)
     h->model_allocs.push_back(p);
     BFB_CUDA(cudaMemcpy(p, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice));
     h->lik_tab = (double *)p; h->lik_nr = nr;
+    M.lik_tab = h->lik_tab; M.lik_nr = nr;          // the sampler kernels read the table through the model (bfb_dmma.cuh, MV bit 3)
     return BFB_OK;
 }
 

@@ -867,6 +867,16 @@ int bfb_launch_hmc_dmma_headline(bfb_context *h, const bfb_run_out &o, int n_ite
 int bfb_launch_hmc_dmma(bfb_context *h, const bfb_run_out &o, int n_iter)
 {
     const DevModel &M = h->dm;
+    if (M.epilogue) {                       // likelihood pipeline (model variant bit 3): operand streamed from L2
+        if (!M.lik_tab) return 1;
+        if (const char *e = getenv("BFB200_SAMPLER")) { if (strcmp(e, "dmma")) return 1; }
+        switch (M.lik_nr) {
+        case 4: return launch_hmc_dmma_w<4, 8>(h, o, n_iter);
+        case 7: return launch_hmc_dmma_w<7, 8>(h, o, n_iter);
+        case 8: return launch_hmc_dmma_w<8, 8>(h, o, n_iter);
+        }
+        return 1;
+    }
     if (M.frag_nr == 0 || (M.has_c3 && (M.c3_kt == 0 || !M.has_c2))) return 1;
     if (const char *e = getenv("BFB200_SAMPLER")) { if (strcmp(e, "dmma")) return 1; }
     const int mv = (M.has_c2 ? 1 : 0) | (M.frag_ext ? 2 : 0) | (M.has_c3 ? 4 : 0);
@@ -961,6 +971,16 @@ int bfb_launch_nuts_dmma_headline(bfb_context *h, const bfb_run_out &o, int n_it
 int bfb_launch_nuts_dmma(bfb_context *h, const bfb_run_out &o, int n_iter)
 {
     const DevModel &M = h->dm;
+    if (M.epilogue) {                       // likelihood pipeline (model variant bit 3): operand streamed from L2
+        if (!M.lik_tab || h->scfg.max_treedepth > 10) return 1;
+        if (const char *e = getenv("BFB200_SAMPLER")) { if (strcmp(e, "dmma")) return 1; }
+        switch (M.lik_nr) {
+        case 4: return launch_dmma_w<4, 8>(h, o, n_iter);
+        case 7: return launch_dmma_w<7, 8>(h, o, n_iter);
+        case 8: return launch_dmma_w<8, 8>(h, o, n_iter);
+        }
+        return 1;
+    }
     if (M.frag_nr == 0 || (M.has_c3 && (M.c3_kt == 0 || !M.has_c2))) return 1;
     if (h->scfg.max_treedepth > 10) return 1;
     if (const char *e = getenv("BFB200_SAMPLER")) { if (strcmp(e, "dmma")) return 1; }

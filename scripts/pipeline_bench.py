@@ -35,11 +35,20 @@ print('pipeline eval: n=%d m=%d  %d points  %.2f ms  %.3e points/s' % (n, m, X.s
 cfg = dict(n_warmup=100, max_treedepth=10, n_int_step=0, max_change=1000., adapt_step_size=1, target_accept=0.8, gamma=0.05,
            k=0.75, t0=10., adapt_metric=1, initial_weight=10., adapt_window=60, update_window=1, doubling=1, seed=1, chain0=0)
 x0 = rng.normal(size=(C, n)) * 0.2
-h.sampler_init(cfg, x0, 1. / n**0.25, np.ones(n), x0)
-r = h.sampler_run('NUTS', 200, out_ptrs={})
-ms = h.last_kernel_ms()
-print('pipeline NUTS (%s kernel): %d chains x 200 iterations  %.1f ms  %.3e leapfrogs/s  mean tree size %.2f' % (
-    h.sampler_last_path(), C, ms, r['total_tree_size'] / ms * 1e3, r['total_tree_size'] / (C * 200.)), flush=True)
+flops = m * (2. * n * n + 5. * n) + 9. * n          # algorithmic flops per evaluation / leapfrog (S_o x, f_o, gradient accumulation)
+print('  = %.2f TFLOP/s algorithmic' % (X.shape[0] / ms * 1e3 * flops / 1e12), flush=True)
+for fam in ('dmma', 'generic'):
+    os.environ['BFB200_SAMPLER'] = fam
+    for sampler, kw in (('NUTS', {}), ('HMC', {'n_int_step': 16})):
+        if fam == 'generic' and sampler == 'HMC':
+            continue
+        h.sampler_init(dict(cfg, **kw), x0, 1. / n**0.25 if sampler == 'NUTS' else 0.2, np.ones(n), x0)
+        r = h.sampler_run(sampler, 200, out_ptrs={})
+        ms = h.last_kernel_ms()
+        print('pipeline %s (%s kernel): %d chains x 200 iterations  %.1f ms  %.3e leapfrogs/s = %.2f TFLOP/s  mean tree size %.2f' % (
+            sampler, h.sampler_last_path(), C, ms, r['total_tree_size'] / ms * 1e3, r['total_tree_size'] / ms * 1e3 * flops / 1e12,
+            r['total_tree_size'] / (C * 200.)), flush=True)
+os.environ.pop('BFB200_SAMPLER')
 if '--cpu' in sys.argv:
     from oracle import bf_oracle
     bf_oracle.build()

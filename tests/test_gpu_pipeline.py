@@ -181,3 +181,35 @@ def test_likelihood_with_bound_takes_generic_kernel(handle, oracle):
     lpo, go = oracle.OracleDensity(spec).logp_and_grad_batch(X)
     assert np.sum(np.linalg.norm(X, axis=1) > 1.5) > 5
     assert np.allclose(lp, lpo, rtol=1e-10, atol=1e-10) and np.allclose(g, go, rtol=1e-10, atol=1e-10 * np.abs(go).max())
+
+
+@pytest.mark.parametrize('n,m,C,sampler', [(26, 30, 40, 'NUTS'), (12, 17, 21, 'NUTS'), (16, 9, 16, 'HMC')])
+def test_likelihood_tensor_core_samplers(handle, oracle, monkeypatch, n, m, C, sampler):
+    """NUTS / HMC of the likelihood pipeline on the tensor-core kernels (model variant bit 3 of bfb_dmma.cuh: the outputs'
+    operand streamed from L2): integer outcomes identical to the oracle fed with the device's own draws and to the generic
+    kernel"""
+    from bayesfast_b200.density import whiten_spec, GaussianLikelihood
+    rng = np.random.default_rng(300 + n + m)
+    spec = _lik_spec(rng, n, m)
+    ep = spec['epilogue']
+    handle.set_model(whiten_spec(to_device_spec(spec), GaussianLikelihood(ep['d'], ep['cinv'], ep['c0'])))
+    n_iter, seed = 30, 909
+    kw = {'n_int_step': 8} if sampler == 'HMC' else {}
+    x0 = rng.normal(size=(C, n)) * 0.3
+    step0 = 0.3 if sampler == 'HMC' else 1. / n**0.25
+    outs = {}
+    for fam in ('dmma', 'generic'):
+        monkeypatch.setenv('BFB200_SAMPLER', fam)
+        handle.sampler_init(cfg_from(kw, n_iter // 2, seed), x0, step0, np.ones(n), x0)
+        outs[fam] = handle.sampler_run(sampler, n_iter)
+        assert handle.sampler_last_path() == fam
+        st = handle.sampler_state()
+        assert np.all(st['status'] == 0)
+    monkeypatch.delenv('BFB200_SAMPLER')
+    U, Z = device_draws(handle, seed, st['n_draws'])
+    ref = oracle.OracleDensity(spec).run(sampler, dict(n_iter=n_iter, n_warmup=n_iter // 2, **kw), x0, step0, np.ones(n),
+                                         draws_u=U, draws_z=Z)
+    for fam in ('dmma', 'generic'):
+        for k in INT_STATS:
+            assert np.array_equal(outs[fam][k], ref[k]), (fam, k)
+        check_floats(outs[fam]['samples'], ref['samples'], fam)
