@@ -43,6 +43,9 @@ struct DmmaShape {
     static constexpr int MSM_DOUBLES = EXT ? 288 : 64;    // per-dimension tables staged next to the operand table
     static constexpr int NTP = (NT + 1) / 2;              // tile pairs: the B fragments of two tiles are one 16-byte load
     static constexpr int FRAG_DOUBLES = LIK ? 0 : NR * NTP * 64;
+    // shared memory in front of the per-dimension tables: the operand table, or (likelihood pipeline) two staged operand
+    // records per warp, filled by the warp itself with cp.async one output ahead of the DMMAs
+    __host__ __device__ static constexpr int frag_doubles(int warps) { return LIK ? warps * 2 * lik_rec_doubles(NR) : FRAG_DOUBLES; }
 };
 
 inline int bfb_frag_tiles(int nr, bool c2, bool ext) { return (c2 ? nr : (nr + 1) / 2) + (c2 ? (nr + 1) / 2 : 0) + (ext ? 2 : 1) * ((nr + 1) / 2); }
@@ -176,34 +179,52 @@ __device__ __forceinline__ void dmma_logp_grad(const double *bsm, int lane, cons
     using SH = DmmaShape<NR, MV>;
     constexpr bool C2 = SH::C2, EXT = SH::EXT;
     if constexpr (SH::LIK) {
-        // likelihood pipeline: y_o = S_o x for every output as DMMAs against the output's record in L2 (the 8 points of the warp
-        // are the rows), f_o by one quad reduction, sum f_o^2 and the gradient accumulated on the fly (bfb_lik_dmma.cu)
+        // likelihood pipeline: y_o = S_o x for every output as DMMAs against the output's record (the 8 points of the warp are
+        // the rows), f_o by one quad reduction, sum f_o^2 and the gradient accumulated on the fly (bfb_lik_dmma.cu).  The
+        // records stream from L2 through two per-warp shared-memory slots: cp.async of output o + 1 runs under the DMMAs of o.
         constexpr int NT4 = (NR + 1) / 2, REC = lik_rec_doubles(NR), OL = NR * NT4 * 32;
         const int lg_ = lane & 3;
+        double *buf = const_cast<double *>(bsm) + (size_t)(threadIdx.x >> 5) * 2 * REC;
+        auto stage = [&](int o) {
+            const double *src = K.lik_tab + (size_t)o * REC;
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(buf + (size_t)(o & 1) * REC);
+#pragma unroll
+            for (int i = 0; i < (REC / 2 + 31) / 32; ++i) {
+                const int e = i * 32 + lane;
+                if (e < REC / 2) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst + 16u * e), "l"(src + 2 * e) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
         double acc2 = 0.;
 #pragma unroll
         for (int r = 0; r < NR; ++r) gn[r] = 0.;
-        const double *rec = K.lik_tab + lane;
+        __syncwarp();
+        stage(0);
 #pragma unroll 1
-        for (int o = 0; o < K.m; ++o, rec += REC) {
+        for (int o = 0; o < K.m; ++o) {
+            if (o + 1 < K.m) { stage(o + 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+            else asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncwarp();
+            const double *rec = buf + (size_t)(o & 1) * REC;
             double a_[NT4][2];
 #pragma unroll
             for (int t = 0; t < NT4; ++t) a_[t][0] = a_[t][1] = 0.;
 #pragma unroll
             for (int kt = 0; kt < NR; ++kt)
 #pragma unroll
-                for (int t = 0; t < NT4; ++t) dmma884(a_[t][0], a_[t][1], x_in[kt], __ldg(rec + (kt * NT4 + t) * 32));
+                for (int t = 0; t < NT4; ++t) dmma884(a_[t][0], a_[t][1], x_in[kt], rec[(kt * NT4 + t) * 32 + lane]);
             double fpart = 0., jr[NR];
 #pragma unroll
             for (int r = 0; r < NR; ++r) {
-                const double l_ = __ldg(rec - lane + OL + 4 * r + lg_), y_ = a_[r / 2][r % 2];
+                const double l_ = rec[OL + 4 * r + lg_], y_ = a_[r / 2][r % 2];
                 fpart = fma(fma(0.5, y_, l_), x_in[r], fpart);
                 jr[r] = l_ + y_;
             }
-            const double f_ = __ldg(rec - lane + OL + 32) + qsum(fpart);
+            const double f_ = rec[OL + 32] + qsum(fpart);
             acc2 = fma(f_, f_, acc2);
 #pragma unroll
             for (int r = 0; r < NR; ++r) gn[r] = fma(-f_, jr[r], gn[r]);
+            __syncwarp();                                  // slot (o & 1) is refilled by the stage() of the next iteration
         }
         lp = K.e_c0 - 0.5 * acc2;
         ke = qsum(ke_of(gn));

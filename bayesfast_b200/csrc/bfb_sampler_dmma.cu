@@ -85,13 +85,13 @@ __global__ void __launch_bounds__(32 * W, 1) nuts_dmma_kernel(DevModel M, bfb_sa
     constexpr int SLOT = NR * 32;
     extern __shared__ double smem[];
     double *bsm = smem;                       // coefficient operand table
-    double *msm = smem + SH::FRAG_DOUBLES;    // per-dimension tables (dmma_stage_tables)
-    for (int i = threadIdx.x; i < SH::FRAG_DOUBLES; i += blockDim.x) bsm[i] = M.bfrag[i];
+    double *msm = smem + SH::frag_doubles(W);    // per-dimension tables (dmma_stage_tables)
+    if (!SH::LIK) { for (int i = threadIdx.x; i < SH::FRAG_DOUBLES; i += blockDim.x) bsm[i] = M.bfrag[i]; }
     dmma_stage_tables<MV>(M, msm);
     __syncthreads();
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, gi = lane >> 2, lg = lane & 3;
     const int c3x = SH::C3 ? dmma_c3_doubles(NR, M.c3_kt, W) : 0;          // cubic-3 operand table, pair table, x scratch
-    double *wsm = smem + SH::FRAG_DOUBLES + SH::MSM_DOUBLES + c3x + (size_t)wib * warp_smem_doubles(NR, LS);
+    double *wsm = smem + SH::frag_doubles(W) + SH::MSM_DOUBLES + c3x + (size_t)wib * warp_smem_doubles(NR, LS);
     double *sTL = wsm, *sTR = wsm + 3 * SLOT, *sPS = wsm + 6 * SLOT, *sPB = wsm + 7 * SLOT, *sST = wsm + 8 * SLOT;
     double *ssc = wsm + (8 + 3 * LS) * SLOT + gi;        // scalar (field f, level l) of this chain at ssc[(f * 10 + l) * 8]
     const int n = M.n;
@@ -605,8 +605,8 @@ __global__ void __launch_bounds__(32 * W, 1) hmc_dmma_kernel(DevModel M, bfb_sam
     using SH = DmmaShape<NR, MV>;
     extern __shared__ double smem[];
     double *bsm = smem;
-    double *msm = smem + SH::FRAG_DOUBLES;    // per-dimension tables (dmma_stage_tables)
-    for (int i = threadIdx.x; i < SH::FRAG_DOUBLES; i += blockDim.x) bsm[i] = M.bfrag[i];
+    double *msm = smem + SH::frag_doubles(W);    // per-dimension tables (dmma_stage_tables)
+    if (!SH::LIK) { for (int i = threadIdx.x; i < SH::FRAG_DOUBLES; i += blockDim.x) bsm[i] = M.bfrag[i]; }
     dmma_stage_tables<MV>(M, msm);
     __syncthreads();
     const int lane = threadIdx.x & 31, gi = lane >> 2, lg = lane & 3;
@@ -805,7 +805,7 @@ static int launch_hmc_dmma(bfb_context *h, const bfb_run_out &o, int n_iter)
     using SH = DmmaShape<NR, MV>;
     const int64_t C = h->cs.C;
     const int n_groups = (int)((C + 7) / 8);
-    const size_t smem = sizeof(double) * (SH::FRAG_DOUBLES + SH::MSM_DOUBLES + (SH::C3 ? dmma_c3_doubles(NR, h->dm.c3_kt, W) : 0));
+    const size_t smem = sizeof(double) * (SH::frag_doubles(W) + SH::MSM_DOUBLES + (SH::C3 ? dmma_c3_doubles(NR, h->dm.c3_kt, W) : 0));
     if (smem > (size_t)(227 * 1024)) return 1;
     BFB_CUDA(cudaFuncSetAttribute(hmc_dmma_kernel<NR, MV, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     RunOutDevF od;
@@ -845,6 +845,7 @@ static int launch_hmc_dmma_w(bfb_context *h, const bfb_run_out &o, int n_iter)
     // 56.0 / 57.9 / 57.9 % with 8 / 12 / 16
     int W = groups > sms * 16 ? 12 : groups > sms * 4 ? 8 : 4;
     if (const char *e = getenv("BFB200_HMC_WARPS_PER_SM")) { int v = atoi(e); if (v == 4 || v == 8 || v == 12 || v == 16) W = v; }
+    if (DmmaShape<NR, MV>::LIK && W > 12) W = 12;        // 2 staged operand records per warp (15 KB): at most 12 warps per block
     else if (const char *e2 = getenv("BFB200_WARPS_PER_SM")) { int v = atoi(e2); if (v == 4 || v == 8) W = v; }
     switch (W) {
     case 16: return launch_hmc_dmma<NR, MV, 16>(h, o, n_iter);
@@ -905,7 +906,7 @@ static int launch_dmma(bfb_context *h, const bfb_run_out &o, int n_iter, int cpg
     // one persistent block of W warps per SM (W = 4: one warp per scheduler, 4096 chains = 512 warps on 592 schedulers;
     // W = 8 when there are more groups than that); the first LS levels of the tree stack live in shared memory, deeper
     // (rarely touched) levels in an L2-resident buffer
-    const size_t fixed = sizeof(double) * (SH::FRAG_DOUBLES + SH::MSM_DOUBLES + (SH::C3 ? dmma_c3_doubles(NR, h->dm.c3_kt, W) : 0));
+    const size_t fixed = sizeof(double) * (SH::frag_doubles(W) + SH::MSM_DOUBLES + (SH::C3 ? dmma_c3_doubles(NR, h->dm.c3_kt, W) : 0));
     if (fixed + sizeof(double) * W * warp_smem_doubles(NR, 1) > (size_t)(227 * 1024)) return 1;      // does not fit: generic kernel
     const size_t budget = (size_t)(227 * 1024) - 1024 - fixed;
     int LS = L;
@@ -961,6 +962,7 @@ static int launch_dmma_w(bfb_context *h, const bfb_run_out &o, int n_iter)
     if (const char *e = getenv("BFB200_CHAINS_PER_GROUP")) { int v = atoi(e); if (v >= 1 && v <= 8) cpg = v; }
     int W = ((C + cpg - 1) / cpg > slots4) ? 8 : 4;
     if (const char *e = getenv("BFB200_WARPS_PER_SM")) { int v = atoi(e); if (v == 4 || v == 8) W = v; }
+    if (DmmaShape<NR, MV>::LIK) W = 4;        // staged operand records + tree state of 8 warps do not fit; the persistent warps queue up
     return W == 8 ? launch_dmma<NR, MV, 8>(h, o, n_iter, cpg) : launch_dmma<NR, MV, 4>(h, o, n_iter, cpg);
 }
 
