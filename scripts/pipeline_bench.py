@@ -12,6 +12,7 @@ from _specs import to_device_spec
 n = 26
 m = int(sys.argv[1]) if len(sys.argv) > 1 else 457
 C = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
+N_IT = int(sys.argv[3]) if len(sys.argv) > 3 and sys.argv[3].isdigit() else 200      # a short run for ncu
 rng = np.random.default_rng(0)
 nb = 8                                                  # blocks of outputs, each a quadratic in 10 of the 26 inputs
 edges = np.linspace(0, m, nb + 1).astype(int)
@@ -32,7 +33,7 @@ for rep in range(3):
     lp, g = h.logp_and_grad_batch(X)
     ms = h.last_kernel_ms()
 print('pipeline eval: n=%d m=%d  %d points  %.2f ms  %.3e points/s' % (n, m, X.shape[0], ms, X.shape[0] / ms * 1e3), flush=True)
-cfg = dict(n_warmup=100, max_treedepth=10, n_int_step=0, max_change=1000., adapt_step_size=1, target_accept=0.8, gamma=0.05,
+cfg = dict(n_warmup=N_IT // 2, max_treedepth=10, n_int_step=0, max_change=1000., adapt_step_size=1, target_accept=0.8, gamma=0.05,
            k=0.75, t0=10., adapt_metric=1, initial_weight=10., adapt_window=60, update_window=1, doubling=1, seed=1, chain0=0)
 x0 = rng.normal(size=(C, n)) * 0.2
 flops = m * (2. * n * n + 5. * n) + 9. * n          # algorithmic flops per evaluation / leapfrog (S_o x, f_o, gradient accumulation)
@@ -43,11 +44,11 @@ for fam in ('dmma', 'generic'):
         if fam == 'generic' and sampler == 'HMC':
             continue
         h.sampler_init(dict(cfg, **kw), x0, 1. / n**0.25 if sampler == 'NUTS' else 0.2, np.ones(n), x0)
-        r = h.sampler_run(sampler, 200, out_ptrs={})
+        r = h.sampler_run(sampler, N_IT, out_ptrs={})
         ms = h.last_kernel_ms()
-        print('pipeline %s (%s kernel): %d chains x 200 iterations  %.1f ms  %.3e leapfrogs/s = %.2f TFLOP/s  mean tree size %.2f' % (
-            sampler, h.sampler_last_path(), C, ms, r['total_tree_size'] / ms * 1e3, r['total_tree_size'] / ms * 1e3 * flops / 1e12,
-            r['total_tree_size'] / (C * 200.)), flush=True)
+        print('pipeline %s (%s kernel): %d chains x %d iterations  %.1f ms  %.3e leapfrogs/s = %.2f TFLOP/s  mean tree size %.2f' % (
+            sampler, h.sampler_last_path(), C, N_IT, ms, r['total_tree_size'] / ms * 1e3, r['total_tree_size'] / ms * 1e3 * flops / 1e12,
+            r['total_tree_size'] / (C * float(N_IT))), flush=True)
 os.environ.pop('BFB200_SAMPLER')
 if '--cpu' in sys.argv:
     from oracle import bf_oracle
