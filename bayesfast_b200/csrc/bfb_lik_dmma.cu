@@ -8,7 +8,8 @@
 // lane lg owns the dimensions 4 r + lg, which is both the A fragment and -- with the columns of S_o ordered on the host --
 // the C fragment).  The m n x n operand (3.3 MB at n = 26, m = 457) does not fit shared memory: the warps of a block walk
 // over the outputs in step, chunks of outputs are staged in shared memory by the whole block, and every warp evaluates PG
-// groups of 8 points against a staged chunk, so the table is read from L2 once per 32 PG points.  y_o never leaves the
+// groups of 8 points against a staged chunk, so the table is read from L2 once per 32 PG points; the chunks alternate between two
+// buffers filled with cp.async, the copy of chunk k + 1 running under the DMMAs of chunk k.  y_o never leaves the
 // registers: f_o (one quad reduction), sum f_o^2 and the gradient accumulate on the fly.
 //
 // Applies to linear + quadratic configs, n <= 32, no radial bound / rescale / decay / transform; everything else runs
@@ -38,18 +39,27 @@ __global__ void __launch_bounds__(128) lik_eval_dmma_kernel(const double *__rest
 #pragma unroll
             for (int r = 0; r < NR; ++r) { x[g][r] = (4 * r + lg < n) ? X[cc * n + 4 * r + lg] : 0.; gr[g][r] = 0.; }
         }
-        for (int o0 = 0; o0 < m; o0 += chunk) {
-            const int cnt = (m - o0 < chunk) ? m - o0 : chunk;
-            __syncthreads();                                   // the previous chunk has been consumed by every warp
-            {
-                const double2 *src = reinterpret_cast<const double2 *>(tab + (size_t)o0 * REC);
-                double2 *dst = reinterpret_cast<double2 *>(sm);
-                for (int i = threadIdx.x; i < cnt * (REC / 2); i += blockDim.x) dst[i] = src[i];
-            }
-            __syncthreads();
+        // chunks of outputs go through two shared-memory buffers: the cp.async copies of chunk k + 1 run under the DMMAs of chunk k
+        const int n_chunks = (m + chunk - 1) / chunk;
+        auto stage = [&](int k) {
+            const int o0 = k * chunk, cnt = (m - o0 < chunk) ? m - o0 : chunk;
+            const double *src = tab + (size_t)o0 * REC;
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(sm + (size_t)(k & 1) * chunk * REC);
+            for (int i = threadIdx.x; i < cnt * (REC / 2); i += blockDim.x)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst + 16u * i), "l"(src + 2 * i) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        __syncthreads();                                       // the buffers of the previous pass have been consumed
+        stage(0);
+        for (int k = 0; k < n_chunks; ++k) {
+            const int o0 = k * chunk, cnt = (m - o0 < chunk) ? m - o0 : chunk;
+            if (k + 1 < n_chunks) { stage(k + 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+            else asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads();                                   // chunk k has landed for every thread
+            const double *cbase = sm + (size_t)(k & 1) * chunk * REC;
 #pragma unroll 1
             for (int oo = 0; oo < cnt; ++oo) {
-                const double *rec = sm + (size_t)oo * REC;
+                const double *rec = cbase + (size_t)oo * REC;
                 double acc[PG][NT][2];
 #pragma unroll
                 for (int g = 0; g < PG; ++g)
@@ -78,6 +88,7 @@ __global__ void __launch_bounds__(128) lik_eval_dmma_kernel(const double *__rest
                     for (int r = 0; r < NR; ++r) gr[g][r] = fma(-f, lin[r] + acc[g][r / 2][r % 2], gr[g][r]);
                 }
             }
+            __syncthreads();                                   // buffer k & 1 is refilled by the stage() of the next iteration
         }
 #pragma unroll
         for (int g = 0; g < PG; ++g) {
@@ -132,10 +143,10 @@ template <int NR>
 static int launch_lik(bfb_context *h, const double *X, int64_t C, double *LP, double *G)
 {
     constexpr int PG = 2, REC = lik_rec_doubles(NR);
-    int chunk = (64 * 1024) / (int)(REC * sizeof(double));           // <= 64 KB of staged records: 3 blocks per SM
-    if (const char *e = getenv("BFB200_LIK_CHUNK")) { int v = atoi(e); if (v >= 1 && (size_t)v * REC * sizeof(double) <= 200 * 1024) chunk = v; }
+    int chunk = (32 * 1024) / (int)(REC * sizeof(double));           // 2 buffers of <= 32 KB of staged records: 3 blocks per SM
+    if (const char *e = getenv("BFB200_LIK_CHUNK")) { int v = atoi(e); if (v >= 1 && (size_t)v * REC * sizeof(double) <= 100 * 1024) chunk = v; }
     if (chunk > h->dm.m) chunk = h->dm.m;
-    const size_t smem = sizeof(double) * (size_t)chunk * REC;
+    const size_t smem = sizeof(double) * 2 * (size_t)chunk * REC;
     BFB_CUDA(cudaFuncSetAttribute(lik_eval_dmma_kernel<NR, PG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t want = (C + 32 * PG - 1) / (32 * PG);
     const int64_t cap = (int64_t)h->sm_count * 3;
