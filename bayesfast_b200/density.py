@@ -48,7 +48,7 @@ class GaussianLikelihood:
         lam, V = np.linalg.eigh(0.5 * (ic + ic.T))
         if not np.all(lam >= -1e-12 * max(1., np.abs(lam).max())):
             raise ValueError('inv_cov should be positive semi-definite.')
-        # inv_cov_sym = Lt^T Lt  (rows of zero eigenvalues dropped later is not needed: they contribute nothing)
+        # symmetric part of inv_cov = Lt^T Lt (rows belonging to zero eigenvalues are zero and contribute nothing)
         self._lt = np.sqrt(np.clip(lam, 0., None))[:, None] * V.T
 
     output_size = property(lambda self: self.mean.size)

@@ -4,7 +4,7 @@ true log-density, training points for the surrogate fit and chain starting point
 """
 import numpy as np
 
-__all__ = ['des_shaped', 'correlated_gaussian', 'n_param']
+__all__ = ['des_shaped', 'correlated_gaussian', 'des_pipeline', 'n_param']
 
 
 def n_param(order, n):
@@ -58,3 +58,32 @@ def correlated_gaussian(n=16, seed=0, n_fit_mult=4, n_chain=4096, order='cubic-2
     x_fit = (L @ rng.normal(size=(n, N))).T
     x_0 = (L @ rng.normal(size=(n, n_chain))).T
     return dict(n=n, order=order, logp=logp, x_fit=x_fit, y_fit=logp(x_fit)[:, None], x_0=x_0, cov=cov, P=P)
+
+
+def des_pipeline(n=26, m=457, seed=0, n_blocks=8, n_in=10):
+    """
+    DES-Y1-shaped two-module pipeline (examples/des-y1-w-cosmosis.ipynb cells 12-18): m surrogate outputs in `n_blocks` blocks,
+    each a quadratic in `n_in` of the n inputs (masked configs) on top of a full linear config, followed by a Gaussian
+    likelihood with a dense inverse covariance.  Returns (spec, GaussianLikelihood): the spec carries dense `coef` (oracle),
+    `packed` (C ABI) and the un-whitened `epilogue`.
+    """
+    from .density import GaussianLikelihood
+    from .poly import pack_dense
+    rng = np.random.default_rng(seed)
+    edges = np.linspace(0, m, n_blocks + 1).astype(int)
+    lin = np.concatenate((rng.normal(size=(m, 1)) * 0.1, rng.normal(size=(m, n)) * 0.3), axis=1)
+    cfgs = [dict(order='linear', input_mask=np.arange(n), output_mask=np.arange(m), coef=lin, packed=lin.copy())]
+    for b in range(n_blocks):
+        k = edges[b + 1] - edges[b]
+        if k == 0:
+            continue
+        ni = min(n_in, n)
+        q = np.triu(rng.normal(size=(k, ni, ni))) * 0.03
+        cfgs.append(dict(order='quadratic', input_mask=np.sort(rng.choice(n, size=ni, replace=False)),
+                         output_mask=np.arange(edges[b], edges[b + 1]), coef=q,
+                         packed=np.array([pack_dense('quadratic', qi, ni) for qi in q])))
+    B = rng.normal(size=(m, m))
+    lik = GaussianLikelihood(rng.normal(size=m) * 0.1, (B @ B.T / m + 0.5 * np.eye(m)) * (float(n) / m), 0.)
+    spec = dict(n=n, m=m, configs=cfgs, use_bound=False, input_scales=None, use_decay=False, transform_ranges=None,
+                epilogue=lik.to_spec())
+    return spec, lik

@@ -13,6 +13,8 @@ data-path collective.  The dominant kernel is nuts_dmma_kernel (bfb_sampler_dmma
 FP64 m8n8k4 DMMAs).  4096 chains are 512 warps -- fewer than the 592 warp schedulers of a B200 -- so the line also
 carries `more_chains` (north_star: "at least 4096 chains per GPU"): the same run with 16384 chains on this GPU, and
 `eval_kernel`: the batched surrogate evaluation kernel alone (bfb_eval_dmma.cu) against the same FP64 peak.
+`pipeline_kernel`: SURVEY 8f rank 1 -- DES-Y1-shaped surrogate -> Gaussian-likelihood pipeline (n = 26, m = 457 outputs) on the
+tensor cores: batched logp + gradient (bfb_lik_dmma.cu) and a 4096-chain NUTS run (model variant bit 3), same FP64 peak.
 
   value : sum(tree_size) of all ranks / max-over-ranks device time of K steps, inputs resident in HBM
   e2e   : the same through bayesfast_b200.sample() with host x_0 and all samples + stats copied back
@@ -338,6 +340,42 @@ def main():
                                      roofline=dict(bound='tensor', achieved=fe / mse / 1e9, peak=peak, unit='TFLOP/s', frac=fe / mse / 1e9 / peak),
                                      hbm_gbs=Ce * (2 * N_DIM + 1) * 8 / mse / 1e6)
         del Xe, lpe, ge
+        # (c) SURVEY 8f rank 1: DES-Y1-shaped surrogate -> Gaussian-likelihood pipeline (n = 26, m = 457 block-quadratic outputs,
+        # dense inverse covariance) on the tensor cores: batched logp + gradient (bfb_lik_dmma.cu) and NUTS (model variant bit 3)
+        try:
+            from bayesfast_b200 import _cabi
+            from bayesfast_b200.density import whiten_spec
+            pspec, plik = synthetic.des_pipeline(N_DIM, 457, seed=0)
+            hp = _cabi.Handle(dev)
+            hp.set_model(whiten_spec(pspec, plik))
+            Cp = 1 << 16
+            Xp = (torch.randn(Cp, N_DIM, dtype=torch.float64, device='cuda:%d' % dev) * 0.3).contiguous()
+            lpp = torch.empty(Cp, dtype=torch.float64, device='cuda:%d' % dev)
+            gp = torch.empty(Cp, N_DIM, dtype=torch.float64, device='cuda:%d' % dev)
+            torch.cuda.synchronize(dev)
+            msp = []
+            for i in range(5):
+                hp.logp_and_grad_batch_dev(Xp.data_ptr(), Cp, lpp.data_ptr(), gp.data_ptr())
+                msp.append(hp.last_kernel_ms())
+            msp = float(np.mean(msp[1:]))
+            fl = 457 * (2 * N_DIM * N_DIM + 5 * N_DIM) + 9 * N_DIM
+            x0p = np.random.default_rng(1).normal(size=(C, N_DIM)) * 0.2
+            cfgp = bfb.NTrace(n_chain=C, n_iter=200, n_warmup=100, x_0=x0p, random_generator=SEED)._cfg_dict(SEED, 0)
+            hp.sampler_init(cfgp, x0p, 1. / N_DIM**0.25, np.ones(N_DIM), x0p)
+            rp = hp.sampler_run('NUTS', 200, out_ptrs={})
+            msn = hp.last_kernel_ms()
+            extras['pipeline_kernel'] = dict(
+                workload='des_y1_shaped_pipeline_n26_m457_gaussian_likelihood', algorithmic_flops_per_evaluation=fl,
+                eval=dict(kernel='lik_eval_dmma_kernel' if hp.eval_last_path() == 'lik_dmma' else hp.eval_last_path(), points=Cp, ms=msp,
+                          points_per_s=Cp / msp * 1e3, roofline=dict(bound='tensor', achieved=fl * Cp / msp / 1e9, peak=peak,
+                                                                     unit='TFLOP/s', frac=fl * Cp / msp / 1e9 / peak)),
+                nuts=dict(kernel='nuts_%s_kernel' % hp.sampler_last_path(), chains_per_gpu=C, iterations=200, kernel_ms=msn,
+                          value=rp['total_tree_size'] / msn * 1e3, unit='leapfrog-steps*chains/s',
+                          roofline_frac=fl * rp['total_tree_size'] / msn / 1e9 / peak))
+            hp.close()
+            del Xp, lpp, gp
+        except Exception as exc:                                   # supplementary measurement: never fails the bench line
+            extras['pipeline_kernel'] = dict(error=repr(exc))
     out = dict(metric='nuts_leapfrog_steps_x_chains_per_s', value=value, unit='leapfrog-steps*chains/s', n_gpus=world,
                steps=args.steps, warmup=args.warmup, ms_per_step=step_ms / args.steps, higher_is_better=True,
                scaling='weak', vs_baseline=None, dtype='f64', data='synthetic', config=config,
