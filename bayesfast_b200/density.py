@@ -3,10 +3,12 @@ Surrogate-only probability density with the interface of bayesfast.core.density.
 (reference: bayesfast/core/density.py:617-838 on top of Pipeline :205-566 and _PipelineBase :28-157).
 
 The reference's Density chains arbitrary Python modules; only a density whose logp is produced by ONE
-PolyModel surrogate can run on the device, so this class holds exactly that: the surrogate,
+PolyModel surrogate -- directly (output #0), or through one closed-form Gaussian-likelihood module placed after it
+(`GaussianLikelihood`: f_1 of examples/2d-donut.ipynb, the chi-square module of examples/des-y1-w-cosmosis.ipynb) -- can run
+on the device, so this class holds exactly that: the surrogate, the optional likelihood,
 the optional bounded<->unbounded variable transform (input_scales / hard_bounds) and the optional decay
 term.  `Density.from_reference(d)` builds one from a fitted reference Density (duck-typed, no import of the
-reference) and refuses anything that is not surrogate-only.
+reference) and refuses anything else.
 """
 from collections import namedtuple
 

@@ -193,3 +193,33 @@ def test_likelihood_whitening_matches_oracle(oracle):
     sur = bfb.PolyModel('quadratic', input_size=2, output_size=1)
     with pytest.raises(ValueError, match='outputs'):
         bfb.Density(sur, likelihood=GaussianLikelihood([0., 0.], np.eye(2)))
+
+
+def test_from_reference_with_likelihood():
+    """a reference Density [module_0 (x -> m), module_1 (m -> logp)] whose surrogate replaces module_0 only (scope (0, 1)) is
+    accepted when the caller restates module_1 as a GaussianLikelihood, and refused otherwise"""
+    from types import SimpleNamespace
+    n = 2
+    conf = SimpleNamespace(order='quadratic', _input_mask=np.arange(n), _output_mask=np.arange(1),
+                           _coef=np.array([[[0.5, 0.1], [0., 0.25]]]))
+    lin = SimpleNamespace(order='linear', _input_mask=np.arange(n), _output_mask=np.arange(1), _coef=np.array([[1., 0.2, -0.3]]))
+    rs = SimpleNamespace(_configs=[lin, conf], _recipe=None, _scope=(0, 1), _use_bound=False, _alpha=None, _alpha_p=100.,
+                         _center_max=True, _input_size=n, _output_size=1, _input_scales=None)
+    ref = SimpleNamespace(_surrogate_list=[rs], _module_list=[object(), object()], use_surrogate=True, _input_scales=None,
+                          _hard_bounds=False, _use_decay=False, _alpha=None, _alpha_p=150., _gamma=0.1, density_name='logp')
+    with pytest.raises(ValueError, match='whole module list'):
+        bfb.Density.from_reference(ref)
+    lik = bfb.GaussianLikelihood([5.], [[4.]])
+    den = bfb.Density.from_reference(ref, likelihood=lik)
+    spec = den.to_spec()
+    assert spec['epilogue']['cinv'][0, 0] == 4. and spec['m'] == 1 and den.likelihood is lik
+    from bayesfast_b200.density import whiten_spec
+    w = whiten_spec(spec, lik)
+    # f' = 2 (f - 5): constant 2 (1 - 5), linear and quadratic coefficients doubled
+    assert np.allclose(w['configs'][0]['packed'], [[-8., 0.4, -0.6]]) and np.allclose(w['configs'][1]['packed'], [[1., 0.2, 0.5]])
+    rs._scope = (0, 2)
+    with pytest.raises(ValueError, match='all modules but the last'):
+        bfb.Density.from_reference(ref, likelihood=lik)
+    import pickle
+    den2 = pickle.loads(pickle.dumps(den))
+    assert den2.likelihood.inv_cov[0, 0] == 4. and den2._handle is None
