@@ -8,26 +8,16 @@ sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import numpy as np
 from bayesfast_b200 import _cabi
 from bayesfast_b200.density import whiten_spec, GaussianLikelihood
-from _specs import to_device_spec
 n = 26
 m = int(sys.argv[1]) if len(sys.argv) > 1 else 457
 C = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
 N_IT = int(sys.argv[3]) if len(sys.argv) > 3 and sys.argv[3].isdigit() else 200      # a short run for ncu
 rng = np.random.default_rng(0)
-nb = 8                                                  # blocks of outputs, each a quadratic in 10 of the 26 inputs
-edges = np.linspace(0, m, nb + 1).astype(int)
-cfgs = [dict(order='linear', input_mask=np.arange(n), output_mask=np.arange(m),
-             coef=np.concatenate((rng.normal(size=(m, 1)) * 0.1, rng.normal(size=(m, n)) * 0.3), axis=1))]
-for b in range(nb):
-    im = np.sort(rng.choice(n, size=10, replace=False))
-    k = edges[b + 1] - edges[b]
-    cfgs.append(dict(order='quadratic', input_mask=im, output_mask=np.arange(edges[b], edges[b + 1]),
-                     coef=np.triu(rng.normal(size=(k, 10, 10))) * 0.03))
-B = rng.normal(size=(m, m))
-ep = dict(d=rng.normal(size=m) * 0.1, cinv=(B @ B.T / m + 0.5 * np.eye(m)) * (26. / m), c0=0.)
-spec = dict(n=n, m=m, configs=cfgs, use_bound=False, input_scales=None, use_decay=False, transform_ranges=None, epilogue=ep)
+from bayesfast_b200 import synthetic
+spec, lik = synthetic.des_pipeline(n, m, seed=0)     # 8 blocks of outputs, each a quadratic in 10 of the 26 inputs
+ep = spec['epilogue']
 h = _cabi.Handle(0)
-h.set_model(whiten_spec(to_device_spec(spec), GaussianLikelihood(ep['d'], ep['cinv'], ep['c0'])))
+h.set_model(whiten_spec(spec, lik))
 X = rng.normal(size=(65536, n)) * 0.3
 for rep in range(3):
     lp, g = h.logp_and_grad_batch(X)
