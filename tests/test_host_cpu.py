@@ -223,3 +223,35 @@ def test_from_reference_with_likelihood():
     import pickle
     den2 = pickle.loads(pickle.dumps(den))
     assert den2.likelihood.inv_cov[0, 0] == 4. and den2._handle is None
+
+
+def test_likelihood_whitening_all_orders_and_masks(oracle):
+    """whiten_spec with masked cubic-2 / cubic-3 configs and overlapping output masks (two configs feeding the same output)"""
+    from _specs import to_device_spec
+    from bayesfast_b200.density import whiten_spec, GaussianLikelihood
+    from bayesfast_b200.poly import unpack_dense
+    rng = np.random.default_rng(12)
+    n, m = 6, 4
+    c3 = np.zeros((2, 4, 4, 4))
+    for j in range(4):
+        for k in range(j + 1, 4):
+            c3[:, j, k, k + 1:] = rng.normal(size=(2, 4 - k - 1)) * 0.1
+    cfgs = [dict(order='linear', input_mask=np.array([0, 2, 5]), output_mask=np.arange(m), coef=rng.normal(size=(m, 4))),
+            dict(order='quadratic', input_mask=np.array([1, 2, 4]), output_mask=np.array([0, 3]), coef=np.triu(rng.normal(size=(2, 3, 3)))),
+            dict(order='quadratic', input_mask=np.arange(n), output_mask=np.array([3]), coef=np.triu(rng.normal(size=(1, n, n))) * 0.3),
+            dict(order='cubic-2', input_mask=np.array([0, 3]), output_mask=np.array([1, 2]), coef=rng.normal(size=(2, 2, 2)) * 0.2),
+            dict(order='cubic-3', input_mask=np.array([0, 1, 3, 5]), output_mask=np.array([0, 2]), coef=c3)]
+    B = rng.normal(size=(m, m))
+    ep = dict(d=rng.normal(size=m), cinv=B @ B.T + 0.1 * np.eye(m), c0=2.5)
+    spec = dict(n=n, m=m, configs=cfgs, use_bound=True, mu=rng.normal(size=n) * 0.1, hess=np.eye(n) * 0.5, alpha=1.2,
+                f_mu=rng.normal(size=m), input_scales=None, use_decay=False, transform_ranges=None, epilogue=ep)
+    lik = GaussianLikelihood(ep['d'], ep['cinv'], ep['c0'])
+    w = whiten_spec(to_device_spec(spec), lik)
+    assert [c['order'] for c in w['configs']] == ['linear', 'quadratic', 'cubic-2', 'cubic-3']
+    for cf in w['configs']:
+        cf['coef'] = np.array([unpack_dense(cf['order'], a, n) for a in cf['packed']])
+    X = np.concatenate((rng.normal(size=(12, n)) * 0.5, rng.normal(size=(8, n)) * 3.))      # inside and outside the bound
+    F, J = oracle.OracleDensity(w).poly_eval_batch(X)
+    lp0, gr0 = oracle.OracleDensity(spec).logp_and_grad_batch(X)
+    assert np.allclose(lik.const - 0.5 * np.sum(F * F, axis=1), lp0, rtol=1e-11, atol=1e-11)
+    assert np.allclose(-np.einsum('co,con->cn', F, J), gr0, rtol=1e-11, atol=1e-11 * np.abs(gr0).max())
