@@ -426,7 +426,7 @@ def make_pipeline():
         return bf.Module(fun=lambda f: np.atleast_1d(c0 - 0.5 * (f - d) @ cinv @ (f - d)),
                          jac=lambda f: np.atleast_2d(-(cs @ (f - d))), input_vars='m', output_vars='logp')
 
-    def finish(name, den, ep, Xt, x0, seed, **trace_kw):
+    def finish(name, den, ep, Xt, x0, seed, **trace_kw):        # appends to the `cases` list current at call time
         lp, gr = [], []
         for x in Xt:
             a_, b_ = den.logp_and_grad(x, original_space=False)
@@ -476,6 +476,33 @@ def make_pipeline():
     Xt = np.concatenate((xf[:8] * 0.7, xf[8:14] * 3.))
     finish('multi_output_n5_m6', den, dict(d=d, cinv=cinv, c0=-1.25), Xt, xf[20:23] * 0.5, 2202, n_iter=60, n_warmup=30)
     gio.save('pipeline.npz', dict(cases=cases))
+
+    # --- second file (oracle pin only): multi-output pipeline with everything on -- radial bound (default bound options, so
+    # far points take PolyModel._fj_bound for every output), module-level input_scales, variable transform with hard bounds,
+    # decay, cubic-2 + quadratic + linear configs ---
+    cases = []
+    n, m = 4, 3
+    cfgs = [PolyConfig('linear'), PolyConfig('quadratic', input_mask=[0, 1, 2], output_mask=[0, 2]), PolyConfig('cubic-2', output_mask=[1])]
+    W = rng.normal(size=(m, n)) * 0.5
+    truth = lambda x: W @ x + 0.1 * np.array([x[0] * x[1], x[2]**2 * x[3], x[1] * x[2]])
+    d = rng.normal(size=m) * 0.2
+    B = rng.normal(size=(m, m))
+    cinv = B @ B.T / m + 0.4 * np.eye(m)
+    ranges = np.stack((-9. - rng.uniform(size=n), 9. + rng.uniform(size=n)), axis=1)
+    hb = np.array([[1, 1], [0, 0], [1, 0], [0, 1]], np.uint8)
+    mA = bf.Module(fun=truth, input_vars='x', output_vars='m')
+    sur = PolyModel(cfgs, input_size=n, output_size=m, input_vars='x', output_vars='m',
+                    input_scales=np.stack((-1.5 + 0.1 * rng.normal(size=n), 2. + 0.1 * rng.normal(size=n)), axis=1))
+    den = bf.Density(module_list=[mA, lik_module(d, cinv, 0.3)], surrogate_list=[sur], input_shapes=[n], input_vars='x',
+                     density_name='logp', decay_options={'use_decay': True}, input_scales=ranges, hard_bounds=hb)
+    xf = rng.normal(size=(4 * sur.n_param, n)) * 1.2
+    den.fit([den.fun(x, original_space=True, use_surrogate=False) for x in xf])
+    den.use_surrogate = True
+    Xo = np.clip(np.concatenate((xf[:8] * 0.8, xf[8:16] * 4.)), -8.5, 8.5)
+    Xt = np.array([den.from_original(x) for x in Xo])
+    x0 = np.array([den.from_original(x) for x in xf[30:33] * 0.5])
+    finish('multi_output_bound_transform_decay', den, dict(d=d, cinv=cinv, c0=0.3), Xt, x0, 2303, n_iter=40, n_warmup=20)
+    gio.save('pipeline_ext.npz', dict(cases=cases))
 
 
 if __name__ == '__main__':

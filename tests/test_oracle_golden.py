@@ -157,3 +157,21 @@ def test_pipeline_cases(oracle):
         for k in FLT_STATS:
             _flt(out[k], r[k], (c['name'], k), early=4)
         _flt(out['samples'], r['samples'], c['name'], early=4)
+
+
+def test_pipeline_extended_case(oracle):
+    """multi-output pipeline with radial bound (far points take _fj_bound for every output), module rescale, variable transform
+    with hard bounds and decay, cubic-2 + quadratic + linear configs: logp_and_grad and a NUTS run of the real reference"""
+    for c in gio.load('pipeline_ext.npz')['cases']:
+        assert c['spec']['use_bound'] and c['spec']['use_decay'] and c['spec']['transform_ranges'] is not None
+        od = oracle.OracleDensity(c['spec'])
+        lp, gr = od.logp_and_grad_batch(c['X'])
+        assert _close(lp, c['logp'], 1e-11), c['name']
+        assert _close(gr, c['grad'], 1e-11), c['name']
+        r = c['result']
+        out = od.run('NUTS', {k: int(v) for k, v in c['trace_kw'].items()}, c['x0'], float(r['step0']), r['var0'],
+                     draws_u=r['draws_u'], draws_z=r['draws_z'])
+        assert np.all(out['status'] == 0) and np.array_equal(out['n_draws'], r['n_draws'])
+        for k in INT_STATS:
+            assert np.array_equal(out[k], r[k].astype(np.int32)), (c['name'], k)
+        _flt(out['samples'], r['samples'], c['name'], early=4)
