@@ -15,6 +15,7 @@ numdifftools) and records inputs + outputs of the hot path:
     fit.npz           PolyModel.fit (+ _set_bound) results
     sampler.npz       NUTS / HMC chains driven by a replayed random stream (include/bfb_rng.h draws)
     pipeline.npz      surrogate + Gaussian-likelihood module pipelines (2-D donut of examples/2d-donut.ipynb, multi-output)
+    pipeline_ext.npz  the same with radial bound + module rescale + variable transform + decay + cubic-2 configs (pins the oracle)
     sampler_dense.npz the same with the dense mass matrix (metric='full' or a covariance; QuadMetricFull / FullAdapt)
 
 The random stream: the reference's per-chain numpy Generator is replaced (after _init_chain) by a
