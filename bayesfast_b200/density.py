@@ -321,9 +321,8 @@ class Density:
             y = np.asarray(y, dtype=np.float64)
             if y.ndim == 1:
                 y = y[:, None]
-            logp = y[:, 0].copy()
-        if self.likelihood is not None:         # logp of the pipeline, for center_max (poly.py:277-286)
-            logp = self.likelihood.logp(y)
+            # logp of the pipeline, for center_max (poly.py:277-286): output #0, or the likelihood of the outputs
+            logp = y[:, 0].copy() if self.likelihood is None else self.likelihood.logp(y)
         if self._use_decay:
             self._set_decay(x)
         su = self._surrogate
