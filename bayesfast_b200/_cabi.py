@@ -312,7 +312,7 @@ class Handle:
 
     def sampler_last_path(self):
         """kernel family of the last sampler run: 'generic', 'fast' (FMA multi-chain) or 'dmma' (FP64 tensor core)"""
-        return {0: 'generic', 1: 'fast', 2: 'dmma'}.get(int(self._L.bfb_sampler_last_path(self._h)), 'none')
+        return {0: 'generic', 1: 'fast', 2: 'dmma', 3: 'team'}.get(int(self._L.bfb_sampler_last_path(self._h)), 'none')
 
     def eval_last_path(self):
         """evaluator of the last logp_and_grad_batch: 'generic', 'dmma' or 'lik_dmma' (tensor-core likelihood pipeline)"""

@@ -60,6 +60,8 @@ struct DevModel {
     // DMMA operand table of output 0 (bfb_dmma.cuh): bfrag[kt][tile][lane]; frag_nr = 0 when the model does not qualify
     const double *bfrag;
     int frag_nr, frag_nt, frag_ext;
+    // operand table of the four-warp team evaluator (bfb_team.cuh): tfrag[w][kt][tile][lane]; null when the model does not qualify
+    const double *tfrag;
     // cubic-3 block of the tensor-core evaluator: operand table bfrag3[kt][tile][lane], pair table c3pair[4 kt] = k | l << 8
     const double *bfrag3;
     const int *c3pair;

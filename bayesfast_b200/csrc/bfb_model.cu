@@ -2,7 +2,7 @@
 // batched evaluation entry points, RNG exposure.
 #include "bfb_common.cuh"
 #include "bfb_eval.cuh"
-#include "bfb_dmma.cuh"
+#include "bfb_team.cuh"
 int bfb_launch_eval_dmma(bfb_context *h, const double *X, int64_t C, double *LP, double *G);
 int bfb_launch_lik_dmma(bfb_context *h, const double *X, int64_t C, double *LP, double *G);   // bfb_lik_dmma.cu
 int bfb_build_lik_table(bfb_context *h);
@@ -284,6 +284,26 @@ int bfb_upload_model(bfb_context *h)
                     }
             if ((rc = upload(h, fr, &D.bfrag))) return rc;
             D.frag_nr = nr; D.frag_nt = NT; D.frag_ext = ext ? 1 : 0;
+            if (!ext) {
+                // operand table of the team evaluator (bfb_team.cuh): warp w owns the rows r = NRW w + v
+                const int nrw = (nr + 3) / 4, ntw = bfb_team_tiles(nr, c2);
+                const int TDw = (nrw + 1) / 2, TXw = c2 ? nrw : (nrw + 1) / 2;
+                std::vector<double> tf((size_t)4 * nr * ntw * 32, 0.);
+                for (int w = 0; w < 4; ++w)
+                    for (int kt = 0; kt < nr; ++kt)
+                        for (int t = 0; t < ntw; ++t)
+                            for (int lane = 0; lane < 32; ++lane) {
+                                const int k = 4 * kt + (lane & 3), gid = lane >> 2, own = gid >> 1, e = gid & 1;
+                                const std::vector<double> *T = nullptr;
+                                int v;
+                                if (t < TDw) { v = 2 * t + e; if (v < nrw) T = &HT; }
+                                else if (t < TDw + TXw) { v = 2 * (t - TDw) + e; if (v < nrw) T = &S; else if (c2 && v < 2 * nrw) { T = &A1T; v -= nrw; } }
+                                else { v = 2 * (t - TDw - TXw) + e; if (v < nrw) T = &A2; }
+                                const int j = 4 * (nrw * w + v) + own;
+                                if (T && !T->empty() && k < n && j < n) tf[(((size_t)w * nr + kt) * ntw + t) * 32 + lane] = (*T)[(size_t)k * np + j];
+                            }
+                if ((rc = upload(h, tf, &D.tfrag))) return rc;
+            }
         }
         // cubic-3 block (bfb_dmma.cuh, MV bit 2): pairs (k < l) in lexicographic order, 4 per k-tile; column (tile t, lane
         // quad-owner `own`, e) holds dimension j = 4 (2 t + e) + own like the other blocks

@@ -20,6 +20,8 @@
 int bfb_launch_nuts_fast(bfb_context *h, const bfb_run_out &o, int n_iter);   // bfb_sampler_fast.cu
 int bfb_launch_nuts_dmma(bfb_context *h, const bfb_run_out &o, int n_iter);   // bfb_sampler_dmma.cu
 int bfb_launch_hmc_dmma(bfb_context *h, const bfb_run_out &o, int n_iter);    // bfb_sampler_dmma.cu
+int bfb_launch_nuts_team(bfb_context *h, const bfb_run_out &o, int n_iter);   // bfb_sampler_team.cu
+int bfb_launch_hmc_team(bfb_context *h, const bfb_run_out &o, int n_iter);    // bfb_sampler_team.cu
 
 struct RunOutDev {
     bfb_run_out o;
@@ -821,8 +823,12 @@ static int launch_run(bfb_context *h, int sampler, int n_iter, const bfb_run_out
         }
     }
     if (sampler == BFB_HMC && !h->dense_metric && !getenv("BFB200_FORCE_GENERIC") && !(sel_ && !strcmp(sel_, "generic"))) {
-        fast_rc = bfb_launch_hmc_dmma(h, od.o, n_iter);
-        if (fast_rc == 0) h->last_path = 2;
+        fast_rc = bfb_launch_hmc_team(h, od.o, n_iter);
+        if (fast_rc == 0) h->last_path = 3;
+        if (fast_rc == 1) {
+            fast_rc = bfb_launch_hmc_dmma(h, od.o, n_iter);
+            if (fast_rc == 0) h->last_path = 2;
+        }
     }
     if (fast_rc < 0) return fast_rc;
     if (fast_rc == 0) return BFB_OK;

@@ -1,0 +1,190 @@
+// bfb_team.cuh -- PolyModel value + gradient for EIGHT chains evaluated by a TEAM of four warps (FP64 tensor cores).
+//
+// Why a team: with one warp per 8-chain group (bfb_dmma.cuh) 4096 chains are 512 warps on the 592 schedulers of a B200 --
+// less than one warp per scheduler, 255 registers each, every dependent instruction exposes its latency (profiles/r01_s:
+// issue slots 16 % busy, DMMA sub-pipe 16 %).  Here the four matrix-vector products of the cubic-2 stack are split over the
+// OUTPUT dimensions: warp w of the team owns the dimensions j = 4 r + lg with r in [NRW w, NRW (w + 1)) (lg = lane & 3,
+// the 8 chains are still the 8 rows of the m8n8k4 DMMA, a chain is still the quad lane >> 2) and computes only the output
+// tiles of those dimensions -- a quarter of the DMMAs, a quarter of every state vector (2 registers instead of 7 at n = 26),
+// ~1/2 of the registers, four times the warps.  What crosses the team goes through shared memory and named barriers
+// (bar.sync id, 128):
+//   * the point: every warp writes its slice of q into the team's x buffer (row r at r * 32 + lane) and reads all of it
+//     back as the A operand (element kt * 32 + lane IS the A fragment of k-tile kt);
+//   * the scalar reductions (Mahalanobis radius; value, J.d and kinetic energy): reduce-scatter over the quad with three
+//     shuffles, one conflict-free store per lane, barrier, the four partials summed in a fixed order by everybody
+//     (bitwise identical totals in all four warps, deterministic).
+// Three barriers per evaluation.  The kinetic energy of the momentum after the second half kick is reduced together with
+// the value; outside the radial bound (poly.py:480-503) the gradient gets the term sfac * H(x - mu) / beta, whose
+// contribution to the kinetic energy is added algebraically (two more sums that ride along in the packed reductions)
+// instead of through a fourth barrier.
+//
+// Operand table (host-built, bfb_upload_model): tfrag[w][kt][tile][lane], tiles of warp w ordered D | x block | x^2 block
+// with the value index v = 2 tile + e of column 2 lg + e (v < NRW: first matrix of the block, dimension r = NRW w + v;
+// NRW <= v < 2 NRW: second matrix of the x block).
+#pragma once
+#include "bfb_dmma.cuh"
+
+template <int NR, int MV>
+struct TeamShape {
+    static constexpr bool C2 = MV & 1;
+    static constexpr int T = 4;                              // warps of a team
+    static constexpr int NRW = (NR + 3) / 4;                 // dimensions per lane and warp
+    static constexpr int NRP = 4 * NRW;                      // rows of a vector slot (>= NR; the padding rows hold zeros)
+    static constexpr int SLOT = NRP * 32;
+    static constexpr int TD = (NRW + 1) / 2;                 // tiles multiplying x - mu
+    static constexpr int TX = C2 ? NRW : (NRW + 1) / 2;      // tiles multiplying x
+    static constexpr int T2 = C2 ? (NRW + 1) / 2 : 0;        // tiles multiplying x^2
+    static constexpr int NTW = TD + TX + T2;                 // tiles per warp and k-tile
+    static constexpr int TAB_DOUBLES = T * NR * NTW * 32;
+    static constexpr int RED_DOUBLES = 2 * 128;              // two alternating reduction buffers [w][chain][4]
+};
+inline int bfb_team_tiles(int nr, bool c2) { const int nrw = (nr + 3) / 4; return (nrw + 1) / 2 + (c2 ? nrw + (nrw + 1) / 2 : (nrw + 1) / 2); }
+
+__device__ __forceinline__ void team_bar(int id) { asm volatile("bar.sync %0, 128;" :: "r"(id) : "memory"); }
+
+// reduce-scatter of four sums over the 4 lanes of a quad: lane lg ends with the total of quantity ((lg & 1) << 1) | (lg >> 1)
+__device__ __forceinline__ double qrs4(double a, double b, double c, double d, int lane)
+{
+    const bool b0 = lane & 1, b1 = lane & 2;
+    double k0 = b0 ? c : a, k1 = b0 ? d : b;
+    const double s0 = b0 ? a : c, s1 = b0 ? b : d;
+    k0 += shx4(s0, 1); k1 += shx4(s1, 1);
+    double k = b1 ? k1 : k0;
+    const double s = b1 ? k0 : k1;
+    k += shx4(s, 2);
+    return k;
+}
+
+// Four sums over all dimensions of each of the 8 chains of the team.  red: the team's RED_DOUBLES, rbuf: which half is
+// written next (flips).  Every lane of every warp returns the same totals a, b; c and d are summed by the leader warp
+// (w == 0) only -- FP64 additions cost pipe cycles that the DMMAs need (the other warps get their own partials back).
+__device__ __forceinline__ void team_sum4(double &a, double &b, double &c, double &d, double *red, int &rbuf, int bar_id, int lane, int w)
+{
+    const int lg = lane & 3, gi = lane >> 2;
+    const double k = qrs4(a, b, c, d, lane);
+    double *buf = red + rbuf * 128;
+    buf[w * 32 + gi * 4 + (((lg & 1) << 1) | (lg >> 1))] = k;
+    team_bar(bar_id);
+    const double2 *rp = reinterpret_cast<const double2 *>(buf + gi * 4);
+    const double2 u0 = rp[0], u1 = rp[16], u2 = rp[32], u3 = rp[48];
+    a = (u0.x + u1.x) + (u2.x + u3.x);
+    b = (u0.y + u1.y) + (u2.y + u3.y);
+    if (w == 0) {
+        const double2 v0 = rp[1], v1 = rp[17], v2 = rp[33], v3 = rp[49];
+        c = (v0.x + v1.x) + (v2.x + v3.x);
+        d = (v0.y + v1.y) + (v2.y + v3.y);
+    }
+    rbuf ^= 1;
+}
+
+// Evaluation at the point whose slices the owners have written to the team's exchange buffers: xb[0 .. SLOT) = x,
+// xb[SLOT .. 2 SLOT) = x - mu, xb[2 SLOT .. 3 SLOT) = x^2 (row r at r * 32 + lane; the caller has passed a team barrier
+// since).  tab_w: this warp's slice of the operand table; q_own / p / var: own dimensions (p = momentum after the first half
+// kick).  Returns the gradient of the own dimensions in every warp; lp and ke = sum_j var_j (p_j + dt g_j)^2 over ALL
+// dimensions of the chain are valid in the leader warp (w == 0) only.
+// Outside the radial bound the owners replace their slices of x and x^2 by the projection x_0 = mu + (alpha / beta)(x - mu)
+// (poly.py:480-503 writes (alpha x + (beta - alpha) mu) / beta) behind one more barrier, so that nobody recomputes the whole
+// point; rounds in which no chain of the team is outside skip it.
+template <int NR, int MV>
+__device__ __forceinline__ void team_logp_grad(const double *tab_w, const double *msm, double *xb, double *red, int &rbuf,
+                                               int bar_id, int lane, int w, const DmmaConsts &K, bool live,
+                                               const double (&q_own)[TeamShape<NR, MV>::NRW], const double (&p)[TeamShape<NR, MV>::NRW],
+                                               const double (&var)[TeamShape<NR, MV>::NRW], double dt,
+                                               double &lp, double (&gn)[TeamShape<NR, MV>::NRW], double &ke)
+{
+    using TS = TeamShape<NR, MV>;
+    constexpr int NRW = TS::NRW, NTW = TS::NTW, TD = TS::TD, TX = TS::TX, T2 = TS::T2, SLOT = TS::SLOT;
+    constexpr bool C2 = TS::C2;
+    const int lg = lane & 3;
+    const double *mu_t = msm, *lin_t = msm + 32;
+    const double *tb = tab_w + lane;
+    double mu_o[NRW], d_o[NRW];
+#pragma unroll
+    for (int i = 0; i < NRW; ++i) { mu_o[i] = mu_t[4 * (NRW * w + i) + lg]; d_o[i] = q_own[i] - mu_o[i]; }
+    // ---- stage A: h = H (x - mu) for the own dimensions; two accumulator sets (even / odd k-tiles) halve the dependent chain ----
+    double ah[TD][2][2];
+#pragma unroll
+    for (int t = 0; t < TD; ++t) ah[t][0][0] = ah[t][0][1] = ah[t][1][0] = ah[t][1][1] = 0.;
+#pragma unroll
+    for (int kt = 0; kt < NR; ++kt) {
+        const double dk = xb[SLOT + kt * 32 + lane];
+#pragma unroll
+        for (int t = 0; t < TD; ++t) dmma884(ah[t][kt & 1][0], ah[t][kt & 1][1], dk, tb[(kt * NTW + t) * 32]);
+    }
+    double h[NRW], bpart = 0., vh2 = 0., z0 = 0., z1 = 0.;
+#pragma unroll
+    for (int i = 0; i < NRW; ++i) {
+        h[i] = ah[i / 2][0][i % 2] + ah[i / 2][1][i % 2];
+        bpart = fma(d_o[i], h[i], bpart);
+        vh2 = fma(var[i] * h[i], h[i], vh2);
+    }
+    team_sum4(bpart, z0, vh2, z1, red, rbuf, bar_id, lane, w);
+    const double beta2 = bpart;
+    const bool outside = live && (beta2 > K.alpha2);
+    double rbeta = 0., beta = 0.;
+    double xo[NRW];
+#pragma unroll
+    for (int i = 0; i < NRW; ++i) xo[i] = q_own[i];
+    if (__any_sync(BFB_FULL, outside)) {           // identical in the four warps: same totals, same flags
+        rbeta = rsqrt(beta2); beta = beta2 * rbeta;
+        const double sc = K.alpha * rbeta;
+#pragma unroll
+        for (int i = 0; i < NRW; ++i) {
+            if (outside) xo[i] = (4 * (NRW * w + i) + lg < K.n) ? fma(sc, d_o[i], mu_o[i]) : 0.;
+            xb[(NRW * w + i) * 32 + lane] = xo[i];
+            xb[2 * SLOT + (NRW * w + i) * 32 + lane] = xo[i] * xo[i];
+        }
+        team_bar(bar_id);
+    }
+    // ---- stage B: the polynomial at x (inside) or at its projection (outside) ----
+    double ax[TX][2], a2[T2 > 0 ? T2 : 1][2];
+#pragma unroll
+    for (int t = 0; t < TX; ++t) ax[t][0] = ax[t][1] = 0.;
+#pragma unroll
+    for (int t = 0; t < (T2 > 0 ? T2 : 1); ++t) a2[t][0] = a2[t][1] = 0.;
+#pragma unroll
+    for (int kt = 0; kt < NR; ++kt) {
+        const double xk = xb[kt * 32 + lane];
+#pragma unroll
+        for (int t = 0; t < TX; ++t) dmma884(ax[t][0], ax[t][1], xk, tb[(kt * NTW + TD + t) * 32]);
+        if (C2) {
+            const double x2k = xb[2 * SLOT + kt * 32 + lane];
+#pragma unroll
+            for (int t = 0; t < T2; ++t) dmma884(a2[t][0], a2[t][1], x2k, tb[(kt * NTW + TD + TX + t) * 32]);
+        }
+    }
+    double fpart = 0., jd = 0., ka = 0., kah = 0.;
+#pragma unroll
+    for (int i = 0; i < NRW; ++i) {
+        const double y = ax[i / 2][i % 2];
+        const double lin_r = lin_t[4 * (NRW * w + i) + lg];
+        double g = lin_r + y;
+        fpart = fma(lin_r, xo[i], fpart);
+        fpart = fma(0.5 * xo[i], y, fpart);
+        if (C2) {
+            const double t = ax[(NRW + i) / 2][(NRW + i) % 2];
+            const double u = a2[i / 2][i % 2];
+            g += fma(2. * xo[i], t, u);
+            fpart = fma(xo[i] * xo[i], t, fpart);
+        }
+        gn[i] = g;
+        jd = fma(g, d_o[i], jd);
+        const double pn = fma(dt, g, p[i]), vpn = var[i] * pn;
+        ka = fma(pn, vpn, ka);
+        kah = fma(vpn, h[i], kah);
+    }
+    team_sum4(fpart, jd, ka, kah, red, rbuf, bar_id, lane, w);
+    double fp = fpart;
+    ke = ka;
+    if (outside) {
+        // PolyModel._fj_bound, poly.py:480-503: J = J0 + outer(sfac, H (x - mu) / beta)
+        const double f0 = K.c0 + fpart;
+        const double cg = ((f0 - K.f_mu) / K.alpha - jd * rbeta) * rbeta;
+#pragma unroll
+        for (int i = 0; i < NRW; ++i) gn[i] = fma(cg, h[i], gn[i]);
+        fp = (beta * f0 - (beta - K.alpha) * K.f_mu) / K.alpha - K.c0;
+        const double cd = dt * cg;
+        ke = fma(cd, fma(cd, vh2, 2. * kah), ka);
+    }
+    lp = K.c0 + fp;
+}

@@ -272,13 +272,16 @@ def test_tensor_core_nuts_resume_and_reset(handle):
         assert np.array_equal(np.concatenate([b1[k], b2[k]], axis=1), a[k]), k
 
 
-@pytest.mark.parametrize('n,order,C,env', [(26, 'cubic-2', 100, {}), (26, 'cubic-2', 100, {'BFB200_WARPS_PER_SM': '8', 'BFB200_CHUNK_ITERS': '7'}),
+@pytest.mark.parametrize('family', ['team', 'dmma'])
+@pytest.mark.parametrize('n,order,C,env', [(26, 'cubic-2', 100, {}), (26, 'cubic-2', 100, {'BFB200_WARPS_PER_SM': '8', 'BFB200_TEAMS_PER_SM': '3', 'BFB200_CHUNK_ITERS': '7'}),
                                            (12, 'cubic-2', 37, {}), (30, 'quadratic', 24, {})])
-def test_tensor_core_hmc_vs_oracle(handle, oracle, monkeypatch, n, order, C, env):
-    """hmc_dmma_kernel (lock-step HMC, 8 chains per warp on FP64 DMMA) vs the oracle fed with the device's draws and vs the
-    generic kernel: accept / divergence decisions identical, states within rounding"""
+def test_tensor_core_hmc_vs_oracle(handle, oracle, monkeypatch, n, order, C, env, family):
+    """hmc_team_kernel (8 chains per team of four warps) / hmc_dmma_kernel (8 chains per warp), lock-step HMC on FP64 DMMA, vs
+    the oracle fed with the device's draws and vs the generic kernel: accept / divergence decisions identical, states
+    within rounding"""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
+    monkeypatch.setenv('BFB200_SAMPLER', family)
     n_iter = 40
     spec, cov = synthetic_spec(n, order, seed=90 + n)
     spec['alpha'] = spec['alpha'] / 1.6
@@ -287,7 +290,7 @@ def test_tensor_core_hmc_vs_oracle(handle, oracle, monkeypatch, n, order, C, env
     cfg = cfg_from({'n_int_step': 12}, 20, 77, chain0=9)
     handle.sampler_init(cfg, x0, 0.5, np.ones(n), x0)
     out = handle.sampler_run('HMC', n_iter)
-    assert handle.sampler_last_path() == 'dmma'
+    assert handle.sampler_last_path() == family
     st = handle.sampler_state()
     assert np.all(st['status'] == 0)
     U, Z = device_draws(handle, 77, st['n_draws'], 9)
