@@ -814,8 +814,12 @@ static int launch_run(bfb_context *h, int sampler, int n_iter, const bfb_run_out
     const char *sel_ = getenv("BFB200_SAMPLER");
     // a dense mass matrix runs on the generic kernel only
     if (sampler == BFB_NUTS && !h->dense_metric && !getenv("BFB200_FORCE_GENERIC") && !(sel_ && !strcmp(sel_, "generic"))) {
-        fast_rc = bfb_launch_nuts_dmma(h, od.o, n_iter);
-        if (fast_rc == 0) h->last_path = 2;
+        fast_rc = bfb_launch_nuts_team(h, od.o, n_iter);
+        if (fast_rc == 0) h->last_path = 3;
+        if (fast_rc == 1) {
+            fast_rc = bfb_launch_nuts_dmma(h, od.o, n_iter);
+            if (fast_rc == 0) h->last_path = 2;
+        }
         if (fast_rc == 1) {
             const char *sel = getenv("BFB200_SAMPLER");
             if (!sel || !strcmp(sel, "fast") || !strcmp(sel, "dmma")) fast_rc = bfb_launch_nuts_fast(h, od.o, n_iter);

@@ -298,13 +298,11 @@ template <int NR, int MV>
 static int launch_hmc_team_g(bfb_context *h, const bfb_run_out &o, int n_iter)
 {
     int G = 4;
-    if (const char *e = getenv("BFB200_TEAMS_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 6) G = v; }
+    if (const char *e = getenv("BFB200_TEAMS_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 5) G = v; }
     switch (G) {
     case 1: return launch_hmc_team<NR, MV, 1>(h, o, n_iter);
-    case 2: return launch_hmc_team<NR, MV, 2>(h, o, n_iter);
     case 3: return launch_hmc_team<NR, MV, 3>(h, o, n_iter);
     case 5: return launch_hmc_team<NR, MV, 5>(h, o, n_iter);
-    case 6: return launch_hmc_team<NR, MV, 6>(h, o, n_iter);
     }
     return launch_hmc_team<NR, MV, 4>(h, o, n_iter);
 }
@@ -317,6 +315,604 @@ int bfb_launch_hmc_team(bfb_context *h, const bfb_run_out &o, int n_iter)
     if (const char *e = getenv("BFB200_SAMPLER")) { if (strcmp(e, "team")) return 1; }
     const int mv = M.has_c2 ? 1 : 0;
 #define BFB_CASE(NR_, MV_) if (M.frag_nr == NR_ && mv == MV_) return launch_hmc_team_g<NR_, MV_>(h, o, n_iter);
+    BFB_CASE(4, 0) BFB_CASE(4, 1) BFB_CASE(7, 0) BFB_CASE(7, 1) BFB_CASE(8, 0) BFB_CASE(8, 1)
+#undef BFB_CASE
+    return 1;
+}
+
+// ----------------------------------------------------------------------------------------------------------------------
+// NUTS.  One round = one leapfrog of every live chain of the team, then whatever each chain needs (the 8 chains are NOT in
+// lock step: own iteration / depth / leaf counters).  Work is split three ways:
+//   * owners (all four warps, own dimensions): leapfrog, evaluation, every elementwise vector update -- proposal store,
+//     sub-tree momentum sums, stack push, tree ends -- done SPECULATIVELY before the decisions (a pushed entry or a stored
+//     proposal of a doubling that turns out to end here is dead data);
+//   * tasks (one warp per tree level, whole vectors, reduction inside the quad only): the U-turn dot products of the merge
+//     at level l for every chain whose leaf index has bit l set, and of Tree.extend for chains at the last leaf of a
+//     doubling -- all levels of a leaf at once, in parallel on different warps (the merge order only matters for the
+//     scalars);
+//   * the leader warp (w == 0): every per-chain scalar -- energies, multinomial weights, uniforms, proposal slots, dual
+//     averaging, statistics -- once per team instead of once per warp, published as one command word per chain.
+// Barriers per round: 3-4 in the evaluation, pbuf, flags, command (+2 when a chain of the team crosses an iteration boundary).
+// ----------------------------------------------------------------------------------------------------------------------
+#define TC_FIN 1
+#define TC_OK 2
+#define TC_IEND 4
+#define TC_RIGHT 8
+#define TC_START (1 << 12)
+#define TC_ENDP (1 << 13)
+#define TC_STOP (1 << 14)
+#define TC_FRESH (1 << 15)
+
+// doubles of shared memory per team: 14 fixed vector slots + 3 per stack level 1..LS | reduction | per-level scalars | flags
+__host__ __device__ inline int team_nuts_doubles(int slot, int LS) { return (14 + 3 * LS) * slot + 256 + 400 + 64; }
+
+template <int NR, int MV, int G>
+__global__ void __launch_bounds__(128 * G, 1) nuts_team_kernel(DevModel M, bfb_sampler_cfg cfg, ChainState st, RunOutDevF out,
+                                                               int L, int LS, double *__restrict__ gstack,
+                                                               double *__restrict__ gprop, int base_iter, int chunk_iters,
+                                                               int n_groups, int n_units, int *__restrict__ queue)
+{
+    using TS = TeamShape<NR, MV>;
+    constexpr int NRW = TS::NRW, SLOT = TS::SLOT;
+    extern __shared__ double smem[];
+    double *tab = smem, *msm = smem + TS::TAB_DOUBLES;
+    for (int i = threadIdx.x; i < TS::TAB_DOUBLES; i += blockDim.x) tab[i] = M.tfrag[i];
+    if (threadIdx.x < 32) { msm[threadIdx.x] = M.use_bound ? M.mu[threadIdx.x] : 0.; msm[32 + threadIdx.x] = M.lin[threadIdx.x]; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, team = wib >> 2, w = wib & 3, gi = lane >> 2, lg = lane & 3;
+    double *tsm = smem + TS::TAB_DOUBLES + 64 + (size_t)team * team_nuts_doubles(SLOT, LS);
+    double *xb = tsm, *sRL = tsm + SLOT, *sRS = tsm + 2 * SLOT, *sPBUF = tsm + 3 * SLOT;
+    double *sTLQ = tsm + 4 * SLOT, *sTLP = tsm + 5 * SLOT, *sTLG = tsm + 6 * SLOT;
+    double *sTRQ = tsm + 7 * SLOT, *sTRP = tsm + 8 * SLOT, *sTRG = tsm + 9 * SLOT;
+    double *sPS = tsm + 10 * SLOT, *sPB = tsm + 11 * SLOT, *sVAR = tsm + 12 * SLOT, *sS0 = tsm + 13 * SLOT, *sSTK = tsm + 14 * SLOT;
+    double *red = tsm + (14 + 3 * LS) * SLOT;
+    double *ssc = red + 256 + gi;                      // scalar (field f, level l) of this chain at ssc[(f * 10 + l) * 8]
+    double *flg = red + 256 + 400;
+    volatile int *ci = reinterpret_cast<volatile int *>(flg);     // [0, 8) command words | [8, 20) level flags | 20 extend flags | 24 unit
+    volatile double *cdv = flg + 16;                               // [0,8) step | [8,16) logp | [16,24) draw counter | [24,32) kinetic energy
+    const int bar_id = 1 + team;
+    const double *tab_w = tab + (size_t)w * NR * TS::NTW * 32;
+    const double *mu_t = msm;
+    const bool lead = (w == 0), leader = (w == 0 && lane == 0), scribe = (w == 0 && lg == 0);
+    const int n = M.n;
+    const DmmaConsts K = dmma_consts(M);
+    volatile int *qv = queue;
+    volatile int *ring = queue + 2 + n_groups;
+    int rbuf = 0;
+    bool first = true;
+    const int slot_id = blockIdx.x + gridDim.x * team;
+#define OWN(i_) ((NRW * w + (i_)) * 32 + lane)
+#define OLD(dst, base) _Pragma("unroll") for (int i_ = 0; i_ < NRW; ++i_) dst[i_] = (base)[OWN(i_)];
+#define OST(base, src) _Pragma("unroll") for (int i_ = 0; i_ < NRW; ++i_) (base)[OWN(i_)] = src[i_];
+
+#pragma unroll 1
+    for (;;) {
+    int group;
+    if (!team_next_unit(queue, ring, n_units, first, slot_id, ci + 24, bar_id, leader, group)) break;
+    const int chunk = qv[2 + group];
+    const int it_lo = chunk * chunk_iters;
+    const int it_hi = min(out.n_iter, it_lo + chunk_iters);
+    const int64_t c_raw = (int64_t)group * 8 + gi;
+    const bool exists = c_raw < st.C;
+    const int64_t c = exists ? c_raw : st.C - 1;
+    const size_t vb = (size_t)c * M.np;
+    double *gst = gstack + (size_t)group * (size_t)(L - 1 > LS ? L - 1 - LS : 0) * 3 * SLOT;      // deep stack levels (L2 resident)
+    double *gpr = gprop + (size_t)group * BFB_NSLOT * 2 * SLOT;                                   // proposal pool (q, grad) per slot
+    auto stk = [&](int lvl) -> double * { return (lvl <= LS) ? (sSTK + (lvl - 1) * 3 * SLOT) : (gst + (size_t)(lvl - 1 - LS) * 3 * SLOT); };
+
+    // ---- chain state: vectors (own dimensions) and the counters every warp keeps in step ----
+    double q[NRW], p[NRW], g[NRW], var[NRW], rpsf[NRW];
+#pragma unroll
+    for (int i = 0; i < NRW; ++i) {
+        const int j = 4 * (NRW * w + i) + lg;
+        q[i] = st.q[vb + j]; g[i] = st.g[vb + j]; var[i] = st.var[vb + j]; p[i] = 0.; rpsf[i] = 0.;
+    }
+    const uint64_t seed = cfg.seed, chain_id = (uint64_t)(cfg.chain0 + c);
+    const int it0 = base_iter;
+    const int status0 = exists ? st.status[c] : 9;
+    int status = status0;
+    int it = it_lo, depth = 0, ileaf = 0, nslot = 1;
+    bool done = (status != 0) || it_lo >= it_hi;
+    double step = 0.;
+    int64_t n_samples = st.n_samples[c], previous_update = st.previous_update[c];
+    int adapt_window = st.adapt_window[c];
+    double fg_n = st.fg_n[c], bg_n = st.bg_n[c];
+    // ---- leader-only scalars ----
+    int64_t t = st.t_draw[c];
+    double logp_q = st.logp[c], log_step = st.log_step[c], log_bar = st.log_bar[c];
+    double e_step = exp(log_step), e_bar = exp(log_bar);
+    double E0 = 0., prop_E = 0., prop_lp = 0., acc_sum = 0., maxdE = 0.;
+    WT Wtree; Wtree.m = 1.; Wtree.k = 0;
+    int n_prop = 0, diverging = 0, prop_slot = 0;
+    unsigned freemask = 0, tree_total = 0;
+
+    // ---- the first command: start the first iteration of the unit ----
+    if (lead) {
+        int cm = 0;
+        if (!done) {
+            const bool warm_new = (it0 + it) < cfg.n_warmup;
+            cdv[gi] = warm_new ? e_step : e_bar; cdv[8 + gi] = logp_q; cdv[16 + gi] = __longlong_as_double(t);
+            t += n;
+            const double ud = team_draw_uniform(seed, chain_id, (uint64_t)t);
+            t += 1;
+            prop_slot = 0;
+            freemask = ((1u << BFB_NSLOT) - 1u) & ~1u;
+            cm = TC_START | TC_FRESH | (ud < 0.5 ? TC_RIGHT : 0) | (1 << 4);
+        }
+        if (lg == 0) ci[gi] = cm;
+    }
+    team_bar(bar_id);
+    bool first_round = true;
+
+#pragma unroll 1
+    for (;;) {
+        // ================= apply the command: Tree.extend bookkeeping, next doubling, iteration boundary =================
+        const int cm = ci[gi];
+        {
+            const bool live = !done;
+            const bool fin = live && (cm & TC_FIN);
+            if (fin) {
+                const bool right_cur = step > 0.;
+                OST(right_cur ? sTRQ : sTLQ, q) OST(right_cur ? sTRP : sTLP, p) OST(right_cur ? sTRG : sTLG, g)
+                depth += 1;
+                if (cm & TC_OK) {
+#pragma unroll
+                    for (int i = 0; i < NRW; ++i) sPS[OWN(i)] += rpsf[i];
+                }
+                if (!(cm & TC_IEND)) {                          // next doubling: nuts.py:210 + the first lines of Tree.extend
+                    const bool right = cm & TC_RIGHT;
+                    OLD(q, right ? sTRQ : sTLQ) OLD(p, right ? sTRP : sTLP) OLD(g, right ? sTRG : sTLG)
+                    OST(sPB, p)
+                    step = right ? fabs(step) : -fabs(step);
+                    ileaf = 0;
+                }
+            } else if (live && !first_round) ileaf += 1;
+            if (live) nslot = (cm >> 4) & 15;
+            const bool endp = live && (cm & TC_ENDP), startp = live && (cm & TC_START);
+            if (__any_sync(BFB_FULL, endp || startp)) {
+                // ---- iteration boundary: base_hmc.py:62-85, Tree.__init__ nuts.py:27-43 ----
+                const bool warm_old = (it0 + it) < cfg.n_warmup;            // of the iteration that ends
+                if (endp) {
+                    const double *src = gpr + (size_t)((cm >> 8) & 15) * 2 * SLOT;
+                    OLD(q, src) OLD(g, src + SLOT)
+                    if (out.o.samples) {
+#pragma unroll
+                        for (int i = 0; i < NRW; ++i) {
+                            const int j = 4 * (NRW * w + i) + lg;
+                            if (j < n) out.o.samples[((size_t)c * out.n_iter + it) * n + j] = q[i];
+                        }
+                    }
+                    if (warm_old && cfg.adapt_metric) {       // windowed Welford metric: metrics.py:186-211, 333-371
+                        const int64_t delta = n_samples - previous_update;
+                        const bool upd = ((delta + 1) % cfg.update_window == 0);
+                        const bool swap = delta >= adapt_window;
+                        fg_n += 1.; bg_n += 1.;
+#pragma unroll
+                        for (int i = 0; i < NRW; ++i) {
+                            const int j = 4 * (NRW * w + i) + lg;
+                            if (j < n) {
+                                double fgm = st.fg_mean[vb + j], fgr = st.fg_raw[vb + j], bgm = st.bg_mean[vb + j], bgr = st.bg_raw[vb + j];
+                                double od = q[i] - fgm;
+                                fgm += od / fg_n;
+                                fgr += 1. * od * (q[i] - fgm);
+                                od = q[i] - bgm;
+                                bgm += od / bg_n;
+                                bgr += 1. * od * (q[i] - bgm);
+                                if (upd) var[i] = fgr / fg_n;
+                                if (swap) { fgm = bgm; fgr = bgr; bgm = 0.; bgr = 0.; }
+                                st.fg_mean[vb + j] = fgm; st.fg_raw[vb + j] = fgr; st.bg_mean[vb + j] = bgm; st.bg_raw[vb + j] = bgr;
+                            }
+                        }
+                        if (swap) { fg_n = bg_n; bg_n = 10.; previous_update = n_samples; if (cfg.doubling) adapt_window *= 2; }
+                        n_samples += 1;
+                    }
+                    it += 1;
+                    if (cm & TC_STOP) done = true;
+                }
+                if (endp || startp) { OST(sVAR, var) }
+                team_bar(bar_id);
+                // momentum draw (metrics.py:83-86), lane = dimension, one chain at a time, the chains dealt to the four warps
+                {
+                    unsigned mask = __ballot_sync(BFB_FULL, startp && !done) & 0x11111111u;
+                    int idx = 0;
+#pragma unroll 1
+                    while (mask) {
+                        const int src = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        if ((idx & 3) == w) {
+                            const int ch = src >> 2, j = lane, e = (j >> 2) * 32 + src + (j & 3);
+                            const int64_t t_s = __double_as_longlong(cdv[16 + ch]);
+                            const uint64_t cid = (uint64_t)(cfg.chain0 + (int64_t)group * 8 + ch);
+                            double p0j = 0., vj = 0.;
+                            if (j < n) { vj = sVAR[e]; p0j = team_draw_normal(seed, cid, (uint64_t)(t_s + j)) / sqrt(vj); }
+                            if (j < 4 * TS::NRP) sPBUF[e] = p0j;
+                            const double ke = warp_sum(p0j * (vj * p0j));
+                            if (lane == 0) cdv[24 + ch] = ke;
+                        }
+                        ++idx;
+                    }
+                }
+                team_bar(bar_id);
+                if (startp && !done) {
+                    OLD(p, sPBUF)
+                    const double lq = cdv[8 + gi];
+                    const double e0 = 0.5 * cdv[24 + gi] - lq;
+                    if (!isfinite(e0)) { status = 2; done = true; if (lead) t -= 1; }        // base_hmc.py:72-76 (the direction draw is undone)
+                    else {
+                        const bool right = cm & TC_RIGHT;
+                        step = right ? cdv[gi] : -cdv[gi];
+                        OST(sTLQ, q) OST(sTLP, p) OST(sTLG, g) OST(sTRQ, q) OST(sTRP, p) OST(sTRG, g) OST(sPS, p) OST(sPB, p)
+                        if (cm & TC_FRESH) { OST(gpr, q) OST(gpr + SLOT, g) }       // starting point = slot 0 = the accepted proposal
+                        depth = 0; ileaf = 0;
+                        if (lead) {
+                            E0 = e0; prop_E = e0; prop_lp = lq; Wtree.m = 1.; Wtree.k = 0; acc_sum = 0.; maxdE = 0.;
+                            n_prop = 0; diverging = 0;
+                        }
+                    }
+                }
+            }
+        }
+        first_round = false;
+        if (!__any_sync(BFB_FULL, !done)) break;
+        const bool live = !done;
+        // ================= leapfrog (integration.py:68-95) and evaluation =================
+        const double dt = 0.5 * step;
+#pragma unroll
+        for (int i = 0; i < NRW; ++i) {
+            if (live) {
+                p[i] = fma(dt, g[i], p[i]);
+                q[i] = fma(step, var[i] * p[i], q[i]);
+            }
+            const int e = OWN(i);
+            xb[e] = q[i]; xb[SLOT + e] = q[i] - mu_t[4 * (NRW * w + i) + lg]; xb[2 * SLOT + e] = q[i] * q[i];
+        }
+        team_bar(bar_id);
+        double lp, ke2;
+        {
+            double gn[NRW];
+            team_logp_grad<NR, MV>(tab_w, msm, xb, red, rbuf, bar_id, lane, w, K, live, q, p, var, dt, lp, gn, ke2);
+            if (live) {
+#pragma unroll
+                for (int i = 0; i < NRW; ++i) { g[i] = gn[i]; p[i] = fma(dt, gn[i], p[i]); }
+            }
+        }
+        // ================= owners: proposal store, sub-tree sums, push (all speculative) =================
+        const int k = live ? (__ffs(~ileaf) - 1) : 0;                       // merges this leaf completes (Tree._build_subtree)
+        const bool last = live && (ileaf + 1 == (1 << depth));
+        const int kmax = __reduce_max_sync(BFB_FULL, k);
+        {
+            OST(sPBUF, p)
+            if (live) { double *slot = gpr + (size_t)nslot * 2 * SLOT; OST(slot, q) OST(slot + SLOT, g) }
+            double rpl[NRW], rps[NRW];
+#pragma unroll
+            for (int i = 0; i < NRW; ++i) { rpl[i] = p[i]; rps[i] = p[i]; }
+            if (kmax >= 1) {
+                double s0[NRW];
+                OLD(s0, sS0)
+                if (k >= 1) {
+#pragma unroll
+                    for (int i = 0; i < NRW; ++i) { rpl[i] = s0[i]; rps[i] += s0[i]; }
+                }
+#pragma unroll 1
+                for (int l = 1; l < kmax; ++l) {
+                    const double *sp = stk(l);
+                    double a[NRW], b[NRW];
+                    OLD(a, sp) OLD(b, sp + 2 * SLOT)
+                    if (k > l) {
+#pragma unroll
+                        for (int i = 0; i < NRW; ++i) { rpl[i] = a[i]; rps[i] += b[i]; }
+                    }
+                }
+            }
+            if (last) {
+                OST(sRL, rpl) OST(sRS, rps)
+#pragma unroll
+                for (int i = 0; i < NRW; ++i) rpsf[i] = rps[i];
+            } else if (live) {
+                if (k == 0) { OST(sS0, p) }
+                else { double *sp = stk(k); OST(sp, rpl) OST(sp + SLOT, p) OST(sp + 2 * SLOT, rps) }
+            }
+        }
+        team_bar(bar_id);
+        // ================= tasks: U-turn dot products of all merges of this leaf and of Tree.extend =================
+#pragma unroll 1
+        for (int l = 0; l < kmax; ++l) {
+            if (((l + 1) & 3) != w) continue;
+            double v0 = 0., v1 = 0., v2 = 1., v3 = 1., v4 = 1., v5 = 1.;
+            if (l == 0) {
+#pragma unroll
+                for (int r = 0; r < NR; ++r) {
+                    const int e = r * 32 + lane;
+                    const double pr = sPBUF[e], vr = sVAR[e], t1 = sS0[e];
+                    const double ps = t1 + pr;
+                    v0 = fma(ps, vr * t1, v0); v1 = fma(ps, vr * pr, v1);
+                }
+            } else {
+                v2 = v3 = v4 = v5 = 0.;
+                const double *sp = stk(l), *spm = (l == 1) ? sS0 : stk(l - 1);
+#pragma unroll 1
+                for (int r = 0; r < NR; ++r) {
+                    const int e = r * 32 + lane;
+                    const double pr = sPBUF[e], vr = sVAR[e];
+                    const double T1pl = sp[e], T1pr = sp[SLOT + e], T1ps = sp[2 * SLOT + e], Rpl = spm[e];
+                    double Rps = pr + sS0[e];
+                    for (int m = 1; m < l; ++m) Rps += stk(m)[2 * SLOT + e];
+                    const double ps = T1ps + Rps, ps1 = T1ps + Rpl, ps2 = T1pr + Rps;
+                    const double vT1pl = vr * T1pl, vp = vr * pr;
+                    v0 = fma(ps, vT1pl, v0); v1 = fma(ps, vp, v1);
+                    v2 = fma(ps1, vT1pl, v2); v3 = fma(ps1, vr * Rpl, v3);
+                    v4 = fma(ps2, vr * T1pr, v4); v5 = fma(ps2, vp, v5);
+                }
+            }
+            const bool turning = team_any_nonpos6(v0, v1, v2, v3, v4, v5, lane);
+            const unsigned bal = __ballot_sync(BFB_FULL, turning);
+            if (lane == 0) ci[8 + l] = (int)bal;
+        }
+        if (w == 3 && __any_sync(BFB_FULL, last)) {
+            // Tree.extend, nuts.py:86-101 (self.p_sum is updated in place BEFORE p_sum1 / p_sum2 are formed)
+            const bool right = step > 0.;
+            double v0 = 0., v1 = 0., v2 = 0., v3 = 0., v4 = 0., v5 = 0.;
+#pragma unroll 1
+            for (int r = 0; r < NR; ++r) {
+                const int e = r * 32 + lane;
+                const double pr = sPBUF[e], vr = sVAR[e], Rpl = sRL[e], Rps = sRS[e], PBr = sPB[e];
+                const double PSn = sPS[e] + Rps;
+                const double TLp = right ? sTLP[e] : pr, TRp = right ? pr : sTRP[e];
+                const double vp = vr * pr, vRpl = vr * Rpl, vPB = vr * PBr, vTL = vr * TLp, vTR = vr * TRp;
+                v0 = fma(PSn, vTL, v0); v1 = fma(PSn, vTR, v1);
+                if (right) {
+                    const double ps1 = PSn + Rpl, ps2 = PBr + Rps;
+                    v2 = fma(ps1, vTL, v2); v3 = fma(ps1, vRpl, v3); v4 = fma(ps2, vPB, v4); v5 = fma(ps2, vp, v5);
+                } else {
+                    const double ps1 = Rps + PBr, ps2 = Rpl + PSn;
+                    v2 = fma(ps1, vp, v2); v3 = fma(ps1, vPB, v3); v4 = fma(ps2, vRpl, v4); v5 = fma(ps2, vTR, v5);
+                }
+            }
+            const bool turning = team_any_nonpos6(v0, v1, v2, v3, v4, v5, lane);
+            const unsigned bal = __ballot_sync(BFB_FULL, turning);
+            if (lane == 0) ci[20] = (int)bal;
+        }
+        // ================= leader: the leaf (Tree._single_step, nuts.py:105-132) and this round's uniforms =================
+        double E = 0., ub0 = 0., ub1 = 0.;
+        WT wl; wl.m = 0.; wl.k = 0;
+        bool div_leaf = false, okl = false;
+        int64_t tb2 = 0;
+        if (lead) {
+            E = 0.5 * ke2 - lp;
+            double dE = E - E0;
+            if (isnan(dE)) dE = INFINITY;
+            if (live) {
+                if (fabs(dE) > fabs(maxdE)) maxdE = dE;
+                n_prop += 1;
+                div_leaf = !(fabs(dE) < cfg.max_change);
+            }
+            wl = wt_from_dE(div_leaf ? 0. : dE);
+            okl = live && !div_leaf;
+            if (okl) { acc_sum += wt_min1(wl); freemask &= ~(1u << nslot); }
+            if (div_leaf) diverging = 1;
+            // lane lg of a quad holds draws 2 (t/2 + lg) + {0, 1} of its chain
+            tb2 = (t >> 1) << 1;
+            const uint64_t blk = (uint64_t)(t >> 1) + (uint64_t)lg;
+            const bfb_philox_block b = bfb_philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)chain_id, (uint32_t)(chain_id >> 32),
+                                                         (uint32_t)seed, (uint32_t)(seed >> 32));
+            ub0 = bfb_u64_to_uniform((uint64_t)b.v[0] | ((uint64_t)b.v[1] << 32));
+            ub1 = bfb_u64_to_uniform((uint64_t)b.v[2] | ((uint64_t)b.v[3] << 32));
+        }
+        team_bar(bar_id);
+        // ================= leader: merges (Tree._build_subtree, nuts.py:134-178), Tree.extend, iteration end =================
+        if (lead) {
+            auto uni = [&](int64_t tt) -> double {
+                const int kk = (int)(tt - tb2);
+                const int sl = (lane & ~3) | ((kk >> 1) & 3);
+                const double a0 = __shfl_sync(BFB_FULL, ub0, sl), a1 = __shfl_sync(BFB_FULL, ub1, sl);
+                double u = (kk & 1) ? a1 : a0;
+                if (__any_sync(BFB_FULL, kk >= 8)) { if (kk >= 8) u = team_draw_uniform(seed, chain_id, (uint64_t)tt); }
+                return u;
+            };
+            WT RW = wl;
+            double REp = E, Rlpp = lp;
+            int Rslot = nslot;
+            bool turn = false;
+            int lvl = 0;
+            bool need = okl && (ileaf & 1);
+#pragma unroll 1
+            while (__any_sync(BFB_FULL, need)) {
+                const int lv = need ? lvl : 0;
+                const bool turning = (ci[8 + lv] >> (gi * 4)) & 1;
+                const double um = uni(t);
+                if (need) {
+                    t += 1;
+                    WT T1W; T1W.m = ssc[lv * 8]; T1W.k = (int)ssc[(10 + lv) * 8];
+                    const int T1slot = (int)ssc[(40 + lv) * 8];
+                    const WT tot = wt_add(T1W, RW);
+                    if (!wt_select(um, tot, RW)) {               // keep tree1's proposal (nuts.py:164-167)
+                        freemask |= 1u << Rslot;
+                        Rslot = T1slot; REp = ssc[(20 + lv) * 8]; Rlpp = ssc[(30 + lv) * 8];
+                    } else {
+                        freemask |= 1u << T1slot;
+                    }
+                    RW = tot;
+                    if (turning) turn = true;
+                    lvl++;
+                }
+                need = need && !turn && ((ileaf >> lvl) & 1);
+            }
+            const bool fin = live && (div_leaf || turn || last);
+            if (live && !fin) {
+                ssc[lvl * 8] = RW.m; ssc[(10 + lvl) * 8] = (double)RW.k; ssc[(20 + lvl) * 8] = REp; ssc[(30 + lvl) * 8] = Rlpp;
+                ssc[(40 + lvl) * 8] = (double)Rslot;
+            }
+            int cmn = 0;
+            bool iter_end = false;
+            if (__any_sync(BFB_FULL, fin)) {
+                // ---- end of a doubling: Tree.extend, nuts.py:45-103 ----
+                const double ue = uni(t);
+                const bool ok = fin && !div_leaf && !turn;
+                if (ok) {
+                    const bool eturn = (ci[20] >> (gi * 4)) & 1;
+                    t += 1;
+                    const WT tot = wt_add(Wtree, RW);
+                    if (wt_select(ue, Wtree, RW)) {               // nuts.py:81-83 biased progressive: log(u) < size2 - size1
+                        freemask |= 1u << prop_slot;
+                        prop_slot = Rslot; prop_E = REp; prop_lp = Rlpp;
+                    } else {
+                        freemask |= 1u << Rslot;
+                    }
+                    Wtree = tot;
+                    if (eturn) turn = true;
+                }
+                iter_end = fin && (div_leaf || turn || (depth + 1 >= cfg.max_treedepth));
+                if (fin) cmn = TC_FIN | (ok ? TC_OK : 0) | (iter_end ? TC_IEND : 0);
+                if (__any_sync(BFB_FULL, iter_end)) {
+                    // ---- end of the iteration: base_hmc.py:77-85 ----
+                    const bool warm_old = (it0 + it) < cfg.n_warmup;
+                    const double accept_stat = acc_sum / (double)(n_prop > 0 ? n_prop : 1);
+                    if (__any_sync(BFB_FULL, iter_end && warm_old && cfg.adapt_step_size)) {      // step_size.py:31-45
+                        const bool da = iter_end && warm_old && cfg.adapt_step_size;
+                        const double hbar0 = st.hbar[c], mu_da = st.mu_da[c];
+                        const int64_t count = st.count[c];
+                        __syncwarp();
+                        const double cnt = (double)count;
+                        const double ww = 1. / (cnt + cfg.t0);
+                        const double hbar = ((1. - ww) * hbar0 + ww * (cfg.target_accept - accept_stat));
+                        const double ls_ = mu_da - hbar * sqrt(cnt) / cfg.gamma;
+                        const double mk = pow(cnt, -cfg.k);
+                        const double lb_ = mk * ls_ + (1. - mk) * log_bar;
+                        const double es_ = exp(ls_), eb_ = exp(lb_);
+                        if (da) {
+                            log_step = ls_; log_bar = lb_; e_step = es_; e_bar = eb_;
+                            if (lg == 0) { st.hbar[c] = hbar; st.log_step[c] = log_step; st.log_bar[c] = log_bar; st.count[c] = count + 1; }
+                        }
+                    }
+                    if (iter_end) {
+                        if (lg == 0) {
+                            const size_t orow = (size_t)c * out.n_iter + it;
+                            if (out.o.logp) out.o.logp[orow] = prop_lp;
+                            if (out.o.energy) out.o.energy[orow] = prop_E;
+                            if (out.o.tree_depth) out.o.tree_depth[orow] = depth + 1;
+                            if (out.o.tree_size) out.o.tree_size[orow] = n_prop;
+                            if (out.o.mean_tree_accept) out.o.mean_tree_accept[orow] = accept_stat;
+                            if (out.o.step_size) out.o.step_size[orow] = e_step;
+                            if (out.o.step_size_bar) out.o.step_size_bar[orow] = e_bar;
+                            if (out.o.energy_change) out.o.energy_change[orow] = prop_E - E0;
+                            if (out.o.max_energy_change) out.o.max_energy_change[orow] = maxdE;
+                            if (out.o.diverging) out.o.diverging[orow] = diverging;
+                        }
+                        logp_q = prop_lp;
+                        tree_total += (unsigned)n_prop;
+                        const bool stop = (it + 1 >= it_hi);
+                        cmn |= TC_ENDP | (prop_slot << 8) | (stop ? TC_STOP : TC_START);
+                        freemask = ((1u << BFB_NSLOT) - 1u) & ~(1u << prop_slot);
+                        if (!stop) {
+                            const bool warm_new = (it0 + it + 1) < cfg.n_warmup;
+                            cdv[gi] = warm_new ? e_step : e_bar; cdv[8 + gi] = logp_q; cdv[16 + gi] = __longlong_as_double(t);
+                            t += n;
+                        }
+                    }
+                }
+                // ---- direction of the next doubling (nuts.py:210), of this iteration or of the next one ----
+                const bool nd = fin && !(cmn & TC_STOP);
+                const double ud = uni(t);
+                if (nd) { t += 1; if (ud < 0.5) cmn |= TC_RIGHT; }
+            }
+            if (live) cmn |= (__ffs(freemask) - 1) << 4;
+            if (lg == 0) ci[gi] = cmn;
+        }
+        team_bar(bar_id);
+    }
+
+    // ---- persist chain state ----
+    if (exists && status0 == 0) {
+#pragma unroll
+        for (int i = 0; i < NRW; ++i) {
+            const int j = 4 * (NRW * w + i) + lg;
+            st.q[vb + j] = q[i]; st.g[vb + j] = g[i]; st.var[vb + j] = var[i];
+        }
+        if (scribe) {
+            st.logp[c] = logp_q; st.t_draw[c] = t; st.iter[c] = it0 + it;
+            st.status[c] = status;
+            st.fg_n[c] = fg_n; st.bg_n[c] = bg_n; st.n_samples[c] = n_samples; st.previous_update[c] = previous_update;
+            st.adapt_window[c] = adapt_window;
+            if (tree_total) atomicAdd(st.tree_total, (unsigned long long)tree_total);
+        }
+    }
+    __threadfence();
+    team_bar(bar_id);
+    if (leader) {
+        qv[2 + group] = chunk + 1;
+        if ((chunk + 1) * chunk_iters < out.n_iter) {
+            const int ti = atomicAdd(queue + 1, 1);
+            __threadfence();
+            ring[ti] = group;
+        }
+    }
+    }   // unit loop
+#undef OWN
+#undef OLD
+#undef OST
+}
+
+template <int NR, int MV, int G>
+static int launch_nuts_team(bfb_context *h, const bfb_run_out &o, int n_iter)
+{
+    using TS = TeamShape<NR, MV>;
+    constexpr int SLOT = TS::SLOT;
+    const int L = h->scfg.max_treedepth;
+    const int64_t C = h->cs.C;
+    const int n_groups = (int)((C + 7) / 8);
+    // stack levels 1..LS in shared memory, deeper (rarely touched) levels in an L2-resident buffer
+    const size_t fixed = sizeof(double) * (TS::TAB_DOUBLES + 64);
+    int LS = L - 1;
+    while (LS > 0 && fixed + sizeof(double) * G * team_nuts_doubles(SLOT, LS) > (size_t)(227 * 1024)) --LS;
+    if (const char *e = getenv("BFB200_STACK_LEVELS_SMEM")) { int v = atoi(e); if (v >= 0 && v < LS) LS = v; }
+    const size_t smem = fixed + sizeof(double) * G * team_nuts_doubles(SLOT, LS);
+    if (smem > (size_t)(227 * 1024)) return 1;
+    BFB_CUDA(cudaFuncSetAttribute(nuts_team_kernel<NR, MV, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t deep = (size_t)(L - 1 > LS ? L - 1 - LS : 0) * 3 * SLOT;
+    const size_t prop = (size_t)BFB_NSLOT * 2 * SLOT;
+    if ((deep + prop) * (size_t)n_groups > h->gstack_len) {
+        if (h->gstack) cudaFree(h->gstack);
+        h->gstack = nullptr; h->gstack_len = 0;
+        BFB_CUDA(cudaMalloc((void **)&h->gstack, sizeof(double) * (deep + prop) * (size_t)n_groups));
+        h->gstack_len = (deep + prop) * (size_t)n_groups;
+    }
+    RunOutDevF od;
+    od.o = o; od.n_iter = n_iter;
+    int blocks = h->sm_count;
+    if ((int64_t)blocks > n_groups) blocks = n_groups;
+    int chunk_iters, n_units, rc;
+    if ((rc = team_queue_setup(h, n_groups, n_iter, blocks * G, chunk_iters, n_units))) return rc;
+    nuts_team_kernel<NR, MV, G><<<blocks, 128 * G, smem, h->stream>>>(h->dm, h->scfg, h->cs, od, L, LS, h->gstack,
+                                                                     h->gstack + deep * (size_t)n_groups, (int)h->iters_done,
+                                                                     chunk_iters, n_groups, n_units, h->queue);
+    h->launches++;
+    BFB_CUDA(cudaGetLastError());
+    return BFB_OK;
+}
+
+template <int NR, int MV>
+static int launch_nuts_team_g(bfb_context *h, const bfb_run_out &o, int n_iter)
+{
+    int G = 4;
+    if (const char *e = getenv("BFB200_TEAMS_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 5) G = v; }
+    switch (G) {
+    case 1: return launch_nuts_team<NR, MV, 1>(h, o, n_iter);
+    case 2: return launch_nuts_team<NR, MV, 2>(h, o, n_iter);
+    case 3: return launch_nuts_team<NR, MV, 3>(h, o, n_iter);
+    case 5: return launch_nuts_team<NR, MV, 5>(h, o, n_iter);
+    }
+    return launch_nuts_team<NR, MV, 4>(h, o, n_iter);
+}
+
+// returns 1 if this path does not apply (caller tries the next kernel), 0 on launch, <0 on error
+int bfb_launch_nuts_team(bfb_context *h, const bfb_run_out &o, int n_iter)
+{
+    const DevModel &M = h->dm;
+    if (M.epilogue || !M.tfrag || M.frag_nr == 0 || M.frag_ext || M.has_c3) return 1;
+    if (h->scfg.max_treedepth > 10 || h->scfg.max_treedepth < 1) return 1;
+    if (const char *e = getenv("BFB200_SAMPLER")) { if (strcmp(e, "team")) return 1; }
+    const int mv = M.has_c2 ? 1 : 0;
+#define BFB_CASE(NR_, MV_) if (M.frag_nr == NR_ && mv == MV_) return launch_nuts_team_g<NR_, MV_>(h, o, n_iter);
     BFB_CASE(4, 0) BFB_CASE(4, 1) BFB_CASE(7, 0) BFB_CASE(7, 1) BFB_CASE(8, 0) BFB_CASE(8, 1)
 #undef BFB_CASE
     return 1;

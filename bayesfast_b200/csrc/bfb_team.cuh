@@ -55,6 +55,20 @@ __device__ __forceinline__ double qrs4(double a, double b, double c, double d, i
     return k;
 }
 
+// per chain: is any of the six sums over its 4 lanes <= 0 ?  (U-turn tests, packed reduction over the quad)
+__device__ __forceinline__ bool team_any_nonpos6(double v0, double v1, double v2, double v3, double v4, double v5, int lane)
+{
+    const bool b0 = lane & 1, b1 = lane & 2;
+    double k0 = b0 ? v4 : v0, k1 = b0 ? v5 : v1, k2 = b0 ? 1. : v2, k3 = b0 ? 1. : v3;
+    const double s0 = b0 ? v0 : v4, s1 = b0 ? v1 : v5, s2 = b0 ? v2 : 1., s3 = b0 ? v3 : 1.;
+    k0 += shx4(s0, 1); k1 += shx4(s1, 1); k2 += shx4(s2, 1); k3 += shx4(s3, 1);
+    double m0 = b1 ? k2 : k0, m1 = b1 ? k3 : k1;
+    const double t0 = b1 ? k0 : k2, t1 = b1 ? k1 : k3;
+    m0 += shx4(t0, 2); m1 += shx4(t1, 2);
+    const unsigned bal = __ballot_sync(BFB_FULL, (m0 <= 0.) || (m1 <= 0.));
+    return ((bal >> (lane & ~3)) & 0xfu) != 0u;
+}
+
 // Four sums over all dimensions of each of the 8 chains of the team.  red: the team's RED_DOUBLES, rbuf: which half is
 // written next (flips).  Every lane of every warp returns the same totals a, b; c and d are summed by the leader warp
 // (w == 0) only -- FP64 additions cost pipe cycles that the DMMAs need (the other warps get their own partials back).

@@ -217,12 +217,17 @@ def test_work_queue_chunking_is_invisible(handle, monkeypatch):
     (31, 'cubic-2', 40, 30, {}),
     (5, 'cubic-2', 50, 40, {}),
     (26, 'quadratic', 100, 40, {}),
+    (26, 'cubic-2', 203, 40, {'BFB200_TEAMS_PER_SM': '3', 'BFB200_STACK_LEVELS_SMEM': '0'}),
+    (16, 'quadratic', 33, 40, {'BFB200_TEAMS_PER_SM': '5', 'BFB200_CHUNK_ITERS': '9'}),
 ])
-def test_tensor_core_nuts_vs_oracle(handle, oracle, monkeypatch, n, order, C, n_iter, env):
-    """bfb_sampler_dmma.cu (8 chains per warp as the rows of FP64 DMMAs): per-chain tree depths / sizes / divergences and
-    draw counts identical to the oracle fed with the device's own draws, and to the generic warp-per-chain kernel"""
+@pytest.mark.parametrize('family', ['team', 'dmma'])
+def test_tensor_core_nuts_vs_oracle(handle, oracle, monkeypatch, n, order, C, n_iter, env, family):
+    """bfb_sampler_team.cu (8 chains per team of four warps) / bfb_sampler_dmma.cu (8 chains per warp), the chains as the rows
+    of FP64 DMMAs: per-chain tree depths / sizes / divergences and draw counts identical to the oracle fed with the device's
+    own draws, and to the generic warp-per-chain kernel"""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
+    monkeypatch.setenv('BFB200_SAMPLER', family)
     spec, cov = synthetic_spec(n, order, seed=70 + n)              # radial bound, no decay / transform: the headline shape
     spec['alpha'] = spec['alpha'] / 1.6 * 0.9                      # tight bound: many leapfrogs leave the ellipsoid
     handle.set_model(to_device_spec(spec))
@@ -232,7 +237,7 @@ def test_tensor_core_nuts_vs_oracle(handle, oracle, monkeypatch, n, order, C, n_
     step0 = 1. / n**0.25
     handle.sampler_init(cfg, x0, step0, np.ones(n), x0)
     out = handle.sampler_run('NUTS', n_iter)
-    assert handle.sampler_last_path() == 'dmma'
+    assert handle.sampler_last_path() == family
     st = handle.sampler_state()
     assert np.all(st['status'] == 0)
     U, Z = device_draws(handle, seed, st['n_draws'], chain0)
@@ -241,11 +246,14 @@ def test_tensor_core_nuts_vs_oracle(handle, oracle, monkeypatch, n, order, C, n_
     assert np.array_equal(st['n_draws'], ref['n_draws'])
     for k in INT_STATS:
         assert np.array_equal(out[k], ref[k]), k
+    # late tolerance: with the tight bound single chains amplify rounding differences ~10x every two iterations (scripts/
+    # team_debug.py: 1e-15 at iteration 1, 1e-9 at 10, 1e-3 at 18 for BOTH kernel families against the oracle, which sums in
+    # a third order); the decisions above must agree regardless
     for k in FLT_STATS:
-        check_floats(out[k], ref[k], k)
-    check_floats(out['samples'], ref['samples'], 'samples')
+        check_floats(out[k], ref[k], k, late=5e-3)
+    check_floats(out['samples'], ref['samples'], 'samples', late=5e-3)
     assert out['total_tree_size'] == int(ref['tree_size'].sum())
-    assert np.allclose(st['final_var'], ref['final_var'], rtol=LATE_TOL)
+    assert np.allclose(st['final_var'], ref['final_var'], rtol=5e-3)
     # same run on the generic kernel
     monkeypatch.setenv('BFB200_SAMPLER', 'generic')
     handle.sampler_init(cfg, x0, step0, np.ones(n), x0)
@@ -255,8 +263,10 @@ def test_tensor_core_nuts_vs_oracle(handle, oracle, monkeypatch, n, order, C, n_
         assert np.array_equal(out[k], gen[k]), k
 
 
-def test_tensor_core_nuts_resume_and_reset(handle):
+@pytest.mark.parametrize('family', ['team', 'dmma'])
+def test_tensor_core_nuts_resume_and_reset(handle, monkeypatch, family):
     """chain state survives between launches (bfb_sampler_run called twice == once), and bfb_sampler_reset restarts it"""
+    monkeypatch.setenv('BFB200_SAMPLER', family)
     n, C = 26, 96
     spec, cov = synthetic_spec(n, 'cubic-2', seed=12)
     handle.set_model(to_device_spec(spec))
@@ -264,7 +274,7 @@ def test_tensor_core_nuts_resume_and_reset(handle):
     cfg = cfg_from({}, 30, 31)
     handle.sampler_init(cfg, x0, 1. / n**0.25, np.ones(n), x0)
     a = handle.sampler_run('NUTS', 50)
-    assert handle.sampler_last_path() == 'dmma'
+    assert handle.sampler_last_path() == family
     handle.sampler_reset()
     b1 = handle.sampler_run('NUTS', 20)
     b2 = handle.sampler_run('NUTS', 30)
@@ -354,12 +364,14 @@ def test_tensor_core_extended_density(handle, oracle, monkeypatch, n, order, sam
     assert np.array_equal(out['tree_depth'], gen['tree_depth']) and np.array_equal(out['diverging'], gen['diverging'])
 
 
+@pytest.mark.parametrize('family', ['team', 'dmma'])
 @pytest.mark.parametrize('env', [{}, {'BFB200_STACK_LEVELS_SMEM': '2'}])
-def test_tensor_core_nuts_deep_trees(handle, oracle, monkeypatch, env):
+def test_tensor_core_nuts_deep_trees(handle, oracle, monkeypatch, env, family):
     """tiny fixed step size: trees reach depth 8-10 (up to 1023 leaves), i.e. every stack level, the L2-resident deep
     levels, the proposal-slot pool and the depth cap are exercised; outcomes identical to the oracle"""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
+    monkeypatch.setenv('BFB200_SAMPLER', family)
     n, C, n_iter = 26, 19, 5
     spec, cov = synthetic_spec(n, 'cubic-2', seed=5)
     handle.set_model(to_device_spec(spec))
@@ -368,7 +380,7 @@ def test_tensor_core_nuts_deep_trees(handle, oracle, monkeypatch, env):
     step0 = 0.0035
     handle.sampler_init(cfg, x0, step0, np.ones(n), x0)
     out = handle.sampler_run('NUTS', n_iter)
-    assert handle.sampler_last_path() == 'dmma'
+    assert handle.sampler_last_path() == family
     assert out["tree_depth"].max() == 10 and out["tree_depth"].min() >= 8
     st = handle.sampler_state()
     U, Z = device_draws(handle, 55, st['n_draws'])
