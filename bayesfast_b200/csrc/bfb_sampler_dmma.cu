@@ -65,6 +65,19 @@ static __device__ __noinline__ double2 philox_pair_ni(uint64_t seed, uint64_t ch
     u1 = bfb_u64_to_uniform((uint64_t)b.v[2] | ((uint64_t)b.v[3] << 32));
     return make_double2(u0, u1);
 }
+// Nesterov dual averaging of the step size, step_size.py:31-45 -- out of line: pow and exp are ~250 instructions that only
+// warm-up iteration boundaries execute, and the hot loop is larger than the instruction cache
+static __device__ __noinline__ void dual_average_ni(double cnt, double hbar0, double mu_da, double accept_stat, double log_bar,
+                                                    double t0, double target, double gamma, double kk,
+                                                    double &hbar, double &log_step, double &log_bar_new, double &e_step, double &e_bar)
+{
+    const double w = 1. / (cnt + t0);
+    hbar = ((1. - w) * hbar0 + w * (target - accept_stat));
+    log_step = mu_da - hbar * sqrt(cnt) / gamma;
+    const double mk = pow(cnt, -kk);
+    log_bar_new = mk * log_step + (1. - mk) * log_bar;
+    e_step = exp(log_step); e_bar = exp(log_bar_new);
+}
 __device__ __forceinline__ int64_t shfl64(int64_t v, int src)
 {
     return (int64_t)__shfl_sync(BFB_FULL, (long long)v, src);
@@ -193,17 +206,12 @@ __global__ void __launch_bounds__(32 * W, 1) nuts_dmma_kernel(DevModel M, bfb_sa
                 const double hbar0 = st.hbar[c], mu_da = st.mu_da[c];
                 const int64_t count = st.count[c];
                 __syncwarp();
+                double hbar_, ls_, lb_, es_, eb_;
+                dual_average_ni((double)count, hbar0, mu_da, accept_stat, log_bar, cfg.t0, cfg.target_accept, cfg.gamma, cfg.k, hbar_, ls_, lb_, es_, eb_);
                 if (endp && warm_old && cfg.adapt_step_size) {
-                    const double cnt = (double)count;
-                    const double w = 1. / (cnt + cfg.t0);
-                    const double hbar = ((1. - w) * hbar0 + w * (cfg.target_accept - accept_stat));
-                    log_step = mu_da - hbar * sqrt(cnt) / cfg.gamma;
-                    const double mk = pow(cnt, -cfg.k);
-                    log_bar = mk * log_step + (1. - mk) * log_bar;
-                    if (lg == 0) { st.hbar[c] = hbar; st.log_step[c] = log_step; st.log_bar[c] = log_bar; st.count[c] = count + 1; }
+                    log_step = ls_; log_bar = lb_; e_step = es_; e_bar = eb_;
+                    if (lg == 0) { st.hbar[c] = hbar_; st.log_step[c] = log_step; st.log_bar[c] = log_bar; st.count[c] = count + 1; }
                 }
-                const double es_ = exp(log_step), eb_ = exp(log_bar);
-                if (endp && warm_old && cfg.adapt_step_size) { e_step = es_; e_bar = eb_; }
             }
             if (endp) {
                 if (lg == 0) {
