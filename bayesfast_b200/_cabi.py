@@ -47,6 +47,10 @@ class RunOut(C.Structure):
                 ('tree_depth', C.c_void_p), ('tree_size', C.c_void_p), ('diverging', C.c_void_p)]
 
 
+class RunOpts(C.Structure):
+    _fields_ = [('skip', C.c_int32), ('thin', C.c_int32), ('mean', C.c_void_p), ('cov', C.c_void_p)]
+
+
 FLOAT_STATS = ('logp', 'energy', 'mean_tree_accept', 'step_size', 'step_size_bar', 'energy_change',
                'max_energy_change')
 INT_STATS = ('tree_depth', 'tree_size', 'diverging')
@@ -83,6 +87,7 @@ def lib():
             L.bfb_sampler_get_cov.argtypes = [C.c_void_p, _dp, _ip]
             L.bfb_sampler_reset.argtypes = [C.c_void_p]
             L.bfb_sampler_run.argtypes = [C.c_void_p, C.c_int, C.c_int32, C.POINTER(RunOut), C.c_int, _lp]
+            L.bfb_sampler_run_ex.argtypes = [C.c_void_p, C.c_int, C.c_int32, C.POINTER(RunOut), C.c_int, C.POINTER(RunOpts), _lp]
             L.bfb_sampler_get_state.argtypes = [C.c_void_p, _dp, _dp, _lp, _ip, _dp]
             L.bfb_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
             L.bfb_launch_count.argtypes = [C.c_void_p]
@@ -167,6 +172,7 @@ class Handle:
         """spec: the dict produced by PolyModel.to_spec() / Density.to_spec() with packed coefficients
         (key 'packed' per config, shape (n_out, n_packed))."""
         n, m = int(spec['n']), int(spec['m'])
+        self.generation = getattr(self, 'generation', 0) + 1      # chains set up before this call belong to another model
         cfgs = spec['configs']
         d = ModelDesc()
         order = np.array([ORDER_CODE[c['order']] for c in cfgs], np.int32)
@@ -243,6 +249,7 @@ class Handle:
     # ------------------------------------------------------------------ sampler
     def sampler_init(self, cfg, x0, step0, var0, mean0, dense=False):
         n = self.n
+        self.generation = getattr(self, 'generation', 0) + 1      # a TraceTuple of earlier chains can no longer be continued
         x0 = f64(x0).reshape(-1, n)
         nc = x0.shape[0]
         c = SamplerCfg()
@@ -260,32 +267,44 @@ class Handle:
             check(self._L.bfb_sampler_init(self._h, C.byref(c), nc, _d(x0), _d(step0), _d(var0), _d(mean0)))
         self.n_chain = nc
 
-    def sampler_run(self, sampler, n_iter, out_ptrs=None, fields=None):
-        """Host outputs (default): returns dict of numpy arrays [C, n_iter(, n)].
-        out_ptrs: dict name -> device pointer (int) for device-resident outputs."""
+    def sampler_run(self, sampler, n_iter, out_ptrs=None, fields=None, skip=0, thin=1, summaries=False):
+        """Host outputs (default): returns dict of numpy arrays [C, n_keep(, n)], n_keep = ceil((n_iter - skip) / thin):
+        the records of the first `skip` iterations are not produced, of the rest every thin-th is kept ('iters': their
+        iteration index within this call).  summaries: 'mean' [n] and 'cov' [n, n] of the samples of all iterations after
+        `skip` over all chains, accumulated on the device (bfb_sampler_run_ex).
+        out_ptrs: dict name -> device pointer (int) for device-resident outputs, laid out [C, n_iter - skip(, n)]."""
         ro = RunOut()
         res = {}
         nc, n = self.n_chain, self.n
+        skip, thin = int(skip), int(thin)
+        n_keep = (int(n_iter) - skip + thin - 1) // thin
         if out_ptrs is None:
             want = fields if fields is not None else ('samples',) + FLOAT_STATS + INT_STATS
             from . import _pinned
             for k in want:
                 if k == 'samples':
-                    res[k] = _pinned.empty((nc, n_iter, n))
+                    res[k] = _pinned.empty((nc, n_keep, n))
                 elif k in FLOAT_STATS:
-                    res[k] = _pinned.empty((nc, n_iter))
+                    res[k] = _pinned.empty((nc, n_keep))
                 else:
-                    res[k] = _pinned.empty((nc, n_iter), np.int32)
+                    res[k] = _pinned.empty((nc, n_keep), np.int32)
                 setattr(ro, k, res[k].ctypes.data)
             loc = BFB_HOST
         else:
             for k, p in out_ptrs.items():
                 setattr(ro, k, int(p))
             loc = BFB_DEVICE
+        op = RunOpts()
+        op.skip, op.thin = skip, thin
+        if summaries:
+            res['mean'], res['cov'] = np.empty(n), np.empty((n, n))
+            op.mean, op.cov = res['mean'].ctypes.data, res['cov'].ctypes.data
         tot = C.c_int64(0)
-        check(self._L.bfb_sampler_run(self._h, SAMPLER_CODE[sampler.upper()], int(n_iter), C.byref(ro), loc,
-                                      C.byref(tot)))
+        check(self._L.bfb_sampler_run_ex(self._h, SAMPLER_CODE[sampler.upper()], int(n_iter), C.byref(ro), loc,
+                                         C.byref(op), C.byref(tot)))
         res['total_tree_size'] = int(tot.value)
+        res['iters'] = skip + thin * np.arange(n_keep)
+        self.generation_runs = getattr(self, 'generation_runs', 0) + 1
         return res
 
     def sampler_reset(self):

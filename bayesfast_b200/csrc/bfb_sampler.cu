@@ -870,13 +870,72 @@ static int launch_run(bfb_context *h, int sampler, int n_iter, const bfb_run_out
 // byte size of one (chain, iteration) record of output field f (order of bfb_run_out)
 static size_t field_bytes(int f, int n) { return f == 0 ? sizeof(double) * n : (f <= 7 ? sizeof(double) : sizeof(int32_t)); }
 
+// ---- reduced outputs (bfb_sampler_run_ex): thinning and summaries on the device ----
+// dst[c][i] = src[c][i * thin] for records of `rec` doubles (samples: n) or of one 4-byte / 8-byte word
+template <class T>
+__global__ void thin_kernel(const T *__restrict__ src, T *__restrict__ dst, int64_t C, int K, int kk, int thin, int rec)
+{
+    const int64_t total = C * (int64_t)kk * rec;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int j = (int)(i % rec);
+        const int64_t r = i / rec;
+        const int it = (int)(r % kk);
+        const int64_t c = r / kk;
+        dst[i] = src[(c * K + (int64_t)it * thin) * rec + j];
+    }
+}
+// shifted first and second moments of the rows x[r][0..n): per-block partials part[b][n + n*n] (sum (x - s), sum (x - s)(x - s)^T),
+// rows dealt to the blocks in tiles of 32; a second kernel adds the partials in a fixed order (deterministic)
+static __global__ void __launch_bounds__(256) trace_moments_partial_kernel(const double *__restrict__ x, int64_t rows, int n, const double *__restrict__ shift,
+                                                             double *__restrict__ part)
+{
+    extern __shared__ double xs[];        // [32][n]
+    const int ne = n + n * n;
+    double acc[72];                       // entries tid, tid + 256, ...: n <= 128 -> at most 65 per thread
+    const int nacc = (ne + 255) / 256;
+    for (int a = 0; a < nacc; ++a) acc[a] = 0.;
+    for (int64_t r0 = (int64_t)blockIdx.x * 32; r0 < rows; r0 += (int64_t)gridDim.x * 32) {
+        const int nr = (int)((rows - r0 < 32) ? rows - r0 : 32);
+        __syncthreads();
+        for (int i = threadIdx.x; i < nr * n; i += 256) xs[i] = x[r0 * n + i] - shift[i % n];
+        __syncthreads();
+        for (int a = 0; a < nacc; ++a) {
+            const int e = threadIdx.x + a * 256;
+            if (e >= ne) break;
+            double v = acc[a];
+            if (e < n) { for (int r = 0; r < nr; ++r) v += xs[r * n + e]; }
+            else { const int j = (e - n) / n, k = (e - n) % n; for (int r = 0; r < nr; ++r) v = fma(xs[r * n + j], xs[r * n + k], v); }
+            acc[a] = v;
+        }
+    }
+    for (int a = 0; a < nacc; ++a) { const int e = threadIdx.x + a * 256; if (e < ne) part[(size_t)blockIdx.x * ne + e] = acc[a]; }
+}
+static __global__ void trace_moments_reduce_kernel(const double *__restrict__ part, int nb, int ne, double *__restrict__ accum)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= ne) return;
+    double v = accum[e];
+    for (int b = 0; b < nb; ++b) v += part[(size_t)b * ne + e];
+    accum[e] = v;
+}
+
 extern "C" int bfb_sampler_run(bfb_handle h, int sampler, int32_t n_iter, const bfb_run_out *out, int loc,
                                int64_t *total_tree_size)
+{
+    return bfb_sampler_run_ex(h, sampler, n_iter, out, loc, nullptr, total_tree_size);
+}
+
+extern "C" int bfb_sampler_run_ex(bfb_handle h, int sampler, int32_t n_iter, const bfb_run_out *out, int loc,
+                                  const bfb_run_opts *opts, int64_t *total_tree_size)
 {
     BFB_REQUIRE(h && h->has_model && h->has_chains, BFB_ERR_STATE, "bfb_sampler_run: call bfb_sampler_init first");
     BFB_REQUIRE(sampler == BFB_NUTS || sampler == BFB_HMC, BFB_ERR_ARG, "unknown sampler %d", sampler);
     BFB_REQUIRE(n_iter > 0 && out, BFB_ERR_ARG, "bfb_sampler_run: bad arguments");
     BFB_REQUIRE(sampler != BFB_HMC || h->scfg.n_int_step > 0, BFB_ERR_ARG, "n_int_step must be positive");
+    const int skip = opts ? opts->skip : 0, thin = opts ? opts->thin : 1;
+    const bool want_mom = opts && (opts->mean || opts->cov);
+    BFB_REQUIRE(skip >= 0 && skip <= n_iter && thin >= 1, BFB_ERR_ARG, "bfb_sampler_run_ex: need 0 <= skip <= n_iter and thin >= 1");
+    BFB_REQUIRE(loc == BFB_HOST || (thin == 1 && !want_mom), BFB_ERR_ARG, "bfb_sampler_run_ex: thinning and summaries need host outputs");
     BFB_CUDA(cudaSetDevice(h->device));
     const int64_t C = h->cs.C;
     const int n = h->n;
@@ -884,23 +943,36 @@ extern "C" int bfb_sampler_run(bfb_handle h, int sampler, int32_t n_iter, const 
                             out->energy_change, out->max_energy_change, out->tree_depth, out->tree_size, out->diverging};
     BFB_CUDA(cudaMemsetAsync(h->cs.tree_total, 0, 16 * sizeof(unsigned long long), h->stream));
     unsigned long long tt = 0;
-    if (loc == BFB_DEVICE) {
-        BFB_CUDA(cudaEventRecord(h->ev0, h->stream));
-        int rc = launch_run(h, sampler, n_iter, *out);
+    const bfb_run_out none = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    BFB_CUDA(cudaEventRecord(h->ev0, h->stream));
+    if (skip > 0) {                         // warm-up iterations whose records nobody wants: no output traffic at all
+        int rc = launch_run(h, sampler, skip, none);
         if (rc) return rc;
-        h->iters_done += n_iter;
-        BFB_CUDA(cudaEventRecord(h->ev1, h->stream));
+        h->iters_done += skip;
+    }
+    const int R = n_iter - skip;            // iterations with records
+    const int n_keep = (R + thin - 1) / thin;
+    if (R == 0) {
+    } else if (loc == BFB_DEVICE) {
+        int rc = launch_run(h, sampler, R, *out);
+        if (rc) return rc;
+        h->iters_done += R;
     } else {
         // Host outputs: the run is cut into chunks of iterations; chunk k's kernel writes a device staging buffer while
         // chunk k-1 is copied to the caller's arrays on a second stream (strided 2-D copies: the host layout is
-        // chain-major).  With pinned host memory (bfb_host_alloc) the copies are hidden behind the kernels.
-        int n_chunks = n_iter >= 512 ? 6 : (n_iter >= 128 ? 3 : 1);
-        if (const char *e = getenv("BFB200_E2E_CHUNKS")) { int v = atoi(e); if (v >= 1 && v <= n_iter) n_chunks = v; }
-        const int K = (n_iter + n_chunks - 1) / n_chunks;
-        n_chunks = (n_iter + K - 1) / K;
+        // chain-major).  With pinned host memory (bfb_host_alloc) the copies are hidden behind the kernels.  Thinned
+        // records are compacted on the device first; the summaries are accumulated from the staging buffer.
+        int n_chunks = R >= 512 ? 6 : (R >= 128 ? 3 : 1);
+        if (const char *e = getenv("BFB200_E2E_CHUNKS")) { int v = atoi(e); if (v >= 1 && v <= R) n_chunks = v; }
+        int K = (R + n_chunks - 1) / n_chunks;
+        K = ((K + thin - 1) / thin) * thin;                 // chunk boundaries on kept iterations
+        n_chunks = (R + K - 1) / K;
         size_t rec = 0;
         for (int f = 0; f < 11; ++f) if (user[f]) rec += field_bytes(f, n);
-        const size_t need = rec * (size_t)C * K;
+        const bool stage_samples = want_mom && !user[0];    // the summaries need the samples even if the caller does not
+        if (stage_samples) rec += field_bytes(0, n);
+        const size_t full = rec * (size_t)C * K;
+        const size_t need = full + (thin > 1 ? rec * (size_t)C * ((K + thin - 1) / thin) : 0);
         if (!h->copy_stream) {
             BFB_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
             for (int i = 0; i < 2; ++i) { BFB_CUDA(cudaEventCreateWithFlags(&h->ev_k[i], cudaEventDisableTiming));
@@ -914,36 +986,76 @@ extern "C" int bfb_sampler_run(bfb_handle h, int sampler, int32_t n_iter, const 
                 h->stage_len[i] = need;
             }
         }
-        BFB_CUDA(cudaEventRecord(h->ev0, h->stream));
+        const int ne = n + n * n, nb = h->sm_count * 2;
+        double *mom = nullptr;              // [n] shift | [ne] accumulators | [nb][ne] partials
+        if (want_mom) {
+            BFB_CUDA(cudaMalloc((void **)&mom, sizeof(double) * ((size_t)n + ne + (size_t)nb * ne)));
+            BFB_CUDA(cudaMemsetAsync(mom, 0, sizeof(double) * ((size_t)n + ne), h->stream));
+        }
         for (int k = 0; k < n_chunks; ++k) {
-            const int it_begin = k * K, Kk = (it_begin + K <= n_iter) ? K : n_iter - it_begin;
+            const int it_begin = k * K, Kk = (it_begin + K <= R) ? K : R - it_begin;
+            const int kk = (Kk + thin - 1) / thin, keep_begin = it_begin / thin;
             const int sb = k & 1;
             if (k >= 2) BFB_CUDA(cudaStreamWaitEvent(h->stream, h->ev_c[sb], 0));   // staging buffer free again
-            void *dptr[11];
-            char *base = (char *)h->stage[sb];
+            void *dptr[11], *cptr[11];
+            char *base = (char *)h->stage[sb], *cbase = (char *)h->stage[sb] + full;
             for (int f = 0; f < 11; ++f) {
-                dptr[f] = nullptr;
-                if (user[f]) { dptr[f] = base; base += field_bytes(f, n) * (size_t)C * Kk; }
+                dptr[f] = cptr[f] = nullptr;
+                if (user[f] || (f == 0 && stage_samples)) {
+                    dptr[f] = base; base += field_bytes(f, n) * (size_t)C * Kk;
+                    cptr[f] = cbase; cbase += field_bytes(f, n) * (size_t)C * kk;
+                }
             }
             bfb_run_out dev = {(double *)dptr[0], (double *)dptr[1], (double *)dptr[2], (double *)dptr[3], (double *)dptr[4],
                                (double *)dptr[5], (double *)dptr[6], (double *)dptr[7], (int32_t *)dptr[8],
                                (int32_t *)dptr[9], (int32_t *)dptr[10]};
             int rc = launch_run(h, sampler, Kk, dev);
-            if (rc) return rc;
+            if (rc) { if (mom) cudaFree(mom); return rc; }
             h->iters_done += Kk;
+            if (want_mom) {
+                if (k == 0) BFB_CUDA(cudaMemcpyAsync(mom, dptr[0], sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));   // shift = first record
+                trace_moments_partial_kernel<<<nb, 256, sizeof(double) * 32 * n, h->stream>>>((const double *)dptr[0], C * (int64_t)Kk, n, mom, mom + n + ne);
+                trace_moments_reduce_kernel<<<(ne + 127) / 128, 128, 0, h->stream>>>(mom + n + ne, nb, ne, mom + n);
+                h->launches += 2;
+            }
+            if (thin > 1) {
+                for (int f = 0; f < 11; ++f) {
+                    if (!user[f]) continue;
+                    const int64_t tot = C * (int64_t)kk * (f == 0 ? n : 1);
+                    const unsigned gb = (unsigned)((tot + 255) / 256 < 4096 ? (tot + 255) / 256 : 4096);
+                    if (f <= 7) thin_kernel<double><<<gb, 256, 0, h->stream>>>((const double *)dptr[f], (double *)cptr[f], C, Kk, kk, thin, f == 0 ? n : 1);
+                    else thin_kernel<int32_t><<<gb, 256, 0, h->stream>>>((const int32_t *)dptr[f], (int32_t *)cptr[f], C, Kk, kk, thin, 1);
+                    h->launches++;
+                }
+            }
+            BFB_CUDA(cudaGetLastError());
             BFB_CUDA(cudaEventRecord(h->ev_k[sb], h->stream));
             BFB_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_k[sb], 0));
             for (int f = 0; f < 11; ++f) {
                 if (!user[f]) continue;
                 const size_t fb = field_bytes(f, n);
-                BFB_CUDA(cudaMemcpy2DAsync((char *)user[f] + fb * (size_t)it_begin, fb * (size_t)n_iter, dptr[f], fb * (size_t)Kk,
-                                           fb * (size_t)Kk, (size_t)C, cudaMemcpyDeviceToHost, h->copy_stream));
+                BFB_CUDA(cudaMemcpy2DAsync((char *)user[f] + fb * (size_t)keep_begin, fb * (size_t)n_keep, thin > 1 ? cptr[f] : dptr[f],
+                                           fb * (size_t)kk, fb * (size_t)kk, (size_t)C, cudaMemcpyDeviceToHost, h->copy_stream));
             }
             BFB_CUDA(cudaEventRecord(h->ev_c[sb], h->copy_stream));
+        }
+        if (want_mom) {
+            // mean = s + S1 / N, cov = (S2 - S1 S1^T / N) / (N - 1)   (np.cov: unbiased)
+            std::vector<double> m((size_t)n + ne);
+            BFB_CUDA(cudaMemcpyAsync(m.data(), mom, sizeof(double) * m.size(), cudaMemcpyDeviceToHost, h->stream));
+            BFB_CUDA(cudaStreamSynchronize(h->stream));
+            const double N = (double)C * (double)R;
+            if (opts->mean) for (int j = 0; j < n; ++j) opts->mean[j] = m[j] + m[n + j] / N;
+            if (opts->cov)
+                for (int j = 0; j < n; ++j)
+                    for (int k2 = 0; k2 < n; ++k2)
+                        opts->cov[(size_t)j * n + k2] = (m[2 * n + (size_t)j * n + k2] - m[n + j] * m[n + k2] / N) / (N - 1.);
+            cudaFree(mom);
         }
         BFB_CUDA(cudaEventRecord(h->ev1, h->stream));
         BFB_CUDA(cudaStreamSynchronize(h->copy_stream));
     }
+    if (R == 0 || loc == BFB_DEVICE) BFB_CUDA(cudaEventRecord(h->ev1, h->stream));
     BFB_CUDA(cudaMemcpyAsync(&tt, h->cs.tree_total, sizeof(tt), cudaMemcpyDeviceToHost, h->stream));
     BFB_CUDA(cudaStreamSynchronize(h->stream));
     BFB_CUDA(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));

@@ -378,32 +378,50 @@ class TraceTuple:
     numpy arrays: samples [C, n_iter, n], samples_original, logp_original and the stats fields [C, n_iter].
     """
 
-    def __init__(self, template, arrays, final_state, chain0=0, device_state=None):
+    def __init__(self, template, arrays, final_state, chain0=0, device_state=None, iters=None, i_iter=None, out_opts=None,
+                 generation=None):
         self._template = template
         self._sampler = 'NUTS' if isinstance(template, NTrace) else 'HMC'
         self._arrays = arrays
         self._final = final_state
         self._chain0 = int(chain0)
         self._device_state = device_state       # live device handle: lets sample() continue these chains
+        self._generation = generation           # ... as long as nothing else was started on it since (Handle.generation)
+        self._out_opts = out_opts or dict(fields=None, keep='all', thin=1, summaries=False)
+        n_rec = next(iter(arrays.values())).shape[1] if arrays else 0
+        # iteration index of every stored record (sample(keep='post_warmup', thin=k) stores a subset) and iterations done
+        self._iters = np.arange(n_rec) if iters is None else np.asarray(iters)
+        self._i_iter = n_rec if i_iter is None else int(i_iter)
+        self.total_tree_size = 0
+        self.summaries = {}
         self._cache = {}
 
+    def _arr(self, name):
+        try:
+            return self._arrays[name]
+        except KeyError:
+            raise KeyError("'{}' was not brought back to the host (sample(fields=...)).".format(name)) from None
+
     sampler = property(lambda self: self._sampler)
-    n_chain = property(lambda self: self._arrays['samples'].shape[0])
+    n_chain = property(lambda self: next(iter(self._arrays.values())).shape[0])
     n_iter = property(lambda self: self._template.n_iter)
     n_warmup = property(lambda self: self._template.n_warmup)
-    i_iter = property(lambda self: self._arrays['samples'].shape[1])
-    input_size = property(lambda self: self._arrays['samples'].shape[-1])
-    samples = property(lambda self: self._arrays['samples'])
-    samples_original = property(lambda self: self._arrays['samples_original'])
-    logp = property(lambda self: self._arrays['logp'])
-    logp_original = property(lambda self: self._arrays['logp_original'])
+    i_iter = property(lambda self: self._i_iter)
+    iters = property(lambda self: self._iters)
+    input_size = property(lambda self: self._arr('samples').shape[-1])
+    samples = property(lambda self: self._arr('samples'))
+    samples_original = property(lambda self: self._arr('samples_original'))
+    logp = property(lambda self: self._arr('logp'))
+    logp_original = property(lambda self: self._arr('logp_original'))
     finished = property(lambda self: self.i_iter >= self.n_iter)
     arrays = property(lambda self: self._arrays)
 
     @property
     def n_call(self):
         if self._sampler == 'NUTS':
-            return int(np.sum(self._arrays['tree_size'][:, 1:])) + self.n_chain * (self.n_iter + 1)
+            if len(self._iters) == self._i_iter and 'tree_size' in self._arrays:
+                return int(np.sum(self._arrays['tree_size'][:, 1:])) + self.n_chain * (self.n_iter + 1)
+            return int(self.total_tree_size) + self.n_chain * (self.n_iter + 1)      # reduced records: all iterations counted
         return self.n_chain * (self.n_iter * (self._template.n_int_step + 1) + 1)
 
     def _make(self, i):
@@ -412,26 +430,21 @@ class TraceTuple:
         t._chain_id = self._chain0 + i
         t._chain_initialized = True
         A = self._arrays
-        t._samples = A['samples'][i]
-        t._samples_original = A['samples_original'][i]
-        t._logp_original = A['logp_original'][i]
+        for name in ('samples', 'samples_original', 'logp_original'):
+            setattr(t, '_' + name, A[name][i] if name in A else None)
         t._x_0 = None if self._final.get('x_0') is None else self._final['x_0'][i]
         st = NStats() if self._sampler == 'NUTS' else HStats()
-        n_it = A['samples'].shape[1]
-        warm = np.arange(n_it) < t._n_warmup
+        warm = self._iters < t._n_warmup
+        alias = {'diverging': ('diverging', bool), 'n_int_step': ('tree_size', None), 'accepted': ('tree_depth', bool),
+                 'accept_stat': ('mean_tree_accept', None)}
         for si in st.stats_items:
             if si == 'warmup':
                 v = warm
-            elif si == 'diverging':
-                v = A['diverging'][i].astype(bool)
-            elif si == 'n_int_step':
-                v = A['tree_size'][i]
-            elif si == 'accepted':
-                v = A['tree_depth'][i].astype(bool)
-            elif si == 'accept_stat':
-                v = A['mean_tree_accept'][i]
             else:
-                v = A[si][i]
+                key, cast = alias.get(si, (si, None))
+                if key not in A:                      # sample(fields=...) left this statistic on the device
+                    continue
+                v = A[key][i].astype(cast) if cast else A[key][i]
             setattr(st, '_' + si, v)
         t._stats = st
         fs = self._final['final_step'][i]
@@ -483,11 +496,12 @@ class TraceTuple:
         since_iter = int(since_iter)
         if since_iter >= self.i_iter - 1:
             raise ValueError('since_iter is too large. Nothing to return.')
+        first = int(np.searchsorted(self._iters, since_iter))         # stored records may be a subset of the iterations
         if return_type == 'samples':
-            s = (self.samples_original if original_space else self.samples)[:, since_iter:]
+            s = (self.samples_original if original_space else self.samples)[:, first:]
             return s.reshape((-1, self.input_size)) if flatten else s
         if return_type == 'logp':
-            l = (self.logp_original if original_space else self.logp)[:, since_iter:]
+            l = (self.logp_original if original_space else self.logp)[:, first:]
             return l.flatten() if flatten else l
         raise ValueError('invalid value for return_type.')
 

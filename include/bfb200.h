@@ -167,6 +167,18 @@ int bfb_sampler_reset(bfb_handle h);
  * sum over chains and iterations of tree_size = leapfrog steps performed in trees. */
 int bfb_sampler_run(bfb_handle h, int sampler, int32_t n_iter, const bfb_run_out *out, int loc,
                     int64_t *total_tree_size);
+/* Reduced outputs: what SampleTrace.get hands to its callers (samplers/sample_trace.py:762-787: the samples after
+ * warm-up, flattened) instead of every record of every iteration -- a 4096 x 1500 run at n = 26 is 1.7 GB per GPU otherwise.
+ * skip: the records of the first `skip` iterations of this call are not written at all; thin >= 1: of the following
+ * iterations every thin-th is kept, the out arrays are then [C, n_keep(, n)] with n_keep = ceil((n_iter - skip) / thin)
+ * (host outputs only for thin > 1); mean [n] / cov [n,n] (host, may be NULL): mean and unbiased covariance (np.cov) of the
+ * samples of ALL iterations after `skip` over all chains, accumulated on the device.  opts == NULL: bfb_sampler_run. */
+typedef struct {
+    int32_t skip, thin;
+    double *mean, *cov;
+} bfb_run_opts;
+int bfb_sampler_run_ex(bfb_handle h, int sampler, int32_t n_iter, const bfb_run_out *out, int loc,
+                       const bfb_run_opts *opts, int64_t *total_tree_size);
 /* which kernel family ran the last bfb_sampler_run of this handle: 0 = generic warp-per-chain (bfb_sampler.cu),
  * 1 = FMA multi-chain-per-warp (bfb_sampler_fast.cu), 2 = FP64 tensor core, 8 chains per warp (bfb_sampler_dmma.cu);
  * -1 before the first run.  The environment variable BFB200_SAMPLER = dmma | fast | generic pins one (tests, profiles). */

@@ -84,3 +84,39 @@ def synthetic_spec(n, order='cubic-2', seed=0, cubic_scale=0.02, cond=30., bound
         hb[min(2, n - 1)] = (1, 0)
         spec.update(transform_ranges=ranges, hard_bounds=hb)
     return spec, cov
+
+
+def unpack(order, a, n):
+    """inverse of pack(): dense reference-layout tensor from the packed coefficient vector (PolyConfig._set, poly.py:131-158)"""
+    a = np.asarray(a, dtype=np.float64)
+    if order == 'linear':
+        return a.copy()
+    if order == 'quadratic':
+        c = np.zeros((n, n))
+        c[np.triu_indices(n)] = a
+        return c
+    if order == 'cubic-2':
+        return a.reshape(n, n).copy()
+    c = np.zeros((n, n, n))
+    i = 0
+    for j in range(n):
+        for k in range(j + 1, n):
+            m = n - k - 1
+            c[j, k, k + 1:] = a[i:i + m]
+            i += m
+    return c
+
+
+def c3n64_spec(g):
+    """the 64-D cubic-3 stack of tests/golden/poly_eval_c3n64.npz: coefficients regenerated from the recorded seed (the same
+    numpy calls as make_golden.seeded_coefs), bound parameters from the fixture"""
+    n = int(g['n'])
+    orders = ('linear', 'quadratic', 'cubic-2', 'cubic-3')
+    shapes = {'linear': n + 1, 'quadratic': n * (n + 1) // 2, 'cubic-2': n * n, 'cubic-3': n * (n - 1) * (n - 2) // 6}
+    rng = np.random.default_rng(int(g['seed']))
+    cfgs = []
+    for o in orders:
+        a = rng.normal(size=shapes[o]) * float(g['scales'][o])
+        cfgs.append(dict(order=o, input_mask=np.arange(n), output_mask=np.arange(1), coef=unpack(o, a, n)[None]))
+    return dict(n=n, m=1, configs=cfgs, use_bound=True, mu=g['mu'], hess=g['hess'], alpha=float(g['alpha']), f_mu=g['f_mu'],
+                input_scales=None, use_decay=False, transform_ranges=None)

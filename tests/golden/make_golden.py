@@ -506,6 +506,144 @@ def make_pipeline():
     gio.save('pipeline_ext.npz', dict(cases=cases))
 
 
+def make_sampler_d26():
+    """The headline shape pinned directly: d = 26 cubic-2 surrogate with the radial bound, 4 chains x 60 iterations, and the
+    same with the logit transform on 5 coordinates."""
+    rng = np.random.default_rng(2626)
+    cases = []
+
+    def add(name, den, x0, seed, **trace_kw):
+        r = run_reference_chains(den, 'NUTS', trace_kw, x0, seed, 60000)
+        cases.append(dict(name=name, sampler='NUTS', spec=density_spec(den), x0=x0, seed=seed,
+                          trace_kw={k: (v if not isinstance(v, bool) else int(v)) for k, v in trace_kw.items()}, result=r))
+        print(name, 'mean depth', np.mean(r['tree_depth']), 'n_div', int(np.sum(r['diverging'])), 'draws', r['n_draws'])
+
+    den, cov, xf = make_density(26, 'cubic-2', rng)
+    assert den._surrogate_list[0]._use_bound
+    add('nuts_c2_n26_bound', den, xf[:4].copy(), 2601, n_iter=60, n_warmup=30)
+    # hard bounds (logit transform) on 5 coordinates, soft ranges elsewhere, like cell 16 of the DES notebook
+    n = 26
+    A = rng.normal(size=(n, n))
+    cov = A @ A.T / n + np.eye(n)
+    P = np.linalg.inv(cov)
+    mod = bf.Module(fun=target_logp(P), input_vars='x', output_vars='logp')
+    sur = PolyModel('cubic-2', input_size=n, output_size=1, input_vars='x', output_vars='logp')
+    ranges = np.stack((-9. - rng.uniform(size=n), 9. + rng.uniform(size=n)), axis=1)
+    hb = np.zeros((n, 2), np.uint8)
+    for j in (0, 4, 6, 16, 17):
+        hb[j] = (1, 1)
+    den = bf.Density(density_name='logp', module_list=[mod], surrogate_list=[sur], input_vars='x',
+                     decay_options={'use_decay': False}, input_scales=ranges, hard_bounds=hb)
+    L = np.linalg.cholesky(cov)
+    xf = np.clip((L @ rng.normal(size=(n, 4 * sur.n_param))).T, -8.5, 8.5)
+    den.fit([den.fun(x, original_space=True, use_surrogate=False) for x in xf])
+    den.use_surrogate = True
+    x0 = np.array([den.from_original(x) for x in xf[:4]])
+    add('nuts_c2_n26_bound_transform5', den, x0, 2602, n_iter=60, n_warmup=30)
+    gio.save('sampler_d26.npz', dict(cases=cases))
+
+
+def seeded_coefs(n, orders, seed, scales):
+    """packed coefficient vectors from a seed: the test regenerates them instead of storing 2 MB of cubic-3 coefficients"""
+    rng = np.random.default_rng(seed)
+    shapes = {'linear': n + 1, 'quadratic': n * (n + 1) // 2, 'cubic-2': n * n, 'cubic-3': n * (n - 1) * (n - 2) // 6}
+    return [rng.normal(size=shapes[o]) * scales[o] for o in orders]
+
+
+def make_poly_eval_c3n64():
+    """BASELINE configs[3]: 64-D cubic-3 stack (P = 47905) with injected coefficients and the radial bound"""
+    n = 64
+    orders = ('linear', 'quadratic', 'cubic-2', 'cubic-3')
+    scales = {'linear': 0.3, 'quadratic': 0.15 / np.sqrt(n), 'cubic-2': 0.03 / n, 'cubic-3': 0.03 / n}
+    sur = PolyModel('cubic-3', input_size=n, output_size=1)
+    for conf, a in zip(sur._configs, seeded_coefs(n, orders, 6464, scales)):
+        assert conf.order == orders[sur._configs.index(conf)]
+        conf._set(a.reshape(conf._a_shape) if hasattr(conf, '_a_shape') else a, 0)
+    rng = np.random.default_rng(65)
+    train = rng.normal(size=(6 * n + 10, n)) * 0.5
+    set_bound_from(sur, train)
+    X = np.concatenate((rng.normal(size=(8, n)) * 0.35, rng.normal(size=(4, n)) * 3.))
+    raw_f, raw_j = [], []
+    for xi in X:
+        f, j = sur._fun_and_jac(xi)
+        raw_f.append(f), raw_j.append(j)
+    gio.save('poly_eval_c3n64.npz', dict(n=n, seed=6464, scales=scales, X=X, raw_f=np.array(raw_f), raw_j=np.array(raw_j),
+                                         mu=sur._mu, hess=sur._hess, alpha=float(sur._alpha), f_mu=np.atleast_1d(sur._f_mu)))
+    print('c3_n64 beta/alpha of the points', [float(np.sqrt((x - sur._mu) @ sur._hess @ (x - sur._mu)) / sur._alpha) for x in X])
+
+
+def make_pipeline_des():
+    """The DES-Y1 example's density shape (examples/des-y1-w-cosmosis.ipynb cells 12-18): three modules -- surrogate
+    x (27) -> m outputs from a linear config plus a quadratic config on the SHARED mask `nonlinear_indices`, module
+    input_scales = para_range; chi2 module like = -1/2 |m - d|^2 + norm; posterior module logp = like + Gaussian prior on 13 of
+    the x -- in a Density with input_scales = para_range and hard_bounds = True (logit transform on every coordinate), radial
+    bound on (default bound options).  m = 40 here to keep the fixture small."""
+    rng = np.random.default_rng(1812)
+    n, m = 27, 40
+    para_range = np.array([[0.1, 0.9], [0.55, 0.9], [0.03, 0.07], [0.87, 1.07], [0.5e-9, 5.0e-9], [0.0006, 0.01], [-2, -0.333],
+                           [0.8, 3.0], [0.8, 3.0], [0.8, 3.0], [0.8, 3.0], [0.8, 3.0], [-0.1, 0.1], [-0.1, 0.1], [-0.1, 0.1],
+                           [-0.1, 0.1], [-5.0, 5.0], [-5.0, 5.0], [-0.1, 0.1], [-0.1, 0.1], [-0.1, 0.1], [-0.1, 0.1],
+                           [-0.05, 0.05], [-0.05, 0.05], [-0.05, 0.05], [-0.05, 0.05], [-0.05, 0.05]])
+    nonlinear_indices = np.array([0, 1, 2, 3, 4, 5, 6, 16, 17])
+    prior_idx = np.array([18, 19, 20, 21, 12, 13, 14, 15, 22, 23, 24, 25, 26])
+    prior_mu = np.array([-0.001, -0.019, 0.009, -0.018, 0.012, 0.012, 0.012, 0.012, 0.008, -0.005, 0.006, 0.0, 0.0])
+    prior_sig = np.array([0.016, 0.013, 0.011, 0.022, 0.023, 0.023, 0.023, 0.023, 0.007, 0.007, 0.006, 0.01, 0.01]) * 3.
+    prior_c0 = -1.75
+    width = para_range[:, 1] - para_range[:, 0]
+    mid = para_range.mean(axis=1)
+    W1 = rng.normal(size=(m, n)) * 1.5
+    W2 = rng.normal(size=(m, 9, 9)) * 0.8
+
+    def theory(x):
+        u = (x - mid) / width
+        v = u[nonlinear_indices]
+        return W1 @ u + np.einsum('ojk,j,k->o', W2, v, v) + 0.05 * np.sin(3. * (W1 @ u))
+
+    u_true = rng.normal(size=n) * 0.05
+    d_vec = theory(mid + u_true * width) + 0.05 * rng.normal(size=m)
+    norm_c = 3.25
+
+    def prior_f(x):
+        return -0.5 * np.sum(((x[prior_idx] - prior_mu) / prior_sig)**2) + prior_c0
+
+    def prior_j(x):
+        foo = np.zeros((1, n))
+        foo[0, prior_idx] = -(x[prior_idx] - prior_mu) / prior_sig**2
+        return foo
+
+    module_0 = bf.Module(fun=theory, input_vars='x', output_vars='m')
+    module_1 = bf.Module(fun=lambda mm: np.atleast_1d(-0.5 * np.sum((mm - d_vec)**2) + norm_c),
+                         fun_and_jac=lambda mm: (np.atleast_1d(-0.5 * np.sum((mm - d_vec)**2) + norm_c), -(mm - d_vec)[np.newaxis]),
+                         input_vars='m', output_vars='like')
+    module_2 = bf.Module(fun=lambda like, x: like + prior_f(x),
+                         fun_and_jac=lambda like, x: (like + prior_f(x), np.concatenate((np.ones((1, 1)), prior_j(x)), axis=-1)),
+                         input_vars=['like', 'x'], output_vars='logp')
+    den = bf.Density(density_name='logp', module_list=[module_0, module_1, module_2], input_vars='x', input_shapes=n,
+                     input_scales=para_range, hard_bounds=True)
+    sur = PolyModel([PolyConfig('linear'), PolyConfig('quadratic', input_mask=nonlinear_indices)], input_size=n, output_size=m,
+                    input_vars='x', output_vars='m', input_scales=para_range)
+    den.surrogate_list = [sur]
+    xf = mid + np.clip(rng.normal(size=(3 * sur.n_param, n)) * 0.08, -0.45, 0.45) * width
+    den.fit([den.fun(x, original_space=True, use_surrogate=False) for x in xf])
+    den.use_surrogate = True
+    assert sur._use_bound
+    Xo = np.concatenate((xf[:8], mid + np.clip(rng.normal(size=(6, n)) * 0.3, -0.47, 0.47) * width))
+    Xt = np.array([den.from_original(x) for x in Xo])
+    lp, gr = [], []
+    for x in Xt:
+        a_, b_ = den.logp_and_grad(x, original_space=False)
+        lp.append(float(a_)), gr.append(np.array(b_))
+    x0 = np.array([den.from_original(x) for x in xf[20:24]])
+    r = run_reference_chains(den, 'NUTS', dict(n_iter=40, n_warmup=20), x0, 2404, 60000)
+    spec = density_spec(den)
+    spec['epilogue'] = dict(d=d_vec, cinv=np.eye(m), c0=norm_c)
+    spec['prior'] = dict(idx=prior_idx, mu=prior_mu, sig=prior_sig, c0=prior_c0)
+    print('des_shaped mean depth', np.mean(r['tree_depth']), 'n_div', int(np.sum(r['diverging'])), 'draws', r['n_draws'],
+          'outside', [float(np.sqrt(((x - mid) / width * 0 + 1) @ np.ones(n))) for x in Xo[:1]])
+    gio.save('pipeline_des.npz', dict(cases=[dict(name='des_shaped_n27_m40', spec=spec, X=Xt, logp=np.array(lp), grad=np.array(gr),
+                                                  x0=x0, seed=2404, trace_kw=dict(n_iter=40, n_warmup=20), result=r)]))
+
+
 if __name__ == '__main__':
     which = sys.argv[1:] or ['poly_kat', 'poly_eval', 'density', 'fit', 'sampler', 'sampler_dense', 'pipeline']
     if 'poly_kat' in which:
@@ -518,6 +656,12 @@ if __name__ == '__main__':
         make_fit()
     if 'sampler' in which:
         make_sampler()
+    if 'sampler_d26' in which:
+        make_sampler_d26()
+    if 'poly_eval_c3n64' in which:
+        make_poly_eval_c3n64()
+    if 'pipeline_des' in which:
+        make_pipeline_des()
     if 'sampler_dense' in which:
         make_sampler_dense()
     if 'pipeline' in which:

@@ -43,6 +43,17 @@ def test_poly_eval_golden(handle, oracle):
         assert rel_err(F, Fo) < RTOL and rel_err(J, Jo) < RTOL, c['name']
 
 
+def test_poly_eval_c3n64_golden(handle, oracle):
+    """BASELINE configs[3] at its named size (64-D cubic-3, P = 47905) against the real reference, inside and far outside the bound"""
+    from _specs import c3n64_spec
+    g = gio.load('poly_eval_c3n64.npz')
+    handle.set_model(to_device_spec(c3n64_spec(g)))
+    F, J = handle.poly_eval_batch(g['X'])
+    assert rel_err(F, g['raw_f']) < RTOL and rel_err(J, g['raw_j']) < RTOL
+    lp, gr = handle.logp_and_grad_batch(g['X'])
+    assert rel_err(lp, g['raw_f'][:, 0]) < RTOL and rel_err(gr, g['raw_j'][:, 0]) < RTOL
+
+
 def test_poly_kat(handle):
     g = gio.load('poly_kat.npz')
     c = g['logp']

@@ -46,7 +46,7 @@ def check_floats(a, b, tag, late=LATE_TOL):
     assert np.allclose(a, b, rtol=late, atol=late, equal_nan=True), tag
 
 
-@pytest.mark.parametrize('case', gio.load('sampler.npz')['cases'], ids=lambda c: c['name'])
+@pytest.mark.parametrize('case', gio.load('sampler.npz')['cases'] + gio.load('sampler_d26.npz')['cases'], ids=lambda c: c['name'])
 def test_golden_chains(handle, oracle, case):
     """same seeds and draw stream as the recorded runs of the real reference"""
     r, kw = case['result'], case['trace_kw']
@@ -76,7 +76,7 @@ def test_golden_chains(handle, oracle, case):
 
 
 @pytest.mark.parametrize('n,order,C,n_iter', [(26, 'cubic-2', 256, 40), (16, 'cubic-2', 130, 40), (40, 'cubic-3', 6, 12),
-                                               (2, 'quadratic', 64, 60)])
+                                               (2, 'quadratic', 64, 60), (64, 'cubic-3', 64, 20)])
 def test_teacher_forced_vs_oracle(handle, oracle, n, order, C, n_iter):
     """per-chain tree depths / sizes / divergences identical to the oracle fed with the device's own draws"""
     spec, cov = synthetic_spec(n, order, seed=7 + n, decay=True)
@@ -172,6 +172,13 @@ def test_sample_api(oracle):
     U, Z = device_draws(den._sync(False), 5, tt._final['n_draws'])
     ref = od.run('NUTS', dict(n_iter=60, n_warmup=30), den.from_original(x0), 1. / n**0.25, np.ones(n), draws_u=U, draws_z=Z)
     assert np.array_equal(tt.arrays['tree_depth'], ref['tree_depth'])
+    # resume: the chains are still resident (sample.py:91-98)
+    tt2 = bfb.sample(den, tt, n_run=10, verbose=False)
+    assert tt2.samples.shape == (16, 70, n) and np.array_equal(tt2.samples[:, :60], tt.samples)
+    ref70 = od.run('NUTS', dict(n_iter=70, n_warmup=30), den.from_original(x0), 1. / n**0.25, np.ones(n), draws_u=U, draws_z=Z) \
+        if U.shape[1] >= int(tt2._final['n_draws'].max()) else None
+    if ref70 is not None:
+        assert np.array_equal(tt2.arrays['tree_depth'], ref70['tree_depth'])
     # dense mass matrix through the same API (sample_trace.py:430-431, 445-449): identity start, adapted covariance back
     ttf = bfb.sample(den, dict(n_chain=16, n_iter=60, n_warmup=30, x_0=x0, random_generator=5, metric='full'), verbose=False)
     assert isinstance(ttf[2].metric, bfb.sample_trace.QuadMetricFullAdapt) and ttf[2].metric._cov.shape == (n, n)
@@ -181,14 +188,58 @@ def test_sample_api(oracle):
     assert np.array_equal(ttf.arrays['tree_depth'], reff['tree_depth'])
     assert np.allclose(ttf._final['final_var'], reff['final_var'], rtol=1e-3, atol=1e-3 * np.abs(reff['final_var']).max())
     assert bfb.sample_trace._get_metric(ttf, 'full', from_samples=False).shape == (n, n)
-    # resume
-    tt2 = bfb.sample(den, tt, n_run=10, verbose=False)
-    assert tt2.samples.shape == (16, 70, n) and np.array_equal(tt2.samples[:, :60], tt.samples)
+    # other chains were started on this density since: the first run cannot be continued any more
+    with pytest.raises(RuntimeError):
+        bfb.sample(den, tt2, n_run=10, verbose=False)
     # errors surface like the reference's (base_hmc.py:42-46)
     bad = x0.copy()
     bad[2] = np.nan
     with pytest.raises(ValueError):
         bfb.sample(den, dict(n_chain=16, n_iter=20, n_warmup=10, x_0=bad, random_generator=5), verbose=False)
+
+
+def test_sample_reduced_outputs():
+    """sample(keep='post_warmup', thin=k, summaries=True): warm-up records never leave the device, thinned records are the
+    same numbers as in the full run, mean / covariance over ALL post-warm-up samples are accumulated on the device
+    (SampleTrace.get, sample_trace.py:762-787, only ever hands out post-warm-up samples)"""
+    import bayesfast_b200 as bfb
+    n, C, n_iter, n_warmup = 9, 50, 173, 61
+    spec, cov = synthetic_spec(n, 'cubic-2', seed=14)
+    sur = bfb.PolyModel('cubic-2', input_size=n, output_size=1)
+    from _specs import pack
+    for conf, cf in zip(sur.configs, spec['configs']):
+        conf._set(pack(cf['order'], cf['coef'][0], n), 0)
+    sur._mu, sur._hess, sur._alpha, sur._f_mu = spec['mu'], spec['hess'], spec['alpha'], spec['f_mu']
+    den = bfb.Density(sur)
+    x0 = (np.linalg.cholesky(cov) @ np.random.default_rng(1).normal(size=(n, C))).T
+    kw = dict(n_chain=C, n_iter=n_iter, n_warmup=n_warmup, x_0=x0, random_generator=11)
+    full = bfb.sample(den, dict(kw), verbose=False)
+    for sampler, thin in (('NUTS', 3), ('NUTS', 1), ('HMC', 4)):
+        if sampler == 'HMC':
+            full = bfb.sample(den, dict(kw, n_int_step=5), sampler='HMC', verbose=False)
+        red = bfb.sample(den, dict(kw, **({'n_int_step': 5} if sampler == 'HMC' else {})), sampler=sampler, verbose=False,
+                         keep='post_warmup', thin=thin, summaries=True)
+        sel = np.arange(n_warmup, n_iter, thin)
+        assert np.array_equal(red.iters, sel) and red.i_iter == n_iter
+        for k in ('samples', 'logp', 'energy', 'tree_depth', 'tree_size', 'diverging', 'step_size'):
+            assert np.array_equal(red.arrays[k], full.arrays[k][:, sel]), (sampler, thin, k)
+        assert red.total_tree_size == full.total_tree_size
+        post = full.samples[:, n_warmup:].reshape(-1, n)
+        assert np.allclose(red.summaries['mean'], post.mean(axis=0), rtol=1e-11, atol=1e-12)
+        assert np.allclose(red.summaries['cov'], np.cov(post, rowvar=False), rtol=1e-10, atol=1e-13)
+        assert np.array_equal(red.get(), full.get()[:: 1].reshape(C, -1, n)[:, ::thin].reshape(-1, n))
+        assert red[2].samples.shape == (len(sel), n) and not red[2].stats._warmup.any()
+    # a run that ends inside the warm-up brings back nothing, and continues into the kept part
+    a = bfb.sample(den, dict(kw), n_run=40, verbose=False, keep='post_warmup', thin=2, fields=('samples', 'logp', 'tree_size'))
+    assert a.samples.shape == (C, 0, n) and a.i_iter == 40
+    b = bfb.sample(den, a, n_run=60, verbose=False)
+    full = bfb.sample(den, dict(kw), verbose=False)
+    sel = np.arange(n_warmup, 100, 2)
+    assert np.array_equal(b.iters, sel) and np.array_equal(b.samples, full.samples[:, sel]) and b.i_iter == 100
+    assert set(b.arrays) == {'samples', 'logp', 'tree_size', 'samples_original', 'logp_original'}
+    # ... but `b` cannot be continued any more: other chains were started on the density since
+    with pytest.raises(RuntimeError):
+        bfb.sample(den, b, n_run=5, verbose=False)
 
 
 def test_work_queue_chunking_is_invisible(handle, monkeypatch):

@@ -104,7 +104,7 @@ def _flt(a, b, tag, early=EARLY):
     assert np.allclose(a, b, rtol=LATE_TOL, atol=LATE_TOL, equal_nan=True), tag
 
 
-@pytest.mark.parametrize('golden', ['sampler.npz', 'sampler_dense.npz'])
+@pytest.mark.parametrize('golden', ['sampler.npz', 'sampler_dense.npz', 'sampler_d26.npz'])
 def test_sampler_cases(oracle, golden):
     """sampler_dense.npz: the dense mass matrix (metrics.py:94-132, 240-330); var0 / final_var are covariances"""
     g = gio.load(golden)
@@ -175,3 +175,13 @@ def test_pipeline_extended_case(oracle):
         for k in INT_STATS:
             assert np.array_equal(out[k], r[k].astype(np.int32)), (c['name'], k)
         _flt(out['samples'], r['samples'], c['name'], early=4)
+
+
+def test_poly_eval_c3n64(oracle):
+    """BASELINE configs[3] at its named size: 64-D cubic-3 stack (P = 47905), real-reference values inside and far outside
+    the radial bound"""
+    from _specs import c3n64_spec
+    g = gio.load('poly_eval_c3n64.npz')
+    F, J = oracle.OracleDensity(c3n64_spec(g)).poly_eval_batch(g['X'])
+    assert np.allclose(F, g['raw_f'], rtol=1e-11, atol=1e-11 * np.abs(g['raw_f']).max())
+    assert np.allclose(J, g['raw_j'], rtol=1e-11, atol=1e-11 * np.abs(g['raw_j']).max())
