@@ -101,6 +101,9 @@ def lib():
                     ('bfb_fit_accumulate', [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int], C.c_int),
                     ('bfb_fit_buffer_size', [C.c_void_p], C.c_int64),
                     ('bfb_fit_buffer', [C.c_void_p, C.POINTER(C.c_void_p)], C.c_int),
+                    ('bfb_fit_exchange_pack', [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)], C.c_int),
+                    ('bfb_fit_exchange_host', [C.c_void_p, C.c_void_p, C.c_int], C.c_int),
+                    ('bfb_fit_exchange_unpack', [C.c_void_p], C.c_int),
                     ('bfb_fit_solve', [C.c_void_p, _dp, _dp], C.c_int),
                     ('bfb_fit_moments', [C.c_void_p, _dp, _dp], C.c_int),
                     ('bfb_fit_max_beta', [C.c_void_p, C.c_void_p, C.c_int64, _dp, _dp, C.POINTER(C.c_double), C.c_void_p, C.c_int], C.c_int),

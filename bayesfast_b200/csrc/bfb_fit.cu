@@ -31,6 +31,7 @@ struct FitState {
     std::vector<FitGroup> groups;
     double *buf = nullptr;
     int64_t buf_len = 0;
+    double *xbuf = nullptr;      // packed exchange buffer (bfb_fit_exchange_pack)
     size_t off_s1 = 0, off_s2 = 0, off_cnt = 0;
     double *d_shift = nullptr;
     std::vector<double> shift;
@@ -334,6 +335,86 @@ extern "C" int bfb_fit_begin(bfb_handle h, const double *shift)
 }
 
 extern "C" int64_t bfb_fit_buffer_size(bfb_handle h) { return (h && h->fit) ? h->fit->buf_len : -1; }
+
+// ---- exchange buffer of the sharded fit: only the upper block triangle of every Gram (the kernel writes no other tile)
+// plus the moments, contiguous: P = 1585 (+ 1 y column) is 325 tiles = 10.6 MB instead of the 25 x 25 tiles = 20.5 MB of
+// the working buffer ----
+// dir 0: tiles (ti <= tj) of the Ptp x Ptp matrix -> packed, dir 1: packed -> matrix
+static __global__ void fit_pack_tiles_kernel(double *__restrict__ gram, double *__restrict__ packed, int nt, int Ptp, int dir)
+{
+    int t = blockIdx.x, ti = 0;
+    while (t >= nt - ti) { t -= nt - ti; ++ti; }              // tile index -> (ti, tj = ti + t)
+    const int tj = ti + t;
+    double *dst = packed + (size_t)blockIdx.x * TS * TS;
+    for (int e = threadIdx.x; e < TS * TS; e += blockDim.x) {
+        const size_t g = (size_t)(ti * TS + e / TS) * Ptp + (size_t)tj * TS + e % TS;
+        if (dir == 0) dst[e] = gram[g]; else gram[g] = dst[e];
+    }
+}
+
+static int fit_exchange_len(const FitState *fs, int n, int64_t *len)
+{
+    int64_t l = 0;
+    for (const FitGroup &g : fs->groups) l += (int64_t)g.nt * (g.nt + 1) / 2 * TS * TS;
+    *len = l + n + (int64_t)n * n + 1;
+    return BFB_OK;
+}
+
+static int fit_exchange_copy(bfb_context *h, int dir)
+{
+    FitState *fs = h->fit;
+    const int n = h->n;
+    int64_t len;
+    fit_exchange_len(fs, n, &len);
+    if (!fs->xbuf) {
+        void *p = nullptr;
+        BFB_CUDA(cudaMalloc(&p, sizeof(double) * len));
+        fs->allocs.push_back(p);
+        fs->xbuf = (double *)p;
+    }
+    size_t off = 0;
+    for (FitGroup &g : fs->groups) {
+        const int ntile = g.nt * (g.nt + 1) / 2;
+        fit_pack_tiles_kernel<<<ntile, 256, 0, h->stream>>>(fs->buf + g.g_off, fs->xbuf + off, g.nt, g.Ptp, dir);
+        h->launches++;
+        off += (size_t)ntile * TS * TS;
+    }
+    const size_t tail = (size_t)n + (size_t)n * n + 1;       // s1 | s2 | count are contiguous in the working buffer
+    if (dir == 0) BFB_CUDA(cudaMemcpyAsync(fs->xbuf + off, fs->buf + fs->off_s1, sizeof(double) * tail, cudaMemcpyDeviceToDevice, h->stream));
+    else BFB_CUDA(cudaMemcpyAsync(fs->buf + fs->off_s1, fs->xbuf + off, sizeof(double) * tail, cudaMemcpyDeviceToDevice, h->stream));
+    BFB_CUDA(cudaGetLastError());
+    BFB_CUDA(cudaStreamSynchronize(h->stream));
+    return BFB_OK;
+}
+
+extern "C" int bfb_fit_exchange_pack(bfb_handle h, double **dev_ptr, int64_t *len)
+{
+    BFB_REQUIRE(h && h->fit && dev_ptr && len, BFB_ERR_STATE, "bfb_fit_exchange_pack: call bfb_fit_begin first");
+    BFB_CUDA(cudaSetDevice(h->device));
+    int rc = fit_exchange_copy(h, 0);
+    if (rc) return rc;
+    *dev_ptr = h->fit->xbuf;
+    return fit_exchange_len(h->fit, h->n, len);
+}
+
+extern "C" int bfb_fit_exchange_unpack(bfb_handle h)
+{
+    BFB_REQUIRE(h && h->fit && h->fit->xbuf, BFB_ERR_STATE, "bfb_fit_exchange_unpack: call bfb_fit_exchange_pack first");
+    BFB_CUDA(cudaSetDevice(h->device));
+    return fit_exchange_copy(h, 1);
+}
+
+// host staging of the packed exchange buffer (a backend without device collectives: gloo); dir 0: device -> host, 1: host -> device
+extern "C" int bfb_fit_exchange_host(bfb_handle h, double *host, int dir)
+{
+    BFB_REQUIRE(h && h->fit && h->fit->xbuf && host, BFB_ERR_STATE, "bfb_fit_exchange_host: call bfb_fit_exchange_pack first");
+    BFB_CUDA(cudaSetDevice(h->device));
+    int64_t len;
+    fit_exchange_len(h->fit, h->n, &len);
+    if (dir == 0) BFB_CUDA(cudaMemcpy(host, h->fit->xbuf, sizeof(double) * len, cudaMemcpyDeviceToHost));
+    else BFB_CUDA(cudaMemcpy(h->fit->xbuf, host, sizeof(double) * len, cudaMemcpyHostToDevice));
+    return BFB_OK;
+}
 
 extern "C" int bfb_fit_buffer(bfb_handle h, double **dev_ptr)
 {

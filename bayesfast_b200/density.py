@@ -184,13 +184,14 @@ class Density:
         self._gamma = gamma
         self._dirty = True
 
-    def _set_decay(self, x):
-        """ellipsoid of the fit points in the ORIGINAL space (density.py:796-811)"""
+    def _set_decay(self, x, comm=None):
+        """ellipsoid of the fit points in the ORIGINAL space (density.py:796-811); with rows sharded over ranks (comm) the
+        moments and the largest radius are all-reduced like PolyModel's bound, so every rank holds the same density"""
         from .fit import ellipsoid
         x = np.ascontiguousarray(x, dtype=np.float64)
         if x.ndim != 2:
             raise ValueError('invalid value for x.')
-        self._mu, self._hess, a = ellipsoid(self._surrogate, x, self._alpha_p)
+        self._mu, self._hess, a = ellipsoid(self._surrogate, x, self._alpha_p, comm=comm)
         if self._alpha_p is not None:
             self._alpha, self._alpha_2 = a, a**2
         self._dirty = True
@@ -324,7 +325,7 @@ class Density:
             # logp of the pipeline, for center_max (poly.py:277-286): output #0, or the likelihood of the outputs
             logp = y[:, 0].copy() if self.likelihood is None else self.likelihood.logp(y)
         if self._use_decay:
-            self._set_decay(x)
+            self._set_decay(x, comm=comm)
         su = self._surrogate
         xs = x
         if su._input_scales is not None:

@@ -12,24 +12,43 @@ import ctypes as C
 import numpy as np
 
 from . import _cabi
-from .runtime import dist_info
+from .runtime import dist_info, allreduce_values, broadcast_vector, pick_center
 
 
-def _allreduce_buffer(h, group, op='sum'):
-    """in-place NCCL all-reduce of the handle's partial-sum buffer (device pointer wrapped as a torch tensor)"""
+def _allreduce_buffer(h, group, stats=None):
+    """The exchange step of a sharded fit: the packed partial sums (upper block triangle of the Gram, X^T y, shifted moments,
+    row count: bfb_fit_exchange_pack) are all-reduced in place -- NCCL on the device buffer (zero-copy torch view), or staged
+    through the host for a backend without device collectives (gloo) -- and unpacked.  stats: dict receiving bytes / seconds."""
+    import time
     import torch
     import torch.distributed as dist
     L = _cabi.lib()
-    n = int(L.bfb_fit_buffer_size(h._h))
-    ptr = C.c_void_p()
-    _cabi.check(L.bfb_fit_buffer(h._h, C.byref(ptr)))
+    ptr, n = C.c_void_p(), C.c_int64(0)
+    _cabi.check(L.bfb_fit_exchange_pack(h._h, C.byref(ptr), C.byref(n)))
+    n = int(n.value)
+    t0 = time.perf_counter()
     if dist.get_backend(group) == 'nccl':
         t = _wrap_device_ptr(ptr.value, n, h.device)
-        h.synchronize()
         dist.all_reduce(t, group=group)
         torch.cuda.synchronize(h.device)
-    else:   # gloo (CPU tests): stage through the host
-        raise RuntimeError('sharded fit needs the nccl backend')
+    else:
+        host = np.empty(n)
+        _cabi.check(L.bfb_fit_exchange_host(h._h, host.ctypes.data, 0))
+        t = torch.from_numpy(host)
+        dist.all_reduce(t, group=group)
+        _cabi.check(L.bfb_fit_exchange_host(h._h, host.ctypes.data, 1))
+    dt = time.perf_counter() - t0
+    _cabi.check(L.bfb_fit_exchange_unpack(h._h))
+    if stats is not None:
+        stats.update(allreduce_bytes=8 * n, allreduce_s=dt, backend=dist.get_backend(group))
+
+
+def _common_shift(x, n, rank, world, group, device):
+    """reference point of the shifted moments, identical on all ranks: the first row of rank 0 (zeros if it has none)"""
+    shift = np.ascontiguousarray(x[0] if x.shape[0] else np.zeros(n), dtype=np.float64)
+    if world > 1:
+        shift = np.ascontiguousarray(broadcast_vector(shift if rank == 0 else np.zeros(n), 0, group, device))
+    return shift
 
 
 def _wrap_device_ptr(ptr, n, device):
@@ -65,11 +84,7 @@ def fit_polymodel(model, x, y, logp=None, w=None, comm=None, refine=1):
     rank, world, group = dist_info(comm)
     n_total = x.shape[0]
     if world > 1:
-        import torch
-        import torch.distributed as dist
-        t = torch.tensor([n_total], dtype=torch.int64, device='cuda:{}'.format(model._dev().device))
-        dist.all_reduce(t, group=group)
-        n_total = int(t.item())
+        n_total = int(allreduce_values([n_total], 'sum', group, model._dev().device, 'int64')[0])
     if n_total < model.n_param:
         raise ValueError('I need at least {} points, but you only gave me {}.'.format(model.n_param, n_total))
     if w is not None:
@@ -78,7 +93,7 @@ def fit_polymodel(model, x, y, logp=None, w=None, comm=None, refine=1):
             raise ValueError('invalid shape for w.')
     h = _handle_for(model)
     L = _cabi.lib()
-    shift = np.ascontiguousarray(x[0] if (world == 1 and x.shape[0]) else np.zeros(n))
+    shift = _common_shift(x, n, rank, world, group, h.device)
     _cabi.check(L.bfb_fit_begin(h._h, shift.ctypes.data))
     xc, yc = _cabi.f64(x), _cabi.f64(y)
     wc = None if w is None else _cabi.f64(w)
@@ -86,7 +101,8 @@ def fit_polymodel(model, x, y, logp=None, w=None, comm=None, refine=1):
                                      xc.shape[0], _cabi.BFB_HOST))
     model._fit_kernel_ms = h.last_kernel_ms()
     if world > 1:
-        _allreduce_buffer(h, group)
+        model._fit_exchange = {}
+        _allreduce_buffer(h, group, model._fit_exchange)
     total = sum(_cabi.n_packed(c.order, c.input_size) * c.output_size for c in model._configs)
     coef = np.empty(total)
     rr = C.c_double(0.)
@@ -113,7 +129,7 @@ def ellipsoid(model, x, alpha_p, _handle=None, _have_moments=False, comm=None):
     if not _have_moments:
         if x.shape[1] != model._input_size:
             raise ValueError('invalid value for x.')
-        shift = np.ascontiguousarray(x[0] if world == 1 else np.zeros(n))
+        shift = _common_shift(x, n, rank, world, group, h.device)
         _cabi.check(L.bfb_fit_begin(h._h, shift.ctypes.data))
         xc = _cabi.f64(x)
         yz = np.zeros((xc.shape[0], model._output_size))
@@ -138,13 +154,9 @@ def ellipsoid(model, x, alpha_p, _handle=None, _have_moments=False, comm=None):
                                           'rows; use alpha_p >= 100.')
             alpha = float(np.percentile(beta, alpha_p))       # poly.py:273
         else:
-            mx = float(mb.value)
+            mx = float(mb.value) if xc.shape[0] else 0.
             if world > 1:
-                import torch
-                import torch.distributed as dist
-                t = torch.tensor([mx], dtype=torch.float64, device='cuda:{}'.format(h.device))
-                dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
-                mx = float(t.item())
+                mx = float(allreduce_values([mx], 'max', group, h.device)[0])
             alpha = mx * alpha_p / 100.                       # poly.py:275
     return mu, hess, alpha
 
@@ -162,23 +174,28 @@ def set_bound(model, x, logp=None, _handle=None, _have_moments=False, comm=None)
         model._alpha = alpha
     mu_f = mu
     if model._center_max:
+        # the local candidate is validated BEFORE any collective, and every rank always takes part in it (a rank without
+        # rows or with an invalid logp contributes -inf), so the ranks can neither hang nor pick different centres
+        best, x_best = -np.inf, np.zeros(model._input_size)
         try:
-            logp = np.asarray(logp, dtype=np.float64)
-            assert x.shape[0] == logp.shape[0] and logp.ndim == 1
-            i = int(np.argmax(logp))
-            mu_f, best = x[i], float(logp[i])
-            if world > 1:
-                import torch
-                import torch.distributed as dist
-                dev = 'cuda:{}'.format(model._dev().device)
-                cand = torch.tensor(np.concatenate(([best], mu_f)), dtype=torch.float64, device=dev)
-                allc = [torch.empty_like(cand) for _ in range(world)]
-                dist.all_gather(allc, cand, group=group)
-                allc = torch.stack(allc).cpu().numpy()
-                mu_f = allc[int(np.argmax(allc[:, 0])), 1:]
+            lp = np.asarray(logp, dtype=np.float64)
+            assert lp.ndim == 1 and lp.shape[0] == x.shape[0]
+            if x.shape[0] > 0:
+                i = int(np.argmax(lp))                      # poly.py:281
+                best, x_best = float(lp[i]), x[i]
+                if world > 1 and not np.isfinite(best):     # a NaN / inf maximum cannot win the vote over the ranks
+                    best = -np.inf
+            valid = x.shape[0] > 0 or world > 1
         except Exception:
+            valid = False
+        if world > 1:
+            picked = pick_center(best if valid else -np.inf, x_best, group, model._dev().device)
+        else:
+            picked = x_best if valid else None
+        if picked is None:
             warn_center_max()
-            mu_f = mu
+        else:
+            mu_f = picked
     # f_mu is evaluated with the bound disabled (poly.py:288-292)
     save = model._use_bound
     try:

@@ -25,6 +25,52 @@ def dist_info(comm=None):
     return dist.get_rank(group), dist.get_world_size(group), group
 
 
+def _coll_device(group, device):
+    """tensors of a collective live on the GPU for nccl, on the host for gloo (CPU tests, single-GPU multi-process runs)"""
+    import torch.distributed as dist
+    return 'cuda:{}'.format(int(device)) if dist.get_backend(group) == 'nccl' else 'cpu'
+
+
+def allreduce_values(values, op, group, device, dtype='float64'):
+    """all-reduce of a few host numbers (op: 'sum' | 'max'); returns a numpy array.  Used for row counts and radii of a fit
+    whose rows are sharded over ranks."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor(np.atleast_1d(values), dtype=getattr(torch, dtype), device=_coll_device(group, device))
+    dist.all_reduce(t, op=dist.ReduceOp.MAX if op == 'max' else dist.ReduceOp.SUM, group=group)
+    return t.cpu().numpy()
+
+
+def allgather_vector(vec, group, device):
+    """every rank's copy of a small float64 vector, stacked [world, len]"""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor(np.asarray(vec, dtype=np.float64), device=_coll_device(group, device))
+    out = [torch.empty_like(t) for _ in range(dist.get_world_size(group))]
+    dist.all_gather(out, t, group=group)
+    return torch.stack(out).cpu().numpy()
+
+
+def broadcast_vector(vec, src, group, device):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor(np.asarray(vec, dtype=np.float64), device=_coll_device(group, device))
+    dist.broadcast(t, src=dist.get_global_rank(group, src) if group is not None else src, group=group)
+    return t.cpu().numpy()
+
+
+def pick_center(best, x_best, group, device):
+    """PolyModel._set_bound's center_max point (poly.py:277-287) over sharded rows: every rank contributes its best local
+    (logp, x) -- or -inf when it has no valid candidate -- and all ranks pick the same winner; None when no rank has one."""
+    import numpy as np
+    allc = allgather_vector(np.concatenate(([best], x_best)), group, device)
+    i = int(np.argmax(allc[:, 0]))
+    return None if not np.isfinite(allc[i, 0]) else allc[i, 1:]
+
+
 def shard_bounds(total, rank, world):
     """contiguous shard [lo, hi) of `total` items for `rank` of `world` (first `total % world` ranks get one more)."""
     base, rem = divmod(int(total), int(world))

@@ -114,6 +114,13 @@ int bfb_fit_accumulate(bfb_handle h, const double *x, const double *y, const dou
 int64_t bfb_fit_buffer_size(bfb_handle h);
 /* device pointer of that buffer (for an in-place NCCL all-reduce by the host framework) */
 int bfb_fit_buffer(bfb_handle h, double **dev_ptr);
+/* The exchange step of a fit whose rows are sharded over GPUs (replaces nothing in the reference: its fit is single-process,
+ * modules/poly.py:505-589): pack the partial sums -- the upper block triangle of every Gram, X^T y, the shifted moments, the
+ * row count -- into ONE contiguous device buffer of *len doubles (10.6 MB at P = 1585), all-reduce it (sum) over the ranks
+ * (NCCL on *dev_ptr; or staged through the host with bfb_fit_exchange_host, dir 0 device -> host, 1 host -> device), unpack. */
+int bfb_fit_exchange_pack(bfb_handle h, double **dev_ptr, int64_t *len);
+int bfb_fit_exchange_host(bfb_handle h, double *host, int dir);
+int bfb_fit_exchange_unpack(bfb_handle h);
 /* solve the normal equations (equilibrated Cholesky + refinement), write packed coefficients in the
  * layout of bfb_model_desc.cfg_coef; also installs them into the handle's model. */
 int bfb_fit_solve(bfb_handle h, double *coef_out, double *rel_resid);

@@ -40,9 +40,19 @@ def _worker(rank, world, port, q):
     s2 = buf[P * P + P + n:-1].reshape(n, n)
     cnt = buf[-1]
     cov = (s2 - np.outer(s1, s1) / cnt) / (cnt - 1)
+    # the product's own small collectives of the sharded fit (bayesfast_b200/runtime.py, fit.py): row count, largest radius,
+    # the common shift of the moments, the center_max vote with a rank that has no valid candidate
+    from bayesfast_b200.runtime import allreduce_values, pick_center
+    from bayesfast_b200.fit import _common_shift
+    tot = int(allreduce_values([hi - lo], 'sum', g, 0, 'int64')[0])
+    mx = float(allreduce_values([1.5 + rank], 'max', g, 0)[0])
+    sh = _common_shift(x[lo:hi], n, rank, world, g, 0)
+    c1 = pick_center(7.5 if rank == 1 else -np.inf, np.full(n, 1. + rank), g, 0)          # rank 0: invalid logp
+    c2 = pick_center(-np.inf, np.zeros(n), g, 0)                                           # nobody has a candidate
+    extra = dict(tot=tot, mx=mx, shift=sh, c1=c1, c2_none=c2 is None)
     # chain sharding of sample()
     lo_c, hi_c = shard_bounds(37, rank, world)
-    q.put((rank, coef, cov, cnt, (lo_c, hi_c)))
+    q.put((rank, coef, cov, cnt, (lo_c, hi_c), extra))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -66,7 +76,9 @@ def test_fit_allreduce_and_chain_sharding_gloo(oracle):
     cfgs = [dict(order=k, input_mask=np.arange(n), output_mask=np.arange(1)) for k in ('linear', 'quadratic', 'cubic-2')]
     ref = oracle.fit(cfgs, n, 1, x, y)
     packed = np.concatenate([ref[0][0], ref[1][0][np.triu_indices(n)], ref[2][0].ravel()])
-    for rank, coef, cov, cnt, _ in res:
+    for rank, coef, cov, cnt, _, ex in res:
+        assert ex['tot'] == N and ex['mx'] == 2.5 and ex['c2_none']
+        assert np.array_equal(ex['shift'], x[0]) and np.array_equal(ex['c1'], np.full(n, 2.))
         assert cnt == N
         assert np.allclose(coef, packed, rtol=1e-8, atol=1e-10)
         assert np.allclose(cov, np.cov(x, rowvar=False), rtol=1e-10)

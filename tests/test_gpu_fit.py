@@ -1,7 +1,10 @@
 """GPU parity of PolyModel.fit (fused feature expansion + DMMA Gram + Cholesky) vs the reference's lstsq results."""
 import warnings
 
+import os
 import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 import pytest
 
 import _golden_io as gio
@@ -124,3 +127,67 @@ def test_density_fit_and_sample():
     assert post.shape == (256 * 200, n)
     assert np.all(np.abs(post.mean(axis=0)) < 0.05 * np.sqrt(np.diag(cov)) * 3)
     assert np.allclose(np.cov(post, rowvar=False), cov, atol=0.08 * np.max(np.diag(cov)))
+
+
+def _sharded_fit_worker(rank, world, port, q):
+    import os, sys
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'], os.environ['MASTER_PORT'] = '127.0.0.1', str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)        # two ranks share cuda:0: the exchange is host-staged
+    import bayesfast_b200 as bfb
+    from bayesfast_b200.runtime import shard_bounds
+    x, y = _sharded_problem()
+    lo, hi = shard_bounds(x.shape[0], rank, world) if rank >= 0 else (0, x.shape[0])
+    if rank == 1:
+        lo, hi = lo + 37, hi          # uneven shards
+    elif rank == 0:
+        hi = hi + 37
+    sur = bfb.PolyModel('cubic-2', input_size=x.shape[1], output_size=1)
+    den = bfb.Density(sur, decay_options=dict(use_decay=True))
+    den.fit(x[lo:hi], y[lo:hi], comm=True)
+    q.put((rank, [np.array(c._coef) for c in sur.configs], sur._mu, sur._hess, sur._alpha, sur._f_mu, den._mu, den._hess,
+           den._alpha, dict(sur._fit_exchange)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _sharded_problem():
+    rng = np.random.default_rng(21)
+    n, N = 7, 900
+    x = rng.normal(size=(N, n)) * 0.8 + 0.1
+    y = (-0.5 * np.sum(x**2, axis=1) + 0.1 * x[:, 0] * x[:, 1]**2 + 0.01 * rng.normal(size=N))[:, None]
+    return x, y
+
+
+def test_sharded_fit_product_path_two_ranks():
+    """Density.fit(..., comm=True) of two ranks (gloo, both on cuda:0) against the single-process fit: the packed exchange
+    buffer (upper block triangle of the Gram + moments), the all-reduced bound radius, the center_max vote and the decay
+    ellipsoid give every rank the SAME model as one process with all rows"""
+    import torch.multiprocessing as mp
+    import bayesfast_b200 as bfb
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29700 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_sharded_fit_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=300) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    x, y = _sharded_problem()
+    sur = bfb.PolyModel('cubic-2', input_size=x.shape[1], output_size=1)
+    den = bfb.Density(sur, decay_options=dict(use_decay=True))
+    den.fit(x, y)
+    for r in res:
+        for a, b in zip(r[1], [np.array(c._coef) for c in sur.configs]):
+            assert np.allclose(a, b, rtol=1e-9, atol=1e-11 * np.abs(b).max())
+        assert np.allclose(r[2], sur._mu, rtol=1e-12, atol=1e-14) and np.allclose(r[3], sur._hess, rtol=1e-10)
+        assert np.isclose(r[4], sur._alpha, rtol=1e-10) and np.allclose(r[5], sur._f_mu, rtol=1e-9)
+        assert np.allclose(r[6], den._mu, rtol=1e-12, atol=1e-14) and np.allclose(r[7], den._hess, rtol=1e-10)
+        assert np.isclose(r[8], den._alpha, rtol=1e-10)
+        assert r[9]['allreduce_bytes'] < 8 * (2 * 64 * 64 * 3 // 2 + 64)       # packed upper triangle, not the full P x P
+    for k in range(1, 9):                                # identical on both ranks: no broadcast needed after the solve
+        a, b = res[0][k], res[1][k]
+        assert all(np.array_equal(u, v) for u, v in zip(a, b)) if isinstance(a, list) else np.array_equal(a, b)
