@@ -82,6 +82,7 @@ def lib():
             L.bfb_logp_and_grad_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int]
             L.bfb_fit_begin.argtypes = [C.c_void_p, C.c_void_p]
             L.bfb_set_epilogue.argtypes = [C.c_void_p, C.c_int, C.c_double]
+            L.bfb_set_prior.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]
             L.bfb_sampler_init.argtypes = [C.c_void_p, C.POINTER(SamplerCfg), C.c_int64, _dp, _dp, _dp, _dp]
             L.bfb_sampler_init_dense.argtypes = [C.c_void_p, C.POINTER(SamplerCfg), C.c_int64, _dp, _dp, _dp, _dp]
             L.bfb_sampler_get_cov.argtypes = [C.c_void_p, _dp, _ip]
@@ -222,6 +223,13 @@ class Handle:
         check(self._L.bfb_set_model(self._h, C.byref(d)))
         self.n, self.m = n, m
         self._keep = keep
+        pr = spec.get('prior', None)              # dict(idx, mu, sig, c0): Gaussian prior on original-space inputs (third module)
+        if pr is not None:
+            w, mu = np.zeros(n), np.zeros(n)
+            idx = np.asarray(pr['idx'], dtype=np.int64)
+            w[idx] = 1. / np.asarray(pr['sig'], dtype=np.float64)**2
+            mu[idx] = np.asarray(pr['mu'], dtype=np.float64)
+            check(self._L.bfb_set_prior(self._h, w.ctypes.data, mu.ctypes.data, float(pr.get('c0', 0.))))
         ss = spec.get('epilogue_sumsq', None)     # set by Density._sync: logp = c0 - 1/2 sum_o f_o^2 over whitened outputs
         if ss is not None:
             check(self._L.bfb_set_epilogue(self._h, 1, float(ss)))

@@ -73,6 +73,12 @@ struct DevModel {
     // operand table of the tensor-core likelihood pipeline (bfb_lik_dmma.cu: one record per output), or null
     const double *lik_tab;
     int lik_nr;
+    int lik_ext;         // the pipeline has a radial bound / module rescale / variable transform / prior: model variant bits 3 | 1
+    // third module of the pipeline (bfb_set_prior): independent Gaussian prior on the original-space inputs,
+    // logp += p_c0 - 1/2 sum_j p_w[j] (x_j - p_mu[j])^2
+    int use_prior;
+    const double *p_w, *p_mu;   // [np]
+    double p_c0;
 };
 
 struct HostConfig {
@@ -121,7 +127,8 @@ struct bfb_context {
     std::vector<HostConfig> configs;
     std::vector<double> packed;          // host copy of packed coefficients
     bfb_model_desc desc_flags;           // scalar flags only (pointers invalid)
-    std::vector<double> h_mu, h_hess, h_fmu, h_s0, h_sdiff, h_dmu, h_dhess, h_ranges;
+    std::vector<double> h_mu, h_hess, h_fmu, h_s0, h_sdiff, h_dmu, h_dhess, h_ranges, h_pw, h_pmu;
+    double h_pc0;
     std::vector<uint8_t> h_hb;
     std::vector<void *> model_allocs;
     DevModel dm;

@@ -84,6 +84,127 @@ __device__ __forceinline__ double qsum(double v)
     return v;
 }
 
+// ----------------------------------------------------------------------------------------------------------------------
+// Extended likelihood pipeline (model variant bits 3 | 1): the DES-Y1 example's density shape (examples/des-y1-w-cosmosis.ipynb
+// cells 12-18) -- variable transform with hard bounds, module rescale, radial bound, m whitened outputs, Gaussian prior on
+// the original-space inputs -- around the per-output DMMAs.  Per point only the scalars of the bound (beta, outside) live
+// across the loop over the outputs; everything elementwise is recomputed afterwards, and the bound's Jacobian term is
+// applied ONCE to the accumulated gradient:  with G0 = -sum_o f_o J0_o and S1 = sum_o f_o (f0_o - f_mu_o) / alpha,
+//     grad = G0 - (S1 + (G0 . d) / beta) (H d / beta)          (PolyModel._fj_bound, poly.py:480-503, summed over the outputs)
+// Record m of the operand table holds H (fragments, like an S_o); slot OL + 33 of record o holds f_mu_o.
+// Per-dimension tables et[k * 32 + j]: k = 0 mu, 1 s0, 2 sdiff, 3 r_lo, 4 r_w, 5 hard-bound code, 6 log|r_w|, 7 p_w, 8 p_mu.
+// ----------------------------------------------------------------------------------------------------------------------
+struct LikExt {
+    int use_transform, use_scales, use_bound, use_prior;
+    double alpha, p_c0;
+};
+
+template <int NR>
+__device__ __forceinline__ void lik_elementwise(const double *et, const LikExt &E, int n, int lg, const double (&xt)[NR],
+                                                double (&xo)[NR], double (&xs)[NR], double (&tj)[NR], double (&tjj)[NR])
+{
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        const int j = 4 * r + lg;
+        double v = xt[r];
+        tj[r] = 1.; tjj[r] = 0.;
+        if (E.use_transform && j < n) {
+            const int hbj = (int)et[5 * 32 + j];
+            if (hbj != 0) to_original_1(xt[r], et[3 * 32 + j], et[4 * 32 + j], hbj, v, tj[r], tjj[r]);
+            else { v = et[3 * 32 + j] + xt[r] * et[4 * 32 + j]; tj[r] = et[4 * 32 + j]; }
+        }
+        xo[r] = v;
+        if (E.use_scales) v = (v - et[1 * 32 + j]) / et[2 * 32 + j];
+        xs[r] = (j < n) ? v : 0.;
+    }
+}
+
+// H d for the 8 points of the warp against the H record (global / L2: two calls per evaluation, not worth staging)
+template <int NR>
+__device__ __forceinline__ void lik_hd(const double *hrec, int lane, const double (&d)[NR], double (&Hd)[NR])
+{
+    constexpr int NT4 = (NR + 1) / 2;
+    double a_[NT4][2];
+#pragma unroll
+    for (int t = 0; t < NT4; ++t) a_[t][0] = a_[t][1] = 0.;
+#pragma unroll
+    for (int kt = 0; kt < NR; ++kt)
+#pragma unroll
+        for (int t = 0; t < NT4; ++t) dmma884(a_[t][0], a_[t][1], d[kt], __ldg(hrec + (kt * NT4 + t) * 32 + lane));
+#pragma unroll
+    for (int r = 0; r < NR; ++r) Hd[r] = a_[r / 2][r % 2];
+}
+
+// before the loop over the outputs: the point the outputs are evaluated at (x rescaled, or its projection onto the bound)
+template <int NR>
+__device__ __forceinline__ void lik_pre(const double *et, const LikExt &E, int n, int lane, const double (&xt)[NR], const double *hrec,
+                                        bool live, double (&xe)[NR], bool &outside, double &beta)
+{
+    const int lg = lane & 3;
+    double xo[NR], tj[NR], tjj[NR];
+    lik_elementwise<NR>(et, E, n, lg, xt, xo, xe, tj, tjj);
+    outside = false; beta = 0.;
+    if (E.use_bound) {
+        double d[NR], Hd[NR], part = 0.;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) d[r] = (4 * r + lg < n) ? xe[r] - et[4 * r + lg] : 0.;
+        lik_hd<NR>(hrec, lane, d, Hd);
+#pragma unroll
+        for (int r = 0; r < NR; ++r) part = fma(d[r], Hd[r], part);
+        beta = sqrt(qsum(part));
+        outside = live && (beta > E.alpha);
+        if (outside) {
+#pragma unroll
+            for (int r = 0; r < NR; ++r) xe[r] = (4 * r + lg < n) ? (E.alpha * xe[r] + (beta - E.alpha) * et[4 * r + lg]) / beta : 0.;
+        }
+    }
+}
+
+// after the loop: gr holds G0 = -sum_o f_o J0_o on entry, the gradient with respect to the transformed point on exit
+template <int NR>
+__device__ __forceinline__ void lik_post(const double *et, const LikExt &E, int n, int lane, const double (&xt)[NR], const double *hrec,
+                                         bool outside, double beta, double S1, double acc2, double e_c0, double (&gr)[NR], double &lp)
+{
+    const int lg = lane & 3;
+    double xo[NR], xs[NR], tj[NR], tjj[NR];
+    lik_elementwise<NR>(et, E, n, lg, xt, xo, xs, tj, tjj);
+    if (E.use_bound && __any_sync(BFB_FULL, outside)) {
+        double d[NR], Hd[NR], part = 0.;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) { d[r] = (4 * r + lg < n) ? xs[r] - et[4 * r + lg] : 0.; part = fma(gr[r], d[r], part); }
+        lik_hd<NR>(hrec, lane, d, Hd);
+        const double g0d = qsum(part);
+        if (outside) {
+            const double c = (S1 + g0d / beta) / beta;
+#pragma unroll
+            for (int r = 0; r < NR; ++r) gr[r] = fma(-c, Hd[r], gr[r]);
+        }
+    }
+    double ppart = 0., tpart = 0.;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        const int j = 4 * r + lg;
+        double g = gr[r];
+        if (E.use_scales) g = g / et[2 * 32 + j];
+        if (E.use_prior && j < n) {
+            const double dk = xo[r] - et[8 * 32 + j], wk = et[7 * 32 + j];
+            ppart = fma(wk * dk, dk, ppart);
+            g -= wk * dk;
+        }
+        g *= tj[r];
+        if (E.use_transform && j < n) {
+            if ((int)et[5 * 32 + j] != 0) { tpart += log(fabs(tj[r])); g += tjj[r] / tj[r]; }
+            else tpart += et[6 * 32 + j];
+        }
+        gr[r] = (j < n) ? g : 0.;
+    }
+    double z0 = 0., z1 = 0.;
+    qsum4(ppart, tpart, z0, z1, lane);
+    lp = e_c0 - 0.5 * acc2;
+    if (E.use_prior) lp += E.p_c0 - 0.5 * ppart;
+    if (E.use_transform) lp += tpart;
+}
+
 // One evaluation = two GEMM stages.  Stage A: h = H (x - mu) (the TD tiles of the D block; with the extended density also
 // h2 = H_decay (x_orig - mu_decay)) gives the Mahalanobis radius, i.e. the inside / outside decision of the radial bound
 // (poly.py:466-469).  Outside points are then REPLACED by their projection onto the ellipsoid before stage B, so the
@@ -127,6 +248,7 @@ struct DmmaConsts {
     const double *lik_tab;
     int m;
     double e_c0;
+    LikExt lx;
 };
 
 __device__ __forceinline__ DmmaConsts dmma_consts(const DevModel &M)
@@ -138,6 +260,8 @@ __device__ __forceinline__ DmmaConsts dmma_consts(const DevModel &M)
     K.use_transform = M.use_transform; K.use_scales = M.use_scales; K.use_decay = M.use_decay;
     K.c3_kt = M.c3_kt;
     K.lik_tab = M.lik_tab; K.m = M.m; K.e_c0 = M.e_c0;
+    K.lx.use_transform = M.use_transform; K.lx.use_scales = M.use_scales; K.lx.use_bound = M.use_bound; K.lx.use_prior = M.use_prior;
+    K.lx.alpha = M.alpha; K.lx.p_c0 = M.p_c0;
     return K;
 }
 
@@ -145,6 +269,19 @@ __device__ __forceinline__ DmmaConsts dmma_consts(const DevModel &M)
 template <int MV>
 __device__ __forceinline__ void dmma_stage_tables(const DevModel &M, double *msm)
 {
+    if ((MV & 8) && (MV & 2)) {
+        // extended likelihood pipeline: the per-dimension tables of lik_pre / lik_post
+        if (threadIdx.x < 32) {
+            const int j = threadIdx.x;
+            msm[j] = M.use_bound ? M.mu[j] : 0.;
+            msm[32 + j] = M.use_scales ? M.s0[j] : 0.; msm[64 + j] = M.use_scales ? M.sdiff[j] : 1.;
+            msm[96 + j] = M.use_transform ? M.r_lo[j] : 0.; msm[128 + j] = M.use_transform ? M.r_w[j] : 1.;
+            msm[160 + j] = M.use_transform ? (double)M.hb[j] : 0.;
+            msm[192 + j] = M.use_transform ? log(fabs(M.r_w[j])) : 0.;
+            msm[224 + j] = M.use_prior ? M.p_w[j] : 0.; msm[256 + j] = M.use_prior ? M.p_mu[j] : 0.;
+        }
+        return;
+    }
     if (threadIdx.x < 32) {
         const int j = threadIdx.x;
         msm[j] = M.use_bound ? M.mu[j] : 0.;
@@ -195,9 +332,13 @@ __device__ __forceinline__ void dmma_logp_grad(const double *bsm, int lane, cons
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
-        double acc2 = 0.;
+        double acc2 = 0., S1 = 0., beta = 0.;
+        bool outside = false;
+        double xe[NR];
 #pragma unroll
-        for (int r = 0; r < NR; ++r) gn[r] = 0.;
+        for (int r = 0; r < NR; ++r) { gn[r] = 0.; xe[r] = x_in[r]; }
+        const double *hrec = K.lik_tab + (size_t)K.m * REC;
+        if (EXT) lik_pre<NR>(msm, K.lx, K.n, lane, x_in, hrec, live, xe, outside, beta);
         __syncwarp();
         stage(0);
 #pragma unroll 1
@@ -212,21 +353,27 @@ __device__ __forceinline__ void dmma_logp_grad(const double *bsm, int lane, cons
 #pragma unroll
             for (int kt = 0; kt < NR; ++kt)
 #pragma unroll
-                for (int t = 0; t < NT4; ++t) dmma884(a_[t][0], a_[t][1], x_in[kt], rec[(kt * NT4 + t) * 32 + lane]);
+                for (int t = 0; t < NT4; ++t) dmma884(a_[t][0], a_[t][1], xe[kt], rec[(kt * NT4 + t) * 32 + lane]);
             double fpart = 0., jr[NR];
 #pragma unroll
             for (int r = 0; r < NR; ++r) {
                 const double l_ = rec[OL + 4 * r + lg_], y_ = a_[r / 2][r % 2];
-                fpart = fma(fma(0.5, y_, l_), x_in[r], fpart);
+                fpart = fma(fma(0.5, y_, l_), xe[r], fpart);
                 jr[r] = l_ + y_;
             }
-            const double f_ = rec[OL + 32] + qsum(fpart);
+            double f_ = rec[OL + 32] + qsum(fpart);
+            if (EXT && K.lx.use_bound) {
+                const double fmu = rec[OL + 33], f0 = f_;
+                if (outside) f_ = (beta * f0 - (beta - K.lx.alpha) * fmu) / K.lx.alpha;
+                S1 = fma(f_, (f0 - fmu) / K.lx.alpha, S1);
+            }
             acc2 = fma(f_, f_, acc2);
 #pragma unroll
             for (int r = 0; r < NR; ++r) gn[r] = fma(-f_, jr[r], gn[r]);
             __syncwarp();                                  // slot (o & 1) is refilled by the stage() of the next iteration
         }
-        lp = K.e_c0 - 0.5 * acc2;
+        if (EXT) lik_post<NR>(msm, K.lx, K.n, lane, x_in, hrec, outside, beta, S1, acc2, K.e_c0, gn, lp);
+        else lp = K.e_c0 - 0.5 * acc2;
         ke = qsum(ke_of(gn));
         return;
     }

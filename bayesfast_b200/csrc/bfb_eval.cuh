@@ -289,6 +289,21 @@ __device__ __forceinline__ void density_eval(const DevModel &M, const double (&x
 #pragma unroll
         for (int r = 0; r < NPL; ++r) grad[r] = J[r] * tj[r];
     }
+    if (M.use_prior) {
+        // third module (inputs ['like', 'x'], examples/des-y1-w-cosmosis.ipynb cells 12, 14): Gaussian prior on the original-space
+        // inputs, its Jacobian chained with the variable transform like the surrogate's (density.py:533-565)
+        double part = 0.;
+#pragma unroll
+        for (int r = 0; r < NPL; ++r) {
+            int j = lane + 32 * r;
+            if (j < n) {
+                const double dk = xo[r] - M.p_mu[j], wk = M.p_w[j];
+                part = fma(wk * dk, dk, part);
+                grad[r] -= wk * dk * tj[r];
+            }
+        }
+        f += M.p_c0 - 0.5 * warp_sum(part);
+    }
     if (M.use_decay) {
         double d[NPL], Hd[NPL];
 #pragma unroll

@@ -12,32 +12,47 @@
 // buffers filled with cp.async, the copy of chunk k + 1 running under the DMMAs of chunk k.  y_o never leaves the
 // registers: f_o (one quad reduction), sum f_o^2 and the gradient accumulate on the fly.
 //
-// Applies to linear + quadratic configs, n <= 32, no radial bound / rescale / decay / transform; everything else runs
-// density_eval (bfb_eval.cuh) on the generic kernel.
+// Applies to linear + quadratic configs, n <= 32.  With a radial bound, module rescale, variable transform or a Gaussian prior on
+// the inputs (the DES-Y1 example's density, examples/des-y1-w-cosmosis.ipynb cells 12-18) the EXT instantiation wraps the loop
+// over the outputs in lik_pre / lik_post (bfb_dmma.cuh); a decay term, cubic configs or n > 32 run density_eval (bfb_eval.cuh)
+// on the generic kernel.
 #include "bfb_dmma.cuh"
 #include <cstring>
 #include <cstdlib>
 
 
-template <int NR, int PG>
+template <int NR, int PG, bool EXT>
 __global__ void __launch_bounds__(128) lik_eval_dmma_kernel(const double *__restrict__ tab, int m, int n, double e_c0, int chunk,
                                                             const double *__restrict__ X, int64_t C,
-                                                            double *__restrict__ LP, double *__restrict__ G)
+                                                            double *__restrict__ LP, double *__restrict__ G, LikExt E)
 {
     constexpr int NT = (NR + 1) / 2, REC = lik_rec_doubles(NR), OL = NR * NT * 32;
     extern __shared__ double sm[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, gi = lane >> 2, lg = lane & 3;
     const int64_t per_block = 32 * PG;
+    // extended pipeline: per-dimension tables (after the H record) staged behind the two chunk buffers
+    const double *hrec = tab + (size_t)m * REC;
+    double *et = sm + (size_t)2 * chunk * REC;
+    if (EXT) {
+        for (int i = threadIdx.x; i < 288; i += blockDim.x) et[i] = hrec[REC + i];
+        __syncthreads();
+    }
     for (int64_t base = (int64_t)blockIdx.x * per_block; base < C; base += (int64_t)gridDim.x * per_block) {
-        double x[PG][NR], gr[PG][NR], acc2[PG];
+        double x[PG][NR], gr[PG][NR], acc2[PG], xt[EXT ? PG : 1][NR], S1[PG], beta[PG];
+        bool outside[PG];
         int64_t c[PG];
 #pragma unroll
         for (int g = 0; g < PG; ++g) {
             c[g] = base + (int64_t)(g * 4 + wib) * 8 + gi;
             const int64_t cc = c[g] < C ? c[g] : C - 1;
-            acc2[g] = 0.;
+            acc2[g] = 0.; S1[g] = 0.; beta[g] = 0.; outside[g] = false;
 #pragma unroll
             for (int r = 0; r < NR; ++r) { x[g][r] = (4 * r + lg < n) ? X[cc * n + 4 * r + lg] : 0.; gr[g][r] = 0.; }
+            if constexpr (EXT) {
+#pragma unroll
+                for (int r = 0; r < NR; ++r) xt[g][r] = x[g][r];
+                lik_pre<NR>(et, E, n, lane, xt[g], hrec, true, x[g], outside[g], beta[g]);
+            }
         }
         // chunks of outputs go through two shared-memory buffers: the cp.async copies of chunk k + 1 run under the DMMAs of chunk k
         const int n_chunks = (m + chunk - 1) / chunk;
@@ -82,7 +97,12 @@ __global__ void __launch_bounds__(128) lik_eval_dmma_kernel(const double *__rest
                     double fpart = 0.;
 #pragma unroll
                     for (int r = 0; r < NR; ++r) fpart = fma(fma(0.5, acc[g][r / 2][r % 2], lin[r]), x[g][r], fpart);
-                    const double f = c0 + qsum(fpart);
+                    double f = c0 + qsum(fpart);
+                    if (EXT && E.use_bound) {
+                        const double fmu = rec[OL + 33], f0 = f;
+                        if (outside[g]) f = (beta[g] * f0 - (beta[g] - E.alpha) * fmu) / E.alpha;
+                        S1[g] = fma(f, (f0 - fmu) / E.alpha, S1[g]);
+                    }
                     acc2[g] = fma(f, f, acc2[g]);
 #pragma unroll
                     for (int r = 0; r < NR; ++r) gr[g][r] = fma(-f, lin[r] + acc[g][r / 2][r % 2], gr[g][r]);
@@ -92,8 +112,10 @@ __global__ void __launch_bounds__(128) lik_eval_dmma_kernel(const double *__rest
         }
 #pragma unroll
         for (int g = 0; g < PG; ++g) {
+            double lpv = e_c0 - 0.5 * acc2[g];
+            if constexpr (EXT) lik_post<NR>(et, E, n, lane, xt[g], hrec, outside[g], beta[g], S1[g], acc2[g], e_c0, gr[g], lpv);
             if (c[g] < C) {
-                if (lg == 0) LP[c[g]] = e_c0 - 0.5 * acc2[g];
+                if (lg == 0) LP[c[g]] = lpv;
 #pragma unroll
                 for (int r = 0; r < NR; ++r) if (4 * r + lg < n) G[c[g] * n + 4 * r + lg] = gr[g][r];
             }
@@ -110,10 +132,10 @@ int bfb_build_lik_table(bfb_context *h)
     h->lik_tab = nullptr; h->lik_nr = 0;
     const int n = M.n, np = M.np, m = M.m;
     const int nr = bfb_frag_nr(n);
-    if (nr == 0 || np != 32 || !M.has_quad || M.has_c2 || M.has_c3 || M.use_bound || M.use_scales || M.use_decay || M.use_transform)
-        return BFB_OK;
+    if (nr == 0 || np != 32 || !M.has_quad || M.has_c2 || M.has_c3 || M.use_decay) return BFB_OK;
     const int NT = (nr + 1) / 2, REC = lik_rec_doubles(nr), OL = nr * NT * 32;
-    std::vector<double> S((size_t)m * n * np), lin((size_t)m * np), c0(m), tab((size_t)m * REC, 0.);
+    // m output records | the H record (radial bound; fragments like an S_o) | per-dimension tables of the extended pipeline
+    std::vector<double> S((size_t)m * n * np), lin((size_t)m * np), c0(m), tab((size_t)(m + 1) * REC + 288, 0.);
     BFB_CUDA(cudaMemcpy(S.data(), M.S, sizeof(double) * S.size(), cudaMemcpyDeviceToHost));
     BFB_CUDA(cudaMemcpy(lin.data(), M.lin, sizeof(double) * lin.size(), cudaMemcpyDeviceToHost));
     BFB_CUDA(cudaMemcpy(c0.data(), M.c0, sizeof(double) * c0.size(), cudaMemcpyDeviceToHost));
@@ -129,7 +151,33 @@ int bfb_build_lik_table(bfb_context *h)
                 }
         for (int j = 0; j < n; ++j) rec[OL + j] = lin[(size_t)o * np + j];
         rec[OL + 32] = c0[o];
+        if (M.use_bound && o < (int)h->h_fmu.size()) rec[OL + 33] = h->h_fmu[o];
     }
+    const bool ext = M.use_bound || M.use_scales || M.use_transform || M.use_prior;
+    if (ext) {
+        double *rec = tab.data() + (size_t)m * REC, *et = rec + REC;
+        if (M.use_bound)
+            for (int kt = 0; kt < nr; ++kt)
+                for (int t = 0; t < NT; ++t)
+                    for (int lane = 0; lane < 32; ++lane) {
+                        const int k = 4 * kt + (lane & 3), gid = lane >> 2, own = gid >> 1, e = gid & 1;
+                        const int v = 2 * t + e, j = 4 * v + own;
+                        if (v < nr && k < n && j < n) rec[(kt * NT + t) * 32 + lane] = h->h_hess[(size_t)j * n + k];
+                    }
+        for (int j = 0; j < 32; ++j) { et[2 * 32 + j] = 1.; et[4 * 32 + j] = 1.; }
+        for (int j = 0; j < n; ++j) {
+            if (M.use_bound) et[j] = h->h_mu[j];
+            if (M.use_scales) { et[32 + j] = h->h_s0[j]; et[64 + j] = h->h_sdiff[j]; }
+            if (M.use_transform) {
+                const double lo = h->h_ranges[2 * j], w = h->h_ranges[2 * j + 1] - h->h_ranges[2 * j];
+                et[96 + j] = lo; et[128 + j] = w;
+                et[160 + j] = (double)((h->h_hb[2 * j] ? 1 : 0) | (h->h_hb[2 * j + 1] ? 2 : 0));
+                et[192 + j] = log(fabs(w));
+            }
+            if (M.use_prior) { et[224 + j] = h->h_pw[j]; et[256 + j] = h->h_pmu[j]; }
+        }
+    }
+    M.lik_ext = ext ? 1 : 0;
     void *p = nullptr;
     BFB_CUDA(cudaMalloc(&p, sizeof(double) * tab.size()));
     h->model_allocs.push_back(p);
@@ -146,12 +194,21 @@ static int launch_lik(bfb_context *h, const double *X, int64_t C, double *LP, do
     int chunk = (32 * 1024) / (int)(REC * sizeof(double));           // 2 buffers of <= 32 KB of staged records: 3 blocks per SM
     if (const char *e = getenv("BFB200_LIK_CHUNK")) { int v = atoi(e); if (v >= 1 && (size_t)v * REC * sizeof(double) <= 100 * 1024) chunk = v; }
     if (chunk > h->dm.m) chunk = h->dm.m;
-    const size_t smem = sizeof(double) * 2 * (size_t)chunk * REC;
-    BFB_CUDA(cudaFuncSetAttribute(lik_eval_dmma_kernel<NR, PG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem = sizeof(double) * (2 * (size_t)chunk * REC + 288);
     const int64_t want = (C + 32 * PG - 1) / (32 * PG);
     const int64_t cap = (int64_t)h->sm_count * 3;
     const int blocks = (int)(want < cap ? want : cap);
-    lik_eval_dmma_kernel<NR, PG><<<blocks, 128, smem, h->stream>>>(h->lik_tab, h->dm.m, h->dm.n, h->dm.e_c0, chunk, X, C, LP, G);
+    const DevModel &M = h->dm;
+    LikExt E;
+    E.use_transform = M.use_transform; E.use_scales = M.use_scales; E.use_bound = M.use_bound; E.use_prior = M.use_prior;
+    E.alpha = M.alpha; E.p_c0 = M.p_c0;
+    if (M.lik_ext) {
+        BFB_CUDA(cudaFuncSetAttribute(lik_eval_dmma_kernel<NR, PG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        lik_eval_dmma_kernel<NR, PG, true><<<blocks, 128, smem, h->stream>>>(h->lik_tab, M.m, M.n, M.e_c0, chunk, X, C, LP, G, E);
+    } else {
+        BFB_CUDA(cudaFuncSetAttribute(lik_eval_dmma_kernel<NR, PG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        lik_eval_dmma_kernel<NR, PG, false><<<blocks, 128, smem, h->stream>>>(h->lik_tab, M.m, M.n, M.e_c0, chunk, X, C, LP, G, E);
+    }
     h->launches++;
     BFB_CUDA(cudaGetLastError());
     return BFB_OK;

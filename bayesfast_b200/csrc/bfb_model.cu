@@ -422,6 +422,31 @@ extern "C" int bfb_set_model(bfb_handle h, const bfb_model_desc *d)
     return BFB_OK;
 }
 
+// Third module of the DES-Y1 example's pipeline (examples/des-y1-w-cosmosis.ipynb cells 12-14: des_post_f(like, x) = like +
+// prior(x)): independent Gaussian prior on original-space inputs, logp += c0 - 1/2 sum_j w[j] (x_j - mu[j])^2 with w = 1 /
+// sigma^2 (0 where an input has no prior).  w == NULL removes it.  Call after bfb_set_model and before bfb_set_epilogue.
+extern "C" int bfb_set_prior(bfb_handle h, const double *w, const double *mu, double c0)
+{
+    BFB_REQUIRE(h && h->has_model, BFB_ERR_STATE, "bfb_set_prior: no model set");
+    BFB_CUDA(cudaSetDevice(h->device));
+    BFB_CUDA(cudaStreamSynchronize(h->stream));
+    DevModel &D = h->dm;
+    if (!w) { D.use_prior = 0; h->h_pw.clear(); h->h_pmu.clear(); return BFB_OK; }
+    BFB_REQUIRE(mu, BFB_ERR_ARG, "bfb_set_prior: mu missing");
+    const int n = h->n, np = h->np;
+    for (int j = 0; j < n; ++j) BFB_REQUIRE(w[j] >= 0. && std::isfinite(w[j]) && std::isfinite(mu[j]), BFB_ERR_ARG, "bfb_set_prior: bad weight / mean at input %d", j);
+    h->h_pw.assign(w, w + n); h->h_pmu.assign(mu, mu + n); h->h_pc0 = c0;
+    std::vector<double> pw(np, 0.), pm(np, 0.);
+    for (int j = 0; j < n; ++j) { pw[j] = w[j]; pm[j] = mu[j]; }
+    int rc;
+    if ((rc = upload(h, pw, &D.p_w))) return rc;
+    if ((rc = upload(h, pm, &D.p_mu))) return rc;
+    D.use_prior = 1; D.p_c0 = c0;
+    D.frag_nr = 0;                       // logp is no longer output 0 alone: the single-output tensor-core evaluators are off
+    BFB_CUDA(cudaStreamSynchronize(h->stream));
+    return BFB_OK;
+}
+
 // Second module of a two-module pipeline (core/density.py:487-566: surrogate x -> m outputs, then a user Module m -> logp):
 // kind 1 = Gaussian likelihood logp = c0 - 1/2 |f|^2 of the m outputs of the model set before, which the caller has
 // pre-whitened (f' = Lt (f - d) with Cinv = Lt^T Lt folds into the polynomial coefficients, the constants and f_mu because

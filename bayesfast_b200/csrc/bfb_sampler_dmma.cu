@@ -879,10 +879,13 @@ int bfb_launch_hmc_dmma(bfb_context *h, const bfb_run_out &o, int n_iter)
     if (M.epilogue) {                       // likelihood pipeline (model variant bit 3): operand streamed from L2
         if (!M.lik_tab) return 1;
         if (const char *e = getenv("BFB200_SAMPLER")) { if (strcmp(e, "dmma")) return 1; }
-        switch (M.lik_nr) {
-        case 4: return launch_hmc_dmma_w<4, 8>(h, o, n_iter);
-        case 7: return launch_hmc_dmma_w<7, 8>(h, o, n_iter);
-        case 8: return launch_hmc_dmma_w<8, 8>(h, o, n_iter);
+        switch (M.lik_nr * 2 + (M.lik_ext ? 1 : 0)) {
+        case 8: return launch_hmc_dmma_w<4, 8>(h, o, n_iter);
+        case 14: return launch_hmc_dmma_w<7, 8>(h, o, n_iter);
+        case 16: return launch_hmc_dmma_w<8, 8>(h, o, n_iter);
+        case 9: return launch_hmc_dmma_w<4, 10>(h, o, n_iter);       // bound / rescale / transform / prior around the outputs
+        case 15: return launch_hmc_dmma_w<7, 10>(h, o, n_iter);
+        case 17: return launch_hmc_dmma_w<8, 10>(h, o, n_iter);
         }
         return 1;
     }
@@ -984,10 +987,13 @@ int bfb_launch_nuts_dmma(bfb_context *h, const bfb_run_out &o, int n_iter)
     if (M.epilogue) {                       // likelihood pipeline (model variant bit 3): operand streamed from L2
         if (!M.lik_tab || h->scfg.max_treedepth > 10) return 1;
         if (const char *e = getenv("BFB200_SAMPLER")) { if (strcmp(e, "dmma")) return 1; }
-        switch (M.lik_nr) {
-        case 4: return launch_dmma_w<4, 8>(h, o, n_iter);
-        case 7: return launch_dmma_w<7, 8>(h, o, n_iter);
-        case 8: return launch_dmma_w<8, 8>(h, o, n_iter);
+        switch (M.lik_nr * 2 + (M.lik_ext ? 1 : 0)) {
+        case 8: return launch_dmma_w<4, 8>(h, o, n_iter);
+        case 14: return launch_dmma_w<7, 8>(h, o, n_iter);
+        case 16: return launch_dmma_w<8, 8>(h, o, n_iter);
+        case 9: return launch_dmma_w<4, 10>(h, o, n_iter);           // bound / rescale / transform / prior around the outputs
+        case 15: return launch_dmma_w<7, 10>(h, o, n_iter);
+        case 17: return launch_dmma_w<8, 10>(h, o, n_iter);
         }
         return 1;
     }

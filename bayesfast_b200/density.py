@@ -18,7 +18,7 @@ from . import transforms as tf
 from ._cabi import n_packed
 from .poly import PolyModel, PolyConfig, pack_dense, unpack_dense
 
-__all__ = ['Density', 'DecayOptions', 'GaussianLikelihood', 'whiten_spec']
+__all__ = ['Density', 'DecayOptions', 'GaussianLikelihood', 'GaussianPrior', 'whiten_spec']
 
 DecayOptions = namedtuple('DecayOptions', ('use_decay', 'alpha', 'alpha_p', 'gamma'))
 
@@ -63,6 +63,39 @@ class GaussianLikelihood:
 
     def to_spec(self):
         return dict(d=self.mean.copy(), cinv=self.inv_cov.copy(), c0=self.const)
+
+
+class GaussianPrior:
+    """
+    The third module of the DES-Y1 example's pipeline (examples/des-y1-w-cosmosis.ipynb cells 12-14): an independent Gaussian
+    prior on some of the ORIGINAL-space inputs added to the likelihood,
+
+        logp = like + const - 1/2 sum_k ((x[indices[k]] - mean[k]) / sigma[k])^2
+
+    (des_post_f / des_post_fj, a user Module with inputs ['like', 'x'] in the reference).  It is evaluated at the point itself,
+    not at its projection onto the surrogate's radial bound, and its Jacobian is chained with the variable transform.
+    """
+
+    def __init__(self, indices, mean, sigma, const=0.):
+        self.indices = np.atleast_1d(np.asarray(indices, dtype=np.int64))
+        self.mean = np.atleast_1d(np.asarray(mean, dtype=np.float64))
+        self.sigma = np.atleast_1d(np.asarray(sigma, dtype=np.float64))
+        if not (self.indices.ndim == 1 and self.mean.shape == self.indices.shape == self.sigma.shape):
+            raise ValueError('indices, mean and sigma should be 1-d arrays of the same length.')
+        if np.unique(self.indices).size != self.indices.size or np.any(self.indices < 0):
+            raise ValueError('indices should be unique and non-negative.')
+        if not np.all(self.sigma > 0):
+            raise ValueError('sigma should be positive.')
+        self.const = float(const)
+
+    def logp(self, x):
+        x = np.asarray(x, dtype=np.float64)
+        return self.const - 0.5 * np.sum(((x[..., self.indices] - self.mean) / self.sigma)**2, axis=-1)
+
+    __call__ = logp
+
+    def to_spec(self):
+        return dict(idx=self.indices.copy(), mu=self.mean.copy(), sig=self.sigma.copy(), c0=self.const)
 
 
 def whiten_spec(spec, lik):
@@ -117,7 +150,7 @@ class Density:
     """
 
     def __init__(self, surrogate, input_scales=None, hard_bounds=False, decay_options=None,
-                 density_name='__var__', input_vars='__var__', likelihood=None):
+                 density_name='__var__', input_vars='__var__', likelihood=None, prior=None):
         if not isinstance(surrogate, PolyModel):
             raise ValueError('surrogate should be a bayesfast_b200.PolyModel: only surrogate-only densities run '
                              'on the device, there is no CPU fallback.')
@@ -128,6 +161,11 @@ class Density:
             raise ValueError('the likelihood takes {} inputs but the surrogate has {} outputs.'.format(
                 likelihood.output_size, surrogate.output_size))
         self._likelihood = likelihood
+        if prior is not None and not isinstance(prior, GaussianPrior):
+            raise ValueError('prior should be a GaussianPrior: arbitrary Python modules cannot run on the device.')
+        if prior is not None and prior.indices.size and prior.indices.max() >= surrogate.input_size:
+            raise ValueError('the prior refers to input {} but the density has {} inputs.'.format(int(prior.indices.max()), surrogate.input_size))
+        self._prior = prior
         self.density_name = str(density_name)
         self.input_vars = [input_vars] if isinstance(input_vars, str) else list(input_vars)
         n = surrogate.input_size
@@ -145,6 +183,7 @@ class Density:
     surrogate = property(lambda self: self._surrogate)
     surrogate_list = property(lambda self: [self._surrogate])
     likelihood = property(lambda self: self.__dict__.get('_likelihood', None))
+    prior = property(lambda self: self.__dict__.get('_prior', None))
     input_size = property(lambda self: self._surrogate.input_size)
     input_scales = property(lambda self: self._input_scales)
     hard_bounds = property(lambda self: self._hard_bounds)
@@ -254,6 +293,8 @@ class Density:
             spec['hard_bounds'] = self._hard_bounds.copy()
         if self.likelihood is not None:
             spec['epilogue'] = self.likelihood.to_spec()      # un-whitened (what the oracle restates); _sync whitens
+        if getattr(self, '_prior', None) is not None:
+            spec['prior'] = self._prior.to_spec()
         return spec
 
     def _sync(self, original_space=False):
@@ -324,6 +365,8 @@ class Density:
                 y = y[:, None]
             # logp of the pipeline, for center_max (poly.py:277-286): output #0, or the likelihood of the outputs
             logp = y[:, 0].copy() if self.likelihood is None else self.likelihood.logp(y)
+            if getattr(self, '_prior', None) is not None:
+                logp = logp + self._prior.logp(x)
         if self._use_decay:
             self._set_decay(x, comm=comm)
         su = self._surrogate
@@ -335,12 +378,13 @@ class Density:
 
     # ------------------------------------------------------------------ adapter
     @classmethod
-    def from_reference(cls, ref, device=None, likelihood=None):
+    def from_reference(cls, ref, device=None, likelihood=None, prior=None):
         """
         Build from a fitted bayesfast.Density (duck-typed: reads _surrogate_list, _module_list, _input_scales,
         _hard_bounds, decay attributes).  Raises if the density is not surrogate-only / PolyModel-representable.
-        With `likelihood` (a GaussianLikelihood restating the LAST module of the reference's list) the surrogate
-        must replace every module but that one.
+        With `likelihood` (a GaussianLikelihood restating the module after the surrogate) the surrogate must replace
+        every module but that one; with `prior` as well (a GaussianPrior restating a further, last module that adds a prior on
+        the inputs to the likelihood: module_2 of examples/des-y1-w-cosmosis.ipynb) every module but those two.
         """
         sl = list(getattr(ref, '_surrogate_list', []))
         if len(sl) != 1:
@@ -350,10 +394,14 @@ class Density:
             raise ValueError('the surrogate is not a PolyModel.')
         n_mod = len(getattr(ref, '_module_list', []))
         i_step, n_step = rs._scope
+        if prior is not None and likelihood is None:
+            raise ValueError('a prior module needs the likelihood module it is added to.')
         if likelihood is not None:
-            if not (i_step == 0 and n_step == n_mod - 1):
-                raise ValueError('with a likelihood the surrogate must replace all modules but the last '
-                                 '(scope={}, {} modules).'.format(tuple(rs._scope), n_mod))
+            n_tail = 1 + (prior is not None)
+            if not (i_step == 0 and n_step == n_mod - n_tail):
+                raise ValueError('with a likelihood{} the surrogate must replace all modules but the last {} '
+                                 '(scope={}, {} modules).'.format(' and a prior' if prior is not None else '', n_tail,
+                                                                  tuple(rs._scope), n_mod))
         elif not (i_step % max(n_mod, 1) == 0 and n_step == n_mod):
             raise ValueError('the surrogate must replace the whole module list (scope={}, {} modules): arbitrary '
                              'Python modules cannot run on the device.'.format(tuple(rs._scope), n_mod))
@@ -380,7 +428,7 @@ class Density:
                   hard_bounds=hb if isinstance(hb, bool) else np.array(hb),
                   decay_options=dict(use_decay=ref._use_decay, alpha=ref._alpha, alpha_p=ref._alpha_p,
                                      gamma=ref._gamma),
-                  density_name=getattr(ref, 'density_name', '__var__'), likelihood=likelihood)
+                  density_name=getattr(ref, 'density_name', '__var__'), likelihood=likelihood, prior=prior)
         if ref._use_decay and hasattr(ref, '_mu'):
             den._mu, den._hess = np.array(ref._mu), np.array(ref._hess)
             den._alpha_2 = float(ref._alpha_2)

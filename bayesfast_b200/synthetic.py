@@ -4,7 +4,7 @@ true log-density, training points for the surrogate fit and chain starting point
 """
 import numpy as np
 
-__all__ = ['des_shaped', 'correlated_gaussian', 'des_pipeline', 'n_param']
+__all__ = ['des_shaped', 'correlated_gaussian', 'des_pipeline', 'cubic3_stack', 'n_param']
 
 
 def n_param(order, n):
@@ -87,3 +87,24 @@ def des_pipeline(n=26, m=457, seed=0, n_blocks=8, n_in=10):
     spec = dict(n=n, m=m, configs=cfgs, use_bound=False, input_scales=None, use_decay=False, transform_ranges=None,
                 epilogue=lik.to_spec())
     return spec, lik
+
+
+def cubic3_stack(n=64, seed=3, cond=30., cubic_scale=0.02):
+    """BASELINE configs[3]: a 64-D cubic-3 surrogate (linear + quadratic + cubic-2 + cubic-3 configs, P = 47905 at n = 64) with
+    INJECTED coefficients -- a random SPD quadratic part (condition number `cond`) plus small random cubic terms, so that the
+    curvature varies along a trajectory and the NUTS tree depths of the chains spread.  Returns (device spec with packed
+    coefficients, covariance of the Gaussian part)."""
+    rng = np.random.default_rng(seed)
+    P = _spd(n, cond, rng)
+    cov = np.linalg.inv(P)
+    lin = np.zeros((1, n + 1))
+    lin[0, 1:] = 0.05 * rng.normal(size=n)
+    iu = np.triu_indices(n)
+    quad = np.where(iu[0] == iu[1], -0.5 * P[iu], -P[iu])[None]
+    c2 = (cubic_scale * rng.normal(size=(1, n * n)) / n)
+    c3 = (cubic_scale * rng.normal(size=(1, n * (n - 1) * (n - 2) // 6)) / n)
+    full = np.arange(n)
+    cfgs = [dict(order=o, input_mask=full, output_mask=np.arange(1), packed=a)
+            for o, a in (('linear', lin), ('quadratic', quad), ('cubic-2', c2), ('cubic-3', c3))]
+    spec = dict(n=n, m=1, configs=cfgs, use_bound=False, input_scales=None, use_decay=False, transform_ranges=None)
+    return spec, cov

@@ -17,11 +17,18 @@ carries `more_chains` (north_star: "at least 4096 chains per GPU"): the same run
 tensor cores: batched logp + gradient (bfb_lik_dmma.cu) and a 4096-chain NUTS run (model variant bit 3), same FP64 peak.
 
   value : sum(tree_size) of all ranks / max-over-ranks device time of K steps, inputs resident in HBM
-  e2e   : the same through bayesfast_b200.sample() with host x_0 and all samples + stats copied back
+  e2e   : the same through bayesfast_b200.sample(keep='post_warmup') with host x_0; the samples and all statistics of the
+          1000 post-warm-up iterations come back to pinned host memory (what SampleTrace.get hands to its callers,
+          sample_trace.py:762-787; the warm-up records never leave the device).  `e2e_variants` (N = 1): every record of every
+          iteration (round-1 definition), and thin=10 + on-device mean / covariance.
   roofline : algorithmic FP64 flops (8n^2+24n per chain-leapfrog) / kernel time (CUDA events on
              the launching stream) vs the FP64 peak measured in this run (MEASURED_PEAKS.json has no FP64 entry)
-  cpu_baseline : the oracle (C restatement of the reference path, OpenMP over chains) on this box's host cores,
-             bounded sample of the same workload.  `--impl reference` runs only that.
+  cpu_baseline : the UNMODIFIED reference (baseline/_ref, installed by __graft_entry__.build()) through its own public API
+             and multiprocess chain pool (bf.sample + set_backend(cores)) on this box's host cores, full-length chains of the
+             same workload; next to it `port`: the oracle (C restatement, OpenMP over chains).  `--impl reference` runs only
+             the reference arm (the port when baseline/_ref is missing; the line says which).
+  extras (N = 1 unless noted): more_chains, team_kernel, hmc_kernel, eval_kernel, pipeline_kernel, config3 (64-D cubic-3),
+             fit_sweep (d = 32 cubic-2, N = 1e4 .. 1e7 rows; at N > 1 GPUs rows sharded + the NCCL all-reduce timed).
 """
 import argparse
 import json
@@ -110,6 +117,247 @@ def run_cpu_baseline(spec, prob, budget_s=15., n_threads=0):
                        '3.2e4/s on 8 cores (BASELINE.md)'.format(chains, N_ITER, N_WARMUP, leaves, dt)), leaves, dt
 
 
+def run_reference_python(prob, cores, per=2, n_iter=N_ITER, n_warmup=N_WARMUP, timeout=900):
+    """the real reference (baseline/_ref) in a subprocess: bf.sample over its own process pool; None if it is not installed"""
+    import glob
+    import tempfile
+    if not glob.glob(os.path.join(ROOT, 'baseline', '_ref', 'bayesfast', 'modules', '_poly*.so')):
+        return None
+    n_chain = cores * per
+    with tempfile.TemporaryDirectory() as d:
+        f = os.path.join(d, 'in.npz')
+        np.savez(f, x_fit=prob['x_fit'], y_fit=prob['y_fit'], x_0=prob['x_0'][:n_chain], n_iter=n_iter, n_warmup=n_warmup, order=ORDER)
+        env = dict(os.environ, OMP_NUM_THREADS='1', OPENBLAS_NUM_THREADS='1', MKL_NUM_THREADS='1')
+        try:
+            r = subprocess.run([sys.executable, os.path.join(ROOT, 'baseline', 'ref_runner.py'), f, str(cores), str(per)],
+                               capture_output=True, text=True, timeout=timeout, env=env)
+            out = json.loads(r.stdout.strip().splitlines()[-1])
+        except Exception as exc:
+            return dict(error=repr(exc))
+    return dict(value=out['value'], unit='leapfrog-steps*chains/s', cores=cores, kind='reference', leaves=out['leaves'], seconds=out['wall_s'],
+                per_core=out['value'] / cores, fit_seconds=out['fit_s'], mean_tree_size=out['mean_tree_size'],
+                sample='h3jia/bayesfast unmodified (baseline/_ref): bf.sample, NUTS, set_backend({0}), {1} full chains (n_iter={2}, '
+                       'n_warmup={3}) of the same workload, {4} leapfrogs in {5:.1f} s wall including pool start-up'.format(
+                           cores, out['n_chain'], n_iter, n_warmup, out['leaves'], out['wall_s']))
+
+
+def extra_measurements(args, bfb, torch, den, h, prob, x0, trace_kw, flush, peak, dev, C):
+    """supplementary numbers of the bench line (rank 0, single GPU): none of them enters `value` / `e2e`"""
+    from bayesfast_b200 import synthetic, _cabi
+    extras = {}
+    # (a) the same run with 16384 chains on this GPU (two warps per scheduler instead of one): kernel-only value
+    C2 = 16384
+    prob2 = synthetic.des_shaped(N_DIM, seed=1, n_chain=C2, order=ORDER)
+    cfg2 = bfb.NTrace(n_chain=C2, n_iter=N_ITER, n_warmup=N_WARMUP, x_0=prob2['x_0'], random_generator=SEED)._cfg_dict(SEED, 0)
+    h.sampler_init(cfg2, prob2['x_0'], 1. / N_DIM**0.25, np.ones(N_DIM), prob2['x_0'])
+    best = None
+    for i in range(3):
+        h.sampler_reset()
+        flush.zero_()
+        torch.cuda.synchronize(dev)
+        r2 = h.sampler_run('NUTS', N_ITER, out_ptrs={})
+        ms2 = h.last_kernel_ms()
+        if i > 0 and (best is None or ms2 < best[1]):
+            best = (r2['total_tree_size'], ms2)
+    tf2 = FLOPS_PER_LEAF * best[0] / (best[1] * 1e-3) / 1e12
+    extras['more_chains'] = dict(chains_per_gpu=C2, value=best[0] / (best[1] * 1e-3), unit='leapfrog-steps*chains/s',
+                                 kernel_ms=best[1], outputs='none written (kernel only)', kernel=h.sampler_last_path(),
+                                 roofline_frac=tf2 / peak, achieved_tflops=tf2)
+    # (a2) lock-step HMC (hmc.py:16-49, n_int_step = 32) on the same chains: the tensor-core integrator without the NUTS
+    # tree bookkeeping (hmc_dmma_kernel), kernel only
+    hm = {}
+    for Ch, x0h in ((C, x0), (C2, prob2['x_0'])):
+        cfgh = bfb.HTrace(n_chain=Ch, n_iter=300, n_warmup=100, x_0=x0h, n_int_step=32, random_generator=SEED)._cfg_dict(SEED, 0)
+        h.sampler_init(cfgh, x0h, 1. / N_DIM**0.25, np.ones(N_DIM), x0h)
+        h.sampler_run('HMC', 100, out_ptrs={})                         # step-size adaptation
+        rh = h.sampler_run('HMC', 100, out_ptrs={})
+        msh = h.last_kernel_ms()
+        tfh = FLOPS_PER_LEAF * rh['total_tree_size'] / (msh * 1e-3) / 1e12
+        hm[str(Ch)] = dict(chains_per_gpu=Ch, value=rh['total_tree_size'] / (msh * 1e-3), unit='leapfrog-steps*chains/s',
+                           kernel='hmc_%s_kernel' % h.sampler_last_path(), kernel_ms=msh, roofline_frac=tfh / peak, achieved_tflops=tfh)
+    extras['hmc_kernel'] = dict(n_int_step=32, iterations=100, outputs='none written (kernel only)', runs=hm,
+                                note='hmc_team_kernel (8 chains per team of four warps) up to 4 groups per SM, hmc_dmma_kernel (8 chains per warp) above')
+    # (b) the surrogate evaluation kernel alone: logp + gradient of 2^22 device-resident points
+    Ce = 1 << 22
+    Xe = torch.randn(Ce, N_DIM, dtype=torch.float64, device='cuda:%d' % dev) @ torch.tensor(np.linalg.cholesky(prob['cov']).T, device='cuda:%d' % dev)
+    Xe = Xe.contiguous()
+    lpe = torch.empty(Ce, dtype=torch.float64, device='cuda:%d' % dev)
+    ge = torch.empty(Ce, N_DIM, dtype=torch.float64, device='cuda:%d' % dev)
+    torch.cuda.synchronize(dev)
+    mse = []
+    for i in range(6):
+        h.logp_and_grad_batch_dev(Xe.data_ptr(), Ce, lpe.data_ptr(), ge.data_ptr())
+        mse.append(h.last_kernel_ms())
+    mse = float(np.mean(mse[1:]))
+    fe = (8 * N_DIM * N_DIM + 15 * N_DIM) * Ce
+    extras['eval_kernel'] = dict(kernel='eval_dmma_kernel', points=Ce, ms=mse, points_per_s=Ce / mse * 1e3,
+                                 algorithmic_flops_per_point=8 * N_DIM * N_DIM + 15 * N_DIM,
+                                 roofline=dict(bound='tensor', achieved=fe / mse / 1e9, peak=peak, unit='TFLOP/s', frac=fe / mse / 1e9 / peak),
+                                 hbm_gbs=Ce * (2 * N_DIM + 1) * 8 / mse / 1e6)
+    del Xe, lpe, ge
+    # (c) SURVEY 8f rank 1: DES-Y1-shaped surrogate -> Gaussian-likelihood pipeline (n = 26, m = 457 block-quadratic outputs,
+    # dense inverse covariance) on the tensor cores: batched logp + gradient (bfb_lik_dmma.cu) and NUTS (model variant bit 3)
+    try:
+        from bayesfast_b200 import _cabi
+        from bayesfast_b200.density import whiten_spec
+        pspec, plik = synthetic.des_pipeline(N_DIM, 457, seed=0)
+        hp = _cabi.Handle(dev)
+        hp.set_model(whiten_spec(pspec, plik))
+        Cp = 1 << 16
+        Xp = (torch.randn(Cp, N_DIM, dtype=torch.float64, device='cuda:%d' % dev) * 0.3).contiguous()
+        lpp = torch.empty(Cp, dtype=torch.float64, device='cuda:%d' % dev)
+        gp = torch.empty(Cp, N_DIM, dtype=torch.float64, device='cuda:%d' % dev)
+        torch.cuda.synchronize(dev)
+        msp = []
+        for i in range(5):
+            hp.logp_and_grad_batch_dev(Xp.data_ptr(), Cp, lpp.data_ptr(), gp.data_ptr())
+            msp.append(hp.last_kernel_ms())
+        msp = float(np.mean(msp[1:]))
+        fl = 457 * (2 * N_DIM * N_DIM + 5 * N_DIM) + 9 * N_DIM
+        x0p = np.random.default_rng(1).normal(size=(C, N_DIM)) * 0.2
+        cfgp = bfb.NTrace(n_chain=C, n_iter=200, n_warmup=100, x_0=x0p, random_generator=SEED)._cfg_dict(SEED, 0)
+        hp.sampler_init(cfgp, x0p, 1. / N_DIM**0.25, np.ones(N_DIM), x0p)
+        rp = hp.sampler_run('NUTS', 200, out_ptrs={})
+        msn = hp.last_kernel_ms()
+        extras['pipeline_kernel'] = dict(
+            workload='des_y1_shaped_pipeline_n26_m457_gaussian_likelihood', algorithmic_flops_per_evaluation=fl,
+            eval=dict(kernel='lik_eval_dmma_kernel' if hp.eval_last_path() == 'lik_dmma' else hp.eval_last_path(), points=Cp, ms=msp,
+                      points_per_s=Cp / msp * 1e3, roofline=dict(bound='tensor', achieved=fl * Cp / msp / 1e9, peak=peak,
+                                                                 unit='TFLOP/s', frac=fl * Cp / msp / 1e9 / peak)),
+            nuts=dict(kernel='nuts_%s_kernel' % hp.sampler_last_path(), chains_per_gpu=C, iterations=200, kernel_ms=msn,
+                      value=rp['total_tree_size'] / msn * 1e3, unit='leapfrog-steps*chains/s',
+                      roofline_frac=fl * rp['total_tree_size'] / msn / 1e9 / peak))
+        hp.close()
+        del Xp, lpp, gp
+    except Exception as exc:                                   # supplementary measurement: never fails the bench line
+        extras['pipeline_kernel'] = dict(error=repr(exc))
+
+    # (d) the four-warp team kernels (bfb_sampler_team.cu) on the headline run, kernel only: NUTS team is the alternative family
+    # (the one-warp-per-group kernel is the default: see DESIGN.md 4.1), HMC team is the default up to 4 groups per SM
+    try:
+        os.environ['BFB200_SAMPLER'] = 'team'
+        cfgt = bfb.NTrace(**trace_kw)._cfg_dict(SEED, 0)
+        h.sampler_init(cfgt, x0, 1. / N_DIM**0.25, np.ones(N_DIM), x0)
+        best = None
+        for i in range(2):
+            h.sampler_reset()
+            flush.zero_()
+            torch.cuda.synchronize(dev)
+            rt = h.sampler_run('NUTS', N_ITER, out_ptrs={})
+            mst = h.last_kernel_ms()
+            if best is None or mst < best[1]:
+                best = (rt['total_tree_size'], mst)
+        extras['team_kernel'] = dict(kernel='nuts_%s_kernel' % h.sampler_last_path(), chains_per_gpu=C, value=best[0] / best[1] * 1e3,
+                                     unit='leapfrog-steps*chains/s', kernel_ms=best[1],
+                                     roofline_frac=FLOPS_PER_LEAF * best[0] / (best[1] * 1e-3) / 1e12 / peak)
+    except Exception as exc:
+        extras['team_kernel'] = dict(error=repr(exc))
+    finally:
+        os.environ.pop('BFB200_SAMPLER', None)
+    # (e) BASELINE configs[3]: 64-D cubic-3 stack (P = 47905), NUTS with per-chain divergent tree depths
+    try:
+        spec3, cov3 = synthetic.cubic3_stack(64, seed=3)
+        h3 = _cabi.Handle(dev)
+        h3.set_model(spec3)
+        C3 = 1024
+        x03 = (np.linalg.cholesky(cov3) @ np.random.default_rng(0).normal(size=(64, C3))).T
+        cfg3 = bfb.NTrace(n_chain=C3, n_iter=300, n_warmup=100, x_0=x03, random_generator=SEED)._cfg_dict(SEED, 0)
+        h3.sampler_init(cfg3, x03, 1. / 64**0.25, np.ones(64), x03)
+        h3.sampler_run('NUTS', 100, out_ptrs={})
+        r3 = h3.sampler_run('NUTS', 60, fields=('tree_depth',))
+        ms3 = h3.last_kernel_ms()
+        fl3 = 8 * 64 * 64 + 24 * 64 + 1.5 * 64 * 63 * 62
+        hist = np.bincount(r3['tree_depth'].ravel(), minlength=11)
+        size = 2.**np.arange(len(hist))                      # leaves of a full tree of that depth
+        extras['config3'] = dict(workload='64-D cubic-3 stack (P=47905), injected coefficients, 1024 chains', kernel='nuts_%s_kernel' % h3.sampler_last_path(),
+                                 iterations=60, kernel_ms=ms3, value=r3['total_tree_size'] / ms3 * 1e3, unit='leapfrog-steps*chains/s',
+                                 algorithmic_flops_per_leapfrog=fl3, roofline_frac=fl3 * r3['total_tree_size'] / (ms3 * 1e-3) / 1e12 / peak,
+                                 tree_depth_histogram=hist.tolist(), mean_tree_depth=float(r3['tree_depth'].mean()),
+                                 lockstep_efficiency=float((hist * size).sum() / (hist.sum() * size[np.nonzero(hist)[0].max()])),
+                                 note='lockstep_efficiency: mean tree size over the size of the deepest tree = the row utilisation a kernel '
+                                      'keeping all chains in lock step per iteration would have; the kernels here let every chain run on')
+        h3.close()
+    except Exception as exc:
+        extras['config3'] = dict(error=repr(exc))
+    # (f) e2e variants through the public API (one timed call each after a warm call)
+    try:
+        ev = {}
+        for name, kw in (('all_records', dict(keep='all')), ('post_warmup_thin10_summaries', dict(keep='post_warmup', thin=10, summaries=True))):
+            tt = None
+            for i in range(2):
+                del tt                                   # hand the pinned output buffers back to the pool before the next call
+                flush.zero_()
+                torch.cuda.synchronize(dev)
+                t0 = time.perf_counter()
+                tt = bfb.sample(den, dict(trace_kw), verbose=False, **kw)
+                torch.cuda.synchronize(dev)
+                dt = time.perf_counter() - t0
+            ev[name] = dict(value=tt.total_tree_size / dt, ms_per_step=dt * 1e3, kernel_ms=tt.kernel_ms,
+                            d2h_bytes_per_step=int(sum(v.nbytes for k, v in tt.arrays.items() if k not in ('samples_original', 'logp_original'))))
+            del tt
+        extras['e2e_variants'] = ev
+    except Exception as exc:
+        extras['e2e_variants'] = dict(error=repr(exc))
+    return extras
+
+
+def fit_sweep(torch, dist, dev, rank, world, peak_dmma=None):
+    """BASELINE configs[4]: cubic-2 fit, d = 32 (P = 1585), N = 1e4 .. 1e7 rows resident on the device(s): Gram kernel time
+    (CUDA events) and algorithmic TFLOP/s = N P (P + 1) / t; with world > 1 the rows are sharded and the packed exchange
+    buffer is all-reduced over NCCL (timed), then every rank solves."""
+    import ctypes as CT
+    import bayesfast_b200 as bfb
+    from bayesfast_b200 import _cabi
+    from bayesfast_b200.fit import _allreduce_buffer
+    n = 32
+    sur = bfb.PolyModel('cubic-2', input_size=n, output_size=1, device=dev)
+    P = sur.n_param
+    h = sur._dev()
+    h.set_model(sur.to_spec(with_bound=False))
+    L = _cabi.lib()
+    peak = peak_dmma or h.fp64_peak(1)
+    d = torch.device('cuda', dev)
+    rows = []
+    for N in (10**4, 10**5, 10**6, 10**7):
+        Nl = N // world
+        g = torch.Generator(device=d).manual_seed(1000 + rank)
+        x = torch.randn(Nl, n, dtype=torch.float64, device=d, generator=g)
+        coef = torch.randn(n, dtype=torch.float64, device=d, generator=torch.Generator(device=d).manual_seed(7))
+        y = (-0.5 * (x * x).sum(1) + x @ coef + 0.05 * (x ** 3).sum(1)
+             + 1e-3 * torch.randn(Nl, dtype=torch.float64, device=d, generator=g))[:, None].contiguous()
+        torch.cuda.synchronize(d)
+        best, ex = 1e30, {}
+        for rep in range(3 if N < 10**7 else 2):
+            _cabi.check(L.bfb_fit_begin(h._h, None))
+            _cabi.check(L.bfb_fit_accumulate(h._h, x.data_ptr(), y.data_ptr(), None, Nl, _cabi.BFB_DEVICE))
+            best = min(best, h.last_kernel_ms())
+            if world > 1:
+                dist.barrier()
+                st = {}
+                _allreduce_buffer(h, None, st)
+                if not ex or st['allreduce_s'] < ex['allreduce_s']:
+                    ex = st
+        t0 = time.time()
+        out = np.empty(P)
+        rr = CT.c_double(0)
+        _cabi.check(L.bfb_fit_solve(h._h, out.ctypes.data_as(_cabi._dp), CT.byref(rr)))
+        solve_s = time.time() - t0
+        if world > 1:
+            t = torch.tensor([best], dtype=torch.float64, device=d)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            best = float(t[0])
+        flops = float(Nl * world) * P * (P + 1) + 2. * Nl * world * P
+        row = dict(N=Nl * world, rows_per_gpu=Nl, P=P, gram_ms=best, tflops_all_gpus=flops / (best * 1e-3) / 1e12,
+                   frac_of_fp64_peak=flops / (best * 1e-3) / 1e12 / (peak * world), solve_s=solve_s, rel_resid=rr.value)
+        if ex:
+            row.update(allreduce_ms=ex['allreduce_s'] * 1e3, allreduce_bytes=ex['allreduce_bytes'],
+                       allreduce_gbs=ex['allreduce_bytes'] / ex['allreduce_s'] / 1e9)
+        rows.append(row)
+        del x, y
+    return dict(workload='PolyModel cubic-2 fit sweep, d=32, P=1585, rows resident on the device(s)', n_gpus=world, fp64_peak_tflops_per_gpu=peak,
+                rows=rows)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -137,12 +385,23 @@ def main():
     if args.impl == 'reference':
         if rank != 0:
             return
-        spec = oracle_spec_cpu(prob)
-        vals = []
-        for s in range(args.warmup + args.steps):
-            cb, leaves, dt = run_cpu_baseline(spec, prob, budget_s=min(args.cpu_budget, 10.))
-            if s >= args.warmup:
-                vals.append((leaves, dt))
+        cores = cpu_cores()
+        vals, cb = [], None
+        for s_ in range(args.warmup + args.steps):
+            cb = run_reference_python(prob, cores, per=1)
+            if cb is None or 'error' in cb:
+                break
+            if s_ >= args.warmup:
+                vals.append((cb['leaves'], cb['seconds']))
+        if cb is None or 'error' in cb:             # not installed on this box: the C port of the same path
+            why = 'baseline/_ref missing' if cb is None else cb['error']
+            spec = oracle_spec_cpu(prob)
+            vals = []
+            for s_ in range(args.warmup + args.steps):
+                cb, leaves, dt = run_cpu_baseline(spec, prob, budget_s=min(args.cpu_budget, 10.))
+                if s_ >= args.warmup:
+                    vals.append((leaves, dt))
+            cb['fallback'] = why
         leaves = sum(v[0] for v in vals)
         dt = sum(v[1] for v in vals)
         cb['value'] = leaves / dt
@@ -244,7 +503,7 @@ def main():
         flush.zero_()
         barrier()
         t0 = time.perf_counter()
-        tt = bfb.sample(den, dict(trace_kw), verbose=False)
+        tt = bfb.sample(den, dict(trace_kw), verbose=False, keep='post_warmup')
         barrier()
         if i > 0:
             e2e_ms += (time.perf_counter() - t0) * 1e3
@@ -264,6 +523,12 @@ def main():
         e2e_leaves = int(t[0])
     e2e_value = e2e_leaves / (e2e_ms * 1e-3)
 
+    fsweep = None
+    if not args.no_extras:
+        try:
+            fsweep = fit_sweep(torch, dist, dev, rank, world)        # all ranks: rows sharded, the exchange buffer all-reduced over NCCL
+        except Exception as exc:
+            fsweep = dict(error=repr(exc))
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -290,106 +555,32 @@ def main():
                     hbm=dict(algorithmic_bytes_per_launch=hbm_bytes, achieved_gbs=hbm_bytes / (k_ms * 1e-3) / 1e9,
                              peak_gbs=peaks.get('hbm_gbs'), note='outputs only; the tree state stays in shared memory'))
     extras = {}
-    if not args.no_extras:
-        # (a) the same run with 16384 chains on this GPU (two warps per scheduler instead of one): kernel-only value
-        C2 = 16384
-        prob2 = synthetic.des_shaped(N_DIM, seed=1, n_chain=C2, order=ORDER)
-        cfg2 = bfb.NTrace(n_chain=C2, n_iter=N_ITER, n_warmup=N_WARMUP, x_0=prob2['x_0'], random_generator=SEED)._cfg_dict(SEED, 0)
-        h.sampler_init(cfg2, prob2['x_0'], 1. / N_DIM**0.25, np.ones(N_DIM), prob2['x_0'])
-        best = None
-        for i in range(3):
-            h.sampler_reset()
-            flush.zero_()
-            torch.cuda.synchronize(dev)
-            r2 = h.sampler_run('NUTS', N_ITER, out_ptrs={})
-            ms2 = h.last_kernel_ms()
-            if i > 0 and (best is None or ms2 < best[1]):
-                best = (r2['total_tree_size'], ms2)
-        tf2 = FLOPS_PER_LEAF * best[0] / (best[1] * 1e-3) / 1e12
-        extras['more_chains'] = dict(chains_per_gpu=C2, value=best[0] / (best[1] * 1e-3), unit='leapfrog-steps*chains/s',
-                                     kernel_ms=best[1], outputs='none written (kernel only)', kernel=h.sampler_last_path(),
-                                     roofline_frac=tf2 / peak, achieved_tflops=tf2)
-        # (a2) lock-step HMC (hmc.py:16-49, n_int_step = 32) on the same chains: the tensor-core integrator without the NUTS
-        # tree bookkeeping (hmc_dmma_kernel), kernel only
-        hm = {}
-        for Ch, x0h in ((C, x0), (C2, prob2['x_0'])):
-            cfgh = bfb.HTrace(n_chain=Ch, n_iter=300, n_warmup=100, x_0=x0h, n_int_step=32, random_generator=SEED)._cfg_dict(SEED, 0)
-            h.sampler_init(cfgh, x0h, 1. / N_DIM**0.25, np.ones(N_DIM), x0h)
-            h.sampler_run('HMC', 100, out_ptrs={})                         # step-size adaptation
-            rh = h.sampler_run('HMC', 100, out_ptrs={})
-            msh = h.last_kernel_ms()
-            tfh = FLOPS_PER_LEAF * rh['total_tree_size'] / (msh * 1e-3) / 1e12
-            hm[str(Ch)] = dict(chains_per_gpu=Ch, value=rh['total_tree_size'] / (msh * 1e-3), unit='leapfrog-steps*chains/s',
-                               kernel_ms=msh, roofline_frac=tfh / peak, achieved_tflops=tfh)
-        extras['hmc_kernel'] = dict(kernel='hmc_dmma_kernel', n_int_step=32, iterations=100, outputs='none written (kernel only)', runs=hm)
-        # (b) the surrogate evaluation kernel alone: logp + gradient of 2^22 device-resident points
-        Ce = 1 << 22
-        Xe = torch.randn(Ce, N_DIM, dtype=torch.float64, device='cuda:%d' % dev) @ torch.tensor(np.linalg.cholesky(prob['cov']).T, device='cuda:%d' % dev)
-        Xe = Xe.contiguous()
-        lpe = torch.empty(Ce, dtype=torch.float64, device='cuda:%d' % dev)
-        ge = torch.empty(Ce, N_DIM, dtype=torch.float64, device='cuda:%d' % dev)
-        torch.cuda.synchronize(dev)
-        mse = []
-        for i in range(6):
-            h.logp_and_grad_batch_dev(Xe.data_ptr(), Ce, lpe.data_ptr(), ge.data_ptr())
-            mse.append(h.last_kernel_ms())
-        mse = float(np.mean(mse[1:]))
-        fe = (8 * N_DIM * N_DIM + 15 * N_DIM) * Ce
-        extras['eval_kernel'] = dict(kernel='eval_dmma_kernel', points=Ce, ms=mse, points_per_s=Ce / mse * 1e3,
-                                     algorithmic_flops_per_point=8 * N_DIM * N_DIM + 15 * N_DIM,
-                                     roofline=dict(bound='tensor', achieved=fe / mse / 1e9, peak=peak, unit='TFLOP/s', frac=fe / mse / 1e9 / peak),
-                                     hbm_gbs=Ce * (2 * N_DIM + 1) * 8 / mse / 1e6)
-        del Xe, lpe, ge
-        # (c) SURVEY 8f rank 1: DES-Y1-shaped surrogate -> Gaussian-likelihood pipeline (n = 26, m = 457 block-quadratic outputs,
-        # dense inverse covariance) on the tensor cores: batched logp + gradient (bfb_lik_dmma.cu) and NUTS (model variant bit 3)
-        try:
-            from bayesfast_b200 import _cabi
-            from bayesfast_b200.density import whiten_spec
-            pspec, plik = synthetic.des_pipeline(N_DIM, 457, seed=0)
-            hp = _cabi.Handle(dev)
-            hp.set_model(whiten_spec(pspec, plik))
-            Cp = 1 << 16
-            Xp = (torch.randn(Cp, N_DIM, dtype=torch.float64, device='cuda:%d' % dev) * 0.3).contiguous()
-            lpp = torch.empty(Cp, dtype=torch.float64, device='cuda:%d' % dev)
-            gp = torch.empty(Cp, N_DIM, dtype=torch.float64, device='cuda:%d' % dev)
-            torch.cuda.synchronize(dev)
-            msp = []
-            for i in range(5):
-                hp.logp_and_grad_batch_dev(Xp.data_ptr(), Cp, lpp.data_ptr(), gp.data_ptr())
-                msp.append(hp.last_kernel_ms())
-            msp = float(np.mean(msp[1:]))
-            fl = 457 * (2 * N_DIM * N_DIM + 5 * N_DIM) + 9 * N_DIM
-            x0p = np.random.default_rng(1).normal(size=(C, N_DIM)) * 0.2
-            cfgp = bfb.NTrace(n_chain=C, n_iter=200, n_warmup=100, x_0=x0p, random_generator=SEED)._cfg_dict(SEED, 0)
-            hp.sampler_init(cfgp, x0p, 1. / N_DIM**0.25, np.ones(N_DIM), x0p)
-            rp = hp.sampler_run('NUTS', 200, out_ptrs={})
-            msn = hp.last_kernel_ms()
-            extras['pipeline_kernel'] = dict(
-                workload='des_y1_shaped_pipeline_n26_m457_gaussian_likelihood', algorithmic_flops_per_evaluation=fl,
-                eval=dict(kernel='lik_eval_dmma_kernel' if hp.eval_last_path() == 'lik_dmma' else hp.eval_last_path(), points=Cp, ms=msp,
-                          points_per_s=Cp / msp * 1e3, roofline=dict(bound='tensor', achieved=fl * Cp / msp / 1e9, peak=peak,
-                                                                     unit='TFLOP/s', frac=fl * Cp / msp / 1e9 / peak)),
-                nuts=dict(kernel='nuts_%s_kernel' % hp.sampler_last_path(), chains_per_gpu=C, iterations=200, kernel_ms=msn,
-                          value=rp['total_tree_size'] / msn * 1e3, unit='leapfrog-steps*chains/s',
-                          roofline_frac=fl * rp['total_tree_size'] / msn / 1e9 / peak))
-            hp.close()
-            del Xp, lpp, gp
-        except Exception as exc:                                   # supplementary measurement: never fails the bench line
-            extras['pipeline_kernel'] = dict(error=repr(exc))
+    if fsweep is not None:
+        extras['fit_sweep'] = fsweep
+    if not args.no_extras and world == 1:
+        extras.update(extra_measurements(args, bfb, torch, den, h, prob, x0, trace_kw, flush, peak, dev, C))
     out = dict(metric='nuts_leapfrog_steps_x_chains_per_s', value=value, unit='leapfrog-steps*chains/s', n_gpus=world,
                steps=args.steps, warmup=args.warmup, ms_per_step=step_ms / args.steps, higher_is_better=True,
                scaling='weak', vs_baseline=None, dtype='f64', data='synthetic', config=config,
                e2e=dict(value=e2e_value, unit='leapfrog-steps*chains/s', h2d_bytes_per_step=int(h2d),
                         d2h_bytes_per_step=int(d2h), ms_per_step=e2e_ms / n_e2e, kernel_ms_per_step=e2e_kernel_ms / n_e2e,
+                        api="bayesfast_b200.sample(density, trace, keep='post_warmup'): samples + 10 statistics of the {} post-warm-up "
+                            "iterations of every chain to pinned host memory".format(N_ITER - N_WARMUP),
                         numa_cpus_rank0=(len(numa_cpus) if numa_cpus else None)),
                gpu_launches=int(launches_all), roofline=roofline, clocks=summarize_clocks(samples),
                fit=dict(seconds=fit_s, seconds_warm=fit_warm_s, kernel_ms=getattr(sur, '_fit_kernel_ms', None), n=N_DIM,
                         P=config['n_param'], N=config['n_fit'], rel_resid=getattr(sur, '_fit_rel_resid', None)),
                mean_tree_size=leaves / args.steps / (C * N_ITER), kernel='nuts_%s_kernel' % kernel_family, **extras)
     if world == 1 and not args.no_cpu_baseline:
-        spec = den.to_spec()
-        out['cpu_baseline'] = run_cpu_baseline(spec, prob, budget_s=args.cpu_budget)[0]
-        out['cpu_baseline']['gpu_over_cpu_e2e'] = e2e_value / out['cpu_baseline']['value']
+        cores = cpu_cores()
+        port = run_cpu_baseline(den.to_spec(), prob, budget_s=args.cpu_budget)[0]
+        ref = run_reference_python(prob, cores, per=2)
+        if ref is not None and 'error' not in ref:
+            out['cpu_baseline'] = dict(ref, port=port)
+        else:
+            out['cpu_baseline'] = dict(port, reference=ref)
+        out['cpu_baseline']['note'] = ('absolute rates with their core counts; the GPU/CPU ratio depends on how many cores the box has '
+                                       '(round 1: 16 and 32 cores gave ratios 82 and 45 for the same GPU number)')
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -99,6 +99,11 @@ int bfb_eval_last_path(bfb_handle h);
  * Density-level calls (bfb_logp_and_grad_batch, the samplers) then evaluate the pipeline; bfb_poly_eval_batch still
  * returns the (whitened) outputs.  bfb_set_model / bfb_fit_solve reset it. */
 int bfb_set_epilogue(bfb_handle h, int kind, double c0);
+/* Third module of the DES-Y1 example's pipeline (examples/des-y1-w-cosmosis.ipynb cells 12-14, des_post_f / des_post_fj:
+ * logp = like + prior(x), a user Module with inputs ['like', 'x'] in the reference): independent Gaussian prior on the
+ * ORIGINAL-space inputs, logp += c0 - 1/2 sum_j w[j] (x_j - mu[j])^2, w [n] = 1 / sigma^2 (0: no prior on that input),
+ * mu [n]; host pointers; w == NULL removes it.  After bfb_set_model, before bfb_set_epilogue. */
+int bfb_set_prior(bfb_handle h, const double *w, const double *mu, double c0);
 
 /* ------------------------------------------------------------------------------------------------
  * Fit: replaces PolyModel.fit (poly.py:505-589): the design-matrix builders _lsq_* (_poly.pyx:143-177),

@@ -384,6 +384,17 @@ void bfo_logp_and_grad(const bfo_density *den, const double *x, double *logp, do
         free(r); free(w);
     } else
     for (int k = 0; k < n; ++k) grad[k] = jac[k] * tj[k];         /* density.py:558 np.dot(J, diag) */
+    if (den->use_prior) {
+        /* third module of the pipeline (inputs ['like', 'x']): logp = like + prior(x), Jacobian [1 | d prior / dx] chained
+         * with the variable transform like every other module input (density.py:533-565) */
+        double s = 0.;
+        for (int k = 0; k < n; ++k) {
+            const double dk = xo[k] - den->p_mu[k];
+            s += den->p_w[k] * dk * dk;
+            grad[k] -= den->p_w[k] * dk * tj[k];
+        }
+        lp += den->p_c0 - 0.5 * s;
+    }
     if (den->use_decay) {                                         /* density.py:740-746 */
         double *d = (double *)malloc(sizeof(double) * (size_t)n);
         double beta2 = mahalanobis(xo, den->d_mu, den->d_hess, n, d);

@@ -52,7 +52,7 @@ class _Density(C.Structure):
     _fields_ = [('model', C.POINTER(_PolyModel)), ('use_decay', C.c_int32), ('d_mu', _dp), ('d_hess', _dp),
                 ('d_alpha2', C.c_double), ('d_gamma', C.c_double), ('use_transform', C.c_int32),
                 ('ranges', _dp), ('hard_bounds', _bp), ('use_epilogue', C.c_int32), ('e_d', _dp), ('e_cinv', _dp),
-                ('e_c0', C.c_double)]
+                ('e_c0', C.c_double), ('use_prior', C.c_int32), ('p_w', _dp), ('p_mu', _dp), ('p_c0', C.c_double)]
 
 
 class _Cfg(C.Structure):
@@ -170,6 +170,16 @@ class OracleDensity:
         dn.e_c0 = float(ep.get('c0', 0.)) if ep is not None else 0.
         self._keep += [e_d, e_ci]
         dn.e_d, dn.e_cinv = _d(e_d), _d(e_ci)
+        pr = spec.get('prior', None)          # dict(idx, mu, sig, c0): independent Gaussian prior on some original-space inputs
+        dn.use_prior = int(pr is not None)
+        p_w, p_mu = np.zeros(n), np.zeros(n)
+        if pr is not None:
+            idx = np.asarray(pr['idx'], dtype=np.int64)
+            p_w[idx] = 1. / np.asarray(pr['sig'], dtype=np.float64)**2
+            p_mu[idx] = np.asarray(pr['mu'], dtype=np.float64)
+            dn.p_c0 = float(pr.get('c0', 0.))
+        self._keep += [p_w, p_mu]
+        dn.p_w, dn.p_mu = _d(p_w), _d(p_mu)
         self._dn = dn
 
     # PolyModel.fun_and_jac for a batch of points (module rescale included, no Density wrapper)

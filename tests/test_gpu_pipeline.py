@@ -168,19 +168,23 @@ def test_likelihood_tensor_core_evaluator(handle, oracle, monkeypatch, n, m, C):
     assert np.array_equal(lp2, lp) and np.array_equal(g2, g)
 
 
-def test_likelihood_with_bound_takes_generic_kernel(handle, oracle):
-    """a radial bound (poly.py:466-503) applies to every output: such a model stays on the generic evaluator and still matches"""
+def test_likelihood_with_bound_on_both_evaluators(handle, oracle, monkeypatch):
+    """a radial bound (poly.py:466-503) applies to every output: the tensor-core evaluator (bound term applied once to the
+    accumulated gradient, bfb_dmma.cuh lik_post) and the generic one both match the oracle"""
     from bayesfast_b200.density import whiten_spec, GaussianLikelihood
     rng = np.random.default_rng(4)
     spec = _lik_spec(rng, 8, 12, with_bound=True)
     ep = spec['epilogue']
     handle.set_model(whiten_spec(to_device_spec(spec), GaussianLikelihood(ep['d'], ep['cinv'], ep['c0'])))
     X = rng.normal(size=(40, 8)) * 0.9              # radius 1.5: a good part of the points is outside
-    lp, g = handle.logp_and_grad_batch(X)
-    assert handle.eval_last_path() == 'generic'
     lpo, go = oracle.OracleDensity(spec).logp_and_grad_batch(X)
     assert np.sum(np.linalg.norm(X, axis=1) > 1.5) > 5
-    assert np.allclose(lp, lpo, rtol=1e-10, atol=1e-10) and np.allclose(g, go, rtol=1e-10, atol=1e-10 * np.abs(go).max())
+    for path in ('lik_dmma', 'generic'):
+        if path == 'generic':
+            monkeypatch.setenv('BFB200_EVAL', 'generic')
+        lp, g = handle.logp_and_grad_batch(X)
+        assert handle.eval_last_path() == path
+        assert np.allclose(lp, lpo, rtol=1e-10, atol=1e-10) and np.allclose(g, go, rtol=1e-10, atol=1e-10 * np.abs(go).max())
 
 
 @pytest.mark.parametrize('n,m,C,sampler', [(26, 30, 40, 'NUTS'), (12, 17, 21, 'NUTS'), (16, 9, 16, 'HMC')])
@@ -213,3 +217,82 @@ def test_likelihood_tensor_core_samplers(handle, oracle, monkeypatch, n, m, C, s
         for k in INT_STATS:
             assert np.array_equal(outs[fam][k], ref[k]), (fam, k)
         check_floats(outs[fam]['samples'], ref['samples'], fam)
+
+
+DES = gio.load('pipeline_des.npz')['cases'][0]
+
+
+@pytest.mark.parametrize('path', ['tensor', 'generic'])
+def test_pipeline_des_shaped_golden(handle, monkeypatch, path):
+    """The DES-Y1 example's three-module density (examples/des-y1-w-cosmosis.ipynb cells 12-18: linear + shared-mask quadratic
+    surrogate with module input_scales -> chi2 -> posterior module with a Gaussian prior on 13 inputs; Density input_scales,
+    hard_bounds=True, radial bound) against the real reference: logp_and_grad at 1e-10 (6 of the 14 points lie outside the
+    bound) and a NUTS run with identical integer outcomes -- on the tensor-core kernels (model variant bits 3 | 1) and on the
+    generic ones."""
+    if path == 'generic':
+        monkeypatch.setenv('BFB200_EVAL', 'generic')
+        monkeypatch.setenv('BFB200_SAMPLER', 'generic')
+    case = DES
+    handle.set_model(_whitened(case))
+    lp, g = handle.logp_and_grad_batch(case['X'])
+    assert handle.eval_last_path() == ('lik_dmma' if path == 'tensor' else 'generic')
+    assert np.allclose(lp, case['logp'], rtol=1e-10, atol=1e-10)
+    assert np.allclose(g, case['grad'], rtol=1e-10, atol=1e-10 * np.abs(case['grad']).max())
+    r, kw = case['result'], case['trace_kw']
+    n_iter, n_warmup = int(kw['n_iter']), int(kw['n_warmup'])
+    handle.sampler_init(cfg_from(kw, n_warmup, int(case['seed'])), case['x0'], float(r['step0']), r['var0'], case['x0'])
+    out = handle.sampler_run('NUTS', n_iter)
+    assert handle.sampler_last_path() == ('dmma' if path == 'tensor' else 'generic')
+    st = handle.sampler_state()
+    assert np.all(st['status'] == 0) and np.array_equal(st['n_draws'], r['n_draws'])
+    for k in INT_STATS:
+        assert np.array_equal(out[k], r[k].astype(np.int32)), k
+    assert int(out['diverging'].sum()) == int(r['diverging'].sum()) >= 1
+    for k in FLT_STATS:
+        assert np.allclose(out[k][:, :4], r[k][:, :4], rtol=1e-9, atol=1e-9), k
+    assert np.allclose(out['samples'][:, :4], r['samples'][:, :4], rtol=1e-9, atol=1e-9)
+    assert np.allclose(out['samples'], r['samples'], rtol=1e-3, atol=1e-3)
+
+
+def test_des_shaped_public_api_and_large_batch(oracle):
+    """the same density shape through the public interface (PolyModel with a shared-mask quadratic config, GaussianLikelihood,
+    GaussianPrior, input_scales + hard_bounds=True): fit on the device, batched logp_and_grad of 3000 points (ragged) on the
+    tensor-core evaluator against the oracle evaluating the device-fitted coefficients, HMC and NUTS decisions against the
+    oracle fed with the device's draws"""
+    import bayesfast_b200 as bfb
+    sp = DES['spec']
+    n, m = int(sp['n']), int(sp['m'])
+    rng = np.random.default_rng(4)
+    rg = sp['transform_ranges']
+    mid, width = rg.mean(axis=1), rg[:, 1] - rg[:, 0]
+    nl = np.asarray(sp['configs'][1]['input_mask'])
+    W1, W2 = rng.normal(size=(m, n)), rng.normal(size=(m, nl.size, nl.size)) * 0.5
+    sur = bfb.PolyModel([bfb.PolyConfig('linear'), bfb.PolyConfig('quadratic', input_mask=nl)], input_size=n, output_size=m,
+                        input_scales=rg)
+    pr = sp['prior']
+    d_vec = rng.normal(size=m) * 0.1
+    den = bfb.Density(sur, input_scales=rg, hard_bounds=True, likelihood=bfb.GaussianLikelihood(d_vec, np.ones(m), 1.5),
+                      prior=bfb.GaussianPrior(pr['idx'], pr['mu'], pr['sig'], float(pr['c0'])))
+    xf = mid + np.clip(rng.normal(size=(3 * sur.n_param, n)) * 0.08, -0.45, 0.45) * width
+    u = (xf - mid) / width
+    yf = u @ W1.T + np.einsum('ojk,nj,nk->no', W2, u[:, nl], u[:, nl])
+    den.fit(xf, yf)
+    od = oracle.OracleDensity(den.to_spec())
+    Xo = mid + np.clip(rng.normal(size=(3000 - 7, n)) * np.where(np.arange(3000 - 7) % 2, 0.05, 0.15)[:, None], -0.49, 0.49) * width
+    Xt = den.from_original(Xo)
+    lp, g = den.logp_and_grad(Xt, original_space=False)
+    assert den._sync(False).eval_last_path() == 'lik_dmma'
+    lpo, go = od.logp_and_grad_batch(Xt)
+    assert np.allclose(lp, lpo, rtol=1e-10, atol=1e-9) and np.allclose(g, go, rtol=1e-9, atol=1e-10 * np.abs(go).max())
+    beta = np.sqrt(np.einsum('ij,jk,ik->i', (Xo - rg[:, 0]) / width - sur._mu, sur._hess, (Xo - rg[:, 0]) / width - sur._mu))
+    assert 0.05 < np.mean(beta > sur._alpha) < 0.95                   # both sides of the radial bound
+    x0 = den.from_original(xf[:24])
+    for sampler, kw in (('NUTS', {}), ('HMC', dict(n_int_step=6))):
+        tt = bfb.sample(den, dict(n_chain=24, n_iter=30, n_warmup=15, x_0=xf[:24], random_generator=9, **kw),
+                        sampler=sampler, verbose=False)
+        assert den._sync(False).sampler_last_path() == 'dmma'
+        U, Z = device_draws(den._sync(False), 9, tt._final['n_draws'])
+        ref = od.run(sampler, dict(n_iter=30, n_warmup=15, **kw), x0, 1. / n**0.25, np.ones(n), draws_u=U, draws_z=Z)
+        assert np.array_equal(tt._final['n_draws'], ref['n_draws'])
+        assert np.array_equal(tt.arrays['tree_depth'], ref['tree_depth']) and np.array_equal(tt.arrays['diverging'], ref['diverging'])
+        assert np.allclose(tt.samples[:, :4], ref['samples'][:, :4], rtol=1e-8, atol=1e-8)

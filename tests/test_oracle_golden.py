@@ -185,3 +185,25 @@ def test_poly_eval_c3n64(oracle):
     F, J = oracle.OracleDensity(c3n64_spec(g)).poly_eval_batch(g['X'])
     assert np.allclose(F, g['raw_f'], rtol=1e-11, atol=1e-11 * np.abs(g['raw_f']).max())
     assert np.allclose(J, g['raw_j'], rtol=1e-11, atol=1e-11 * np.abs(g['raw_j']).max())
+
+
+def test_pipeline_des_shaped_case(oracle):
+    """the DES-Y1 example's three-module density (examples/des-y1-w-cosmosis.ipynb cells 12-18): surrogate with a linear config
+    and a quadratic config on one shared 9-D mask -> chi2 module -> posterior module adding a Gaussian prior on 13 inputs;
+    module input_scales, Density input_scales with hard_bounds=True on all 27 inputs, radial bound on.  logp_and_grad and a NUTS
+    run (4 divergences) of the real reference."""
+    for c in gio.load('pipeline_des.npz')['cases']:
+        sp = c['spec']
+        assert sp['use_bound'] and sp['transform_ranges'] is not None and sp['prior'] is not None and int(sp['n']) == 27
+        od = oracle.OracleDensity(sp)
+        lp, gr = od.logp_and_grad_batch(c['X'])
+        assert _close(lp, c['logp'], 1e-11), c['name']
+        assert _close(gr, c['grad'], 1e-11), c['name']
+        r = c['result']
+        out = od.run('NUTS', {k: int(v) for k, v in c['trace_kw'].items()}, c['x0'], float(r['step0']), r['var0'],
+                     draws_u=r['draws_u'], draws_z=r['draws_z'])
+        assert np.all(out['status'] == 0) and np.array_equal(out['n_draws'], r['n_draws'])
+        for k in INT_STATS:
+            assert np.array_equal(out[k], r[k].astype(np.int32)), (c['name'], k)
+        assert int(r['diverging'].sum()) >= 1
+        _flt(out['samples'], r['samples'], c['name'], early=4)
