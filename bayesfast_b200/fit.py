@@ -69,7 +69,62 @@ def _handle_for(model):
     return h
 
 
+def _is_cuda(t):
+    return hasattr(t, 'is_cuda') and t.is_cuda
+
+
+def _fit_polymodel_device(model, x, y, logp, w, comm):
+    """PolyModel.fit on DEVICE-RESIDENT rows (CUDA torch tensors, float64): the samples of a run that stayed on the GPU feed the
+    next surrogate fit without a host round trip (Recipe._sam_step, core/recipe.py:1074-1157); only the n-vector shift, the
+    center_max row and the packed coefficients cross PCIe."""
+    import torch
+    n, m = model._input_size, model._output_size
+    if not (x.dim() == 2 and x.shape[1] == n and y.dim() == 2 and y.shape[1] == m and x.shape[0] == y.shape[0]):
+        raise ValueError('x should have shape (N, {}) and y (N, {}).'.format(n, m))
+    x, y = x.contiguous().double(), y.contiguous().double()
+    rank, world, group = dist_info(comm)
+    h = _handle_for(model)
+    if x.device.index != h.device:
+        raise ValueError('the rows live on cuda:{} but the model on cuda:{}.'.format(x.device.index, h.device))
+    n_total = x.shape[0]
+    if world > 1:
+        n_total = int(allreduce_values([n_total], 'sum', group, h.device, 'int64')[0])
+    if n_total < model.n_param:
+        raise ValueError('I need at least {} points, but you only gave me {}.'.format(model.n_param, n_total))
+    wd = None
+    if w is not None:
+        wd = (w if _is_cuda(w) else torch.as_tensor(np.asarray(w, dtype=np.float64), device=x.device)).contiguous().double()
+        if wd.shape != (x.shape[0],):
+            raise ValueError('invalid shape for w.')
+    L = _cabi.lib()
+    x0 = x[0].cpu().numpy() if x.shape[0] else np.zeros(n)
+    shift = _common_shift(x0[None] if x.shape[0] else np.zeros((0, n)), n, rank, world, group, h.device)
+    torch.cuda.current_stream(x.device).synchronize()
+    _cabi.check(L.bfb_fit_begin(h._h, shift.ctypes.data))
+    _cabi.check(L.bfb_fit_accumulate(h._h, x.data_ptr(), y.data_ptr(), None if wd is None else wd.data_ptr(), x.shape[0],
+                                     _cabi.BFB_DEVICE))
+    model._fit_kernel_ms = h.last_kernel_ms()
+    if world > 1:
+        model._fit_exchange = {}
+        _allreduce_buffer(h, group, model._fit_exchange)
+    total = sum(_cabi.n_packed(c.order, c.input_size) * c.output_size for c in model._configs)
+    coef = np.empty(total)
+    rr = C.c_double(0.)
+    _cabi.check(L.bfb_fit_solve(h._h, coef.ctypes.data_as(_cabi._dp), C.byref(rr)))
+    model._fit_rel_resid = float(rr.value)
+    off, packed = 0, []
+    for c in model._configs:
+        k = _cabi.n_packed(c.order, c.input_size)
+        packed.append(coef[off:off + k * c.output_size].reshape(c.output_size, k))
+        off += k * c.output_size
+    model._install(packed)
+    if model._use_bound and not model._all_linear:
+        set_bound(model, x, logp, _handle=h, _have_moments=True, comm=comm)
+
+
 def fit_polymodel(model, x, y, logp=None, w=None, comm=None, refine=1):
+    if _is_cuda(x):
+        return _fit_polymodel_device(model, x, y, logp, w, comm)
     x = np.asarray(x, dtype=np.float64)
     y = np.asarray(y, dtype=np.float64)
     n, m = model._input_size, model._output_size
@@ -141,13 +196,23 @@ def ellipsoid(model, x, alpha_p, _handle=None, _have_moments=False, comm=None):
     hess = np.linalg.inv(cov)                        # n x n host glue, the same LAPACK call as poly.py:268
     alpha = None
     if alpha_p is not None:
-        xc = _cabi.f64(x)
         mb = C.c_double(0.)
         want_all = alpha_p < 100.
-        beta = np.empty(xc.shape[0]) if want_all else None
-        _cabi.check(L.bfb_fit_max_beta(h._h, xc.ctypes.data, xc.shape[0], mu.ctypes.data_as(_cabi._dp),
-                                       hess.ctypes.data_as(_cabi._dp), C.byref(mb),
-                                       None if beta is None else beta.ctypes.data, _cabi.BFB_HOST))
+        if _is_cuda(x):
+            import torch
+            xc = x.contiguous().double()
+            bt = torch.empty(xc.shape[0], dtype=torch.float64, device=xc.device) if want_all else None
+            torch.cuda.current_stream(xc.device).synchronize()
+            _cabi.check(L.bfb_fit_max_beta(h._h, xc.data_ptr(), xc.shape[0], mu.ctypes.data_as(_cabi._dp),
+                                           hess.ctypes.data_as(_cabi._dp), C.byref(mb), None if bt is None else bt.data_ptr(),
+                                           _cabi.BFB_DEVICE))
+            beta = None if bt is None else bt.cpu().numpy()
+        else:
+            xc = _cabi.f64(x)
+            beta = np.empty(xc.shape[0]) if want_all else None
+            _cabi.check(L.bfb_fit_max_beta(h._h, xc.ctypes.data, xc.shape[0], mu.ctypes.data_as(_cabi._dp),
+                                           hess.ctypes.data_as(_cabi._dp), C.byref(mb),
+                                           None if beta is None else beta.ctypes.data, _cabi.BFB_HOST))
         if want_all:
             if world > 1:
                 raise NotImplementedError('alpha_p < 100 (a percentile of the radii) is not supported with sharded '
@@ -164,9 +229,13 @@ def ellipsoid(model, x, alpha_p, _handle=None, _have_moments=False, comm=None):
 def set_bound(model, x, logp=None, _handle=None, _have_moments=False, comm=None):
     """PolyModel._set_bound (poly.py:262-292)"""
     from .poly import warn_center_max
-    x = np.ascontiguousarray(x, dtype=np.float64)
-    if not (x.ndim == 2 and x.shape[-1] == model._input_size):
-        raise ValueError('invalid value for x.')
+    if _is_cuda(x):
+        if not (x.dim() == 2 and x.shape[-1] == model._input_size):
+            raise ValueError('invalid value for x.')
+    else:
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        if not (x.ndim == 2 and x.shape[-1] == model._input_size):
+            raise ValueError('invalid value for x.')
     rank, world, group = dist_info(comm)
     mu, hess, alpha = ellipsoid(model, x, model._alpha_p, _handle, _have_moments, comm)
     model._mu, model._hess = mu, hess
@@ -178,11 +247,17 @@ def set_bound(model, x, logp=None, _handle=None, _have_moments=False, comm=None)
         # rows or with an invalid logp contributes -inf), so the ranks can neither hang nor pick different centres
         best, x_best = -np.inf, np.zeros(model._input_size)
         try:
-            lp = np.asarray(logp, dtype=np.float64)
-            assert lp.ndim == 1 and lp.shape[0] == x.shape[0]
+            if _is_cuda(logp):                              # device-resident logp: only the winning row comes to the host
+                assert logp.dim() == 1 and logp.shape[0] == x.shape[0]
+                lp = logp
+                i = int(lp.argmax()) if x.shape[0] > 0 else 0
+            else:
+                lp = np.asarray(logp, dtype=np.float64)
+                assert lp.ndim == 1 and lp.shape[0] == x.shape[0]
+                i = int(np.argmax(lp)) if x.shape[0] > 0 else 0                      # poly.py:281
             if x.shape[0] > 0:
-                i = int(np.argmax(lp))                      # poly.py:281
-                best, x_best = float(lp[i]), x[i]
+                best = float(lp[i])
+                x_best = x[i].cpu().numpy() if _is_cuda(x) else x[i]
                 if world > 1 and not np.isfinite(best):     # a NaN / inf maximum cannot win the vote over the ranks
                     best = -np.inf
             valid = x.shape[0] > 0 or world > 1

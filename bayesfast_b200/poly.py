@@ -404,6 +404,8 @@ class PolyModel:
         Least-squares fit of all configs (poly.py:505-589).  x (N, n), y (N, m), optional logp (N,) for
         center_max and row weights w (N,).  With `comm` (a torch.distributed process group or True for the
         default group) x/y/w are this rank's rows and the Gram / moment partial sums are all-reduced over NCCL.
+        x / y (/ logp / w) may be CUDA torch tensors: device-resident rows (e.g. samples that never left the GPU) are
+        accumulated where they are, only the coefficients come back.
         """
         from .fit import fit_polymodel
         fit_polymodel(self, x, y, logp, w, comm=comm, refine=refine)

@@ -204,6 +204,17 @@ int bfb_host_free(void *ptr);
  * 3 nan in logbern); q [C,n] current position.  Host pointers, any may be NULL. */
 int bfb_sampler_get_state(bfb_handle h, double *final_step, double *final_var, int64_t *n_draws,
                           int32_t *status, double *q);
+/* The steps on either side of the sampler inside Recipe._sam_step / _pos_step on device-resident (loc == BFB_DEVICE) or host
+ * arrays:
+ * bfb_importance_weights -- PostStep, core/recipe.py:1286-1297: weights [N] = exp(logp - logq), weights_trunc [N] =
+ *   clip(weights, 0, mean(weights) * N^k_trunc) (k_trunc < 0: no truncation); either output may be NULL; stats [5] (host, may be
+ *   NULL) = sum weights | cap | sum weights_trunc | sum weights_trunc^2 | max weights_trunc.
+ * bfb_argsort_gather -- SystematicResampler.run, utils/misc.py:62-108: out[i] = argsort(a)[pos[i]] for the n systematic positions
+ *   pos (which the host mirror computes exactly like the reference's np.linspace(...).astype(int)); ties are ordered by index,
+ *   NaN sorts last; N < 2^31. */
+int bfb_importance_weights(bfb_handle h, const double *logp, const double *logq, int64_t N, double k_trunc,
+                           double *weights, double *weights_trunc, double *stats, int loc);
+int bfb_argsort_gather(bfb_handle h, const double *a, int64_t N, const int64_t *pos, int64_t n, int64_t *out, int loc);
 /* device time of the last bfb_sampler_run / bfb_fit_accumulate / bfb_poly_eval_batch kernel(s), CUDA events
  * on the handle's stream, milliseconds */
 int bfb_last_kernel_ms(bfb_handle h, float *ms);

@@ -368,3 +368,32 @@ def bound_from_points(x, alpha_p=100.):
     else:
         alpha = np.max(beta) * alpha_p / 100.
     return mu, hess, float(alpha)
+
+
+# ---------------------------------------------------------------------------------------------
+# The steps on either side of the sampler in Recipe, numpy restatements
+# ---------------------------------------------------------------------------------------------
+def systematic_resample(a, n, nodes=(1., 100.), weights=None):
+    """SystematicResampler.run, bayesfast/utils/misc.py:62-108 (the uniqueness check is the caller's)"""
+    nodes = np.asarray(nodes, dtype=np.float64)
+    n_node = nodes.size
+    w = np.ones(n_node - 1) / (n_node - 1) if weights is None else np.asarray(weights, dtype=np.float64) / np.sum(weights)
+    a = np.asarray(a, dtype=np.float64)
+    n_w = (n * w).astype(np.int64)
+    n_w[-1] += n - np.sum(n_w)
+    n_c = np.cumsum(np.insert(n_w, 0, 0))
+    i_all = np.empty(n, dtype=np.int64)
+    m = len(a)
+    for j in range(n_node - 1):
+        ep = (j == n_node - 2)
+        i_j = np.linspace(nodes[j] * (m - 1) / 100, nodes[j + 1] * (m - 1) / 100, n_w[j], ep)
+        i_all[n_c[j]:n_c[j + 1]] = i_j.astype(np.int64)
+    return np.argsort(a, kind='stable')[i_all], i_all
+
+
+def importance_weights(logp, logq, k_trunc):
+    """PostStep, bayesfast/core/recipe.py:1286-1297"""
+    weights = np.exp(np.asarray(logp) - np.asarray(logq))
+    if k_trunc < 0:
+        return weights, weights.copy()
+    return weights, np.clip(weights, 0, np.mean(weights) * weights.size**k_trunc)

@@ -644,6 +644,22 @@ def make_pipeline_des():
                                                   x0=x0, seed=2404, trace_kw=dict(n_iter=40, n_warmup=20), result=r)]))
 
 
+def make_post():
+    """SystematicResampler.run of the real reference (utils/misc.py:21-110) on seeded arrays, and PostStep's weight lines"""
+    from bayesfast.utils.misc import SystematicResampler
+    rng = np.random.default_rng(404)
+    cases = []
+    for name, m, n, nodes, weights in (('default', 5000, 400, (1., 100.), None), ('three_nodes', 20000, 1500, (0., 50., 100.), (1., 3.)),
+                                       ('small', 97, 31, (1., 100.), None), ('ragged', 30011, 4216, (1., 99.5, 100.), (40., 1.))):
+        a = rng.normal(size=m) * 3. - 10.
+        i = SystematicResampler(nodes=nodes, weights=weights).run(a, n)
+        cases.append(dict(name=name, a=a, n=n, nodes=np.asarray(nodes), weights=weights, idx=np.asarray(i, np.int64)))
+    logp, logq = rng.normal(size=2000) - 5., rng.normal(size=2000) * 0.9 - 5.
+    weights = np.exp(logp - logq)
+    wt = np.clip(weights, 0, np.mean(weights) * 2000**0.25)                 # recipe.py:1291-1297 with n_is = 2000, k_trunc = 0.25
+    gio.save('post.npz', dict(cases=cases, logp=logp, logq=logq, k_trunc=0.25, weights=weights, weights_trunc=wt))
+
+
 if __name__ == '__main__':
     which = sys.argv[1:] or ['poly_kat', 'poly_eval', 'density', 'fit', 'sampler', 'sampler_dense', 'pipeline']
     if 'poly_kat' in which:
@@ -662,6 +678,8 @@ if __name__ == '__main__':
         make_poly_eval_c3n64()
     if 'pipeline_des' in which:
         make_pipeline_des()
+    if 'post' in which:
+        make_post()
     if 'sampler_dense' in which:
         make_sampler_dense()
     if 'pipeline' in which:

@@ -191,3 +191,60 @@ def test_sharded_fit_product_path_two_ranks():
     for k in range(1, 9):                                # identical on both ranks: no broadcast needed after the solve
         a, b = res[0][k], res[1][k]
         assert all(np.array_equal(u, v) for u, v in zip(a, b)) if isinstance(a, list) else np.array_equal(a, b)
+
+
+def test_post_step_on_device(oracle):
+    """importance weights + truncation and SystematicResampler on the device (bitonic argsort, csrc/bfb_post.cu)
+    against the real reference's outputs (tests/golden/post.npz), against the oracle at sizes with ragged / non-power-of-two
+    lengths, and with device-resident (torch) inputs"""
+    import torch
+    from bayesfast_b200.post import SystematicResampler, importance_weights
+    g = gio.load('post.npz')
+    for c in g['cases']:
+        rs = SystematicResampler(nodes=c['nodes'], weights=c['weights'])
+        assert np.array_equal(rs.run(c['a'], int(c['n'])), c['idx']), c['name']
+        d = rs.run(torch.from_numpy(c['a']).cuda(), int(c['n']))
+        assert d.is_cuda and np.array_equal(d.cpu().numpy(), c['idx']), c['name']
+    w, wt, st = importance_weights(g['logp'], g['logq'], float(g['k_trunc']))
+    assert np.allclose(w, g['weights'], rtol=1e-14) and np.allclose(wt, g['weights_trunc'], rtol=1e-13)
+    assert np.isclose(st['sum'], g['weights'].sum(), rtol=1e-13) and np.isclose(st['max_trunc'], g['weights_trunc'].max(), rtol=1e-13)
+    rng = np.random.default_rng(9)
+    for m, n in ((1, 1), (2047, 100), (2049, 333), (1 << 20, 5000), (3000001, 47905)):
+        a = rng.normal(size=m)
+        a[rng.integers(0, m, size=min(m, 50))] = a[0]                       # ties: ordered by index like a stable argsort
+        rs = SystematicResampler(require_unique=False)
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            got = rs.run(torch.from_numpy(a).cuda(), n).cpu().numpy()
+        ref, _ = oracle.systematic_resample(a, n)
+        assert np.array_equal(got, ref), (m, n)
+    lp, lq = torch.randn(1 << 21, dtype=torch.float64, device='cuda'), torch.randn(1 << 21, dtype=torch.float64, device='cuda')
+    for kt in (0.25, -1.):
+        w, wt, st = importance_weights(lp, lq, kt)
+        wo, wto = oracle.importance_weights(lp.cpu().numpy(), lq.cpu().numpy(), kt)
+        assert np.allclose(w.cpu().numpy(), wo, rtol=1e-14) and np.allclose(wt.cpu().numpy(), wto, rtol=1e-12)
+        assert np.isclose(st['n_eff'], wto.sum()**2 / (wto**2).sum(), rtol=1e-10)
+    with pytest.raises(RuntimeError):
+        SystematicResampler().run(np.arange(10.), 50)                        # not unique (utils/misc.py:102-106)
+    with pytest.raises(ValueError):
+        SystematicResampler(nodes=(5., 1.))
+
+
+def test_fit_from_device_resident_rows():
+    """PolyModel.fit on CUDA torch tensors (rows that never left the GPU) == the same fit from host arrays, bound included"""
+    import torch
+    import bayesfast_b200 as bfb
+    rng = np.random.default_rng(31)
+    n, N = 9, 1500
+    x = rng.normal(size=(N, n)) * 0.7 + 0.2
+    y = (-0.5 * np.sum(x**2, axis=1) + 0.2 * x[:, 1] * x[:, 2]**2 + 0.01 * rng.normal(size=N))[:, None]
+    w = rng.uniform(0.5, 1.5, size=N)
+    a = bfb.PolyModel('cubic-2', input_size=n, output_size=1)
+    a.fit(x, y, logp=y[:, 0], w=w)
+    b = bfb.PolyModel('cubic-2', input_size=n, output_size=1)
+    xd, yd = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    b.fit(xd, yd, logp=yd[:, 0].contiguous(), w=torch.from_numpy(w).cuda())
+    for ca, cb in zip(a.configs, b.configs):
+        assert np.array_equal(np.asarray(ca._coef), np.asarray(cb._coef))
+    assert np.array_equal(a._mu, b._mu) and np.array_equal(a._hess, b._hess) and a._alpha == b._alpha
+    assert np.array_equal(a._f_mu, b._f_mu)

@@ -207,3 +207,13 @@ def test_pipeline_des_shaped_case(oracle):
             assert np.array_equal(out[k], r[k].astype(np.int32)), (c['name'], k)
         assert int(r['diverging'].sum()) >= 1
         _flt(out['samples'], r['samples'], c['name'], early=4)
+
+
+def test_post_step_restatements(oracle):
+    """SystematicResampler.run (utils/misc.py:62-108) and PostStep's weights (recipe.py:1286-1297) against the real reference"""
+    g = gio.load('post.npz')
+    for c in g['cases']:
+        idx, _ = oracle.systematic_resample(c['a'], int(c['n']), c['nodes'], c['weights'])
+        assert np.array_equal(idx, c['idx']), c['name']
+    w, wt = oracle.importance_weights(g['logp'], g['logq'], float(g['k_trunc']))
+    assert np.array_equal(w, g['weights']) and np.array_equal(wt, g['weights_trunc'])
