@@ -11,15 +11,17 @@ import numpy as np
 from . import _cabi
 
 _free = {}          # nbytes -> [ptr, ...]
-_lock = threading.Lock()
+_lock = threading.RLock()      # re-entrant: _release runs in GC finalizers, which may fire while this thread holds the lock
 _MAX_POOLED = 24 << 30
+_pooled = 0                    # bytes currently in the pool (kept as a counter: no allocation under the lock)
 
 
 def _release(ptr, nbytes):
+    global _pooled
     with _lock:
-        total = sum(k * len(v) for k, v in _free.items())
-        if total + nbytes <= _MAX_POOLED:
+        if _pooled + nbytes <= _MAX_POOLED:
             _free.setdefault(nbytes, []).append(ptr)
+            _pooled += nbytes
             return
     _cabi.lib().bfb_host_free(C.c_void_p(ptr))
 
@@ -29,11 +31,13 @@ def empty(shape, dtype=np.float64):
     dtype = np.dtype(dtype)
     nbytes = int(np.prod(shape)) * dtype.itemsize
     nbytes_al = max(4096, (nbytes + 4095) // 4096 * 4096)
+    global _pooled
     ptr = None
     with _lock:
         lst = _free.get(nbytes_al)
         if lst:
             ptr = lst.pop()
+            _pooled -= nbytes_al
     if ptr is None:
         p = C.c_void_p()
         L = _cabi.lib()
@@ -49,8 +53,10 @@ def empty(shape, dtype=np.float64):
 
 def trim():
     """free every pooled buffer"""
+    global _pooled
     with _lock:
         items = [(k, p) for k, v in _free.items() for p in v]
         _free.clear()
+        _pooled = 0
     for _, p in items:
         _cabi.lib().bfb_host_free(C.c_void_p(p))

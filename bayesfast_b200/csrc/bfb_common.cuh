@@ -7,6 +7,7 @@
 #include "../../include/bfb200.h"
 #include "../../include/bfb_rng.h"
 
+#define BFB_NSTAGE 3    // device staging buffers of the host-output pipeline of bfb_sampler_run
 #define BFB_WARP 32
 #define BFB_FULL 0xffffffffu
 
@@ -143,9 +144,9 @@ struct bfb_context {
     int64_t alloc_C;           // shape the chain arrays were allocated for (reused by bfb_sampler_init)
     int alloc_np;
     cudaStream_t copy_stream;  // device-to-host output pipeline of bfb_sampler_run
-    cudaEvent_t ev_k[2], ev_c[2];
-    void *stage[2];
-    size_t stage_len[2];
+    cudaEvent_t ev_k[BFB_NSTAGE], ev_c[BFB_NSTAGE];
+    void *stage[BFB_NSTAGE];
+    size_t stage_len[BFB_NSTAGE];
     int *queue;                // work queue of the multi-chain kernel
     size_t queue_len;
     int last_path;             // kernel family of the last sampler launch: 0 generic, 1 FMA multi-chain, 2 tensor core

@@ -15,6 +15,16 @@ __device__ __forceinline__ int64_t c3_index(int a, int b, int c, int n)
     return before_a + before_b + (c - b - 1);
 }
 
+// the same in 32-bit arithmetic (n <= 128: C(128, 3) = 341376): the 64-bit products and the division by 6 of c3_index cost more
+// instructions than the row of coefficients they locate
+__device__ __forceinline__ int c3_index32(int a, int b, int c, int n)
+{
+    const int na = n - a, nb = n - b;
+    const int before_a = (n * (n - 1) * (n - 2) - na * (na - 1) * (na - 2)) / 6;
+    const int before_b = ((na - 1) * (na - 2) - nb * (nb - 1)) / 2;
+    return before_a + before_b + (c - b - 1);
+}
+
 // Polynomial value f (all lanes) and Jacobian row J (lane-owned entries) of output `o` at the point whose
 // coordinates are staged in shared memory xsm[0..n) (and held per lane in x[]).
 // Restates _quadratic_f/_j, _cubic_2_f/_j, _cubic_3_f/_j (modules/_poly.pyx:13-137) and _linear (poly.py:339-352).
@@ -76,28 +86,45 @@ __device__ __forceinline__ void poly_fg(const DevModel &M, int o, const double *
         //                      P3 = sum_j x_j * (first sum)
         //   pass B (k outer):  dP3/dx_k |_(k middle)   = sum_j x_j sum_l a_jkl x_l   -> one warp reduction per k
         const double *c3 = M.c3 + (size_t)o * M.n_c3;
-        const int *row = M.c3_row;
+        // Row (j, k) starts at c3_index(j, k, k + 1): computed arithmetically (a table lookup in front of every row made
+        // each row two DEPENDENT L2 round trips), and the rows of a (j, .) / (., k) sweep are loaded RB at a time before any
+        // of them is used, so that RB * NPL coalesced loads are in flight per warp instead of one.  The evaluation is
+        // bound by the latency of these L2 reads (333 KB of coefficients at n = 64 do not fit next to the tree state).
+        constexpr int RB = (NPL <= 2) ? 8 : 4;
         double Gl[NPL], f3 = 0.;
 #pragma unroll
         for (int r = 0; r < NPL; ++r) Gl[r] = 0.;
         for (int j = 0; j < n - 2; ++j) {
             const double xj = xsm[j];
             double pj = 0.;
-#pragma unroll 4
-            for (int k = j + 1; k < n - 1; ++k) {
-                const double xk = xsm[k], xjk = xj * xk;
-                const double *rp = c3 + __ldg(row + j * n + k) - (k + 1);        // rp[l] = a_jkl
+            int off = c3_index32(j, j + 1, j + 2, n);              // row (j, j + 1); row (j, k + 1) follows after n - k - 1 entries
+            for (int k0 = j + 1; k0 < n - 1; k0 += RB) {
+                double a[RB][NPL];
+                int o2 = off;
 #pragma unroll
-                for (int r = 0; r < NPL; ++r) {
-                    if (32 * r + 31 > k) {
+                for (int b = 0; b < RB; ++b) {
+                    const int k = k0 + b;
+                    const double *rp = c3 + o2 - (k + 1);            // rp[l] = a_jkl
+#pragma unroll
+                    for (int r = 0; r < NPL; ++r) {
                         const int l = lane + 32 * r;
-                        if (l > k && l < n) {
-                            const double a = __ldg(rp + l);
-                            pj = fma(xk, a * x[r], pj);
-                            Gl[r] = fma(a, xjk, Gl[r]);
+                        a[b][r] = (k < n - 1 && l > k && l < n) ? __ldg(rp + l) : 0.;
+                    }
+                    o2 += n - k - 1;
+                }
+#pragma unroll
+                for (int b = 0; b < RB; ++b) {
+                    const int k = k0 + b;
+                    if (k < n - 1) {
+                        const double xk = xsm[k], xjk = xj * xk;
+#pragma unroll
+                        for (int r = 0; r < NPL; ++r) {
+                            pj = fma(xk, a[b][r] * x[r], pj);
+                            Gl[r] = fma(a[b][r], xjk, Gl[r]);
                         }
                     }
                 }
+                off = o2;
             }
             const double tot = warp_sum(pj);
             f3 = fma(xj, tot, f3);
@@ -106,15 +133,25 @@ __device__ __forceinline__ void poly_fg(const DevModel &M, int o, const double *
         }
         for (int k = 1; k < n - 1; ++k) {
             double qk = 0.;
-#pragma unroll 4
-            for (int j = 0; j < k; ++j) {
-                const double xj = xsm[j];
-                const double *rp = c3 + __ldg(row + j * n + k) - (k + 1);
+            for (int j0 = 0; j0 < k; j0 += RB) {
+                double a[RB][NPL];
 #pragma unroll
-                for (int r = 0; r < NPL; ++r) {
-                    if (32 * r + 31 > k) {
+                for (int b = 0; b < RB; ++b) {
+                    const int j = j0 + b;
+                    const double *rp = c3 + (j < k ? c3_index32(j, k, k + 1, n) : 0) - (k + 1);
+#pragma unroll
+                    for (int r = 0; r < NPL; ++r) {
                         const int l = lane + 32 * r;
-                        if (l > k && l < n) qk = fma(xj, __ldg(rp + l) * x[r], qk);
+                        a[b][r] = (j < k && l > k && l < n) ? __ldg(rp + l) : 0.;
+                    }
+                }
+#pragma unroll
+                for (int b = 0; b < RB; ++b) {
+                    const int j = j0 + b;
+                    if (j < k) {
+                        const double xj = xsm[j];
+#pragma unroll
+                        for (int r = 0; r < NPL; ++r) qk = fma(xj, a[b][r] * x[r], qk);
                     }
                 }
             }

@@ -20,6 +20,11 @@
 #define KC 32          // rows per pipeline stage
 #define LDP (TS + 4)   // padded leading dimension: conflict-free DMMA fragment loads (LDP % 16 == 4)
 
+// temporary device allocations of one call: freed on every return path (the error paths used to leak them)
+struct TmpList : std::vector<void *> {
+    ~TmpList() { for (void *p : *this) cudaFree(p); }
+};
+
 struct FitGroup {
     std::vector<int> cfg_ids, outputs;
     int P, Pt, Ptp, nt;
@@ -444,7 +449,7 @@ extern "C" int bfb_fit_accumulate(bfb_handle h, const double *x, const double *y
     FitState *fs = h->fit;
     const int n = h->n, m = h->m;
     const double *dx = x, *dy = y, *dw = w;
-    std::vector<void *> tmp;
+    TmpList tmp;
     if (loc == BFB_HOST) {
         void *p;
         BFB_CUDA(cudaMalloc(&p, sizeof(double) * N * n)); tmp.push_back(p);
@@ -496,6 +501,7 @@ extern "C" int bfb_fit_accumulate(bfb_handle h, const double *x, const double *y
     BFB_CUDA(cudaStreamSynchronize(h->stream));
     BFB_CUDA(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
     for (void *p : tmp) cudaFree(p);
+    tmp.clear();
     return BFB_OK;
 }
 
@@ -559,7 +565,7 @@ extern "C" int bfb_fit_max_beta(bfb_handle h, const double *x, int64_t N, const 
     BFB_REQUIRE(h && h->has_model && x && mu && hess && max_beta && N > 0, BFB_ERR_ARG, "bfb_fit_max_beta: bad arguments");
     BFB_CUDA(cudaSetDevice(h->device));
     const int n = h->n;
-    std::vector<void *> tmp;
+    TmpList tmp;
     auto dmal = [&](size_t bytes, void **p) -> int { BFB_CUDA(cudaMalloc(p, bytes)); tmp.push_back(*p); return BFB_OK; };
     int rc;
     void *dmu, *dh, *dmax, *dxv = (void *)x, *dbeta = (void *)beta_out;
@@ -585,6 +591,7 @@ extern "C" int bfb_fit_max_beta(bfb_handle h, const double *x, int64_t N, const 
     BFB_CUDA(cudaStreamSynchronize(h->stream));
     memcpy(max_beta, &bits, 8);
     for (void *p : tmp) cudaFree(p);
+    tmp.clear();
     return BFB_OK;
 }
 
@@ -784,7 +791,7 @@ extern "C" int bfb_fit_solve(bfb_handle h, double *coef_out, double *rel_resid)
         const int P = g.P, nr = (int)g.outputs.size();
         double *A, *As, *U, *Bs, *X, *R, *D, *dsc;
         int *d_info;
-        std::vector<void *> tmp;
+        TmpList tmp;
         auto dmal = [&](size_t bytes, void **p) -> int { BFB_CUDA(cudaMalloc(p, bytes)); tmp.push_back(*p); return BFB_OK; };
         int rc;
         if ((rc = dmal(sizeof(double) * P * P, (void **)&A)) || (rc = dmal(sizeof(double) * P * P, (void **)&As)) ||
@@ -824,6 +831,7 @@ extern "C" int bfb_fit_solve(bfb_handle h, double *coef_out, double *rel_resid)
         BFB_CUDA(cudaMemcpyAsync(&info, d_info, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         BFB_CUDA(cudaStreamSynchronize(h->stream));
         for (void *p : tmp) cudaFree(p);
+    tmp.clear();
         BFB_REQUIRE(info == 0, BFB_ERR_NUMERIC,
                     "fit: the normal equations are not positive definite (pivot %d of %d): the design matrix is rank "
                     "deficient (duplicated / too few points?)", info, P);

@@ -71,8 +71,7 @@ extern "C" int bfb_create(int device, bfb_handle *out)
     h->iters_done = 0;
     h->last_path = -1;
     h->alloc_C = 0; h->alloc_np = 0;
-    h->stage[0] = h->stage[1] = nullptr;
-    h->stage_len[0] = h->stage_len[1] = 0;
+    for (int i = 0; i < BFB_NSTAGE; ++i) { h->stage[i] = nullptr; h->stage_len[i] = 0; }
     memset(&h->dm, 0, sizeof(h->dm));
     memset(&h->cs, 0, sizeof(h->cs));
     BFB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
@@ -96,9 +95,9 @@ extern "C" int bfb_destroy(bfb_handle h)
     bfb_fit_free(h);
     if (h->gstack) cudaFree(h->gstack);
     if (h->queue) cudaFree(h->queue);
-    for (int i = 0; i < 2; ++i) if (h->stage[i]) cudaFree(h->stage[i]);
+    for (int i = 0; i < BFB_NSTAGE; ++i) if (h->stage[i]) cudaFree(h->stage[i]);
     if (h->copy_stream) {
-        for (int i = 0; i < 2; ++i) { cudaEventDestroy(h->ev_k[i]); cudaEventDestroy(h->ev_c[i]); }
+        for (int i = 0; i < BFB_NSTAGE; ++i) { cudaEventDestroy(h->ev_k[i]); cudaEventDestroy(h->ev_c[i]); }
         cudaStreamDestroy(h->copy_stream);
     }
     cudaEventDestroy(h->ev0);
@@ -527,6 +526,7 @@ __global__ void __launch_bounds__(128) density_eval_kernel(DevModel M, const dou
 struct DevBuf {
     // stages a caller buffer on the device when it lives on the host
     void *dev = nullptr; const void *host_src = nullptr; void *host_dst = nullptr; size_t bytes = 0; bool owned = false;
+    ~DevBuf() { if (owned && dev) cudaFree(dev); }        // every early return of the callers frees the staged copies
 };
 
 static int stage_in(bfb_context *h, const void *p, size_t bytes, int loc, DevBuf &b)

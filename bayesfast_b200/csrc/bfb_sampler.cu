@@ -975,10 +975,10 @@ extern "C" int bfb_sampler_run_ex(bfb_handle h, int sampler, int32_t n_iter, con
         const size_t need = full + (thin > 1 ? rec * (size_t)C * ((K + thin - 1) / thin) : 0);
         if (!h->copy_stream) {
             BFB_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-            for (int i = 0; i < 2; ++i) { BFB_CUDA(cudaEventCreateWithFlags(&h->ev_k[i], cudaEventDisableTiming));
-                                          BFB_CUDA(cudaEventCreateWithFlags(&h->ev_c[i], cudaEventDisableTiming)); }
+            for (int i = 0; i < BFB_NSTAGE; ++i) { BFB_CUDA(cudaEventCreateWithFlags(&h->ev_k[i], cudaEventDisableTiming));
+                                                   BFB_CUDA(cudaEventCreateWithFlags(&h->ev_c[i], cudaEventDisableTiming)); }
         }
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < BFB_NSTAGE; ++i) {
             if (h->stage_len[i] < need) {
                 if (h->stage[i]) cudaFree(h->stage[i]);
                 h->stage[i] = nullptr; h->stage_len[i] = 0;
@@ -995,8 +995,8 @@ extern "C" int bfb_sampler_run_ex(bfb_handle h, int sampler, int32_t n_iter, con
         for (int k = 0; k < n_chunks; ++k) {
             const int it_begin = k * K, Kk = (it_begin + K <= R) ? K : R - it_begin;
             const int kk = (Kk + thin - 1) / thin, keep_begin = it_begin / thin;
-            const int sb = k & 1;
-            if (k >= 2) BFB_CUDA(cudaStreamWaitEvent(h->stream, h->ev_c[sb], 0));   // staging buffer free again
+            const int sb = k % BFB_NSTAGE;
+            if (k >= BFB_NSTAGE) BFB_CUDA(cudaStreamWaitEvent(h->stream, h->ev_c[sb], 0));   // staging buffer free again
             void *dptr[11], *cptr[11];
             char *base = (char *)h->stage[sb], *cbase = (char *)h->stage[sb] + full;
             for (int f = 0; f < 11; ++f) {
