@@ -74,6 +74,12 @@ struct DevModel {
     // operand table of the tensor-core likelihood pipeline (bfb_lik_dmma.cu: one record per output), or null
     const double *lik_tab;
     int lik_nr;
+    // feature form of the likelihood pipeline (model variant bit 4, bfb_dmma.cuh): outputs = Phi(x) C^T over the features
+    // 1 | x_j | x_a x_b (a <= b in the UNION of the quadratic configs' masks); records of 8 outputs, feature / gradient tables
+    const double *lik_ftab;
+    const int *lik_fpt;  // [4 KT1][2] feature -> (a, b): -1,-1 constant; a,-1 linear; a,b product; -2,-2 padding
+    const int *lik_fgt;  // [32][1 + 3 QMAX] per dimension: count, then (feature index, partner dimension, factor) triples
+    int lik_kt1, lik_nt2, lik_nt1, lik_frec;
     int lik_ext;         // the pipeline has a radial bound / module rescale / variable transform / prior: model variant bits 3 | 1
     // third module of the pipeline (bfb_set_prior): independent Gaussian prior on the original-space inputs,
     // logp += p_c0 - 1/2 sum_j p_w[j] (x_j - p_mu[j])^2

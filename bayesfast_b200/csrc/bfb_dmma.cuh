@@ -28,11 +28,18 @@
 // its operand table (k-tiles x N3T tiles) follows the per-dimension tables in shared memory, P3 = (sum_j x_j dP3/dx_j) / 3
 // bit 3 = likelihood pipeline (bfb_set_epilogue, bfb_lik_dmma.cu): logp = c0 - 1/2 sum_o f_o^2 over the m pre-whitened
 // quadratic outputs; the m n x n operand is streamed from L2 (one record per output), nothing is staged in shared memory.
+// feature form of the likelihood pipeline: at most LIKF_KT k-tiles of features (P_f <= 4 LIKF_KT) and LIKF_NT2 feature tiles
+// of the second GEMM; per warp two staged records of 8 outputs, the point (8 x 32) and the second GEMM's result (8 x 8 LIKF_NT2)
+#define LIKF_KT 20
+#define LIKF_NT2 10
+#define LIKF_QMAX 12
+__host__ __device__ constexpr int likf_rec_doubles(int kt1, int nt2) { return (kt1 + 2 * nt2) * 32 + 8; }
+#define LIKF_WARP_DOUBLES (2 * likf_rec_doubles(LIKF_KT, LIKF_NT2) + 256 + 8 * 8 * LIKF_NT2)
 __host__ __device__ constexpr int lik_rec_doubles(int NR) { return NR * ((NR + 1) / 2) * 32 + 40; }   // fragments | lin[32] | c0 | pad
 
 template <int NR, int MV>
 struct DmmaShape {
-    static constexpr bool C2 = MV & 1, EXT = (MV & 2) != 0, C3 = (MV & 4) != 0, LIK = (MV & 8) != 0;
+    static constexpr bool C2 = MV & 1, EXT = (MV & 2) != 0, C3 = (MV & 4) != 0, LIK = (MV & 8) != 0, FEAT = (MV & 16) != 0;
     static constexpr int N3T = (NR + 1) / 2;              // output tiles of the cubic-3 GEMM
     static constexpr int TX = C2 ? NR : (NR + 1) / 2;     // tiles of the block multiplying x
     static constexpr int T2 = C2 ? (NR + 1) / 2 : 0;      // tiles multiplying x^2
@@ -45,7 +52,7 @@ struct DmmaShape {
     static constexpr int FRAG_DOUBLES = LIK ? 0 : NR * NTP * 64;
     // shared memory in front of the per-dimension tables: the operand table, or (likelihood pipeline) two staged operand
     // records per warp, filled by the warp itself with cp.async one output ahead of the DMMAs
-    __host__ __device__ static constexpr int frag_doubles(int warps) { return LIK ? warps * 2 * lik_rec_doubles(NR) : FRAG_DOUBLES; }
+    __host__ __device__ static constexpr int frag_doubles(int warps) { return FEAT ? warps * LIKF_WARP_DOUBLES : LIK ? warps * 2 * lik_rec_doubles(NR) : FRAG_DOUBLES; }
 };
 
 inline int bfb_frag_tiles(int nr, bool c2, bool ext) { return (c2 ? nr : (nr + 1) / 2) + (c2 ? (nr + 1) / 2 : 0) + (ext ? 2 : 1) * ((nr + 1) / 2); }
@@ -205,6 +212,94 @@ __device__ __forceinline__ void lik_post(const double *et, const LikExt &E, int 
     if (E.use_transform) lp += tpart;
 }
 
+// ----------------------------------------------------------------------------------------------------------------------
+// Feature form of the likelihood pipeline (model variant bit 4).  When the quadratic configs of all outputs live on one small
+// set Q of inputs (the DES-Y1 example: one 9-D mask shared by 457 outputs, examples/des-y1-w-cosmosis.ipynb cell 18), the m
+// outputs are  F = Phi(x) C^T  over the P_f = 1 + n + q (q + 1) / 2 features  1 | x_j | x_a x_b (a <= b in Q)  and the gradient is
+//     grad = - sum_o f_o grad f_o = - (dPhi/dx)^T (C^T f) :
+// two chained GEMMs per 8 outputs, [8 points x P_f] . [P_f x 8] and [8 points x 8] . [8 x P_f], 4 m P_f flops per point instead
+// of the m (2 n^2 + 5 n) of one n x n product per output (73 features against 27 x 27: 5.7 x less at the DES shape).  The
+// columns of an output tile are ordered so that the C fragment of the first GEMM (lane lg: outputs 8 t + lg and 8 t + 4 + lg)
+// IS the A fragment of the two k-tiles of the second: the outputs never leave the registers.
+// Record of output tile t: g1[kt][lane] (KT1 x 32) | g2[e][t2][lane] (2 x NT2 x 32) | f_mu[8].
+// ----------------------------------------------------------------------------------------------------------------------
+struct LikFeatAcc {
+    double acc2, S1;                    // lane partials: sum f^2, sum f (f0 - f_mu) / alpha over the lane's outputs
+    double w[LIKF_NT2][2];              // second GEMM: C^T f, lane lg holds features 8 t2 + 2 lg + {0, 1} of its point
+};
+
+// the features of the 8 points of the warp as A fragments: lane lg of quad gi holds Phi[point gi][4 kt + lg]
+__device__ __forceinline__ void likf_features(const int *fpt, int kt1, int lane, const double *xs /* [8][32] */, double (&phi)[LIKF_KT])
+{
+    const double *xr = xs + (lane >> 2) * 32;
+#pragma unroll
+    for (int kt = 0; kt < LIKF_KT; ++kt) {
+        double v = 0.;
+        if (kt < kt1) {
+            const int2 ab = __ldg(reinterpret_cast<const int2 *>(fpt) + 4 * kt + (lane & 3));
+            v = (ab.x == -1) ? 1. : (ab.x < 0) ? 0. : (ab.y < 0) ? xr[ab.x] : xr[ab.x] * xr[ab.y];
+        }
+        phi[kt] = v;
+    }
+}
+
+// one record (8 outputs) against the features: both GEMMs, bound extrapolation of the values in between
+__device__ __forceinline__ void likf_tile(const double *rec, int kt1, int nt2, int lane, const double (&phi)[LIKF_KT], bool use_bound,
+                                          bool outside, double beta, double alpha, LikFeatAcc &A)
+{
+    double f0 = 0., f1 = 0.;
+#pragma unroll
+    for (int kt = 0; kt < LIKF_KT; ++kt)
+        if (kt < kt1) dmma884(f0, f1, phi[kt], rec[kt * 32 + lane]);
+    if (use_bound) {
+        const double m0 = rec[(kt1 + 2 * nt2) * 32 + (lane & 3)], m1 = rec[(kt1 + 2 * nt2) * 32 + 4 + (lane & 3)];
+        const double g0 = f0, g1 = f1;
+        if (outside) { f0 = (beta * g0 - (beta - alpha) * m0) / alpha; f1 = (beta * g1 - (beta - alpha) * m1) / alpha; }
+        A.S1 = fma(f0, (g0 - m0) / alpha, A.S1);
+        A.S1 = fma(f1, (g1 - m1) / alpha, A.S1);
+    }
+    A.acc2 = fma(f0, f0, A.acc2);
+    A.acc2 = fma(f1, f1, A.acc2);
+    const double *g2 = rec + kt1 * 32 + lane;
+#pragma unroll
+    for (int t2 = 0; t2 < LIKF_NT2; ++t2)
+        if (t2 < nt2) {
+            dmma884(A.w[t2][0], A.w[t2][1], f0, g2[t2 * 32]);
+            dmma884(A.w[t2][0], A.w[t2][1], f1, g2[(nt2 + t2) * 32]);
+        }
+}
+
+// after the last record: totals over the quad, and G0 = -(dPhi/dx)^T w for the own dimensions (ws: [8][8 LIKF_NT2] scratch)
+template <int NR>
+__device__ __forceinline__ void likf_finish(const int *fgt, int nt2, int n, int lane, const double *xs, double *ws, LikFeatAcc &A,
+                                            double &acc2, double &S1, double (&g0)[NR])
+{
+    const int gi = lane >> 2, lg = lane & 3;
+    double z0 = 0., z1 = 0.;
+    acc2 = A.acc2; S1 = A.S1;
+    qsum4(acc2, S1, z0, z1, lane);
+    double *wr = ws + gi * (8 * LIKF_NT2);
+    __syncwarp();
+#pragma unroll
+    for (int t2 = 0; t2 < LIKF_NT2; ++t2)
+        if (t2 < nt2) *reinterpret_cast<double2 *>(wr + 8 * t2 + 2 * lg) = make_double2(A.w[t2][0], A.w[t2][1]);
+    __syncwarp();
+    const double *xr = xs + gi * 32;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        const int j = 4 * r + lg;
+        const int *gt = fgt + j * (1 + 3 * LIKF_QMAX);
+        double s = (j < n) ? wr[1 + j] : 0.;          // linear feature of dimension j
+        const int cnt = __ldg(gt);
+        for (int i = 0; i < cnt; ++i) {
+            const int fi = __ldg(gt + 1 + 3 * i), b = __ldg(gt + 2 + 3 * i), fac = __ldg(gt + 3 + 3 * i);
+            s = fma((double)fac * wr[fi], xr[b], s);
+        }
+        g0[r] = -s;
+    }
+    __syncwarp();
+}
+
 // One evaluation = two GEMM stages.  Stage A: h = H (x - mu) (the TD tiles of the D block; with the extended density also
 // h2 = H_decay (x_orig - mu_decay)) gives the Mahalanobis radius, i.e. the inside / outside decision of the radial bound
 // (poly.py:466-469).  Outside points are then REPLACED by their projection onto the ellipsoid before stage B, so the
@@ -249,6 +344,8 @@ struct DmmaConsts {
     int m;
     double e_c0;
     LikExt lx;
+    const double *lik_ftab; const int *lik_fpt, *lik_fgt;
+    int kt1, nt2, nt1, frec;
 };
 
 __device__ __forceinline__ DmmaConsts dmma_consts(const DevModel &M)
@@ -262,6 +359,8 @@ __device__ __forceinline__ DmmaConsts dmma_consts(const DevModel &M)
     K.lik_tab = M.lik_tab; K.m = M.m; K.e_c0 = M.e_c0;
     K.lx.use_transform = M.use_transform; K.lx.use_scales = M.use_scales; K.lx.use_bound = M.use_bound; K.lx.use_prior = M.use_prior;
     K.lx.alpha = M.alpha; K.lx.p_c0 = M.p_c0;
+    K.lik_ftab = M.lik_ftab; K.lik_fpt = M.lik_fpt; K.lik_fgt = M.lik_fgt;
+    K.kt1 = M.lik_kt1; K.nt2 = M.lik_nt2; K.nt1 = M.lik_nt1; K.frec = M.lik_frec;
     return K;
 }
 
@@ -319,6 +418,52 @@ __device__ __forceinline__ void dmma_logp_grad(const double *bsm, int lane, cons
         // likelihood pipeline: y_o = S_o x for every output as DMMAs against the output's record (the 8 points of the warp are
         // the rows), f_o by one quad reduction, sum f_o^2 and the gradient accumulated on the fly (bfb_lik_dmma.cu).  The
         // records stream from L2 through two per-warp shared-memory slots: cp.async of output o + 1 runs under the DMMAs of o.
+        if constexpr (SH::FEAT) {
+            // feature form: the records (8 outputs each) stream from L2 through two per-warp slots like below
+            const int REC = K.frec, gi_ = lane >> 2, lg_ = lane & 3;
+            double *wb = const_cast<double *>(bsm) + (size_t)(threadIdx.x >> 5) * LIKF_WARP_DOUBLES;
+            double *xs = wb + 2 * likf_rec_doubles(LIKF_KT, LIKF_NT2), *ws = xs + 256;
+            auto stage = [&](int t) {
+                const double *src = K.lik_ftab + (size_t)t * REC;
+                const unsigned dst = (unsigned)__cvta_generic_to_shared(wb + (size_t)(t & 1) * likf_rec_doubles(LIKF_KT, LIKF_NT2));
+                for (int e = lane; e < REC / 2; e += 32)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst + 16u * e), "l"(src + 2 * e) : "memory");
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            };
+            double beta = 0., xe[NR];
+            bool outside = false;
+#pragma unroll
+            for (int r = 0; r < NR; ++r) xe[r] = x_in[r];
+            const double *hrec = K.lik_tab + (size_t)K.m * lik_rec_doubles(NR);
+            if (EXT) lik_pre<NR>(msm, K.lx, K.n, lane, x_in, hrec, live, xe, outside, beta);
+            __syncwarp();
+            stage(0);
+#pragma unroll
+            for (int r = 0; r < NR; ++r) xs[gi_ * 32 + 4 * r + lg_] = xe[r];
+            if (NR < 8) { for (int r = NR; r < 8; ++r) xs[gi_ * 32 + 4 * r + lg_] = 0.; }
+            __syncwarp();
+            double phi[LIKF_KT];
+            likf_features(K.lik_fpt, K.kt1, lane, xs, phi);
+            LikFeatAcc A;
+            A.acc2 = 0.; A.S1 = 0.;
+#pragma unroll
+            for (int t2 = 0; t2 < LIKF_NT2; ++t2) A.w[t2][0] = A.w[t2][1] = 0.;
+#pragma unroll 1
+            for (int t = 0; t < K.nt1; ++t) {
+                if (t + 1 < K.nt1) { stage(t + 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+                else asm volatile("cp.async.wait_group 0;" ::: "memory");
+                __syncwarp();
+                likf_tile(wb + (size_t)(t & 1) * likf_rec_doubles(LIKF_KT, LIKF_NT2), K.kt1, K.nt2, lane, phi, EXT && K.lx.use_bound, outside, beta,
+                          K.lx.alpha, A);
+                __syncwarp();
+            }
+            double acc2, S1;
+            likf_finish<NR>(K.lik_fgt, K.nt2, K.n, lane, xs, ws, A, acc2, S1, gn);
+            if (EXT) lik_post<NR>(msm, K.lx, K.n, lane, x_in, hrec, outside, beta, S1, acc2, K.e_c0, gn, lp);
+            else lp = K.e_c0 - 0.5 * acc2;
+            ke = qsum(ke_of(gn));
+            return;
+        }
         constexpr int NT4 = (NR + 1) / 2, REC = lik_rec_doubles(NR), OL = NR * NT4 * 32;
         const int lg_ = lane & 3;
         double *buf = const_cast<double *>(bsm) + (size_t)(threadIdx.x >> 5) * 2 * REC;

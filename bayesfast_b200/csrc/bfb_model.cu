@@ -613,7 +613,7 @@ extern "C" int bfb_logp_and_grad_batch(bfb_handle h, const double *X, int64_t C,
     size_t smem = sizeof(double) * wpb * 2 * h->np;
     BFB_CUDA(cudaEventRecord(h->ev0, h->stream));
     rc = bfb_launch_lik_dmma(h, (const double *)bx.dev, C, (double *)bl.dev, (double *)bg.dev);
-    h->last_eval_path = 3;
+    h->last_eval_path = (h->dm.lik_ftab && !getenv("BFB200_LIK_DENSE")) ? 4 : 3;
     if (rc == 1) { rc = bfb_launch_eval_dmma(h, (const double *)bx.dev, C, (double *)bl.dev, (double *)bg.dev); h->last_eval_path = 2; }
     if (rc < 0) return rc;
     if (rc == 1) h->last_eval_path = 0;

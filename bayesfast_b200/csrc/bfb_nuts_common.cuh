@@ -62,10 +62,12 @@ __device__ __forceinline__ double rng_uniform(RngF &r, int64_t t)
 
 // queue[0] = head, queue[1] = tail, queue[2 .. 2 + n_groups) = chunks finished per group, then ring[n_units]: ids of the
 // groups whose next chunk can start (initially every group once; a group is appended again when one of its chunks completes)
-static __global__ void queue_init_kernel(int *queue, int n_groups, int n_units)
+// head0 > 0: the first head0 units are pre-assigned (warp slot s = blockIdx.x + gridDim.x * warp takes unit s without an atomic),
+// which deals the groups evenly over ALL blocks when there are fewer groups than warp slots
+static __global__ void queue_init_kernel(int *queue, int n_groups, int n_units, int head0 = 0)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) { queue[0] = 0; queue[1] = n_groups; }
+    if (i == 0) { queue[0] = head0; queue[1] = n_groups; }
     if (i < n_groups) queue[2 + i] = 0;
     if (i < n_units) queue[2 + n_groups + i] = (i < n_groups) ? i : -1;
 }

@@ -122,13 +122,15 @@ __global__ void __launch_bounds__(32 * W, 1) nuts_dmma_kernel(DevModel M, bfb_sa
 
     volatile int *qv = queue;
     volatile int *ring = queue + 2 + n_groups;
+    bool first_unit = true;                       // the first unit of a warp is pre-assigned: 512 groups spread over all 148 SMs
 #pragma unroll 1
     for (;;) {
     int idx = 0, group = 0;
     if (lane == 0) {
-        idx = atomicAdd(queue, 1);
-        if (idx < n_units) { while ((group = ring[idx]) < 0) __nanosleep(100); }
+        idx = first_unit ? (int)(blockIdx.x + gridDim.x * wib) : atomicAdd(queue, 1);
+        if (idx < n_units) { while ((group = ring[idx]) < 0) __nanosleep(1000); }
     }
+    first_unit = false;
     idx = __shfl_sync(BFB_FULL, idx, 0);
     if (idx >= n_units) break;
     group = __shfl_sync(BFB_FULL, group, 0);
@@ -854,6 +856,7 @@ static int launch_hmc_dmma_w(bfb_context *h, const bfb_run_out &o, int n_iter)
     int W = groups > sms * 16 ? 12 : groups > sms * 4 ? 8 : 4;
     if (const char *e = getenv("BFB200_HMC_WARPS_PER_SM")) { int v = atoi(e); if (v == 4 || v == 8 || v == 12 || v == 16) W = v; }
     if (DmmaShape<NR, MV>::LIK && W > 12) W = 12;        // 2 staged operand records per warp (15 KB): at most 12 warps per block
+    if (DmmaShape<NR, MV>::FEAT) W = 4;                  // feature form: 28 KB of staged records, point and second-GEMM scratch per warp
     else if (const char *e2 = getenv("BFB200_WARPS_PER_SM")) { int v = atoi(e2); if (v == 4 || v == 8) W = v; }
     switch (W) {
     case 16: return launch_hmc_dmma<NR, MV, 16>(h, o, n_iter);
@@ -879,6 +882,17 @@ int bfb_launch_hmc_dmma(bfb_context *h, const bfb_run_out &o, int n_iter)
     if (M.epilogue) {                       // likelihood pipeline (model variant bit 3): operand streamed from L2
         if (!M.lik_tab) return 1;
         if (const char *e = getenv("BFB200_SAMPLER")) { if (strcmp(e, "dmma")) return 1; }
+        if (M.lik_ftab) {                 // feature form: two chained GEMMs per 8 outputs (model variant bit 4)
+            switch (M.lik_nr * 2 + (M.lik_ext ? 1 : 0)) {
+            case 8: return launch_hmc_dmma_w<4, 24>(h, o, n_iter);
+            case 14: return launch_hmc_dmma_w<7, 24>(h, o, n_iter);
+            case 16: return launch_hmc_dmma_w<8, 24>(h, o, n_iter);
+            case 9: return launch_hmc_dmma_w<4, 26>(h, o, n_iter);
+            case 15: return launch_hmc_dmma_w<7, 26>(h, o, n_iter);
+            case 17: return launch_hmc_dmma_w<8, 26>(h, o, n_iter);
+            }
+            return 1;
+        }
         switch (M.lik_nr * 2 + (M.lik_ext ? 1 : 0)) {
         case 8: return launch_hmc_dmma_w<4, 8>(h, o, n_iter);
         case 14: return launch_hmc_dmma_w<7, 8>(h, o, n_iter);
@@ -949,11 +963,12 @@ static int launch_dmma(bfb_context *h, const bfb_run_out &o, int n_iter, int cpg
         BFB_CUDA(cudaMalloc((void **)&h->queue, sizeof(int) * qlen));
         h->queue_len = qlen;
     }
-    queue_init_kernel<<<(unsigned)((n_units64 + 255) / 256), 256, 0, h->stream>>>(h->queue, n_groups, (int)n_units64);
-    h->launches++;
+    // one block per SM whenever there are at least as many groups as SMs: with 512 groups (4096 chains) every SM then runs 3 or
+    // 4 warps instead of 128 SMs running 4 and 20 none
     int blocks = h->sm_count;
-    const int64_t want = (n_groups + W - 1) / W;          // more warps than groups would only poll the queue
-    if ((int64_t)blocks > want) blocks = (int)want;
+    if ((int64_t)blocks > n_groups) blocks = n_groups;
+    queue_init_kernel<<<(unsigned)((n_units64 + 255) / 256), 256, 0, h->stream>>>(h->queue, n_groups, (int)n_units64, blocks * W);
+    h->launches++;
     nuts_dmma_kernel<NR, MV, W><<<blocks, 32 * W, smem, h->stream>>>(h->dm, h->scfg, h->cs, od, L, LS, h->gstack,
                                                                     h->gstack + deep * (size_t)n_groups, (int)h->iters_done,
                                                                     chunk_iters, n_groups, (int)n_units64, h->queue, cpg);
@@ -987,6 +1002,17 @@ int bfb_launch_nuts_dmma(bfb_context *h, const bfb_run_out &o, int n_iter)
     if (M.epilogue) {                       // likelihood pipeline (model variant bit 3): operand streamed from L2
         if (!M.lik_tab || h->scfg.max_treedepth > 10) return 1;
         if (const char *e = getenv("BFB200_SAMPLER")) { if (strcmp(e, "dmma")) return 1; }
+        if (M.lik_ftab) {                 // feature form: two chained GEMMs per 8 outputs (model variant bit 4)
+            switch (M.lik_nr * 2 + (M.lik_ext ? 1 : 0)) {
+            case 8: return launch_dmma_w<4, 24>(h, o, n_iter);
+            case 14: return launch_dmma_w<7, 24>(h, o, n_iter);
+            case 16: return launch_dmma_w<8, 24>(h, o, n_iter);
+            case 9: return launch_dmma_w<4, 26>(h, o, n_iter);
+            case 15: return launch_dmma_w<7, 26>(h, o, n_iter);
+            case 17: return launch_dmma_w<8, 26>(h, o, n_iter);
+            }
+            return 1;
+        }
         switch (M.lik_nr * 2 + (M.lik_ext ? 1 : 0)) {
         case 8: return launch_dmma_w<4, 8>(h, o, n_iter);
         case 14: return launch_dmma_w<7, 8>(h, o, n_iter);

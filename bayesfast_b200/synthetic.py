@@ -4,7 +4,7 @@ true log-density, training points for the surrogate fit and chain starting point
 """
 import numpy as np
 
-__all__ = ['des_shaped', 'correlated_gaussian', 'des_pipeline', 'cubic3_stack', 'n_param']
+__all__ = ['des_shaped', 'correlated_gaussian', 'des_pipeline', 'des_y1_like', 'cubic3_stack', 'n_param']
 
 
 def n_param(order, n):
@@ -108,3 +108,38 @@ def cubic3_stack(n=64, seed=3, cond=30., cubic_scale=0.02):
             for o, a in (('linear', lin), ('quadratic', quad), ('cubic-2', c2), ('cubic-3', c3))]
     spec = dict(n=n, m=1, configs=cfgs, use_bound=False, input_scales=None, use_decay=False, transform_ranges=None)
     return spec, cov
+
+
+DES_PARA_RANGE = np.array([[0.1, 0.9], [0.55, 0.9], [0.03, 0.07], [0.87, 1.07], [0.5e-9, 5.0e-9], [0.0006, 0.01], [-2, -0.333],
+                           [0.8, 3.0], [0.8, 3.0], [0.8, 3.0], [0.8, 3.0], [0.8, 3.0], [-0.1, 0.1], [-0.1, 0.1], [-0.1, 0.1],
+                           [-0.1, 0.1], [-5.0, 5.0], [-5.0, 5.0], [-0.1, 0.1], [-0.1, 0.1], [-0.1, 0.1], [-0.1, 0.1],
+                           [-0.05, 0.05], [-0.05, 0.05], [-0.05, 0.05], [-0.05, 0.05], [-0.05, 0.05]])
+DES_NONLINEAR = np.array([0, 1, 2, 3, 4, 5, 6, 16, 17])
+DES_PRIOR = dict(idx=np.array([18, 19, 20, 21, 12, 13, 14, 15, 22, 23, 24, 25, 26]),
+                 mu=np.array([-0.001, -0.019, 0.009, -0.018, 0.012, 0.012, 0.012, 0.012, 0.008, -0.005, 0.006, 0.0, 0.0]),
+                 sig=np.array([0.016, 0.013, 0.011, 0.022, 0.023, 0.023, 0.023, 0.023, 0.007, 0.007, 0.006, 0.01, 0.01]))
+
+
+def des_y1_like(m=457, seed=0, n_fit_mult=2):
+    """The density shape of examples/des-y1-w-cosmosis.ipynb (cells 9-18) with a synthetic theory vector: n = 27 inputs with the
+    notebook's parameter ranges (module rescale AND hard-bounded variable transform), m whitened outputs from a linear config
+    plus a quadratic config on the notebook's shared 9-D mask, chi^2 likelihood, Gaussian prior on 13 inputs.
+    Returns dict(ranges, nonlinear, prior, d, x_fit (original space), y_fit, x_0 (original space))."""
+    rng = np.random.default_rng(seed)
+    rg = DES_PARA_RANGE
+    n = rg.shape[0]
+    mid, width = rg.mean(axis=1), rg[:, 1] - rg[:, 0]
+    W1 = rng.normal(size=(m, n)) * 1.5
+    W2 = rng.normal(size=(m, 9, 9)) * 0.8
+
+    def theory(x):
+        u = (np.atleast_2d(x) - mid) / width
+        v = u[:, DES_NONLINEAR]
+        return u @ W1.T + np.einsum('ojk,nj,nk->no', W2, v, v)
+
+    P = n + 1 + 9 * 10 // 2
+    x_fit = mid + np.clip(rng.normal(size=(n_fit_mult * P, n)) * 0.08, -0.45, 0.45) * width
+    d = theory(mid + rng.normal(size=n) * 0.03 * width)[0] + 0.05 * rng.normal(size=m)
+    x_0 = mid + np.clip(rng.normal(size=(4096, n)) * 0.03, -0.45, 0.45) * width
+    return dict(n=n, m=m, ranges=rg, nonlinear=DES_NONLINEAR, prior=DES_PRIOR, d=d, theory=theory, x_fit=x_fit, y_fit=theory(x_fit),
+                x_0=x_0)

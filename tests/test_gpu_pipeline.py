@@ -153,7 +153,7 @@ def test_likelihood_tensor_core_evaluator(handle, oracle, monkeypatch, n, m, C):
     lpo, go = oracle.OracleDensity(spec).logp_and_grad_batch(X)
     handle.set_model(w)
     lp, g = handle.logp_and_grad_batch(X)
-    assert handle.eval_last_path() == 'lik_dmma'
+    assert handle.eval_last_path() in ('lik_dmma', 'lik_feat')      # the feature form when the outputs' masks have a small union
     monkeypatch.setenv('BFB200_EVAL', 'generic')
     lpg, gg = handle.logp_and_grad_batch(X)
     assert handle.eval_last_path() == 'generic'
@@ -179,11 +179,11 @@ def test_likelihood_with_bound_on_both_evaluators(handle, oracle, monkeypatch):
     X = rng.normal(size=(40, 8)) * 0.9              # radius 1.5: a good part of the points is outside
     lpo, go = oracle.OracleDensity(spec).logp_and_grad_batch(X)
     assert np.sum(np.linalg.norm(X, axis=1) > 1.5) > 5
-    for path in ('lik_dmma', 'generic'):
+    for path in ('tensor', 'generic'):
         if path == 'generic':
             monkeypatch.setenv('BFB200_EVAL', 'generic')
         lp, g = handle.logp_and_grad_batch(X)
-        assert handle.eval_last_path() == path
+        assert handle.eval_last_path() == ('generic' if path == 'generic' else 'lik_feat')       # n = 8: P_f = 45 features
         assert np.allclose(lp, lpo, rtol=1e-10, atol=1e-10) and np.allclose(g, go, rtol=1e-10, atol=1e-10 * np.abs(go).max())
 
 
@@ -222,7 +222,7 @@ def test_likelihood_tensor_core_samplers(handle, oracle, monkeypatch, n, m, C, s
 DES = gio.load('pipeline_des.npz')['cases'][0]
 
 
-@pytest.mark.parametrize('path', ['tensor', 'generic'])
+@pytest.mark.parametrize('path', ['tensor', 'tensor_dense', 'generic'])
 def test_pipeline_des_shaped_golden(handle, monkeypatch, path):
     """The DES-Y1 example's three-module density (examples/des-y1-w-cosmosis.ipynb cells 12-18: linear + shared-mask quadratic
     surrogate with module input_scales -> chi2 -> posterior module with a Gaussian prior on 13 inputs; Density input_scales,
@@ -232,17 +232,19 @@ def test_pipeline_des_shaped_golden(handle, monkeypatch, path):
     if path == 'generic':
         monkeypatch.setenv('BFB200_EVAL', 'generic')
         monkeypatch.setenv('BFB200_SAMPLER', 'generic')
+    if path == 'tensor_dense':
+        monkeypatch.setenv('BFB200_LIK_DENSE', '1')       # one n x n product per output instead of the feature form Phi(x) C^T
     case = DES
     handle.set_model(_whitened(case))
     lp, g = handle.logp_and_grad_batch(case['X'])
-    assert handle.eval_last_path() == ('lik_dmma' if path == 'tensor' else 'generic')
+    assert handle.eval_last_path() == {'generic': 'generic', 'tensor': 'lik_feat', 'tensor_dense': 'lik_dmma'}[path]
     assert np.allclose(lp, case['logp'], rtol=1e-10, atol=1e-10)
     assert np.allclose(g, case['grad'], rtol=1e-10, atol=1e-10 * np.abs(case['grad']).max())
     r, kw = case['result'], case['trace_kw']
     n_iter, n_warmup = int(kw['n_iter']), int(kw['n_warmup'])
     handle.sampler_init(cfg_from(kw, n_warmup, int(case['seed'])), case['x0'], float(r['step0']), r['var0'], case['x0'])
     out = handle.sampler_run('NUTS', n_iter)
-    assert handle.sampler_last_path() == ('dmma' if path == 'tensor' else 'generic')
+    assert handle.sampler_last_path() == ('generic' if path == 'generic' else 'dmma')
     st = handle.sampler_state()
     assert np.all(st['status'] == 0) and np.array_equal(st['n_draws'], r['n_draws'])
     for k in INT_STATS:
@@ -281,7 +283,7 @@ def test_des_shaped_public_api_and_large_batch(oracle):
     Xo = mid + np.clip(rng.normal(size=(3000 - 7, n)) * np.where(np.arange(3000 - 7) % 2, 0.05, 0.15)[:, None], -0.49, 0.49) * width
     Xt = den.from_original(Xo)
     lp, g = den.logp_and_grad(Xt, original_space=False)
-    assert den._sync(False).eval_last_path() == 'lik_dmma'
+    assert den._sync(False).eval_last_path() == 'lik_feat'
     lpo, go = od.logp_and_grad_batch(Xt)
     assert np.allclose(lp, lpo, rtol=1e-10, atol=1e-9) and np.allclose(g, go, rtol=1e-9, atol=1e-10 * np.abs(go).max())
     beta = np.sqrt(np.einsum('ij,jk,ik->i', (Xo - rg[:, 0]) / width - sur._mu, sur._hess, (Xo - rg[:, 0]) / width - sur._mu))
