@@ -195,40 +195,44 @@ def extra_measurements(args, bfb, torch, den, h, prob, x0, trace_kw, flush, peak
                                  roofline=dict(bound='tensor', achieved=fe / mse / 1e9, peak=peak, unit='TFLOP/s', frac=fe / mse / 1e9 / peak),
                                  hbm_gbs=Ce * (2 * N_DIM + 1) * 8 / mse / 1e6)
     del Xe, lpe, ge
-    # (c) SURVEY 8f rank 1: DES-Y1-shaped surrogate -> Gaussian-likelihood pipeline (n = 26, m = 457 block-quadratic outputs,
-    # dense inverse covariance) on the tensor cores: batched logp + gradient (bfb_lik_dmma.cu) and NUTS (model variant bit 3)
+    # (c) SURVEY 8f rank 1: the DES-Y1 example's three-module density (examples/des-y1-w-cosmosis.ipynb cells 9-18): n = 27 inputs with
+    # module rescale + hard-bounded transform, m = 457 whitened outputs from a linear config and a quadratic config on the shared 9-D
+    # mask, chi^2 likelihood, Gaussian prior on 13 inputs, radial bound -- fitted on the device, then batched logp + gradient and NUTS
+    # on the tensor cores in feature form Phi(x) C^T (bfb_dmma.cuh, model variant bits 3|1|4).  Fractions are against the MINIMAL
+    # algorithmic work 4 m P_f (P_f = 1 + 27 + 45 features), not against the n x n product per output the kernels used to do.
     try:
-        from bayesfast_b200 import _cabi
-        from bayesfast_b200.density import whiten_spec
-        pspec, plik = synthetic.des_pipeline(N_DIM, 457, seed=0)
-        hp = _cabi.Handle(dev)
-        hp.set_model(whiten_spec(pspec, plik))
+        pd_ = synthetic.des_y1_like(457)
+        np_, mp_ = pd_['n'], pd_['m']
+        surp = bfb.PolyModel([bfb.PolyConfig('linear'), bfb.PolyConfig('quadratic', input_mask=pd_['nonlinear'])], input_size=np_,
+                             output_size=mp_, input_scales=pd_['ranges'], device=dev)
+        denp = bfb.Density(surp, input_scales=pd_['ranges'], hard_bounds=True, likelihood=bfb.GaussianLikelihood(pd_['d'], np.ones(mp_), 0.),
+                           prior=bfb.GaussianPrior(pd_['prior']['idx'], pd_['prior']['mu'], pd_['prior']['sig']))
+        denp.fit(pd_['x_fit'], pd_['y_fit'])
+        Pf = 1 + np_ + 45
+        fl_min = 4 * mp_ * Pf
+        hp = denp._sync(False)
         Cp = 1 << 16
-        Xp = (torch.randn(Cp, N_DIM, dtype=torch.float64, device='cuda:%d' % dev) * 0.3).contiguous()
+        Xp = torch.tensor(denp.from_original(np.tile(pd_['x_0'], (Cp // pd_['x_0'].shape[0], 1))), device='cuda:%d' % dev).contiguous()
         lpp = torch.empty(Cp, dtype=torch.float64, device='cuda:%d' % dev)
-        gp = torch.empty(Cp, N_DIM, dtype=torch.float64, device='cuda:%d' % dev)
+        gp = torch.empty(Cp, np_, dtype=torch.float64, device='cuda:%d' % dev)
         torch.cuda.synchronize(dev)
         msp = []
         for i in range(5):
             hp.logp_and_grad_batch_dev(Xp.data_ptr(), Cp, lpp.data_ptr(), gp.data_ptr())
             msp.append(hp.last_kernel_ms())
         msp = float(np.mean(msp[1:]))
-        fl = 457 * (2 * N_DIM * N_DIM + 5 * N_DIM) + 9 * N_DIM
-        x0p = np.random.default_rng(1).normal(size=(C, N_DIM)) * 0.2
-        cfgp = bfb.NTrace(n_chain=C, n_iter=200, n_warmup=100, x_0=x0p, random_generator=SEED)._cfg_dict(SEED, 0)
-        hp.sampler_init(cfgp, x0p, 1. / N_DIM**0.25, np.ones(N_DIM), x0p)
-        rp = hp.sampler_run('NUTS', 200, out_ptrs={})
-        msn = hp.last_kernel_ms()
+        ttp = bfb.sample(denp, dict(n_chain=C, n_iter=200, n_warmup=100, x_0=pd_['x_0'][:C], random_generator=SEED), verbose=False,
+                         fields=('tree_depth',))
         extras['pipeline_kernel'] = dict(
-            workload='des_y1_shaped_pipeline_n26_m457_gaussian_likelihood', algorithmic_flops_per_evaluation=fl,
-            eval=dict(kernel='lik_eval_dmma_kernel' if hp.eval_last_path() == 'lik_dmma' else hp.eval_last_path(), points=Cp, ms=msp,
-                      points_per_s=Cp / msp * 1e3, roofline=dict(bound='tensor', achieved=fl * Cp / msp / 1e9, peak=peak,
-                                                                 unit='TFLOP/s', frac=fl * Cp / msp / 1e9 / peak)),
-            nuts=dict(kernel='nuts_%s_kernel' % hp.sampler_last_path(), chains_per_gpu=C, iterations=200, kernel_ms=msn,
-                      value=rp['total_tree_size'] / msn * 1e3, unit='leapfrog-steps*chains/s',
-                      roofline_frac=fl * rp['total_tree_size'] / msn / 1e9 / peak))
-        hp.close()
-        del Xp, lpp, gp
+            workload='des_y1_example_shape_n27_m457_shared_9d_mask_hard_bounds_prior_bound', features=Pf, algorithmic_flops_per_evaluation=fl_min,
+            flops_note='minimal: 4 m P_f (value GEMM + gradient GEMM over the features); one n x n product per output would be m (2 n^2 + 5 n) = %d' % (mp_ * (2 * np_ * np_ + 5 * np_)),
+            eval=dict(kernel={'lik_feat': 'likf_eval_dmma_kernel', 'lik_dmma': 'lik_eval_dmma_kernel'}.get(hp.eval_last_path(), hp.eval_last_path()),
+                      points=Cp, ms=msp, points_per_s=Cp / msp * 1e3,
+                      roofline=dict(bound='tensor', achieved=fl_min * Cp / msp / 1e9, peak=peak, unit='TFLOP/s', frac=fl_min * Cp / msp / 1e9 / peak)),
+            nuts=dict(kernel='nuts_%s_kernel' % hp.sampler_last_path(), chains_per_gpu=C, iterations=200, kernel_ms=ttp.kernel_ms,
+                      value=ttp.total_tree_size / ttp.kernel_ms * 1e3, unit='leapfrog-steps*chains/s',
+                      roofline_frac=fl_min * ttp.total_tree_size / ttp.kernel_ms / 1e9 / peak, mean_tree_depth=float(ttp.arrays['tree_depth'].mean())))
+        del Xp, lpp, gp, ttp
     except Exception as exc:                                   # supplementary measurement: never fails the bench line
         extras['pipeline_kernel'] = dict(error=repr(exc))
 
