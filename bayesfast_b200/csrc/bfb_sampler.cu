@@ -22,6 +22,7 @@ int bfb_launch_nuts_dmma(bfb_context *h, const bfb_run_out &o, int n_iter);   //
 int bfb_launch_hmc_dmma(bfb_context *h, const bfb_run_out &o, int n_iter);    // bfb_sampler_dmma.cu
 int bfb_launch_nuts_team(bfb_context *h, const bfb_run_out &o, int n_iter);   // bfb_sampler_team.cu
 int bfb_launch_hmc_team(bfb_context *h, const bfb_run_out &o, int n_iter);    // bfb_sampler_team.cu
+int bfb_launch_nuts_pair(bfb_context *h, const bfb_run_out &o, int n_iter);   // bfb_sampler_pair.cu
 
 struct RunOutDev {
     bfb_run_out o;
@@ -817,6 +818,10 @@ static int launch_run(bfb_context *h, int sampler, int n_iter, const bfb_run_out
         fast_rc = bfb_launch_nuts_team(h, od.o, n_iter);
         if (fast_rc == 0) h->last_path = 3;
         if (fast_rc == 1) {
+            fast_rc = bfb_launch_nuts_pair(h, od.o, n_iter);
+            if (fast_rc == 0) h->last_path = 4;
+        }
+        if (fast_rc == 1) {
             fast_rc = bfb_launch_nuts_dmma(h, od.o, n_iter);
             if (fast_rc == 0) h->last_path = 2;
         }
@@ -1068,6 +1073,11 @@ extern "C" int bfb_sampler_run_ex(bfb_handle h, int sampler, int32_t n_iter, con
             fprintf(stderr, "[bfb200] team kernel, leader-warp cycles per round: apply %.0f boundary %.0f leapfrog+eval %.0f owners %.0f tasks+leaf %.0f decisions %.0f command-barrier %.0f\n",
                     (double)dbg[4] / dbg[1], (double)dbg[5] / dbg[1], (double)dbg[6] / dbg[1], (double)dbg[7] / dbg[1],
                     (double)dbg[8] / dbg[1], (double)dbg[9] / dbg[1], (double)dbg[10] / dbg[1]);
+        else if (dbg[1] && h->last_path == 4)
+            fprintf(stderr, "[bfb200] pair kernel, tree warp cycles per round: boundary %.0f rng+dbl %.0f wait-for-leaves %.0f leaf-pair %.0f merges %.0f push %.0f extend %.0f hand-over %.0f | integrator (%llu rounds): wait-unit %.0f wait-tree %.0f compute %.0f\n",
+                    (double)dbg[4] / dbg[1], (double)dbg[5] / dbg[1], (double)dbg[6] / dbg[1], (double)dbg[7] / dbg[1],
+                    (double)dbg[8] / dbg[1], (double)dbg[9] / dbg[1], (double)dbg[10] / dbg[1], (double)dbg[11] / dbg[1], dbg[12],
+                    (double)dbg[13] / (dbg[12] ? dbg[12] : 1), (double)dbg[14] / (dbg[12] ? dbg[12] : 1), (double)dbg[15] / (dbg[12] ? dbg[12] : 1));
         else if (dbg[1]) fprintf(stderr, "[bfb200] cycles per warp-round: boundary %.0f rng+dbl %.0f (unused) %.0f leaf-pair %.0f merges %.0f push %.0f extend %.0f | unit setup+teardown per round %.0f\n",
                             (double)dbg[4] / dbg[1], (double)dbg[5] / dbg[1], (double)dbg[6] / dbg[1], (double)dbg[7] / dbg[1],
                             (double)dbg[8] / dbg[1], (double)dbg[9] / dbg[1], (double)dbg[10] / dbg[1], (double)dbg[11] / dbg[1]);
