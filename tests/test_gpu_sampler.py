@@ -271,10 +271,10 @@ def test_work_queue_chunking_is_invisible(handle, monkeypatch):
     (26, 'cubic-2', 203, 40, {'BFB200_TEAMS_PER_SM': '3', 'BFB200_STACK_LEVELS_SMEM': '0'}),
     (16, 'quadratic', 33, 40, {'BFB200_TEAMS_PER_SM': '5', 'BFB200_CHUNK_ITERS': '9'}),
 ])
-@pytest.mark.parametrize('family', ['team', 'dmma'])
+@pytest.mark.parametrize('family', ['team', 'dmma', 'pair'])
 def test_tensor_core_nuts_vs_oracle(handle, oracle, monkeypatch, n, order, C, n_iter, env, family):
-    """bfb_sampler_team.cu (8 chains per team of four warps) / bfb_sampler_dmma.cu (8 chains per warp), the chains as the rows
-    of FP64 DMMAs: per-chain tree depths / sizes / divergences and draw counts identical to the oracle fed with the device's
+    """bfb_sampler_team.cu (8 chains per team of four warps) / bfb_sampler_dmma.cu (8 chains per warp) / bfb_sampler_pair.cu
+    (integrator warp + tree warp per 8 chains, speculative trajectory), the chains as the rows of FP64 DMMAs: per-chain tree depths / sizes / divergences and draw counts identical to the oracle fed with the device's
     own draws, and to the generic warp-per-chain kernel"""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
@@ -314,7 +314,7 @@ def test_tensor_core_nuts_vs_oracle(handle, oracle, monkeypatch, n, order, C, n_
         assert np.array_equal(out[k], gen[k]), k
 
 
-@pytest.mark.parametrize('family', ['team', 'dmma'])
+@pytest.mark.parametrize('family', ['team', 'dmma', 'pair'])
 def test_tensor_core_nuts_resume_and_reset(handle, monkeypatch, family):
     """chain state survives between launches (bfb_sampler_run called twice == once), and bfb_sampler_reset restarts it"""
     monkeypatch.setenv('BFB200_SAMPLER', family)
@@ -415,7 +415,7 @@ def test_tensor_core_extended_density(handle, oracle, monkeypatch, n, order, sam
     assert np.array_equal(out['tree_depth'], gen['tree_depth']) and np.array_equal(out['diverging'], gen['diverging'])
 
 
-@pytest.mark.parametrize('family', ['team', 'dmma'])
+@pytest.mark.parametrize('family', ['team', 'dmma', 'pair'])
 @pytest.mark.parametrize('env', [{}, {'BFB200_STACK_LEVELS_SMEM': '2'}])
 def test_tensor_core_nuts_deep_trees(handle, oracle, monkeypatch, env, family):
     """tiny fixed step size: trees reach depth 8-10 (up to 1023 leaves), i.e. every stack level, the L2-resident deep
