@@ -41,6 +41,21 @@ def _out_plan(trace, i_iter, n_run, keep, thin):
     return skip, thin
 
 
+
+def sobol_multivariate_normal(dim, size, skip=1):
+    """bayesfast.utils.sobol.multivariate_normal(zeros(dim), eye(dim), size) (utils/sobol.py:48-60, utils/_sobol.pyx): the first
+    `size` points after `skip` of the Joe-Kuo Sobol sequence (Gray-code order, direction numbers new-joe-kuo-6.21201), mapped through
+    the normal quantile function.  scipy's unscrambled qmc.Sobol uses the same direction numbers and order: identical to the
+    reference's Cython generator bit for bit (tests/golden/sobol_x0.npz)."""
+    from scipy.stats import qmc, norm
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')                # scipy warns when size + skip is not a power of two
+        pts = qmc.Sobol(int(dim), scramble=False).random(int(size) + int(skip))[int(skip):]
+    a, w = np.linalg.eigh(np.eye(int(dim)))            # the reference's eigen-decomposition of the (identity) covariance
+    return (norm.ppf(pts) * a**0.5) @ w.T
+
+
 def sample(density, sample_trace=None, sampler='NUTS', n_run=None, parallel_backend='b200', verbose=True,
            comm=None, fields=None, keep='all', thin=1, summaries=False):
     """
@@ -97,8 +112,7 @@ def sample(density, sample_trace=None, sampler='NUTS', n_run=None, parallel_back
     hostrng = np.random.default_rng(seed)
     C = trace.n_chain
     if trace.x_0 is None:
-        # the reference seeds x_0 with Sobol multivariate-normal points (sample.py:107-112); plain normals here
-        x0 = hostrng.normal(size=(C, n))
+        x0 = sobol_multivariate_normal(n, C)           # sample.py:107-112: Sobol points through Phi^-1, identity covariance
         trace._x_0_transformed = True
     else:
         x0 = np.asarray(trace.x_0, dtype=np.float64).reshape((-1, trace.x_0.shape[-1]))

@@ -1,24 +1,25 @@
 """Turn the raw ncu artefacts of a gpurun call (gpurun_out/) into the tracked summaries under profiles/.
-usage: python scripts/summarize_profiles.py <tag> <launches.csv> <name=report.ncu-rep> ..."""
+usage: python scripts/summarize_profiles.py <tag> <launches.csv | -> <name=report.ncu-rep> ..."""
 import csv, io, json, os, subprocess, sys, collections, shutil
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag, launches = sys.argv[1], sys.argv[2]
 out_dir = os.path.join(ROOT, 'profiles')
 UNIT = {'Mbyte': 1e6, 'Gbyte': 1e9, 'Kbyte': 1e3, 'byte': 1., 'Tbyte': 1e12}
 
-rows = [r for r in csv.reader(open(launches)) if len(r) > 10 and r[0].isdigit()]
+rows = [] if launches == '-' else [r for r in csv.reader(open(launches)) if len(r) > 10 and r[0].isdigit()]
 per = collections.OrderedDict()
 for r in rows:
     name = r[4].split('(')[0].replace('void ', '')
     per.setdefault(name, []).append(float(r[-1]))
 tot = sum(sum(v) for v in per.values())
-with open(os.path.join(out_dir, tag + '_launches_summary.md'), 'w') as f:
-    f.write('# ncu launch list (gpu__time_duration.sum, --clock-control none): `python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-extras`\n')
-    f.write('per-launch times are cold-cache and serialised; what must agree with bench.py is each kernel\'s SHARE\n\n')
-    f.write('| kernel | launches | total ms | mean ms | share |\n|---|---|---|---|---|\n')
-    for k, v in sorted(per.items(), key=lambda kv: -sum(kv[1])):
-        f.write('| {} | {} | {:.3f} | {:.4f} | {:.2%} |\n'.format(k, len(v), sum(v) / 1e6, sum(v) / len(v) / 1e6, sum(v) / tot))
-shutil.copy(launches, os.path.join(out_dir, tag + '_launches.csv'))
+if rows:
+  with open(os.path.join(out_dir, tag + '_launches_summary.md'), 'w') as f:
+      f.write('# ncu launch list (gpu__time_duration.sum, --clock-control none): `python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-extras`\n')
+      f.write('per-launch times are cold-cache and serialised; what must agree with bench.py is each kernel\'s SHARE\n\n')
+      f.write('| kernel | launches | total ms | mean ms | share |\n|---|---|---|---|---|\n')
+      for k, v in sorted(per.items(), key=lambda kv: -sum(kv[1])):
+          f.write('| {} | {} | {:.3f} | {:.4f} | {:.2%} |\n'.format(k, len(v), sum(v) / 1e6, sum(v) / len(v) / 1e6, sum(v) / tot))
+  shutil.copy(launches, os.path.join(out_dir, tag + '_launches.csv'))
 
 WANT = ['gpu__time_duration.sum', 'launch__grid_size', 'launch__block_size', 'launch__registers_per_thread',
         'launch__waves_per_multiprocessor', 'smsp__inst_executed.sum',
@@ -28,7 +29,7 @@ WANT = ['gpu__time_duration.sum', 'launch__grid_size', 'launch__block_size', 'la
         'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
         'l1tex__t_sector_hit_rate.pct', 'lts__t_sector_hit_rate.pct', 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum',
         'smsp__sass_inst_executed_op_global_ld.sum', 'smsp__sass_inst_executed_op_shared_ld.sum',
-        'sass__inst_executed_local_loads', 'sass__inst_executed_local_stores']
+        'sass__inst_executed_local_loads', 'sass__inst_executed_local_stores', 'sm__icc_request_hit_rate.pct', 'sm__icc_requests.sum']
 traffic = {}
 for spec in sys.argv[3:]:
     name, rep = spec.split('=')

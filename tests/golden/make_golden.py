@@ -660,6 +660,15 @@ def make_post():
     gio.save('post.npz', dict(cases=cases, logp=logp, logq=logq, k_trunc=0.25, weights=weights, weights_trunc=wt))
 
 
+def make_sobol_x0():
+    """default x_0 of bayesfast.sample (core/sample.py:107-112): utils.sobol.multivariate_normal of the real reference"""
+    from bayesfast.utils.sobol import multivariate_normal
+    out = {}
+    for d, n in ((2, 4), (26, 37), (64, 50)):
+        out['d%d_n%d' % (d, n)] = multivariate_normal(np.zeros(d), np.eye(d), n)
+    np.savez_compressed(os.path.join(gio.GOLDEN_DIR, 'sobol_x0.npz'), **out)
+
+
 if __name__ == '__main__':
     which = sys.argv[1:] or ['poly_kat', 'poly_eval', 'density', 'fit', 'sampler', 'sampler_dense', 'pipeline']
     if 'poly_kat' in which:
@@ -680,6 +689,8 @@ if __name__ == '__main__':
         make_pipeline_des()
     if 'post' in which:
         make_post()
+    if 'sobol_x0' in which:
+        make_sobol_x0()
     if 'sampler_dense' in which:
         make_sampler_dense()
     if 'pipeline' in which:

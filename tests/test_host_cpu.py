@@ -255,3 +255,14 @@ def test_likelihood_whitening_all_orders_and_masks(oracle):
     lp0, gr0 = oracle.OracleDensity(spec).logp_and_grad_batch(X)
     assert np.allclose(lik.const - 0.5 * np.sum(F * F, axis=1), lp0, rtol=1e-11, atol=1e-11)
     assert np.allclose(-np.einsum('co,con->cn', F, J), gr0, rtol=1e-11, atol=1e-11 * np.abs(gr0).max())
+
+
+def test_default_x0_is_the_reference_sobol_sequence():
+    """sample() without x_0 starts the chains at the reference's Sobol multivariate-normal points (core/sample.py:107-112,
+    utils/sobol.py:48-60): bit-identical to utils.sobol.multivariate_normal of the real reference (tests/golden/sobol_x0.npz)"""
+    import os
+    from bayesfast_b200.sample import sobol_multivariate_normal
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'sobol_x0.npz'))
+    for k in g.files:
+        d, n = int(k.split('_')[0][1:]), int(k.split('_')[1][1:])
+        assert np.array_equal(sobol_multivariate_normal(d, n), g[k]), k
