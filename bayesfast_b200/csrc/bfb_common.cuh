@@ -162,6 +162,16 @@ struct bfb_context {
     int last_eval_path;        // evaluator of the last bfb_logp_and_grad_batch: 0 generic, 2 tensor core, 3 tensor-core likelihood pipeline
     double *gstack;            // deep NUTS stack levels of the multi-chain kernel (L2 resident)
     size_t gstack_len;
+    // progress reporting of a single-launch run (bfb_sampler_run_ex, host outputs): the kernel counts the groups that finished
+    // iteration chunk k in progress_dev[k]; the last one writes k + 1 to *progress_host (mapped pinned memory), and the host
+    // thread starts the device-to-host copy of that chunk while the kernel goes on
+    int *progress_dev;
+    size_t progress_len;
+    int *progress_host;        // host address of the flag; progress_host_dev = the same word as seen from the device
+    int *progress_host_dev;
+    int progress_arm;          // > 0: the next NUTS launch should report progress in about this many chunks
+    int progress_chunk_iters;  // set by the launcher that honoured the request (0: not honoured)
+    int progress_n_chunks;
     // fit
     FitState *fit;
 };

@@ -875,6 +875,96 @@ static int launch_run(bfb_context *h, int sampler, int n_iter, const bfb_run_out
 // byte size of one (chain, iteration) record of output field f (order of bfb_run_out)
 static size_t field_bytes(int f, int n) { return f == 0 ? sizeof(double) * n : (f <= 7 ? sizeof(double) : sizeof(int32_t)); }
 
+static int launch_run(bfb_context *h, int sampler, int n_iter, const bfb_run_out &dev_out);
+
+// Host outputs from ONE launch (the tensor-core NUTS kernel reports progress; anything else returns 1 before launching and the
+// caller falls back to the chunked launches): device buffer [C, R(, n)] per field, the host thread polls the progress word the
+// kernel writes into mapped pinned memory and queues the strided copy of every finished chunk on the copy stream.
+// Returns BFB_OK when the run was done (ev1 recorded, copies complete), 1 when this path does not apply, < 0 on error.
+static int single_launch_host_outputs(bfb_context *h, int sampler, int R, void *const user[11], int n_keep)
+{
+    const DevModel &M = h->dm;
+    // only nuts_dmma_kernel reports progress: the same conditions as bfb_launch_nuts_dmma, default kernel selection
+    if (getenv("BFB200_SAMPLER") || getenv("BFB200_FORCE_GENERIC") || getenv("BFB200_CHAINS_PER_GROUP")) return 1;
+    if (M.epilogue || M.frag_nr == 0 || M.has_c3 || h->scfg.max_treedepth > 10) return 1;
+    const int64_t C = h->cs.C;
+    const int n = h->n;
+    size_t rec = 0;
+    for (int f = 0; f < 11; ++f) if (user[f]) rec += field_bytes(f, n);
+    if (rec == 0) return 1;
+    const size_t need = rec * (size_t)C * (size_t)R;
+    if (!h->copy_stream) {
+        BFB_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < BFB_NSTAGE; ++i) { BFB_CUDA(cudaEventCreateWithFlags(&h->ev_k[i], cudaEventDisableTiming));
+                                               BFB_CUDA(cudaEventCreateWithFlags(&h->ev_c[i], cudaEventDisableTiming)); }
+    }
+    if (h->stage_len[0] < need) {
+        if (h->stage[0]) cudaFree(h->stage[0]);
+        h->stage[0] = nullptr; h->stage_len[0] = 0;
+        if (cudaMalloc(&h->stage[0], need) != cudaSuccess) { cudaGetLastError(); return 1; }     // does not fit: chunked launches
+        h->stage_len[0] = need;
+    }
+    if (!h->progress_host) {
+        BFB_CUDA(cudaHostAlloc((void **)&h->progress_host, 64, cudaHostAllocMapped));
+        BFB_CUDA(cudaHostGetDevicePointer((void **)&h->progress_host_dev, h->progress_host, 0));
+    }
+    void *dptr[11];
+    char *base = (char *)h->stage[0];
+    for (int f = 0; f < 11; ++f) {
+        dptr[f] = nullptr;
+        if (user[f]) { dptr[f] = base; base += field_bytes(f, n) * (size_t)C * (size_t)R; }
+    }
+    bfb_run_out dev = {(double *)dptr[0], (double *)dptr[1], (double *)dptr[2], (double *)dptr[3], (double *)dptr[4],
+                       (double *)dptr[5], (double *)dptr[6], (double *)dptr[7], (int32_t *)dptr[8],
+                       (int32_t *)dptr[9], (int32_t *)dptr[10]};
+    volatile int *flag = h->progress_host;
+    *flag = 0;
+    int want = 16;
+    if (const char *e = getenv("BFB200_E2E_CHUNKS")) { int v = atoi(e); if (v >= 1) want = v; }
+    h->progress_arm = want; h->progress_chunk_iters = 0; h->progress_n_chunks = 0;
+    int rc = launch_run(h, sampler, R, dev);
+    h->progress_arm = 0;
+    if (rc) return rc;
+    h->iters_done += R;
+    BFB_CUDA(cudaEventRecord(h->ev1, h->stream));
+    auto copy_range = [&](int it_begin, int its) -> int {
+        for (int f = 0; f < 11; ++f) {
+            if (!user[f]) continue;
+            const size_t fb = field_bytes(f, n);
+            BFB_CUDA(cudaMemcpy2DAsync((char *)user[f] + fb * (size_t)it_begin, fb * (size_t)n_keep, (char *)dptr[f] + fb * (size_t)it_begin,
+                                       fb * (size_t)R, fb * (size_t)its, (size_t)C, cudaMemcpyDeviceToHost, h->copy_stream));
+        }
+        return BFB_OK;
+    };
+    if (h->last_path != 2 || h->progress_chunk_iters == 0) {
+        // another kernel family took the launch: no progress reports, one copy after the kernel
+        BFB_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev1, 0));
+        if ((rc = copy_range(0, R))) return rc;
+        BFB_CUDA(cudaStreamSynchronize(h->copy_stream));
+        return BFB_OK;
+    }
+    const int K = h->progress_chunk_iters, nch = h->progress_n_chunks;
+    int copied = 0;                                  // chunks whose copies are queued
+    unsigned spins = 0;
+    while (copied < nch) {
+        int seen = *flag;
+        if (seen <= copied) {
+            if ((++spins & 0x3ff) == 0) {
+                const cudaError_t q = cudaStreamQuery(h->stream);     // the kernel ended (or failed) without the last report?
+                if (q == cudaSuccess) seen = (*flag > copied) ? *flag : nch;
+                else if (q != cudaErrorNotReady) { bfb_set_error("bfb_sampler_run_ex: %s", cudaGetErrorString(q)); return BFB_ERR_CUDA; }
+            }
+            if (seen <= copied) continue;
+        }
+        const int it_begin = copied * K, it_end = (seen * K < R) ? seen * K : R;
+        if ((rc = copy_range(it_begin, it_end - it_begin))) return rc;
+        copied = seen;
+    }
+    BFB_CUDA(cudaStreamSynchronize(h->stream));
+    BFB_CUDA(cudaStreamSynchronize(h->copy_stream));
+    return BFB_OK;
+}
+
 // ---- reduced outputs (bfb_sampler_run_ex): thinning and summaries on the device ----
 // dst[c][i] = src[c][i * thin] for records of `rec` doubles (samples: n) or of one 4-byte / 8-byte word
 template <class T>
@@ -957,11 +1047,19 @@ extern "C" int bfb_sampler_run_ex(bfb_handle h, int sampler, int32_t n_iter, con
     }
     const int R = n_iter - skip;            // iterations with records
     const int n_keep = (R + thin - 1) / thin;
+    int single_rc = 1;
+    if (R >= 64 && loc == BFB_HOST && sampler == BFB_NUTS && !h->dense_metric && thin == 1 && !want_mom && !getenv("BFB200_E2E_MULTI_LAUNCH")) {
+        single_rc = single_launch_host_outputs(h, sampler, R, user, n_keep);
+        if (single_rc < 0) return single_rc;
+    }
     if (R == 0) {
     } else if (loc == BFB_DEVICE) {
         int rc = launch_run(h, sampler, R, *out);
         if (rc) return rc;
         h->iters_done += R;
+    } else if (single_rc == BFB_OK) {
+        // done: ONE launch for all R iterations into a device buffer laid out like the caller's arrays; the kernel reported every
+        // finished chunk of iterations and the host copied it out while the kernel went on (no launch boundaries, no tails)
     } else {
         // Host outputs: the run is cut into chunks of iterations; chunk k's kernel writes a device staging buffer while
         // chunk k-1 is copied to the caller's arrays on a second stream (strided 2-D copies: the host layout is

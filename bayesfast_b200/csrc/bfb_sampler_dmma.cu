@@ -49,7 +49,8 @@ template <int NR, int MV, int W>
 __global__ void __launch_bounds__(32 * W, 1) nuts_dmma_kernel(DevModel M, bfb_sampler_cfg cfg, ChainState st, RunOutDevF out,
                                                               int L, int LS, double *__restrict__ gstack,
                                                               double *__restrict__ gprop, int base_iter, int chunk_iters,
-                                                              int n_groups, int n_units, int *__restrict__ queue, int cpg)
+                                                              int n_groups, int n_units, int *__restrict__ queue, int cpg,
+                                                              int *__restrict__ progress, int *progress_flag)
 {
     using SH = DmmaShape<NR, MV>;
     constexpr int SLOT = NR * 32;
@@ -548,6 +549,14 @@ __global__ void __launch_bounds__(32 * W, 1) nuts_dmma_kernel(DevModel M, bfb_sa
         atomicAdd(st.tree_total + 11, (unsigned long long)(clock64() - t_unit0 - tsum));
 #endif
         qv[2 + group] = chunk + 1;
+        if (progress) {
+            // the records of iterations [chunk * chunk_iters, ...) of this group are complete (fenced above); the last group to
+            // get here tells the host, which then copies the chunk out while the kernel goes on (bfb_sampler_run_ex)
+            if (atomicAdd(progress + chunk, 1) == n_groups - 1) {
+                *(volatile int *)progress_flag = chunk + 1;
+                __threadfence_system();
+            }
+        }
         if ((chunk + 1) * chunk_iters < out.n_iter) {
             const int ti = atomicAdd(queue + 1, 1);
             __threadfence();
@@ -910,6 +919,11 @@ static int launch_dmma(bfb_context *h, const bfb_run_out &o, int n_iter, int cpg
     int chunk_iters = (n_iter + 5) / 6;
     if (chunk_iters < 16) chunk_iters = n_iter < 16 ? n_iter : 16;
     if (const char *e = getenv("BFB200_CHUNK_ITERS")) { int v = atoi(e); if (v >= 1) chunk_iters = v; }
+    const bool report = h->progress_arm > 0;
+    if (report) {                                  // finer units: the host copies a chunk out as soon as every group finished it
+        chunk_iters = (n_iter + h->progress_arm - 1) / h->progress_arm;
+        if (chunk_iters < 8) chunk_iters = n_iter < 8 ? n_iter : 8;
+    }
     const int n_chunks = (n_iter + chunk_iters - 1) / chunk_iters;
     const int64_t n_units64 = (int64_t)n_groups * n_chunks;
     BFB_REQUIRE(n_units64 < (1ll << 31), BFB_ERR_ARG, "too many work units");
@@ -920,6 +934,18 @@ static int launch_dmma(bfb_context *h, const bfb_run_out &o, int n_iter, int cpg
         BFB_CUDA(cudaMalloc((void **)&h->queue, sizeof(int) * qlen));
         h->queue_len = qlen;
     }
+    int *progress = nullptr;
+    if (report) {
+        if ((size_t)n_chunks > h->progress_len) {
+            if (h->progress_dev) cudaFree(h->progress_dev);
+            h->progress_dev = nullptr; h->progress_len = 0;
+            BFB_CUDA(cudaMalloc((void **)&h->progress_dev, sizeof(int) * (size_t)n_chunks));
+            h->progress_len = (size_t)n_chunks;
+        }
+        BFB_CUDA(cudaMemsetAsync(h->progress_dev, 0, sizeof(int) * (size_t)n_chunks, h->stream));
+        progress = h->progress_dev;
+        h->progress_chunk_iters = chunk_iters; h->progress_n_chunks = n_chunks;
+    }
     // one block per SM whenever there are at least as many groups as SMs: with 512 groups (4096 chains) every SM then runs 3 or
     // 4 warps instead of 128 SMs running 4 and 20 none
     int blocks = h->sm_count;
@@ -928,7 +954,8 @@ static int launch_dmma(bfb_context *h, const bfb_run_out &o, int n_iter, int cpg
     h->launches++;
     nuts_dmma_kernel<NR, MV, W><<<blocks, 32 * W, smem, h->stream>>>(h->dm, h->scfg, h->cs, od, L, LS, h->gstack,
                                                                     h->gstack + deep * (size_t)n_groups, (int)h->iters_done,
-                                                                    chunk_iters, n_groups, (int)n_units64, h->queue, cpg);
+                                                                    chunk_iters, n_groups, (int)n_units64, h->queue, cpg,
+                                                                    progress, h->progress_host_dev);
     h->launches++;
     BFB_CUDA(cudaGetLastError());
     return BFB_OK;

@@ -242,6 +242,35 @@ def test_sample_reduced_outputs():
         bfb.sample(den, b, n_run=5, verbose=False)
 
 
+def test_single_launch_host_outputs_match_chunked_launches(handle, monkeypatch):
+    """bfb_sampler_run_ex with host outputs: ONE launch whose finished iteration chunks the host copies out while the kernel goes on
+    (progress word in mapped pinned memory) against the chunked launches through staging buffers -- same records, bit for bit,
+    for full and post-warm-up outputs, ragged chunk counts and a field subset"""
+    n, C, n_iter = 26, 203, 150
+    spec, cov = synthetic_spec(n, 'cubic-2', seed=21)
+    handle.set_model(to_device_spec(spec))
+    x0 = (np.linalg.cholesky(cov) @ np.random.default_rng(9).normal(size=(n, C))).T
+    cfg = cfg_from({}, 60, 17)
+    runs = {}
+    for name, env, kw in (('multi', {'BFB200_E2E_MULTI_LAUNCH': '1'}, {}), ('single', {}, {}), ('single7', {'BFB200_E2E_CHUNKS': '7'}, {}),
+                          ('multi_post', {'BFB200_E2E_MULTI_LAUNCH': '1'}, dict(skip=60)), ('single_post', {'BFB200_E2E_CHUNKS': '100'}, dict(skip=60)),
+                          ('single_sub', {}, dict(fields=('samples', 'tree_depth')))):
+        for k in ('BFB200_E2E_MULTI_LAUNCH', 'BFB200_E2E_CHUNKS'):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        handle.sampler_init(cfg, x0, 1. / n**0.25, np.ones(n), x0)
+        runs[name] = handle.sampler_run('NUTS', n_iter, **kw)
+        assert handle.sampler_last_path() == 'dmma'
+        assert np.all(handle.sampler_state()['status'] == 0)
+    for a, b in (('single', 'multi'), ('single7', 'multi'), ('single_post', 'multi_post')):
+        for k, v in runs[b].items():
+            assert np.array_equal(np.asarray(runs[a][k]), np.asarray(v)), (a, k)
+    for k in ('samples', 'tree_depth'):
+        assert np.array_equal(runs['single_sub'][k], runs['multi'][k]), k
+    assert np.array_equal(runs['single_post']['samples'], runs['multi']['samples'][:, 60:])
+
+
 def test_work_queue_chunking_is_invisible(handle, monkeypatch):
     """the fast path cuts a launch into (chain-group, iteration-chunk) work units handed out by an atomic queue;
     results must not depend on the chunk length (chain state is carried through global memory between units)"""
