@@ -163,10 +163,8 @@ struct bfb_context {
     double *gstack;            // deep NUTS stack levels of the multi-chain kernel (L2 resident)
     size_t gstack_len;
     // progress reporting of a single-launch run (bfb_sampler_run_ex, host outputs): the kernel counts the groups that finished
-    // iteration chunk k in progress_dev[k]; the last one writes k + 1 to *progress_host (mapped pinned memory), and the host
-    // thread starts the device-to-host copy of that chunk while the kernel goes on
-    int *progress_dev;
-    size_t progress_len;
+    // iteration chunk k in a block behind its work queue; the last one writes k + 1 to *progress_host (mapped pinned memory), and
+    // the host thread starts the device-to-host copy of that chunk while the kernel goes on
     int *progress_host;        // host address of the flag; progress_host_dev = the same word as seen from the device
     int *progress_host_dev;
     int progress_arm;          // > 0: the next NUTS launch should report progress in about this many chunks

@@ -65,7 +65,7 @@ extern "C" int bfb_create(int device, bfb_handle *out)
     h->fit = nullptr;
     h->gstack = nullptr;
     h->gstack_len = 0;
-    h->progress_dev = nullptr; h->progress_len = 0; h->progress_host = nullptr; h->progress_host_dev = nullptr;
+    h->progress_host = nullptr; h->progress_host_dev = nullptr;
     h->progress_arm = 0; h->progress_chunk_iters = 0; h->progress_n_chunks = 0;
     h->copy_stream = nullptr;
     h->queue = nullptr;
@@ -97,7 +97,6 @@ extern "C" int bfb_destroy(bfb_handle h)
     bfb_fit_free(h);
     if (h->gstack) cudaFree(h->gstack);
     if (h->queue) cudaFree(h->queue);
-    if (h->progress_dev) cudaFree(h->progress_dev);
     if (h->progress_host) cudaFreeHost(h->progress_host);
     for (int i = 0; i < BFB_NSTAGE; ++i) if (h->stage[i]) cudaFree(h->stage[i]);
     if (h->copy_stream) {

@@ -49,8 +49,7 @@ template <int NR, int MV, int W>
 __global__ void __launch_bounds__(32 * W, 1) nuts_dmma_kernel(DevModel M, bfb_sampler_cfg cfg, ChainState st, RunOutDevF out,
                                                               int L, int LS, double *__restrict__ gstack,
                                                               double *__restrict__ gprop, int base_iter, int chunk_iters,
-                                                              int n_groups, int n_units, int *__restrict__ queue, int cpg,
-                                                              int *__restrict__ progress, int *progress_flag)
+                                                              int n_groups, int n_units, int *__restrict__ queue, int cpg)
 {
     using SH = DmmaShape<NR, MV>;
     constexpr int SLOT = NR * 32;
@@ -549,12 +548,17 @@ __global__ void __launch_bounds__(32 * W, 1) nuts_dmma_kernel(DevModel M, bfb_sa
         atomicAdd(st.tree_total + 11, (unsigned long long)(clock64() - t_unit0 - tsum));
 #endif
         qv[2 + group] = chunk + 1;
-        if (progress) {
-            // the records of iterations [chunk * chunk_iters, ...) of this group are complete (fenced above); the last group to
-            // get here tells the host, which then copies the chunk out while the kernel goes on (bfb_sampler_run_ex)
-            if (atomicAdd(progress + chunk, 1) == n_groups - 1) {
-                *(volatile int *)progress_flag = chunk + 1;
-                __threadfence_system();
+        {
+            // progress block behind the ring: [0] armed, [1..2] address of the host's progress word, [4 + k] groups that finished
+            // chunk k.  The records of iterations [chunk * chunk_iters, ...) of this group are complete (fenced above); the last
+            // group to get here tells the host, which then copies the chunk out while the kernel goes on (bfb_sampler_run_ex)
+            int *pg = queue + 2 + n_groups + n_units;
+            if (qv[2 + n_groups + n_units]) {
+                if (atomicAdd(pg + 4 + chunk, 1) == n_groups - 1) {
+                    int *flag = reinterpret_cast<int *>(((unsigned long long)(unsigned)pg[2] << 32) | (unsigned long long)(unsigned)pg[1]);
+                    *(volatile int *)flag = chunk + 1;
+                    __threadfence_system();
+                }
             }
         }
         if ((chunk + 1) * chunk_iters < out.n_iter) {
@@ -927,24 +931,23 @@ static int launch_dmma(bfb_context *h, const bfb_run_out &o, int n_iter, int cpg
     const int n_chunks = (n_iter + chunk_iters - 1) / chunk_iters;
     const int64_t n_units64 = (int64_t)n_groups * n_chunks;
     BFB_REQUIRE(n_units64 < (1ll << 31), BFB_ERR_ARG, "too many work units");
-    const size_t qlen = 2 + (size_t)n_groups + (size_t)n_units64;
+    // work queue, then the progress block (see the end of the kernel's unit loop): 4 + n_chunks ints
+    const size_t qlen = 2 + (size_t)n_groups + (size_t)n_units64 + 4 + (size_t)n_chunks;
     if (qlen > h->queue_len) {
         if (h->queue) cudaFree(h->queue);
         h->queue = nullptr; h->queue_len = 0;
         BFB_CUDA(cudaMalloc((void **)&h->queue, sizeof(int) * qlen));
         h->queue_len = qlen;
     }
-    int *progress = nullptr;
-    if (report) {
-        if ((size_t)n_chunks > h->progress_len) {
-            if (h->progress_dev) cudaFree(h->progress_dev);
-            h->progress_dev = nullptr; h->progress_len = 0;
-            BFB_CUDA(cudaMalloc((void **)&h->progress_dev, sizeof(int) * (size_t)n_chunks));
-            h->progress_len = (size_t)n_chunks;
+    {
+        int *pg = h->queue + 2 + (size_t)n_groups + (size_t)n_units64;
+        BFB_CUDA(cudaMemsetAsync(pg, 0, sizeof(int) * (4 + (size_t)n_chunks), h->stream));
+        if (report) {
+            const unsigned long long fa = (unsigned long long)h->progress_host_dev;
+            const int hdr[3] = {1, (int)(unsigned)(fa & 0xffffffffull), (int)(unsigned)(fa >> 32)};
+            BFB_CUDA(cudaMemcpyAsync(pg, hdr, sizeof(hdr), cudaMemcpyHostToDevice, h->stream));
+            h->progress_chunk_iters = chunk_iters; h->progress_n_chunks = n_chunks;
         }
-        BFB_CUDA(cudaMemsetAsync(h->progress_dev, 0, sizeof(int) * (size_t)n_chunks, h->stream));
-        progress = h->progress_dev;
-        h->progress_chunk_iters = chunk_iters; h->progress_n_chunks = n_chunks;
     }
     // one block per SM whenever there are at least as many groups as SMs: with 512 groups (4096 chains) every SM then runs 3 or
     // 4 warps instead of 128 SMs running 4 and 20 none
@@ -954,8 +957,7 @@ static int launch_dmma(bfb_context *h, const bfb_run_out &o, int n_iter, int cpg
     h->launches++;
     nuts_dmma_kernel<NR, MV, W><<<blocks, 32 * W, smem, h->stream>>>(h->dm, h->scfg, h->cs, od, L, LS, h->gstack,
                                                                     h->gstack + deep * (size_t)n_groups, (int)h->iters_done,
-                                                                    chunk_iters, n_groups, (int)n_units64, h->queue, cpg,
-                                                                    progress, h->progress_host_dev);
+                                                                    chunk_iters, n_groups, (int)n_units64, h->queue, cpg);
     h->launches++;
     BFB_CUDA(cudaGetLastError());
     return BFB_OK;

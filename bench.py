@@ -27,7 +27,7 @@ tensor cores: batched logp + gradient (bfb_lik_dmma.cu) and a 4096-chain NUTS ru
              and multiprocess chain pool (bf.sample + set_backend(cores)) on this box's host cores, full-length chains of the
              same workload; next to it `port`: the oracle (C restatement, OpenMP over chains).  `--impl reference` runs only
              the reference arm (the port when baseline/_ref is missing; the line says which).
-  extras (N = 1 unless noted): more_chains, team_kernel, hmc_kernel, eval_kernel, pipeline_kernel, config3 (64-D cubic-3),
+  extras (N = 1 unless noted): more_chains, team_kernel, pair_kernel, hmc_kernel, eval_kernel, pipeline_kernel, config3 (64-D cubic-3),
              fit_sweep (d = 32 cubic-2, N = 1e4 .. 1e7 rows; at N > 1 GPUs rows sharded + the NCCL all-reduce timed).
 """
 import argparse
@@ -236,28 +236,30 @@ def extra_measurements(args, bfb, torch, den, h, prob, x0, trace_kw, flush, peak
     except Exception as exc:                                   # supplementary measurement: never fails the bench line
         extras['pipeline_kernel'] = dict(error=repr(exc))
 
-    # (d) the four-warp team kernels (bfb_sampler_team.cu) on the headline run, kernel only: NUTS team is the alternative family
-    # (the one-warp-per-group kernel is the default: see DESIGN.md 4.1), HMC team is the default up to 4 groups per SM
-    try:
-        os.environ['BFB200_SAMPLER'] = 'team'
-        cfgt = bfb.NTrace(**trace_kw)._cfg_dict(SEED, 0)
-        h.sampler_init(cfgt, x0, 1. / N_DIM**0.25, np.ones(N_DIM), x0)
-        best = None
-        for i in range(2):
-            h.sampler_reset()
-            flush.zero_()
-            torch.cuda.synchronize(dev)
-            rt = h.sampler_run('NUTS', N_ITER, out_ptrs={})
-            mst = h.last_kernel_ms()
-            if best is None or mst < best[1]:
-                best = (rt['total_tree_size'], mst)
-        extras['team_kernel'] = dict(kernel='nuts_%s_kernel' % h.sampler_last_path(), chains_per_gpu=C, value=best[0] / best[1] * 1e3,
-                                     unit='leapfrog-steps*chains/s', kernel_ms=best[1],
-                                     roofline_frac=FLOPS_PER_LEAF * best[0] / (best[1] * 1e-3) / 1e12 / peak)
-    except Exception as exc:
-        extras['team_kernel'] = dict(error=repr(exc))
-    finally:
-        os.environ.pop('BFB200_SAMPLER', None)
+    # (d) the alternative NUTS kernel families on the headline run, kernel only (the one-warp-per-group kernel is the default: see
+    # DESIGN.md 4.1): four-warp team per group (bfb_sampler_team.cu; HMC team is the default up to 4 groups per SM), and integrator
+    # warp + tree warp per group with a speculative trajectory (bfb_sampler_pair.cu)
+    for fam in ('team', 'pair'):
+        try:
+            os.environ['BFB200_SAMPLER'] = fam
+            cfgt = bfb.NTrace(**trace_kw)._cfg_dict(SEED, 0)
+            h.sampler_init(cfgt, x0, 1. / N_DIM**0.25, np.ones(N_DIM), x0)
+            best = None
+            for i in range(2):
+                h.sampler_reset()
+                flush.zero_()
+                torch.cuda.synchronize(dev)
+                rt = h.sampler_run('NUTS', N_ITER, out_ptrs={})
+                mst = h.last_kernel_ms()
+                if best is None or mst < best[1]:
+                    best = (rt['total_tree_size'], mst)
+            extras[fam + '_kernel'] = dict(kernel='nuts_%s_kernel' % h.sampler_last_path(), chains_per_gpu=C, value=best[0] / best[1] * 1e3,
+                                           unit='leapfrog-steps*chains/s', kernel_ms=best[1],
+                                           roofline_frac=FLOPS_PER_LEAF * best[0] / (best[1] * 1e-3) / 1e12 / peak)
+        except Exception as exc:
+            extras[fam + '_kernel'] = dict(error=repr(exc))
+        finally:
+            os.environ.pop('BFB200_SAMPLER', None)
     # (e) BASELINE configs[3]: 64-D cubic-3 stack (P = 47905), NUTS with per-chain divergent tree depths
     try:
         spec3, cov3 = synthetic.cubic3_stack(64, seed=3)
@@ -569,7 +571,8 @@ def main():
                e2e=dict(value=e2e_value, unit='leapfrog-steps*chains/s', h2d_bytes_per_step=int(h2d),
                         d2h_bytes_per_step=int(d2h), ms_per_step=e2e_ms / n_e2e, kernel_ms_per_step=e2e_kernel_ms / n_e2e,
                         api="bayesfast_b200.sample(density, trace, keep='post_warmup'): samples + 10 statistics of the {} post-warm-up "
-                            "iterations of every chain to pinned host memory".format(N_ITER - N_WARMUP),
+                            "iterations of every chain to pinned host memory (one launch for the warm-up, one for the kept iterations "
+                            "whose finished chunks are copied out while it runs)".format(N_ITER - N_WARMUP),
                         numa_cpus_rank0=(len(numa_cpus) if numa_cpus else None)),
                gpu_launches=int(launches_all), roofline=roofline, clocks=summarize_clocks(samples),
                fit=dict(seconds=fit_s, seconds_warm=fit_warm_s, kernel_ms=getattr(sur, '_fit_kernel_ms', None), n=N_DIM,
