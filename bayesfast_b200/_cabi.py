@@ -341,8 +341,8 @@ class Handle:
         return float(ms.value)
 
     def sampler_last_path(self):
-        """kernel family of the last sampler run: 'generic', 'fast' (FMA multi-chain), 'dmma' (FP64 tensor core), 'team' or 'pair'"""
-        return {0: 'generic', 1: 'fast', 2: 'dmma', 3: 'team', 4: 'pair'}.get(int(self._L.bfb_sampler_last_path(self._h)), 'none')
+        """kernel family of the last sampler run: 'generic', or a tensor-core family: 'dmma' (one warp per 8 chains), 'team', 'pair'"""
+        return {0: 'generic', 2: 'dmma', 3: 'team', 4: 'pair'}.get(int(self._L.bfb_sampler_last_path(self._h)), 'none')
 
     def eval_last_path(self):
         """evaluator of the last logp_and_grad_batch: 'generic', 'dmma', 'lik_dmma' (tensor-core likelihood pipeline, one n x n

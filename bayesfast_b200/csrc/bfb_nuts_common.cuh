@@ -1,5 +1,5 @@
-// bfb_nuts_common.cuh -- pieces shared by the multi-chain-per-warp NUTS kernels (bfb_sampler_fast.cu, bfb_sampler_dmma.cu):
-// linear-domain multinomial weights, cached Philox uniforms, the run-output descriptor and the work-queue initialiser.
+// bfb_nuts_common.cuh -- pieces shared by the multi-chain-per-warp NUTS kernels (bfb_sampler_dmma.cu, bfb_sampler_team.cu,
+// bfb_sampler_pair.cu): linear-domain multinomial weights, the run-output descriptor and the work-queue initialiser.
 #pragma once
 #include "bfb_common.cuh"
 
@@ -40,23 +40,6 @@ __device__ __forceinline__ bool wt_select(double u, WT a, WT b)
     return u * a.m < b.m * pow2i(b.k - a.k);
 }
 __device__ __forceinline__ double wt_min1(WT w) { return (w.k >= 0) ? 1. : w.m * pow2i(w.k); }
-
-struct RngF {
-    uint64_t seed, chain, cached;
-    uint32_t w0, w1, w2, w3;
-};
-__device__ __forceinline__ double rng_uniform(RngF &r, int64_t t)
-{
-    const uint64_t blk = (uint64_t)t >> 1;
-    if (blk != r.cached) {
-        bfb_philox_block b = bfb_philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)r.chain,
-                                               (uint32_t)(r.chain >> 32), (uint32_t)r.seed, (uint32_t)(r.seed >> 32));
-        r.w0 = b.v[0]; r.w1 = b.v[1]; r.w2 = b.v[2]; r.w3 = b.v[3];
-        r.cached = blk;
-    }
-    const uint64_t w = (t & 1) ? ((uint64_t)r.w2 | ((uint64_t)r.w3 << 32)) : ((uint64_t)r.w0 | ((uint64_t)r.w1 << 32));
-    return bfb_u64_to_uniform(w);
-}
 
 #define BFB_NSLOT 12   // proposal slots per chain: tree proposal + one per pending subtree (<= L - 1) + the current one
 

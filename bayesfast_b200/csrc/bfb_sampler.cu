@@ -17,7 +17,6 @@
 #include <cstdio>
 #include <cstdlib>
 
-int bfb_launch_nuts_fast(bfb_context *h, const bfb_run_out &o, int n_iter);   // bfb_sampler_fast.cu
 int bfb_launch_nuts_dmma(bfb_context *h, const bfb_run_out &o, int n_iter);   // bfb_sampler_dmma.cu
 int bfb_launch_hmc_dmma(bfb_context *h, const bfb_run_out &o, int n_iter);    // bfb_sampler_dmma.cu
 int bfb_launch_nuts_team(bfb_context *h, const bfb_run_out &o, int n_iter);   // bfb_sampler_team.cu
@@ -810,8 +809,8 @@ static int launch_run(bfb_context *h, int sampler, int n_iter, const bfb_run_out
     od.n_iter = n_iter;
     od.o = dev_out;
     int rc = BFB_OK, fast_rc = 1;
-    // NUTS kernel selection: tensor-core path, then the FMA multi-chain path, then the generic warp-per-chain kernel
-    // (BFB200_SAMPLER = dmma | fast | generic pins one for tests and profiles)
+    // NUTS kernel selection: a tensor-core family (one warp per 8-chain group by default; BFB200_SAMPLER = team | pair select the
+    // alternatives), then the generic warp-per-chain kernel (BFB200_SAMPLER = dmma | team | pair | generic pins one for tests and profiles)
     const char *sel_ = getenv("BFB200_SAMPLER");
     // a dense mass matrix runs on the generic kernel only
     if (sampler == BFB_NUTS && !h->dense_metric && !getenv("BFB200_FORCE_GENERIC") && !(sel_ && !strcmp(sel_, "generic"))) {
@@ -824,11 +823,6 @@ static int launch_run(bfb_context *h, int sampler, int n_iter, const bfb_run_out
         if (fast_rc == 1) {
             fast_rc = bfb_launch_nuts_dmma(h, od.o, n_iter);
             if (fast_rc == 0) h->last_path = 2;
-        }
-        if (fast_rc == 1) {
-            const char *sel = getenv("BFB200_SAMPLER");
-            if (!sel || !strcmp(sel, "fast") || !strcmp(sel, "dmma")) fast_rc = bfb_launch_nuts_fast(h, od.o, n_iter);
-            if (fast_rc == 0) h->last_path = 1;
         }
     }
     if (sampler == BFB_HMC && !h->dense_metric && !getenv("BFB200_FORCE_GENERIC") && !(sel_ && !strcmp(sel_, "generic"))) {

@@ -2,13 +2,13 @@
 //
 // Applies to input_size <= 32 (<= 28 with cubic-3 configs), logp = output 0 of a linear + quadratic (+ cubic-2 (+ cubic-3))
 // PolyModel with or without radial bound, decay, variable transform and module rescale (model variants of bfb_dmma.cuh; the
-// BASELINE.json headline configuration is NR = 7, MV = 1); anything else runs the kernels of bfb_sampler_fast.cu /
+// BASELINE.json headline configuration is NR = 7, MV = 1); anything else runs the generic kernel of
 // bfb_sampler.cu.  Same algorithm, same draw order (SURVEY.md 8a N-RNG).
 //
 // Mapping (bfb_dmma.cuh): a chain is owned by the 4 lanes of a quad, lane lg owning the dimensions j = 4 r + lg; the
 // 8 chains of a warp are the 8 rows of an m8n8k4 DMMA whose B operand is the (chain-independent) coefficient table, so one
 // leapfrog of 8 chains is 105 DMMAs (n = 26, cubic-2) instead of ~1500 warp-wide DFMAs + their operand loads.
-// Everything else follows the asynchronous state machine of bfb_sampler_fast.cu: the chains of a warp are NOT in lock
+// Everything else is an asynchronous state machine: the chains of a warp are NOT in lock
 // step (own iteration / depth / leaf counters); the warp loops over rounds -- "two leapfrogs for every live chain (one if
 // its doubling has a single leaf), then whatever each chain needs" -- with every section entered on __any_sync and
 // committed per chain by predication; the per-dimension work of an iteration boundary (sample output, Welford metric,
