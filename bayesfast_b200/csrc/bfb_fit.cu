@@ -717,31 +717,78 @@ __global__ void transpose_lower_kernel(const double *__restrict__ L, int P, doub
     if (ii < P && jj < P) U[(size_t)ii * P + jj] = t[threadIdx.x][threadIdx.y];
 }
 
-// one CTA per right-hand side: L z = b (using U = L^T for coalesced rows), then L^T c = z
+// one CTA per right-hand side: L z = b (using U = L^T for coalesced rows), then L^T c = z.  Column-oriented substitution: step j
+// fixes one unknown and updates the rest with one AXPY over a row of U (of L on the way back), one barrier per step.  The row of
+// step j + 1 is loaded into registers while step j runs (the steps are latency bound: 2 P dependent steps, each a barrier, a shared-
+// memory read, a division and the row load -- unpipelined the L2 latency of that load was most of the 1.7 ms at P = 1054).
 __global__ void __launch_bounds__(1024) chol_solve_kernel(const double *__restrict__ L, const double *__restrict__ U, int P,
                                                           const double *__restrict__ B, int nr, double *__restrict__ X)
 {
     extern __shared__ double sm[];
     double *z = sm, *o = sm + P;
-    const int col = blockIdx.x;
-    for (int i = threadIdx.x; i < P; i += blockDim.x) z[i] = B[(size_t)i * nr + col];
-    for (int j = 0; j < P; ++j) {
+    const int col = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    constexpr int PF = 4;                                   // row elements per thread held in registers: P <= PF * blockDim.x
+    for (int i = tid; i < P; i += nt) z[i] = B[(size_t)i * nr + col];
+    if (P > PF * nt) {                                      // (not reached: the fit caps P far below) unpipelined fall-back
+        for (int j = 0; j < P; ++j) {
+            __syncthreads();
+            const double zj = z[j] / U[(size_t)j * P + j];
+            if (tid == 0) o[j] = zj;
+            const double *Uj = U + (size_t)j * P;
+            for (int i = j + 1 + tid; i < P; i += nt) z[i] = fma(-Uj[i], zj, z[i]);
+        }
         __syncthreads();
-        const double zj = z[j] / U[(size_t)j * P + j];
-        if (threadIdx.x == 0) o[j] = zj;
-        const double *Uj = U + (size_t)j * P;
-        for (int i = j + 1 + threadIdx.x; i < P; i += blockDim.x) z[i] = fma(-Uj[i], zj, z[i]);
+        for (int j = P - 1; j >= 0; --j) {
+            __syncthreads();
+            const double cj = o[j] / L[(size_t)j * P + j];
+            if (tid == 0) z[j] = cj;
+            const double *Lj = L + (size_t)j * P;
+            for (int k = tid; k < j; k += nt) o[k] = fma(-Lj[k], cj, o[k]);
+        }
+    } else {
+        double u[PF], d;
+        auto load_u = [&](int j) {                          // row j of U right of the diagonal, and the diagonal
+            const double *Uj = U + (size_t)j * P;
+            d = Uj[j];
+#pragma unroll
+            for (int e = 0; e < PF; ++e) { const int i = j + 1 + tid + e * nt; u[e] = (i < P) ? Uj[i] : 0.; }
+        };
+        load_u(0);
+        for (int j = 0; j < P; ++j) {
+            __syncthreads();
+            const double zj = z[j] / d;
+            if (tid == 0) o[j] = zj;
+            double un[PF];
+#pragma unroll
+            for (int e = 0; e < PF; ++e) un[e] = u[e];
+            const int jn = (j + 1 < P) ? j + 1 : j;
+            load_u(jn);                                     // in flight across the barrier of the next step
+#pragma unroll
+            for (int e = 0; e < PF; ++e) { const int i = j + 1 + tid + e * nt; if (i < P) z[i] = fma(-un[e], zj, z[i]); }
+        }
+        __syncthreads();
+        auto load_l = [&](int j) {                          // row j of L left of the diagonal, and the diagonal
+            const double *Lj = L + (size_t)j * P;
+            d = Lj[j];
+#pragma unroll
+            for (int e = 0; e < PF; ++e) { const int k = tid + e * nt; u[e] = (k < j) ? Lj[k] : 0.; }
+        };
+        load_l(P - 1);
+        for (int j = P - 1; j >= 0; --j) {
+            __syncthreads();
+            const double cj = o[j] / d;
+            if (tid == 0) z[j] = cj;                        // z now collects the solution
+            double un[PF];
+#pragma unroll
+            for (int e = 0; e < PF; ++e) un[e] = u[e];
+            const int jn = (j > 0) ? j - 1 : 0;
+            load_l(jn);
+#pragma unroll
+            for (int e = 0; e < PF; ++e) { const int k = tid + e * nt; if (k < j) o[k] = fma(-un[e], cj, o[k]); }
+        }
     }
     __syncthreads();
-    for (int j = P - 1; j >= 0; --j) {
-        __syncthreads();
-        const double cj = o[j] / L[(size_t)j * P + j];
-        if (threadIdx.x == 0) z[j] = cj;       // z now collects the solution
-        const double *Lj = L + (size_t)j * P;
-        for (int k = threadIdx.x; k < j; k += blockDim.x) o[k] = fma(-Lj[k], cj, o[k]);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < P; i += blockDim.x) X[(size_t)i * nr + col] = z[i];
+    for (int i = tid; i < P; i += nt) X[(size_t)i * nr + col] = z[i];
 }
 
 // R = Bs - As * X   (As symmetric P x P, X and Bs are P x nr); one warp per (row, rhs)
