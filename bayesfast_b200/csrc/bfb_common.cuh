@@ -63,6 +63,12 @@ struct DevModel {
     int frag_nr, frag_nt, frag_ext;
     // operand table of the four-warp team evaluator (bfb_team.cuh): tfrag[w][kt][tile][lane]; null when the model does not qualify
     const double *tfrag;
+    int team_nr;         // dimensions per lane-quad of the team tables: frag_nr for n <= 32, 16 for 32 < n <= 64 (team kernels only)
+    // cubic-3 block of the team evaluator: tfrag3[kt][warp][tile][lane] (streamed from L2), pair table tpair[4 kt] = k | l << 8,
+    // t3_kt k-tiles (padded to a multiple of 8)
+    const double *tfrag3;
+    const int *tpair;
+    int t3_kt;
     // cubic-3 block of the tensor-core evaluator: operand table bfrag3[kt][tile][lane], pair table c3pair[4 kt] = k | l << 8
     const double *bfrag3;
     const int *c3pair;

@@ -346,6 +346,8 @@ struct DmmaConsts {
     LikExt lx;
     const double *lik_ftab; const int *lik_fpt, *lik_fgt;
     int kt1, nt2, nt1, frec;
+    // cubic-3 block of the team evaluator (bfb_team.cuh): operand streamed from L2
+    const double *team3; const int *team_pairs; int team3_kt;
 };
 
 __device__ __forceinline__ DmmaConsts dmma_consts(const DevModel &M)
@@ -361,6 +363,7 @@ __device__ __forceinline__ DmmaConsts dmma_consts(const DevModel &M)
     K.lx.alpha = M.alpha; K.lx.p_c0 = M.p_c0;
     K.lik_ftab = M.lik_ftab; K.lik_fpt = M.lik_fpt; K.lik_fgt = M.lik_fgt;
     K.kt1 = M.lik_kt1; K.nt2 = M.lik_nt2; K.nt1 = M.lik_nt1; K.frec = M.lik_frec;
+    K.team3 = M.tfrag3; K.team_pairs = M.tpair; K.team3_kt = M.t3_kt;
     return K;
 }
 

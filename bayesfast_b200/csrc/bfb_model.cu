@@ -262,6 +262,29 @@ int bfb_upload_model(bfb_context *h)
                 for (int k = 0; k < n; ++k) HT[(size_t)k * np + j] = h->h_hess[(size_t)j * n + k];
         if ((rc = upload(h, pad(h->h_mu, 0.), &D.mu))) return rc;
         if ((rc = upload(h, HT, &D.HT))) return rc;
+        // operand table of the team evaluator (bfb_team.cuh) for `nr` dimensions per lane-quad: warp w owns the rows r = NRW w + v
+        auto build_team_table = [&](int nr) -> int {
+            const bool c2 = h2;
+            const int nrw = (nr + 3) / 4, ntw = bfb_team_tiles(nr, c2);
+            const int TDw = (nrw + 1) / 2, TXw = c2 ? nrw : (nrw + 1) / 2;
+            std::vector<double> tf((size_t)4 * nr * ntw * 32, 0.);
+            for (int w = 0; w < 4; ++w)
+                for (int kt = 0; kt < nr; ++kt)
+                    for (int t = 0; t < ntw; ++t)
+                        for (int lane = 0; lane < 32; ++lane) {
+                            const int k = 4 * kt + (lane & 3), gid = lane >> 2, own = gid >> 1, e = gid & 1;
+                            const std::vector<double> *T = nullptr;
+                            int v;
+                            if (t < TDw) { v = 2 * t + e; if (v < nrw) T = &HT; }
+                            else if (t < TDw + TXw) { v = 2 * (t - TDw) + e; if (v < nrw) T = &S; else if (c2 && v < 2 * nrw) { T = &A1T; v -= nrw; } }
+                            else { v = 2 * (t - TDw - TXw) + e; if (v < nrw) T = &A2; }
+                            const int j = 4 * (nrw * w + v) + own;
+                            if (T && !T->empty() && k < n && j < n) tf[(((size_t)w * nr + kt) * ntw + t) * 32 + lane] = (*T)[(size_t)k * np + j];
+                        }
+            const int rc_ = upload(h, tf, &D.tfrag);
+            if (!rc_) D.team_nr = nr;
+            return rc_;
+        };
         // operand table of the tensor-core evaluator (bfb_dmma.cuh), output 0
         const int nr = bfb_frag_nr(n);
         if (nr > 0 && np == 32) {
@@ -287,24 +310,40 @@ int bfb_upload_model(bfb_context *h)
             if ((rc = upload(h, fr, &D.bfrag))) return rc;
             D.frag_nr = nr; D.frag_nt = NT; D.frag_ext = ext ? 1 : 0;
             if (!ext) {
-                // operand table of the team evaluator (bfb_team.cuh): warp w owns the rows r = NRW w + v
-                const int nrw = (nr + 3) / 4, ntw = bfb_team_tiles(nr, c2);
-                const int TDw = (nrw + 1) / 2, TXw = c2 ? nrw : (nrw + 1) / 2;
-                std::vector<double> tf((size_t)4 * nr * ntw * 32, 0.);
-                for (int w = 0; w < 4; ++w)
-                    for (int kt = 0; kt < nr; ++kt)
-                        for (int t = 0; t < ntw; ++t)
+                if ((rc = build_team_table(nr))) return rc;
+            }
+        }
+        // 32 < n <= 64: only the team kernels (four warps per 8-chain group, 16 dimensions per warp) reach the tensor cores; with
+        // cubic-3 configs their pair-product operand (1 MB at n = 64) is streamed from L2 (bfb_team.cuh)
+        if (n > 32 && n <= 64 && !(F.use_decay || F.use_transform || F.use_scales) && (!h3 || h2)) {
+            if ((rc = build_team_table(16))) return rc;
+            if (h3) {
+                const int nrw = 4, tn3 = 2, n_pairs = n * (n - 1) / 2, kt3 = ((n_pairs + 3) / 4 + 7) / 8 * 8;
+                std::vector<int> pairs((size_t)kt3 * 4, 0);
+                {
+                    int p = 0;
+                    for (int k = 0; k < n; ++k)
+                        for (int l = k + 1; l < n; ++l) pairs[p++] = k | (l << 8);
+                }
+                std::vector<double> f3((size_t)kt3 * 4 * tn3 * 32, 0.);
+                for (int kt = 0; kt < kt3; ++kt)
+                    for (int w = 0; w < 4; ++w)
+                        for (int t = 0; t < tn3; ++t)
                             for (int lane = 0; lane < 32; ++lane) {
-                                const int k = 4 * kt + (lane & 3), gid = lane >> 2, own = gid >> 1, e = gid & 1;
-                                const std::vector<double> *T = nullptr;
-                                int v;
-                                if (t < TDw) { v = 2 * t + e; if (v < nrw) T = &HT; }
-                                else if (t < TDw + TXw) { v = 2 * (t - TDw) + e; if (v < nrw) T = &S; else if (c2 && v < 2 * nrw) { T = &A1T; v -= nrw; } }
-                                else { v = 2 * (t - TDw - TXw) + e; if (v < nrw) T = &A2; }
-                                const int j = 4 * (nrw * w + v) + own;
-                                if (T && !T->empty() && k < n && j < n) tf[(((size_t)w * nr + kt) * ntw + t) * 32 + lane] = (*T)[(size_t)k * np + j];
+                                const int p = 4 * kt + (lane & 3), gid = lane >> 2, own = gid >> 1, e = gid & 1;
+                                const int v = 2 * t + e, j = 4 * (nrw * w + v) + own;
+                                if (p >= n_pairs || v >= nrw || j >= n) continue;
+                                const int k = pairs[p] & 0xff, l = pairs[p] >> 8;
+                                if (j == k || j == l) continue;
+                                int a = j, b = k, c = l;
+                                if (a > b) std::swap(a, b);
+                                if (b > c) std::swap(b, c);
+                                if (a > b) std::swap(a, b);
+                                f3[(((size_t)kt * 4 + w) * tn3 + t) * 32 + lane] = c3[c3_index_host(a, b, c, n)];     // output 0
                             }
-                if ((rc = upload(h, tf, &D.tfrag))) return rc;
+                if ((rc = upload(h, f3, &D.tfrag3))) return rc;
+                if ((rc = upload(h, pairs, &D.tpair))) return rc;
+                D.t3_kt = kt3;
             }
         }
         // cubic-3 block (bfb_dmma.cuh, MV bit 2): pairs (k < l) in lexicographic order, 4 per k-tile; column (tile t, lane

@@ -70,10 +70,10 @@ __global__ void __launch_bounds__(128 * G, 1) hmc_team_kernel(DevModel M, bfb_sa
     extern __shared__ double smem[];
     double *tab = smem, *msm = smem + TS::TAB_DOUBLES;
     for (int i = threadIdx.x; i < TS::TAB_DOUBLES; i += blockDim.x) tab[i] = M.tfrag[i];
-    if (threadIdx.x < 32) { msm[threadIdx.x] = M.use_bound ? M.mu[threadIdx.x] : 0.; msm[32 + threadIdx.x] = M.lin[threadIdx.x]; }
+    for (int i = threadIdx.x; i < TS::MSM_HALF && i < M.np; i += blockDim.x) { msm[i] = M.use_bound ? M.mu[i] : 0.; msm[TS::MSM_HALF + i] = M.lin[i]; }
     __syncthreads();
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, team = wib >> 2, w = wib & 3, gi = lane >> 2, lg = lane & 3;
-    double *tsm = smem + TS::TAB_DOUBLES + 64 + (size_t)team * team_base_doubles<NR, MV>();
+    double *tsm = smem + TS::TAB_DOUBLES + TS::MSM + (size_t)team * team_base_doubles<NR, MV>();
     double *xbuf = tsm, *red = tsm + 3 * TS::SLOT;
     const double *mu_t = msm;
     volatile int *tctl = reinterpret_cast<volatile int *>(red + TS::RED_DOUBLES);
@@ -292,7 +292,8 @@ static int launch_hmc_team(bfb_context *h, const bfb_run_out &o, int n_iter)
     using TS = TeamShape<NR, MV>;
     const int64_t C = h->cs.C;
     const int n_groups = (int)((C + 7) / 8);
-    const size_t smem = sizeof(double) * (TS::TAB_DOUBLES + 64 + (size_t)G * team_base_doubles<NR, MV>());
+    const size_t smem = sizeof(double) * (TS::TAB_DOUBLES + TS::MSM + (size_t)G * team_base_doubles<NR, MV>());
+    if (smem > (size_t)(227 * 1024)) return 1;
     BFB_CUDA(cudaFuncSetAttribute(hmc_team_kernel<NR, MV, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     RunOutDevF od;
     od.o = o; od.n_iter = n_iter;
@@ -324,13 +325,21 @@ static int launch_hmc_team_g(bfb_context *h, const bfb_run_out &o, int n_iter)
 int bfb_launch_hmc_team(bfb_context *h, const bfb_run_out &o, int n_iter)
 {
     const DevModel &M = h->dm;
-    if (M.epilogue || !M.tfrag || M.frag_nr == 0 || M.frag_ext || M.has_c3) return 1;
+    if (M.epilogue || !M.tfrag || M.team_nr == 0 || M.frag_ext) return 1;
+    if (M.has_c3 && !(M.team_nr == 16 && M.tfrag3 && M.has_c2)) return 1;
+    if (M.team_nr == 16) {
+        // 32 < n <= 64: the only tensor-core path (the one-warp kernels hold at most 8 dimensions per lane); one team per SM (the
+        // operand table alone is 128 KB), more groups than SMs queue
+        if (const char *e = getenv("BFB200_SAMPLER")) { if (strcmp(e, "team")) return 1; }
+        if (M.has_c3) return launch_hmc_team<16, 5, 1>(h, o, n_iter);
+        return M.has_c2 ? launch_hmc_team<16, 1, 1>(h, o, n_iter) : launch_hmc_team<16, 0, 1>(h, o, n_iter);
+    }
     // default for up to four groups per SM (4736 chains on a B200): 4096 chains 2.20e9 leapfrogs/s here against 2.06e9 with one
     // warp per group; above that the one-warp kernel has enough warps and fewer instructions (16384 chains: 2.5e9 against 3.2e9)
     if (const char *e = getenv("BFB200_SAMPLER")) { if (strcmp(e, "team")) return 1; }
     else if ((h->cs.C + 7) / 8 > (int64_t)h->sm_count * 4) return 1;
     const int mv = M.has_c2 ? 1 : 0;
-#define BFB_CASE(NR_, MV_) if (M.frag_nr == NR_ && mv == MV_) return launch_hmc_team_g<NR_, MV_>(h, o, n_iter);
+#define BFB_CASE(NR_, MV_) if (M.team_nr == NR_ && mv == MV_) return launch_hmc_team_g<NR_, MV_>(h, o, n_iter);
     BFB_CASE(4, 0) BFB_CASE(4, 1) BFB_CASE(7, 0) BFB_CASE(7, 1) BFB_CASE(8, 0) BFB_CASE(8, 1)
 #undef BFB_CASE
     return 1;
@@ -378,11 +387,11 @@ __global__ void __launch_bounds__(128 * G, 1) nuts_team_kernel(DevModel M, bfb_s
     extern __shared__ double smem[];
     double *tab = smem, *msm = smem + TS::TAB_DOUBLES;
     for (int i = threadIdx.x; i < TS::TAB_DOUBLES; i += blockDim.x) tab[i] = M.tfrag[i];
-    if (threadIdx.x < 32) { msm[threadIdx.x] = M.use_bound ? M.mu[threadIdx.x] : 0.; msm[32 + threadIdx.x] = M.lin[threadIdx.x]; }
+    for (int i = threadIdx.x; i < TS::MSM_HALF && i < M.np; i += blockDim.x) { msm[i] = M.use_bound ? M.mu[i] : 0.; msm[TS::MSM_HALF + i] = M.lin[i]; }
     __syncthreads();
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, team = wib >> 2, w = wib & 3, gi = lane >> 2, lg = lane & 3;
     const int cc = 2 * w + (lane >> 4), cl = lane & 15;         // control chain of this lane, lane index within its half warp
-    double *tsm = smem + TS::TAB_DOUBLES + 64 + team * tstride;
+    double *tsm = smem + TS::TAB_DOUBLES + TS::MSM + team * tstride;
     double *xb = tsm, *sRL = tsm + SLOT, *sRS = tsm + 2 * SLOT, *sPBUF = tsm + 3 * SLOT;
     double *sTLQ = tsm + 4 * SLOT, *sTLP = tsm + 5 * SLOT, *sTLG = tsm + 6 * SLOT;
     double *sTRQ = tsm + 7 * SLOT, *sTRP = tsm + 8 * SLOT, *sTRG = tsm + 9 * SLOT;
@@ -562,14 +571,21 @@ __global__ void __launch_bounds__(128 * G, 1) nuts_team_kernel(DevModel M, bfb_s
                         const int src = __ffs(mask) - 1;
                         mask &= mask - 1;
                         if ((idx & 3) == w) {
-                            const int ch = src >> 2, j = lane, e = (j >> 2) * 32 + src + (j & 3);
+                            const int ch = src >> 2;
                             const int64_t t_s = __double_as_longlong(cdv[16 + ch]);
                             const uint64_t cid = (uint64_t)(cfg.chain0 + (int64_t)group * 8 + ch);
-                            double p0j = 0., vj = 0.;
-                            if (j < n) { vj = sVAR[e]; p0j = team_draw_normal(seed, cid, (uint64_t)(t_s + j)) / sqrt(vj); }
-                            else if (j == n) cdv[32 + ch] = team_draw_uniform(seed, cid, (uint64_t)(t_s + n));
-                            if (j < 4 * TS::NRP) sPBUF[e] = p0j;
-                            const double ke = warp_sum(p0j * (vj * p0j));
+                            double kpart = 0.;
+                            const int npass = n / 32 + 1;            // lane-indexed dimensions j = 32 pass + lane <= n (dimension n = the uniform)
+#pragma unroll 1
+                            for (int pass = 0; pass < npass; ++pass) {
+                                const int j = 32 * pass + lane, e = (j >> 2) * 32 + src + (j & 3);
+                                double p0j = 0., vj = 0.;
+                                if (j < n) { vj = sVAR[e]; p0j = team_draw_normal(seed, cid, (uint64_t)(t_s + j)) / sqrt(vj); }
+                                else if (j == n) cdv[32 + ch] = team_draw_uniform(seed, cid, (uint64_t)(t_s + n));
+                                if (j < 4 * TS::NRP) sPBUF[e] = p0j;
+                                kpart = fma(p0j, vj * p0j, kpart);
+                            }
+                            const double ke = warp_sum(kpart);
                             if (lane == 0) cdv[24 + ch] = ke;
                         }
                         ++idx;
@@ -943,7 +959,7 @@ static int launch_nuts_team(bfb_context *h, const bfb_run_out &o, int n_iter)
     const int64_t C = h->cs.C;
     const int n_groups = (int)((C + 7) / 8);
     // stack levels 1..LS in shared memory, deeper (rarely touched) levels in an L2-resident buffer
-    const size_t fixed = sizeof(double) * (TS::TAB_DOUBLES + 64);
+    const size_t fixed = sizeof(double) * (TS::TAB_DOUBLES + TS::MSM);
     int LS = L - 1;
     while (LS > 0 && fixed + sizeof(double) * G * team_nuts_doubles(SLOT, LS) > (size_t)(227 * 1024)) --LS;
     if (const char *e = getenv("BFB200_STACK_LEVELS_SMEM")) { int v = atoi(e); if (v >= 0 && v < LS) LS = v; }
@@ -992,14 +1008,21 @@ static int launch_nuts_team_g(bfb_context *h, const bfb_run_out &o, int n_iter)
 int bfb_launch_nuts_team(bfb_context *h, const bfb_run_out &o, int n_iter)
 {
     const DevModel &M = h->dm;
-    if (M.epilogue || !M.tfrag || M.frag_nr == 0 || M.frag_ext || M.has_c3) return 1;
+    if (M.epilogue || !M.tfrag || M.team_nr == 0 || M.frag_ext) return 1;
+    if (M.has_c3 && !(M.team_nr == 16 && M.tfrag3 && M.has_c2)) return 1;
     if (h->scfg.max_treedepth > 10 || h->scfg.max_treedepth < 1) return 1;
+    if (M.team_nr == 16) {
+        // 32 < n <= 64 (BASELINE configs[3]: 64-D cubic-3): the only tensor-core path, default; one team per SM
+        if (const char *e = getenv("BFB200_SAMPLER")) { if (strcmp(e, "team")) return 1; }
+        if (M.has_c3) return launch_nuts_team<16, 5, 1>(h, o, n_iter);
+        return M.has_c2 ? launch_nuts_team<16, 1, 1>(h, o, n_iter) : launch_nuts_team<16, 0, 1>(h, o, n_iter);
+    }
     // Measured (d = 26 cubic-2, B200, profiles/r02_a_team_*): one group alone on an SM makes a leaf in 6.8 k cycles here against
     // 10 k on the one-warp-per-group kernel, but three resident teams slow each other to 10.6 k (4096 chains: 5.2e8 against
     // 7.1e8 leapfrogs/s), so the one-warp kernel stays the default and this one is selected with BFB200_SAMPLER=team.
     { const char *e = getenv("BFB200_SAMPLER"); if (!e || strcmp(e, "team")) return 1; }
     const int mv = M.has_c2 ? 1 : 0;
-#define BFB_CASE(NR_, MV_) if (M.frag_nr == NR_ && mv == MV_) return launch_nuts_team_g<NR_, MV_>(h, o, n_iter);
+#define BFB_CASE(NR_, MV_) if (M.team_nr == NR_ && mv == MV_) return launch_nuts_team_g<NR_, MV_>(h, o, n_iter);
     BFB_CASE(4, 0) BFB_CASE(4, 1) BFB_CASE(7, 0) BFB_CASE(7, 1) BFB_CASE(8, 0) BFB_CASE(8, 1)
 #undef BFB_CASE
     return 1;

@@ -27,6 +27,7 @@
 template <int NR, int MV>
 struct TeamShape {
     static constexpr bool C2 = MV & 1;
+    static constexpr bool C3 = (MV & 4) != 0;                // cubic-3 configs: the pair-product GEMM, operand streamed from L2
     static constexpr int T = 4;                              // warps of a team
     static constexpr int NRW = (NR + 3) / 4;                 // dimensions per lane and warp
     static constexpr int NRP = 4 * NRW;                      // rows of a vector slot (>= NR; the padding rows hold zeros)
@@ -36,6 +37,9 @@ struct TeamShape {
     static constexpr int T2 = C2 ? (NRW + 1) / 2 : 0;        // tiles multiplying x^2
     static constexpr int NTW = TD + TX + T2;                 // tiles per warp and k-tile
     static constexpr int TAB_DOUBLES = T * NR * NTW * 32;
+    static constexpr int TN3 = C3 ? (NRW + 1) / 2 : 0;       // output tiles of the cubic-3 GEMM per warp
+    static constexpr int MSM_HALF = 4 * NRP > 32 ? 4 * NRP : 32;   // per-dimension tables staged behind the operand table: mu | lin
+    static constexpr int MSM = 2 * MSM_HALF;
     static constexpr int RED_DOUBLES = 2 * 128;              // two alternating reduction buffers [w][chain][4]
 };
 inline int bfb_team_tiles(int nr, bool c2) { const int nrw = (nr + 3) / 4; return (nrw + 1) / 2 + (c2 ? nrw + (nrw + 1) / 2 : (nrw + 1) / 2); }
@@ -110,7 +114,7 @@ __device__ __forceinline__ void team_logp_grad(const double *tab_w, const double
     constexpr int NRW = TS::NRW, NTW = TS::NTW, TD = TS::TD, TX = TS::TX, T2 = TS::T2, SLOT = TS::SLOT;
     constexpr bool C2 = TS::C2;
     const int lg = lane & 3;
-    const double *mu_t = msm, *lin_t = msm + 32;
+    const double *mu_t = msm, *lin_t = msm + TS::MSM_HALF;
     const double *tb = tab_w + lane;
     double mu_o[NRW], d_o[NRW];
 #pragma unroll
@@ -167,6 +171,59 @@ __device__ __forceinline__ void team_logp_grad(const double *tab_w, const double
             for (int t = 0; t < T2; ++t) dmma884(a2[t][0], a2[t][1], x2k, tb[(kt * NTW + TD + TX + t) * 32]);
         }
     }
+    // ---- cubic-3 (MV bit 2): gradient of P3 = sum_(j<k<l) a_jkl x_j x_k x_l as the GEMM [8 chains x pairs (k < l)] . [pairs x n]
+    // of the pair products of the (possibly projected) point, like bfb_dmma.cuh -- but at n = 64 the operand is 1 MB (2016
+    // pairs x 64 dimensions), so it streams from L2: every warp reads only the columns of its own dimensions (TN3 tiles per
+    // k-tile, table layout [kt][warp][tile][lane]), U k-tiles of operand and pair indices are loaded while the previous U run
+    // on the tensor cores.  Same accumulation order as the shared-memory version (k-tiles in sequence).
+    double g3[NRW];
+#pragma unroll
+    for (int i = 0; i < NRW; ++i) g3[i] = 0.;
+    if constexpr (TS::C3) {
+        constexpr int TN3 = TS::TN3, U = 8;
+        double a3[TN3][2];
+#pragma unroll
+        for (int t = 0; t < TN3; ++t) a3[t][0] = a3[t][1] = 0.;
+        const int gi4 = lane & ~3;
+        const double *t3 = K.team3 + (size_t)w * TN3 * 32 + lane;
+        const int *pr = K.team_pairs + lg;
+        const int nkt = K.team3_kt;                             // a multiple of U (padded with zero columns)
+        int pk[U];
+        double b[U][TN3];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            pk[u] = __ldg(pr + 4 * u);
+#pragma unroll
+            for (int t = 0; t < TN3; ++t) b[u][t] = __ldg(t3 + ((size_t)u * 4 * TN3 + t) * 32);
+        }
+#pragma unroll 1
+        for (int k0 = 0; k0 < nkt; k0 += U) {
+            const int k1 = (k0 + U < nkt) ? k0 + U : k0;       // the last block re-loads itself
+            int pkn[U];
+            double bn[U][TN3];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                pkn[u] = __ldg(pr + 4 * (k1 + u));
+#pragma unroll
+                for (int t = 0; t < TN3; ++t) bn[u][t] = __ldg(t3 + ((size_t)(k1 + u) * 4 * TN3 + t) * 32);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int ka_ = pk[u] & 0xff, kb_ = pk[u] >> 8;
+                const double a = xb[(ka_ >> 2) * 32 + gi4 + (ka_ & 3)] * xb[(kb_ >> 2) * 32 + gi4 + (kb_ & 3)];
+#pragma unroll
+                for (int t = 0; t < TN3; ++t) dmma884(a3[t][0], a3[t][1], a, b[u][t]);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                pk[u] = pkn[u];
+#pragma unroll
+                for (int t = 0; t < TN3; ++t) b[u][t] = bn[u][t];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < NRW; ++i) g3[i] = a3[i / 2][i % 2];
+    }
     double fpart = 0., jd = 0., ka = 0., kah = 0.;
 #pragma unroll
     for (int i = 0; i < NRW; ++i) {
@@ -181,6 +238,7 @@ __device__ __forceinline__ void team_logp_grad(const double *tab_w, const double
             g += fma(2. * xo[i], t, u);
             fpart = fma(xo[i] * xo[i], t, fpart);
         }
+        if (TS::C3) { g += g3[i]; fpart = fma(xo[i] * (1. / 3.), g3[i], fpart); }     // Euler: sum_j x_j dP3/dx_j = 3 P3
         gn[i] = g;
         jd = fma(g, d_o[i], jd);
         const double pn = fma(dt, g, p[i]), vpn = var[i] * pn;

@@ -472,6 +472,44 @@ def test_tensor_core_nuts_deep_trees(handle, oracle, monkeypatch, env, family):
     check_floats(out['samples'], ref['samples'], 'samples')
 
 
+@pytest.mark.parametrize('n,order,sampler,C,n_iter', [(64, 'cubic-3', 'NUTS', 64, 20), (64, 'cubic-3', 'HMC', 40, 16), (40, 'cubic-3', 'NUTS', 21, 24),
+                                                       (48, 'cubic-2', 'NUTS', 50, 30), (64, 'quadratic', 'NUTS', 33, 30), (33, 'cubic-2', 'HMC', 17, 20)])
+def test_team_kernels_above_32_dimensions(handle, oracle, monkeypatch, n, order, sampler, C, n_iter):
+    """32 < n <= 64 (BASELINE configs[3]: 64-D cubic-3): the four-warp team kernels are the tensor-core path -- 16 dimensions per
+    warp, the cubic-3 pair-product operand (1 MB at n = 64) streamed from L2 -- and the default; decisions identical to the oracle fed
+    with the device's own draws and to the generic warp-per-chain kernel, tight bound so that leapfrogs leave the ellipsoid"""
+    spec, cov = synthetic_spec(n, order, seed=80 + n, cubic_scale=0.05)
+    spec['alpha'] = spec['alpha'] / 1.6
+    handle.set_model(to_device_spec(spec))
+    x0 = (np.linalg.cholesky(cov) @ np.random.default_rng(13).normal(size=(n, C))).T
+    seed, chain0 = 909, 77
+    kw = {'n_int_step': 6} if sampler == 'HMC' else {}
+    cfg = cfg_from(kw, n_iter // 2, seed, chain0)
+    step0 = 1. / n**0.25
+    handle.sampler_init(cfg, x0, step0, np.ones(n), x0)
+    out = handle.sampler_run(sampler, n_iter)
+    assert handle.sampler_last_path() == 'team'
+    st = handle.sampler_state()
+    assert np.all(st['status'] == 0)
+    U, Z = device_draws(handle, seed, st['n_draws'], chain0)
+    ref = oracle.OracleDensity(spec).run(sampler, dict(n_iter=n_iter, n_warmup=n_iter // 2, **kw), x0, step0, np.ones(n), draws_u=U, draws_z=Z)
+    assert np.array_equal(st['n_draws'], ref['n_draws'])
+    ints = INT_STATS if sampler == 'NUTS' else ('tree_depth', 'diverging')      # HMC: accepted flag, divergence
+    for k in ints:
+        assert np.array_equal(out[k], ref[k]), k
+    if sampler == 'NUTS':
+        for k in FLT_STATS:
+            check_floats(out[k], ref[k], k, late=5e-3)
+        assert out['total_tree_size'] == int(ref['tree_size'].sum())
+    check_floats(out['samples'], ref['samples'], 'samples', late=1e-2 if sampler == 'HMC' else 5e-3)
+    monkeypatch.setenv('BFB200_SAMPLER', 'generic')
+    handle.sampler_init(cfg, x0, step0, np.ones(n), x0)
+    gen = handle.sampler_run(sampler, n_iter)
+    assert handle.sampler_last_path() == 'generic'
+    for k in ints:
+        assert np.array_equal(out[k], gen[k]), k
+
+
 @pytest.mark.parametrize('n,sampler,C', [(26, 'NUTS', 50), (10, 'NUTS', 33), (26, 'HMC', 40)])
 def test_tensor_core_cubic3_samplers(handle, oracle, monkeypatch, n, sampler, C):
     """cubic-3 surrogates (n <= 28) on the tensor-core NUTS / HMC kernels: decisions identical to the oracle and the generic kernel"""
