@@ -346,8 +346,8 @@ class Handle:
 
     def eval_last_path(self):
         """evaluator of the last logp_and_grad_batch: 'generic', 'dmma', 'lik_dmma' (tensor-core likelihood pipeline, one n x n
-        product per output) or 'lik_feat' (its feature form Phi(x) C^T)"""
-        return {0: 'generic', 2: 'dmma', 3: 'lik_dmma', 4: 'lik_feat'}.get(int(self._L.bfb_eval_last_path(self._h)), 'none')
+        product per output), 'lik_feat' (its feature form Phi(x) C^T) or 'team' (four warps per 8 points, 32 < n <= 64)"""
+        return {0: 'generic', 2: 'dmma', 3: 'lik_dmma', 4: 'lik_feat', 5: 'team'}.get(int(self._L.bfb_eval_last_path(self._h)), 'none')
 
     def dmma_issue_test(self, nacc, src, warps_per_sm):
         v = C.c_double(0)

@@ -4,6 +4,7 @@
 #include "bfb_eval.cuh"
 #include "bfb_team.cuh"
 int bfb_launch_eval_dmma(bfb_context *h, const double *X, int64_t C, double *LP, double *G);
+int bfb_launch_eval_team(bfb_context *h, const double *X, int64_t C, double *LP, double *G);    // bfb_eval_team.cu: 32 < n <= 64
 int bfb_launch_lik_dmma(bfb_context *h, const double *X, int64_t C, double *LP, double *G);   // bfb_lik_dmma.cu
 int bfb_build_lik_table(bfb_context *h);
 #include <algorithm>
@@ -617,6 +618,8 @@ extern "C" int bfb_poly_eval_batch(bfb_handle h, const double *X, int64_t C, dou
     int fast = 1;
     if (m == 1 && bj.dev && !h->dm.use_decay && !h->dm.use_transform)
         fast = bfb_launch_eval_dmma(h, (const double *)bx.dev, C, (double *)bf.dev, (double *)bj.dev);
+    if (fast == 1 && m == 1 && bj.dev && !h->dm.use_decay && !h->dm.use_transform)
+        fast = bfb_launch_eval_team(h, (const double *)bx.dev, C, (double *)bf.dev, (double *)bj.dev);
     if (fast < 0) return fast;
     if (fast == 1) {
     switch (npl) {
@@ -657,6 +660,7 @@ extern "C" int bfb_logp_and_grad_batch(bfb_handle h, const double *X, int64_t C,
     rc = bfb_launch_lik_dmma(h, (const double *)bx.dev, C, (double *)bl.dev, (double *)bg.dev);
     h->last_eval_path = (h->dm.lik_ftab && !getenv("BFB200_LIK_DENSE")) ? 4 : 3;
     if (rc == 1) { rc = bfb_launch_eval_dmma(h, (const double *)bx.dev, C, (double *)bl.dev, (double *)bg.dev); h->last_eval_path = 2; }
+    if (rc == 1) { rc = bfb_launch_eval_team(h, (const double *)bx.dev, C, (double *)bl.dev, (double *)bg.dev); h->last_eval_path = 5; }
     if (rc < 0) return rc;
     if (rc == 1) h->last_eval_path = 0;
     if (rc == 1) {

@@ -272,10 +272,22 @@ def extra_measurements(args, bfb, torch, den, h, prob, x0, trace_kw, flush, peak
         h3.sampler_run('NUTS', 100, out_ptrs={})
         r3 = h3.sampler_run('NUTS', 60, fields=('tree_depth',))
         ms3 = h3.last_kernel_ms()
+        fam3 = h3.sampler_last_path()
+        gen3 = None
+        try:                                                     # the same 60 iterations on the generic warp-per-chain kernel
+            os.environ['BFB200_SAMPLER'] = 'generic'
+            h3.sampler_init(cfg3, x03, 1. / 64**0.25, np.ones(64), x03)
+            h3.sampler_run('NUTS', 100, out_ptrs={})
+            rg = h3.sampler_run('NUTS', 60, fields=('tree_depth',))
+            gen3 = dict(kernel='nuts_%s_kernel' % h3.sampler_last_path(), kernel_ms=h3.last_kernel_ms(),
+                        value=rg['total_tree_size'] / h3.last_kernel_ms() * 1e3)
+        finally:
+            os.environ.pop('BFB200_SAMPLER', None)
         fl3 = 8 * 64 * 64 + 24 * 64 + 1.5 * 64 * 63 * 62
         hist = np.bincount(r3['tree_depth'].ravel(), minlength=11)
         size = 2.**np.arange(len(hist))                      # leaves of a full tree of that depth
-        extras['config3'] = dict(workload='64-D cubic-3 stack (P=47905), injected coefficients, 1024 chains', kernel='nuts_%s_kernel' % h3.sampler_last_path(),
+        extras['config3'] = dict(workload='64-D cubic-3 stack (P=47905), injected coefficients, 1024 chains', kernel='nuts_%s_kernel' % fam3,
+                                 generic_kernel=gen3,
                                  iterations=60, kernel_ms=ms3, value=r3['total_tree_size'] / ms3 * 1e3, unit='leapfrog-steps*chains/s',
                                  algorithmic_flops_per_leapfrog=fl3, roofline_frac=fl3 * r3['total_tree_size'] / (ms3 * 1e-3) / 1e12 / peak,
                                  tree_depth_histogram=hist.tolist(), mean_tree_depth=float(r3['tree_depth'].mean()),

@@ -93,6 +93,28 @@ def test_density_large_batch_vs_oracle(handle, oracle, n, order):
     assert rel_err(lp, lpo) < RTOL and rel_err(g, go) < RTOL
 
 
+@pytest.mark.parametrize('n,order,C', [(64, 'cubic-3', 1003), (40, 'cubic-3', 77), (48, 'cubic-2', 2500), (64, 'quadratic', 9), (33, 'cubic-2', 8)])
+def test_team_evaluator_above_32_dimensions(handle, oracle, monkeypatch, n, order, C):
+    """32 < n <= 64: logp + gradient on the tensor cores by teams of four warps (bfb_eval_team.cu; the cubic-3 pair-product operand
+    streamed from L2) against the oracle and the generic kernel; points inside and far outside the radial bound, ragged counts"""
+    spec, cov = synthetic_spec(n, order, seed=50 + n, cubic_scale=0.05)
+    spec['alpha'] = spec['alpha'] / 1.6
+    handle.set_model(to_device_spec(spec))
+    rng = np.random.default_rng(2)
+    X = (np.linalg.cholesky(cov) @ rng.normal(size=(n, C))).T * rng.choice([0.5, 1., 3.], size=(C, 1))
+    lp, g = handle.logp_and_grad_batch(X)
+    assert handle.eval_last_path() == 'team'
+    lpo, go = oracle.OracleDensity(spec).logp_and_grad_batch(X)
+    assert rel_err(lp, lpo) < RTOL and rel_err(g, go) < RTOL
+    F, J = handle.poly_eval_batch(X)                     # PolyModel._fun_and_jac through the same evaluator
+    Fo, Jo = oracle.OracleDensity(spec).poly_eval_batch(X)
+    assert rel_err(F, Fo) < RTOL and rel_err(J, Jo) < RTOL
+    monkeypatch.setenv('BFB200_EVAL', 'generic')
+    lpg, gg = handle.logp_and_grad_batch(X)
+    assert handle.eval_last_path() == 'generic'
+    assert rel_err(lp, lpg) < RTOL and rel_err(g, gg) < RTOL
+
+
 def test_empty_batch_and_errors(handle):
     spec, _ = synthetic_spec(5)
     handle.set_model(to_device_spec(spec))
