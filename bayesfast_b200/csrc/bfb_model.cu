@@ -343,6 +343,8 @@ int bfb_upload_model(bfb_context *h)
                                 f3[(((size_t)kt * 4 + w) * tn3 + t) * 32 + lane] = c3[c3_index_host(a, b, c, n)];     // output 0
                             }
                 if ((rc = upload(h, f3, &D.tfrag3))) return rc;
+                // the device reads a pair as the offsets of its two factors inside a chain's quad of the exchange buffer
+                for (int &pe : pairs) { const int k = pe & 0xff, l = pe >> 8; pe = ((k >> 2) * 32 + (k & 3)) | (((l >> 2) * 32 + (l & 3)) << 16); }
                 if ((rc = upload(h, pairs, &D.tpair))) return rc;
                 D.t3_kt = kt3;
             }

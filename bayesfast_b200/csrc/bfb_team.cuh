@@ -24,6 +24,10 @@
 #pragma once
 #include "bfb_dmma.cuh"
 
+#ifndef BFB_TEAM_C3_NACC
+#define BFB_TEAM_C3_NACC 1       // accumulator sets of the cubic-3 stage (team_logp_grad); measured with 2: evaluation kernel +4 %, NUTS -14 %
+#endif
+
 template <int NR, int MV>
 struct TeamShape {
     static constexpr bool C2 = MV & 1;
@@ -180,11 +184,13 @@ __device__ __forceinline__ void team_logp_grad(const double *tab_w, const double
 #pragma unroll
     for (int i = 0; i < NRW; ++i) g3[i] = 0.;
     if constexpr (TS::C3) {
-        constexpr int TN3 = TS::TN3, U = 8;
-        double a3[TN3][2];
+        constexpr int TN3 = TS::TN3, U = 8, NACC = BFB_TEAM_C3_NACC;
+        double a3[NACC][TN3][2];                                // k-tile kt accumulates into set kt mod NACC: shorter dependent DMMA chains
 #pragma unroll
-        for (int t = 0; t < TN3; ++t) a3[t][0] = a3[t][1] = 0.;
-        const int gi4 = lane & ~3;
+        for (int s_ = 0; s_ < NACC; ++s_)
+#pragma unroll
+            for (int t = 0; t < TN3; ++t) a3[s_][t][0] = a3[s_][t][1] = 0.;
+        const double *xq = xb + (lane & ~3);                  // the quad of this lane's chain inside a row of the exchange buffer
         const double *t3 = K.team3 + (size_t)w * TN3 * 32 + lane;
         const int *pr = K.team_pairs + lg;
         const int nkt = K.team3_kt;                             // a multiple of U (padded with zero columns)
@@ -209,10 +215,11 @@ __device__ __forceinline__ void team_logp_grad(const double *tab_w, const double
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const int ka_ = pk[u] & 0xff, kb_ = pk[u] >> 8;
-                const double a = xb[(ka_ >> 2) * 32 + gi4 + (ka_ & 3)] * xb[(kb_ >> 2) * 32 + gi4 + (kb_ & 3)];
+                // a pair entry holds the offsets of its two factors in the exchange buffer, (k >> 2) * 32 + (k & 3), as half-words
+                // (computing them here from (k, l) was 40 % of the kernel's instructions: profiles/r02_h)
+                const double a = xq[pk[u] & 0xffff] * xq[pk[u] >> 16];
 #pragma unroll
-                for (int t = 0; t < TN3; ++t) dmma884(a3[t][0], a3[t][1], a, b[u][t]);
+                for (int t = 0; t < TN3; ++t) dmma884(a3[u % NACC][t][0], a3[u % NACC][t][1], a, b[u][t]);
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -222,7 +229,12 @@ __device__ __forceinline__ void team_logp_grad(const double *tab_w, const double
             }
         }
 #pragma unroll
-        for (int i = 0; i < NRW; ++i) g3[i] = a3[i / 2][i % 2];
+        for (int i = 0; i < NRW; ++i) {
+            double s_ = a3[0][i / 2][i % 2];
+#pragma unroll
+            for (int k_ = 1; k_ < NACC; ++k_) s_ += a3[k_][i / 2][i % 2];
+            g3[i] = s_;
+        }
     }
     double fpart = 0., jd = 0., ka = 0., kah = 0.;
 #pragma unroll
