@@ -666,10 +666,11 @@ static void metric_update(metric_t *mt, const double *sample, int warmup)
 }
 
 /* integration.py:10 State */
-typedef struct { double *q, *p, *v, *g; double energy, logp; } state_t;
+typedef struct { double *q, *p, *v, *g; double energy, logp; double u, vt, weight; } state_t;   /* u, vt (TState.v), weight: integration.py:13 TState */
 
 typedef struct {
     const bfo_density *den; metric_t *mt; int n;
+    const bfo_density *den_base; double logxi;   /* tempered samplers (base_hmc.py:220-231): base density, log xi */
     double *arena; size_t arena_states, arena_used;
     int64_t n_eval;
 } integ_t;
@@ -682,6 +683,86 @@ static state_t new_state(integ_t *ig)
     ig->arena_used++;
     s.q = base; s.p = base + ig->n; s.v = base + 2 * ig->n; s.g = base + 3 * ig->n;
     s.energy = s.logp = 0.;
+    s.u = s.vt = 0.; s.weight = 1.;
+    return s;
+}
+
+/* integration.py:104-128: inverse temperature, its derivative, the temperature term of the potential and its derivative */
+static double t_beta(double u) { return 1. / (1. + exp(-u)); }
+static double t_d_beta(double u) { double e = exp(-u); return e / ((1. + e) * (1. + e)); }
+static double t_temp_potential(double u) { return u + 2. * log(1. + exp(-u)); }
+static double t_d_temp_potential(double u) { double e = exp(u); return (e - 1.) / (e + 1.); }
+
+/* phi = -logp(q), psi = -(logp_base(q) + logxi) (base_hmc.py:228-231) and their gradients (NULL: values only) */
+static void t_potentials(integ_t *ig, const double *q, double *phi, double *dphi, double *psi, double *dpsi, double *tmp)
+{
+    int n = ig->n;
+    double lp;
+    bfo_logp_and_grad(ig->den, q, &lp, tmp); ig->n_eval++;
+    *phi = -lp;
+    if (dphi) for (int i = 0; i < n; ++i) dphi[i] = -tmp[i];
+    bfo_logp_and_grad(ig->den_base, q, &lp, tmp);
+    *psi = -(lp + ig->logxi);
+    if (dpsi) for (int i = 0; i < n; ++i) dpsi[i] = -tmp[i];
+}
+
+/* the tail both compute_state (integration.py:139-150) and _step (:205-222) share */
+static void t_finish(integ_t *ig, state_t *s, double phi, double psi)
+{
+    int n = ig->n;
+    double kin = 0.;
+    for (int i = 0; i < n; ++i) kin += s->p[i] * s->v[i];
+    kin = 0.5 * kin + s->vt * s->vt / 2.;
+    double beta = t_beta(s->u), U = t_temp_potential(s->u);
+    double potential = beta * phi + (1. - beta) * psi + U;
+    s->energy = kin + potential;
+    s->logp = -phi;
+    double delta = phi - psi;
+    s->weight = delta == 0. ? 1. : delta / expm1(delta);
+}
+
+/* integration.py:130-150 TCpuLeapfrogIntegrator.compute_state, Q = (u, q), P = (v, p) */
+static state_t t_compute_state(integ_t *ig, const double *q, double u, const double *p, double vt)
+{
+    int n = ig->n;
+    state_t s = new_state(ig);
+    memcpy(s.q, q, sizeof(double) * (size_t)n);
+    memcpy(s.p, p, sizeof(double) * (size_t)n);
+    s.u = u; s.vt = vt;
+    double phi, psi;
+    t_potentials(ig, s.q, &phi, NULL, &psi, NULL, s.g);
+    metric_velocity(ig->mt, s.p, s.v);
+    t_finish(ig, &s, phi, psi);
+    return s;
+}
+
+/* integration.py:152-222 TCpuLeapfrogIntegrator._step: half drift, full kick at the midpoint, half drift */
+static state_t t_leapfrog(integ_t *ig, double epsilon, const state_t *st)
+{
+    int n = ig->n;
+    state_t s = new_state(ig);
+    double dt = 0.5 * epsilon;
+    double u = st->u, vt = st->vt;
+    u += vt * dt;
+    for (int i = 0; i < n; ++i) s.q[i] = st->q[i] + dt * st->v[i];         /* axpy */
+    double phi, psi;
+    double *dphi = s.v, *dpsi = s.g;                                       /* scratch until the velocity is recomputed */
+    double *tmp = (double *)malloc(sizeof(double) * (size_t)n);
+    t_potentials(ig, s.q, &phi, dphi, &psi, dpsi, tmp);
+    double beta = t_beta(u), d_beta = t_d_beta(u), dU = t_d_temp_potential(u);
+    double d_pot_du = d_beta * (phi - psi) + dU;
+    vt += -d_pot_du * epsilon;
+    for (int i = 0; i < n; ++i) {
+        double d_pot_dq = beta * dphi[i] + (1. - beta) * dpsi[i];
+        s.p[i] = st->p[i] + epsilon * (-d_pot_dq);                         /* axpy */
+    }
+    u += vt * dt;
+    metric_velocity(ig->mt, s.p, s.v);
+    for (int i = 0; i < n; ++i) s.q[i] = s.q[i] + dt * s.v[i];             /* axpy */
+    s.u = u; s.vt = vt;
+    t_potentials(ig, s.q, &phi, NULL, &psi, NULL, tmp);
+    free(tmp);
+    t_finish(ig, &s, phi, psi);
     return s;
 }
 
@@ -704,6 +785,7 @@ static state_t compute_state(integ_t *ig, const double *q, const double *p)
 /* integration.py:68-95 _step; metrics.py:88-91 velocity_energy */
 static state_t leapfrog(integ_t *ig, double epsilon, const state_t *st)
 {
+    if (ig->den_base) return t_leapfrog(ig, epsilon, st);
     int n = ig->n;
     state_t s = new_state(ig);
     double dt = 0.5 * epsilon;
@@ -723,7 +805,7 @@ static state_t leapfrog(integ_t *ig, double epsilon, const state_t *st)
 /* ------------------------------------------------------------------------------------------
  * bayesfast/samplers/nuts.py
  * ---------------------------------------------------------------------------------------- */
-typedef struct { const double *q; double energy, logp; } proposal_t;
+typedef struct { const double *q; double energy, logp; double u, weight; } proposal_t;   /* u, weight: tnuts.py:12 TProposal */
 typedef struct {
     state_t left, right; double *p_sum; proposal_t proposal; double log_size, accept_sum; int64_t n_proposals;
     int valid;
@@ -779,6 +861,7 @@ static subtree_t single_step(tree_t *t, const state_t *left, double epsilon, int
         double e = exp(-energy_change);
         st.left = right; st.right = right; st.p_sum = right.p;
         st.proposal.q = right.q; st.proposal.energy = right.energy; st.proposal.logp = right.logp;
+        st.proposal.u = right.u; st.proposal.weight = right.weight;
         st.log_size = -energy_change; st.accept_sum = e < 1. ? e : 1.; st.n_proposals = 1; st.valid = 1;
         *diverging = 0;
         return st;
@@ -877,9 +960,12 @@ static void tree_extend(tree_t *t, int direction, int *diverging, int *turning)
 /* ------------------------------------------------------------------------------------------
  * chain drivers: base_hmc.py:62-85 (astep), :87-172 (run); nuts.py:205-217; hmc.py:16-49
  * ---------------------------------------------------------------------------------------- */
+/* tempered samplers (thmc.py, tnuts.py, base_hmc.py:220-262): base density, log xi, u_0 [C], outputs u / weight [C, n_iter] */
+typedef struct { const bfo_density *base; double logxi; const double *u0; double *out_u, *out_w; } temper_t;
+
 static int run_chain(const bfo_density *den, const bfo_sampler_cfg *cfg, int is_nuts, int64_t c, int64_t chain_id,
                      const double *x0, double step0, const double *var0, const double *mean0,
-                     const double *ru, const double *rz, int64_t n_replay, bfo_run_out *out)
+                     const double *ru, const double *rz, int64_t n_replay, bfo_run_out *out, const temper_t *tm)
 {
     int n = den->model->n;
     int n_iter = cfg->n_iter;
@@ -889,6 +975,8 @@ static int run_chain(const bfo_density *den, const bfo_sampler_cfg *cfg, int is_
     dual_avg da; da_init(&da, step0, cfg->target_accept, cfg->gamma, cfg->k, cfg->t0, cfg->adapt_step_size);
     metric_t mt; metric_init(&mt, n, mean0, var0, cfg);
     integ_t ig; ig.den = den; ig.mt = &mt; ig.n = n; ig.n_eval = 0;
+    ig.den_base = tm ? tm->base : NULL; ig.logxi = tm ? tm->logxi : 0.;
+    double u_cur = tm ? tm->u0[c] : 0.;                                            /* base_hmc.py:236-243 */
     int maxd = is_nuts ? cfg->max_treedepth : 0;
     ig.arena_states = ((size_t)1 << maxd) + (size_t)cfg->n_int_step + 8;
     ig.arena = (double *)malloc(sizeof(double) * ig.arena_states * 4 * (size_t)n);
@@ -916,8 +1004,13 @@ static int run_chain(const bfo_density *den, const bfo_sampler_cfg *cfg, int is_
         ig.arena_used = 0;
         for (int i = 0; i < n; ++i) zz[i] = rng_normal(&rng);
         metric_random(&mt, zz, p0);                                               /* metrics.py:83-86, 123-127 */
-        state_t start = compute_state(&ig, q, p0);
+        state_t start;
+        if (tm) {
+            double v0 = rng_normal(&rng);                                         /* base_hmc.py:244-247 */
+            start = t_compute_state(&ig, q, u_cur, p0, v0);
+        } else start = compute_state(&ig, q, p0);
         if (!isfinite(start.energy)) { status = 2; break; }
+        double st_u = 0., st_w = 1.;
         double step_size = da_current(&da, warmup);
         double accept_stat, st_logp, st_energy, st_echange, st_maxe = 0.;
         int st_depth, st_size, diverging = 0;
@@ -926,6 +1019,7 @@ static int run_chain(const bfo_density *den, const bfo_sampler_cfg *cfg, int is_
             tree_t t; memset(&t, 0, sizeof(t));
             t.ig = &ig; t.rng = &rng; t.n = n; t.start = start; t.left = start; t.right = start;
             t.proposal.q = start.q; t.proposal.energy = start.energy; t.proposal.logp = start.logp;
+            t.proposal.u = start.u; t.proposal.weight = start.weight;
             t.depth = 0; t.log_size = 0.; t.accept_sum = 0.; t.n_proposals = 0;
             memcpy(psum, start.p, sizeof(double) * (size_t)n); t.p_sum = psum;
             t.max_energy_change = 0.; t.max_change = cfg->max_change; t.start_energy = start.energy; t.step_size = step_size;
@@ -942,6 +1036,7 @@ static int run_chain(const bfo_density *den, const bfo_sampler_cfg *cfg, int is_
             st_logp = t.proposal.logp; st_energy = t.proposal.energy; st_depth = t.depth; st_size = (int)t.n_proposals;
             st_echange = t.proposal.energy - start.energy; st_maxe = t.max_energy_change;
             end_q = t.proposal.q;
+            st_u = t.proposal.u; st_w = t.proposal.weight;                         /* tnuts.py:22-33 */
         } else {
             state_t state = start;
             for (int s = 0; s < cfg->n_int_step; ++s) state = leapfrog(&ig, step_size, &state);
@@ -957,6 +1052,12 @@ static int run_chain(const bfo_density *den, const bfo_sampler_cfg *cfg, int is_
             else { end_q = state.q; accepted = 1; }
             st_logp = state.logp; st_energy = state.energy; st_depth = accepted; st_size = cfg->n_int_step;
             st_echange = energy_change;
+            st_u = state.u; st_w = state.weight;                                   /* thmc.py:16-27: of the integrated state, accepted or not */
+        }
+        if (tm) {
+            u_cur = st_u;                                                          /* base_hmc.py:237 u0 = stats._u[-1] */
+            if (tm->out_u) tm->out_u[(size_t)c * n_iter + it] = st_u;
+            if (tm->out_w) tm->out_w[(size_t)c * n_iter + it] = st_w;
         }
         da_update(&da, accept_stat, warmup);
         metric_update(&mt, end_q, warmup);
@@ -993,7 +1094,7 @@ done:
 
 static int run_all(const bfo_density *den, const bfo_sampler_cfg *cfg, int is_nuts, int64_t C, int64_t chain0,
                    const double *x0, const double *step0, const double *var0, const double *mean0,
-                   const double *ru, const double *rz, int64_t n_replay, bfo_run_out *out)
+                   const double *ru, const double *rz, int64_t n_replay, bfo_run_out *out, const temper_t *tm)
 {
     int n = den->model->n;
     int bad = 0;
@@ -1004,7 +1105,7 @@ static int run_all(const bfo_density *den, const bfo_sampler_cfg *cfg, int is_nu
 #endif
     for (int64_t c = 0; c < C; ++c) {
         int s = run_chain(den, cfg, is_nuts, c, chain0 + c, x0 + c * n, step0[c], var0 + c * (cfg->dense_metric ? (int64_t)n * n : n), mean0 + c * n,
-                          ru ? ru + c * n_replay : NULL, rz ? rz + c * n_replay : NULL, n_replay, out);
+                          ru ? ru + c * n_replay : NULL, rz ? rz + c * n_replay : NULL, n_replay, out, tm);
         bad |= (s != 0);
     }
     (void)nt;
@@ -1015,12 +1116,24 @@ int bfo_nuts_run(const bfo_density *den, const bfo_sampler_cfg *cfg, int64_t C, 
                  const double *x0, const double *step0, const double *var0, const double *mean0,
                  const double *draws_u, const double *draws_z, int64_t n_replay, bfo_run_out *out)
 {
-    return run_all(den, cfg, 1, C, chain0, x0, step0, var0, mean0, draws_u, draws_z, n_replay, out);
+    return run_all(den, cfg, 1, C, chain0, x0, step0, var0, mean0, draws_u, draws_z, n_replay, out, NULL);
 }
 
 int bfo_hmc_run(const bfo_density *den, const bfo_sampler_cfg *cfg, int64_t C, int64_t chain0,
                 const double *x0, const double *step0, const double *var0, const double *mean0,
                 const double *draws_u, const double *draws_z, int64_t n_replay, bfo_run_out *out)
 {
-    return run_all(den, cfg, 0, C, chain0, x0, step0, var0, mean0, draws_u, draws_z, n_replay, out);
+    return run_all(den, cfg, 0, C, chain0, x0, step0, var0, mean0, draws_u, draws_z, n_replay, out, NULL);
+}
+
+/* TNUTS / THMC (samplers/tnuts.py, thmc.py, hmc_utils/base_hmc.py:220-262, integration.py:98-222); diagonal metric only */
+int bfo_tempered_run(const bfo_density *den, const bfo_density *den_base, double logxi, int is_nuts,
+                     const bfo_sampler_cfg *cfg, int64_t C, int64_t chain0,
+                     const double *x0, const double *u0, const double *step0, const double *var0, const double *mean0,
+                     const double *draws_u, const double *draws_z, int64_t n_replay, bfo_run_out *out,
+                     double *out_u, double *out_weight)
+{
+    temper_t tm; tm.base = den_base; tm.logxi = logxi; tm.u0 = u0; tm.out_u = out_u; tm.out_w = out_weight;
+    if (cfg->dense_metric) return -1;
+    return run_all(den, cfg, is_nuts, C, chain0, x0, step0, var0, mean0, draws_u, draws_z, n_replay, out, &tm);
 }

@@ -95,6 +95,10 @@ def lib():
             f.argtypes = [C.POINTER(_Density), C.POINTER(_Cfg), C.c_int64, C.c_int64, _dp, _dp, _dp, _dp,
                           _dp, _dp, C.c_int64, C.POINTER(_Out)]
             f.restype = C.c_int
+        L.bfo_tempered_run.argtypes = [C.POINTER(_Density), C.POINTER(_Density), C.c_double, C.c_int, C.POINTER(_Cfg),
+                                       C.c_int64, C.c_int64, _dp, _dp, _dp, _dp, _dp, _dp, _dp, C.c_int64,
+                                       C.POINTER(_Out), _dp, _dp]
+        L.bfo_tempered_run.restype = C.c_int
         L.bfo_rng_fill.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int64, _dp, _dp]
         L.bfo_philox_raw.argtypes = [C.c_uint32] * 6 + [C.POINTER(C.c_uint32)]
         L.bfo_to_original.argtypes = [_dp, _dp, _bp, C.c_int, _dp, _dp, _dp]
@@ -198,9 +202,11 @@ class OracleDensity:
         lib().bfo_logp_and_grad_batch(C.byref(self._dn), _d(X), X.shape[0], _d(lp), _d(g), n_threads)
         return lp, g
 
-    def run(self, sampler, cfg, x0, step0, var0, mean0=None, draws_u=None, draws_z=None, chain0=0):
+    def run(self, sampler, cfg, x0, step0, var0, mean0=None, draws_u=None, draws_z=None, chain0=0,
+            base=None, logxi=0., u0=None):
         """cfg: dict with the _Cfg fields (missing ones take the reference defaults of
-        bayesfast/samplers/sample_trace.py:157-166, 499-512)."""
+        bayesfast/samplers/sample_trace.py:157-166, 499-512).  sampler 'TNUTS' / 'THMC' (samplers/tnuts.py, thmc.py):
+        base = OracleDensity of TNTrace.density_base, logxi, u0 [C]; the result then also has 'u' and 'weight'."""
         n = self.n
         x0 = _f64(x0).reshape(-1, n)
         nc = x0.shape[0]
@@ -234,6 +240,15 @@ class OracleDensity:
             draws_z = _f64(draws_z).reshape(nc, -1)
             nrep = draws_u.shape[1]
             pu, pz = _d(draws_u), _d(draws_z)
+        if sampler.upper() in ('TNUTS', 'THMC'):
+            assert base is not None and base.n == n
+            u0 = _f64(np.broadcast_to(u0, (nc,)))
+            res['u'], res['weight'] = np.zeros((nc, ni)), np.zeros((nc, ni))
+            rc = lib().bfo_tempered_run(C.byref(self._dn), C.byref(base._dn), float(logxi), int(sampler.upper() == 'TNUTS'),
+                                        C.byref(c), nc, int(chain0), _d(x0), _d(u0), _d(step0), _d(var0), _d(mean0),
+                                        pu, pz, nrep, C.byref(o), _d(res['u']), _d(res['weight']))
+            assert rc >= 0
+            return res
         f = lib().bfo_nuts_run if sampler.upper() == 'NUTS' else lib().bfo_hmc_run
         f(C.byref(self._dn), C.byref(c), nc, int(chain0), _d(x0), _d(step0), _d(var0), _d(mean0), pu, pz, nrep,
           C.byref(o))

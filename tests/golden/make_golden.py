@@ -17,6 +17,7 @@ numdifftools) and records inputs + outputs of the hot path:
     pipeline.npz      surrogate + Gaussian-likelihood module pipelines (2-D donut of examples/2d-donut.ipynb, multi-output)
     pipeline_ext.npz  the same with radial bound + module rescale + variable transform + decay + cubic-2 configs (pins the oracle)
     sampler_dense.npz the same with the dense mass matrix (metric='full' or a covariance; QuadMetricFull / FullAdapt)
+    sampler_tempered.npz  TNUTS / THMC chains (samplers/tnuts.py, thmc.py) against a second, base density
 
 The random stream: the reference's per-chain numpy Generator is replaced (after _init_chain) by a
 duck-typed object that serves draw t of the Philox stream -- normal(size=k) consumes k draws through
@@ -300,7 +301,11 @@ class Replay:
     def __init__(self, u, z):
         self.u, self.z, self.t = u, z, 0
 
-    def normal(self, size=None):
+    def normal(self, *args, size=None):
+        if len(args) == 1:                      # normal(size=k) of metrics.py:85; normal(0, 1) of base_hmc.py:245
+            size = args[0]
+        else:
+            assert args in ((), (0, 1))
         k = 1 if size is None else int(size)
         v = self.z[self.t:self.t + k].copy()
         assert v.size == k, 'replay stream exhausted'
@@ -352,6 +357,122 @@ def run_reference_chains(den, sampler, trace_kw, x0, seed, n_draw_cap):
     out['step0'] = step0
     out['var0'] = var0
     return out
+
+
+def run_reference_tempered(den, den_base, logxi, sampler, trace_kw, x0, u0, seed, n_draw_cap=60000):
+    """TNUTS / THMC of the real reference, driven directly (core/sample.py:64-70 tests isinstance(trace, NTrace) first, so
+    bf.sample() would run plain NUTS on a TNTrace).  The tempering variable of the first iteration comes from numpy's GLOBAL
+    generator in the reference (base_hmc.py:242): served from u0 here.  THTrace.__init__ raises in the reference
+    (sample_trace.py:600 calls HTrace.__init__ without self, and never installs THStats), so for THMC the trace object is
+    assembled from the two base initialisers by hand -- the sampler code that then runs is the unmodified reference."""
+    from bayesfast.samplers import TNUTS, THMC, TNTrace
+    from bayesfast.samplers.sample_trace import THTrace, _TTrace
+    from bayesfast.samplers.hmc_utils.stats import THStats
+    n_chain = x0.shape[0]
+    if sampler == 'TNUTS':
+        cls = TNUTS
+        base = TNTrace(den_base, logxi, n_chain=n_chain, x_0=x0, random_generator=0, **trace_kw)
+        names = ('u', 'weight', 'logp', 'energy', 'tree_depth', 'tree_size', 'mean_tree_accept', 'step_size', 'step_size_bar',
+                 'energy_change', 'max_energy_change', 'diverging')
+    else:
+        cls = THMC
+        base = THTrace.__new__(THTrace)
+        _TTrace.__init__(base, den_base, logxi)
+        HTrace.__init__(base, n_chain=n_chain, x_0=x0, random_generator=0, **trace_kw)
+        base._stats = THStats()
+        names = ('u', 'weight', 'logp', 'energy', 'n_int_step', 'accept_stat', 'accepted', 'step_size', 'step_size_bar',
+                 'energy_change', 'diverging')
+    res = dict(samples=[], final_step=[], final_var=[], n_draws=[], draws_u=[], draws_z=[])
+    for k in names:
+        res[k] = []
+    step0 = var0 = None
+    for i in range(n_chain):
+        t = deepcopy(base)
+        t._init_chain(i)
+        u, z = bf_oracle.rng_fill(seed, i, 0, n_draw_cap)
+        rep = Replay(u, z)
+        t._random_generator = rep
+        if i == 0:
+            step0 = float(np.exp(t.step_size._log_step))
+            var0 = np.array(t.metric._var)
+        keep = np.random.normal
+        np.random.normal = lambda *a, **k: float(u0[i])
+        try:
+            with warnings.catch_warnings():
+                warnings.simplefilter('ignore')
+                cls(logp_and_grad=lambda x: den.logp_and_grad(x, original_space=False), sample_trace=t).run(verbose=False)
+        finally:
+            np.random.normal = keep
+        res['samples'].append(np.array(t._samples))
+        for k in names:
+            res[k].append(np.array(getattr(t.stats, '_' + k), dtype=float))
+        ss = t.step_size
+        res['final_step'].append([ss._log_step, ss._log_bar, ss._hbar, ss._count])
+        res['final_var'].append(np.array(t.metric._var))
+        res['n_draws'].append(rep.t)
+        res['draws_u'].append(u), res['draws_z'].append(z)
+    nmax = max(res['n_draws']) + 4
+    out = {k: np.array(v) for k, v in res.items()}
+    out['draws_u'] = out['draws_u'][:, :nmax]
+    out['draws_z'] = out['draws_z'][:, :nmax]
+    out['step0'] = step0
+    out['var0'] = var0
+    return out
+
+
+def make_tempered_pair(n, order, rng, transform=False, decay=False, temperature=3.):
+    """target: `order` surrogate of the usual test density; base: quadratic surrogate of the same density at a higher
+    temperature (a broad Gaussian), same variable transform."""
+    A = rng.normal(size=(n, n))
+    cov = A @ A.T / n + np.eye(n)
+    P = np.linalg.inv(cov)
+    dkw = {}
+    if transform:
+        ranges = np.stack((-12. - rng.uniform(size=n), 12. + rng.uniform(size=n)), axis=1)
+        hb = np.zeros((n, 2), np.uint8)
+        hb[0] = (1, 1)
+        if n > 2:
+            hb[2] = (1, 0)
+        dkw.update(input_scales=ranges, hard_bounds=hb)
+    L = np.linalg.cholesky(cov)
+    dens = []
+    for o, fun, dc, spread in ((order, target_logp(P), decay, 1.), ('quadratic', target_logp(P / temperature), False, 1.5)):
+        mod = bf.Module(fun=fun, input_vars='x', output_vars='logp')
+        sur = PolyModel(o, input_size=n, output_size=1, input_vars='x', output_vars='logp')
+        den = bf.Density(density_name='logp', module_list=[mod], surrogate_list=[sur], input_vars='x',
+                         decay_options={'use_decay': dc}, **dkw)
+        xf = (L @ rng.normal(size=(n, 4 * sur.n_param))).T * spread
+        if transform:
+            xf = np.clip(xf, -11., 11.)
+        den.fit([den.fun(x, original_space=True, use_surrogate=False) for x in xf])
+        den.use_surrogate = True
+        dens.append(den)
+    return dens[0], dens[1], xf
+
+
+def make_sampler_tempered():
+    rng = np.random.default_rng(4242)
+    cases = []
+
+    def add(name, sampler, den, db, logxi, x0, u0, seed, **trace_kw):
+        r = run_reference_tempered(den, db, logxi, sampler, trace_kw, x0, u0, seed)
+        cases.append(dict(name=name, sampler=sampler, spec=density_spec(den), base_spec=density_spec(db), logxi=logxi,
+                          x0=x0, u0=np.asarray(u0, dtype=float), seed=seed,
+                          trace_kw={k: (v if not isinstance(v, bool) else int(v)) for k, v in trace_kw.items()}, result=r))
+        print(name, 'mean depth', np.mean(r['tree_depth']) if sampler == 'TNUTS' else '-', 'n_div', int(np.sum(r['diverging'])),
+              'draws', r['n_draws'], 'u range', float(np.min(r['u'])), float(np.max(r['u'])),
+              'weight range', float(np.min(r['weight'])), float(np.max(r['weight'])))
+
+    den, db, xf = make_tempered_pair(3, 'quadratic', rng)
+    add('tnuts_quad_n3', 'TNUTS', den, db, 0., xf[:2].copy() / 1.5, [0.3, -1.2], 11, n_iter=50, n_warmup=25)
+    add('thmc_quad_n3', 'THMC', den, db, 0.1, xf[:2].copy() / 1.5, [-0.4, 0.9], 44, n_iter=40, n_warmup=20, n_int_step=6)
+    den, db, xf = make_tempered_pair(6, 'cubic-2', rng, transform=True, decay=True)
+    x0 = np.array([den.from_original(x / 1.5) for x in xf[:3]])
+    add('tnuts_c2_n6_tr_decay', 'TNUTS', den, db, 0.4, x0, [0.5, 2.0, -0.7], 22, n_iter=40, n_warmup=20)
+    add('tnuts_c2_n6_depthcap', 'TNUTS', den, db, -0.2, x0[:2], [0., 1.], 33, n_iter=24, n_warmup=8, max_treedepth=3)
+    den, db, xf = make_tempered_pair(16, 'cubic-2', rng)
+    add('tnuts_c2_n16', 'TNUTS', den, db, 0., xf[:2].copy() / 1.5, [1.1, -0.3], 55, n_iter=30, n_warmup=15)
+    gio.save('sampler_tempered.npz', dict(cases=cases))
 
 
 def make_sampler():
@@ -681,6 +802,8 @@ if __name__ == '__main__':
         make_fit()
     if 'sampler' in which:
         make_sampler()
+    if 'sampler_tempered' in which:
+        make_sampler_tempered()
     if 'sampler_d26' in which:
         make_sampler_d26()
     if 'poly_eval_c3n64' in which:

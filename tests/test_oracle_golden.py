@@ -136,6 +136,39 @@ def test_sampler_cases(oracle, golden):
         assert np.allclose(out['final_var'], r['final_var'], rtol=LATE_TOL), c['name']
 
 
+def _check_tempered(out, c, tag, early=EARLY):
+    """shared with tests/test_gpu_tempered.py: integer outcomes and draw counts identical, floats by the two windows"""
+    r = c['result']
+    assert np.all(out['status'] == 0), tag
+    assert np.array_equal(out['n_draws'], r['n_draws']), tag
+    if c['sampler'] == 'TNUTS':
+        for k in INT_STATS:
+            assert np.array_equal(out[k], r[k].astype(np.int32)), (tag, k)
+        for k in FLT_STATS + ('u', 'weight'):
+            _flt(out[k], r[k], (tag, k), early)
+    else:
+        assert np.array_equal(out['tree_depth'], r['accepted'].astype(np.int32)), tag
+        assert np.array_equal(out['diverging'], r['diverging'].astype(np.int32)), tag
+        for k, k2 in (('logp', 'logp'), ('energy', 'energy'), ('mean_tree_accept', 'accept_stat'), ('step_size', 'step_size'),
+                      ('step_size_bar', 'step_size_bar'), ('energy_change', 'energy_change'), ('u', 'u'), ('weight', 'weight')):
+            _flt(out[k], r[k2], (tag, k), early)
+    _flt(out['samples'], r['samples'], tag, early)
+
+
+def test_tempered_sampler_cases(oracle):
+    """TNUTS / THMC (samplers/tnuts.py, thmc.py, hmc_utils/base_hmc.py:220-262, integration.py:98-222) against runs of the real
+    reference: target density + quadratic base density, log xi, stats 'u' and 'weight'"""
+    for c in gio.load('sampler_tempered.npz')['cases']:
+        r = c['result']
+        od, ob = oracle.OracleDensity(c['spec']), oracle.OracleDensity(c['base_spec'])
+        cfg = {k: int(v) for k, v in c['trace_kw'].items()}
+        out = od.run(c['sampler'], cfg, c['x0'], float(r['step0']), r['var0'], draws_u=r['draws_u'], draws_z=r['draws_z'],
+                     base=ob, logxi=float(c['logxi']), u0=c['u0'])
+        _check_tempered(out, c, c['name'])
+        assert np.allclose(out['final_step'], r['final_step'], rtol=LATE_TOL), c['name']
+        assert np.allclose(out['final_var'], r['final_var'], rtol=LATE_TOL), c['name']
+
+
 def test_pipeline_cases(oracle):
     """surrogate + Gaussian-likelihood module (2-D donut of examples/2d-donut.ipynb = BASELINE configs[0]; multi-output with
     masked configs): Density.logp_and_grad and NUTS runs of the real reference"""
