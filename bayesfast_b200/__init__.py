@@ -8,10 +8,10 @@ include/bfb200.h); there is no CPU fallback.
 """
 from .poly import PolyConfig, PolyModel
 from .density import Density, GaussianLikelihood, GaussianPrior
-from .sample_trace import NTrace, HTrace, TraceTuple, SampleTrace
+from .sample_trace import NTrace, HTrace, TNTrace, THTrace, TraceTuple, SampleTrace
 from .sample import sample
 from . import random
 
-__all__ = ['PolyConfig', 'PolyModel', 'Density', 'GaussianLikelihood', 'GaussianPrior', 'NTrace', 'HTrace', 'TraceTuple', 'SampleTrace', 'sample',
+__all__ = ['PolyConfig', 'PolyModel', 'Density', 'GaussianLikelihood', 'GaussianPrior', 'NTrace', 'HTrace', 'TNTrace', 'THTrace', 'TraceTuple', 'SampleTrace', 'sample',
            'random']
 __version__ = '0.1.0'

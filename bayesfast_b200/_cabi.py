@@ -89,6 +89,8 @@ def lib():
             L.bfb_sampler_reset.argtypes = [C.c_void_p]
             L.bfb_sampler_run.argtypes = [C.c_void_p, C.c_int, C.c_int32, C.POINTER(RunOut), C.c_int, _lp]
             L.bfb_sampler_run_ex.argtypes = [C.c_void_p, C.c_int, C.c_int32, C.POINTER(RunOut), C.c_int, C.POINTER(RunOpts), _lp]
+            L.bfb_tsampler_init.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.POINTER(SamplerCfg), C.c_int64, _dp, _dp, _dp, _dp, _dp]
+            L.bfb_tsampler_run.argtypes = [C.c_void_p, C.c_int, C.c_int32, C.POINTER(RunOut), C.c_void_p, C.c_void_p, C.c_int, _lp]
             L.bfb_sampler_get_state.argtypes = [C.c_void_p, _dp, _dp, _lp, _ip, _dp]
             L.bfb_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
             L.bfb_launch_count.argtypes = [C.c_void_p]
@@ -316,6 +318,50 @@ class Handle:
         res['total_tree_size'] = int(tot.value)
         res['iters'] = skip + thin * np.arange(n_keep)
         self.generation_runs = getattr(self, 'generation_runs', 0) + 1
+        return res
+
+    # ------------------------------------------------------------------ tempered samplers (TNUTS / THMC)
+    def tsampler_init(self, base, logxi, cfg, x0, u0, step0, var0, mean0):
+        """base: Handle holding the base density's model (TNTrace.density_base); u0 [C]: tempering variable of the first iteration"""
+        n = self.n
+        self.generation = getattr(self, 'generation', 0) + 1
+        x0 = f64(x0).reshape(-1, n)
+        nc = x0.shape[0]
+        c = SamplerCfg()
+        for k, v in cfg.items():
+            setattr(c, k, v)
+        step0 = f64(np.broadcast_to(step0, (nc,)))
+        mean0 = f64(np.broadcast_to(mean0, (nc, n)))
+        var0 = f64(np.broadcast_to(var0, (nc, n)))
+        u0 = f64(np.broadcast_to(u0, (nc,)))
+        self.dense = False
+        self._tbase = base                                         # keeps the base handle alive as long as these chains
+        check(self._L.bfb_tsampler_init(self._h, base._h, float(logxi), C.byref(c), nc, _d(x0), _d(u0), _d(step0), _d(var0),
+                                        _d(mean0)))
+        self.n_chain = nc
+
+    def tsampler_run(self, sampler, n_iter, fields=None):
+        """sampler 'TNUTS' / 'THMC'; returns dict of host arrays [C, n_iter(, n)] incl. 'u' and 'weight'"""
+        ro = RunOut()
+        res = {}
+        nc, n, n_iter = self.n_chain, self.n, int(n_iter)
+        want = fields if fields is not None else ('samples', 'u', 'weight') + FLOAT_STATS + INT_STATS
+        for k in want:
+            if k == 'samples':
+                res[k] = np.empty((nc, n_iter, n))
+            elif k in FLOAT_STATS or k in ('u', 'weight'):
+                res[k] = np.empty((nc, n_iter))
+            else:
+                res[k] = np.empty((nc, n_iter), np.int32)
+            if k not in ('u', 'weight'):
+                setattr(ro, k, res[k].ctypes.data)
+        tot = C.c_int64(0)
+        pu = res['u'].ctypes.data if 'u' in res else None
+        pw = res['weight'].ctypes.data if 'weight' in res else None
+        check(self._L.bfb_tsampler_run(self._h, SAMPLER_CODE[sampler.upper()[1:]], n_iter, C.byref(ro), pu, pw, BFB_HOST,
+                                       C.byref(tot)))
+        res['total_tree_size'] = int(tot.value)
+        res['iters'] = np.arange(n_iter)
         return res
 
     def sampler_reset(self):

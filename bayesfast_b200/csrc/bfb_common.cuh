@@ -176,6 +176,10 @@ struct bfb_context {
     int progress_arm;          // > 0: the next NUTS launch should report progress in about this many chunks
     int progress_chunk_iters;  // set by the launcher that honoured the request (0: not honoured)
     int progress_n_chunks;
+    // tempered samplers (bfb_sampler_tempered.cu): handle of the base density, log xi, tempering variable [C] current | [C] initial
+    const bfb_context *t_base;
+    double t_logxi;
+    double *t_u;
     // fit
     FitState *fit;
 };

@@ -598,6 +598,8 @@ extern "C" int bfb_sampler_reset(bfb_handle h)
             BFB_CUDA(cudaMemcpyAsync(live[i], h->dense_allocs[6 + i], MB, cudaMemcpyDeviceToDevice, h->stream));
         BFB_CUDA(cudaMemsetAsync(s.chol_error, 0, sizeof(int32_t) * s.C, h->stream));
     }
+    if (h->t_u)      // tempered chains: u back to u_0
+        BFB_CUDA(cudaMemcpyAsync(h->t_u, h->t_u + h->cs.C, sizeof(double) * h->cs.C, cudaMemcpyDeviceToDevice, h->stream));
     h->iters_done = 0;
     return BFB_OK;
 }
@@ -698,6 +700,8 @@ extern "C" int bfb_sampler_init(bfb_handle h, const bfb_sampler_cfg *cfg, int64_
     BFB_REQUIRE(h, BFB_ERR_STATE, "bfb_sampler_init: null handle");
     bfb_free_list(h->dense_allocs);
     h->dense_metric = false;
+    if (h->t_u) { cudaSetDevice(h->device); cudaStreamSynchronize(h->stream); cudaFree(h->t_u); h->t_u = nullptr; }
+    h->t_base = nullptr;
     return sampler_init_common(h, cfg, C, x0, step0, var0, mean0);
 }
 
@@ -735,6 +739,8 @@ extern "C" int bfb_sampler_init_dense(bfb_handle h, const bfb_sampler_cfg *cfg, 
     }
     bfb_free_list(h->dense_allocs);
     h->dense_metric = false;
+    if (h->t_u) { cudaSetDevice(h->device); cudaStreamSynchronize(h->stream); cudaFree(h->t_u); h->t_u = nullptr; }
+    h->t_base = nullptr;
     std::vector<double> ones((size_t)C * n, 1.);
     int rc = sampler_init_common(h, cfg, C, x0, step0, ones.data(), mean0);
     if (rc) return rc;

@@ -12,7 +12,7 @@ from . import _cabi
 from .density import Density
 from .random import get_generator, new_seed
 from .runtime import dist_info, shard_bounds
-from .sample_trace import NTrace, HTrace, TraceTuple, SampleTrace, DualAverageAdaptation, QuadMetricDiag, QuadMetricFull
+from .sample_trace import NTrace, HTrace, TNTrace, THTrace, TraceTuple, SampleTrace, DualAverageAdaptation, QuadMetricDiag, QuadMetricFull
 
 __all__ = ['sample']
 
@@ -83,6 +83,10 @@ def sample(density, sample_trace=None, sampler='NUTS', n_run=None, parallel_back
         resume = sample_trace
         sampler = resume.sampler
         trace = resume._template
+    elif isinstance(sample_trace, TNTrace):            # before NTrace: the reference tests NTrace first (core/sample.py:64-70)
+        sampler, trace = 'TNUTS', sample_trace         # and so runs plain NUTS on a TNTrace; TNUTS is what the trace asks for
+    elif isinstance(sample_trace, THTrace):
+        sampler, trace = 'THMC', sample_trace
     elif isinstance(sample_trace, NTrace):
         sampler, trace = 'NUTS', sample_trace
     elif isinstance(sample_trace, HTrace):
@@ -93,7 +97,11 @@ def sample(density, sample_trace=None, sampler='NUTS', n_run=None, parallel_back
             trace = NTrace(**kw)
         elif sampler == 'HMC':
             trace = HTrace(**kw)
-        elif sampler in ('TNUTS', 'THMC', 'Ensemble'):
+        elif sampler == 'TNUTS':                       # density_base is a required argument of the trace
+            trace = TNTrace(**kw)
+        elif sampler == 'THMC':
+            trace = THTrace(**kw)
+        elif sampler == 'Ensemble':
             raise NotImplementedError('{} is not available on the device.'.format(sampler))
         else:
             raise ValueError('unexpected value for sampler.')
@@ -148,6 +156,9 @@ def sample(density, sample_trace=None, sampler='NUTS', n_run=None, parallel_back
     var0 = np.broadcast_to(m, (Cl, n, n) if dense else (Cl, n))
     mean0 = x0 if trace._initial_mean is None else np.broadcast_to(trace._initial_mean, (Cl, n))
 
+    if sampler in ('TNUTS', 'THMC'):
+        return _sample_tempered(den, trace, sampler, n_run, verbose, fields, keep, thin, summaries, seed, lo, x0, step0,
+                                dense, var0, mean0)
     h = den._sync(False)
     # a dense mass matrix (metric='full' / a covariance: QuadMetricFull(Adapt), metrics.py:94-132, 240-330) runs on the
     # generic warp-per-chain kernel; the diagonal default takes the tensor-core path
@@ -173,6 +184,47 @@ def sample(density, sample_trace=None, sampler='NUTS', n_run=None, parallel_back
         print(' B200 : sampling finished [ {} / {} ], {} chains, {} leapfrog steps in {:.2f} seconds '
               '(kernel {:.1f} ms).'.format(n_run, trace.n_iter, Cl, res['total_tree_size'], time.time() - t0,
                                            tt.kernel_ms))
+    return tt
+
+
+def _sample_tempered(den, trace, sampler, n_run, verbose, fields, keep, thin, summaries, seed, lo, x0, step0, dense, var0, mean0):
+    """TNUTS / THMC (samplers/tnuts.py, thmc.py, hmc_utils/base_hmc.py:220-262): the base density sits in a second device handle;
+    one warp per chain (csrc/bfb_sampler_tempered.cu).  Full records only."""
+    if dense:
+        raise NotImplementedError('the tempered samplers run with the diagonal metric on the device.')
+    if keep != 'all' or int(thin) != 1 or summaries:
+        raise NotImplementedError('reduced outputs (keep / thin / summaries) are not available for the tempered samplers.')
+    base = _as_density(trace.density_base)
+    if base is den:
+        raise ValueError('density_base should be a density object of its own.')
+    if base.input_size != den.input_size:
+        raise ValueError('density_base should have {} inputs.'.format(den.input_size))
+    Cl = x0.shape[0]
+    if trace.u_0 is None:
+        u0 = np.array([np.random.normal(0, 1) for _ in range(trace.n_chain)])[lo:lo + Cl]     # base_hmc.py:242
+    else:
+        u0 = np.broadcast_to(trace.u_0, (trace.n_chain,))[lo:lo + Cl]
+    h, hb = den._sync(False), base._sync(False)
+    h.tsampler_init(hb, trace.logxi, trace._cfg_dict(seed, lo), x0, u0, step0, np.ascontiguousarray(var0),
+                    np.ascontiguousarray(mean0))
+    n_run = trace.n_iter if n_run is None else int(n_run)
+    if n_run <= 0:
+        raise ValueError('invalid value for n_run.')
+    if n_run > trace.n_iter:
+        trace._n_iter = n_run
+    t0 = time.time()
+    res = h.tsampler_run(sampler, n_run, fields=fields)
+    final = h.sampler_state()
+    _raise_status(final['status'], lo)
+    final['step0'], final['x_0'] = step0, x0
+    arrays = _finish_arrays(den, res)
+    tt = TraceTuple(trace, arrays, final, chain0=lo, device_state=None, iters=res['iters'], i_iter=n_run,
+                    out_opts=dict(fields=fields, keep='all', thin=1, summaries=False), generation=h.generation)
+    tt.total_tree_size = res['total_tree_size']
+    tt.kernel_ms = h.last_kernel_ms()
+    if verbose:
+        print(' B200 : {} finished [ {} / {} ], {} chains, {} leapfrog steps in {:.2f} seconds (kernel {:.1f} ms).'.format(
+            sampler, n_run, trace.n_iter, Cl, res['total_tree_size'], time.time() - t0, tt.kernel_ms))
     return tt
 
 

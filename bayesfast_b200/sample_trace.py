@@ -11,13 +11,18 @@ from collections import OrderedDict, namedtuple
 
 import numpy as np
 
-__all__ = ['SampleTrace', 'NTrace', 'HTrace', 'TraceTuple', 'DualAverageAdaptation', 'QuadMetricDiag',
+__all__ = ['SampleTrace', 'NTrace', 'HTrace', 'TNTrace', 'THTrace', 'TNStats', 'THStats', 'TraceTuple', 'DualAverageAdaptation', 'QuadMetricDiag',
            'QuadMetricDiagAdapt', 'QuadMetricFull', 'QuadMetricFullAdapt', 'NStats', 'HStats', 'NStepStats', 'HStepStats', '_get_step_size', '_get_metric']
 
 hstats_items = ('logp', 'energy', 'n_int_step', 'accept_stat', 'accepted', 'step_size', 'step_size_bar', 'warmup',
                 'energy_change', 'diverging')
 nstats_items = ('logp', 'energy', 'tree_depth', 'tree_size', 'mean_tree_accept', 'step_size', 'step_size_bar',
                 'warmup', 'energy_change', 'max_energy_change', 'diverging')
+# hmc_utils/stats.py:9-24: the tempered samplers put 'u' and 'weight' in front
+thstats_items = ('u', 'weight') + hstats_items
+tnstats_items = ('u', 'weight') + nstats_items
+THStepStats = namedtuple('THStepStats', thstats_items)
+TNStepStats = namedtuple('TNStepStats', tnstats_items)
 HStepStats = namedtuple('HStepStats', hstats_items)
 NStepStats = namedtuple('NStepStats', nstats_items)
 
@@ -123,6 +128,28 @@ class HStats(_Stats):
 
     def __init__(self):
         super().__init__(hstats_items)
+
+
+class TNStats(_Stats):
+    """hmc_utils/stats.py:112-118"""
+    _step_stats = TNStepStats
+
+    def __init__(self):
+        super().__init__(tnstats_items)
+
+    u = property(lambda self: self._u)
+    weight = property(lambda self: self._weight)
+
+
+class THStats(_Stats):
+    """hmc_utils/stats.py:103-109"""
+    _step_stats = THStepStats
+
+    def __init__(self):
+        super().__init__(thstats_items)
+
+    u = property(lambda self: self._u)
+    weight = property(lambda self: self._weight)
 
 
 def _pos_int(v, name, allow_zero=False):
@@ -372,6 +399,60 @@ class NTrace(_HTrace):
         return int(np.sum(self._stats._tree_size[1:])) + self.n_iter + 1
 
 
+class _TTrace:
+    """sample_trace.py:540-588: the base density and log xi of the tempered samplers; get(return_type='weights')"""
+
+    def _t_init(self, density_base, logxi, u_0):
+        if not (hasattr(density_base, 'logp_and_grad') or hasattr(density_base, '_surrogate_list')):
+            raise ValueError('invalid value for density_base.')
+        self._density_base = density_base
+        try:
+            self._logxi = float(logxi)
+        except Exception:
+            raise ValueError('invalid value for logxi.')
+        self._u_0 = None if u_0 is None else np.atleast_1d(np.asarray(u_0, dtype=np.float64))
+
+    density_base = property(lambda self: self._density_base)
+    logxi = property(lambda self: self._logxi)
+    u_0 = property(lambda self: self._u_0)
+    weights = property(lambda self: np.asarray(self.stats._weight))
+
+    _all_return = ['samples', 'logp', 'weights']
+
+    def get(self, since_iter=None, include_warmup=False, original_space=True, return_type='samples', flatten=True):
+        if return_type == 'weights':                   # sample_trace.py:574-585
+            if since_iter is None:
+                since_iter = 0 if include_warmup else self.n_warmup
+            if int(since_iter) >= self.i_iter - 1:
+                raise ValueError('since_iter is too large. Nothing to return.')
+            return self.weights[int(since_iter):]
+        return _HTrace.get(self, since_iter, include_warmup, original_space, return_type, flatten)
+
+    __call__ = get
+
+
+class THTrace(_TTrace, HTrace):
+    """Trace of the THMC sampler (sample_trace.py:590-604; the reference's own constructor raises -- it calls
+    HTrace.__init__ without self -- so this follows what it evidently means).  u_0: tempering variable of the first iteration,
+    one per chain (default: numpy's global generator, base_hmc.py:242)."""
+
+    def __init__(self, density_base, logxi=0., n_chain=4, n_iter=1500, n_warmup=500, n_int_step=32, x_0=None,
+                 random_generator=None, step_size=1., u_0=None, **kwargs):
+        self._t_init(density_base, logxi, u_0)
+        HTrace.__init__(self, n_chain, n_iter, n_warmup, n_int_step, x_0, random_generator, step_size, **kwargs)
+        self._stats = THStats()
+
+
+class TNTrace(_TTrace, NTrace):
+    """Trace of the TNUTS sampler (sample_trace.py:607-622).  u_0 as in THTrace."""
+
+    def __init__(self, density_base, logxi=0., n_chain=4, n_iter=1500, n_warmup=500, x_0=None, random_generator=None,
+                 step_size=1., u_0=None, **kwargs):
+        self._t_init(density_base, logxi, u_0)
+        NTrace.__init__(self, n_chain, n_iter, n_warmup, x_0, random_generator, step_size, **kwargs)
+        self._stats = TNStats()
+
+
 class TraceTuple:
     """
     Results of all chains of one sample() call (sample_trace.py:631-801).  `arrays` maps names to chain-major
@@ -381,7 +462,8 @@ class TraceTuple:
     def __init__(self, template, arrays, final_state, chain0=0, device_state=None, iters=None, i_iter=None, out_opts=None,
                  generation=None):
         self._template = template
-        self._sampler = 'NUTS' if isinstance(template, NTrace) else 'HMC'
+        self._sampler = ('TNUTS' if isinstance(template, TNTrace) else 'THMC' if isinstance(template, THTrace) else
+                         'NUTS' if isinstance(template, NTrace) else 'HMC')
         self._arrays = arrays
         self._final = final_state
         self._chain0 = int(chain0)
@@ -418,7 +500,7 @@ class TraceTuple:
 
     @property
     def n_call(self):
-        if self._sampler == 'NUTS':
+        if self._sampler in ('NUTS', 'TNUTS'):
             if len(self._iters) == self._i_iter and 'tree_size' in self._arrays:
                 return int(np.sum(self._arrays['tree_size'][:, 1:])) + self.n_chain * (self.n_iter + 1)
             return int(self.total_tree_size) + self.n_chain * (self.n_iter + 1)      # reduced records: all iterations counted
@@ -433,7 +515,7 @@ class TraceTuple:
         for name in ('samples', 'samples_original', 'logp_original'):
             setattr(t, '_' + name, A[name][i] if name in A else None)
         t._x_0 = None if self._final.get('x_0') is None else self._final['x_0'][i]
-        st = NStats() if self._sampler == 'NUTS' else HStats()
+        st = {'NUTS': NStats, 'HMC': HStats, 'TNUTS': TNStats, 'THMC': THStats}[self._sampler]()
         warm = self._iters < t._n_warmup
         alias = {'diverging': ('diverging', bool), 'n_int_step': ('tree_size', None), 'accepted': ('tree_depth', bool),
                  'accept_stat': ('mean_tree_accept', None)}

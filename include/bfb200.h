@@ -191,6 +191,19 @@ typedef struct {
 } bfb_run_opts;
 int bfb_sampler_run_ex(bfb_handle h, int sampler, int32_t n_iter, const bfb_run_out *out, int loc,
                        const bfb_run_opts *opts, int64_t *total_tree_size);
+/* Tempered samplers: replace TNUTS / THMC (samplers/tnuts.py, thmc.py), BaseTHMC.astep (samplers/hmc_utils/base_hmc.py:220-262)
+ * and TCpuLeapfrogIntegrator (samplers/hmc_utils/integration.py:98-222) for C chains at once.  The Hamiltonian lives on (u, q) with
+ * potential beta(u) phi(q) + (1 - beta(u)) psi(q) + U(u), phi = -logp of h's model, psi = -(logp of h_base's model + logxi)
+ * (TNTrace.density_base / logxi, samplers/sample_trace.py:540-567); h_base is a second handle on the same device that must outlive
+ * the run.  u0 [C] (host): the tempering variable of the first iteration (the reference draws it from numpy's global generator,
+ * base_hmc.py:242).  Everything else as bfb_sampler_init (diagonal metric only); draw order per iteration: n normals (momentum),
+ * 1 normal (momentum of u), then as NUTS / HMC.  bfb_tsampler_run: sampler = BFB_NUTS (TNUTS) or BFB_HMC (THMC); u / weight
+ * [C, n_iter] = the stats 'u' and 'weight' (stats.py TNStepStats / THStepStats), the rest as bfb_sampler_run; pointers in `loc`,
+ * any may be NULL.  Runs on a warp-per-chain kernel (bfb_sampler_tempered.cu); bfb_sampler_reset / bfb_sampler_get_state apply. */
+int bfb_tsampler_init(bfb_handle h, bfb_handle h_base, double logxi, const bfb_sampler_cfg *cfg, int64_t C, const double *x0,
+                      const double *u0, const double *step0, const double *var0, const double *mean0);
+int bfb_tsampler_run(bfb_handle h, int sampler, int32_t n_iter, const bfb_run_out *out, double *u, double *weight, int loc,
+                     int64_t *total_tree_size);
 /* which kernel family ran the last bfb_sampler_run of this handle: 0 = generic warp-per-chain (bfb_sampler.cu),
  * 1 = FMA multi-chain-per-warp (bfb_sampler_fast.cu), 2 = FP64 tensor core, 8 chains per warp (bfb_sampler_dmma.cu);
  * -1 before the first run.  The environment variable BFB200_SAMPLER = dmma | fast | generic pins one (tests, profiles). */
