@@ -297,6 +297,23 @@ def extra_measurements(args, bfb, torch, den, h, prob, x0, trace_kw, flush, peak
         h3.close()
     except Exception as exc:
         extras['config3'] = dict(error=repr(exc))
+    # (g) tempered NUTS (TNUTS): the headline target + a quadratic base density, warp-per-chain kernel
+    try:
+        sb = bfb.PolyModel('quadratic', input_size=N_DIM, output_size=1)
+        sb.fit(prob['x_fit'] * 1.5, prob['y_fit'] / 3., logp=prob['y_fit'][:, 0] / 3.)
+        base = bfb.Density(sb)
+        ttn = None
+        for i in range(2):
+            ttn = bfb.sample(den, bfb.TNTrace(base, 0., n_chain=C, n_iter=200, n_warmup=100, x_0=x0, random_generator=SEED,
+                                              u_0=np.zeros(C)), verbose=False, fields=('tree_size', 'weight'))
+        extras['tempered_kernel'] = dict(kernel='tsampler_kernel (one warp per chain)', sampler='TNUTS', chains_per_gpu=C, iterations=200,
+                                         kernel_ms=ttn.kernel_ms, value=ttn.total_tree_size / ttn.kernel_ms * 1e3,
+                                         unit='leapfrog-steps*chains/s', density_evaluations_per_leapfrog=4,
+                                         evaluations_per_s=4 * ttn.total_tree_size / ttn.kernel_ms * 1e3,
+                                         mean_tree_size=float(ttn.arrays['tree_size'].mean()))
+        del ttn
+    except Exception as exc:
+        extras['tempered_kernel'] = dict(error=repr(exc))
     # (f) e2e variants through the public API (one timed call each after a warm call)
     try:
         ev = {}
