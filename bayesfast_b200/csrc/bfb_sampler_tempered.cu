@@ -29,11 +29,42 @@ __host__ __device__ inline size_t t_warp_smem_doubles(int np, int L)
     return (s + 1) & ~(size_t)1;
 }
 
+// shared memory in front of the per-warp areas: the two DevModels
+constexpr size_t T_MODEL_DOUBLES = (2 * sizeof(DevModel) + 15) / 16 * 2;
+
 // integration.py:104-128
 __device__ __forceinline__ double t_beta(double u) { return 1. / (1. + exp(-u)); }
 __device__ __forceinline__ double t_d_beta(double u) { const double e = exp(-u); return e / ((1. + e) * (1. + e)); }
 __device__ __forceinline__ double t_temp_potential(double u) { return u + 2. * log(1. + exp(-u)); }
 __device__ __forceinline__ double t_d_temp_potential(double u) { const double e = exp(u); return (e - 1.) / (e + 1.); }
+
+// ONE out-of-line copy of the evaluator for both densities and all six call sites of an iteration (start state: 2, leapfrog: 4).
+// Inlined six times the kernel was bound by instruction fetch (ncu, profiles/r02_i_tsampler_tnuts_ncu_summary.md:
+// sm__icc_request_hit_rate 43 %, 17.9 no_instruction stall cycles per issued instruction with 14 warps per SM at different places of
+// ~6 x the evaluator's code); the two models sit in shared memory so that the callee reads their fields through one pointer.
+template <int NPL> struct TVec { double v[NPL]; };
+template <int NPL> struct TEval { double lp; double g[NPL]; };
+
+template <int NPL>
+__device__ __noinline__ TEval<NPL> t_eval_ool(const DevModel *M, TVec<NPL> q, int lane, double *xsm, double *dsm)
+{
+    TEval<NPL> r;
+    density_eval<NPL>(*M, q.v, lane, xsm, dsm, r.lp, r.g);
+    return r;
+}
+
+template <int NPL>
+__device__ __forceinline__ void t_eval(const DevModel *M, const double (&q)[NPL], int lane, double *xsm, double *dsm, double &lp,
+                                       double (&g)[NPL])
+{
+    TVec<NPL> a;
+#pragma unroll
+    for (int r = 0; r < NPL; ++r) a.v[r] = q[r];
+    const TEval<NPL> e = t_eval_ool<NPL>(M, a, lane, xsm, dsm);
+    lp = e.lp;
+#pragma unroll
+    for (int r = 0; r < NPL; ++r) g[r] = e.g[r];
+}
 
 // the tail compute_state (integration.py:139-150) and _step (:205-222) share: energy, logp, weight of a state
 template <int NPL>
@@ -54,7 +85,7 @@ __device__ __forceinline__ void t_finish(const double (&var)[NPL], const double 
 
 // integration.py:152-222 TCpuLeapfrogIntegrator._step
 template <int NPL>
-__device__ __forceinline__ void t_leapfrog(const DevModel &M, const DevModel &MB, double logxi, double eps, const double (&var)[NPL],
+__device__ __forceinline__ void t_leapfrog(const DevModel *M, const DevModel *MB, double logxi, double eps, const double (&var)[NPL],
                                            double (&q)[NPL], double (&p)[NPL], double &u, double &vt, int lane, double *xsm,
                                            double *dsm, double &logp, double &energy, double &weight)
 {
@@ -63,8 +94,8 @@ __device__ __forceinline__ void t_leapfrog(const DevModel &M, const DevModel &MB
     u += vt * dt;
 #pragma unroll
     for (int r = 0; r < NPL; ++r) q[r] = fma(dt, var[r] * p[r], q[r]);
-    density_eval<NPL>(M, q, lane, xsm, dsm, lp, g1);
-    density_eval<NPL>(MB, q, lane, xsm, dsm, lpb, g2);
+    t_eval<NPL>(M, q, lane, xsm, dsm, lp, g1);
+    t_eval<NPL>(MB, q, lane, xsm, dsm, lpb, g2);
     {
         const double phi = -lp, psi = -(lpb + logxi);
         const double beta = t_beta(u), d_beta = t_d_beta(u), dU = t_d_temp_potential(u);
@@ -79,8 +110,8 @@ __device__ __forceinline__ void t_leapfrog(const DevModel &M, const DevModel &MB
     u += vt * dt;
 #pragma unroll
     for (int r = 0; r < NPL; ++r) q[r] = fma(dt, var[r] * p[r], q[r]);
-    density_eval<NPL>(M, q, lane, xsm, dsm, lp, g1);
-    density_eval<NPL>(MB, q, lane, xsm, dsm, lpb, g2);
+    t_eval<NPL>(M, q, lane, xsm, dsm, lp, g1);
+    t_eval<NPL>(MB, q, lane, xsm, dsm, lpb, g2);
     logp = lp;
     t_finish<NPL>(var, p, u, vt, lp, lpb, logxi, energy, weight);
 }
@@ -101,15 +132,19 @@ __device__ __forceinline__ double t_vdot(const double (&a)[NPL], const double (&
 #define UDOT(a, b) t_vdot<NPL>(a, var, b)
 
 template <int NPL, int SAMPLER>
-__global__ void __launch_bounds__(256) tsampler_kernel(DevModel M, DevModel MB, double logxi, bfb_sampler_cfg cfg, ChainState st,
+__global__ void __launch_bounds__(256) tsampler_kernel(DevModel Mpar, DevModel MBpar, double logxi, bfb_sampler_cfg cfg, ChainState st,
                                                        double *__restrict__ tu, TRunOutDev out, int L)
 {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    // both models at the head of the block's shared memory (read by the out-of-line evaluator through a pointer)
+    DevModel *M = reinterpret_cast<DevModel *>(smem), *MB = M + 1;
+    if (threadIdx.x == 0) { *M = Mpar; *MB = MBpar; }
+    __syncthreads();
     const int64_t c = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
     if (c >= st.C) return;
-    const int n = M.n, np = M.np;
-    double *wsm = smem + (size_t)wib * t_warp_smem_doubles(np, L);
+    const int n = Mpar.n, np = Mpar.np;
+    double *wsm = smem + T_MODEL_DOUBLES + (size_t)wib * t_warp_smem_doubles(np, L);
     double *xsm = wsm, *dsm = wsm + np;
     const int oTL = 2 * np, oTR = 4 * np, oPS = 6 * np, oPQ = 7 * np, oPB = 8 * np, oST = 9 * np, SV = 4;
     double *ssc = wsm + (size_t)(9 + SV * L) * np;      // [5][L]: log_size, energy, logp, u, weight of the stacked proposals
@@ -155,8 +190,8 @@ __global__ void __launch_bounds__(256) tsampler_kernel(DevModel M, DevModel MB, 
         double E0, w0, lp0;
         {
             double gt[NPL], lpb;
-            density_eval<NPL>(M, q, lane, xsm, dsm, lp0, gt);
-            density_eval<NPL>(MB, q, lane, xsm, dsm, lpb, gt);
+            t_eval<NPL>(M, q, lane, xsm, dsm, lp0, gt);
+            t_eval<NPL>(MB, q, lane, xsm, dsm, lpb, gt);
             t_finish<NPL>(var, p0, u_cur, vt0, lp0, lpb, logxi, E0, w0);
         }
         if (!isfinite(E0)) { status = 2; break; }                     // base_hmc.py:249-253
@@ -394,10 +429,10 @@ int launch_t(bfb_context *h, const bfb_context *hb, const TRunOutDev &out)
     int wpb = 1;
     size_t best = 0;
     for (int w = 1; w <= 8; ++w) {                       // resident warps per SM = blocks that fit x warps per block
-        const size_t resident = (cap / (w * per_warp + 1024)) * w;
+        const size_t resident = (cap / (w * per_warp + sizeof(double) * T_MODEL_DOUBLES + 1024)) * w;
         if (resident > best) { best = resident; wpb = w; }
     }
-    const size_t smem = per_warp * wpb;
+    const size_t smem = per_warp * wpb + sizeof(double) * T_MODEL_DOUBLES;
     BFB_REQUIRE(smem <= cap, BFB_ERR_ARG, "tempered sampler needs %zu bytes of shared memory per block (> 227 KB)", smem);
     BFB_CUDA(cudaFuncSetAttribute(tsampler_kernel<NPL, SAMPLER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int blocks = (int)((h->cs.C + wpb - 1) / wpb);
