@@ -266,3 +266,47 @@ def test_default_x0_is_the_reference_sobol_sequence():
     for k in g.files:
         d, n = int(k.split('_')[0][1:]), int(k.split('_')[1][1:])
         assert np.array_equal(sobol_multivariate_normal(d, n), g[k]), k
+
+
+def test_tempered_trace_objects():
+    """TNTrace / THTrace (samplers/sample_trace.py:540-622), TNStats / THStats (hmc_utils/stats.py:9-24, 103-118): host mirrors"""
+    from bayesfast_b200.sample_trace import TNTrace, THTrace, TNStats, THStats, tnstats_items, thstats_items
+    base = SimpleNamespace(logp_and_grad=lambda x: (0., x))
+    with pytest.raises(ValueError, match='density_base'):
+        TNTrace(object())
+    with pytest.raises(ValueError, match='logxi'):
+        TNTrace(base, logxi='a')
+    t = TNTrace(base, 0.3, n_chain=3, n_iter=6, n_warmup=2, x_0=np.zeros((3, 2)), random_generator=7, u_0=[0.1, 0.2, 0.3],
+                max_treedepth=7)
+    assert t.logxi == 0.3 and t.density_base is base and np.array_equal(t.u_0, [0.1, 0.2, 0.3]) and t.max_treedepth == 7
+    assert isinstance(t, NTrace) and isinstance(t.stats, TNStats) and t.stats.stats_items == tnstats_items
+    assert tnstats_items[:2] == ('u', 'weight') and thstats_items[:3] == ('u', 'weight', 'logp')
+    th = THTrace(base, n_int_step=5, n_chain=2)
+    assert isinstance(th, HTrace) and isinstance(th.stats, THStats) and th.n_int_step == 5 and th.u_0 is None and th.logxi == 0.
+    assert t._cfg_dict(1, 0)['max_treedepth'] == 7 and th._cfg_dict(1, 0)['n_int_step'] == 5
+    C, n_it, n = 3, 6, 2
+    rng = np.random.default_rng(0)
+    arrays = dict(samples=rng.normal(size=(C, n_it, n)), logp=rng.normal(size=(C, n_it)), u=rng.normal(size=(C, n_it)),
+                  weight=rng.uniform(size=(C, n_it)))
+    arrays['samples_original'], arrays['logp_original'] = arrays['samples'], arrays['logp']
+    for k in ('energy', 'mean_tree_accept', 'step_size', 'step_size_bar', 'energy_change', 'max_energy_change'):
+        arrays[k] = rng.normal(size=(C, n_it))
+    arrays['tree_depth'] = np.full((C, n_it), 2, np.int32)
+    arrays['tree_size'] = np.full((C, n_it), 3, np.int32)
+    arrays['diverging'] = np.zeros((C, n_it), np.int32)
+    final = dict(final_step=np.tile([np.log(0.3), np.log(0.25), 0.1, 4.], (C, 1)), final_var=np.ones((C, n)),
+                 step0=np.full(C, 0.5), x_0=np.zeros((C, n)))
+    tt = TraceTuple(t, arrays, final)
+    assert tt.sampler == 'TNUTS' and tt.n_call == 3 * (15 + 7)
+    t1 = tt[1]
+    assert isinstance(t1, TNTrace) and isinstance(t1.stats, TNStats)
+    assert np.array_equal(t1.stats._u, arrays['u'][1]) and np.array_equal(t1.stats.weight, arrays['weight'][1])
+    assert np.array_equal(t1.get(return_type='weights'), arrays['weight'][1][2:])            # sample_trace.py:574-585
+    s, lp, w = t1.get(return_type='all')
+    assert s.shape == (4, n) and lp.shape == (4,) and w.shape == (4,)
+    tth = TraceTuple(th, dict(arrays), dict(final))
+    assert tth.sampler == 'THMC' and isinstance(tth[0].stats, THStats) and tth[0].stats._accepted.dtype == bool
+    assert np.array_equal(tth[0].stats._n_int_step, arrays['tree_size'][0])
+    # sample(): the sampler names are accepted, the trace needs its base density
+    with pytest.raises(TypeError):
+        bfb.sample(bfb.Density(bfb.PolyModel('quadratic', input_size=2, output_size=1)), {}, sampler='TNUTS')
