@@ -45,6 +45,17 @@ tt_1 = bfb.sample(den, dict(kw), verbose=False)
 clo, chi = shard_bounds(64, rank, world)
 ok_smp = np.array_equal(tt_d.samples, tt_1.samples[clo:chi]) and np.array_equal(tt_d.arrays['tree_depth'], tt_1.arrays['tree_depth'][clo:chi]) \
     and tt_d[0].chain_id == clo
+# sharded TNUTS (tempered sampler, second density in a handle of its own): same chains as the single-GPU run, u_0 sharded like x_0
+s_b = bfb.PolyModel('quadratic', input_size=n, output_size=1, device=local)
+s_b.fit(x * 1.5, y / 3., logp=y[:, 0] / 3.)
+base = bfb.Density(s_b)
+u0 = np.linspace(-1., 1., 64)
+tkw = dict(n_chain=64, n_iter=40, n_warmup=20, x_0=prob['x_0'], random_generator=11, u_0=u0)
+tn_d = bfb.sample(den, bfb.TNTrace(base, 0.2, **tkw), verbose=False, comm=True)
+tn_1 = bfb.sample(den, bfb.TNTrace(base, 0.2, **tkw), verbose=False)
+ok_tmp = all(np.array_equal(tn_d.arrays[k], tn_1.arrays[k][clo:chi]) for k in ('samples', 'u', 'weight', 'tree_size')) \
+    and tn_d[0].chain_id == clo and tn_d.sampler == 'TNUTS'
+ok_smp = ok_smp and ok_tmp
 # sharded fit sweep timing (d=32, N rows per rank resident on the device)
 import ctypes as C
 from bayesfast_b200 import _cabi, fit as bfit
@@ -69,7 +80,7 @@ for Ntot in (100000, 1000000):
                     buffer_mb=int(L.bfb_fit_buffer_size(h._h)) * 8 / 1e6))
 if rank == 0:
     print(json.dumps(dict(world=world, fit_coef_err=errs, ok_fit=bool(ok_fit), ok_identical_across_ranks=bool(ok_same),
-                          ok_sharded_sampling=bool(ok_smp), fit_sweep=res)))
+                          ok_sharded_sampling=bool(ok_smp), ok_sharded_tempered=bool(ok_tmp), fit_sweep=res)))
 ok = torch.tensor([int(ok_fit and ok_same and ok_smp)], device='cuda')
 dist.all_reduce(ok, op=dist.ReduceOp.MIN)
 dist.destroy_process_group()
