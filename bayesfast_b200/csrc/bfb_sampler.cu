@@ -919,27 +919,75 @@ static int single_launch_host_outputs(bfb_context *h, int sampler, int R, void *
                        (int32_t *)dptr[9], (int32_t *)dptr[10]};
     volatile int *flag = h->progress_host;
     *flag = 0;
-    int want = 16;
+    // report chunks: the kernel counts, per chain, the chains that finished each chunk of iterations (independent of its work units) and
+    // the host copies a chunk out as soon as the last chain is through.  Finer chunks start the copies earlier and leave a smaller last
+    // chunk behind the kernel; what bounds the drain with eight GPUs on one host is that host's aggregate ingest (94 GB/s whatever the
+    // copy pattern, scripts/d2h_probe.py), see DESIGN.md 7
+    int want = 64;
     if (const char *e = getenv("BFB200_E2E_CHUNKS")) { int v = atoi(e); if (v >= 1) want = v; }
     h->progress_arm = want; h->progress_chunk_iters = 0; h->progress_n_chunks = 0;
+    // After the warm-up (or with a fixed step) a chain's step_size / step_size_bar records repeat one value (step_size.py:25-45: dual
+    // averaging only moves in the warm-up): ONE column of each crosses PCIe and the host thread replicates it over the iterations while
+    // it waits for the kernel -- 16 of the 276 bytes of a record at n = 26, which matters when eight GPUs drain into one host.
+    const bool const_steps = h->iters_done >= (int64_t)h->scfg.n_warmup || !h->scfg.adapt_step_size;
     int rc = launch_run(h, sampler, R, dev);
     h->progress_arm = 0;
     if (rc) return rc;
     h->iters_done += R;
     BFB_CUDA(cudaEventRecord(h->ev1, h->stream));
+    const bool rep[2] = {const_steps && user[4] != nullptr, const_steps && user[5] != nullptr};
+    double *col = nullptr;                          // pinned [2][C]: the first record of the two fields
+    struct ColGuard { double *&p; ~ColGuard() { if (p) cudaFreeHost(p); } } col_guard{col};
+    if (rep[0] || rep[1]) BFB_CUDA(cudaHostAlloc((void **)&col, sizeof(double) * 2 * (size_t)C, cudaHostAllocDefault));
+    bool col_queued = false, col_ready = false;
+    int filled = 0;                                 // iterations of the replicated fields already written on the host
+    auto fill_to = [&](int it_end) {
+        for (int k = 0; k < 2; ++k) {
+            if (!rep[k]) continue;
+            double *dst = (double *)user[4 + k];
+            const double *src = col + (size_t)k * C;
+            for (int64_t c = 0; c < C; ++c) {
+                double *row = dst + (size_t)c * n_keep;
+                const double v = src[c];
+                for (int i = filled; i < it_end; ++i) row[i] = v;
+            }
+        }
+        filled = it_end;
+    };
     auto copy_range = [&](int it_begin, int its) -> int {
         for (int f = 0; f < 11; ++f) {
             if (!user[f]) continue;
+            if ((f == 4 && rep[0]) || (f == 5 && rep[1])) continue;
             const size_t fb = field_bytes(f, n);
             BFB_CUDA(cudaMemcpy2DAsync((char *)user[f] + fb * (size_t)it_begin, fb * (size_t)n_keep, (char *)dptr[f] + fb * (size_t)it_begin,
                                        fb * (size_t)R, fb * (size_t)its, (size_t)C, cudaMemcpyDeviceToHost, h->copy_stream));
         }
+        if (!col_queued && (rep[0] || rep[1])) {     // first record of the replicated fields (the kernel has written it by now)
+            for (int k = 0; k < 2; ++k)
+                if (rep[k])
+                    BFB_CUDA(cudaMemcpy2DAsync(col + (size_t)k * C, sizeof(double), dptr[4 + k], sizeof(double) * (size_t)R, sizeof(double),
+                                               (size_t)C, cudaMemcpyDeviceToHost, h->copy_stream));
+            BFB_CUDA(cudaEventRecord(h->ev_c[0], h->copy_stream));
+            col_queued = true;
+        }
+        return BFB_OK;
+    };
+    // replicate up to the iterations whose copies are queued, as soon as the column has arrived (never blocks before the end)
+    auto replicate = [&](int it_end, bool wait) -> int {
+        if (!(rep[0] || rep[1]) || !col_queued) return BFB_OK;
+        if (!col_ready) {
+            if (wait) BFB_CUDA(cudaEventSynchronize(h->ev_c[0]));
+            else if (cudaEventQuery(h->ev_c[0]) != cudaSuccess) { cudaGetLastError(); return BFB_OK; }
+            col_ready = true;
+        }
+        fill_to(it_end);
         return BFB_OK;
     };
     if (h->last_path != 2 || h->progress_chunk_iters == 0) {
         // another kernel family took the launch: no progress reports, one copy after the kernel
         BFB_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev1, 0));
         if ((rc = copy_range(0, R))) return rc;
+        if ((rc = replicate(R, true))) return rc;
         BFB_CUDA(cudaStreamSynchronize(h->copy_stream));
         return BFB_OK;
     }
@@ -959,7 +1007,9 @@ static int single_launch_host_outputs(bfb_context *h, int sampler, int R, void *
         const int it_begin = copied * K, it_end = (seen * K < R) ? seen * K : R;
         if ((rc = copy_range(it_begin, it_end - it_begin))) return rc;
         copied = seen;
+        if (copied < nch && (rc = replicate(it_end, false))) return rc;     // host work while the kernel goes on
     }
+    if ((rc = replicate(R, true))) return rc;
     BFB_CUDA(cudaStreamSynchronize(h->stream));
     BFB_CUDA(cudaStreamSynchronize(h->copy_stream));
     return BFB_OK;

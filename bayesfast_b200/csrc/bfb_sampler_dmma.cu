@@ -123,6 +123,11 @@ __global__ void __launch_bounds__(32 * W, 1) nuts_dmma_kernel(DevModel M, bfb_sa
     long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64(); (void)tacc; (void)tlast;
     bool done = (status != 0) || it_lo >= it_hi;
     int it = it_lo;
+    // progress reports (host outputs of a single launch, bfb_sampler_run_ex): every chain counts itself in when it has finished a
+    // report chunk of rep_it iterations -- independent of the work units, whose ends synchronise the 8 chains of a group
+    const int *pgb = queue + 2 + n_groups + n_units;            // [0] armed, [1..2] host flag address, [3] rep_it, [4 + k] counts
+    const int rep_it = pgb[0] ? pgb[3] : 0;
+    int next_rep = rep_it > 0 ? min((it_lo / rep_it + 1) * rep_it, out.n_iter) : -1;
 
     // transition state
     double E0 = 0., step = 0., prop_E = 0., prop_lp = 0., acc_sum = 0., maxdE = 0.;
@@ -242,6 +247,25 @@ __global__ void __launch_bounds__(32 * W, 1) nuts_dmma_kernel(DevModel M, bfb_sa
                 }
             }
             __syncwarp();
+            {
+                const bool hit = endp && it == next_rep;          // this chain's records of report chunk (it - 1) / rep_it are written
+                if (__any_sync(BFB_FULL, hit)) {
+                    __threadfence();                              // ... by several lanes (statistics: its quad, sample: lane per dimension)
+                    __syncwarp();
+                    if (hit) {
+                        if (lg == 0) {
+                            int *pg = queue + 2 + n_groups + n_units;
+                            const int k = (it - 1) / rep_it;
+                            if (atomicAdd(pg + 4 + k, 1) == (int)st.C - 1) {      // the last chain: tell the host (mapped pinned memory)
+                                int *flag = reinterpret_cast<int *>(((unsigned long long)(unsigned)pg[2] << 32) | (unsigned long long)(unsigned)pg[1]);
+                                *(volatile int *)flag = k + 1;
+                                __threadfence_system();
+                            }
+                        }
+                        next_rep = min(next_rep + rep_it, out.n_iter);
+                    }
+                }
+            }
             // ---- (3) per chain, predicated: the new state and the empty tree ----
             double p0[NR], part = 0.;
             {
@@ -548,19 +572,6 @@ __global__ void __launch_bounds__(32 * W, 1) nuts_dmma_kernel(DevModel M, bfb_sa
         atomicAdd(st.tree_total + 11, (unsigned long long)(clock64() - t_unit0 - tsum));
 #endif
         qv[2 + group] = chunk + 1;
-        {
-            // progress block behind the ring: [0] armed, [1..2] address of the host's progress word, [4 + k] groups that finished
-            // chunk k.  The records of iterations [chunk * chunk_iters, ...) of this group are complete (fenced above); the last
-            // group to get here tells the host, which then copies the chunk out while the kernel goes on (bfb_sampler_run_ex)
-            int *pg = queue + 2 + n_groups + n_units;
-            if (qv[2 + n_groups + n_units]) {
-                if (atomicAdd(pg + 4 + chunk, 1) == n_groups - 1) {
-                    int *flag = reinterpret_cast<int *>(((unsigned long long)(unsigned)pg[2] << 32) | (unsigned long long)(unsigned)pg[1]);
-                    *(volatile int *)flag = chunk + 1;
-                    __threadfence_system();
-                }
-            }
-        }
         if ((chunk + 1) * chunk_iters < out.n_iter) {
             const int ti = atomicAdd(queue + 1, 1);
             __threadfence();
@@ -927,16 +938,20 @@ static int launch_dmma(bfb_context *h, const bfb_run_out &o, int n_iter, int cpg
     int chunk_iters = (n_iter + 11) / 12;
     if (chunk_iters < 16) chunk_iters = n_iter < 16 ? n_iter : 16;
     if (const char *e = getenv("BFB200_CHUNK_ITERS")) { int v = atoi(e); if (v >= 1) chunk_iters = v; }
+    // progress reports for host outputs: chunks of rep_iters iterations counted per CHAIN at its iteration boundary (the work units keep
+    // their length: a unit end synchronises the 8 chains of a group, which costs ~3 % of the kernel at 48 units per group)
     const bool report = h->progress_arm > 0;
-    if (report) {                                  // finer units: the host copies a chunk out as soon as every group finished it
-        chunk_iters = (n_iter + h->progress_arm - 1) / h->progress_arm;
-        if (chunk_iters < 8) chunk_iters = n_iter < 8 ? n_iter : 8;
+    int rep_iters = 0, n_rep = 0;
+    if (report) {
+        rep_iters = (n_iter + h->progress_arm - 1) / h->progress_arm;
+        if (rep_iters < 4) rep_iters = n_iter < 4 ? n_iter : 4;
+        n_rep = (n_iter + rep_iters - 1) / rep_iters;
     }
     const int n_chunks = (n_iter + chunk_iters - 1) / chunk_iters;
     const int64_t n_units64 = (int64_t)n_groups * n_chunks;
     BFB_REQUIRE(n_units64 < (1ll << 31), BFB_ERR_ARG, "too many work units");
-    // work queue, then the progress block (see the end of the kernel's unit loop): 4 + n_chunks ints
-    const size_t qlen = 2 + (size_t)n_groups + (size_t)n_units64 + 4 + (size_t)n_chunks;
+    // work queue, then the progress block (see the iteration boundary of the kernel): 4 + n_rep ints
+    const size_t qlen = 2 + (size_t)n_groups + (size_t)n_units64 + 4 + (size_t)n_rep;
     if (qlen > h->queue_len) {
         if (h->queue) cudaFree(h->queue);
         h->queue = nullptr; h->queue_len = 0;
@@ -945,12 +960,12 @@ static int launch_dmma(bfb_context *h, const bfb_run_out &o, int n_iter, int cpg
     }
     {
         int *pg = h->queue + 2 + (size_t)n_groups + (size_t)n_units64;
-        BFB_CUDA(cudaMemsetAsync(pg, 0, sizeof(int) * (4 + (size_t)n_chunks), h->stream));
+        BFB_CUDA(cudaMemsetAsync(pg, 0, sizeof(int) * (4 + (size_t)n_rep), h->stream));
         if (report) {
             const unsigned long long fa = (unsigned long long)h->progress_host_dev;
-            const int hdr[3] = {1, (int)(unsigned)(fa & 0xffffffffull), (int)(unsigned)(fa >> 32)};
+            const int hdr[4] = {1, (int)(unsigned)(fa & 0xffffffffull), (int)(unsigned)(fa >> 32), rep_iters};
             BFB_CUDA(cudaMemcpyAsync(pg, hdr, sizeof(hdr), cudaMemcpyHostToDevice, h->stream));
-            h->progress_chunk_iters = chunk_iters; h->progress_n_chunks = n_chunks;
+            h->progress_chunk_iters = rep_iters; h->progress_n_chunks = n_rep;
         }
     }
     // one block per SM whenever there are at least as many groups as SMs: with 512 groups (4096 chains) every SM then runs 3 or

@@ -546,6 +546,9 @@ def main():
             e2e_leaves += tt.total_tree_size
             h2d = x0.nbytes * 2 + 8 * C + x0.nbytes
             d2h = sum(v.nbytes for k, v in tt.arrays.items() if k not in ('samples_original', 'logp_original'))
+            # step_size / step_size_bar are constant per chain after the warm-up: one column of each crosses PCIe, the host
+            # replicates it (bfb_sampler.cu: single_launch_host_outputs)
+            d2h -= sum(tt.arrays[k].nbytes - 8 * C for k in ('step_size', 'step_size_bar') if k in tt.arrays)
         del tt
     stop.set()
     th.join(timeout=2)
@@ -601,7 +604,8 @@ def main():
                         d2h_bytes_per_step=int(d2h), ms_per_step=e2e_ms / n_e2e, kernel_ms_per_step=e2e_kernel_ms / n_e2e,
                         api="bayesfast_b200.sample(density, trace, keep='post_warmup'): samples + 10 statistics of the {} post-warm-up "
                             "iterations of every chain to pinned host memory (one launch for the warm-up, one for the kept iterations "
-                            "whose finished chunks are copied out while it runs)".format(N_ITER - N_WARMUP),
+                            "whose finished chunks are copied out while it runs; the two per-chain constant step-size statistics cross PCIe as one "
+                            "column each and are replicated by the host thread)".format(N_ITER - N_WARMUP),
                         numa_cpus_rank0=(len(numa_cpus) if numa_cpus else None)),
                gpu_launches=int(launches_all), roofline=roofline, clocks=summarize_clocks(samples),
                fit=dict(seconds=fit_s, seconds_warm=fit_warm_s, kernel_ms=getattr(sur, '_fit_kernel_ms', None), n=N_DIM,
