@@ -204,9 +204,10 @@ int bfb_tsampler_init(bfb_handle h, bfb_handle h_base, double logxi, const bfb_s
                       const double *u0, const double *step0, const double *var0, const double *mean0);
 int bfb_tsampler_run(bfb_handle h, int sampler, int32_t n_iter, const bfb_run_out *out, double *u, double *weight, int loc,
                      int64_t *total_tree_size);
-/* which kernel family ran the last bfb_sampler_run of this handle: 0 = generic warp-per-chain (bfb_sampler.cu),
- * 1 = FMA multi-chain-per-warp (bfb_sampler_fast.cu), 2 = FP64 tensor core, 8 chains per warp (bfb_sampler_dmma.cu);
- * -1 before the first run.  The environment variable BFB200_SAMPLER = dmma | fast | generic pins one (tests, profiles). */
+/* which kernel family ran the last bfb_sampler_run / bfb_tsampler_run of this handle: 0 = warp-per-chain (bfb_sampler.cu,
+ * bfb_sampler_tempered.cu), 2 = FP64 tensor core, one warp per 8 chains (bfb_sampler_dmma.cu), 3 = tensor core, four-warp team per
+ * 8 chains (bfb_sampler_team.cu), 4 = tensor core, integrator warp + tree warp (bfb_sampler_pair.cu); -1 before the first run.
+ * The environment variable BFB200_SAMPLER = dmma | team | pair | generic pins one (tests, profiles). */
 int bfb_sampler_last_path(bfb_handle h);
 /* page-locked host memory for the outputs of bfb_sampler_run: with it the device-to-host copies of one chunk of
  * iterations overlap the kernel of the next chunk */
